@@ -1,0 +1,302 @@
+/* mmk_rng.h — counter-based variate streams shared by the sm_100a kernels and the
+ * CPU checker.
+ *
+ * Every random number in a simulation is a pure function of
+ *     (seed, sample, purpose, group g, slot m, draw index)
+ * through Philox4x32-10 (Salmon et al., SC'11; constants as in Random123).  There is no
+ * sequential generator state anywhere, so a molecule can be sampled by any thread of any
+ * GPU and still consume exactly the variates the reference's loop would have consumed at
+ * that point of its sequential stream (SURVEY.md §8a-bis lists the order, taken from
+ * mimick/MimickLinkedReads.jl/src/Main.jl:44-59 and src/Breakpoints.jl).
+ *
+ * The transforms from 64 random bits to u01 / randexp / randn / randint use only IEEE-754
+ * add, sub, mul, div and sqrt, each rounded once (no FMA contraction: __dmul_rn & co. on the
+ * device, -ffp-contract=off on the host), plus a polynomial log/exp written in those
+ * operations.  Host and device therefore produce bit-identical doubles, and replay parity
+ * tests compare sampling *logic*, not two libm implementations.
+ *
+ * Plain C99 / CUDA C++; no dependencies.
+ */
+#ifndef MMK_RNG_H
+#define MMK_RNG_H
+
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define MMK_HD __host__ __device__ __forceinline__
+#else
+#define MMK_HD static inline
+#endif
+
+/* ---- single-rounding arithmetic ------------------------------------------------------- */
+#if defined(__CUDA_ARCH__)
+#define MMK_MUL(a, b) __dmul_rn((a), (b))
+#define MMK_ADD(a, b) __dadd_rn((a), (b))
+#define MMK_SUB(a, b) __dsub_rn((a), (b))
+#define MMK_DIV(a, b) __ddiv_rn((a), (b))
+#define MMK_SQRT(a) __dsqrt_rn((a))
+#else
+#include <math.h>
+#define MMK_MUL(a, b) ((double)(a) * (double)(b))
+#define MMK_ADD(a, b) ((double)(a) + (double)(b))
+#define MMK_SUB(a, b) ((double)(a) - (double)(b))
+#define MMK_DIV(a, b) ((double)(a) / (double)(b))
+#define MMK_SQRT(a) sqrt((double)(a))
+#endif
+
+MMK_HD uint64_t mmk_d2u(double d) {
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(d);
+#else
+    uint64_t u;
+    memcpy(&u, &d, 8);
+    return u;
+#endif
+}
+MMK_HD double mmk_u2d(uint64_t u) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)u);
+#else
+    double d;
+    memcpy(&d, &u, 8);
+    return d;
+#endif
+}
+MMK_HD uint64_t mmk_mulhi64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(a, b);
+#else
+    return (uint64_t)(((unsigned __int128)a * (unsigned __int128)b) >> 64);
+#endif
+}
+MMK_HD uint32_t mmk_mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+/* ---- deterministic elementary functions ---------------------------------------------- */
+#define MMK_LN2_HI 6.93147180369123816490e-01 /* 0x3fe62e42fee00000 */
+#define MMK_LN2_LO 1.90821492927058770002e-10 /* 0x3dea39ef35793c76 */
+#define MMK_INV_LN2 1.44269504088896338700e+00
+#define MMK_SQRT2 1.41421356237309514547e+00
+#define MMK_INF (mmk_u2d(0x7ff0000000000000ull))
+
+/* log(x) for finite normal x > 0.  |rel err| ~ 2e-16 (checked against libm in tests). */
+MMK_HD double mmk_log(double x) {
+    uint64_t b = mmk_d2u(x);
+    int e = (int)(b >> 52) - 1023;
+    double m = mmk_u2d((b & 0x000fffffffffffffull) | 0x3ff0000000000000ull); /* [1,2) */
+    if (m > MMK_SQRT2) {
+        m = MMK_MUL(m, 0.5);
+        e += 1;
+    }
+    double f = MMK_SUB(m, 1.0);
+    double s = MMK_DIV(f, MMK_ADD(2.0, f));
+    double z = MMK_MUL(s, s);
+    /* 2*atanh(s) = 2s * sum_k z^k/(2k+1); |s| <= 0.1716 so 12 terms reach 1e-19 */
+    double p = 1.0 / 25.0;
+    p = MMK_ADD(MMK_MUL(p, z), 1.0 / 23.0);
+    p = MMK_ADD(MMK_MUL(p, z), 1.0 / 21.0);
+    p = MMK_ADD(MMK_MUL(p, z), 1.0 / 19.0);
+    p = MMK_ADD(MMK_MUL(p, z), 1.0 / 17.0);
+    p = MMK_ADD(MMK_MUL(p, z), 1.0 / 15.0);
+    p = MMK_ADD(MMK_MUL(p, z), 1.0 / 13.0);
+    p = MMK_ADD(MMK_MUL(p, z), 1.0 / 11.0);
+    p = MMK_ADD(MMK_MUL(p, z), 1.0 / 9.0);
+    p = MMK_ADD(MMK_MUL(p, z), 1.0 / 7.0);
+    p = MMK_ADD(MMK_MUL(p, z), 1.0 / 5.0);
+    p = MMK_ADD(MMK_MUL(p, z), 1.0 / 3.0);
+    /* log(m) = 2s + 2s*z*p, kept as two terms so the small correction is added last */
+    double two_s = MMK_ADD(s, s);
+    double corr = MMK_MUL(MMK_MUL(two_s, z), p);
+    double de = (double)e;
+    double lo = MMK_ADD(MMK_MUL(de, MMK_LN2_LO), corr);
+    return MMK_ADD(MMK_MUL(de, MMK_LN2_HI), MMK_ADD(two_s, lo));
+}
+
+/* exp(x); returns 0 below the normal range and +inf above it (deterministic flush). */
+MMK_HD double mmk_exp(double x) {
+    if (x != x) return x;
+    if (x > 709.0) return MMK_INF;
+    if (x < -708.0) return 0.0;
+    double t = MMK_MUL(x, MMK_INV_LN2);
+    long long k = (long long)(t >= 0.0 ? MMK_ADD(t, 0.5) : MMK_SUB(t, 0.5));
+    double dk = (double)k;
+    double r = MMK_SUB(MMK_SUB(x, MMK_MUL(dk, MMK_LN2_HI)), MMK_MUL(dk, MMK_LN2_LO));
+    /* Taylor to degree 14 on |r| <= 0.3466 */
+    double p = 1.0 / 87178291200.0;
+    p = MMK_ADD(MMK_MUL(p, r), 1.0 / 6227020800.0);
+    p = MMK_ADD(MMK_MUL(p, r), 1.0 / 479001600.0);
+    p = MMK_ADD(MMK_MUL(p, r), 1.0 / 39916800.0);
+    p = MMK_ADD(MMK_MUL(p, r), 1.0 / 3628800.0);
+    p = MMK_ADD(MMK_MUL(p, r), 1.0 / 362880.0);
+    p = MMK_ADD(MMK_MUL(p, r), 1.0 / 40320.0);
+    p = MMK_ADD(MMK_MUL(p, r), 1.0 / 5040.0);
+    p = MMK_ADD(MMK_MUL(p, r), 1.0 / 720.0);
+    p = MMK_ADD(MMK_MUL(p, r), 1.0 / 120.0);
+    p = MMK_ADD(MMK_MUL(p, r), 1.0 / 24.0);
+    p = MMK_ADD(MMK_MUL(p, r), 1.0 / 6.0);
+    p = MMK_ADD(MMK_MUL(p, r), 0.5);
+    p = MMK_ADD(MMK_MUL(p, r), 1.0);
+    p = MMK_ADD(MMK_MUL(p, r), 1.0);
+    /* scale by 2^k (k in [-1022, 1023] given the input clamp) */
+    return MMK_MUL(p, mmk_u2d((uint64_t)(k + 1023) << 52));
+}
+
+/* log1p / expm1 by Kahan's compensation on top of mmk_log / mmk_exp. */
+MMK_HD double mmk_log1p(double x) {
+    double u = MMK_ADD(1.0, x);
+    if (u == 1.0) return x;
+    if (u == 0.0) return -MMK_INF;
+    return MMK_MUL(mmk_log(u), MMK_DIV(x, MMK_SUB(u, 1.0)));
+}
+MMK_HD double mmk_expm1(double x) {
+    double u = mmk_exp(x);
+    if (u == 1.0) return x;
+    double um1 = MMK_SUB(u, 1.0);
+    if (um1 == -1.0) return -1.0;
+    if (u == MMK_INF) return u;
+    return MMK_MUL(um1, MMK_DIV(x, mmk_log(u)));
+}
+/* log(1 - exp(x)) for x <= 0 (LogExpFunctions.log1mexp split at -ln 2) */
+MMK_HD double mmk_log1mexp(double x) {
+    if (x == 0.0) return -MMK_INF;
+    if (x < -0.6931471805599453) return mmk_log1p(-mmk_exp(x));
+    return mmk_log(-mmk_expm1(x));
+}
+/* log(|exp(a) - exp(b)|) */
+MMK_HD double mmk_logsubexp(double a, double b) {
+    double mx = a > b ? a : b;
+    double d = a > b ? MMK_SUB(b, a) : MMK_SUB(a, b); /* -|a-b| */
+    if (a == b) return -MMK_INF;
+    if (mx == -MMK_INF) return -MMK_INF;
+    return MMK_ADD(mx, mmk_log1mexp(d));
+}
+/* log(exp(a) + exp(b)) */
+MMK_HD double mmk_logaddexp(double a, double b) {
+    double mx = a > b ? a : b;
+    double mn = a > b ? b : a;
+    if (mn == -MMK_INF) return mx;
+    return MMK_ADD(mx, mmk_log1p(mmk_exp(MMK_SUB(mn, mx))));
+}
+
+/* ---- Philox4x32-10 --------------------------------------------------------------------- */
+#define MMK_PHILOX_M0 0xD2511F53u
+#define MMK_PHILOX_M1 0xCD9E8D57u
+#define MMK_PHILOX_W0 0x9E3779B9u
+#define MMK_PHILOX_W1 0xBB67AE85u
+
+MMK_HD void mmk_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = mmk_mulhi32(MMK_PHILOX_M0, c0), lo0 = MMK_PHILOX_M0 * c0;
+        uint32_t hi1 = mmk_mulhi32(MMK_PHILOX_M1, c2), lo1 = MMK_PHILOX_M1 * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0;
+        uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0;
+        c1 = lo1;
+        c2 = n2;
+        c3 = lo0;
+        k0 += MMK_PHILOX_W0;
+        k1 += MMK_PHILOX_W1;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+
+/* ---- stream addressing ----------------------------------------------------------------
+ * key     = (seed low 32, seed high 32)
+ * counter = (block, purpose | sample<<8 | g[39:32]<<24, g[31:0], m)
+ * One Philox block yields two 64-bit draws: draw 2b is words (0,1), draw 2b+1 is words (2,3).
+ */
+enum mmk_purpose {
+    MMK_P_MASK = 1,     /* N masking: g = contig index, m = haplotype file index, draw = position */
+    MMK_P_NMOL = 2,     /* group: molecules-per-barcode draw(s)                   Common.jl:89-91 */
+    MMK_P_TARGET = 3,   /* group: draw j = target pick of slot j                  Main.jl:47      */
+    MMK_P_MOLSIZE = 4,  /* molecule: molecule length draw(s)                      Breakpoints.jl:155-158 */
+    MMK_P_SINGLETON = 5,/* molecule: singleton test                               Breakpoints.jl:173 */
+    MMK_P_NFRAGS = 6,   /* molecule: number of inserts draw(s)                    Breakpoints.jl:191-192 */
+    MMK_P_INSERT = 7,   /* molecule: insert length normals                        Breakpoints.jl:207,211 */
+    MMK_P_START = 8,    /* molecule: start position                               Breakpoints.jl:240 */
+    MMK_P_GAP = 9       /* molecule: draw i = gap before insert i                 Breakpoints.jl:28 */
+};
+
+typedef struct mmk_stream {
+    uint32_t key[2];
+    uint32_t c1, c2, c3;
+    uint32_t next; /* index of the next 64-bit draw */
+    uint32_t blk;  /* Philox block currently held in buf (0xffffffff = none) */
+    uint32_t buf[4];
+} mmk_stream;
+
+MMK_HD void mmk_stream_init(mmk_stream *s, uint64_t seed, uint32_t sample, uint32_t purpose,
+                            uint64_t g, uint32_t m) {
+    s->key[0] = (uint32_t)seed;
+    s->key[1] = (uint32_t)(seed >> 32);
+    s->c1 = (purpose & 0xffu) | ((sample & 0xffffu) << 8) | ((uint32_t)((g >> 32) & 0xffu) << 24);
+    s->c2 = (uint32_t)g;
+    s->c3 = m;
+    s->next = 0;
+    s->blk = 0xffffffffu;
+}
+MMK_HD void mmk_stream_seek(mmk_stream *s, uint32_t draw) { s->next = draw; }
+MMK_HD uint64_t mmk_stream_at(const mmk_stream *s, uint32_t draw) {
+    uint32_t ctr[4] = {draw >> 1, s->c1, s->c2, s->c3};
+    uint32_t o[4];
+    mmk_philox4x32_10(ctr, s->key, o);
+    return (draw & 1u) ? (((uint64_t)o[3] << 32) | o[2]) : (((uint64_t)o[1] << 32) | o[0]);
+}
+MMK_HD uint64_t mmk_stream_next64(mmk_stream *s) {
+    uint32_t d = s->next++;
+    if ((d >> 1) != s->blk) {
+        uint32_t ctr[4] = {d >> 1, s->c1, s->c2, s->c3};
+        mmk_philox4x32_10(ctr, s->key, s->buf);
+        s->blk = d >> 1;
+    }
+    return (d & 1u) ? (((uint64_t)s->buf[3] << 32) | s->buf[2])
+                    : (((uint64_t)s->buf[1] << 32) | s->buf[0]);
+}
+
+/* ---- variates ---------------------------------------------------------------------------- */
+/* u01 in [0,1): 53 random bits */
+MMK_HD double mmk_bits_to_u01(uint64_t x) { return MMK_MUL((double)(x >> 11), 1.1102230246251565e-16); }
+/* standard exponential by inversion: -log(1-u), 1-u is exact and in (0,1] */
+MMK_HD double mmk_bits_to_exp(uint64_t x) {
+    double v = -mmk_log(MMK_SUB(1.0, mmk_bits_to_u01(x)));
+    return v == 0.0 ? 0.0 : v; /* canonical +0 */
+}
+/* integer in [0, n): multiply-high (bias <= n / 2^64) */
+MMK_HD uint64_t mmk_bits_to_index(uint64_t x, uint64_t n) { return mmk_mulhi64(x, n); }
+
+MMK_HD double mmk_next_u01(mmk_stream *s) { return mmk_bits_to_u01(mmk_stream_next64(s)); }
+MMK_HD double mmk_next_exp(mmk_stream *s) { return mmk_bits_to_exp(mmk_stream_next64(s)); }
+MMK_HD uint64_t mmk_next_index(mmk_stream *s, uint64_t n) {
+    return mmk_bits_to_index(mmk_stream_next64(s), n);
+}
+/* standard normal, Marsaglia polar method; each attempt consumes two draws (one block when
+ * the stream is block-aligned, which it is for MMK_P_INSERT). */
+MMK_HD double mmk_next_normal(mmk_stream *s) {
+    for (;;) {
+        double u1 = mmk_bits_to_u01(mmk_stream_next64(s));
+        double u2 = mmk_bits_to_u01(mmk_stream_next64(s));
+        double v1 = MMK_SUB(MMK_ADD(u1, u1), 1.0);
+        double v2 = MMK_SUB(MMK_ADD(u2, u2), 1.0);
+        double q = MMK_ADD(MMK_MUL(v1, v1), MMK_MUL(v2, v2));
+        if (q < 1.0 && q > 0.0) {
+            double f = MMK_SQRT(MMK_DIV(MMK_MUL(-2.0, mmk_log(q)), q));
+            return MMK_MUL(v1, f);
+        }
+    }
+}
+
+#endif /* MMK_RNG_H */
