@@ -1,0 +1,380 @@
+"""Host-side mirror of the reference's Julia API on top of the C ABI.
+
+`mimick(...)` keeps the two methods and the keyword surface of
+mimick/MimickLinkedReads.jl/src/Main.jl:24 (single sample, N haplotype FASTA files) and :88 (one
+FASTA + VCF, every sample), including their defaults (singletons=0.70, attempts=25) and output
+naming (`<prefix>.R{1,2}.fq`, `<outdir>/<sample>.R{1,2}.fq`).  Differences, all deliberate:
+
+* output is uncompressed FASTQ text (`.fq`); BGZF compression is outside this stage;
+* `seed < 0` draws a seed from the OS, which `Simulator.seed` reports (the reference leaves the
+  task-local RNG unseeded);
+* extra keywords select the device, the shard of a multi-GPU run and the wrap mode.
+
+`Simulator` exposes the stages (load → plan → place → emit) for callers that keep the FASTQ in
+device memory.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import Chunk, MimickError, MolRecord, Params, PlaceInfo, PlanInfo, SchemaInfo
+
+VARIATE_DTYPE = np.dtype([("tag", "<u4"), ("aux", "<u4"), ("bits", "<u8")])
+MOL_DTYPE = np.dtype([("group", "<i8"), ("slot", "<i4"), ("schema", "<i4"), ("start", "<i8"), ("molsize", "<i8"),
+                      ("n_frags", "<i8"), ("first_read", "<i8"), ("barcode_index", "<i8")])
+
+
+def interperet_format(fmt: str):
+    """src/Common.jl:56-74 → (barcode_format, out_format) as enum ints."""
+    L = _lib.load()
+    bc, fq = C.c_int32(), C.c_int32()
+    rc = L.mmk_interpret_format(fmt.encode(), C.byref(bc), C.byref(fq))
+    if rc:
+        raise MimickError(rc, f"Barcode format {fmt} is not recognized as one of: haplotagging, stlfr, tellseq, tenx")
+    return bc.value, fq.value
+
+
+class Vcf:
+    """One-pass VCF reader handle (mmk_vcf_*)."""
+
+    def __init__(self, path: str):
+        L = _lib.load()
+        self._h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        rc = L.mmk_vcf_open(os.fspath(path).encode(), C.byref(self._h), err, len(err))
+        if rc:
+            raise MimickError(rc, err.value.decode())
+        self.samples = [L.mmk_vcf_sample_name(self._h, i).decode() for i in range(L.mmk_vcf_n_samples(self._h))]
+        self.contigs = [L.mmk_vcf_contig_name(self._h, i).decode() for i in range(L.mmk_vcf_n_contigs(self._h))]
+        self.ploidy = L.mmk_vcf_ploidy(self._h)
+        self.n_records = L.mmk_vcf_n_records(self._h)
+
+    def close(self):
+        if self._h:
+            _lib.load().mmk_vcf_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Simulator:
+    """A simulation context bound to one CUDA device (mmk_ctx)."""
+
+    def __init__(self, format="standard:haplotagging", *, coverage=30, n_molecules=2, mol_coverage=0.2,
+                 mol_length=80000, insert_length=500, insert_stdev=50, read_length=(150, 150), singletons=0.70,
+                 circular=False, attempts=25, seed=-1, mask=False, device=0, strict_wrap=False,
+                 force_generic=False, max_chunk_bytes=0, plan_batch_groups=0):
+        L = _lib.load()
+        self._L = L
+        bc, fq = interperet_format(format)
+        read_length = list(read_length)
+        if len(read_length) == 1:  # "Using it for both R1 and R2" (Main.jl:30-32, without its vector-of-vectors bug)
+            read_length = read_length * 2
+        p = Params()
+        L.mmk_params_default(C.byref(p))
+        p.device = int(device)
+        p.fq_format, p.bc_format = fq, bc
+        p.coverage = float(coverage)
+        p.n_molecules = int(n_molecules)
+        p.attempts = int(attempts)
+        p.mol_coverage = float(mol_coverage)
+        p.mol_length = int(mol_length)
+        p.insert_length = int(insert_length)
+        p.insert_stdev = int(insert_stdev)
+        p.length_r1, p.length_r2 = int(read_length[0]), int(read_length[1])
+        p.singletons = float(singletons)
+        p.circular = int(bool(circular))
+        p.mask = int(bool(mask))
+        p.seed = int(seed)
+        p.strict_wrap = int(bool(strict_wrap))
+        p.force_generic = int(bool(force_generic))
+        p.max_chunk_bytes = int(max_chunk_bytes)
+        p.plan_batch_groups = int(plan_batch_groups)
+        self.params = p
+        self._h = C.c_void_p()
+        rc = L.mmk_create(C.byref(p), C.byref(self._h))
+        if rc:
+            msg = L.mmk_last_error(self._h).decode() if self._h else "mmk_create failed"
+            if self._h:
+                L.mmk_destroy(self._h)
+                self._h = C.c_void_p()
+            raise MimickError(rc, msg)
+        self.plan_info = None
+        self.place_info = None
+
+    # ---- plumbing -------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc:
+            raise MimickError(rc, self._L.mmk_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.mmk_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def seed(self) -> int:
+        return int(self._L.mmk_seed(self._h))
+
+    @property
+    def cuda_stream(self) -> int:
+        return int(self._L.mmk_cuda_stream(self._h) or 0)
+
+    # ---- inputs ---------------------------------------------------------------------------
+    def add_contig(self, name: str, bases, haplotype: int = 1):
+        """`bases`: bytes / bytearray / numpy uint8 array / (address, length) tuple of host memory."""
+        if isinstance(bases, tuple):
+            addr, n = bases
+        else:
+            arr = bases if isinstance(bases, np.ndarray) else np.frombuffer(bases, dtype=np.uint8)
+            arr = np.ascontiguousarray(arr, dtype=np.uint8)
+            addr, n = arr.ctypes.data, arr.size
+        self._ck(self._L.mmk_add_contig(self._h, name.encode(), C.c_void_p(addr), n, int(haplotype)))
+
+    def load_fasta(self, path, haplotype: int = 1):
+        self._ck(self._L.mmk_load_fasta(self._h, os.fspath(path).encode(), int(haplotype)))
+
+    def apply_vcf_sample(self, vcf: Vcf, sample_index: int):
+        self._ck(self._L.mmk_apply_vcf_sample(self._h, vcf._h, int(sample_index)))
+
+    def set_sample_variants(self, sample_stream, ploidy, vcf_contigs, contig, pos, type, ref_len, alts, hap):
+        """Raw SoA entry point; `alts` is a list of bytes."""
+        vc = np.ascontiguousarray(vcf_contigs, dtype=np.int32)
+        contig = np.ascontiguousarray(contig, dtype=np.int32)
+        pos = np.ascontiguousarray(pos, dtype=np.int64)
+        typ = np.ascontiguousarray(type, dtype=np.uint8)
+        ref_len = np.ascontiguousarray(ref_len, dtype=np.int32)
+        hap = np.ascontiguousarray(hap, dtype=np.uint8)
+        alt_len = np.array([len(a) for a in alts], dtype=np.int32)
+        alt_off = np.zeros(len(alts), dtype=np.int64)
+        if len(alts):
+            alt_off[1:] = np.cumsum(alt_len[:-1])
+        blob = b"".join(alts)
+        self._ck(self._L.mmk_set_sample_variants(
+            self._h, int(sample_stream), int(ploidy), vc.ctypes.data, len(vc), len(pos), contig.ctypes.data,
+            pos.ctypes.data, typ.ctypes.data, ref_len.ctypes.data, alt_off.ctypes.data, alt_len.ctypes.data,
+            hap.ctypes.data, blob, len(blob)))
+
+    def schemas(self):
+        out = []
+        for i in range(self._L.mmk_n_schemas(self._h)):
+            s = SchemaInfo()
+            self._ck(self._L.mmk_schema_get(self._h, i, C.byref(s)))
+            out.append(dict(name=s.name.decode(), haplotype=s.haplotype, contig=s.contig, length=s.length,
+                            reads_required=s.reads_required, reads_current=s.reads_current))
+        return out
+
+    def schema_bases(self, i: int) -> bytes:
+        s = SchemaInfo()
+        self._ck(self._L.mmk_schema_get(self._h, i, C.byref(s)))
+        # length may change once the schema set is finalised; ask again afterwards
+        buf = C.create_string_buffer(max(int(s.length), 1) + 64)
+        self._ck(self._L.mmk_schema_bases(self._h, i, buf, len(buf)))
+        self._ck(self._L.mmk_schema_get(self._h, i, C.byref(s)))
+        return buf.raw[: s.length]
+
+    # ---- stages ---------------------------------------------------------------------------
+    def plan(self) -> PlanInfo:
+        info = PlanInfo()
+        self._ck(self._L.mmk_plan(self._h, C.byref(info)))
+        self.plan_info = info
+        return info
+
+    def set_shard(self, rank: int, world: int):
+        self._ck(self._L.mmk_set_shard(self._h, int(rank), int(world)))
+
+    def place(self) -> PlaceInfo:
+        info = PlaceInfo()
+        self._ck(self._L.mmk_place(self._h, C.byref(info)))
+        self.place_info = info
+        return info
+
+    def emit_chunk(self) -> Chunk:
+        ch = Chunk()
+        self._ck(self._L.mmk_emit_chunk(self._h, C.byref(ch)))
+        return ch
+
+    def rewind(self):
+        self._ck(self._L.mmk_rewind(self._h))
+
+    def copy_chunk(self, ch: Chunk):
+        r1 = np.empty(ch.r1_bytes, dtype=np.uint8)
+        r2 = np.empty(ch.r2_bytes, dtype=np.uint8)
+        self._ck(self._L.mmk_copy_chunk(self._h, C.byref(ch), r1.ctypes.data, r2.ctypes.data))
+        return r1, r2
+
+    def emit_to_host(self, r1=None, r2=None):
+        """Whole shard into host memory. `r1`/`r2`: optional (address, capacity) of caller buffers
+        (e.g. pinned); otherwise numpy arrays are allocated and returned."""
+        pi = self.place_info
+        if r1 is None:
+            a1 = np.empty(pi.r1_bytes, dtype=np.uint8)
+            a2 = np.empty(pi.r2_bytes, dtype=np.uint8)
+            self._ck(self._L.mmk_emit_to_host(self._h, a1.ctypes.data, a1.size, a2.ctypes.data, a2.size))
+            return a1, a2
+        self._ck(self._L.mmk_emit_to_host(self._h, C.c_void_p(r1[0]), r1[1], C.c_void_p(r2[0]), r2[1]))
+        return None
+
+    def run(self):
+        """plan → place → emit everything to host; returns (R1 bytes, R2 bytes)."""
+        self.plan()
+        self.place()
+        a1, a2 = self.emit_to_host()
+        return a1.tobytes(), a2.tobytes()
+
+    # ---- introspection --------------------------------------------------------------------
+    def molecules(self, first=0, n=None) -> np.ndarray:
+        if n is None:
+            n = self.plan_info.n_molecules - first
+        out = np.zeros(n, dtype=MOL_DTYPE)
+        assert MOL_DTYPE.itemsize == C.sizeof(MolRecord)
+        self._ck(self._L.mmk_dump_molecules(self._h, first, n, out.ctypes.data))
+        return out
+
+    def inserts(self, first=0, n=None):
+        if n is None:
+            n = self.place_info.n_pairs - first
+        st = np.zeros(n, dtype=np.int64)
+        en = np.zeros(n, dtype=np.int64)
+        self._ck(self._L.mmk_dump_inserts(self._h, first, n, st.ctypes.data, en.ctypes.data))
+        return st, en
+
+    def variates(self) -> np.ndarray:
+        n = C.c_uint64()
+        self._ck(self._L.mmk_dump_variates(self._h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=VARIATE_DTYPE)
+        self._ck(self._L.mmk_dump_variates(self._h, out.ctypes.data, out.size, C.byref(n)))
+        return out
+
+    def mask_variates(self) -> np.ndarray:
+        n = C.c_uint64()
+        self._ck(self._L.mmk_dump_mask_variates(self._h, None, 0, C.byref(n)))
+        out = np.zeros(n.value, dtype=VARIATE_DTYPE)
+        if n.value:
+            self._ck(self._L.mmk_dump_mask_variates(self._h, out.ctypes.data, out.size, C.byref(n)))
+        return out
+
+    def kat_philox(self, ctr, key):
+        c = np.array(ctr, dtype=np.uint32)
+        k = np.array(key, dtype=np.uint32)
+        o = np.zeros(4, dtype=np.uint32)
+        self._ck(self._L.mmk_kat_philox(self._h, c.ctypes.data, k.ctypes.data, o.ctypes.data))
+        return o
+
+    def kat_math(self, kind: int, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        o = np.zeros_like(x)
+        self._ck(self._L.mmk_kat_math(self._h, kind, x.ctypes.data, o.ctypes.data, x.size))
+        return o
+
+
+# ------------------------------------------------------------------------------------------
+# the reference's public function
+# ------------------------------------------------------------------------------------------
+_SIM_KW = ("coverage", "n_molecules", "mol_coverage", "mol_length", "insert_length", "insert_stdev", "read_length",
+           "singletons", "circular", "attempts", "seed", "mask", "device", "strict_wrap", "max_chunk_bytes")
+
+
+@dataclass
+class SampleOutput:
+    name: str
+    r1_path: str
+    r2_path: str
+    n_pairs: int
+    n_molecules: int
+    r1_bytes: int
+    r2_bytes: int
+    seed: int
+
+
+def _write_shard(sim: Simulator, r1_path: str, r2_path: str, mode: str):
+    with open(r1_path, mode) as f1, open(r2_path, mode) as f2:
+        sim.rewind()
+        while True:
+            ch = sim.emit_chunk()
+            if ch.n_pairs:
+                a1, a2 = sim.copy_chunk(ch)
+                f1.write(memoryview(a1))
+                f2.write(memoryview(a2))
+            if ch.done:
+                break
+
+
+def mimick(*args, prefix: str = "simulated/SIM", outdir: str = "simulated", quiet: bool = False,
+           rank: int = 0, world: int = 1, **kw):
+    """mimick(fasta::Vector{String}, format; ...)            — src/Main.jl:24
+    mimick(fasta::String, vcf::String, format; outdir, ...) — src/Main.jl:88
+
+    `rank`/`world` shard one run over several GPUs: every rank plans the same schedule and
+    writes its own contiguous part to `<...>.R1.fq.part<rank>` (concatenate in rank order), or —
+    in VCF mode — takes samples `rank, rank+world, ...`.
+    """
+    unknown = set(kw) - set(_SIM_KW)
+    if unknown:
+        raise TypeError(f"mimick() got unexpected keyword arguments {sorted(unknown)}")
+    if len(args) == 2:
+        fasta, fmt = args
+        vcf = None
+        if isinstance(fasta, (str, os.PathLike)):
+            fasta = [fasta]
+    elif len(args) == 3:
+        fasta, vcf, fmt = args
+    else:
+        raise TypeError("mimick(fasta_list, format, ...) or mimick(fasta, vcf, format, ...)")
+    L = _lib.load()
+    outs = []
+    if vcf is None:
+        with Simulator(fmt, **kw) as sim:
+            for hap, path in enumerate(fasta, start=1):
+                sim.load_fasta(path, hap)
+            d = os.path.dirname(prefix)
+            if d:
+                os.makedirs(d, exist_ok=True)
+            plan = sim.plan()
+            sim.set_shard(rank, world)
+            place = sim.place()
+            suffix = "" if world == 1 else f".part{rank}"
+            r1p, r2p = f"{prefix}.R1.fq{suffix}", f"{prefix}.R2.fq{suffix}"
+            _write_shard(sim, r1p, r2p, "wb")
+            outs.append(SampleOutput("", r1p, r2p, place.n_pairs, place.n_molecules, place.r1_bytes, place.r2_bytes, sim.seed))
+        return outs
+    rc = L.mmk_check_variant_path(os.fspath(vcf).encode())
+    if rc:
+        raise MimickError(rc, "BCF file type is not yet supported")
+    v = Vcf(vcf)
+    os.makedirs(outdir, exist_ok=True)
+    with Simulator(fmt, **kw) as sim:
+        sim.load_fasta(fasta, 1)  # master schema once, masking included (Main.jl:92)
+        for si in range(rank, len(v.samples), world):  # Threads.@threads over samples → samples over GPUs
+            sim.apply_vcf_sample(v, si)
+            plan = sim.plan()
+            sim.set_shard(0, 1)
+            place = sim.place()
+            r1p = os.path.join(outdir, f"{v.samples[si]}.R1.fq")
+            r2p = os.path.join(outdir, f"{v.samples[si]}.R2.fq")
+            _write_shard(sim, r1p, r2p, "wb")
+            outs.append(SampleOutput(v.samples[si], r1p, r2p, place.n_pairs, place.n_molecules, place.r1_bytes,
+                                     place.r2_bytes, sim.seed))
+    v.close()
+    return outs

@@ -1,0 +1,978 @@
+// mmk_device.cu — sm_100a kernels of the simulation core and their launchers.
+//
+// Kernel inventory (DESIGN.md §4 has the data layout and the roofline of each):
+//   k_normalize / k_mask_n / k_count      FASTA symbols → validated upper-case, N masking   ProcessFASTA.jl:29-36,52-57
+//   k_scatter_snps / k_pack_pieces        haplotype construction: SNP scatter + segmented    ProcessVariants.jl:143-176
+//                                         gather of indel pieces, packed to 2 or 4 bits/base
+//   k_group_nmol / k_plan_groups          barcode groups → molecules (target, size, #inserts) Main.jl:44-51, Breakpoints.jl:149-196
+//   k_hist / k_cross_* / k_cut / k_sums   coverage tracker + pruning point of a batch          Main.jl:54,58
+//   k_place                               insert sizes, start, gap chain, header text          Breakpoints.jl:205-251,21-35
+//   k_tile_sums                           record lengths per tile → byte offsets (with scan)   FormatFASTQ.jl
+//   k_emit                                extraction, reverse complement, FASTQ text           Breakpoints.jl:95-140, FormatFASTQ.jl
+#include <cstddef>
+#include <cstdio>
+
+#include "mmk_internal.h"
+#include "mmk_sampling.cuh"
+
+namespace mmkdev {
+
+// ------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ndigits_u64(uint64_t v) {
+    uint32_t d = 1;
+    while (v >= 10) {
+        v /= 10;
+        ++d;
+    }
+    return d;
+}
+__device__ __forceinline__ uint32_t ndigits_u32(uint32_t v) {
+    return 1u + (v >= 10u) + (v >= 100u) + (v >= 1000u) + (v >= 10000u) + (v >= 100000u) + (v >= 1000000u) +
+           (v >= 10000000u) + (v >= 100000000u) + (v >= 1000000000u);
+}
+__constant__ uint32_t c_pow10[10] = {1u, 10u, 100u, 1000u, 10000u, 100000u, 1000000u, 10000000u, 100000000u, 1000000000u};
+
+// 4-bit code (BioSequences bit mask A=1 C=2 G=4 T=8) of an ASCII symbol, 0xff if invalid.
+__device__ __forceinline__ uint32_t ascii_to_code4(uint32_t c) {
+    c &= 0xdfu;  // upper-case letters; '-' (0x2d) → 0x0d handled below
+    switch (c) {
+    case 'A': return 1; case 'C': return 2; case 'G': return 4; case 'T': return 8;
+    case 'M': return 3; case 'R': return 5; case 'W': return 9; case 'S': return 6;
+    case 'Y': return 10; case 'K': return 12; case 'V': return 7; case 'H': return 11;
+    case 'D': return 13; case 'B': return 14; case 'N': return 15;
+    default: return 0xffu;
+    }
+}
+__device__ __forceinline__ char code4_to_ascii(uint32_t k) { return "-ACMGRSVTWYHKDBN"[k & 15u]; }
+__device__ __forceinline__ uint32_t code4_to_code2(uint32_t k) { return (k == 2u) ? 1u : (k == 4u) ? 2u : (k == 8u) ? 3u : 0u; }
+__device__ __forceinline__ uint32_t comp4(uint32_t k) { return (__brev(k) >> 28) & 15u; }
+
+// ------------------------------------------------------------------------------------------
+// FASTA symbols
+// ------------------------------------------------------------------------------------------
+__global__ void k_normalize(char *bases, int64_t len, ContigStats *stats) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long nN = 0, nX = 0, bad = ~0ull;
+    for (; i < len; i += stride) {
+        uint32_t c = (uint8_t)bases[i];
+        uint32_t k = (c == '-') ? 0u : ascii_to_code4(c);
+        if (k == 0xffu || ((c & 0xdfu) < 'A' && c != '-')) {
+            if ((unsigned long long)i < bad) bad = (unsigned long long)i;
+            continue;
+        }
+        char u = code4_to_ascii(k);
+        bases[i] = u;
+        nN += (k == 15u);
+        nX += !(k == 1u || k == 2u || k == 4u || k == 8u);
+    }
+    for (int o = 16; o; o >>= 1) {
+        nN += __shfl_down_sync(0xffffffffu, nN, o);
+        nX += __shfl_down_sync(0xffffffffu, nX, o);
+        unsigned long long b2 = __shfl_down_sync(0xffffffffu, bad, o);
+        bad = b2 < bad ? b2 : bad;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (nN) atomicAdd(&stats->n_N, nN);
+        if (nX) atomicAdd(&stats->n_nonACGT, nX);
+        if (bad != ~0ull) atomicMin(&stats->first_bad, bad);
+    }
+}
+
+__global__ void k_count(const char *bases, int64_t len, ContigStats *stats) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long nN = 0, nX = 0;
+    for (; i < len; i += stride) {
+        char c = bases[i];
+        nN += (c == 'N');
+        nX += !(c == 'A' || c == 'C' || c == 'G' || c == 'T');
+    }
+    for (int o = 16; o; o >>= 1) {
+        nN += __shfl_down_sync(0xffffffffu, nN, o);
+        nX += __shfl_down_sync(0xffffffffu, nX, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (nN) atomicAdd(&stats->n_N, nN);
+        if (nX) atomicAdd(&stats->n_nonACGT, nX);
+    }
+}
+
+// mask_N!: every N ← (A,C,G,T)[pick(4)], the pick addressed by (contig, haplotype file, position)
+__global__ void k_mask_n(char *bases, int64_t len, uint64_t seed, uint32_t contig, uint32_t hap) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    mmk_stream s;
+    mmk_stream_init(&s, seed, 0, MMK_P_MASK, contig, hap);
+    for (; i < len; i += stride) {
+        if (bases[i] != 'N') continue;
+        uint32_t k = (uint32_t)mmk_bits_to_index(mmk_stream_at(&s, (uint32_t)i), 4);
+        bases[i] = "ACGT"[k];
+    }
+}
+
+__global__ void k_scatter_snps(char *bases, const int64_t *pos, const char *alt, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) bases[pos[i] - 1] = alt[i];
+}
+
+// Segmented gather + pack. One thread per output word.
+template <int BPB>
+__global__ void k_pack_pieces(const char *__restrict__ master, const char *__restrict__ alt,
+                              const int64_t *__restrict__ dst, const int64_t *__restrict__ src,
+                              const uint8_t *__restrict__ kind, int32_t n_pieces, int64_t out_len,
+                              uint32_t *__restrict__ words, ContigStats *stats) {
+    constexpr int PER = 32 / BPB;
+    int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t o = w * PER;
+    if (o >= out_len) return;
+    // piece containing o
+    int32_t lo = 0, hi = n_pieces - 1;
+    while (lo < hi) {
+        int32_t mid = (lo + hi + 1) >> 1;
+        if (dst[mid] <= o) lo = mid; else hi = mid - 1;
+    }
+    int32_t p = lo;
+    int64_t pdst = dst[p], psrc = src[p];
+    int64_t pend = (p + 1 < n_pieces) ? dst[p + 1] : out_len;
+    const char *base = kind[p] ? alt : master;
+    uint32_t word = 0;
+    bool bad = false;
+#pragma unroll 1
+    for (int j = 0; j < PER && o + j < out_len; ++j) {
+        int64_t q = o + j;
+        while (q >= pend) {
+            ++p;
+            pdst = dst[p];
+            psrc = src[p];
+            pend = (p + 1 < n_pieces) ? dst[p + 1] : out_len;
+            base = kind[p] ? alt : master;
+        }
+        uint32_t c = (uint8_t)base[psrc + (q - pdst)];
+        uint32_t k4 = (c == '-') ? 0u : ascii_to_code4(c);
+        if (BPB == 2) {
+            bad |= !(k4 == 1u || k4 == 2u || k4 == 4u || k4 == 8u);
+            word |= code4_to_code2(k4) << (2 * j);
+        } else {
+            bad |= (k4 == 0xffu);
+            word |= (k4 & 15u) << (4 * j);
+        }
+    }
+    words[w] = word;
+    if (bad) atomicMin(&stats->first_bad, (unsigned long long)o);
+}
+
+template <int BPB>
+__global__ void k_unpack(const uint32_t *__restrict__ words, int64_t len, char *__restrict__ out) {
+    constexpr int PER = 32 / BPB;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    uint32_t w = words[i / PER];
+    uint32_t k = (w >> (BPB * (i % PER))) & ((1u << BPB) - 1u);
+    out[i] = BPB == 2 ? "ACGT"[k] : code4_to_ascii(k);
+}
+
+static inline int grid_for(int64_t n, int block, int cap = 148 * 16) {
+    int64_t g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+
+void normalize_ascii(char *d, int64_t len, ContigStats *st, cudaStream_t s) {
+    k_normalize<<<grid_for(len, 256), 256, 0, s>>>(d, len, st);
+}
+void count_bases(const char *d, int64_t len, ContigStats *st, cudaStream_t s) {
+    k_count<<<grid_for(len, 256), 256, 0, s>>>(d, len, st);
+}
+void mask_n(char *d, int64_t len, uint64_t seed, uint32_t contig, uint32_t hap, cudaStream_t s) {
+    k_mask_n<<<grid_for(len, 256), 256, 0, s>>>(d, len, seed, contig, hap);
+}
+void scatter_snps(char *d, const int64_t *pos, const char *alt, int64_t n, cudaStream_t s) {
+    if (n > 0) k_scatter_snps<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d, pos, alt, n);
+}
+void pack_pieces(const char *master, const char *alt, const int64_t *dst, const int64_t *src, const uint8_t *kind,
+                 int32_t n_pieces, int64_t out_len, uint32_t *words, int bpb, ContigStats *st, cudaStream_t s) {
+    if (out_len <= 0) return;
+    int per = 32 / bpb;
+    int64_t nw = (out_len + per - 1) / per;
+    unsigned g = (unsigned)((nw + 255) / 256);
+    if (bpb == 2)
+        k_pack_pieces<2><<<g, 256, 0, s>>>(master, alt, dst, src, kind, n_pieces, out_len, words, st);
+    else
+        k_pack_pieces<4><<<g, 256, 0, s>>>(master, alt, dst, src, kind, n_pieces, out_len, words, st);
+}
+void unpack(const uint32_t *words, int64_t len, int bpb, char *out, cudaStream_t s) {
+    if (len <= 0) return;
+    unsigned g = (unsigned)((len + 255) / 256);
+    if (bpb == 2) k_unpack<2><<<g, 256, 0, s>>>(words, len, out);
+    else k_unpack<4><<<g, 256, 0, s>>>(words, len, out);
+}
+
+// ------------------------------------------------------------------------------------------
+// exclusive scan u32 → u64 (reduce / spine / apply; 1024 items per block)
+// ------------------------------------------------------------------------------------------
+constexpr int SCAN_T = 256, SCAN_I = 4, SCAN_B = SCAN_T * SCAN_I;
+
+__device__ __forceinline__ uint64_t block_exclusive_u64(uint64_t v, uint64_t *s_warp, uint64_t &total) {
+    // inclusive warp scan
+    uint64_t x = v;
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint64_t w = lane < (blockDim.x >> 5) ? s_warp[lane] : 0;
+        uint64_t ws = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint64_t y = __shfl_up_sync(0xffffffffu, ws, o);
+            if (lane >= o) ws += y;
+        }
+        s_warp[lane] = ws - w;                  // exclusive per warp
+        if (lane == 31) s_warp[32] = ws;        // block total
+    }
+    __syncthreads();
+    uint64_t res = s_warp[wid] + x - v;
+    total = s_warp[32];
+    __syncthreads();
+    return res;
+}
+
+__global__ void k_scan_reduce(const uint32_t *in, uint64_t n, uint64_t *block_sums) {
+    __shared__ uint64_t s_warp[33];
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_B + (uint64_t)threadIdx.x * SCAN_I;
+    uint64_t v = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_I; ++j)
+        if (base + j < n) v += in[base + j];
+    uint64_t total;
+    block_exclusive_u64(v, s_warp, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void k_scan_spine(uint64_t *block_sums, uint64_t nb) {
+    __shared__ uint64_t s_warp[33];
+    uint64_t carry = 0;
+    for (uint64_t base = 0; base < nb; base += blockDim.x) {
+        uint64_t i = base + threadIdx.x;
+        uint64_t v = i < nb ? block_sums[i] : 0;
+        uint64_t total;
+        uint64_t ex = block_exclusive_u64(v, s_warp, total);
+        if (i < nb) block_sums[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) block_sums[nb] = carry;
+}
+__global__ void k_scan_apply(const uint32_t *in, uint64_t n, const uint64_t *block_sums, uint64_t *out) {
+    __shared__ uint64_t s_warp[33];
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_B + (uint64_t)threadIdx.x * SCAN_I;
+    uint32_t it[SCAN_I];
+    uint64_t v = 0;
+#pragma unroll
+    for (int j = 0; j < SCAN_I; ++j) {
+        it[j] = base + j < n ? in[base + j] : 0;
+        v += it[j];
+    }
+    uint64_t total;
+    uint64_t ex = block_exclusive_u64(v, s_warp, total) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < SCAN_I; ++j) {
+        if (base + j < n) out[base + j] = ex;
+        ex += it[j];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = block_sums[gridDim.x];
+}
+void exclusive_scan_u32(const uint32_t *in, uint64_t *out, uint64_t n, uint64_t *tmp, cudaStream_t s) {
+    if (n == 0) {
+        cudaMemsetAsync(out, 0, 8, s);
+        return;
+    }
+    unsigned nb = (unsigned)((n + SCAN_B - 1) / SCAN_B);
+    k_scan_reduce<<<nb, SCAN_T, 0, s>>>(in, n, tmp);
+    k_scan_spine<<<1, 1024, 0, s>>>(tmp, nb);
+    k_scan_apply<<<nb, SCAN_T, 0, s>>>(in, n, tmp, out);
+}
+
+// ------------------------------------------------------------------------------------------
+// planning: barcode groups → molecules, coverage tracker, pruning point
+// ------------------------------------------------------------------------------------------
+__global__ void k_group_nmol(SimConst sc, uint64_t g0, uint32_t n_groups, uint32_t *nmol) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_groups) return;
+    NoRec rec;
+    nmol[i] = draw_nmol(sc, g0 + i, rec);
+}
+
+__global__ void k_plan_groups(SimConst sc, const SchemaDev *__restrict__ sch, const uint16_t *__restrict__ live,
+                              uint32_t n_live, uint16_t epoch, uint64_t g0, uint32_t n_groups,
+                              const uint32_t *__restrict__ nmol, const uint64_t *__restrict__ off, PlanDev plan,
+                              uint64_t mol_base) {
+    uint32_t gl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gl >= n_groups) return;
+    uint64_t g = g0 + gl;
+    uint32_t n = nmol[gl];
+    uint64_t o = mol_base + off[gl];
+    NoRec rec;
+    for (uint32_t m = 0; m < n; ++m) {
+        uint32_t t = live[draw_target(sc, g, m, n_live)];
+        uint32_t seq_len = sch[t].len;
+        uint32_t molsize, nfrags;
+        uint32_t status = molecule_shape(sc, g, m, seq_len, molsize, nfrags, rec);
+        plan.group[o + m] = g;
+        plan.slot[o + m] = m;
+        plan.schema[o + m] = (uint16_t)t;
+        plan.epoch[o + m] = epoch;
+        plan.size[o + m] = molsize;
+        plan.nfrags[o + m] = nfrags;
+        plan.status[o + m] = (uint8_t)status;
+    }
+}
+
+constexpr uint32_t HCH = 4096;  // molecules per histogram chunk
+
+__global__ void k_fill_lpos(const uint16_t *live, uint32_t n_live, uint16_t *lpos) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_live) lpos[live[i]] = (uint16_t)i;
+}
+
+// hist[c * n_live + lpos] += nfrags of chunk c's molecules of that live schema. The number of
+// molecules in the batch is only known on the device (off[n_groups]).
+__global__ void k_hist(const uint16_t *__restrict__ schema, const uint32_t *__restrict__ nfrags,
+                       const uint64_t *__restrict__ off, uint32_t n_groups, const uint16_t *__restrict__ lpos,
+                       uint32_t n_live, unsigned long long *hist) {
+    uint64_t n_mol = off[n_groups];
+    uint64_t c = blockIdx.x;
+    uint64_t lo = c * HCH;
+    if (lo >= n_mol) return;
+    uint64_t hi = lo + HCH < n_mol ? lo + HCH : n_mol;
+    unsigned long long *row = hist + c * n_live;
+    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
+        atomicAdd(&row[lpos[schema[i]]], (unsigned long long)nfrags[i]);
+}
+
+// One warp per live schema: the chunk in which its cumulative insert count reaches `need`, then
+// the molecule inside that chunk; reports that molecule's barcode group (Main.jl:54,58: a schema
+// is pruned at the END of the group in which it reaches reads_required).
+__global__ void k_cross(const uint16_t *__restrict__ schema, const uint32_t *__restrict__ nfrags,
+                        const uint64_t *__restrict__ group, const uint64_t *__restrict__ off, uint32_t n_groups,
+                        const uint16_t *__restrict__ live, uint32_t n_live, const unsigned long long *__restrict__ hist,
+                        const int64_t *__restrict__ need, uint64_t g0, unsigned long long *cross_group) {
+    uint64_t n_mol = off[n_groups];
+    uint32_t n_chunks = (uint32_t)((n_mol + HCH - 1) / HCH);
+    uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    if (s >= n_live) return;
+    int64_t want = need[s];
+    if (want <= 0) {  // already complete: pruned at the end of the batch's first group
+        if (lane == 0) cross_group[s] = g0;
+        return;
+    }
+    uint16_t sid = live[s];
+    unsigned long long cum = 0;
+    uint32_t found_chunk = 0xffffffffu;
+    for (uint32_t c0 = 0; c0 < n_chunks && found_chunk == 0xffffffffu; c0 += 32) {
+        uint32_t c = c0 + lane;
+        unsigned long long v = c < n_chunks ? hist[(uint64_t)c * n_live + s] : 0ull;
+        unsigned long long inc = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        unsigned ball = __ballot_sync(0xffffffffu, (long long)(cum + inc) >= want);
+        if (ball) {
+            int l = __ffs(ball) - 1;
+            unsigned long long before = __shfl_sync(0xffffffffu, inc - v, l);
+            found_chunk = c0 + l;
+            cum += before;
+        } else {
+            cum += __shfl_sync(0xffffffffu, inc, 31);
+        }
+    }
+    if (found_chunk == 0xffffffffu) {
+        if (lane == 0) cross_group[s] = ~0ull;
+        return;
+    }
+    constexpr uint32_t PER = HCH / 32;  // each lane owns PER consecutive molecules of the chunk
+    uint64_t lo = (uint64_t)found_chunk * HCH + (uint64_t)lane * PER;
+    unsigned long long part = 0;
+    for (uint32_t j = 0; j < PER; ++j) {
+        uint64_t i = lo + j;
+        if (i < n_mol && schema[i] == sid) part += nfrags[i];
+    }
+    unsigned long long inc = part;
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    unsigned ball = __ballot_sync(0xffffffffu, (long long)(cum + inc) >= want);
+    int l = __ffs(ball) - 1;  // non-zero by construction
+    if ((int)lane == l) {
+        unsigned long long run = cum + inc - part;
+        for (uint32_t j = 0; j < PER; ++j) {
+            uint64_t i = lo + j;
+            if (i < n_mol && schema[i] == sid) {
+                run += nfrags[i];
+                if ((long long)run >= want) {
+                    cross_group[s] = group[i];
+                    break;
+                }
+            }
+        }
+    }
+}
+
+__global__ void k_cut(const unsigned long long *cross_group, uint32_t n_live, uint64_t g0, uint32_t n_groups,
+                      const uint64_t *off, const uint8_t *status, BatchResult *res) {
+    __shared__ unsigned long long s_cut, s_err;
+    __shared__ uint64_t s_commit;
+    if (threadIdx.x == 0) {
+        s_cut = ~0ull;
+        s_err = ~0ull;
+    }
+    __syncthreads();
+    unsigned long long mine = ~0ull;
+    for (uint32_t i = threadIdx.x; i < n_live; i += blockDim.x) mine = cross_group[i] < mine ? cross_group[i] : mine;
+    if (mine != ~0ull) atomicMin(&s_cut, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t total = off[n_groups];
+        s_commit = (s_cut == ~0ull) ? total : off[(uint32_t)(s_cut - g0) + 1];
+    }
+    __syncthreads();
+    uint64_t nc = s_commit;
+    unsigned long long e = ~0ull;
+    for (uint64_t i = threadIdx.x; i < nc; i += blockDim.x)
+        if (status[i] && i < e) e = i;
+    if (e != ~0ull) atomicMin(&s_err, e);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        res->cut_group = s_cut;
+        res->n_commit = nc;
+        res->first_error = s_err;
+        res->error_code = s_err != ~0ull ? status[s_err] : 0;
+    }
+}
+
+__global__ void k_sums(const uint16_t *__restrict__ schema, const uint32_t *__restrict__ nfrags,
+                       const uint16_t *__restrict__ lpos, uint32_t n_live, BatchResult *res) {
+    uint64_t n = res->n_commit;
+    unsigned long long *sums = (unsigned long long *)res->sums;
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    extern __shared__ unsigned long long s_h[];
+    if (n_live <= 2048) {
+        for (uint32_t j = threadIdx.x; j < n_live; j += blockDim.x) s_h[j] = 0;
+        __syncthreads();
+        for (; i < n; i += stride) atomicAdd(&s_h[lpos[schema[i]]], (unsigned long long)nfrags[i]);
+        __syncthreads();
+        for (uint32_t j = threadIdx.x; j < n_live; j += blockDim.x)
+            if (s_h[j]) atomicAdd(&sums[j], s_h[j]);
+    } else {
+        for (; i < n; i += stride) atomicAdd(&sums[lpos[schema[i]]], (unsigned long long)nfrags[i]);
+    }
+}
+
+uint32_t plan_hist_chunks(uint64_t max_molecules) { return (uint32_t)((max_molecules + HCH - 1) / HCH); }
+
+void plan_batch(const SimConst &sc, const SchemaDev *d_sch, const uint16_t *d_live, uint32_t n_live, uint16_t epoch,
+                uint64_t g0, uint32_t n_groups, uint32_t *d_nmol, uint64_t *d_off, uint64_t *d_scan_tmp, PlanDev plan,
+                uint64_t mol_base, uint64_t max_mol, const int64_t *d_need, unsigned long long *d_hist,
+                unsigned long long *d_cross, uint16_t *d_lpos, BatchResult *d_res, cudaStream_t st) {
+    k_group_nmol<<<(n_groups + 255) / 256, 256, 0, st>>>(sc, g0, n_groups, d_nmol);
+    exclusive_scan_u32(d_nmol, d_off, n_groups, d_scan_tmp, st);
+    k_plan_groups<<<(n_groups + 127) / 128, 128, 0, st>>>(sc, d_sch, d_live, n_live, epoch, g0, n_groups, d_nmol, d_off,
+                                                          plan, mol_base);
+    uint32_t n_chunks = plan_hist_chunks(max_mol);
+    cudaMemsetAsync(d_hist, 0, (size_t)n_chunks * n_live * sizeof(unsigned long long), st);
+    k_fill_lpos<<<(n_live + 255) / 256, 256, 0, st>>>(d_live, n_live, d_lpos);
+    k_hist<<<n_chunks, 256, 0, st>>>(plan.schema + mol_base, plan.nfrags + mol_base, d_off, n_groups, d_lpos, n_live, d_hist);
+    k_cross<<<(n_live * 32 + 127) / 128, 128, 0, st>>>(plan.schema + mol_base, plan.nfrags + mol_base, plan.group + mol_base,
+                                                       d_off, n_groups, d_live, n_live, d_hist, d_need, g0, d_cross);
+    k_cut<<<1, 1024, 0, st>>>(d_cross, n_live, g0, n_groups, d_off, plan.status + mol_base, d_res);
+    cudaMemsetAsync((char *)d_res + offsetof(BatchResult, sums), 0, (size_t)n_live * 8, st);
+    size_t sm = n_live <= 2048 ? (size_t)n_live * 8 : 0;
+    k_sums<<<148 * 4, 256, sm, st>>>(plan.schema + mol_base, plan.nfrags + mol_base, d_lpos, n_live, d_res);
+}
+
+// ------------------------------------------------------------------------------------------
+// sharding
+// ------------------------------------------------------------------------------------------
+__global__ void k_shard_bounds(const uint64_t *read_off, uint64_t n_mol, uint64_t n_pairs, int32_t world, uint64_t *bounds) {
+    int w = threadIdx.x;
+    if (w > world) return;
+    if (w == world) {
+        bounds[w] = n_mol;
+        return;
+    }
+    uint64_t target = n_pairs / (uint64_t)world * (uint64_t)w + n_pairs % (uint64_t)world * (uint64_t)w / (uint64_t)world;
+    uint64_t lo = 0, hi = n_mol;  // smallest m with read_off[m] >= target
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        if (read_off[mid] >= target) hi = mid; else lo = mid + 1;
+    }
+    bounds[w] = lo;
+}
+void shard_bounds(const uint64_t *d_read_off, uint64_t n_mol, uint64_t n_pairs, int32_t world, uint64_t *d_bounds,
+                  cudaStream_t st) {
+    k_shard_bounds<<<1, 1024, 0, st>>>(d_read_off, n_mol, n_pairs, world, d_bounds);
+}
+
+// ------------------------------------------------------------------------------------------
+// placement
+// ------------------------------------------------------------------------------------------
+// Length of circular_index(seq, a:b) (Breakpoints.jl:111-121) for a sequence of n bases.
+__device__ __forceinline__ uint32_t window_len(int64_t a, int64_t b, uint32_t n, int strict) {
+    if (strict || b <= (int64_t)n) return (uint32_t)(b - a + 1);
+    uint32_t part1 = a <= (int64_t)n ? (uint32_t)((int64_t)n - a + 1) : 0u;
+    return part1 + (uint32_t)b % n;  // b < 2^32: contigs are < 2^31 bases
+}
+
+__device__ __forceinline__ uint8_t *put_dec(uint8_t *p, uint64_t v) {
+    char tmp[20];
+    int n = 0;
+    do {
+        tmp[n++] = (char)('0' + v % 10);
+        v /= 10;
+    } while (v);
+    while (n) *p++ = (uint8_t)tmp[--n];
+    return p;
+}
+__device__ __forceinline__ uint8_t *put_str(uint8_t *p, const char *s) {
+    while (*s) *p++ = (uint8_t)*s++;
+    return p;
+}
+__device__ __forceinline__ uint8_t *put_barcode(uint8_t *p, int bc_format, uint64_t k) {
+    switch (bc_format) {
+    case MMK_FMT_HAPLOTAGGING: {
+        uint32_t v[4] = {(uint32_t)(k % 96), (uint32_t)(k / 96 % 96), (uint32_t)(k / 9216 % 96), (uint32_t)(k / 884736)};
+        const char L[4] = {'A', 'C', 'B', 'D'};
+        for (int i = 0; i < 4; ++i) {
+            uint32_t x = v[i] + 1;
+            *p++ = (uint8_t)L[i];
+            *p++ = (uint8_t)('0' + x / 10);
+            *p++ = (uint8_t)('0' + x % 10);
+        }
+        return p;
+    }
+    case MMK_FMT_STLFR:
+        p = put_dec(p, k % 2000 + 1);
+        *p++ = '_';
+        p = put_dec(p, k / 2000 % 2000 + 1);
+        *p++ = '_';
+        return put_dec(p, k / 4000000 + 1);
+    default: {
+        int n = bc_format == MMK_FMT_TELLSEQ ? 18 : 16;
+        for (int t = 0; t < n; ++t) *p++ = (uint8_t)"ATGC"[(k >> (2 * t)) & 3];
+        return p;
+    }
+    }
+}
+
+// Read-window checks the reference would fail on (BoundsError) and the quality-string lengths,
+// which follow the molecule's FIRST reads (FormatFASTQ.jl:14: "I"^length(read_sequences.first[1])).
+// __noinline__: cicc 12.9 crashes when this loop is inlined behind molecule_place.
+__device__ __noinline__ uint32_t check_windows(const uint2 *ins, uint32_t nfrags, int64_t start, uint32_t n, int r1, int r2,
+                                               int strict, uint32_t &q1, uint32_t &q2) {
+    uint32_t status = 0;
+    for (uint32_t k = 0; k < nfrags; ++k) {
+        int64_t bs = start + ins[k].x, be = bs + ins[k].y - 1;
+        int64_t a2 = be - r2 + 1;
+        if (!strict && a2 < 1) status = MMK_ERR_BOUNDS;
+        if (k == 0) {
+            q1 = window_len(bs, bs + r1 - 1, n, strict);
+            q2 = (a2 >= 1 || strict) ? window_len(a2, be, n, strict) : 0u;
+        }
+    }
+    return status;
+}
+
+__global__ void k_place(SimConst sc, const SchemaDev *__restrict__ sch, PlanDev plan, uint64_t mol0, uint32_t n_mol,
+                        const uint64_t *__restrict__ roff_g, uint2 *ins, MolRec *mol, uint8_t *text, uint32_t text_stride,
+                        uint64_t *roff_l, unsigned long long *err) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n_mol) return;
+    uint64_t base = roff_g[mol0];
+    if (i == n_mol) {
+        roff_l[i] = roff_g[mol0 + n_mol] - base;
+        return;
+    }
+    uint64_t gi = mol0 + i;
+    uint64_t ro = roff_g[gi] - base;
+    roff_l[i] = ro;
+    uint64_t g = plan.group[gi];
+    uint32_t m = plan.slot[gi];
+    uint32_t t = plan.schema[gi];
+    uint32_t molsize = plan.size[gi], nfrags = plan.nfrags[gi];
+    const SchemaDev &S = sch[t];
+    NoRec rec;
+    int64_t start;
+    uint32_t status = molecule_place(sc, g, m, S.len, molsize, nfrags, ins + ro, start, rec);
+    uint32_t n = S.len;
+    uint32_t q1 = 0, q2 = 0;
+    if (!status) status = check_windows(ins + ro, nfrags, start, n, sc.r1, sc.r2, sc.strict, q1, q2);
+    if (sc.fq_format == MMK_FMT_TENX) q1 += 16;
+    if (status) {
+        atomicMin(&err[0], (unsigned long long)gi);
+        plan.status[gi] = (uint8_t)status;
+    }
+    // header text: "@chrom:hap|start:end|" then the format's tail with read digit '1'
+    uint8_t *tp = text + (uint64_t)i * text_stride;
+    uint8_t *p = tp;
+    *p++ = '@';
+    for (int k = 0; k < S.name_len; ++k) *p++ = (uint8_t)S.name[k];
+    *p++ = ':';
+    p = put_dec(p, S.haplotype);
+    *p++ = '|';
+    p = put_dec(p, (uint64_t)start);
+    *p++ = ':';
+    p = put_dec(p, (uint64_t)(start + molsize));
+    *p++ = '|';
+    uint32_t plen = (uint32_t)(p - tp);
+    uint8_t *sp = p;
+    switch (sc.fq_format) {
+    case MMK_FMT_STLFR: *p++ = '#'; p = put_barcode(p, sc.bc_format, gi); p = put_str(p, " 1:N:0:ATGACA\n"); break;
+    case MMK_FMT_HAPLOTAGGING: p = put_str(p, "/1\tBX:Z:"); p = put_barcode(p, sc.bc_format, gi); *p++ = '\n'; break;
+    case MMK_FMT_TELLSEQ: *p++ = ':'; p = put_barcode(p, sc.bc_format, gi); p = put_str(p, " 1:N:0:ATGACA\n"); break;
+    case MMK_FMT_TENX: *p++ = '|'; p = put_barcode(p, sc.bc_format, gi); p = put_str(p, " 1:N:0:ATGACA\n"); break;
+    default: p = put_str(p, "/1\tVX:i:1\tBX:Z:"); p = put_barcode(p, sc.bc_format, gi); *p++ = '\n'; break;
+    }
+    MolRec r;
+    r.start = start;
+    r.size = molsize;
+    r.schema = (uint16_t)t;
+    r.prefix_len = (uint8_t)plen;
+    r.suffix_len = (uint8_t)(p - sp);
+    r.qual1 = q1;
+    r.qual2 = q2;
+    mol[i] = r;
+}
+void place(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol,
+           const uint64_t *d_read_off_global, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
+           uint64_t *d_read_off_local, unsigned long long *d_err, cudaStream_t st) {
+    k_place<<<(n_mol + 1 + 127) / 128, 128, 0, st>>>(sc, d_sch, plan, mol0, n_mol, d_read_off_global, d_ins, d_mol, d_text,
+                                                     text_stride, d_read_off_local, d_err);
+}
+
+// ------------------------------------------------------------------------------------------
+// records: shared decode of one read pair
+// ------------------------------------------------------------------------------------------
+struct PairDesc {
+    uint32_t mol;        // shard-relative molecule index
+    uint32_t bstart, bend;   // 1-based inclusive insert breakpoints (fit u32: contigs < 2^31)
+    uint32_t d1, d2;     // decimal widths
+    uint32_t hdr;        // header line length incl. '\n'
+    uint32_t sq1, sq2;   // sequence lengths
+    uint32_t len1, len2; // record lengths
+};
+
+__device__ __forceinline__ uint32_t find_mol(const uint64_t *__restrict__ roff, uint32_t lo, uint32_t hi, uint64_t p) {
+    // largest m in [lo, hi] with roff[m] <= p
+    while (lo < hi) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (roff[mid] <= p) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ void decode_pair(const EmitArgs &a, uint64_t p, uint32_t m, PairDesc &d, MolRec &mr) {
+    mr = a.mol[m];
+    uint2 in = a.ins[p];
+    d.mol = m;
+    d.bstart = (uint32_t)(mr.start + in.x);
+    d.bend = d.bstart + in.y - 1;
+    d.d1 = ndigits_u32(d.bstart);
+    d.d2 = ndigits_u32(d.bend);
+    d.hdr = mr.prefix_len + d.d1 + 1 + d.d2 + mr.suffix_len;
+    uint32_t n = a.sch[mr.schema].len;
+    d.sq1 = window_len(d.bstart, (int64_t)d.bstart + a.r1 - 1, n, a.strict);
+    d.sq2 = window_len((int64_t)d.bend - a.r2 + 1, d.bend, n, a.strict);
+    d.len1 = d.hdr + a.bclen_inline + d.sq1 + 3 + mr.qual1 + 1;
+    d.len2 = d.hdr + d.sq2 + 3 + mr.qual2 + 1;
+}
+
+// Base (as ASCII) number j of circular_index(seq, a:b), forward orientation.
+__device__ __forceinline__ uint32_t window_pos(int64_t a, int64_t b, uint32_t n, int strict, uint32_t j) {
+    if (strict) {
+        int64_t q = a - 1 + (int64_t)j;  // may be negative when the insert is shorter than R2 near position 1
+        if (q < 0) q += (int64_t)n * ((-q) / (int64_t)n + 1);
+        return (uint32_t)((uint64_t)q % n);
+    }
+    if (b <= (int64_t)n) return (uint32_t)(a - 1 + j);
+    uint32_t part1 = a <= (int64_t)n ? (uint32_t)((int64_t)n - a + 1) : 0u;
+    return j < part1 ? (uint32_t)(a - 1 + j) : j - part1;
+}
+template <int BPB>
+__device__ __forceinline__ uint32_t fetch_code(const uint32_t *__restrict__ w, uint32_t pos) {
+    constexpr uint32_t PER = 32 / BPB;
+    return (__ldg(&w[pos / PER]) >> (BPB * (pos % PER))) & ((1u << BPB) - 1u);
+}
+
+// General byte-wise record writer: any read length, wrap mode, quality length. One warp per record.
+template <int BPB>
+__device__ void write_record_generic(const EmitArgs &a, const PairDesc &d, const MolRec &mr, int rd, uint8_t *out, uint32_t lane) {
+    const uint8_t *tx = a.text + (uint64_t)d.mol * a.text_stride;
+    const SchemaDev &S = a.sch[mr.schema];
+    const uint32_t *hw = a.hap + S.word_off;
+    const uint32_t n = S.len;
+    const uint32_t P = mr.prefix_len, SUF = mr.suffix_len;
+    const uint32_t rd_pos = (a.fq_format == MMK_FMT_HAPLOTAGGING || a.fq_format == MMK_FMT_STANDARD) ? 1u : SUF - 13u;
+    const uint32_t inl = rd == 1 ? (uint32_t)a.bclen_inline : 0u;
+    const uint32_t sq = rd == 1 ? d.sq1 : d.sq2;
+    const uint32_t q = rd == 1 ? mr.qual1 : mr.qual2;
+    const uint32_t len = rd == 1 ? d.len1 : d.len2;
+    const int64_t wa = rd == 1 ? (int64_t)d.bstart : (int64_t)d.bend - a.r2 + 1;
+    const int64_t wb = rd == 1 ? (int64_t)d.bstart + a.r1 - 1 : (int64_t)d.bend;
+    for (uint32_t k0 = lane; k0 < len; k0 += 32) {
+        uint32_t k = k0;
+        uint8_t c;
+        if (k < P) c = tx[k];
+        else if ((k -= P) < d.d1) c = (uint8_t)('0' + (d.bstart / c_pow10[d.d1 - 1 - k]) % 10);
+        else if ((k -= d.d1) == 0) c = ':';
+        else if ((k -= 1) < d.d2) c = (uint8_t)('0' + (d.bend / c_pow10[d.d2 - 1 - k]) % 10);
+        else if ((k -= d.d2) < SUF) c = (k == rd_pos) ? (uint8_t)('0' + rd) : tx[P + k];
+        else if ((k -= SUF) < inl) c = tx[P + 1 + k];
+        else if ((k -= inl) < sq) {
+            uint32_t j = rd == 1 ? sq - 1 - k : k;
+            uint32_t code = fetch_code<BPB>(hw, window_pos(wa, wb, n, a.strict, j));
+            if (BPB == 2) c = (uint8_t)(rd == 1 ? "TGCA"[code] : "ACGT"[code]);
+            else c = (uint8_t)code4_to_ascii(rd == 1 ? comp4(code) : code);
+        } else if ((k -= sq) < 3) c = (uint8_t)(k == 1 ? '+' : '\n');
+        else if ((k -= 3) < q) c = 'I';
+        else c = '\n';
+        out[k0] = c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// tile sums: record lengths of every tile of `tile_pairs` pairs
+// ------------------------------------------------------------------------------------------
+__global__ void k_tile_sums(EmitArgs a, uint32_t n_tiles, uint32_t *sum1, uint32_t *sum2, unsigned long long *gather) {
+    __shared__ uint32_t s_m0, s_m1;
+    __shared__ uint32_t s_acc[3];
+    uint32_t tile = blockIdx.x;
+    if (tile >= n_tiles) return;
+    uint64_t p0 = (uint64_t)tile * a.tile_pairs;
+    uint32_t np = (uint32_t)((a.n_pairs - p0) < a.tile_pairs ? (a.n_pairs - p0) : a.tile_pairs);
+    if (threadIdx.x == 0) {
+        s_m0 = find_mol(a.read_off, 0, a.n_mol - 1, p0);
+        s_acc[0] = s_acc[1] = s_acc[2] = 0;
+    }
+    if (threadIdx.x == 32) s_m1 = find_mol(a.read_off, 0, a.n_mol - 1, p0 + np - 1);
+    __syncthreads();
+    uint32_t l1 = 0, l2 = 0, gb = 0;
+    if (threadIdx.x < np) {
+        uint64_t p = p0 + threadIdx.x;
+        uint32_t m = find_mol(a.read_off, s_m0, s_m1, p);
+        PairDesc d;
+        MolRec mr;
+        decode_pair(a, p, m, d, mr);
+        l1 = d.len1;
+        l2 = d.len2;
+        gb = (d.sq1 * a.bpb + 7) / 8 + (d.sq2 * a.bpb + 7) / 8;
+    }
+    for (int o = 16; o; o >>= 1) {
+        l1 += __shfl_down_sync(0xffffffffu, l1, o);
+        l2 += __shfl_down_sync(0xffffffffu, l2, o);
+        gb += __shfl_down_sync(0xffffffffu, gb, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_acc[0], l1);
+        atomicAdd(&s_acc[1], l2);
+        atomicAdd(&s_acc[2], gb);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sum1[tile] = s_acc[0];
+        sum2[tile] = s_acc[1];
+        atomicAdd(gather, (unsigned long long)s_acc[2]);
+    }
+}
+void tile_sums(const EmitArgs &a, uint32_t n_tiles_total, uint32_t *d_sum1, uint32_t *d_sum2, unsigned long long *d_gather,
+               cudaStream_t st) {
+    if (n_tiles_total == 0) return;
+    uint32_t threads = (a.tile_pairs + 31) / 32 * 32;
+    if (threads < 64) threads = 64;
+    k_tile_sums<<<n_tiles_total, threads, 0, st>>>(a, n_tiles_total, d_sum1, d_sum2, d_gather);
+}
+
+__global__ void k_find_tile(const uint64_t *off1, const uint64_t *off2, uint32_t tile0, uint32_t n_tiles, uint64_t cap,
+                            uint32_t *out) {
+    if (threadIdx.x >= 2) return;
+    const uint64_t *off = threadIdx.x ? off2 : off1;
+    uint64_t base = off[tile0];
+    uint32_t lo = tile0, hi = n_tiles;  // largest t with off[t] - base <= cap
+    while (lo < hi) {
+        uint32_t mid = (uint32_t)(((uint64_t)lo + hi + 1) >> 1);
+        if (off[mid] - base <= cap) lo = mid; else hi = mid - 1;
+    }
+    out[threadIdx.x] = lo;
+}
+void find_tile(const uint64_t *d_off1, const uint64_t *d_off2, uint32_t tile0, uint32_t n_tiles, uint64_t cap, uint32_t *d_out,
+               cudaStream_t st) {
+    k_find_tile<<<1, 32, 0, st>>>(d_off1, d_off2, tile0, n_tiles, cap, d_out);
+}
+
+// ------------------------------------------------------------------------------------------
+// emit
+// ------------------------------------------------------------------------------------------
+constexpr int EMIT_THREADS = 256;
+constexpr int EMIT_MAX_TP = 64;
+
+template <int BPB>
+__global__ void __launch_bounds__(EMIT_THREADS) k_emit(const __grid_constant__ EmitArgs a) {
+    __shared__ uint32_t s_m0, s_m1;
+    __shared__ PairDesc s_d[EMIT_MAX_TP];
+    __shared__ uint32_t s_off1[EMIT_MAX_TP + 1], s_off2[EMIT_MAX_TP + 1];
+    const uint32_t tile = a.tile0 + blockIdx.x;
+    const uint64_t p0 = (uint64_t)tile * a.tile_pairs;
+    const uint32_t np = (uint32_t)((a.n_pairs - p0) < a.tile_pairs ? (a.n_pairs - p0) : a.tile_pairs);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_m0 = find_mol(a.read_off, 0, a.n_mol - 1, p0);
+    if (threadIdx.x == 32) s_m1 = find_mol(a.read_off, 0, a.n_mol - 1, p0 + np - 1);
+    __syncthreads();
+    if (threadIdx.x < np) {
+        uint64_t p = p0 + threadIdx.x;
+        uint32_t m = find_mol(a.read_off, s_m0, s_m1, p);
+        PairDesc d;
+        MolRec mr;
+        decode_pair(a, p, m, d, mr);
+        s_d[threadIdx.x] = d;
+    }
+    __syncthreads();
+    // exclusive scan of record lengths within the tile (np <= 64: two items per lane of warp 0)
+    if (warp == 0) {
+        uint32_t a1 = lane * 2 < np ? s_d[lane * 2].len1 : 0, b1 = lane * 2 + 1 < np ? s_d[lane * 2 + 1].len1 : 0;
+        uint32_t a2 = lane * 2 < np ? s_d[lane * 2].len2 : 0, b2 = lane * 2 + 1 < np ? s_d[lane * 2 + 1].len2 : 0;
+        uint32_t x1 = a1 + b1, x2 = a2 + b2;
+        uint32_t i1 = x1, i2 = x2;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y1 = __shfl_up_sync(0xffffffffu, i1, o), y2 = __shfl_up_sync(0xffffffffu, i2, o);
+            if (lane >= o) {
+                i1 += y1;
+                i2 += y2;
+            }
+        }
+        uint32_t e1 = i1 - x1, e2 = i2 - x2;
+        if (lane * 2 <= np) { s_off1[lane * 2] = e1; s_off2[lane * 2] = e2; }
+        if (lane * 2 + 1 <= np) { s_off1[lane * 2 + 1] = e1 + a1; s_off2[lane * 2 + 1] = e2 + a2; }
+        if (lane == 31 && np == 64) { s_off1[64] = i1; s_off2[64] = i2; }
+    }
+    __syncthreads();
+    uint8_t *o1 = a.out1 + (a.tile_off1[tile] - a.chunk_off1);
+    uint8_t *o2 = a.out2 + (a.tile_off2[tile] - a.chunk_off2);
+    for (uint32_t t = warp; t < np; t += EMIT_THREADS / 32) {
+        PairDesc d = s_d[t];
+        MolRec mr = a.mol[d.mol];
+        write_record_generic<BPB>(a, d, mr, 1, o1 + s_off1[t], lane);
+        write_record_generic<BPB>(a, d, mr, 2, o2 + s_off2[t], lane);
+    }
+}
+void emit(const EmitArgs &a, cudaStream_t st) {
+    if (a.n_tiles == 0) return;
+    if (a.bpb == 2) k_emit<2><<<a.n_tiles, EMIT_THREADS, 0, st>>>(a);
+    else k_emit<4><<<a.n_tiles, EMIT_THREADS, 0, st>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------
+// variate dump (replay stream for the oracle)
+// ------------------------------------------------------------------------------------------
+template <class R>
+__device__ __forceinline__ void dump_molecule(const SimConst &sc, const SchemaDev *sch, const PlanDev &plan, uint64_t i,
+                                              const uint64_t *roff, uint2 *ins, const uint32_t *epoch_nlive, R &rec) {
+    uint64_t g = plan.group[i];
+    uint32_t m = plan.slot[i];
+    uint32_t seq_len = sch[plan.schema[i]].len;
+    if (m == 0) {
+        uint32_t n = draw_nmol(sc, g, rec);
+        uint32_t n_live = epoch_nlive[plan.epoch[i]];
+        for (uint32_t j = 0; j < n; ++j) rec.put(MMK_P_TARGET, n_live, draw_target(sc, g, j, n_live));
+    }
+    uint32_t molsize, nfrags;
+    molecule_shape(sc, g, m, seq_len, molsize, nfrags, rec);
+    int64_t start;
+    molecule_place(sc, g, m, seq_len, molsize, nfrags, ins + roff[i], start, rec);
+}
+__global__ void k_dump_count(SimConst sc, const SchemaDev *sch, PlanDev plan, uint64_t n_mol, const uint64_t *roff, uint2 *ins,
+                             const uint32_t *epoch_nlive, uint32_t *counts) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_mol) return;
+    CountRec rec;
+    dump_molecule(sc, sch, plan, i, roff, ins, epoch_nlive, rec);
+    counts[i] = rec.n;
+}
+__global__ void k_dump_write(SimConst sc, const SchemaDev *sch, PlanDev plan, uint64_t n_mol, const uint64_t *roff, uint2 *ins,
+                             const uint32_t *epoch_nlive, const uint64_t *offsets, mmk_variate *out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_mol) return;
+    WriteRec rec{out + offsets[i]};
+    dump_molecule(sc, sch, plan, i, roff, ins, epoch_nlive, rec);
+}
+void dump_variates(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t n_mol, const uint64_t *d_read_off,
+                   const uint2 *d_ins, const uint32_t *d_epoch_nlive, const uint16_t *, uint32_t, uint32_t *d_counts,
+                   uint64_t *d_offsets, uint64_t *d_scan_tmp, mmk_variate *d_out, int pass, cudaStream_t st) {
+    if (n_mol == 0) return;
+    unsigned g = (unsigned)((n_mol + 127) / 128);
+    if (pass == 0) {
+        k_dump_count<<<g, 128, 0, st>>>(sc, d_sch, plan, n_mol, d_read_off, (uint2 *)d_ins, d_epoch_nlive, d_counts);
+        exclusive_scan_u32(d_counts, d_offsets, n_mol, d_scan_tmp, st);
+    } else {
+        k_dump_write<<<g, 128, 0, st>>>(sc, d_sch, plan, n_mol, d_read_off, (uint2 *)d_ins, d_epoch_nlive, d_offsets, d_out);
+    }
+}
+
+__global__ void k_mask_flags(const char *raw, int64_t len, uint32_t *flags) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < len) flags[i] = raw[i] == 'N';
+}
+__global__ void k_mask_write(const char *raw, int64_t len, uint64_t seed, uint32_t contig, uint32_t hap, const uint64_t *off,
+                             mmk_variate *out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len || raw[i] != 'N') return;
+    mmk_stream s;
+    mmk_stream_init(&s, seed, 0, MMK_P_MASK, contig, hap);
+    mmk_variate v;
+    v.tag = MMK_P_MASK;
+    v.aux = 4;
+    v.v.i = (int64_t)mmk_bits_to_index(mmk_stream_at(&s, (uint32_t)i), 4);
+    out[off[i]] = v;
+}
+void dump_mask(const char *d_raw_upper, int64_t len, uint64_t seed, uint32_t contig, uint32_t hap, uint32_t *d_flags,
+               uint64_t *d_off, uint64_t *d_scan_tmp, mmk_variate *d_out, int pass, cudaStream_t st) {
+    if (len <= 0) return;
+    unsigned g = (unsigned)((len + 255) / 256);
+    if (pass == 0) {
+        k_mask_flags<<<g, 256, 0, st>>>(d_raw_upper, len, d_flags);
+        exclusive_scan_u32(d_flags, d_off, (uint64_t)len, d_scan_tmp, st);
+    } else {
+        k_mask_write<<<g, 256, 0, st>>>(d_raw_upper, len, seed, contig, hap, d_off, d_out);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// known-answer hooks
+// ------------------------------------------------------------------------------------------
+__global__ void k_kat_philox(const uint32_t *in6, uint32_t *out4) { mmk_philox4x32_10(in6, in6 + 4, out4); }
+void kat_philox(const uint32_t *d_in6, uint32_t *d_out4, cudaStream_t st) { k_kat_philox<<<1, 1, 0, st>>>(d_in6, d_out4); }
+
+__global__ void k_kat_math(int kind, const double *in, double *out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x = in[i];
+    if (kind == 0) out[i] = mmk_log(x);
+    else if (kind == 1) out[i] = mmk_exp(x);
+    else if (kind == 2) out[i] = mmk_bits_to_exp(mmk_d2u(x));
+    else {
+        mmk_stream s;
+        mmk_stream_init(&s, mmk_d2u(x), 0, MMK_P_INSERT, (uint64_t)i, 0);
+        out[i] = mmk_next_normal(&s);
+    }
+}
+void kat_math(int kind, const double *d_in, double *d_out, int64_t n, cudaStream_t st) {
+    if (n > 0) k_kat_math<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(kind, d_in, d_out, n);
+}
+
+}  // namespace mmkdev

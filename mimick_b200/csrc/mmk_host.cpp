@@ -1,0 +1,1392 @@
+// mmk_host.cpp — the context behind the C ABI (include/mimick_b200.h): parameter freezing,
+// schema bookkeeping, the epoch loop of the planner, sharding, chunked emission.
+//
+// Reference anchors (mimick/MimickLinkedReads.jl/src): Main.jl:24-62, :88-131 (drivers),
+// Structs.jl:54-70 (SimParams), ProcessFASTA.jl:45-95 (schemas), ProcessVariants.jl:157-185
+// (sample haplotypes).  All sampling, extraction and formatting happens in mmk_device.cu; this
+// file only sequences kernels and moves small control values.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <random>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "mmk_host.h"
+#include "mmk_internal.h"
+
+using namespace mmkdev;
+
+// ------------------------------------------------------------------------------------------
+// device buffer helper
+// ------------------------------------------------------------------------------------------
+template <class T>
+struct DBuf {
+    T *p = nullptr;
+    size_t cap = 0;  // elements
+    ~DBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    // grow to at least n elements; keeps the first `keep` elements
+    cudaError_t ensure(size_t n, size_t keep = 0, cudaStream_t st = 0) {
+        if (n <= cap) return cudaSuccess;
+        size_t nc = std::max(n, cap + cap / 2);
+        T *q = nullptr;
+        cudaError_t e = cudaMalloc((void **)&q, nc * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (p && keep) {
+            e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        }
+        if (p) cudaFree(p);
+        p = q;
+        cap = nc;
+        return e;
+    }
+};
+
+struct Contig {
+    std::string name;
+    int32_t haplotype = 1;
+    int64_t len = 0;
+    char *d_ascii = nullptr;  // upper-case, masked; kept while variants may still be applied
+    int64_t reads_required = 0;
+    uint64_t n_N = 0, n_nonACGT = 0;
+    std::vector<mmk_variate> mask_variates;
+};
+struct Schema {
+    int32_t contig = 0;
+    int32_t haplotype = 1;
+    int64_t len = 0;
+    int64_t required = 0, current = 0;
+    uint64_t word_off = 0;
+    std::string name;
+};
+
+struct mmk_ctx {
+    mmk_params par;
+    SimConst sc;
+    uint64_t seed = 0;
+    cudaStream_t st = nullptr, st_copy = nullptr;
+    std::string err;
+
+    std::vector<Contig> contigs;
+    std::vector<Schema> schemas;
+    bool schemas_ready = false;  // arena packed + SchemaDev uploaded
+    bool multi_mode = false;
+    int bpb = 2;
+    DBuf<uint32_t> d_hap;
+    DBuf<SchemaDev> d_sch;
+    ContigStats *d_stats = nullptr;
+    ContigStats *h_stats = nullptr;  // pinned
+
+    // plan
+    bool planned = false;
+    DBuf<uint64_t> p_group;
+    DBuf<uint32_t> p_slot;
+    DBuf<uint16_t> p_schema;
+    DBuf<uint16_t> p_epoch;
+    DBuf<uint32_t> p_size;
+    DBuf<uint32_t> p_nfrags;
+    DBuf<uint8_t> p_status;
+    DBuf<uint64_t> d_read_off;  // [n_mol + 1]
+    uint64_t n_mol = 0, n_pairs = 0, n_groups = 0;
+    std::vector<uint32_t> epoch_nlive;
+    mmk_plan_info plan_info{};
+
+    // shard + placement
+    int32_t rank = 0, world = 1;
+    bool placed = false;
+    uint64_t mol0 = 0, s_nmol = 0, pair0 = 0, s_npairs = 0;
+    DBuf<uint2> d_ins;
+    DBuf<MolRec> d_mol;
+    DBuf<uint8_t> d_text;
+    DBuf<uint64_t> d_roff_l;
+    DBuf<uint64_t> d_tile_off1, d_tile_off2;
+    uint32_t text_stride = 0, tile_pairs = 64, n_tiles = 0;
+    mmk_place_info place_info{};
+
+    // emission
+    uint8_t *out[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [slot][read]
+    uint64_t out_cap = 0;
+    uint32_t tile_cursor = 0;
+    int slot = 0;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_emit[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+    uint32_t *d_u32x2 = nullptr;
+    uint32_t *h_u32x2 = nullptr;  // pinned
+};
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static int32_t fail(mmk_ctx *c, int32_t code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t e_ = (call);                                                                        \
+        if (e_ != cudaSuccess)                                                                          \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? MMK_ERR_NOMEM : MMK_ERR_CUDA, "%s: %s", #call, \
+                        cudaGetErrorString(e_));                                                        \
+    } while (0)
+
+extern "C" const char *mmk_strerror(int32_t s) {
+    switch (s) {
+    case MMK_OK: return "ok";
+    case MMK_ERR_INVALID_ARG: return "invalid argument";
+    case MMK_ERR_BAD_FORMAT: return "barcode format not recognized";
+    case MMK_ERR_INSERTS_UNFITTABLE: return "failed to find practical read sizes less than molecule";
+    case MMK_ERR_BARCODES_EXHAUSTED: return "no more barcodes available for the selected barcode type";
+    case MMK_ERR_CONTIG_TOO_AMBIGUOUS: return "contig lacks 95% of the read length sum as unambiguous bases";
+    case MMK_ERR_BCF_UNSUPPORTED: return "BCF file type is not yet supported";
+    case MMK_ERR_TRUNCATION_BOUNDS: return "molecule shorter than two inserts (truncation lower > upper)";
+    case MMK_ERR_BAD_BASE: return "symbol outside the DNA alphabet";
+    case MMK_ERR_IO: return "file does not exist or cannot be read";
+    case MMK_ERR_VCF: return "malformed or inconsistent VCF";
+    case MMK_ERR_BOUNDS: return "read window out of bounds";
+    case MMK_ERR_UNSUPPORTED: return "parameter region not supported";
+    case MMK_ERR_CUDA: return "CUDA error";
+    case MMK_ERR_NOMEM: return "out of memory";
+    case MMK_ERR_REPLAY: return "replay stream mismatch";
+    case MMK_ERR_STATE: return "call out of order";
+    default: return "unknown status";
+    }
+}
+extern "C" const char *mmk_last_error(const mmk_ctx *c) { return c ? c->err.c_str() : "null context"; }
+extern "C" int32_t mmk_abi_version(void) { return MMK_ABI_VERSION; }
+
+// ------------------------------------------------------------------------------------------
+// parameters
+// ------------------------------------------------------------------------------------------
+extern "C" void mmk_params_default(mmk_params *p) {
+    memset(p, 0, sizeof *p);
+    p->struct_size = sizeof *p;
+    p->device = 0;
+    p->fq_format = MMK_FMT_STANDARD;
+    p->bc_format = MMK_FMT_HAPLOTAGGING;
+    p->coverage = 30.0;
+    p->n_molecules = 2;
+    p->attempts = 25;
+    p->mol_coverage = 0.2;
+    p->mol_length = 80000;
+    p->insert_length = 500;
+    p->insert_stdev = 50;
+    p->length_r1 = 150;
+    p->length_r2 = 150;
+    p->singletons = 0.70;
+    p->circular = 0;
+    p->mask = 0;
+    p->seed = -1;
+    p->strict_wrap = 0;
+    p->force_generic = 0;
+    p->max_chunk_bytes = 0;
+    p->plan_batch_groups = 0;
+}
+
+extern "C" int32_t mmk_interpret_format(const char *fmt_c, int32_t *bc, int32_t *fq) {
+    if (!fmt_c || !bc || !fq) return MMK_ERR_INVALID_ARG;
+    std::string fmt(fmt_c);
+    if (fmt == "10x") fmt = "tenx";  // CLI normalisation, mimick/__main__.py:73
+    auto has = [&](const char *s) { return fmt.find(s) != std::string::npos; };
+    if (has("standard")) {
+        *fq = MMK_FMT_STANDARD;
+        if (has("stlfr")) *bc = MMK_FMT_STLFR;
+        else if (has("haplotagging")) *bc = MMK_FMT_HAPLOTAGGING;
+        else *bc = MMK_FMT_TELLSEQ;
+        return MMK_OK;
+    }
+    int v = fmt == "stlfr" ? MMK_FMT_STLFR : fmt == "haplotagging" ? MMK_FMT_HAPLOTAGGING : fmt == "tellseq" ? MMK_FMT_TELLSEQ
+            : fmt == "tenx" ? MMK_FMT_TENX : -1;
+    if (v < 0) return MMK_ERR_BAD_FORMAT;
+    *bc = *fq = v;
+    return MMK_OK;
+}
+
+extern "C" int32_t mmk_check_variant_path(const char *path) {
+    if (!path) return MMK_ERR_INVALID_ARG;
+    std::string s(path);
+    std::transform(s.begin(), s.end(), s.begin(), [](unsigned char c) { return (char)tolower(c); });
+    if (s.size() >= 3 && s.compare(s.size() - 3, 3, "bcf") == 0) return MMK_ERR_BCF_UNSUPPORTED;
+    return MMK_OK;
+}
+
+// truncated(Exponential(theta), lower[, upper]) — host twin of trunc_exp_make in mmk_sampling.cuh
+static bool host_trunc_exp(TruncExp &d, double theta, double lower, bool has_upper, double upper) {
+    memset(&d, 0, sizeof d);
+    d.theta = theta;
+    d.lower = lower;
+    d.upper = upper;
+    d.has_upper = has_upper;
+    if (has_upper && !(lower <= upper)) return false;
+    double zl = MMK_DIV(lower > 0.0 ? lower : 0.0, theta);
+    d.loglcdf = mmk_log1mexp(-zl);
+    d.lcdf = mmk_exp(d.loglcdf);
+    if (has_upper) {
+        double zu = MMK_DIV(upper > 0.0 ? upper : 0.0, theta);
+        d.logtp = mmk_logsubexp(d.loglcdf, mmk_log1mexp(-zu));
+    } else
+        d.logtp = mmk_log1mexp(d.loglcdf);
+    d.tp = mmk_exp(d.logtp);
+    return true;
+}
+
+static uint64_t barcode_capacity(int bc) {
+    switch (bc) {
+    case MMK_FMT_HAPLOTAGGING: return 96ull * 96 * 96 * 96;
+    case MMK_FMT_STLFR: return 8000000000ull;
+    case MMK_FMT_TELLSEQ: return 1ull << 36;
+    case MMK_FMT_TENX: return 1ull << 32;
+    default: return 0;
+    }
+}
+
+extern "C" int32_t mmk_create(const mmk_params *p, mmk_ctx **out) {
+    if (!p || !out) return MMK_ERR_INVALID_ARG;
+    *out = nullptr;
+    mmk_ctx *ctx = new mmk_ctx();
+    *out = ctx;  // returned even on failure so the caller can read the message, then mmk_destroy
+    mmk_params_default(&ctx->par);
+    memcpy(&ctx->par, p, std::min<size_t>(p->struct_size ? p->struct_size : sizeof *p, sizeof *p));
+    const mmk_params &q = ctx->par;
+    if (q.fq_format < 0 || q.fq_format > MMK_FMT_STANDARD || q.bc_format < 0 || q.bc_format > MMK_FMT_TENX)
+        return fail(ctx, MMK_ERR_BAD_FORMAT, "format enum out of range");
+    if (q.fq_format != MMK_FMT_STANDARD && q.fq_format != q.bc_format)
+        return fail(ctx, MMK_ERR_BAD_FORMAT, "barcode style must equal the output style unless the output style is standard");
+    if (q.n_molecules == 0) return fail(ctx, MMK_ERR_INVALID_ARG, "n_molecules = 0 never terminates in the reference");
+    if (q.length_r1 < 1 || q.length_r2 < 1 || q.insert_length < 1 || q.insert_stdev < 0 || q.mol_length < 1 ||
+        !(q.mol_coverage > 0) || q.attempts < 0 || !(q.coverage >= 0) || q.singletons < 0)
+        return fail(ctx, MMK_ERR_INVALID_ARG, "parameter out of range");
+    if (q.length_r1 > 100000 || q.length_r2 > 100000) return fail(ctx, MMK_ERR_UNSUPPORTED, "read length > 100000");
+
+    SimConst &sc = ctx->sc;
+    memset(&sc, 0, sizeof sc);
+    if (q.seed >= 0) ctx->seed = (uint64_t)q.seed;
+    else {
+        std::random_device rd;
+        ctx->seed = (((uint64_t)rd() << 32) | rd()) >> 1;
+    }
+    sc.seed = ctx->seed;
+    sc.sample = 0;
+    // SimParams, Structs.jl:57-69
+    double lowerbound;
+    if (q.mol_coverage < 1.0) {
+        double t = MMK_MUL(MMK_MUL((double)q.mol_length, q.mol_coverage), 0.25);
+        int64_t ti = (int64_t)t;
+        lowerbound = (double)(ti > 3000 ? ti : 3000);
+    } else
+        lowerbound = MMK_MUL(q.mol_coverage, MMK_ADD((double)q.insert_length, MMK_MUL(0.75, (double)q.insert_stdev)));
+    host_trunc_exp(sc.mollen, (double)q.mol_length, lowerbound, false, 0.0);
+    if (q.n_molecules > 0) {
+        sc.nmol_fixed = 0;
+        if (!host_trunc_exp(sc.nmol, (double)q.n_molecules, 1.0, true, MMK_MUL(2.5, (double)q.n_molecules)))
+            return fail(ctx, MMK_ERR_TRUNCATION_BOUNDS, "n_molecules truncation bounds");
+    } else
+        sc.nmol_fixed = -q.n_molecules;
+    sc.ins_mu = (double)q.insert_length;
+    sc.ins_sd = (double)q.insert_stdev;
+    sc.ins_lb = MMK_DIV(MMK_SUB(200.0, sc.ins_mu), sc.ins_sd);
+    {
+        double lcdf = 0.5 * erfc(-sc.ins_lb / sqrt(2.0));
+        if (sc.ins_lb != sc.ins_lb) lcdf = 200.0 > sc.ins_mu ? 1.0 : 0.0;
+        if (!(1.0 - lcdf > 0.3))
+            return fail(ctx, MMK_ERR_UNSUPPORTED,
+                        "insert-size truncation keeps <= 30%% of the normal law (insert_length far below 200): not implemented");
+    }
+    sc.singletons = q.singletons;
+    sc.mol_coverage = q.mol_coverage;
+    sc.insert_length = q.insert_length;
+    sc.attempts = q.attempts;
+    sc.r1 = q.length_r1;
+    sc.r2 = q.length_r2;
+    sc.circular = q.circular ? 1 : 0;
+    sc.strict = q.strict_wrap ? 1 : 0;
+    sc.fq_format = q.fq_format;
+    sc.bc_format = q.bc_format;
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(ctx, MMK_ERR_CUDA, "no CUDA device: %s (this library has no CPU path)", cudaGetErrorString(e));
+    if (q.device < 0 || q.device >= ndev) return fail(ctx, MMK_ERR_INVALID_ARG, "device %d out of range", q.device);
+    CU(cudaSetDevice(q.device));
+    CU(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&ctx->ev_a));
+    CU(cudaEventCreate(&ctx->ev_b));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaEventCreateWithFlags(&ctx->ev_emit[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
+    }
+    CU(cudaMalloc((void **)&ctx->d_stats, sizeof(ContigStats)));
+    CU(cudaMallocHost((void **)&ctx->h_stats, sizeof(ContigStats)));
+    CU(cudaMalloc((void **)&ctx->d_u32x2, 16));
+    CU(cudaMallocHost((void **)&ctx->h_u32x2, 16));
+    return MMK_OK;
+}
+
+static void free_outputs(mmk_ctx *c) {
+    for (int s = 0; s < 2; ++s)
+        for (int r = 0; r < 2; ++r)
+            if (c->out[s][r]) {
+                cudaFree(c->out[s][r]);
+                c->out[s][r] = nullptr;
+            }
+    c->out_cap = 0;
+}
+
+extern "C" void mmk_destroy(mmk_ctx *c) {
+    if (!c) return;
+    if (c->st) {
+        cudaSetDevice(c->par.device);
+        cudaStreamSynchronize(c->st);
+    }
+    for (auto &k : c->contigs)
+        if (k.d_ascii) cudaFree(k.d_ascii);
+    free_outputs(c);
+    if (c->d_stats) cudaFree(c->d_stats);
+    if (c->h_stats) cudaFreeHost(c->h_stats);
+    if (c->d_u32x2) cudaFree(c->d_u32x2);
+    if (c->h_u32x2) cudaFreeHost(c->h_u32x2);
+    if (c->ev_a) cudaEventDestroy(c->ev_a);
+    if (c->ev_b) cudaEventDestroy(c->ev_b);
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_emit[i]) cudaEventDestroy(c->ev_emit[i]);
+        if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
+    }
+    if (c->st_copy) cudaStreamDestroy(c->st_copy);
+    if (c->st) cudaStreamDestroy(c->st);
+    delete c;
+}
+extern "C" uint64_t mmk_seed(const mmk_ctx *c) { return c ? c->seed : 0; }
+extern "C" void *mmk_cuda_stream(const mmk_ctx *c) { return c ? (void *)c->st : nullptr; }
+
+// ------------------------------------------------------------------------------------------
+// inputs
+// ------------------------------------------------------------------------------------------
+static void invalidate_plan(mmk_ctx *c) {
+    c->planned = false;
+    c->placed = false;
+    c->schemas_ready = false;
+    c->tile_cursor = 0;
+}
+
+extern "C" int32_t mmk_add_contig(mmk_ctx *ctx, const char *name, const char *bases, int64_t len, int32_t haplotype) {
+    if (!ctx || !name || (!bases && len > 0) || len < 0) return fail(ctx, MMK_ERR_INVALID_ARG, "mmk_add_contig: bad argument");
+    if (!ctx->st) return fail(ctx, MMK_ERR_STATE, "context was not created successfully");
+    if (ctx->multi_mode) return fail(ctx, MMK_ERR_STATE, "contigs cannot be added after variants were applied");
+    if (len >= (1ll << 31)) return fail(ctx, MMK_ERR_UNSUPPORTED, "contig %s has >= 2^31 bases", name);
+    if (strlen(name) > 55) return fail(ctx, MMK_ERR_UNSUPPORTED, "contig name longer than 55 characters: %s", name);
+    if (haplotype < 0 || haplotype > 65535) return fail(ctx, MMK_ERR_INVALID_ARG, "haplotype index out of range");
+    if (ctx->contigs.size() >= 65535) return fail(ctx, MMK_ERR_UNSUPPORTED, "more than 65535 (contig, haplotype) units");
+    CU(cudaSetDevice(ctx->par.device));
+    Contig k;
+    k.name = name;
+    k.haplotype = haplotype;
+    k.len = len;
+    CU(cudaMalloc((void **)&k.d_ascii, (size_t)len + 64));
+    ctx->contigs.push_back(k);
+    Contig &c = ctx->contigs.back();
+    const mmk_params &q = ctx->par;
+    auto drop = [&]() {
+        cudaFree(c.d_ascii);
+        ctx->contigs.pop_back();
+    };
+    cudaError_t e = cudaMemcpyAsync(c.d_ascii, bases, (size_t)len, cudaMemcpyHostToDevice, ctx->st);
+    ContigStats zero{~0ull, 0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_stats, &zero, sizeof zero, cudaMemcpyHostToDevice, ctx->st);
+    if (e == cudaSuccess) {
+        normalize_ascii(c.d_ascii, len, ctx->d_stats, ctx->st);
+        e = cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, sizeof zero, cudaMemcpyDeviceToHost, ctx->st);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->st);
+    if (e != cudaSuccess) {
+        drop();
+        return fail(ctx, MMK_ERR_CUDA, "upload of contig failed: %s", cudaGetErrorString(e));
+    }
+    if (ctx->h_stats->first_bad != ~0ull) {
+        unsigned long long b = ctx->h_stats->first_bad;
+        drop();
+        return fail(ctx, MMK_ERR_BAD_BASE, "contig %s: symbol at position %llu is not in the DNA alphabet", name, b + 1);
+    }
+    c.n_N = ctx->h_stats->n_N;
+    c.n_nonACGT = ctx->h_stats->n_nonACGT;
+    if (q.mask && c.n_N > 0) {  // mask_N!, ProcessFASTA.jl:29-36,53-55
+        uint32_t ci = 0;        // contig index within its FASTA file (= haplotype)
+        for (size_t i = 0; i + 1 < ctx->contigs.size(); ++i) ci += ctx->contigs[i].haplotype == haplotype;
+        {  // keep the picks for mmk_dump_mask_variates (they are few: one per N)
+            DBuf<uint32_t> flags;
+            DBuf<uint64_t> off, tmp;
+            DBuf<mmk_variate> outv;
+            CU(flags.ensure((size_t)len));
+            CU(off.ensure((size_t)len + 1));
+            CU(tmp.ensure((size_t)len / 1024 + 8));
+            CU(outv.ensure((size_t)c.n_N));
+            dump_mask(c.d_ascii, len, ctx->seed, ci, (uint32_t)haplotype, flags.p, off.p, tmp.p, outv.p, 0, ctx->st);
+            dump_mask(c.d_ascii, len, ctx->seed, ci, (uint32_t)haplotype, flags.p, off.p, tmp.p, outv.p, 1, ctx->st);
+            c.mask_variates.resize((size_t)c.n_N);
+            CU(cudaMemcpyAsync(c.mask_variates.data(), outv.p, (size_t)c.n_N * sizeof(mmk_variate), cudaMemcpyDeviceToHost, ctx->st));
+            CU(cudaStreamSynchronize(ctx->st));
+        }
+        mask_n(c.d_ascii, len, ctx->seed, ci, (uint32_t)haplotype, ctx->st);
+        zero = ContigStats{~0ull, 0, 0};
+        CU(cudaMemcpyAsync(ctx->d_stats, &zero, sizeof zero, cudaMemcpyHostToDevice, ctx->st));
+        count_bases(c.d_ascii, len, ctx->d_stats, ctx->st);
+        CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, sizeof zero, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        c.n_N = ctx->h_stats->n_N;
+        c.n_nonACGT = ctx->h_stats->n_nonACGT;
+    }
+    // process_fasta, ProcessFASTA.jl:47-61
+    int64_t mean_readlen = (int64_t)(q.length_r1 + q.length_r2) / 2;
+    int64_t cutoff = (int64_t)nearbyint((double)(q.length_r1 + q.length_r2) * 0.95);
+    int64_t normalized = len - (int64_t)c.n_N;
+    if (normalized < cutoff) {
+        drop();
+        return fail(ctx, MMK_ERR_CONTIG_TOO_AMBIGUOUS,
+                    "Contigs must have at least 95%% of the requested read length sum as unambiguous (non-N) bases: %s has %lld, needs %lld",
+                    name, (long long)normalized, (long long)cutoff);
+    }
+    if (mean_readlen < 1) {
+        drop();
+        return fail(ctx, MMK_ERR_INVALID_ARG, "mean read length is zero");
+    }
+    double x = MMK_DIV(MMK_DIV(MMK_MUL(q.coverage, (double)normalized), (double)mean_readlen), 2.0);
+    c.reads_required = (int64_t)x;
+    invalidate_plan(ctx);
+    return MMK_OK;
+}
+
+extern "C" int32_t mmk_load_fasta(mmk_ctx *ctx, const char *path, int32_t haplotype) {
+    if (!ctx || !path) return fail(ctx, MMK_ERR_INVALID_ARG, "mmk_load_fasta: bad argument");
+    std::vector<mmkio::FastaRecord> recs;
+    std::string err;
+    int rc = mmkio::read_fasta(path, recs, err);
+    if (rc) return fail(ctx, rc, "%s", err.c_str());
+    for (auto &r : recs) {
+        rc = mmk_add_contig(ctx, r.name.c_str(), r.seq.data(), (int64_t)r.seq.size(), haplotype);
+        if (rc) return rc;
+    }
+    return MMK_OK;
+}
+extern "C" int32_t mmk_n_contigs(const mmk_ctx *c) { return c ? (int32_t)c->contigs.size() : 0; }
+
+// upload SchemaDev table
+static int32_t upload_schemas(mmk_ctx *ctx) {
+    std::vector<SchemaDev> h(ctx->schemas.size());
+    for (size_t i = 0; i < h.size(); ++i) {
+        const Schema &s = ctx->schemas[i];
+        memset(&h[i], 0, sizeof(SchemaDev));
+        h[i].word_off = s.word_off;
+        h[i].len = (uint32_t)s.len;
+        h[i].haplotype = (uint16_t)s.haplotype;
+        h[i].name_len = (uint16_t)s.name.size();
+        memcpy(h[i].name, s.name.data(), s.name.size());
+    }
+    CU(ctx->d_sch.ensure(h.size() ? h.size() : 1));
+    if (!h.empty()) CU(cudaMemcpyAsync(ctx->d_sch.p, h.data(), h.size() * sizeof(SchemaDev), cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return MMK_OK;
+}
+
+static inline uint64_t words_for(int64_t len, int bpb) {
+    uint64_t per = 32 / bpb;
+    uint64_t w = ((uint64_t)len + per - 1) / per + 8;  // 8 pad words: window loads may over-read
+    return (w + 3) & ~3ull;                            // 16-byte aligned starts
+}
+
+// single-sample mode: schemas are the contigs, in the order they were added (setup_schema)
+static int32_t finalize_single(mmk_ctx *ctx) {
+    if (ctx->schemas_ready) return MMK_OK;
+    if (ctx->contigs.empty()) return fail(ctx, MMK_ERR_STATE, "no contigs loaded");
+    ctx->bpb = 2;
+    for (auto &c : ctx->contigs)
+        if (c.n_nonACGT) ctx->bpb = 4;
+    ctx->schemas.clear();
+    uint64_t off = 0;
+    for (size_t i = 0; i < ctx->contigs.size(); ++i) {
+        Contig &c = ctx->contigs[i];
+        if (!c.d_ascii) return fail(ctx, MMK_ERR_STATE, "contig symbols were already released");
+        Schema s;
+        s.contig = (int32_t)i;
+        s.haplotype = c.haplotype;
+        s.len = c.len;
+        s.required = c.reads_required;
+        s.word_off = off;
+        s.name = c.name;
+        off += words_for(c.len, ctx->bpb);
+        ctx->schemas.push_back(s);
+    }
+    CU(ctx->d_hap.ensure(off ? off : 4));
+    CU(cudaMemsetAsync(ctx->d_hap.p, 0, off * 4, ctx->st));
+    ContigStats zero{~0ull, 0, 0};
+    CU(cudaMemcpyAsync(ctx->d_stats, &zero, sizeof zero, cudaMemcpyHostToDevice, ctx->st));
+    DBuf<int64_t> piece;  // dst = 0, src = 0
+    DBuf<uint8_t> kind;
+    CU(piece.ensure(2));
+    CU(kind.ensure(1));
+    CU(cudaMemsetAsync(piece.p, 0, 16, ctx->st));
+    CU(cudaMemsetAsync(kind.p, 0, 1, ctx->st));
+    for (size_t i = 0; i < ctx->contigs.size(); ++i) {
+        Contig &c = ctx->contigs[i];
+        pack_pieces(c.d_ascii, c.d_ascii, piece.p, piece.p + 1, kind.p, 1, c.len, ctx->d_hap.p + ctx->schemas[i].word_off,
+                    ctx->bpb, ctx->d_stats, ctx->st);
+    }
+    CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, sizeof zero, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    if (ctx->h_stats->first_bad != ~0ull) return fail(ctx, MMK_ERR_BAD_BASE, "unencodable symbol while packing");
+    int32_t rc = upload_schemas(ctx);
+    if (rc) return rc;
+    ctx->schemas_ready = true;
+    return MMK_OK;
+}
+
+static bool valid_iupac(char &c) {
+    if (c >= 'a' && c <= 'z') c = (char)(c - 32);
+    return c == '-' || (c != 0 && strchr("ACMGRSVTWYHKDBN", c) != nullptr);
+}
+
+struct Piece {
+    uint8_t kind;  // 0 master (SNP-painted copy), 1 alt bytes
+    int64_t src, len;
+};
+
+extern "C" int32_t mmk_set_sample_variants(mmk_ctx *ctx, uint32_t sample_stream, int32_t ploidy, const int32_t *vcf_contigs,
+                                           int32_t n_vcf_contigs, int64_t n_mut, const int32_t *contig, const int64_t *pos,
+                                           const uint8_t *type, const int32_t *ref_len, const int64_t *alt_off,
+                                           const int32_t *alt_len, const uint8_t *hap, const char *alt_bytes,
+                                           int64_t alt_bytes_len) {
+    if (!ctx || ploidy < 1 || ploidy > 255 || n_vcf_contigs < 0 || n_mut < 0 || (n_vcf_contigs && !vcf_contigs))
+        return fail(ctx, MMK_ERR_INVALID_ARG, "mmk_set_sample_variants: bad argument");
+    if (ctx->contigs.empty()) return fail(ctx, MMK_ERR_STATE, "no master contigs loaded");
+    if ((int64_t)n_vcf_contigs * ploidy > 65535) return fail(ctx, MMK_ERR_UNSUPPORTED, "more than 65535 (contig, haplotype) units");
+    CU(cudaSetDevice(ctx->par.device));
+    for (auto &c : ctx->contigs)
+        if (!c.d_ascii) return fail(ctx, MMK_ERR_STATE, "master symbols were released by a single-sample run");
+    ctx->multi_mode = true;
+    invalidate_plan(ctx);
+    ctx->sc.sample = sample_stream & 0xffffu;
+
+    // group mutations per (vcf contig slot, haplotype), file order kept
+    const int nC = (int)ctx->contigs.size();
+    std::vector<int> slot_of(nC, -1);
+    for (int i = 0; i < n_vcf_contigs; ++i) {
+        if (vcf_contigs[i] < 0 || vcf_contigs[i] >= nC) return fail(ctx, MMK_ERR_VCF, "VCF contig index out of range");
+        slot_of[vcf_contigs[i]] = i;
+    }
+    std::vector<std::vector<int64_t>> by((size_t)n_vcf_contigs * ploidy);
+    std::string alts(alt_bytes ? alt_bytes : "", (size_t)alt_bytes_len);
+    bool alt_ambiguous = false;
+    for (int64_t i = 0; i < n_mut; ++i) {
+        if (contig[i] < 0 || contig[i] >= nC || slot_of[contig[i]] < 0)
+            return fail(ctx, MMK_ERR_VCF, "record %lld names a contig absent from the VCF header", (long long)i);
+        if (hap[i] < 1 || hap[i] > ploidy) return fail(ctx, MMK_ERR_VCF, "record %lld: haplotype slot %d exceeds ploidy %d", (long long)i, hap[i], ploidy);
+        if (alt_off[i] < 0 || alt_len[i] < 0 || alt_off[i] + alt_len[i] > alt_bytes_len) return fail(ctx, MMK_ERR_INVALID_ARG, "alt slice out of range");
+        for (int32_t k = 0; k < alt_len[i]; ++k) {
+            char &ch = alts[(size_t)alt_off[i] + k];
+            if (!valid_iupac(ch)) return fail(ctx, MMK_ERR_BAD_BASE, "ALT allele of record %lld has a symbol outside the DNA alphabet", (long long)i);
+            if (!(ch == 'A' || ch == 'C' || ch == 'G' || ch == 'T')) alt_ambiguous = true;
+        }
+        if (type[i] == 0 && alt_len[i] < 1) return fail(ctx, MMK_ERR_VCF, "empty SNP allele");
+        by[(size_t)slot_of[contig[i]] * ploidy + (hap[i] - 1)].push_back(i);
+    }
+    ctx->bpb = alt_ambiguous ? 4 : 2;
+    for (auto &c : ctx->contigs)
+        if (c.n_nonACGT) ctx->bpb = 4;
+
+    // per schema: SNP table (last write wins per position) and the piece list after all splices
+    struct Build {
+        std::vector<int64_t> snp_pos;
+        std::string snp_alt;
+        std::vector<Piece> pieces;
+        int64_t out_len;
+    };
+    std::vector<Build> builds(by.size());
+    ctx->schemas.clear();
+    uint64_t woff = 0;
+    for (int ci = 0; ci < n_vcf_contigs; ++ci) {
+        const Contig &mc = ctx->contigs[vcf_contigs[ci]];
+        for (int h = 0; h < ploidy; ++h) {
+            Build &b = builds[(size_t)ci * ploidy + h];
+            std::map<int64_t, char> snps;
+            std::vector<int64_t> indels;
+            for (int64_t i : by[(size_t)ci * ploidy + h]) {
+                if (type[i] == 0) {
+                    if (pos[i] < 1 || pos[i] > mc.len) return fail(ctx, MMK_ERR_BOUNDS, "SNP position %lld outside contig %s", (long long)pos[i], mc.name.c_str());
+                    snps[pos[i]] = alts[(size_t)alt_off[i]];
+                } else
+                    indels.push_back(i);
+            }
+            for (auto &kv : snps) {
+                b.snp_pos.push_back(kv.first);
+                b.snp_alt.push_back(kv.second);
+            }
+            // spliceinto!(seq, pos:pos+len(ref)-1, alt) in REVERSE file order on the current sequence
+            std::vector<Piece> &pc = b.pieces;
+            pc.push_back(Piece{0, 0, mc.len});
+            int64_t cur_len = mc.len;
+            for (size_t r = indels.size(); r-- > 0;) {
+                int64_t i = indels[r];
+                int64_t a = pos[i] - 1, e = a + ref_len[i];  // [a, e) 0-based in current coordinates
+                if (a < 0 || e > cur_len || ref_len[i] < 0) return fail(ctx, MMK_ERR_BOUNDS, "indel at %lld outside contig %s", (long long)pos[i], mc.name.c_str());
+                std::vector<Piece> np;
+                np.reserve(pc.size() + 2);
+                int64_t o = 0;
+                bool inserted = false;
+                for (const Piece &p : pc) {
+                    int64_t lo = o, hi = o + p.len;
+                    o = hi;
+                    if (hi <= a) {  // entirely before
+                        np.push_back(p);
+                        continue;
+                    }
+                    if (lo < a) np.push_back(Piece{p.kind, p.src, a - lo});  // head survives
+                    if (!inserted) {
+                        if (alt_len[i] > 0) np.push_back(Piece{1, alt_off[i], alt_len[i]});
+                        inserted = true;
+                    }
+                    if (hi > e) {  // tail survives
+                        int64_t cut = std::max(e, lo) - lo;
+                        np.push_back(Piece{p.kind, p.src + cut, p.len - cut});
+                    }
+                }
+                if (!inserted && alt_len[i] > 0) np.push_back(Piece{1, alt_off[i], alt_len[i]});  // a == cur_len
+                pc.swap(np);
+                cur_len += alt_len[i] - ref_len[i];
+            }
+            b.out_len = cur_len;
+            if (cur_len >= (1ll << 31)) return fail(ctx, MMK_ERR_UNSUPPORTED, "haplotype has >= 2^31 bases");
+            Schema s;
+            s.contig = vcf_contigs[ci];
+            s.haplotype = h + 1;  // parse(Int, split(key, "_")[end])
+            s.len = cur_len;
+            s.required = mc.reads_required;  // inherited from the master (ProcessVariants.jl:181)
+            s.word_off = woff;
+            s.name = mc.name;
+            woff += words_for(cur_len, ctx->bpb);
+            ctx->schemas.push_back(s);
+        }
+    }
+    CU(ctx->d_hap.ensure(woff ? woff : 4));
+    CU(cudaMemsetAsync(ctx->d_hap.p, 0, woff * 4, ctx->st));
+    DBuf<char> d_alt, d_tmp, d_snp_alt;
+    DBuf<int64_t> d_snp_pos, d_dst, d_src;
+    DBuf<uint8_t> d_kind;
+    CU(d_alt.ensure(alts.size() + 16));
+    if (!alts.empty()) CU(cudaMemcpyAsync(d_alt.p, alts.data(), alts.size(), cudaMemcpyHostToDevice, ctx->st));
+    ContigStats zero{~0ull, 0, 0};
+    CU(cudaMemcpyAsync(ctx->d_stats, &zero, sizeof zero, cudaMemcpyHostToDevice, ctx->st));
+    std::vector<int64_t> h_dst, h_src;
+    std::vector<uint8_t> h_kind;
+    for (size_t si = 0; si < builds.size(); ++si) {
+        Build &b = builds[si];
+        const Schema &s = ctx->schemas[si];
+        const Contig &mc = ctx->contigs[s.contig];
+        const char *src_ascii = mc.d_ascii;
+        if (!b.snp_pos.empty()) {  // paint SNPs on a private copy of the master
+            CU(d_tmp.ensure((size_t)mc.len + 16));
+            CU(cudaMemcpyAsync(d_tmp.p, mc.d_ascii, (size_t)mc.len, cudaMemcpyDeviceToDevice, ctx->st));
+            CU(d_snp_pos.ensure(b.snp_pos.size()));
+            CU(d_snp_alt.ensure(b.snp_alt.size()));
+            CU(cudaMemcpyAsync(d_snp_pos.p, b.snp_pos.data(), b.snp_pos.size() * 8, cudaMemcpyHostToDevice, ctx->st));
+            CU(cudaMemcpyAsync(d_snp_alt.p, b.snp_alt.data(), b.snp_alt.size(), cudaMemcpyHostToDevice, ctx->st));
+            scatter_snps(d_tmp.p, d_snp_pos.p, d_snp_alt.p, (int64_t)b.snp_pos.size(), ctx->st);
+            src_ascii = d_tmp.p;
+        }
+        h_dst.clear();
+        h_src.clear();
+        h_kind.clear();
+        int64_t o = 0;
+        for (const Piece &p : b.pieces) {
+            if (p.len <= 0) continue;
+            h_dst.push_back(o);
+            h_src.push_back(p.src);
+            h_kind.push_back(p.kind);
+            o += p.len;
+        }
+        if (h_dst.empty()) continue;  // empty haplotype
+        CU(d_dst.ensure(h_dst.size()));
+        CU(d_src.ensure(h_src.size()));
+        CU(d_kind.ensure(h_kind.size()));
+        CU(cudaMemcpyAsync(d_dst.p, h_dst.data(), h_dst.size() * 8, cudaMemcpyHostToDevice, ctx->st));
+        CU(cudaMemcpyAsync(d_src.p, h_src.data(), h_src.size() * 8, cudaMemcpyHostToDevice, ctx->st));
+        CU(cudaMemcpyAsync(d_kind.p, h_kind.data(), h_kind.size(), cudaMemcpyHostToDevice, ctx->st));
+        pack_pieces(src_ascii, d_alt.p, d_dst.p, d_src.p, d_kind.p, (int32_t)h_dst.size(), b.out_len, ctx->d_hap.p + s.word_off,
+                    ctx->bpb, ctx->d_stats, ctx->st);
+        CU(cudaStreamSynchronize(ctx->st));  // host staging vectors are reused next iteration
+    }
+    CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, sizeof zero, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    if (ctx->h_stats->first_bad != ~0ull) return fail(ctx, MMK_ERR_BAD_BASE, "unencodable symbol while packing a haplotype");
+    int32_t rc = upload_schemas(ctx);
+    if (rc) return rc;
+    ctx->schemas_ready = true;
+    return MMK_OK;
+}
+
+// ---- VCF handle ---------------------------------------------------------------------------
+extern "C" int32_t mmk_vcf_open(const char *path, mmk_vcf **out, char *errbuf, size_t errbuf_len) {
+    if (!path || !out) return MMK_ERR_INVALID_ARG;
+    *out = nullptr;
+    int32_t rc = mmk_check_variant_path(path);
+    std::string err;
+    if (rc) err = "BCF file type is not yet supported";
+    mmk_vcf *v = nullptr;
+    if (!rc) {
+        v = new mmk_vcf();
+        rc = mmkio::read_vcf(path, v->d, err);
+    }
+    if (rc) {
+        if (errbuf && errbuf_len) snprintf(errbuf, errbuf_len, "%s", err.c_str());
+        delete v;
+        return rc;
+    }
+    *out = v;
+    return MMK_OK;
+}
+extern "C" void mmk_vcf_close(mmk_vcf *v) { delete v; }
+extern "C" int32_t mmk_vcf_n_samples(const mmk_vcf *v) { return v ? (int32_t)v->d.samples.size() : 0; }
+extern "C" const char *mmk_vcf_sample_name(const mmk_vcf *v, int32_t i) {
+    return (v && i >= 0 && i < (int32_t)v->d.samples.size()) ? v->d.samples[i].c_str() : nullptr;
+}
+extern "C" int32_t mmk_vcf_ploidy(const mmk_vcf *v) { return v ? v->d.ploidy : 0; }
+extern "C" int32_t mmk_vcf_n_contigs(const mmk_vcf *v) { return v ? (int32_t)v->d.contigs.size() : 0; }
+extern "C" const char *mmk_vcf_contig_name(const mmk_vcf *v, int32_t i) {
+    return (v && i >= 0 && i < (int32_t)v->d.contigs.size()) ? v->d.contigs[i].c_str() : nullptr;
+}
+extern "C" int64_t mmk_vcf_n_records(const mmk_vcf *v) { return v ? (int64_t)v->d.records.size() : 0; }
+
+extern "C" int32_t mmk_apply_vcf_sample(mmk_ctx *ctx, const mmk_vcf *v, int32_t sample) {
+    if (!ctx || !v) return fail(ctx, MMK_ERR_INVALID_ARG, "mmk_apply_vcf_sample: bad argument");
+    const mmkio::VcfData &d = v->d;
+    if (sample < 0 || sample >= (int32_t)d.samples.size()) return fail(ctx, MMK_ERR_INVALID_ARG, "sample index out of range");
+    if (d.ploidy < 1) return fail(ctx, MMK_ERR_VCF, "VCF has no records to take the ploidy from");
+    std::unordered_map<std::string, int> master;
+    for (size_t i = 0; i < ctx->contigs.size(); ++i)
+        if (!master.count(ctx->contigs[i].name)) master[ctx->contigs[i].name] = (int)i;
+    std::vector<int32_t> vc;
+    std::unordered_map<std::string, int> in_header;
+    for (auto &n : d.contigs) {
+        auto it = master.find(n);
+        if (it == master.end()) return fail(ctx, MMK_ERR_VCF, "VCF header contig %s is not in the FASTA", n.c_str());
+        in_header[n] = it->second;
+        vc.push_back(it->second);
+    }
+    std::vector<int32_t> contig, ref_len, alt_len;
+    std::vector<int64_t> pos, alt_off;
+    std::vector<uint8_t> type, hap;
+    std::string alt_bytes;
+    for (auto &r : d.records) {
+        size_t off = 0;
+        for (int s = 0; s < sample; ++s) off += r.ploidy_of[s];
+        int np = r.ploidy_of[sample];
+        for (int a = 0; a < np; ++a) {
+            uint8_t al = r.alleles[off + a];
+            if (!al) continue;
+            auto it = in_header.find(r.chrom);
+            if (it == in_header.end()) return fail(ctx, MMK_ERR_VCF, "record contig %s has no ##contig header line", r.chrom.c_str());
+            if (a + 1 > d.ploidy) return fail(ctx, MMK_ERR_VCF, "genotype at %s:%lld has more alleles than the ploidy", r.chrom.c_str(), (long long)r.pos);
+            const std::string &alt = r.alts[al - 1];
+            contig.push_back(it->second);
+            pos.push_back(r.pos);
+            type.push_back((uint8_t)r.type);
+            ref_len.push_back((int32_t)r.ref.size());
+            alt_off.push_back((int64_t)alt_bytes.size());
+            alt_len.push_back((int32_t)alt.size());
+            hap.push_back((uint8_t)(a + 1));
+            alt_bytes += alt;
+        }
+    }
+    return mmk_set_sample_variants(ctx, (uint32_t)sample, d.ploidy, vc.data(), (int32_t)vc.size(), (int64_t)pos.size(),
+                                   contig.data(), pos.data(), type.data(), ref_len.data(), alt_off.data(), alt_len.data(),
+                                   hap.data(), alt_bytes.data(), (int64_t)alt_bytes.size());
+}
+
+// ---- schema queries ---------------------------------------------------------------------------
+extern "C" int32_t mmk_n_schemas(const mmk_ctx *c) {
+    if (!c) return 0;
+    if (!c->multi_mode && !c->schemas_ready) return (int32_t)c->contigs.size();
+    return (int32_t)c->schemas.size();
+}
+extern "C" int32_t mmk_schema_get(const mmk_ctx *c, int32_t i, mmk_schema_info *out) {
+    if (!c || !out) return MMK_ERR_INVALID_ARG;
+    memset(out, 0, sizeof *out);
+    if (!c->multi_mode && !c->schemas_ready) {
+        if (i < 0 || i >= (int32_t)c->contigs.size()) return MMK_ERR_INVALID_ARG;
+        const Contig &k = c->contigs[i];
+        out->length = k.len;
+        out->reads_required = k.reads_required;
+        out->haplotype = k.haplotype;
+        out->contig = i;
+        snprintf(out->name, sizeof out->name, "%s", k.name.c_str());
+        return MMK_OK;
+    }
+    if (i < 0 || i >= (int32_t)c->schemas.size()) return MMK_ERR_INVALID_ARG;
+    const Schema &s = c->schemas[i];
+    out->length = s.len;
+    out->reads_required = s.required;
+    out->reads_current = s.current;
+    out->haplotype = s.haplotype;
+    out->contig = s.contig;
+    snprintf(out->name, sizeof out->name, "%s", s.name.c_str());
+    return MMK_OK;
+}
+extern "C" int32_t mmk_schema_bases(mmk_ctx *ctx, int32_t i, char *out, int64_t cap) {
+    if (!ctx || !out) return fail(ctx, MMK_ERR_INVALID_ARG, "mmk_schema_bases: bad argument");
+    CU(cudaSetDevice(ctx->par.device));
+    if (!ctx->multi_mode) {
+        int32_t rc = finalize_single(ctx);
+        if (rc) return rc;
+    }
+    if (!ctx->schemas_ready) return fail(ctx, MMK_ERR_STATE, "schemas not built");
+    if (i < 0 || i >= (int32_t)ctx->schemas.size()) return fail(ctx, MMK_ERR_INVALID_ARG, "schema index out of range");
+    const Schema &s = ctx->schemas[i];
+    if (cap < s.len) return fail(ctx, MMK_ERR_INVALID_ARG, "buffer too small");
+    DBuf<char> tmp;
+    CU(tmp.ensure((size_t)s.len + 1));
+    unpack(ctx->d_hap.p + s.word_off, s.len, ctx->bpb, tmp.p, ctx->st);
+    CU(cudaMemcpyAsync(out, tmp.p, (size_t)s.len, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return MMK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// planning: the barcode-group loop of Main.jl:44-59 in speculative batches
+// ------------------------------------------------------------------------------------------
+static PlanDev plan_dev(mmk_ctx *c) {
+    PlanDev p;
+    p.group = c->p_group.p;
+    p.slot = c->p_slot.p;
+    p.schema = c->p_schema.p;
+    p.epoch = c->p_epoch.p;
+    p.size = c->p_size.p;
+    p.nfrags = c->p_nfrags.p;
+    p.status = c->p_status.p;
+    return p;
+}
+static int32_t plan_reserve(mmk_ctx *ctx, uint64_t n, uint64_t keep) {
+    CU(ctx->p_group.ensure(n, keep, ctx->st));
+    CU(ctx->p_slot.ensure(n, keep, ctx->st));
+    CU(ctx->p_schema.ensure(n, keep, ctx->st));
+    CU(ctx->p_epoch.ensure(n, keep, ctx->st));
+    CU(ctx->p_size.ensure(n, keep, ctx->st));
+    CU(ctx->p_nfrags.ensure(n, keep, ctx->st));
+    CU(ctx->p_status.ensure(n, keep, ctx->st));
+    return MMK_OK;
+}
+
+extern "C" int32_t mmk_plan(mmk_ctx *ctx, mmk_plan_info *out) {
+    if (!ctx) return MMK_ERR_INVALID_ARG;
+    if (!ctx->st) return fail(ctx, MMK_ERR_STATE, "context was not created successfully");
+    CU(cudaSetDevice(ctx->par.device));
+    if (!ctx->multi_mode) {
+        int32_t rc = finalize_single(ctx);
+        if (rc) return rc;
+    }
+    if (!ctx->schemas_ready) return fail(ctx, MMK_ERR_STATE, "schemas not built");
+    const uint32_t K = (uint32_t)ctx->schemas.size();
+    for (auto &s : ctx->schemas) s.current = 0;
+    ctx->placed = false;
+    ctx->tile_cursor = 0;
+    ctx->epoch_nlive.clear();
+
+    const uint32_t max_nmol = ctx->sc.nmol_fixed > 0 ? (uint32_t)ctx->sc.nmol_fixed
+                                                     : (uint32_t)nearbyint(2.5 * (double)ctx->par.n_molecules) + 1;
+    const uint64_t Bmax = ctx->par.plan_batch_groups > 0 ? (uint64_t)ctx->par.plan_batch_groups : (1ull << 20);
+    const uint64_t Bmin = std::min<uint64_t>(Bmax, 8192);
+
+    std::vector<uint16_t> live(K);
+    for (uint32_t i = 0; i < K; ++i) live[i] = (uint16_t)i;
+    DBuf<uint16_t> d_live, d_lpos;
+    DBuf<int64_t> d_need;
+    DBuf<uint32_t> d_nmol;
+    DBuf<uint64_t> d_off, d_tmp;
+    DBuf<unsigned long long> d_hist, d_cross;
+    DBuf<uint8_t> d_res;
+    CU(d_live.ensure(K ? K : 1));
+    CU(d_lpos.ensure(65536));
+    CU(d_need.ensure(K ? K : 1));
+    CU(d_cross.ensure(K ? K : 1));
+    size_t res_bytes = sizeof(BatchResult) + (size_t)K * 8;
+    CU(d_res.ensure(res_bytes));
+    std::vector<uint8_t> h_res(res_bytes);
+    std::vector<int64_t> need(K);
+
+    uint64_t g0 = 0, n_mol = 0;
+    uint64_t B = Bmin;
+    int64_t n_batches = 0, n_epochs = 0;
+    bool live_dirty = true;
+    double inserts_per_group_schema = 0.0;  // running estimate, per live schema
+    while (!live.empty()) {
+        const uint32_t n_live = (uint32_t)live.size();
+        if (live_dirty) {
+            CU(cudaMemcpyAsync(d_live.p, live.data(), n_live * 2, cudaMemcpyHostToDevice, ctx->st));
+            ctx->epoch_nlive.push_back(n_live);
+            if (ctx->epoch_nlive.size() > 65535) return fail(ctx, MMK_ERR_UNSUPPORTED, "more than 65535 pruning epochs");
+            live_dirty = false;
+        }
+        int64_t min_need = INT64_MAX;
+        for (uint32_t i = 0; i < n_live; ++i) {
+            need[i] = ctx->schemas[live[i]].required - ctx->schemas[live[i]].current;
+            min_need = std::min(min_need, need[i]);
+        }
+        // size the batch to reach the next pruning point with a small overshoot
+        if (inserts_per_group_schema > 0.0 && min_need > 0) {
+            double est = (double)min_need / inserts_per_group_schema;
+            B = (uint64_t)std::min<double>((double)Bmax, std::max<double>((double)Bmin, est * 1.03 + 2048.0));
+        } else if (min_need <= 0)
+            B = Bmin;
+        const uint32_t nb = (uint32_t)B;
+        const uint64_t max_mol = (uint64_t)nb * max_nmol;
+        int32_t rc = plan_reserve(ctx, n_mol + max_mol, n_mol);
+        if (rc) return rc;
+        CU(d_nmol.ensure(nb));
+        CU(d_off.ensure((size_t)nb + 1));
+        CU(d_tmp.ensure((size_t)nb / 1024 + 8));
+        CU(d_hist.ensure((size_t)plan_hist_chunks(max_mol) * n_live));
+        CU(cudaMemcpyAsync(d_need.p, need.data(), n_live * 8, cudaMemcpyHostToDevice, ctx->st));
+        plan_batch(ctx->sc, ctx->d_sch.p, d_live.p, n_live, (uint16_t)(ctx->epoch_nlive.size() - 1), g0, nb, d_nmol.p, d_off.p,
+                   d_tmp.p, plan_dev(ctx), n_mol, max_mol, d_need.p, d_hist.p, d_cross.p, d_lpos.p, (BatchResult *)d_res.p,
+                   ctx->st);
+        size_t rb = sizeof(BatchResult) + (size_t)(n_live ? n_live - 1 : 0) * 8;
+        CU(cudaMemcpyAsync(h_res.data(), d_res.p, rb, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        CU(cudaGetLastError());
+        ++n_batches;
+        const BatchResult *r = (const BatchResult *)h_res.data();
+        if (r->first_error != ~0ull) {
+            ctx->n_mol = 0;
+            return fail(ctx, (int32_t)r->error_code, "molecule %llu: %s", (unsigned long long)(n_mol + r->first_error),
+                        mmk_strerror((int32_t)r->error_code));
+        }
+        uint64_t batch_inserts = 0;
+        for (uint32_t i = 0; i < n_live; ++i) {
+            ctx->schemas[live[i]].current += (int64_t)r->sums[i];
+            batch_inserts += r->sums[i];
+        }
+        n_mol += r->n_commit;
+        uint64_t groups_done = (r->cut_group == ~0ull) ? nb : (r->cut_group - g0 + 1);
+        if (groups_done > 0 && batch_inserts > 0)
+            inserts_per_group_schema = (double)batch_inserts / (double)groups_done / (double)n_live;
+        g0 += groups_done;
+        if (r->cut_group != ~0ull) {  // filter!(is_incomplete, schema), Main.jl:58
+            std::vector<uint16_t> nl;
+            for (uint16_t s : live)
+                if (ctx->schemas[s].current < ctx->schemas[s].required) nl.push_back(s);
+            if (nl.size() == live.size()) return fail(ctx, MMK_ERR_CUDA, "planner cut without a completed schema (internal error)");
+            live.swap(nl);
+            live_dirty = true;
+            ++n_epochs;
+        }
+        if (n_mol > barcode_capacity(ctx->par.bc_format))
+            return fail(ctx, MMK_ERR_BARCODES_EXHAUSTED, "There are no more barcodes available for the selected barcode type.");
+    }
+    ctx->n_mol = n_mol;
+    ctx->n_groups = g0;
+    // first pair of every molecule
+    CU(ctx->d_read_off.ensure(n_mol + 1));
+    CU(d_tmp.ensure((size_t)n_mol / 1024 + 8));
+    exclusive_scan_u32(ctx->p_nfrags.p, ctx->d_read_off.p, n_mol, d_tmp.p, ctx->st);
+    uint64_t total = 0;
+    CU(cudaMemcpyAsync(&total, ctx->d_read_off.p + n_mol, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->n_pairs = total;
+    ctx->planned = true;
+    ctx->plan_info.n_groups = (int64_t)g0;
+    ctx->plan_info.n_molecules = (int64_t)n_mol;
+    ctx->plan_info.n_pairs = (int64_t)total;
+    ctx->plan_info.n_epochs = n_epochs;
+    ctx->plan_info.n_batches = n_batches;
+    if (out) *out = ctx->plan_info;
+    return MMK_OK;
+}
+
+extern "C" int32_t mmk_set_shard(mmk_ctx *ctx, int32_t rank, int32_t world) {
+    if (!ctx || world < 1 || world > 1023 || rank < 0 || rank >= world) return fail(ctx, MMK_ERR_INVALID_ARG, "bad shard");
+    ctx->rank = rank;
+    ctx->world = world;
+    ctx->placed = false;
+    ctx->tile_cursor = 0;
+    return MMK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// placement + tile offsets for this shard
+// ------------------------------------------------------------------------------------------
+static EmitArgs base_args(mmk_ctx *c) {
+    EmitArgs a;
+    memset(&a, 0, sizeof a);
+    a.hap = c->d_hap.p;
+    a.sch = c->d_sch.p;
+    a.read_off = c->d_roff_l.p;
+    a.mol = c->d_mol.p;
+    a.text = c->d_text.p;
+    a.ins = c->d_ins.p;
+    a.tile_off1 = c->d_tile_off1.p;
+    a.tile_off2 = c->d_tile_off2.p;
+    a.n_pairs = c->s_npairs;
+    a.n_mol = (uint32_t)c->s_nmol;
+    a.tile_pairs = c->tile_pairs;
+    a.text_stride = c->text_stride;
+    a.r1 = c->par.length_r1;
+    a.r2 = c->par.length_r2;
+    a.fq_format = c->par.fq_format;
+    a.bclen_inline = c->par.fq_format == MMK_FMT_TENX ? 16 : 0;
+    a.strict = c->par.strict_wrap ? 1 : 0;
+    a.bpb = c->bpb;
+    a.force_generic = c->par.force_generic;
+    return a;
+}
+
+extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
+    if (!ctx) return MMK_ERR_INVALID_ARG;
+    if (!ctx->planned) return fail(ctx, MMK_ERR_STATE, "mmk_plan has not run");
+    CU(cudaSetDevice(ctx->par.device));
+    // shard bounds
+    DBuf<uint64_t> d_bounds;
+    CU(d_bounds.ensure((size_t)ctx->world + 1));
+    shard_bounds(ctx->d_read_off.p, ctx->n_mol, ctx->n_pairs, ctx->world, d_bounds.p, ctx->st);
+    std::vector<uint64_t> bounds((size_t)ctx->world + 1);
+    CU(cudaMemcpyAsync(bounds.data(), d_bounds.p, bounds.size() * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->mol0 = bounds[ctx->rank];
+    ctx->s_nmol = bounds[ctx->rank + 1] - bounds[ctx->rank];
+    if (ctx->s_nmol >= (1ull << 32) - 2) return fail(ctx, MMK_ERR_UNSUPPORTED, "more than 2^32 molecules in one shard");
+    uint64_t ro[2] = {0, 0};
+    CU(cudaMemcpyAsync(&ro[0], ctx->d_read_off.p + ctx->mol0, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(&ro[1], ctx->d_read_off.p + ctx->mol0 + ctx->s_nmol, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    ctx->pair0 = ro[0];
+    ctx->s_npairs = ro[1] - ro[0];
+
+    // header text stride
+    size_t max_name = 0;
+    int max_hap = 1;
+    for (auto &s : ctx->schemas) {
+        max_name = std::max(max_name, s.name.size());
+        max_hap = std::max(max_hap, s.haplotype);
+    }
+    size_t hap_digits = std::to_string(max_hap).size();
+    size_t max_prefix = 1 + max_name + 1 + hap_digits + 1 + 10 + 1 + 10 + 1;
+    if (max_prefix > 200) return fail(ctx, MMK_ERR_UNSUPPORTED, "header prefix longer than 200 bytes");
+    ctx->text_stride = (uint32_t)((max_prefix + 36 + 15) & ~15ull);
+    ctx->tile_pairs = 64;
+
+    CU(ctx->d_ins.ensure(ctx->s_npairs + 1));
+    CU(ctx->d_mol.ensure(ctx->s_nmol + 1));
+    CU(ctx->d_text.ensure((size_t)(ctx->s_nmol + 1) * ctx->text_stride));
+    CU(ctx->d_roff_l.ensure(ctx->s_nmol + 2));
+    DBuf<unsigned long long> d_err;
+    CU(d_err.ensure(3));
+    unsigned long long init[3] = {~0ull, 0, 0};
+    CU(cudaMemcpyAsync(d_err.p, init, sizeof init, cudaMemcpyHostToDevice, ctx->st));
+    place(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->mol0, (uint32_t)ctx->s_nmol, ctx->d_read_off.p, ctx->d_ins.p, ctx->d_mol.p,
+          ctx->d_text.p, ctx->text_stride, ctx->d_roff_l.p, d_err.p, ctx->st);
+    unsigned long long herr[3];
+    CU(cudaMemcpyAsync(herr, d_err.p, sizeof herr, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaGetLastError());
+    if (herr[0] != ~0ull) {
+        uint8_t code = 0;
+        CU(cudaMemcpy(&code, ctx->p_status.p + herr[0], 1, cudaMemcpyDeviceToHost));
+        return fail(ctx, code, "molecule %llu: %s", herr[0], mmk_strerror(code));
+    }
+    // tile offsets
+    ctx->n_tiles = (uint32_t)((ctx->s_npairs + ctx->tile_pairs - 1) / ctx->tile_pairs);
+    DBuf<uint32_t> d_sum1, d_sum2;
+    DBuf<uint64_t> d_tmp;
+    CU(d_sum1.ensure((size_t)ctx->n_tiles + 1));
+    CU(d_sum2.ensure((size_t)ctx->n_tiles + 1));
+    CU(d_tmp.ensure((size_t)ctx->n_tiles / 1024 + 8));
+    CU(ctx->d_tile_off1.ensure((size_t)ctx->n_tiles + 1));
+    CU(ctx->d_tile_off2.ensure((size_t)ctx->n_tiles + 1));
+    CU(cudaMemsetAsync(d_err.p, 0, 8, ctx->st));
+    EmitArgs a = base_args(ctx);
+    tile_sums(a, ctx->n_tiles, d_sum1.p, d_sum2.p, d_err.p, ctx->st);
+    exclusive_scan_u32(d_sum1.p, ctx->d_tile_off1.p, ctx->n_tiles, d_tmp.p, ctx->st);
+    exclusive_scan_u32(d_sum2.p, ctx->d_tile_off2.p, ctx->n_tiles, d_tmp.p, ctx->st);
+    uint64_t tot[3] = {0, 0, 0};
+    CU(cudaMemcpyAsync(&tot[0], ctx->d_tile_off1.p + ctx->n_tiles, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(&tot[1], ctx->d_tile_off2.p + ctx->n_tiles, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(&tot[2], d_err.p, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaGetLastError());
+    ctx->place_info.first_molecule = (int64_t)ctx->mol0;
+    ctx->place_info.n_molecules = (int64_t)ctx->s_nmol;
+    ctx->place_info.first_pair = (int64_t)ctx->pair0;
+    ctx->place_info.n_pairs = (int64_t)ctx->s_npairs;
+    ctx->place_info.r1_bytes = tot[0];
+    ctx->place_info.r2_bytes = tot[1];
+    ctx->place_info.gather_bytes = tot[2];
+    ctx->placed = true;
+    ctx->tile_cursor = 0;
+    ctx->slot = 0;
+    if (out) *out = ctx->place_info;
+    return MMK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// emission
+// ------------------------------------------------------------------------------------------
+static int32_t ensure_outputs(mmk_ctx *ctx) {
+    uint64_t want = ctx->par.max_chunk_bytes ? ctx->par.max_chunk_bytes : (8ull << 30);
+    uint64_t need = std::max(ctx->place_info.r1_bytes, ctx->place_info.r2_bytes);
+    want = std::min(want, need);
+    want = std::max<uint64_t>(want, 1 << 20);
+    want = (want + 255) & ~255ull;
+    if (ctx->out_cap >= want) return MMK_OK;
+    free_outputs(ctx);
+    int slots = need <= want ? 1 : 2;  // a single chunk needs no ring
+    for (int s = 0; s < slots; ++s)
+        for (int r = 0; r < 2; ++r) CU(cudaMalloc((void **)&ctx->out[s][r], want + 256));
+    ctx->out_cap = want;
+    return MMK_OK;
+}
+
+static int32_t emit_next(mmk_ctx *ctx, mmk_chunk *out, bool sync) {
+    if (!ctx->placed) return fail(ctx, MMK_ERR_STATE, "mmk_place has not run");
+    memset(out, 0, sizeof *out);
+    int32_t rc = ensure_outputs(ctx);
+    if (rc) return rc;
+    if (ctx->tile_cursor >= ctx->n_tiles) {
+        out->done = 1;
+        return MMK_OK;
+    }
+    const uint32_t t0 = ctx->tile_cursor;
+    find_tile(ctx->d_tile_off1.p, ctx->d_tile_off2.p, t0, ctx->n_tiles, ctx->out_cap, ctx->d_u32x2, ctx->st);
+    uint64_t offs[4];
+    CU(cudaMemcpyAsync(ctx->h_u32x2, ctx->d_u32x2, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    uint32_t t1 = std::min(ctx->h_u32x2[0], ctx->h_u32x2[1]);
+    if (t1 <= t0) return fail(ctx, MMK_ERR_INVALID_ARG, "max_chunk_bytes is smaller than one tile of records");
+    CU(cudaMemcpyAsync(&offs[0], ctx->d_tile_off1.p + t0, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(&offs[1], ctx->d_tile_off1.p + t1, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(&offs[2], ctx->d_tile_off2.p + t0, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(&offs[3], ctx->d_tile_off2.p + t1, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    int slot = ctx->out[1][0] ? ctx->slot : 0;
+    EmitArgs a = base_args(ctx);
+    a.out1 = ctx->out[slot][0];
+    a.out2 = ctx->out[slot][1];
+    a.chunk_off1 = offs[0];
+    a.chunk_off2 = offs[2];
+    a.tile0 = t0;
+    a.n_tiles = t1 - t0;
+    CU(cudaStreamWaitEvent(ctx->st, ctx->ev_copy[slot], 0));  // the slot's previous copy-out must be done
+    CU(cudaEventRecord(ctx->ev_a, ctx->st));
+    emit(a, ctx->st);
+    CU(cudaEventRecord(ctx->ev_b, ctx->st));
+    CU(cudaEventRecord(ctx->ev_emit[slot], ctx->st));
+    out->r1_dev = a.out1;
+    out->r2_dev = a.out2;
+    out->r1_bytes = offs[1] - offs[0];
+    out->r2_bytes = offs[3] - offs[2];
+    out->r1_offset = offs[0];
+    out->r2_offset = offs[2];
+    out->first_pair = (int64_t)t0 * ctx->tile_pairs;
+    uint64_t last = std::min<uint64_t>((uint64_t)t1 * ctx->tile_pairs, ctx->s_npairs);
+    out->n_pairs = (int64_t)(last - (uint64_t)out->first_pair);
+    out->slot = slot;
+    ctx->tile_cursor = t1;
+    out->done = t1 >= ctx->n_tiles;
+    ctx->slot ^= 1;
+    if (sync) {
+        CU(cudaStreamSynchronize(ctx->st));
+        CU(cudaGetLastError());
+        CU(cudaEventElapsedTime(&out->kernel_ms, ctx->ev_a, ctx->ev_b));
+    }
+    return MMK_OK;
+}
+
+extern "C" int32_t mmk_emit_chunk(mmk_ctx *ctx, mmk_chunk *out) {
+    if (!ctx || !out) return MMK_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->par.device));
+    return emit_next(ctx, out, true);
+}
+extern "C" int32_t mmk_rewind(mmk_ctx *ctx) {
+    if (!ctx) return MMK_ERR_INVALID_ARG;
+    ctx->tile_cursor = 0;
+    ctx->slot = 0;
+    return MMK_OK;
+}
+extern "C" int32_t mmk_copy_chunk(mmk_ctx *ctx, const mmk_chunk *ch, void *r1_host, void *r2_host) {
+    if (!ctx || !ch) return MMK_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->par.device));
+    if (r1_host && ch->r1_bytes) CU(cudaMemcpyAsync(r1_host, ch->r1_dev, ch->r1_bytes, cudaMemcpyDeviceToHost, ctx->st));
+    if (r2_host && ch->r2_bytes) CU(cudaMemcpyAsync(r2_host, ch->r2_dev, ch->r2_bytes, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    return MMK_OK;
+}
+extern "C" int32_t mmk_emit_to_host(mmk_ctx *ctx, void *r1_host, uint64_t r1_cap, void *r2_host, uint64_t r2_cap) {
+    if (!ctx || !r1_host || !r2_host) return MMK_ERR_INVALID_ARG;
+    if (!ctx->placed) return fail(ctx, MMK_ERR_STATE, "mmk_place has not run");
+    if (r1_cap < ctx->place_info.r1_bytes || r2_cap < ctx->place_info.r2_bytes) return fail(ctx, MMK_ERR_INVALID_ARG, "host buffers too small");
+    CU(cudaSetDevice(ctx->par.device));
+    mmk_rewind(ctx);
+    for (;;) {
+        mmk_chunk ch;
+        int32_t rc = emit_next(ctx, &ch, false);
+        if (rc) return rc;
+        if (ch.n_pairs == 0 && ch.done) break;
+        // copy stream waits for this chunk's kernel; the next emit into this slot waits for the copy
+        CU(cudaStreamWaitEvent(ctx->st_copy, ctx->ev_emit[ch.slot], 0));
+        CU(cudaMemcpyAsync((char *)r1_host + ch.r1_offset, ch.r1_dev, ch.r1_bytes, cudaMemcpyDeviceToHost, ctx->st_copy));
+        CU(cudaMemcpyAsync((char *)r2_host + ch.r2_offset, ch.r2_dev, ch.r2_bytes, cudaMemcpyDeviceToHost, ctx->st_copy));
+        CU(cudaEventRecord(ctx->ev_copy[ch.slot], ctx->st_copy));
+        if (ch.done) break;
+    }
+    CU(cudaStreamSynchronize(ctx->st_copy));
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaGetLastError());
+    return MMK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// introspection
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t mmk_dump_molecules(mmk_ctx *ctx, int64_t first, int64_t n, mmk_mol_record *out) {
+    if (!ctx || !out || first < 0 || n < 0) return MMK_ERR_INVALID_ARG;
+    if (!ctx->planned) return fail(ctx, MMK_ERR_STATE, "mmk_plan has not run");
+    if ((uint64_t)(first + n) > ctx->n_mol) return fail(ctx, MMK_ERR_INVALID_ARG, "molecule range out of bounds");
+    CU(cudaSetDevice(ctx->par.device));
+    std::vector<uint64_t> g(n), ro(n);
+    std::vector<uint32_t> sl(n), sz(n), nf(n);
+    std::vector<uint16_t> sc(n);
+    if (n) {
+        CU(cudaMemcpy(g.data(), ctx->p_group.p + first, n * 8, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(ro.data(), ctx->d_read_off.p + first, n * 8, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(sl.data(), ctx->p_slot.p + first, n * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(sz.data(), ctx->p_size.p + first, n * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(nf.data(), ctx->p_nfrags.p + first, n * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(sc.data(), ctx->p_schema.p + first, n * 2, cudaMemcpyDeviceToHost));
+    }
+    std::vector<MolRec> mr;
+    int64_t lo = 0, hi = 0;  // overlap with the placed shard
+    if (ctx->placed) {
+        lo = std::max<int64_t>(first, (int64_t)ctx->mol0);
+        hi = std::min<int64_t>(first + n, (int64_t)(ctx->mol0 + ctx->s_nmol));
+        if (hi > lo) {
+            mr.resize(hi - lo);
+            CU(cudaMemcpy(mr.data(), ctx->d_mol.p + (lo - (int64_t)ctx->mol0), (hi - lo) * sizeof(MolRec), cudaMemcpyDeviceToHost));
+        }
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        mmk_mol_record &o = out[i];
+        o.group = (int64_t)g[i];
+        o.slot = (int32_t)sl[i];
+        o.schema = sc[i];
+        o.molsize = sz[i];
+        o.n_frags = nf[i];
+        o.first_read = (int64_t)ro[i];
+        o.barcode_index = first + i;
+        int64_t gi = first + i;
+        o.start = (gi >= lo && gi < hi) ? mr[gi - lo].start : 0;
+    }
+    return MMK_OK;
+}
+
+extern "C" int32_t mmk_dump_inserts(mmk_ctx *ctx, int64_t first, int64_t n, int64_t *start, int64_t *stop) {
+    if (!ctx || !start || !stop || first < 0 || n < 0) return MMK_ERR_INVALID_ARG;
+    if (!ctx->placed) return fail(ctx, MMK_ERR_STATE, "mmk_place has not run");
+    if ((uint64_t)(first + n) > ctx->s_npairs) return fail(ctx, MMK_ERR_INVALID_ARG, "pair range out of bounds");
+    CU(cudaSetDevice(ctx->par.device));
+    std::vector<uint2> in(n);
+    std::vector<uint64_t> ro(ctx->s_nmol + 1);
+    std::vector<MolRec> mr(ctx->s_nmol);
+    if (n) CU(cudaMemcpy(in.data(), ctx->d_ins.p + first, n * sizeof(uint2), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(ro.data(), ctx->d_roff_l.p, ro.size() * 8, cudaMemcpyDeviceToHost));
+    if (ctx->s_nmol) CU(cudaMemcpy(mr.data(), ctx->d_mol.p, mr.size() * sizeof(MolRec), cudaMemcpyDeviceToHost));
+    size_t m = std::upper_bound(ro.begin(), ro.end(), (uint64_t)first) - ro.begin();
+    m = m ? m - 1 : 0;
+    for (int64_t i = 0; i < n; ++i) {
+        uint64_t p = (uint64_t)(first + i);
+        while (m + 1 < ro.size() && ro[m + 1] <= p) ++m;
+        start[i] = mr[m].start + in[i].x;
+        stop[i] = start[i] + in[i].y - 1;
+    }
+    return MMK_OK;
+}
+
+extern "C" int32_t mmk_dump_variates(mmk_ctx *ctx, mmk_variate *out, uint64_t cap, uint64_t *n_out) {
+    if (!ctx || !n_out) return MMK_ERR_INVALID_ARG;
+    if (!ctx->placed || ctx->world != 1) return fail(ctx, MMK_ERR_STATE, "mmk_dump_variates needs mmk_place on an unsharded context");
+    CU(cudaSetDevice(ctx->par.device));
+    DBuf<uint32_t> d_counts, d_nlive;
+    DBuf<uint64_t> d_offsets, d_tmp;
+    CU(d_counts.ensure(ctx->n_mol + 1));
+    CU(d_offsets.ensure(ctx->n_mol + 2));
+    CU(d_tmp.ensure(ctx->n_mol / 1024 + 8));
+    CU(d_nlive.ensure(ctx->epoch_nlive.size() + 1));
+    CU(cudaMemcpyAsync(d_nlive.p, ctx->epoch_nlive.data(), ctx->epoch_nlive.size() * 4, cudaMemcpyHostToDevice, ctx->st));
+    dump_variates(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->n_mol, ctx->d_read_off.p, ctx->d_ins.p, d_nlive.p, nullptr, 0,
+                  d_counts.p, d_offsets.p, d_tmp.p, nullptr, 0, ctx->st);
+    uint64_t total = 0;
+    CU(cudaMemcpyAsync(&total, d_offsets.p + ctx->n_mol, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaGetLastError());
+    *n_out = total;
+    if (!out) return MMK_OK;
+    if (cap < total) return fail(ctx, MMK_ERR_INVALID_ARG, "variate buffer too small");
+    DBuf<mmk_variate> d_out;
+    CU(d_out.ensure(total + 1));
+    dump_variates(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->n_mol, ctx->d_read_off.p, ctx->d_ins.p, d_nlive.p, nullptr, 0,
+                  d_counts.p, d_offsets.p, d_tmp.p, d_out.p, 1, ctx->st);
+    CU(cudaMemcpyAsync(out, d_out.p, total * sizeof(mmk_variate), cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaGetLastError());
+    return MMK_OK;
+}
+
+extern "C" int32_t mmk_dump_mask_variates(mmk_ctx *ctx, mmk_variate *out, uint64_t cap, uint64_t *n_out) {
+    if (!ctx || !n_out) return MMK_ERR_INVALID_ARG;
+    uint64_t total = 0;
+    for (auto &c : ctx->contigs) total += c.mask_variates.size();
+    *n_out = total;
+    if (!out) return MMK_OK;
+    if (cap < total) return fail(ctx, MMK_ERR_INVALID_ARG, "variate buffer too small");
+    uint64_t o = 0;
+    for (auto &c : ctx->contigs) {
+        if (!c.mask_variates.empty()) memcpy(out + o, c.mask_variates.data(), c.mask_variates.size() * sizeof(mmk_variate));
+        o += c.mask_variates.size();
+    }
+    return MMK_OK;
+}
+
+extern "C" int32_t mmk_kat_philox(mmk_ctx *ctx, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    if (!ctx || !ctr || !key || !out) return MMK_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->par.device));
+    DBuf<uint32_t> d;
+    CU(d.ensure(10));
+    uint32_t in[6] = {ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]};
+    CU(cudaMemcpyAsync(d.p, in, sizeof in, cudaMemcpyHostToDevice, ctx->st));
+    kat_philox(d.p, d.p + 6, ctx->st);
+    CU(cudaMemcpyAsync(out, d.p + 6, 16, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaGetLastError());
+    return MMK_OK;
+}
+extern "C" int32_t mmk_kat_math(mmk_ctx *ctx, int32_t kind, const double *in, double *out, int64_t n) {
+    if (!ctx || !in || !out || n < 0) return MMK_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->par.device));
+    DBuf<double> d;
+    CU(d.ensure((size_t)2 * n + 2));
+    CU(cudaMemcpyAsync(d.p, in, n * 8, cudaMemcpyHostToDevice, ctx->st));
+    kat_math(kind, d.p, d.p + n, n, ctx->st);
+    CU(cudaMemcpyAsync(out, d.p + n, n * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaGetLastError());
+    return MMK_OK;
+}

@@ -1,0 +1,152 @@
+// mmk_internal.h — types shared by the host driver (mmk_host.cpp) and the kernels (mmk_device.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mimick_b200.h"
+#include "mmk_rng.h"
+
+// Truncated Exponential as Distributions.jl builds it (truncated.jl; restated in DESIGN.md §3).
+struct TruncExp {
+    double theta, lower, upper;
+    int32_t has_upper, pad;
+    double loglcdf, lcdf, tp, logtp;
+};
+
+// Everything the sampling kernels need, frozen at mmk_create (SimParams, src/Structs.jl:54-70).
+struct SimConst {
+    uint64_t seed;
+    uint32_t sample;
+    int32_t nmol_fixed;  // >0: fixed molecules per barcode group; 0: draw from `nmol`
+    TruncExp mollen;     // truncated(Exponential(mol_length), lower = lowerbound)
+    TruncExp nmol;       // truncated(Exponential(N), 1, 2.5N)
+    double ins_mu, ins_sd, ins_lb;  // truncated(Normal(mu, sd), lower = 200), lb standardised
+    double singletons, mol_coverage;
+    int32_t insert_length, attempts;
+    int32_t r1, r2;
+    int32_t circular, strict;
+    int32_t fq_format, bc_format;
+};
+
+// One (contig, haplotype) unit as the kernels see it.
+struct SchemaDev {
+    uint64_t word_off;  // first 32-bit word of the packed haplotype in the arena
+    uint32_t len;       // bases
+    uint16_t haplotype;
+    uint16_t name_len;
+    char name[56];
+};
+static_assert(sizeof(SchemaDev) == 72, "SchemaDev layout");
+
+// Per-molecule record written by the placement kernel, read by the emit kernel.
+struct MolRec {
+    int64_t start;      // 1-based molecule start
+    uint32_t size;      // molecule length (position = start : start+size)
+    uint16_t schema;
+    uint8_t prefix_len; // "@chrom:hap|start:end|"
+    uint8_t suffix_len; // format-specific tail of the header line incl. '\n', read digit = '1'
+    uint32_t qual1, qual2;  // quality-string lengths (length of the molecule's first R1 / R2)
+};
+static_assert(sizeof(MolRec) == 24, "MolRec layout");
+
+// Plan arrays (SoA, device). Index = run-order molecule index.
+struct PlanDev {
+    uint64_t *group;
+    uint32_t *slot;
+    uint16_t *schema;
+    uint16_t *epoch;
+    uint32_t *size;
+    uint32_t *nfrags;
+    uint8_t *status;
+};
+
+struct BatchResult {  // device→host after every speculative batch
+    uint64_t cut_group;   // first group at whose end a live schema reaches its target, or ~0
+    uint64_t n_commit;    // molecules of the batch to keep
+    uint64_t first_error; // batch-local index of the first molecule with status != 0 among kept, or ~0
+    uint32_t error_code;
+    uint32_t pad;
+    uint64_t sums[1];     // [n_live] inserts added per live schema by the kept molecules
+};
+
+struct EmitArgs {
+    const uint32_t *hap;
+    const SchemaDev *sch;
+    const uint64_t *read_off;  // [n_mol_shard + 1] shard-relative first pair of each shard molecule
+    const MolRec *mol;
+    const uint8_t *text;
+    const uint2 *ins;          // (start - mol.start, length) per shard pair
+    const uint64_t *tile_off1; // [n_tiles + 1] shard-relative byte offsets
+    const uint64_t *tile_off2;
+    uint8_t *out1, *out2;
+    uint64_t chunk_off1, chunk_off2;  // byte offset of this chunk in the shard text
+    uint64_t n_pairs;          // pairs in shard
+    uint32_t n_mol;            // molecules in shard
+    uint32_t tile0, n_tiles;
+    uint32_t tile_pairs;
+    uint32_t text_stride;
+    int32_t r1, r2;
+    int32_t fq_format, bclen_inline;  // bclen_inline = 16 for tenx else 0
+    int32_t strict, bpb;
+    int32_t force_generic;
+};
+
+#ifdef __cplusplus
+extern "C++" {
+#endif
+// ---- launchers implemented in mmk_device.cu (all asynchronous on `st`) ---------------------
+namespace mmkdev {
+
+struct ContigStats {
+    unsigned long long first_bad;  // index of first symbol outside the DNA alphabet, or ~0
+    unsigned long long n_N;
+    unsigned long long n_nonACGT;
+};
+void normalize_ascii(char *d_bases, int64_t len, ContigStats *d_stats, cudaStream_t st);
+void mask_n(char *d_bases, int64_t len, uint64_t seed, uint32_t contig, uint32_t hap, cudaStream_t st);
+void count_bases(const char *d_bases, int64_t len, ContigStats *d_stats, cudaStream_t st);
+void scatter_snps(char *d_bases, const int64_t *d_pos, const char *d_alt, int64_t n, cudaStream_t st);
+// segmented gather + pack: output base o comes from piece p = last piece with dst[p] <= o:
+// src_kind 0 → d_master[src[p] + (o - dst[p])], 1 → d_alt[src[p] + (o - dst[p])]
+void pack_pieces(const char *d_master, const char *d_alt, const int64_t *d_dst, const int64_t *d_src,
+                 const uint8_t *d_kind, int32_t n_pieces, int64_t out_len, uint32_t *d_words, int bpb,
+                 ContigStats *d_stats, cudaStream_t st);
+void unpack(const uint32_t *d_words, int64_t len, int bpb, char *d_out, cudaStream_t st);
+
+void exclusive_scan_u32(const uint32_t *d_in, uint64_t *d_out /*[n+1]*/, uint64_t n, uint64_t *d_tmp /*[>= n/1024+2]*/,
+                        cudaStream_t st);
+
+// d_hist needs plan_hist_chunks(max_mol) * n_live entries, d_cross n_live, d_lpos 65536.
+uint32_t plan_hist_chunks(uint64_t max_molecules);
+void plan_batch(const SimConst &sc, const SchemaDev *d_sch, const uint16_t *d_live, uint32_t n_live, uint16_t epoch,
+                uint64_t g0, uint32_t n_groups, uint32_t *d_nmol, uint64_t *d_off, uint64_t *d_scan_tmp,
+                PlanDev plan, uint64_t mol_base, uint64_t max_mol, const int64_t *d_need, unsigned long long *d_hist,
+                unsigned long long *d_cross, uint16_t *d_lpos, BatchResult *d_res, cudaStream_t st);
+
+void shard_bounds(const uint64_t *d_read_off, uint64_t n_mol, uint64_t n_pairs, int32_t world, uint64_t *d_bounds /*[world+1]*/,
+                  cudaStream_t st);
+
+void place(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol,
+           const uint64_t *d_read_off_global, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
+           uint64_t *d_read_off_local, unsigned long long *d_err /*[2]: first bad molecule, code*/, cudaStream_t st);
+
+void tile_sums(const EmitArgs &a, uint32_t n_tiles_total, uint32_t *d_sum1, uint32_t *d_sum2, unsigned long long *d_gather,
+               cudaStream_t st);
+void find_tile(const uint64_t *d_off1, const uint64_t *d_off2, uint32_t tile0, uint32_t n_tiles, uint64_t cap,
+               uint32_t *d_out, cudaStream_t st);
+void emit(const EmitArgs &a, cudaStream_t st);
+
+void dump_variates(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t n_mol, const uint64_t *d_read_off,
+                   const uint2 *d_ins, const uint32_t *d_epoch_nlive, const uint16_t *d_epoch_live, uint32_t live_stride,
+                   uint32_t *d_counts, uint64_t *d_offsets, uint64_t *d_scan_tmp, mmk_variate *d_out, int pass,
+                   cudaStream_t st);
+void dump_mask(const char *d_raw_upper, int64_t len, uint64_t seed, uint32_t contig, uint32_t hap, uint32_t *d_flags,
+               uint64_t *d_off, uint64_t *d_scan_tmp, mmk_variate *d_out, int pass, cudaStream_t st);
+
+void kat_philox(const uint32_t *d_in6, uint32_t *d_out4, cudaStream_t st);
+void kat_math(int kind, const double *d_in, double *d_out, int64_t n, cudaStream_t st);
+
+}  // namespace mmkdev
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,208 @@
+// mmk_sampling.cuh — device-side sampling of one barcode group / one molecule.
+//
+// Behavioural contract (reference = mimick/MimickLinkedReads.jl/src):
+//   draw_nmol            get_n_molecules            Common.jl:89-91, Structs.jl:63-67
+//   molecule_shape       get_molecule_size          Breakpoints.jl:149-163
+//                        calculate_n_frags          Breakpoints.jl:171-196
+//   molecule_place       calculate_insert_sizes     Breakpoints.jl:205-218
+//                        get_sequences (start)      Breakpoints.jl:235-242
+//                        seq_breakpoints!           Breakpoints.jl:21-35
+// Every function is templated on a recorder so the same code path can also report the variates
+// it consumed, in the reference's draw order, for the oracle's replay mode.
+#pragma once
+#include "mmk_internal.h"
+
+struct NoRec {
+    __device__ __forceinline__ void put(uint32_t, uint32_t, uint64_t) {}
+};
+struct CountRec {
+    uint32_t n = 0;
+    __device__ __forceinline__ void put(uint32_t, uint32_t, uint64_t) { ++n; }
+};
+struct WriteRec {
+    mmk_variate *p;
+    __device__ __forceinline__ void put(uint32_t tag, uint32_t aux, uint64_t bits) {
+        p->tag = tag;
+        p->aux = aux;
+        p->v.i = (int64_t)bits;
+        ++p;
+    }
+};
+
+// Build truncated(Exponential(theta), lower, upper) the way Distributions.jl does.
+__device__ __forceinline__ bool trunc_exp_make(TruncExp &d, double theta, double lower, bool has_upper, double upper) {
+    d.theta = theta;
+    d.lower = lower;
+    d.upper = upper;
+    d.has_upper = has_upper;
+    if (has_upper && !(lower <= upper)) return false;
+    double zl = MMK_DIV(lower > 0.0 ? lower : 0.0, theta);
+    d.loglcdf = mmk_log1mexp(-zl);
+    d.lcdf = mmk_exp(d.loglcdf);
+    if (has_upper) {
+        double zu = MMK_DIV(upper > 0.0 ? upper : 0.0, theta);
+        double logucdf = mmk_log1mexp(-zu);
+        d.logtp = mmk_logsubexp(d.loglcdf, logucdf);
+    } else {
+        d.logtp = mmk_log1mexp(d.loglcdf);
+    }
+    d.tp = mmk_exp(d.logtp);
+    return true;
+}
+
+// rand(::Truncated{Exponential}): rejection when tp > 0.25, inverse cdf when tp > sqrt(eps),
+// log-space inverse otherwise.
+template <class R>
+__device__ __forceinline__ double trunc_exp_rand(mmk_stream &s, const TruncExp &d, uint32_t tag, R &rec) {
+    if (d.tp > 0.25) {
+        for (;;) {
+            double e = mmk_next_exp(&s);
+            rec.put(tag, 0, mmk_d2u(e));
+            double r = MMK_MUL(e, d.theta);
+            if (r >= d.lower && (!d.has_upper || r <= d.upper)) return r;
+        }
+    } else if (d.tp > 1.4901161193847656e-08) {
+        double u = mmk_next_u01(&s);
+        rec.put(tag, 0, mmk_d2u(u));
+        double p = MMK_ADD(d.lcdf, MMK_MUL(u, d.tp));
+        return -MMK_MUL(mmk_log1p(-p), d.theta);
+    } else {
+        double e = mmk_next_exp(&s);
+        rec.put(tag, 0, mmk_d2u(e));
+        double lp = mmk_logaddexp(d.loglcdf, MMK_SUB(d.logtp, e));
+        return -MMK_MUL(mmk_log1mexp(lp), d.theta);
+    }
+}
+
+// round to nearest, ties to even (Julia round(x, digits = 0)); x >= 0 here
+__device__ __forceinline__ double round_half_even(double x) { return rint(x); }
+
+template <class R>
+__device__ __forceinline__ uint32_t draw_nmol(const SimConst &sc, uint64_t g, R &rec) {
+    if (sc.nmol_fixed > 0) return (uint32_t)sc.nmol_fixed;
+    mmk_stream s;
+    mmk_stream_init(&s, sc.seed, sc.sample, MMK_P_NMOL, g, 0);
+    double x = trunc_exp_rand(s, sc.nmol, MMK_P_NMOL, rec);
+    return (uint32_t)(long long)round_half_even(x);
+}
+
+// Target pick of slot m in group g: uniform index into the live list (Main.jl:47).
+__device__ __forceinline__ uint32_t draw_target(const SimConst &sc, uint64_t g, uint32_t m, uint32_t n_live) {
+    mmk_stream s;
+    mmk_stream_init(&s, sc.seed, sc.sample, MMK_P_TARGET, g, 0);
+    return (uint32_t)mmk_bits_to_index(mmk_stream_at(&s, m), n_live);
+}
+
+// Molecule length and number of inserts. Returns status (0 ok).
+template <class R>
+__device__ __forceinline__ uint32_t molecule_shape(const SimConst &sc, uint64_t g, uint32_t m, uint32_t seq_len,
+                                                   uint32_t &molsize, uint32_t &nfrags, R &rec) {
+    mmk_stream s;
+    mmk_stream_init(&s, sc.seed, sc.sample, MMK_P_MOLSIZE, g, m);
+    double ml = (double)seq_len + 1.0;
+    int attempts = 0;
+    while (ml > (double)seq_len && attempts < 30) {
+        ++attempts;
+        ml = trunc_exp_rand(s, sc.mollen, MMK_P_MOLSIZE, rec);
+    }
+    if (ml > (double)seq_len) ml = (double)seq_len;
+    molsize = (uint32_t)(long long)ml;
+
+    double N;
+    bool single = false;
+    if (sc.singletons > 0.0) {
+        mmk_stream_init(&s, sc.seed, sc.sample, MMK_P_SINGLETON, g, m);
+        double u = mmk_next_u01(&s);
+        rec.put(MMK_P_SINGLETON, 0, mmk_d2u(u));
+        single = u <= sc.singletons;
+    }
+    uint32_t status = 0;
+    if (single) {
+        N = 1.0;
+    } else {
+        double max_possible = MMK_DIV((double)molsize, (double)sc.insert_length);
+        if (max_possible == 1.0) {
+            N = 1.0;
+        } else {
+            double n_mean;
+            if (sc.mol_coverage < 1.0) {
+                double exact = MMK_DIV(MMK_MUL((double)molsize, sc.mol_coverage), (double)sc.insert_length);
+                n_mean = exact > 2.0 ? exact : 2.0;
+            } else
+                n_mean = sc.mol_coverage;
+            TruncExp d;
+            if (!trunc_exp_make(d, n_mean, 2.0, true, max_possible)) {
+                status = MMK_ERR_TRUNCATION_BOUNDS;
+                N = 1.0;
+            } else {
+                mmk_stream_init(&s, sc.seed, sc.sample, MMK_P_NFRAGS, g, m);
+                N = trunc_exp_rand(s, d, MMK_P_NFRAGS, rec);
+            }
+        }
+    }
+    nfrags = (uint32_t)(long long)N;
+    return status;
+}
+
+// Insert lengths (written to ins[i].y), molecule start, gap chain (ins[i].x = start_i - start).
+template <class R>
+__device__ __forceinline__ uint32_t molecule_place(const SimConst &sc, uint64_t g, uint32_t m, uint32_t seq_len,
+                                                   uint32_t molsize, uint32_t nfrags, uint2 *ins, int64_t &start,
+                                                   R &rec) {
+    mmk_stream s;
+    mmk_stream_init(&s, sc.seed, sc.sample, MMK_P_INSERT, g, m);
+    int attempts = 0;
+    double sum;
+    uint64_t isum;
+    for (;;) {
+        sum = 0.0;
+        isum = 0;
+        for (uint32_t i = 0; i < nfrags; ++i) {
+            double x;
+            for (;;) {
+                double z = mmk_next_normal(&s);
+                rec.put(MMK_P_INSERT, 0, mmk_d2u(z));
+                if (!(z < sc.ins_lb)) {
+                    x = MMK_ADD(sc.ins_mu, MMK_MUL(sc.ins_sd, z));
+                    break;
+                }
+            }
+            sum = MMK_ADD(sum, x);
+            uint32_t li = (uint32_t)(long long)x;
+            ins[i].y = li;
+            isum += li;
+        }
+        if (sum > (double)molsize && attempts < sc.attempts) {
+            ++attempts;
+            continue;
+        }
+        break;
+    }
+    uint32_t status = 0;
+    if (sum > (double)molsize) status = MMK_ERR_INSERTS_UNFITTABLE;
+
+    // start_pos = rand(1:adjusted_end)
+    uint64_t adjusted_end = sc.circular ? (uint64_t)seq_len : (seq_len > molsize + 1u ? (uint64_t)(seq_len - molsize) : 1ull);
+    mmk_stream_init(&s, sc.seed, sc.sample, MMK_P_START, g, m);
+    uint64_t sidx = mmk_next_index(&s, adjusted_end);
+    rec.put(MMK_P_START, (uint32_t)adjusted_end, sidx);
+    start = (int64_t)sidx + 1;
+    if (status) {
+        for (uint32_t i = 0; i < nfrags; ++i) ins[i].x = 0;
+        return status;
+    }
+    // gap chain
+    uint64_t remaining = (uint64_t)molsize + 1 - isum;
+    uint64_t cursor = 0;  // relative to start
+    mmk_stream_init(&s, sc.seed, sc.sample, MMK_P_GAP, g, m);
+    for (uint32_t i = 0; i < nfrags; ++i) {
+        uint64_t gap = mmk_next_index(&s, remaining + 1);
+        rec.put(MMK_P_GAP, (uint32_t)(remaining + 1), gap);
+        uint64_t st = cursor + gap;
+        uint32_t li = ins[i].y;
+        ins[i].x = (uint32_t)st;
+        cursor = st + li;
+        remaining -= gap;
+    }
+    return 0;
+}

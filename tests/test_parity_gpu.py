@@ -1,0 +1,306 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle — the first gate.
+
+Every case runs the same seeded inputs through libmimick_b200.so and oracle/mimick_oracle.c and
+requires byte-identical R1/R2 text, identical plans, and that the oracle, fed ONLY the variates the
+kernels report having consumed (replay mode, no RNG on the CPU side), reproduces the same bytes.
+Bar: bit-exact (integer / byte work; the few FP64 expressions are single-rounded on both sides).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+from helpers import assert_same_bytes, make_ci_haplotypes, random_bases, write_fasta
+
+pytestmark = pytest.mark.gpu
+
+CLI = dict(attempts=300, singletons=0.0)  # CLI defaults that differ from the Julia ones (mimick/__main__.py:46,51)
+
+
+def gpu_single(fastas, fmt, seed, mask=False, variates=True, **kw):
+    import mimick_b200 as M
+    with M.Simulator(fmt, seed=seed, mask=mask, **kw) as sim:
+        for h, p in enumerate(fastas, start=1):
+            sim.load_fasta(p, h)
+        plan = sim.plan()
+        place = sim.place()
+        r1, r2 = sim.emit_to_host()
+        out = dict(r1=r1.tobytes(), r2=r2.tobytes(), mol=sim.molecules(), ins=sim.inserts(), plan=plan, place=place,
+                   schemas=sim.schemas())
+        if variates:
+            out["var"] = np.concatenate([sim.mask_variates(), sim.variates()])
+        return out
+
+
+def compare(gpu, orc, what):
+    assert_same_bytes(gpu["r1"], orc.r1, what + " R1")
+    assert_same_bytes(gpu["r2"], orc.r2, what + " R2")
+    gm, om = gpu["mol"], orc.molecules
+    assert len(gm) == len(om)
+    for f in ("group", "slot", "schema", "start", "molsize", "n_frags", "first_read", "barcode_index"):
+        assert np.array_equal(gm[f], om[f]), f"{what}: molecule field {f}"
+    assert np.array_equal(gpu["ins"][0], orc.insert_start)
+    assert np.array_equal(gpu["ins"][1], orc.insert_stop)
+    assert gpu["plan"].n_groups == orc.n_groups
+    assert [s["reads_current"] for s in gpu["schemas"]] == orc.reads_current
+    assert [s["reads_required"] for s in gpu["schemas"]] == orc.reads_required
+
+
+def check_single(fastas, fmt, seed, mask=False, **kw):
+    gpu = gpu_single(fastas, fmt, seed, mask=mask, **kw)
+    okw = {k: v for k, v in kw.items() if k not in ("force_generic", "max_chunk_bytes", "plan_batch_groups")}
+    orc = O.mimick_single(fastas, fmt, seed=seed, mask=mask, record=True, **okw)
+    compare(gpu, orc, f"{fmt} philox")
+    # the variates the kernels say they consumed == the variates the oracle consumed, bit for bit
+    assert orc.variates is not None and len(orc.variates) == len(gpu["var"])
+    assert np.array_equal(orc.variates["tag"], gpu["var"]["tag"])
+    assert np.array_equal(orc.variates["bits"], gpu["var"]["bits"])
+    # replay: the oracle sees no seed, only the GPU's stream
+    rep = O.mimick_single(fastas, fmt, seed=0xDEAD, mask=mask, replay=gpu["var"], **okw)
+    compare(gpu, rep, f"{fmt} replay")
+    return gpu, orc
+
+
+# ------------------------------------------------------------------------------------------
+def test_device_philox_and_math_are_bit_exact():
+    import mimick_b200 as M
+    L = O.lib()
+    with M.Simulator("haplotagging", seed=1) as sim:
+        for ctr, key, want in [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+                               ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+                               ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+                                (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]:
+            assert tuple(int(x) for x in sim.kat_philox(ctr, key)) == want
+        rng = np.random.default_rng(3)
+        x = np.exp(rng.uniform(-700, 700, 200000))
+        got = sim.kat_math(0, x)
+        want = np.array([L.orc_det_log(float(v)) for v in x[:20000]])
+        assert np.array_equal(got[:20000].view(np.uint64), want.view(np.uint64))
+        assert np.max(np.abs(got - np.log(x)) / np.maximum(np.abs(np.log(x)), 1e-300)) < 1e-15
+        y = rng.uniform(-700, 700, 20000)
+        got = sim.kat_math(1, y)
+        want = np.array([L.orc_det_exp(float(v)) for v in y])
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+
+
+@pytest.mark.parametrize("fmt", ["haplotagging", "stlfr", "tellseq", "10x", "standard:stlfr", "standard", "standard:haplotagging"])
+@pytest.mark.parametrize("mask", [False, True])
+def test_ci_single_sample(tmp_path, fmt, mask):
+    """The reference's CI matrix (.github/workflows/tests.yml:47-57): two generated haplotypes with a
+    1000-base contig + NNNN, -g 10, CLI defaults. Exercises the 4-bit path, N masking, the 30-attempt
+    molecule fallback, the quantile branch of the truncated exponential and the 1-base wrap."""
+    fastas = make_ci_haplotypes(tmp_path, seed=11, big=60000)
+    check_single(fastas, fmt, seed=5, mask=mask, coverage=10, **CLI)
+
+
+def test_c1_multisample(ref_fasta, ref_vcf):
+    """BASELINE config 1: test/fasta.fa.gz + test/test.vcf.gz, haplotagging, -g 5, all 7 samples."""
+    import mimick_b200 as M
+    orc = O.mimick_multi(ref_fasta, ref_vcf, "haplotagging", seed=42, coverage=5, record=True, **CLI)
+    vcf = M.Vcf(ref_vcf)
+    assert vcf.samples == [f"tsk_{i}" for i in range(7)] and vcf.ploidy == 2 and vcf.n_records == 13705
+    replay = {}
+    with M.Simulator("haplotagging", seed=42, coverage=5, **CLI) as sim:
+        sim.load_fasta(ref_fasta, 1)
+        for si, name in enumerate(vcf.samples):
+            sim.apply_vcf_sample(vcf, si)
+            plan = sim.plan()
+            place = sim.place()
+            assert place.n_pairs == plan.n_pairs
+            r1, r2 = sim.emit_to_host()
+            gpu = dict(r1=r1.tobytes(), r2=r2.tobytes(), mol=sim.molecules(), ins=sim.inserts(), plan=plan,
+                       schemas=sim.schemas())
+            compare(gpu, orc[name], name)
+            assert [s["reads_required"] for s in gpu["schemas"]] == [25000, 25000]
+            replay[name] = sim.variates()
+            if si < 2:  # haplotype construction itself
+                vs = O.sample_variants(O.read_vcf(ref_vcf), si)
+                master = O.read_fasta(ref_fasta)[0][1].upper()
+                for h in (1, 2):
+                    assert sim.schema_bases(h - 1) == O.Oracle.mutate(master, vs[f"chr1_{h}"])
+    rep = O.mimick_multi(ref_fasta, ref_vcf, "haplotagging", seed=1, coverage=5, replay=replay, samples=["tsk_0", "tsk_3"], **CLI)
+    for name in ("tsk_0", "tsk_3"):
+        assert rep[name].r1 == orc[name].r1 and rep[name].r2 == orc[name].r2
+
+
+@pytest.mark.parametrize("strict", [False, True])
+def test_circular(tmp_path, strict):
+    """circular=true: molecule starts anywhere; literal mode reproduces the reference's wrap
+    (reads that START past the contig end become hap[1 : stop % n]), strict mode wraps
+    modulo n."""
+    rng = np.random.default_rng(2)
+    p = os.path.join(str(tmp_path), "circ.fa")
+    write_fasta(p, [("plasmid", random_bases(rng, 150000))])
+    gpu, orc = check_single([p], "stlfr", seed=9, coverage=40, circular=True, strict_wrap=strict, mol_length=40000, **CLI)
+    lens = {len(l) for l in gpu["r1"].split(b"\n")[1::4]}
+    if strict:
+        assert lens == {150}
+    else:
+        assert max(lens) > 150  # the D5 giant reads are really there
+
+
+@pytest.mark.parametrize("kw", [
+    dict(singletons=0.35, attempts=300),
+    dict(n_molecules=-3, singletons=0.0, attempts=50),
+    dict(n_molecules=5, mol_coverage=6.0, singletons=0.1, attempts=300),
+    dict(read_length=(132, 150), insert_length=350, insert_stdev=80, singletons=0.0, attempts=300),
+    dict(read_length=(150, 108), mol_length=20000, mol_coverage=0.5, singletons=0.0, attempts=300),
+    dict(mol_length=300, singletons=0.0, attempts=300),   # molecule-length law in its quantile branch (tp = e^-10)
+    dict(read_length=(250, 250), insert_length=600, insert_stdev=150, singletons=0.0, attempts=300),
+])
+def test_parameter_regions(tmp_path, kw):
+    rng = np.random.default_rng(4)
+    p1 = os.path.join(str(tmp_path), "a.fa")
+    p2 = os.path.join(str(tmp_path), "b.fa.gz")
+    write_fasta(p1, [("chrA", random_bases(rng, 90000)), ("chrB", random_bases(rng, 30000))])
+    write_fasta(p2, [("chrA", random_bases(rng, 90100)), ("chrB", random_bases(rng, 29000))])
+    check_single([p1, p2], "tellseq", seed=77, coverage=8, **kw)
+
+
+def test_many_schemas_many_epochs(tmp_path):
+    """40 contigs × 2 haplotypes of very different lengths: dozens of pruning epochs, small batches."""
+    rng = np.random.default_rng(8)
+    recs1 = [(f"ctg{i}", random_bases(rng, int(6000 + 3000 * i))) for i in range(40)]
+    recs2 = [(n, random_bases(rng, len(s) + 17)) for n, s in recs1]
+    p1, p2 = os.path.join(str(tmp_path), "h1.fa"), os.path.join(str(tmp_path), "h2.fa")
+    write_fasta(p1, recs1)
+    write_fasta(p2, recs2)
+    gpu, orc = check_single([p1, p2], "standard:haplotagging", seed=3, coverage=12, plan_batch_groups=512, **CLI)
+    assert gpu["plan"].n_epochs >= 20
+
+
+def test_generic_path_equals_fast_path(tmp_path):
+    fastas = make_ci_haplotypes(tmp_path, seed=21, big=50000)
+    a = gpu_single(fastas, "10x", 6, coverage=6, variates=False, **CLI)
+    b = gpu_single(fastas, "10x", 6, coverage=6, variates=False, force_generic=True, **CLI)
+    assert a["r1"] == b["r1"] and a["r2"] == b["r2"]
+
+
+def test_sharding_and_chunking(tmp_path):
+    import mimick_b200 as M
+    fastas = make_ci_haplotypes(tmp_path, seed=31, big=80000)
+    whole = gpu_single(fastas, "haplotagging", 12, coverage=9, variates=False, **CLI)
+    parts1, parts2, pairs = [], [], 0
+    for rank in range(3):
+        with M.Simulator("haplotagging", seed=12, coverage=9, max_chunk_bytes=1 << 20, **CLI) as sim:
+            for h, p in enumerate(fastas, start=1):
+                sim.load_fasta(p, h)
+            sim.plan()
+            sim.set_shard(rank, 3)
+            place = sim.place()
+            pairs += place.n_pairs
+            n_chunks = 0
+            while True:
+                ch = sim.emit_chunk()
+                if ch.n_pairs:
+                    a1, a2 = sim.copy_chunk(ch)
+                    parts1.append(a1.tobytes())
+                    parts2.append(a2.tobytes())
+                    n_chunks += 1
+                if ch.done:
+                    break
+            assert n_chunks > 1
+            r1, r2 = sim.emit_to_host()  # pipelined path over the same ring
+            assert r1.tobytes() == b"".join(parts1)[-len(r1):]
+    assert pairs == whole["plan"].n_pairs
+    assert b"".join(parts1) == whole["r1"] and b"".join(parts2) == whole["r2"]
+
+
+def _write_vcf(path, contig, length, samples, records):
+    with open(path, "w") as fh:
+        fh.write("##fileformat=VCFv4.2\n")
+        fh.write(f"##contig=<ID={contig},length={length}>\n")
+        fh.write('##FORMAT=<ID=GT,Number=1,Type=String,Description="Genotype">\n')
+        fh.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join(samples) + "\n")
+        for pos, ref, alts, gts in records:
+            fh.write(f"{contig}\t{pos}\t.\t{ref}\t{','.join(alts)}\t.\tPASS\t.\tGT\t" + "\t".join(gts) + "\n")
+
+
+def test_indels_and_multiallelic(tmp_path):
+    """The reference's fixture has no indel; synthesise SNPs, insertions, deletions, MNPs and
+    multi-allelic sites and check haplotype construction + FASTQ against the oracle's literal splices."""
+    import mimick_b200 as M
+    rng = np.random.default_rng(5)
+    L = 120000
+    ref = random_bases(rng, L)
+    fa = os.path.join(str(tmp_path), "ref.fa")
+    write_fasta(fa, [("chr7", ref)])
+    recs, pos = [], 50
+    samples = ["s0", "s1", "s2"]
+    while pos < L - 100:
+        kind = rng.integers(0, 5)
+        r = ref[pos - 1:pos].decode()
+        alt1 = "ACGT"[("ACGT".index(r) + 1) % 4]
+        if kind == 0:
+            ref_a, alts = r, [alt1]
+        elif kind == 1:
+            ref_a, alts = r, [r + random_bases(rng, int(rng.integers(1, 20))).decode()]
+        elif kind == 2:
+            dl = int(rng.integers(1, 20))
+            ref_a, alts = ref[pos - 1:pos + dl].decode(), [r]
+        elif kind == 3:
+            ref_a, alts = r, [alt1, r + "GG"]  # typed :indel for every allele because one ALT is long
+        else:
+            ref_a, alts = ref[pos - 1:pos + 2].decode(), [random_bases(rng, 3).decode()]
+        gts = ["|".join(str(int(rng.integers(0, len(alts) + 1))) for _ in range(2)) for _ in samples]
+        recs.append((pos, ref_a, alts, gts))
+        pos += len(ref_a) + int(rng.integers(1, 400))
+    vcfp = os.path.join(str(tmp_path), "v.vcf")
+    _write_vcf(vcfp, "chr7", L, samples, recs)
+    orc = O.mimick_multi(fa, vcfp, "tellseq", seed=19, coverage=6, **CLI)
+    vcf = M.Vcf(vcfp)
+    with M.Simulator("tellseq", seed=19, coverage=6, **CLI) as sim:
+        sim.load_fasta(fa, 1)
+        for si, name in enumerate(samples):
+            sim.apply_vcf_sample(vcf, si)
+            vs = O.sample_variants(O.read_vcf(vcfp), si)
+            for h in (1, 2):
+                want = O.Oracle.mutate(ref, vs[f"chr7_{h}"])
+                assert sim.schema_bases(h - 1) == want, f"{name} hap {h}"
+            plan = sim.plan()
+            sim.place()
+            r1, r2 = sim.emit_to_host()
+            assert_same_bytes(r1.tobytes(), orc[name].r1, name + " R1")
+            assert_same_bytes(r2.tobytes(), orc[name].r2, name + " R2")
+
+
+def test_error_sites(tmp_path):
+    import mimick_b200 as M
+    rng = np.random.default_rng(6)
+    with pytest.raises(M.MimickError) as e:
+        M.Simulator("nanopore")
+    assert e.value.status == 2
+    with pytest.raises(M.MimickError) as e:
+        M.mimick("x.fa", "calls.BCF", "stlfr")
+    assert e.value.status == 6
+    with M.Simulator("stlfr", seed=1, **CLI) as sim:
+        with pytest.raises(M.MimickError) as e:
+            sim.add_contig("tiny", b"ACGT" * 50 + b"N" * 100)  # 200 unambiguous < round(0.95 * 300)
+        assert e.value.status == 5
+        with pytest.raises(M.MimickError) as e:
+            sim.add_contig("bad", b"ACGT" * 100 + b"J" + b"ACGT" * 100)
+        assert e.value.status == 8
+        with pytest.raises(M.MimickError) as e:
+            sim.load_fasta(os.path.join(str(tmp_path), "missing.fa"))
+        assert e.value.status == 9
+        # a contig shorter than two inserts: truncated(Exponential, 2.0, 700/500) → lower > upper
+        sim.add_contig("short", random_bases(rng, 700))
+        with pytest.raises(M.MimickError) as e:
+            sim.plan()
+        assert e.value.status == 7
+    with pytest.raises(O.OracleError) as eo:
+        p = os.path.join(str(tmp_path), "short.fa")
+        write_fasta(p, [("short", random_bases(np.random.default_rng(6), 700))])
+        O.mimick_single([p], "stlfr", seed=1, **CLI)
+    assert eo.value.code == 7
+    # insert sizes that do not fit: two ~1000±50 bp inserts in a 2004-base molecule with no redraw allowed
+    # fail for about half of the molecules (float sum > molsize)
+    p = os.path.join(str(tmp_path), "c.fa")
+    write_fasta(p, [("c", random_bases(rng, 2004))])
+    with M.Simulator("stlfr", seed=1, insert_length=1000, insert_stdev=50, attempts=0, singletons=0.0, mol_coverage=2.0) as sim:
+        sim.load_fasta(p)
+        sim.plan()
+        with pytest.raises(M.MimickError) as e:
+            sim.place()
+        assert e.value.status == 3
