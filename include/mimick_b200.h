@@ -116,6 +116,8 @@ int32_t mmk_add_contig(mmk_ctx *ctx, const char *name, const char *bases, int64_
  * mmk_add_contig per record. */
 int32_t mmk_load_fasta(mmk_ctx *ctx, const char *path, int32_t haplotype);
 int32_t mmk_n_contigs(const mmk_ctx *ctx);
+/* forgets every contig, schema and plan (device buffers are kept for reuse): a new run on the same context */
+int32_t mmk_clear_contigs(mmk_ctx *ctx);
 
 /* Multi-sample mode (src/Main.jl:88-131): contigs added so far are the master; each call
  * replaces the schema set by this sample's haplotypes (build_sample_schema,
@@ -211,6 +213,25 @@ int32_t mmk_copy_chunk(mmk_ctx *ctx, const mmk_chunk *chunk, void *r1_host, void
 /* Whole shard to host memory: emission of chunk k+1 overlaps the copy of chunk k.
  * r1_host / r2_host need mmk_place_info.r1_bytes / r2_bytes bytes. */
 int32_t mmk_emit_to_host(mmk_ctx *ctx, void *r1_host, uint64_t r1_cap, void *r2_host, uint64_t r2_cap);
+
+/* Whole shard, device-resident: every chunk is generated back to back into the output ring (later
+ * chunks overwrite earlier ones when the shard is larger than the ring — "device-resident FASTQ"
+ * for a 446 GB job means exactly this).  No host copies, one synchronisation at the end.
+ * *kernel_ms = device time from the first to the last emit kernel (CUDA events on the stream). */
+int32_t mmk_emit_all(mmk_ctx *ctx, float *kernel_ms);
+
+/* Whole shard through a bounded host ring: chunk k is copied into r1_host[k % 2] / r2_host[k % 2]
+ * (each `slot_cap` bytes, >= the context's chunk size; pinned memory recommended) while chunk k+1 is
+ * generated.  `cb`, if not NULL, is called once per chunk, in order, when its bytes are in host
+ * memory; the slot is reused after it returns.  A non-zero return from `cb` aborts with that status. */
+typedef int32_t (*mmk_chunk_cb)(void *user, const mmk_chunk *chunk, const void *r1_host, const void *r2_host);
+int32_t mmk_emit_stream(mmk_ctx *ctx, void *const r1_host[2], void *const r2_host[2], uint64_t slot_cap,
+                        mmk_chunk_cb cb, void *user);
+/* bytes each output slot holds for this shard (after mmk_place) and the number of chunks */
+int32_t mmk_chunk_layout(mmk_ctx *ctx, uint64_t *slot_bytes, int32_t *n_chunks);
+
+/* number of kernels this library has launched in this process so far (all contexts) */
+uint64_t mmk_launch_count(void);
 
 /* ---- introspection for the parity tests ------------------------------------------------------ */
 typedef struct mmk_mol_record { /* one per planned molecule, run order */

@@ -73,7 +73,10 @@ EXPORTS = [
     "mmk_apply_vcf_sample", "mmk_n_schemas", "mmk_schema_get", "mmk_schema_bases", "mmk_plan", "mmk_set_shard",
     "mmk_place", "mmk_emit_chunk", "mmk_rewind", "mmk_copy_chunk", "mmk_emit_to_host", "mmk_dump_molecules",
     "mmk_dump_inserts", "mmk_dump_variates", "mmk_dump_mask_variates", "mmk_kat_philox", "mmk_kat_math",
+    "mmk_emit_all", "mmk_emit_stream", "mmk_chunk_layout", "mmk_launch_count", "mmk_clear_contigs",
 ]
+
+CHUNK_CB = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.POINTER(Chunk), C.c_void_p, C.c_void_p)
 
 _LIB = None
 
@@ -85,7 +88,7 @@ def load():
         return _LIB
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            f"{LIB_PATH} is missing. Build it with `python -m mimick_b200.build` (needs nvcc). "
+            f"{LIB_PATH} is missing. Build it with `python mimick_b200/build.py` (needs nvcc). "
             "mimick_b200 has no CPU fallback."
         )
     L = C.CDLL(LIB_PATH)
@@ -110,6 +113,7 @@ def load():
     sig("mmk_add_contig", i32, vp, cp, vp, i64, i32)
     sig("mmk_load_fasta", i32, vp, cp, i32)
     sig("mmk_n_contigs", i32, vp)
+    sig("mmk_clear_contigs", i32, vp)
     sig("mmk_set_sample_variants", i32, vp, u32, i32, vp, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, i64)
     sig("mmk_vcf_open", i32, cp, P(vp), C.c_char_p, C.c_size_t)
     sig("mmk_vcf_close", None, vp)
@@ -130,6 +134,10 @@ def load():
     sig("mmk_rewind", i32, vp)
     sig("mmk_copy_chunk", i32, vp, P(Chunk), vp, vp)
     sig("mmk_emit_to_host", i32, vp, vp, u64, vp, u64)
+    sig("mmk_emit_all", i32, vp, P(C.c_float))
+    sig("mmk_emit_stream", i32, vp, P(vp), P(vp), u64, vp, vp)
+    sig("mmk_chunk_layout", i32, vp, P(u64), P(i32))
+    sig("mmk_launch_count", u64)
     sig("mmk_dump_molecules", i32, vp, i64, i64, vp)
     sig("mmk_dump_inserts", i32, vp, i64, i64, vp, vp)
     sig("mmk_dump_variates", i32, vp, vp, u64, P(u64))

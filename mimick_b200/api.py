@@ -152,6 +152,9 @@ class Simulator:
             addr, n = arr.ctypes.data, arr.size
         self._ck(self._L.mmk_add_contig(self._h, name.encode(), C.c_void_p(addr), n, int(haplotype)))
 
+    def clear_contigs(self):
+        self._ck(self._L.mmk_clear_contigs(self._h))
+
     def load_fasta(self, path, haplotype: int = 1):
         self._ck(self._L.mmk_load_fasta(self._h, os.fspath(path).encode(), int(haplotype)))
 
@@ -236,6 +239,35 @@ class Simulator:
         self._ck(self._L.mmk_emit_to_host(self._h, C.c_void_p(r1[0]), r1[1], C.c_void_p(r2[0]), r2[1]))
         return None
 
+    def emit_all(self) -> float:
+        """Device-resident emission of the whole shard into the output ring; returns kernel ms."""
+        ms = C.c_float()
+        self._ck(self._L.mmk_emit_all(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def chunk_layout(self):
+        sb, n = C.c_uint64(), C.c_int32()
+        self._ck(self._L.mmk_chunk_layout(self._h, C.byref(sb), C.byref(n)))
+        return int(sb.value), int(n.value)
+
+    def emit_stream(self, r1_slots, r2_slots, slot_cap, consumer=None):
+        """Whole shard through two host slots per read (addresses; pinned memory recommended).
+        `consumer(chunk, r1_addr, r2_addr)` is called per chunk once its bytes are in host memory."""
+        a1 = (C.c_void_p * 2)(*r1_slots)
+        a2 = (C.c_void_p * 2)(*r2_slots)
+        cb = None
+        if consumer is not None:
+            def _cb(user, ch, p1, p2):
+                try:
+                    consumer(ch.contents, p1, p2)
+                    return 0
+                except Exception:  # never unwind through C
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            cb = _lib.CHUNK_CB(_cb)
+        self._ck(self._L.mmk_emit_stream(self._h, a1, a2, int(slot_cap), C.cast(cb, C.c_void_p) if cb else None, None))
+
     def run(self):
         """plan → place → emit everything to host; returns (R1 bytes, R2 bytes)."""
         self.plan()
@@ -309,16 +341,15 @@ class SampleOutput:
 
 
 def _write_shard(sim: Simulator, r1_path: str, r2_path: str, mode: str):
+    """File writes of chunk k overlap the generation and copy-out of chunk k+1 (mmk_emit_stream)."""
+    slot_bytes, _ = sim.chunk_layout()
+    slots = [np.empty(slot_bytes, dtype=np.uint8) for _ in range(4)]
     with open(r1_path, mode) as f1, open(r2_path, mode) as f2:
-        sim.rewind()
-        while True:
-            ch = sim.emit_chunk()
-            if ch.n_pairs:
-                a1, a2 = sim.copy_chunk(ch)
-                f1.write(memoryview(a1))
-                f2.write(memoryview(a2))
-            if ch.done:
-                break
+        def consume(ch, p1, p2):
+            f1.write((C.c_char * ch.r1_bytes).from_address(p1))
+            f2.write((C.c_char * ch.r2_bytes).from_address(p2))
+        sim.emit_stream([slots[0].ctypes.data, slots[1].ctypes.data], [slots[2].ctypes.data, slots[3].ctypes.data],
+                        slot_bytes, consume)
 
 
 def mimick(*args, prefix: str = "simulated/SIM", outdir: str = "simulated", quiet: bool = False,

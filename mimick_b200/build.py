@@ -1,6 +1,6 @@
 """Compile libmimick_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU).
 
-    python -m mimick_b200.build [--force]
+    python mimick_b200/build.py [--force] [-v]
 
 The shared library links the CUDA runtime statically and zlib dynamically; it has no Python or
 torch dependency (the C ABI in include/mimick_b200.h is the product boundary).
@@ -26,7 +26,7 @@ HOST_FLAGS = "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall,-Wno-unused-function"
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", HOST_FLAGS, "-I", INCLUDE, "-I", CSRC]
 
 SOURCES = ["mmk_device.cu", "mmk_host.cpp", "mmk_io.cpp"]
-HEADERS = ["mmk_internal.h", "mmk_sampling.cuh", "mmk_host.h", "mmk_emit_fast.cuh"]
+HEADERS = ["mmk_internal.h", "mmk_sampling.cuh", "mmk_host.h", "mmk_emit.cuh"]
 
 
 def _nvcc() -> str:

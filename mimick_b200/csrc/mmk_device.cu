@@ -17,6 +17,14 @@
 
 namespace mmkdev {
 
+static unsigned long long g_launches = 0;  // host-side count of kernel launches (single-threaded per context)
+unsigned long long launch_count() { return g_launches; }
+#define LAUNCH(k, grid, block, smem, st, ...)    \
+    do {                                         \
+        ++g_launches;                            \
+        k<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__); \
+    } while (0)
+
 // ------------------------------------------------------------------------------------------
 // small device helpers
 // ------------------------------------------------------------------------------------------
@@ -182,16 +190,16 @@ static inline int grid_for(int64_t n, int block, int cap = 148 * 16) {
 }
 
 void normalize_ascii(char *d, int64_t len, ContigStats *st, cudaStream_t s) {
-    k_normalize<<<grid_for(len, 256), 256, 0, s>>>(d, len, st);
+    LAUNCH(k_normalize, grid_for(len, 256), 256, 0, s, d, len, st);
 }
 void count_bases(const char *d, int64_t len, ContigStats *st, cudaStream_t s) {
-    k_count<<<grid_for(len, 256), 256, 0, s>>>(d, len, st);
+    LAUNCH(k_count, grid_for(len, 256), 256, 0, s, d, len, st);
 }
 void mask_n(char *d, int64_t len, uint64_t seed, uint32_t contig, uint32_t hap, cudaStream_t s) {
-    k_mask_n<<<grid_for(len, 256), 256, 0, s>>>(d, len, seed, contig, hap);
+    LAUNCH(k_mask_n, grid_for(len, 256), 256, 0, s, d, len, seed, contig, hap);
 }
 void scatter_snps(char *d, const int64_t *pos, const char *alt, int64_t n, cudaStream_t s) {
-    if (n > 0) k_scatter_snps<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d, pos, alt, n);
+    if (n > 0) LAUNCH(k_scatter_snps, (unsigned)((n + 255) / 256), 256, 0, s, d, pos, alt, n);
 }
 void pack_pieces(const char *master, const char *alt, const int64_t *dst, const int64_t *src, const uint8_t *kind,
                  int32_t n_pieces, int64_t out_len, uint32_t *words, int bpb, ContigStats *st, cudaStream_t s) {
@@ -200,15 +208,15 @@ void pack_pieces(const char *master, const char *alt, const int64_t *dst, const 
     int64_t nw = (out_len + per - 1) / per;
     unsigned g = (unsigned)((nw + 255) / 256);
     if (bpb == 2)
-        k_pack_pieces<2><<<g, 256, 0, s>>>(master, alt, dst, src, kind, n_pieces, out_len, words, st);
+        LAUNCH((k_pack_pieces<2>), g, 256, 0, s, master, alt, dst, src, kind, n_pieces, out_len, words, st);
     else
-        k_pack_pieces<4><<<g, 256, 0, s>>>(master, alt, dst, src, kind, n_pieces, out_len, words, st);
+        LAUNCH((k_pack_pieces<4>), g, 256, 0, s, master, alt, dst, src, kind, n_pieces, out_len, words, st);
 }
 void unpack(const uint32_t *words, int64_t len, int bpb, char *out, cudaStream_t s) {
     if (len <= 0) return;
     unsigned g = (unsigned)((len + 255) / 256);
-    if (bpb == 2) k_unpack<2><<<g, 256, 0, s>>>(words, len, out);
-    else k_unpack<4><<<g, 256, 0, s>>>(words, len, out);
+    if (bpb == 2) LAUNCH((k_unpack<2>), g, 256, 0, s, words, len, out);
+    else LAUNCH((k_unpack<4>), g, 256, 0, s, words, len, out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -292,9 +300,9 @@ void exclusive_scan_u32(const uint32_t *in, uint64_t *out, uint64_t n, uint64_t 
         return;
     }
     unsigned nb = (unsigned)((n + SCAN_B - 1) / SCAN_B);
-    k_scan_reduce<<<nb, SCAN_T, 0, s>>>(in, n, tmp);
-    k_scan_spine<<<1, 1024, 0, s>>>(tmp, nb);
-    k_scan_apply<<<nb, SCAN_T, 0, s>>>(in, n, tmp, out);
+    LAUNCH(k_scan_reduce, nb, SCAN_T, 0, s, in, n, tmp);
+    LAUNCH(k_scan_spine, 1, 1024, 0, s, tmp, nb);
+    LAUNCH(k_scan_apply, nb, SCAN_T, 0, s, in, n, tmp, out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -482,20 +490,20 @@ void plan_batch(const SimConst &sc, const SchemaDev *d_sch, const uint16_t *d_li
                 uint64_t g0, uint32_t n_groups, uint32_t *d_nmol, uint64_t *d_off, uint64_t *d_scan_tmp, PlanDev plan,
                 uint64_t mol_base, uint64_t max_mol, const int64_t *d_need, unsigned long long *d_hist,
                 unsigned long long *d_cross, uint16_t *d_lpos, BatchResult *d_res, cudaStream_t st) {
-    k_group_nmol<<<(n_groups + 255) / 256, 256, 0, st>>>(sc, g0, n_groups, d_nmol);
+    LAUNCH(k_group_nmol, (n_groups + 255) / 256, 256, 0, st, sc, g0, n_groups, d_nmol);
     exclusive_scan_u32(d_nmol, d_off, n_groups, d_scan_tmp, st);
-    k_plan_groups<<<(n_groups + 127) / 128, 128, 0, st>>>(sc, d_sch, d_live, n_live, epoch, g0, n_groups, d_nmol, d_off,
+    LAUNCH(k_plan_groups, (n_groups + 127) / 128, 128, 0, st, sc, d_sch, d_live, n_live, epoch, g0, n_groups, d_nmol, d_off,
                                                           plan, mol_base);
     uint32_t n_chunks = plan_hist_chunks(max_mol);
     cudaMemsetAsync(d_hist, 0, (size_t)n_chunks * n_live * sizeof(unsigned long long), st);
-    k_fill_lpos<<<(n_live + 255) / 256, 256, 0, st>>>(d_live, n_live, d_lpos);
-    k_hist<<<n_chunks, 256, 0, st>>>(plan.schema + mol_base, plan.nfrags + mol_base, d_off, n_groups, d_lpos, n_live, d_hist);
-    k_cross<<<(n_live * 32 + 127) / 128, 128, 0, st>>>(plan.schema + mol_base, plan.nfrags + mol_base, plan.group + mol_base,
+    LAUNCH(k_fill_lpos, (n_live + 255) / 256, 256, 0, st, d_live, n_live, d_lpos);
+    LAUNCH(k_hist, n_chunks, 256, 0, st, plan.schema + mol_base, plan.nfrags + mol_base, d_off, n_groups, d_lpos, n_live, d_hist);
+    LAUNCH(k_cross, (n_live * 32 + 127) / 128, 128, 0, st, plan.schema + mol_base, plan.nfrags + mol_base, plan.group + mol_base,
                                                        d_off, n_groups, d_live, n_live, d_hist, d_need, g0, d_cross);
-    k_cut<<<1, 1024, 0, st>>>(d_cross, n_live, g0, n_groups, d_off, plan.status + mol_base, d_res);
+    LAUNCH(k_cut, 1, 1024, 0, st, d_cross, n_live, g0, n_groups, d_off, plan.status + mol_base, d_res);
     cudaMemsetAsync((char *)d_res + offsetof(BatchResult, sums), 0, (size_t)n_live * 8, st);
     size_t sm = n_live <= 2048 ? (size_t)n_live * 8 : 0;
-    k_sums<<<148 * 4, 256, sm, st>>>(plan.schema + mol_base, plan.nfrags + mol_base, d_lpos, n_live, d_res);
+    LAUNCH(k_sums, 148 * 4, 256, sm, st, plan.schema + mol_base, plan.nfrags + mol_base, d_lpos, n_live, d_res);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -518,7 +526,7 @@ __global__ void k_shard_bounds(const uint64_t *read_off, uint64_t n_mol, uint64_
 }
 void shard_bounds(const uint64_t *d_read_off, uint64_t n_mol, uint64_t n_pairs, int32_t world, uint64_t *d_bounds,
                   cudaStream_t st) {
-    k_shard_bounds<<<1, 1024, 0, st>>>(d_read_off, n_mol, n_pairs, world, d_bounds);
+    LAUNCH(k_shard_bounds, 1, 1024, 0, st, d_read_off, n_mol, n_pairs, world, d_bounds);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -579,7 +587,7 @@ __device__ __noinline__ uint32_t check_windows(const uint2 *ins, uint32_t nfrags
                                                int strict, uint32_t &q1, uint32_t &q2) {
     uint32_t status = 0;
     for (uint32_t k = 0; k < nfrags; ++k) {
-        int64_t bs = start + ins[k].x, be = bs + ins[k].y - 1;
+        int64_t bs = start + ins[k].x, be = bs + MMK_INS_LEN(ins[k].y) - 1;
         int64_t a2 = be - r2 + 1;
         if (!strict && a2 < 1) status = MMK_ERR_BOUNDS;
         if (k == 0) {
@@ -590,19 +598,26 @@ __device__ __noinline__ uint32_t check_windows(const uint2 *ins, uint32_t nfrags
     return status;
 }
 
-__global__ void k_place(SimConst sc, const SchemaDev *__restrict__ sch, PlanDev plan, uint64_t mol0, uint32_t n_mol,
-                        const uint64_t *__restrict__ roff_g, uint2 *ins, MolRec *mol, uint8_t *text, uint32_t text_stride,
-                        uint64_t *roff_l, unsigned long long *err) {
+// shard-relative first pair of every shard molecule, and the first molecule of every tile
+__global__ void k_local_roff(const uint64_t *__restrict__ roff_g, uint64_t mol0, uint32_t n_mol, uint64_t *roff_l) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > n_mol) return;
-    uint64_t base = roff_g[mol0];
-    if (i == n_mol) {
-        roff_l[i] = roff_g[mol0 + n_mol] - base;
-        return;
-    }
+    if (i <= n_mol) roff_l[i] = roff_g[mol0 + i] - roff_g[mol0];
+}
+__global__ void k_tile_mol0(const uint64_t *__restrict__ roff_l, uint32_t n_mol, uint32_t tile_pairs, uint32_t *tile_mol0) {
+    uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_mol) return;
+    uint64_t lo = roff_l[m], hi = roff_l[m + 1];  // pairs [lo, hi)
+    if (hi == lo) return;
+    for (uint64_t t = (lo + tile_pairs - 1) / tile_pairs; t * tile_pairs < hi; ++t) tile_mol0[t] = m;
+}
+
+__global__ void k_place(SimConst sc, const SchemaDev *__restrict__ sch, PlanDev plan, uint64_t mol0, uint32_t n_mol,
+                        const uint64_t *__restrict__ roff_l, uint2 *ins, MolRec *mol, uint8_t *text, uint32_t text_stride,
+                        const uint32_t *__restrict__ tile_mol0, uint32_t tile_pairs, unsigned long long *err) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_mol) return;
     uint64_t gi = mol0 + i;
-    uint64_t ro = roff_g[gi] - base;
-    roff_l[i] = ro;
+    uint64_t ro = roff_l[i];
     uint64_t g = plan.group[gi];
     uint32_t m = plan.slot[gi];
     uint32_t t = plan.schema[gi];
@@ -610,7 +625,8 @@ __global__ void k_place(SimConst sc, const SchemaDev *__restrict__ sch, PlanDev 
     const SchemaDev &S = sch[t];
     NoRec rec;
     int64_t start;
-    uint32_t status = molecule_place(sc, g, m, S.len, molsize, nfrags, ins + ro, start, rec);
+    TileRef tr{tile_mol0, ro, i, tile_pairs};
+    uint32_t status = molecule_place(sc, g, m, S.len, molsize, nfrags, ins + ro, tr, start, rec);
     uint32_t n = S.len;
     uint32_t q1 = 0, q2 = 0;
     if (!status) status = check_windows(ins + ro, nfrags, start, n, sc.r1, sc.r2, sc.strict, q1, q2);
@@ -652,151 +668,27 @@ __global__ void k_place(SimConst sc, const SchemaDev *__restrict__ sch, PlanDev 
 }
 void place(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol,
            const uint64_t *d_read_off_global, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
-           uint64_t *d_read_off_local, unsigned long long *d_err, cudaStream_t st) {
-    k_place<<<(n_mol + 1 + 127) / 128, 128, 0, st>>>(sc, d_sch, plan, mol0, n_mol, d_read_off_global, d_ins, d_mol, d_text,
-                                                     text_stride, d_read_off_local, d_err);
+           uint64_t *d_read_off_local, uint32_t *d_tile_mol0, uint32_t tile_pairs, unsigned long long *d_err,
+           cudaStream_t st) {
+    LAUNCH(k_local_roff, (n_mol + 1 + 255) / 256, 256, 0, st, d_read_off_global, mol0, n_mol, d_read_off_local);
+    if (n_mol == 0) return;
+    LAUNCH(k_tile_mol0, (n_mol + 255) / 256, 256, 0, st, d_read_off_local, n_mol, tile_pairs, d_tile_mol0);
+    LAUNCH(k_place, (n_mol + 127) / 128, 128, 0, st, sc, d_sch, plan, mol0, n_mol, d_read_off_local, d_ins, d_mol, d_text,
+           text_stride, d_tile_mol0, tile_pairs, d_err);
 }
 
 // ------------------------------------------------------------------------------------------
-// records: shared decode of one read pair
+// records (decode, generic writer, fast path, tile sums, emit kernel): mmk_emit.cuh
 // ------------------------------------------------------------------------------------------
-struct PairDesc {
-    uint32_t mol;        // shard-relative molecule index
-    uint32_t bstart, bend;   // 1-based inclusive insert breakpoints (fit u32: contigs < 2^31)
-    uint32_t d1, d2;     // decimal widths
-    uint32_t hdr;        // header line length incl. '\n'
-    uint32_t sq1, sq2;   // sequence lengths
-    uint32_t len1, len2; // record lengths
-};
+}  // namespace mmkdev
+#include "mmk_emit.cuh"
+namespace mmkdev {
 
-__device__ __forceinline__ uint32_t find_mol(const uint64_t *__restrict__ roff, uint32_t lo, uint32_t hi, uint64_t p) {
-    // largest m in [lo, hi] with roff[m] <= p
-    while (lo < hi) {
-        uint32_t mid = (lo + hi + 1) >> 1;
-        if (roff[mid] <= p) lo = mid; else hi = mid - 1;
-    }
-    return lo;
-}
-
-__device__ __forceinline__ void decode_pair(const EmitArgs &a, uint64_t p, uint32_t m, PairDesc &d, MolRec &mr) {
-    mr = a.mol[m];
-    uint2 in = a.ins[p];
-    d.mol = m;
-    d.bstart = (uint32_t)(mr.start + in.x);
-    d.bend = d.bstart + in.y - 1;
-    d.d1 = ndigits_u32(d.bstart);
-    d.d2 = ndigits_u32(d.bend);
-    d.hdr = mr.prefix_len + d.d1 + 1 + d.d2 + mr.suffix_len;
-    uint32_t n = a.sch[mr.schema].len;
-    d.sq1 = window_len(d.bstart, (int64_t)d.bstart + a.r1 - 1, n, a.strict);
-    d.sq2 = window_len((int64_t)d.bend - a.r2 + 1, d.bend, n, a.strict);
-    d.len1 = d.hdr + a.bclen_inline + d.sq1 + 3 + mr.qual1 + 1;
-    d.len2 = d.hdr + d.sq2 + 3 + mr.qual2 + 1;
-}
-
-// Base (as ASCII) number j of circular_index(seq, a:b), forward orientation.
-__device__ __forceinline__ uint32_t window_pos(int64_t a, int64_t b, uint32_t n, int strict, uint32_t j) {
-    if (strict) {
-        int64_t q = a - 1 + (int64_t)j;  // may be negative when the insert is shorter than R2 near position 1
-        if (q < 0) q += (int64_t)n * ((-q) / (int64_t)n + 1);
-        return (uint32_t)((uint64_t)q % n);
-    }
-    if (b <= (int64_t)n) return (uint32_t)(a - 1 + j);
-    uint32_t part1 = a <= (int64_t)n ? (uint32_t)((int64_t)n - a + 1) : 0u;
-    return j < part1 ? (uint32_t)(a - 1 + j) : j - part1;
-}
-template <int BPB>
-__device__ __forceinline__ uint32_t fetch_code(const uint32_t *__restrict__ w, uint32_t pos) {
-    constexpr uint32_t PER = 32 / BPB;
-    return (__ldg(&w[pos / PER]) >> (BPB * (pos % PER))) & ((1u << BPB) - 1u);
-}
-
-// General byte-wise record writer: any read length, wrap mode, quality length. One warp per record.
-template <int BPB>
-__device__ void write_record_generic(const EmitArgs &a, const PairDesc &d, const MolRec &mr, int rd, uint8_t *out, uint32_t lane) {
-    const uint8_t *tx = a.text + (uint64_t)d.mol * a.text_stride;
-    const SchemaDev &S = a.sch[mr.schema];
-    const uint32_t *hw = a.hap + S.word_off;
-    const uint32_t n = S.len;
-    const uint32_t P = mr.prefix_len, SUF = mr.suffix_len;
-    const uint32_t rd_pos = (a.fq_format == MMK_FMT_HAPLOTAGGING || a.fq_format == MMK_FMT_STANDARD) ? 1u : SUF - 13u;
-    const uint32_t inl = rd == 1 ? (uint32_t)a.bclen_inline : 0u;
-    const uint32_t sq = rd == 1 ? d.sq1 : d.sq2;
-    const uint32_t q = rd == 1 ? mr.qual1 : mr.qual2;
-    const uint32_t len = rd == 1 ? d.len1 : d.len2;
-    const int64_t wa = rd == 1 ? (int64_t)d.bstart : (int64_t)d.bend - a.r2 + 1;
-    const int64_t wb = rd == 1 ? (int64_t)d.bstart + a.r1 - 1 : (int64_t)d.bend;
-    for (uint32_t k0 = lane; k0 < len; k0 += 32) {
-        uint32_t k = k0;
-        uint8_t c;
-        if (k < P) c = tx[k];
-        else if ((k -= P) < d.d1) c = (uint8_t)('0' + (d.bstart / c_pow10[d.d1 - 1 - k]) % 10);
-        else if ((k -= d.d1) == 0) c = ':';
-        else if ((k -= 1) < d.d2) c = (uint8_t)('0' + (d.bend / c_pow10[d.d2 - 1 - k]) % 10);
-        else if ((k -= d.d2) < SUF) c = (k == rd_pos) ? (uint8_t)('0' + rd) : tx[P + k];
-        else if ((k -= SUF) < inl) c = tx[P + 1 + k];
-        else if ((k -= inl) < sq) {
-            uint32_t j = rd == 1 ? sq - 1 - k : k;
-            uint32_t code = fetch_code<BPB>(hw, window_pos(wa, wb, n, a.strict, j));
-            if (BPB == 2) c = (uint8_t)(rd == 1 ? "TGCA"[code] : "ACGT"[code]);
-            else c = (uint8_t)code4_to_ascii(rd == 1 ? comp4(code) : code);
-        } else if ((k -= sq) < 3) c = (uint8_t)(k == 1 ? '+' : '\n');
-        else if ((k -= 3) < q) c = 'I';
-        else c = '\n';
-        out[k0] = c;
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// tile sums: record lengths of every tile of `tile_pairs` pairs
-// ------------------------------------------------------------------------------------------
-__global__ void k_tile_sums(EmitArgs a, uint32_t n_tiles, uint32_t *sum1, uint32_t *sum2, unsigned long long *gather) {
-    __shared__ uint32_t s_m0, s_m1;
-    __shared__ uint32_t s_acc[3];
-    uint32_t tile = blockIdx.x;
-    if (tile >= n_tiles) return;
-    uint64_t p0 = (uint64_t)tile * a.tile_pairs;
-    uint32_t np = (uint32_t)((a.n_pairs - p0) < a.tile_pairs ? (a.n_pairs - p0) : a.tile_pairs);
-    if (threadIdx.x == 0) {
-        s_m0 = find_mol(a.read_off, 0, a.n_mol - 1, p0);
-        s_acc[0] = s_acc[1] = s_acc[2] = 0;
-    }
-    if (threadIdx.x == 32) s_m1 = find_mol(a.read_off, 0, a.n_mol - 1, p0 + np - 1);
-    __syncthreads();
-    uint32_t l1 = 0, l2 = 0, gb = 0;
-    if (threadIdx.x < np) {
-        uint64_t p = p0 + threadIdx.x;
-        uint32_t m = find_mol(a.read_off, s_m0, s_m1, p);
-        PairDesc d;
-        MolRec mr;
-        decode_pair(a, p, m, d, mr);
-        l1 = d.len1;
-        l2 = d.len2;
-        gb = (d.sq1 * a.bpb + 7) / 8 + (d.sq2 * a.bpb + 7) / 8;
-    }
-    for (int o = 16; o; o >>= 1) {
-        l1 += __shfl_down_sync(0xffffffffu, l1, o);
-        l2 += __shfl_down_sync(0xffffffffu, l2, o);
-        gb += __shfl_down_sync(0xffffffffu, gb, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&s_acc[0], l1);
-        atomicAdd(&s_acc[1], l2);
-        atomicAdd(&s_acc[2], gb);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        sum1[tile] = s_acc[0];
-        sum2[tile] = s_acc[1];
-        atomicAdd(gather, (unsigned long long)s_acc[2]);
-    }
-}
 void tile_sums(const EmitArgs &a, uint32_t n_tiles_total, uint32_t *d_sum1, uint32_t *d_sum2, unsigned long long *d_gather,
                cudaStream_t st) {
     if (n_tiles_total == 0) return;
     uint32_t threads = (a.tile_pairs + 31) / 32 * 32;
-    if (threads < 64) threads = 64;
-    k_tile_sums<<<n_tiles_total, threads, 0, st>>>(a, n_tiles_total, d_sum1, d_sum2, d_gather);
+    LAUNCH(k_tile_sums, n_tiles_total, threads, 0, st, a, n_tiles_total, d_sum1, d_sum2, d_gather);
 }
 
 __global__ void k_find_tile(const uint64_t *off1, const uint64_t *off2, uint32_t tile0, uint32_t n_tiles, uint64_t cap,
@@ -811,70 +703,61 @@ __global__ void k_find_tile(const uint64_t *off1, const uint64_t *off2, uint32_t
     }
     out[threadIdx.x] = lo;
 }
+// Chunk table: tile boundaries so that each chunk's R1 and R2 bytes both fit `cap`.
+// bounds[0] = 0, bounds[k+1] = end tile of chunk k; *n_out = number of chunks (0xffffffff if a
+// single tile exceeds cap).
+__global__ void k_chunk_table(const uint64_t *off1, const uint64_t *off2, uint32_t n_tiles, uint64_t cap, uint32_t *bounds,
+                              uint64_t *boff1, uint64_t *boff2, uint32_t max_chunks, uint32_t *n_out) {
+    uint32_t t0 = 0, k = 0;
+    bounds[0] = 0;
+    boff1[0] = off1[0];
+    boff2[0] = off2[0];
+    while (t0 < n_tiles && k < max_chunks) {
+        uint32_t best = n_tiles;
+        for (int r = 0; r < 2; ++r) {
+            const uint64_t *off = r ? off2 : off1;
+            uint64_t base = off[t0];
+            uint32_t lo = t0, hi = n_tiles;
+            while (lo < hi) {
+                uint32_t mid = (uint32_t)(((uint64_t)lo + hi + 1) >> 1);
+                if (off[mid] - base <= cap) lo = mid; else hi = mid - 1;
+            }
+            best = lo < best ? lo : best;
+        }
+        if (best <= t0) {
+            *n_out = 0xffffffffu;
+            return;
+        }
+        bounds[++k] = best;
+        boff1[k] = off1[best];
+        boff2[k] = off2[best];
+        t0 = best;
+    }
+    *n_out = (t0 < n_tiles) ? 0xfffffffeu : k;
+}
+void chunk_table(const uint64_t *d_off1, const uint64_t *d_off2, uint32_t n_tiles, uint64_t cap, uint32_t *d_bounds,
+                 uint64_t *d_boff1, uint64_t *d_boff2, uint32_t max_chunks, uint32_t *d_n, cudaStream_t st) {
+    LAUNCH(k_chunk_table, 1, 1, 0, st, d_off1, d_off2, n_tiles, cap, d_bounds, d_boff1, d_boff2, max_chunks, d_n);
+}
+
 void find_tile(const uint64_t *d_off1, const uint64_t *d_off2, uint32_t tile0, uint32_t n_tiles, uint64_t cap, uint32_t *d_out,
                cudaStream_t st) {
-    k_find_tile<<<1, 32, 0, st>>>(d_off1, d_off2, tile0, n_tiles, cap, d_out);
+    LAUNCH(k_find_tile, 1, 32, 0, st, d_off1, d_off2, tile0, n_tiles, cap, d_out);
 }
 
-// ------------------------------------------------------------------------------------------
-// emit
-// ------------------------------------------------------------------------------------------
-constexpr int EMIT_THREADS = 256;
-constexpr int EMIT_MAX_TP = 64;
-
-template <int BPB>
-__global__ void __launch_bounds__(EMIT_THREADS) k_emit(const __grid_constant__ EmitArgs a) {
-    __shared__ uint32_t s_m0, s_m1;
-    __shared__ PairDesc s_d[EMIT_MAX_TP];
-    __shared__ uint32_t s_off1[EMIT_MAX_TP + 1], s_off2[EMIT_MAX_TP + 1];
-    const uint32_t tile = a.tile0 + blockIdx.x;
-    const uint64_t p0 = (uint64_t)tile * a.tile_pairs;
-    const uint32_t np = (uint32_t)((a.n_pairs - p0) < a.tile_pairs ? (a.n_pairs - p0) : a.tile_pairs);
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_m0 = find_mol(a.read_off, 0, a.n_mol - 1, p0);
-    if (threadIdx.x == 32) s_m1 = find_mol(a.read_off, 0, a.n_mol - 1, p0 + np - 1);
-    __syncthreads();
-    if (threadIdx.x < np) {
-        uint64_t p = p0 + threadIdx.x;
-        uint32_t m = find_mol(a.read_off, s_m0, s_m1, p);
-        PairDesc d;
-        MolRec mr;
-        decode_pair(a, p, m, d, mr);
-        s_d[threadIdx.x] = d;
-    }
-    __syncthreads();
-    // exclusive scan of record lengths within the tile (np <= 64: two items per lane of warp 0)
-    if (warp == 0) {
-        uint32_t a1 = lane * 2 < np ? s_d[lane * 2].len1 : 0, b1 = lane * 2 + 1 < np ? s_d[lane * 2 + 1].len1 : 0;
-        uint32_t a2 = lane * 2 < np ? s_d[lane * 2].len2 : 0, b2 = lane * 2 + 1 < np ? s_d[lane * 2 + 1].len2 : 0;
-        uint32_t x1 = a1 + b1, x2 = a2 + b2;
-        uint32_t i1 = x1, i2 = x2;
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t y1 = __shfl_up_sync(0xffffffffu, i1, o), y2 = __shfl_up_sync(0xffffffffu, i2, o);
-            if (lane >= o) {
-                i1 += y1;
-                i2 += y2;
-            }
-        }
-        uint32_t e1 = i1 - x1, e2 = i2 - x2;
-        if (lane * 2 <= np) { s_off1[lane * 2] = e1; s_off2[lane * 2] = e2; }
-        if (lane * 2 + 1 <= np) { s_off1[lane * 2 + 1] = e1 + a1; s_off2[lane * 2 + 1] = e2 + a2; }
-        if (lane == 31 && np == 64) { s_off1[64] = i1; s_off2[64] = i2; }
-    }
-    __syncthreads();
-    uint8_t *o1 = a.out1 + (a.tile_off1[tile] - a.chunk_off1);
-    uint8_t *o2 = a.out2 + (a.tile_off2[tile] - a.chunk_off2);
-    for (uint32_t t = warp; t < np; t += EMIT_THREADS / 32) {
-        PairDesc d = s_d[t];
-        MolRec mr = a.mol[d.mol];
-        write_record_generic<BPB>(a, d, mr, 1, o1 + s_off1[t], lane);
-        write_record_generic<BPB>(a, d, mr, 2, o2 + s_off2[t], lane);
-    }
-}
 void emit(const EmitArgs &a, cudaStream_t st) {
     if (a.n_tiles == 0) return;
-    if (a.bpb == 2) k_emit<2><<<a.n_tiles, EMIT_THREADS, 0, st>>>(a);
-    else k_emit<4><<<a.n_tiles, EMIT_THREADS, 0, st>>>(a);
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t smem = 2 * (size_t)a.stage_cap + EMIT_WARPS * EMIT_SCR;
+    if (!attr_set[dev & 63]) {
+        cudaFuncSetAttribute(k_emit<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_emit<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr_set[dev & 63] = true;
+    }
+    if (a.bpb == 2) LAUNCH((k_emit<2>), a.n_tiles, EMIT_THREADS, smem, st, a);
+    else LAUNCH((k_emit<4>), a.n_tiles, EMIT_THREADS, smem, st, a);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -882,7 +765,8 @@ void emit(const EmitArgs &a, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------
 template <class R>
 __device__ __forceinline__ void dump_molecule(const SimConst &sc, const SchemaDev *sch, const PlanDev &plan, uint64_t i,
-                                              const uint64_t *roff, uint2 *ins, const uint32_t *epoch_nlive, R &rec) {
+                                              const uint64_t *roff, uint2 *ins, const uint32_t *epoch_nlive,
+                                              const uint32_t *tile_mol0, uint32_t tile_pairs, R &rec) {
     uint64_t g = plan.group[i];
     uint32_t m = plan.slot[i];
     uint32_t seq_len = sch[plan.schema[i]].len;
@@ -894,33 +778,36 @@ __device__ __forceinline__ void dump_molecule(const SimConst &sc, const SchemaDe
     uint32_t molsize, nfrags;
     molecule_shape(sc, g, m, seq_len, molsize, nfrags, rec);
     int64_t start;
-    molecule_place(sc, g, m, seq_len, molsize, nfrags, ins + roff[i], start, rec);
+    TileRef tr{tile_mol0, roff[i], (uint32_t)i, tile_pairs};
+    molecule_place(sc, g, m, seq_len, molsize, nfrags, ins + roff[i], tr, start, rec);
 }
 __global__ void k_dump_count(SimConst sc, const SchemaDev *sch, PlanDev plan, uint64_t n_mol, const uint64_t *roff, uint2 *ins,
-                             const uint32_t *epoch_nlive, uint32_t *counts) {
+                             const uint32_t *epoch_nlive, const uint32_t *tile_mol0, uint32_t tile_pairs, uint32_t *counts) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_mol) return;
     CountRec rec;
-    dump_molecule(sc, sch, plan, i, roff, ins, epoch_nlive, rec);
+    dump_molecule(sc, sch, plan, i, roff, ins, epoch_nlive, tile_mol0, tile_pairs, rec);
     counts[i] = rec.n;
 }
 __global__ void k_dump_write(SimConst sc, const SchemaDev *sch, PlanDev plan, uint64_t n_mol, const uint64_t *roff, uint2 *ins,
-                             const uint32_t *epoch_nlive, const uint64_t *offsets, mmk_variate *out) {
+                             const uint32_t *epoch_nlive, const uint32_t *tile_mol0, uint32_t tile_pairs,
+                             const uint64_t *offsets, mmk_variate *out) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_mol) return;
     WriteRec rec{out + offsets[i]};
-    dump_molecule(sc, sch, plan, i, roff, ins, epoch_nlive, rec);
+    dump_molecule(sc, sch, plan, i, roff, ins, epoch_nlive, tile_mol0, tile_pairs, rec);
 }
 void dump_variates(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t n_mol, const uint64_t *d_read_off,
-                   const uint2 *d_ins, const uint32_t *d_epoch_nlive, const uint16_t *, uint32_t, uint32_t *d_counts,
-                   uint64_t *d_offsets, uint64_t *d_scan_tmp, mmk_variate *d_out, int pass, cudaStream_t st) {
+                   const uint2 *d_ins, const uint32_t *d_epoch_nlive, const uint32_t *d_tile_mol0, uint32_t tile_pairs,
+                   uint32_t *d_counts, uint64_t *d_offsets, uint64_t *d_scan_tmp, mmk_variate *d_out, int pass,
+                   cudaStream_t st) {
     if (n_mol == 0) return;
     unsigned g = (unsigned)((n_mol + 127) / 128);
     if (pass == 0) {
-        k_dump_count<<<g, 128, 0, st>>>(sc, d_sch, plan, n_mol, d_read_off, (uint2 *)d_ins, d_epoch_nlive, d_counts);
+        LAUNCH(k_dump_count, g, 128, 0, st, sc, d_sch, plan, n_mol, d_read_off, (uint2 *)d_ins, d_epoch_nlive, d_tile_mol0, tile_pairs, d_counts);
         exclusive_scan_u32(d_counts, d_offsets, n_mol, d_scan_tmp, st);
     } else {
-        k_dump_write<<<g, 128, 0, st>>>(sc, d_sch, plan, n_mol, d_read_off, (uint2 *)d_ins, d_epoch_nlive, d_offsets, d_out);
+        LAUNCH(k_dump_write, g, 128, 0, st, sc, d_sch, plan, n_mol, d_read_off, (uint2 *)d_ins, d_epoch_nlive, d_tile_mol0, tile_pairs, d_offsets, d_out);
     }
 }
 
@@ -945,10 +832,10 @@ void dump_mask(const char *d_raw_upper, int64_t len, uint64_t seed, uint32_t con
     if (len <= 0) return;
     unsigned g = (unsigned)((len + 255) / 256);
     if (pass == 0) {
-        k_mask_flags<<<g, 256, 0, st>>>(d_raw_upper, len, d_flags);
+        LAUNCH(k_mask_flags, g, 256, 0, st, d_raw_upper, len, d_flags);
         exclusive_scan_u32(d_flags, d_off, (uint64_t)len, d_scan_tmp, st);
     } else {
-        k_mask_write<<<g, 256, 0, st>>>(d_raw_upper, len, seed, contig, hap, d_off, d_out);
+        LAUNCH(k_mask_write, g, 256, 0, st, d_raw_upper, len, seed, contig, hap, d_off, d_out);
     }
 }
 
@@ -956,7 +843,7 @@ void dump_mask(const char *d_raw_upper, int64_t len, uint64_t seed, uint32_t con
 // known-answer hooks
 // ------------------------------------------------------------------------------------------
 __global__ void k_kat_philox(const uint32_t *in6, uint32_t *out4) { mmk_philox4x32_10(in6, in6 + 4, out4); }
-void kat_philox(const uint32_t *d_in6, uint32_t *d_out4, cudaStream_t st) { k_kat_philox<<<1, 1, 0, st>>>(d_in6, d_out4); }
+void kat_philox(const uint32_t *d_in6, uint32_t *d_out4, cudaStream_t st) { LAUNCH(k_kat_philox, 1, 1, 0, st, d_in6, d_out4); }
 
 __global__ void k_kat_math(int kind, const double *in, double *out, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -972,7 +859,7 @@ __global__ void k_kat_math(int kind, const double *in, double *out, int64_t n) {
     }
 }
 void kat_math(int kind, const double *d_in, double *d_out, int64_t n, cudaStream_t st) {
-    if (n > 0) k_kat_math<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(kind, d_in, d_out, n);
+    if (n > 0) LAUNCH(k_kat_math, (unsigned)((n + 127) / 128), 128, 0, st, kind, d_in, d_out, n);
 }
 
 }  // namespace mmkdev

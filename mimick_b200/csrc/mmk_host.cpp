@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -111,14 +112,18 @@ struct mmk_ctx {
     DBuf<uint8_t> d_text;
     DBuf<uint64_t> d_roff_l;
     DBuf<uint64_t> d_tile_off1, d_tile_off2;
-    uint32_t text_stride = 0, tile_pairs = 64, n_tiles = 0;
+    DBuf<uint32_t> d_tile_mol0;
+    uint32_t text_stride = 0, tile_pairs = 64, n_tiles = 0, stage_cap = 0;
+    int32_t fast_ok = 0;
     mmk_place_info place_info{};
 
     // emission
     uint8_t *out[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [slot][read]
     uint64_t out_cap = 0;
-    uint32_t tile_cursor = 0;
+    uint32_t tile_cursor = 0;  // index into chunk_tiles of the next chunk
     int slot = 0;
+    std::vector<uint32_t> chunk_tiles;          // [n_chunks + 1] tile boundaries
+    std::vector<uint64_t> chunk_off1, chunk_off2;  // [n_chunks + 1] byte offsets at those boundaries
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_emit[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
     uint32_t *d_u32x2 = nullptr;
     uint32_t *h_u32x2 = nullptr;  // pinned
@@ -306,6 +311,8 @@ extern "C" int32_t mmk_create(const mmk_params *p, mmk_ctx **out) {
             return fail(ctx, MMK_ERR_UNSUPPORTED,
                         "insert-size truncation keeps <= 30%% of the normal law (insert_length far below 200): not implemented");
     }
+    if ((double)q.insert_length + 13.0 * (double)q.insert_stdev >= 16777215.0)
+        return fail(ctx, MMK_ERR_UNSUPPORTED, "insert lengths of 2^24 bases or more");
     sc.singletons = q.singletons;
     sc.mol_coverage = q.mol_coverage;
     sc.insert_length = q.insert_length;
@@ -381,6 +388,7 @@ static void invalidate_plan(mmk_ctx *c) {
     c->planned = false;
     c->placed = false;
     c->schemas_ready = false;
+    c->schemas.clear();
     c->tile_cursor = 0;
 }
 
@@ -483,6 +491,20 @@ extern "C" int32_t mmk_load_fasta(mmk_ctx *ctx, const char *path, int32_t haplot
     return MMK_OK;
 }
 extern "C" int32_t mmk_n_contigs(const mmk_ctx *c) { return c ? (int32_t)c->contigs.size() : 0; }
+extern "C" int32_t mmk_clear_contigs(mmk_ctx *ctx) {
+    if (!ctx) return MMK_ERR_INVALID_ARG;
+    if (ctx->st) {
+        CU(cudaSetDevice(ctx->par.device));
+        CU(cudaStreamSynchronize(ctx->st));
+    }
+    for (auto &k : ctx->contigs)
+        if (k.d_ascii) cudaFree(k.d_ascii);
+    ctx->contigs.clear();
+    ctx->multi_mode = false;
+    ctx->sc.sample = 0;
+    invalidate_plan(ctx);
+    return MMK_OK;
+}
 
 // upload SchemaDev table
 static int32_t upload_schemas(mmk_ctx *ctx) {
@@ -504,13 +526,17 @@ static int32_t upload_schemas(mmk_ctx *ctx) {
 
 static inline uint64_t words_for(int64_t len, int bpb) {
     uint64_t per = 32 / bpb;
-    uint64_t w = ((uint64_t)len + per - 1) / per + 8;  // 8 pad words: window loads may over-read
+    uint64_t w = ((uint64_t)len + per - 1) / per + 32;  // pad words: the emit kernel's 16-word window loads over-read
     return (w + 3) & ~3ull;                            // 16-byte aligned starts
 }
 
 // single-sample mode: schemas are the contigs, in the order they were added (setup_schema)
 static int32_t finalize_single(mmk_ctx *ctx) {
     if (ctx->schemas_ready) return MMK_OK;
+    if (!ctx->schemas.empty() && ctx->schemas.size() == ctx->contigs.size() && ctx->d_hap.p && !ctx->contigs[0].d_ascii) {
+        ctx->schemas_ready = true;  // arena from an earlier plan is still valid (no contig was added since)
+        return MMK_OK;
+    }
     if (ctx->contigs.empty()) return fail(ctx, MMK_ERR_STATE, "no contigs loaded");
     ctx->bpb = 2;
     for (auto &c : ctx->contigs)
@@ -550,6 +576,11 @@ static int32_t finalize_single(mmk_ctx *ctx) {
     if (ctx->h_stats->first_bad != ~0ull) return fail(ctx, MMK_ERR_BAD_BASE, "unencodable symbol while packing");
     int32_t rc = upload_schemas(ctx);
     if (rc) return rc;
+    // the packed arena is now the only copy a single-sample run needs
+    for (auto &c : ctx->contigs) {
+        cudaFree(c.d_ascii);
+        c.d_ascii = nullptr;
+    }
     ctx->schemas_ready = true;
     return MMK_OK;
 }
@@ -1035,6 +1066,9 @@ static EmitArgs base_args(mmk_ctx *c) {
     a.mol = c->d_mol.p;
     a.text = c->d_text.p;
     a.ins = c->d_ins.p;
+    a.tile_mol0 = c->d_tile_mol0.p;
+    a.stage_cap = c->stage_cap;
+    a.fast_ok = c->fast_ok;
     a.tile_off1 = c->d_tile_off1.p;
     a.tile_off2 = c->d_tile_off2.p;
     a.n_pairs = c->s_npairs;
@@ -1050,6 +1084,8 @@ static EmitArgs base_args(mmk_ctx *c) {
     a.force_generic = c->par.force_generic;
     return a;
 }
+
+static int32_t prepare_chunks(mmk_ctx *ctx);
 
 extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     if (!ctx) return MMK_ERR_INVALID_ARG;
@@ -1083,7 +1119,20 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     size_t max_prefix = 1 + max_name + 1 + hap_digits + 1 + 10 + 1 + 10 + 1;
     if (max_prefix > 200) return fail(ctx, MMK_ERR_UNSUPPORTED, "header prefix longer than 200 bytes");
     ctx->text_stride = (uint32_t)((max_prefix + 36 + 15) & ~15ull);
-    ctx->tile_pairs = 64;
+    {   // tile geometry: the fast path stages one tile of R1 and of R2 text in shared memory
+        const mmk_params &q = ctx->par;
+        uint32_t inl = q.fq_format == MMK_FMT_TENX ? 16u : 0u;
+        uint32_t max_hdr = (uint32_t)max_prefix + 10 + 1 + 10 + 34;
+        uint32_t max_rec = max_hdr + inl + (uint32_t)std::max(q.length_r1, q.length_r2) * 2 + inl + 4;
+        ctx->fast_ok = q.length_r1 >= 16 && q.length_r1 <= 192 && q.length_r2 >= 16 && q.length_r2 <= 192 && !q.force_generic;
+        uint32_t tp = 48;
+        if (const char *e = getenv("MMK_TILE_PAIRS")) tp = (uint32_t)atoi(e);
+        tp = std::max(8u, std::min(64u, tp));
+        while (tp > 8 && (uint64_t)tp * max_rec + 32 > 40 * 1024) tp -= 8;
+        ctx->tile_pairs = tp;
+        ctx->stage_cap = (uint32_t)(((uint64_t)tp * max_rec + 32 + 15) & ~15ull);
+        if (!ctx->fast_ok) ctx->stage_cap = 16;
+    }
 
     CU(ctx->d_ins.ensure(ctx->s_npairs + 1));
     CU(ctx->d_mol.ensure(ctx->s_nmol + 1));
@@ -1093,8 +1142,10 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     CU(d_err.ensure(3));
     unsigned long long init[3] = {~0ull, 0, 0};
     CU(cudaMemcpyAsync(d_err.p, init, sizeof init, cudaMemcpyHostToDevice, ctx->st));
+    ctx->n_tiles = (uint32_t)((ctx->s_npairs + ctx->tile_pairs - 1) / ctx->tile_pairs);
+    CU(ctx->d_tile_mol0.ensure((size_t)ctx->n_tiles + 1));
     place(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->mol0, (uint32_t)ctx->s_nmol, ctx->d_read_off.p, ctx->d_ins.p, ctx->d_mol.p,
-          ctx->d_text.p, ctx->text_stride, ctx->d_roff_l.p, d_err.p, ctx->st);
+          ctx->d_text.p, ctx->text_stride, ctx->d_roff_l.p, ctx->d_tile_mol0.p, ctx->tile_pairs, d_err.p, ctx->st);
     unsigned long long herr[3];
     CU(cudaMemcpyAsync(herr, d_err.p, sizeof herr, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
@@ -1105,7 +1156,6 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
         return fail(ctx, code, "molecule %llu: %s", herr[0], mmk_strerror(code));
     }
     // tile offsets
-    ctx->n_tiles = (uint32_t)((ctx->s_npairs + ctx->tile_pairs - 1) / ctx->tile_pairs);
     DBuf<uint32_t> d_sum1, d_sum2;
     DBuf<uint64_t> d_tmp;
     CU(d_sum1.ensure((size_t)ctx->n_tiles + 1));
@@ -1131,9 +1181,11 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     ctx->place_info.r1_bytes = tot[0];
     ctx->place_info.r2_bytes = tot[1];
     ctx->place_info.gather_bytes = tot[2];
-    ctx->placed = true;
     ctx->tile_cursor = 0;
     ctx->slot = 0;
+    int32_t rc_chunks = prepare_chunks(ctx);
+    if (rc_chunks) return rc_chunks;
+    ctx->placed = true;
     if (out) *out = ctx->place_info;
     return MMK_OK;
 }
@@ -1141,80 +1193,111 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
 // ------------------------------------------------------------------------------------------
 // emission
 // ------------------------------------------------------------------------------------------
-static int32_t ensure_outputs(mmk_ctx *ctx) {
+static uint64_t wanted_slot_bytes(mmk_ctx *ctx) {
     uint64_t want = ctx->par.max_chunk_bytes ? ctx->par.max_chunk_bytes : (8ull << 30);
     uint64_t need = std::max(ctx->place_info.r1_bytes, ctx->place_info.r2_bytes);
     want = std::min(want, need);
     want = std::max<uint64_t>(want, 1 << 20);
-    want = (want + 255) & ~255ull;
-    if (ctx->out_cap >= want) return MMK_OK;
-    free_outputs(ctx);
+    return (want + 255) & ~255ull;
+}
+
+// output ring + chunk table for the placed shard
+static int32_t prepare_chunks(mmk_ctx *ctx) {
+    uint64_t want = wanted_slot_bytes(ctx);
+    uint64_t need = std::max(ctx->place_info.r1_bytes, ctx->place_info.r2_bytes);
     int slots = need <= want ? 1 : 2;  // a single chunk needs no ring
-    for (int s = 0; s < slots; ++s)
-        for (int r = 0; r < 2; ++r) CU(cudaMalloc((void **)&ctx->out[s][r], want + 256));
-    ctx->out_cap = want;
+    bool have = ctx->out_cap >= want && ctx->out[0][0] && (slots == 1 || ctx->out[1][0]);
+    if (!have) {
+        free_outputs(ctx);
+        for (int s = 0; s < slots; ++s)
+            for (int r = 0; r < 2; ++r) CU(cudaMalloc((void **)&ctx->out[s][r], want + 256));
+        ctx->out_cap = want;
+    }
+    const uint32_t max_chunks = 1 << 16;
+    DBuf<uint32_t> d_bounds, d_n;
+    DBuf<uint64_t> d_b1, d_b2;
+    CU(d_bounds.ensure(max_chunks + 1));
+    CU(d_b1.ensure(max_chunks + 1));
+    CU(d_b2.ensure(max_chunks + 1));
+    CU(d_n.ensure(1));
+    ctx->chunk_tiles.assign(1, 0);
+    ctx->chunk_off1.assign(1, 0);
+    ctx->chunk_off2.assign(1, 0);
+    if (ctx->n_tiles == 0) return MMK_OK;
+    chunk_table(ctx->d_tile_off1.p, ctx->d_tile_off2.p, ctx->n_tiles, ctx->out_cap, d_bounds.p, d_b1.p, d_b2.p, max_chunks,
+                d_n.p, ctx->st);
+    uint32_t n = 0;
+    CU(cudaMemcpyAsync(&n, d_n.p, 4, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    if (n == 0xffffffffu) return fail(ctx, MMK_ERR_INVALID_ARG, "max_chunk_bytes is smaller than one tile of records");
+    if (n == 0xfffffffeu) return fail(ctx, MMK_ERR_INVALID_ARG, "max_chunk_bytes gives more than 65536 chunks");
+    ctx->chunk_tiles.resize(n + 1);
+    ctx->chunk_off1.resize(n + 1);
+    ctx->chunk_off2.resize(n + 1);
+    CU(cudaMemcpyAsync(ctx->chunk_tiles.data(), d_bounds.p, (n + 1) * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(ctx->chunk_off1.data(), d_b1.p, (n + 1) * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(ctx->chunk_off2.data(), d_b2.p, (n + 1) * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
     return MMK_OK;
 }
 
-static int32_t emit_next(mmk_ctx *ctx, mmk_chunk *out, bool sync) {
-    if (!ctx->placed) return fail(ctx, MMK_ERR_STATE, "mmk_place has not run");
-    memset(out, 0, sizeof *out);
-    int32_t rc = ensure_outputs(ctx);
-    if (rc) return rc;
-    if (ctx->tile_cursor >= ctx->n_tiles) {
-        out->done = 1;
-        return MMK_OK;
-    }
-    const uint32_t t0 = ctx->tile_cursor;
-    find_tile(ctx->d_tile_off1.p, ctx->d_tile_off2.p, t0, ctx->n_tiles, ctx->out_cap, ctx->d_u32x2, ctx->st);
-    uint64_t offs[4];
-    CU(cudaMemcpyAsync(ctx->h_u32x2, ctx->d_u32x2, 8, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
-    uint32_t t1 = std::min(ctx->h_u32x2[0], ctx->h_u32x2[1]);
-    if (t1 <= t0) return fail(ctx, MMK_ERR_INVALID_ARG, "max_chunk_bytes is smaller than one tile of records");
-    CU(cudaMemcpyAsync(&offs[0], ctx->d_tile_off1.p + t0, 8, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaMemcpyAsync(&offs[1], ctx->d_tile_off1.p + t1, 8, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaMemcpyAsync(&offs[2], ctx->d_tile_off2.p + t0, 8, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaMemcpyAsync(&offs[3], ctx->d_tile_off2.p + t1, 8, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
-    int slot = ctx->out[1][0] ? ctx->slot : 0;
+// enqueue the emit kernel of chunk k into ring slot `slot` (no synchronisation)
+static int32_t launch_chunk(mmk_ctx *ctx, uint32_t k, int slot, mmk_chunk *out) {
+    const uint32_t t0 = ctx->chunk_tiles[k], t1 = ctx->chunk_tiles[k + 1];
     EmitArgs a = base_args(ctx);
     a.out1 = ctx->out[slot][0];
     a.out2 = ctx->out[slot][1];
-    a.chunk_off1 = offs[0];
-    a.chunk_off2 = offs[2];
+    a.chunk_off1 = ctx->chunk_off1[k];
+    a.chunk_off2 = ctx->chunk_off2[k];
     a.tile0 = t0;
     a.n_tiles = t1 - t0;
-    CU(cudaStreamWaitEvent(ctx->st, ctx->ev_copy[slot], 0));  // the slot's previous copy-out must be done
-    CU(cudaEventRecord(ctx->ev_a, ctx->st));
     emit(a, ctx->st);
-    CU(cudaEventRecord(ctx->ev_b, ctx->st));
-    CU(cudaEventRecord(ctx->ev_emit[slot], ctx->st));
-    out->r1_dev = a.out1;
-    out->r2_dev = a.out2;
-    out->r1_bytes = offs[1] - offs[0];
-    out->r2_bytes = offs[3] - offs[2];
-    out->r1_offset = offs[0];
-    out->r2_offset = offs[2];
-    out->first_pair = (int64_t)t0 * ctx->tile_pairs;
-    uint64_t last = std::min<uint64_t>((uint64_t)t1 * ctx->tile_pairs, ctx->s_npairs);
-    out->n_pairs = (int64_t)(last - (uint64_t)out->first_pair);
-    out->slot = slot;
-    ctx->tile_cursor = t1;
-    out->done = t1 >= ctx->n_tiles;
-    ctx->slot ^= 1;
-    if (sync) {
-        CU(cudaStreamSynchronize(ctx->st));
-        CU(cudaGetLastError());
-        CU(cudaEventElapsedTime(&out->kernel_ms, ctx->ev_a, ctx->ev_b));
+    if (out) {
+        memset(out, 0, sizeof *out);
+        out->r1_dev = a.out1;
+        out->r2_dev = a.out2;
+        out->r1_bytes = ctx->chunk_off1[k + 1] - ctx->chunk_off1[k];
+        out->r2_bytes = ctx->chunk_off2[k + 1] - ctx->chunk_off2[k];
+        out->r1_offset = ctx->chunk_off1[k];
+        out->r2_offset = ctx->chunk_off2[k];
+        out->first_pair = (int64_t)t0 * ctx->tile_pairs;
+        uint64_t last = std::min<uint64_t>((uint64_t)t1 * ctx->tile_pairs, ctx->s_npairs);
+        out->n_pairs = (int64_t)(last - (uint64_t)out->first_pair);
+        out->slot = slot;
+        out->done = (k + 2 >= ctx->chunk_tiles.size());
     }
+    return MMK_OK;
+}
+static inline uint32_t n_chunks_of(const mmk_ctx *c) { return (uint32_t)c->chunk_tiles.size() - 1; }
+
+extern "C" int32_t mmk_chunk_layout(mmk_ctx *ctx, uint64_t *slot_bytes, int32_t *n_chunks) {
+    if (!ctx) return MMK_ERR_INVALID_ARG;
+    if (!ctx->placed) return fail(ctx, MMK_ERR_STATE, "mmk_place has not run");
+    if (slot_bytes) *slot_bytes = ctx->out_cap;
+    if (n_chunks) *n_chunks = (int32_t)n_chunks_of(ctx);
     return MMK_OK;
 }
 
 extern "C" int32_t mmk_emit_chunk(mmk_ctx *ctx, mmk_chunk *out) {
     if (!ctx || !out) return MMK_ERR_INVALID_ARG;
+    if (!ctx->placed) return fail(ctx, MMK_ERR_STATE, "mmk_place has not run");
     CU(cudaSetDevice(ctx->par.device));
-    return emit_next(ctx, out, true);
+    memset(out, 0, sizeof *out);
+    if (ctx->tile_cursor >= n_chunks_of(ctx)) {
+        out->done = 1;
+        return MMK_OK;
+    }
+    int slot = ctx->out[1][0] ? ctx->slot : 0;
+    CU(cudaEventRecord(ctx->ev_a, ctx->st));
+    int32_t rc = launch_chunk(ctx, ctx->tile_cursor, slot, out);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev_b, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaGetLastError());
+    CU(cudaEventElapsedTime(&out->kernel_ms, ctx->ev_a, ctx->ev_b));
+    ctx->tile_cursor++;
+    ctx->slot ^= 1;
+    return MMK_OK;
 }
 extern "C" int32_t mmk_rewind(mmk_ctx *ctx) {
     if (!ctx) return MMK_ERR_INVALID_ARG;
@@ -1230,29 +1313,90 @@ extern "C" int32_t mmk_copy_chunk(mmk_ctx *ctx, const mmk_chunk *ch, void *r1_ho
     CU(cudaStreamSynchronize(ctx->st));
     return MMK_OK;
 }
+
+extern "C" int32_t mmk_emit_all(mmk_ctx *ctx, float *kernel_ms) {
+    if (!ctx) return MMK_ERR_INVALID_ARG;
+    if (!ctx->placed) return fail(ctx, MMK_ERR_STATE, "mmk_place has not run");
+    CU(cudaSetDevice(ctx->par.device));
+    const uint32_t n = n_chunks_of(ctx);
+    CU(cudaEventRecord(ctx->ev_a, ctx->st));
+    for (uint32_t k = 0; k < n; ++k) {
+        int32_t rc = launch_chunk(ctx, k, ctx->out[1][0] ? (int)(k & 1) : 0, nullptr);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(ctx->ev_b, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaGetLastError());
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+    if (kernel_ms) *kernel_ms = ms;
+    return MMK_OK;
+}
+
+// Pipelined whole-shard emission: kernel of chunk k+1 overlaps the device→host copy of chunk k.
+// dst(k, r) gives the host address for read r of chunk k; `after(k)` runs once chunk k is in host memory.
+template <class Dst, class After>
+static int32_t emit_pipeline(mmk_ctx *ctx, Dst dst, After after) {
+    const uint32_t n = n_chunks_of(ctx);
+    const bool ring = ctx->out[1][0] != nullptr;
+    std::vector<mmk_chunk> chunks(n);
+    for (uint32_t k = 0; k < n; ++k) {
+        int slot = ring ? (int)(k & 1) : 0;
+        // the device slot is free once the copy of chunk k-2 (same slot) finished
+        if (k >= 2 || !ring) CU(cudaStreamWaitEvent(ctx->st, ctx->ev_copy[slot], 0));
+        int32_t rc = launch_chunk(ctx, k, slot, &chunks[k]);
+        if (rc) return rc;
+        CU(cudaEventRecord(ctx->ev_emit[slot], ctx->st));
+        // host slot of chunk k is reused from chunk k-2: its consumer must have returned
+        if (k >= 1) {
+            CU(cudaEventSynchronize(ctx->ev_copy[(ring ? (k - 1) & 1 : 0)]));
+            rc = after(k - 1, chunks[k - 1]);
+            if (rc) return rc;
+        }
+        CU(cudaStreamWaitEvent(ctx->st_copy, ctx->ev_emit[slot], 0));
+        const mmk_chunk &ch = chunks[k];
+        if (ch.r1_bytes) CU(cudaMemcpyAsync(dst(k, 0, ch), ch.r1_dev, ch.r1_bytes, cudaMemcpyDeviceToHost, ctx->st_copy));
+        if (ch.r2_bytes) CU(cudaMemcpyAsync(dst(k, 1, ch), ch.r2_dev, ch.r2_bytes, cudaMemcpyDeviceToHost, ctx->st_copy));
+        CU(cudaEventRecord(ctx->ev_copy[slot], ctx->st_copy));
+    }
+    CU(cudaStreamSynchronize(ctx->st_copy));
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaGetLastError());
+    if (n >= 1) {
+        int32_t rc = after(n - 1, chunks[n - 1]);
+        if (rc) return rc;
+    }
+    return MMK_OK;
+}
+
 extern "C" int32_t mmk_emit_to_host(mmk_ctx *ctx, void *r1_host, uint64_t r1_cap, void *r2_host, uint64_t r2_cap) {
     if (!ctx || !r1_host || !r2_host) return MMK_ERR_INVALID_ARG;
     if (!ctx->placed) return fail(ctx, MMK_ERR_STATE, "mmk_place has not run");
     if (r1_cap < ctx->place_info.r1_bytes || r2_cap < ctx->place_info.r2_bytes) return fail(ctx, MMK_ERR_INVALID_ARG, "host buffers too small");
     CU(cudaSetDevice(ctx->par.device));
-    mmk_rewind(ctx);
-    for (;;) {
-        mmk_chunk ch;
-        int32_t rc = emit_next(ctx, &ch, false);
-        if (rc) return rc;
-        if (ch.n_pairs == 0 && ch.done) break;
-        // copy stream waits for this chunk's kernel; the next emit into this slot waits for the copy
-        CU(cudaStreamWaitEvent(ctx->st_copy, ctx->ev_emit[ch.slot], 0));
-        CU(cudaMemcpyAsync((char *)r1_host + ch.r1_offset, ch.r1_dev, ch.r1_bytes, cudaMemcpyDeviceToHost, ctx->st_copy));
-        CU(cudaMemcpyAsync((char *)r2_host + ch.r2_offset, ch.r2_dev, ch.r2_bytes, cudaMemcpyDeviceToHost, ctx->st_copy));
-        CU(cudaEventRecord(ctx->ev_copy[ch.slot], ctx->st_copy));
-        if (ch.done) break;
-    }
-    CU(cudaStreamSynchronize(ctx->st_copy));
-    CU(cudaStreamSynchronize(ctx->st));
-    CU(cudaGetLastError());
-    return MMK_OK;
+    return emit_pipeline(
+        ctx, [&](uint32_t, int r, const mmk_chunk &ch) { return r ? (char *)r2_host + ch.r2_offset : (char *)r1_host + ch.r1_offset; },
+        [&](uint32_t, const mmk_chunk &) { return (int32_t)MMK_OK; });
 }
+
+extern "C" int32_t mmk_emit_stream(mmk_ctx *ctx, void *const r1_host[2], void *const r2_host[2], uint64_t slot_cap,
+                                   mmk_chunk_cb cb, void *user) {
+    if (!ctx || !r1_host || !r2_host || !r1_host[0] || !r1_host[1] || !r2_host[0] || !r2_host[1]) return MMK_ERR_INVALID_ARG;
+    if (!ctx->placed) return fail(ctx, MMK_ERR_STATE, "mmk_place has not run");
+    if (slot_cap < std::min<uint64_t>(ctx->out_cap, std::max(ctx->place_info.r1_bytes, ctx->place_info.r2_bytes)))
+        return fail(ctx, MMK_ERR_INVALID_ARG, "host slots are smaller than the device chunk size");
+    CU(cudaSetDevice(ctx->par.device));
+    return emit_pipeline(
+        ctx, [&](uint32_t k, int r, const mmk_chunk &) { return r ? (char *)r2_host[k & 1] : (char *)r1_host[k & 1]; },
+        [&](uint32_t k, const mmk_chunk &ch) {
+            if (!cb) return (int32_t)MMK_OK;
+            int32_t rc = cb(user, &ch, r1_host[k & 1], r2_host[k & 1]);
+            if (rc) return fail(ctx, rc, "chunk consumer returned %d", rc);
+            return (int32_t)MMK_OK;
+        });
+}
+
+extern "C" uint64_t mmk_launch_count(void) { return (uint64_t)launch_count(); }
 
 // ------------------------------------------------------------------------------------------
 // introspection
@@ -1315,7 +1459,7 @@ extern "C" int32_t mmk_dump_inserts(mmk_ctx *ctx, int64_t first, int64_t n, int6
         uint64_t p = (uint64_t)(first + i);
         while (m + 1 < ro.size() && ro[m + 1] <= p) ++m;
         start[i] = mr[m].start + in[i].x;
-        stop[i] = start[i] + in[i].y - 1;
+        stop[i] = start[i] + (in[i].y & 0x00ffffffu) - 1;
     }
     return MMK_OK;
 }
@@ -1331,8 +1475,8 @@ extern "C" int32_t mmk_dump_variates(mmk_ctx *ctx, mmk_variate *out, uint64_t ca
     CU(d_tmp.ensure(ctx->n_mol / 1024 + 8));
     CU(d_nlive.ensure(ctx->epoch_nlive.size() + 1));
     CU(cudaMemcpyAsync(d_nlive.p, ctx->epoch_nlive.data(), ctx->epoch_nlive.size() * 4, cudaMemcpyHostToDevice, ctx->st));
-    dump_variates(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->n_mol, ctx->d_read_off.p, ctx->d_ins.p, d_nlive.p, nullptr, 0,
-                  d_counts.p, d_offsets.p, d_tmp.p, nullptr, 0, ctx->st);
+    dump_variates(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->n_mol, ctx->d_read_off.p, ctx->d_ins.p, d_nlive.p,
+                  ctx->d_tile_mol0.p, ctx->tile_pairs, d_counts.p, d_offsets.p, d_tmp.p, nullptr, 0, ctx->st);
     uint64_t total = 0;
     CU(cudaMemcpyAsync(&total, d_offsets.p + ctx->n_mol, 8, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
@@ -1342,8 +1486,8 @@ extern "C" int32_t mmk_dump_variates(mmk_ctx *ctx, mmk_variate *out, uint64_t ca
     if (cap < total) return fail(ctx, MMK_ERR_INVALID_ARG, "variate buffer too small");
     DBuf<mmk_variate> d_out;
     CU(d_out.ensure(total + 1));
-    dump_variates(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->n_mol, ctx->d_read_off.p, ctx->d_ins.p, d_nlive.p, nullptr, 0,
-                  d_counts.p, d_offsets.p, d_tmp.p, d_out.p, 1, ctx->st);
+    dump_variates(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->n_mol, ctx->d_read_off.p, ctx->d_ins.p, d_nlive.p,
+                  ctx->d_tile_mol0.p, ctx->tile_pairs, d_counts.p, d_offsets.p, d_tmp.p, d_out.p, 1, ctx->st);
     CU(cudaMemcpyAsync(out, d_out.p, total * sizeof(mmk_variate), cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
     CU(cudaGetLastError());

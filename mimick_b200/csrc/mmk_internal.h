@@ -76,6 +76,7 @@ struct EmitArgs {
     const MolRec *mol;
     const uint8_t *text;
     const uint2 *ins;          // (start - mol.start, length) per shard pair
+    const uint32_t *tile_mol0; // [n_tiles] first shard molecule of every tile
     const uint64_t *tile_off1; // [n_tiles + 1] shard-relative byte offsets
     const uint64_t *tile_off2;
     uint8_t *out1, *out2;
@@ -89,6 +90,8 @@ struct EmitArgs {
     int32_t fq_format, bclen_inline;  // bclen_inline = 16 for tenx else 0
     int32_t strict, bpb;
     int32_t force_generic;
+    uint32_t stage_cap;        // bytes of shared-memory stage per stream (fast path)
+    int32_t fast_ok;           // host-level eligibility of the fast path (read lengths, format)
 };
 
 #ifdef __cplusplus
@@ -128,16 +131,20 @@ void shard_bounds(const uint64_t *d_read_off, uint64_t n_mol, uint64_t n_pairs, 
 
 void place(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol,
            const uint64_t *d_read_off_global, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
-           uint64_t *d_read_off_local, unsigned long long *d_err /*[2]: first bad molecule, code*/, cudaStream_t st);
+           uint64_t *d_read_off_local, uint32_t *d_tile_mol0, uint32_t tile_pairs,
+           unsigned long long *d_err /*[0]: first bad molecule*/, cudaStream_t st);
 
 void tile_sums(const EmitArgs &a, uint32_t n_tiles_total, uint32_t *d_sum1, uint32_t *d_sum2, unsigned long long *d_gather,
                cudaStream_t st);
 void find_tile(const uint64_t *d_off1, const uint64_t *d_off2, uint32_t tile0, uint32_t n_tiles, uint64_t cap,
                uint32_t *d_out, cudaStream_t st);
 void emit(const EmitArgs &a, cudaStream_t st);
+void chunk_table(const uint64_t *d_off1, const uint64_t *d_off2, uint32_t n_tiles, uint64_t cap, uint32_t *d_bounds,
+                 uint64_t *d_boff1, uint64_t *d_boff2, uint32_t max_chunks, uint32_t *d_n, cudaStream_t st);
+unsigned long long launch_count();
 
 void dump_variates(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t n_mol, const uint64_t *d_read_off,
-                   const uint2 *d_ins, const uint32_t *d_epoch_nlive, const uint16_t *d_epoch_live, uint32_t live_stride,
+                   const uint2 *d_ins, const uint32_t *d_epoch_nlive, const uint32_t *d_tile_mol0, uint32_t tile_pairs,
                    uint32_t *d_counts, uint64_t *d_offsets, uint64_t *d_scan_tmp, mmk_variate *d_out, int pass,
                    cudaStream_t st);
 void dump_mask(const char *d_raw_upper, int64_t len, uint64_t seed, uint32_t contig, uint32_t hap, uint32_t *d_flags,

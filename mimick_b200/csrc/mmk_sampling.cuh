@@ -144,11 +144,22 @@ __device__ __forceinline__ uint32_t molecule_shape(const SimConst &sc, uint64_t 
     return status;
 }
 
-// Insert lengths (written to ins[i].y), molecule start, gap chain (ins[i].x = start_i - start).
+// Insert lengths, molecule start, gap chain.  Plan entry of insert i:
+//   ins[i].x = start_i - molecule start
+//   ins[i].y = length (low 24 bits) | (molecule index - first molecule of the insert's tile) << 24
+// The tile-relative molecule index lets the emit kernel find a pair's molecule without searching.
+#define MMK_INS_LEN(y) ((y) & 0x00ffffffu)
+#define MMK_INS_DM(y) ((y) >> 24)
+struct TileRef {
+    const uint32_t *tile_mol0;  // first (shard-relative) molecule of every tile
+    uint64_t pair0;             // shard-relative index of this molecule's first pair
+    uint32_t mol;               // shard-relative molecule index
+    uint32_t tile_pairs;
+};
 template <class R>
 __device__ __forceinline__ uint32_t molecule_place(const SimConst &sc, uint64_t g, uint32_t m, uint32_t seq_len,
-                                                   uint32_t molsize, uint32_t nfrags, uint2 *ins, int64_t &start,
-                                                   R &rec) {
+                                                   uint32_t molsize, uint32_t nfrags, uint2 *ins, const TileRef &tr,
+                                                   int64_t &start, R &rec) {
     mmk_stream s;
     mmk_stream_init(&s, sc.seed, sc.sample, MMK_P_INSERT, g, m);
     int attempts = 0;
@@ -169,6 +180,7 @@ __device__ __forceinline__ uint32_t molecule_place(const SimConst &sc, uint64_t 
             }
             sum = MMK_ADD(sum, x);
             uint32_t li = (uint32_t)(long long)x;
+            if (li > 0x00ffffffu) li = 0x00ffffffu;  // unreachable: mmk_create bounds insert_length + 13 sd below 2^24
             ins[i].y = li;
             isum += li;
         }
@@ -199,8 +211,9 @@ __device__ __forceinline__ uint32_t molecule_place(const SimConst &sc, uint64_t 
         uint64_t gap = mmk_next_index(&s, remaining + 1);
         rec.put(MMK_P_GAP, (uint32_t)(remaining + 1), gap);
         uint64_t st = cursor + gap;
-        uint32_t li = ins[i].y;
-        ins[i].x = (uint32_t)st;
+        uint32_t li = MMK_INS_LEN(ins[i].y);
+        uint32_t dm = tr.mol - tr.tile_mol0[(tr.pair0 + i) / tr.tile_pairs];
+        ins[i] = make_uint2((uint32_t)st, li | (dm << 24));
         cursor = st + li;
         remaining -= gap;
     }

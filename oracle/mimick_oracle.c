@@ -89,6 +89,7 @@ typedef struct {
     char *chrom;
     int haplotype;
     char *seq; /* uppercase IUPAC, 0-based storage of a 1-based sequence */
+    int borrowed; /* seq is owned by the caller (large benchmarks share one copy between threads) */
     int64_t len;
     int64_t reads_required, reads_current;
 } orc_schema;
@@ -144,6 +145,9 @@ typedef struct orc_sim {
     size_t n_ins, cap_ins;
     int64_t n_groups;
     int64_t max_pairs; /* optional stop (bench sampling): 0 = run to completion */
+    int discard;       /* bench: recycle the output buffers after every group, count bytes only */
+    uint64_t bytes_r1, bytes_r2;
+    int64_t total_pairs;
     int err;
     char errmsg[256];
 } orc_sim;
@@ -366,7 +370,7 @@ void orc_destroy(orc_sim *s) {
     if (!s) return;
     for (int i = 0; i < s->n_sch; ++i) {
         free(s->sch[i].chrom);
-        free(s->sch[i].seq);
+        if (!s->sch[i].borrowed) free(s->sch[i].seq);
     }
     free(s->sch);
     free(s->r1.p);
@@ -388,6 +392,7 @@ int orc_add_schema(orc_sim *s, const char *chrom, int haplotype, const char *seq
     orc_schema *c = &s->sch[s->n_sch++];
     c->chrom = strdup(chrom);
     c->haplotype = haplotype;
+    c->borrowed = 0;
     c->seq = (char *)malloc((size_t)len + 1);
     memcpy(c->seq, seq, (size_t)len);
     c->seq[len] = 0;
@@ -396,6 +401,24 @@ int orc_add_schema(orc_sim *s, const char *chrom, int haplotype, const char *seq
     c->reads_current = 0;
     return 0;
 }
+/* same, without copying: `seq` must stay valid and already be upper-case IUPAC */
+int orc_add_schema_borrowed(orc_sim *s, const char *chrom, int haplotype, const char *seq, int64_t len, int64_t reads_required) {
+    if (s->n_sch == s->cap_sch) {
+        s->cap_sch = s->cap_sch ? 2 * s->cap_sch : 8;
+        s->sch = (orc_schema *)realloc(s->sch, (size_t)s->cap_sch * sizeof(orc_schema));
+    }
+    orc_schema *c = &s->sch[s->n_sch++];
+    c->chrom = strdup(chrom);
+    c->haplotype = haplotype;
+    c->borrowed = 1;
+    c->seq = (char *)seq;
+    c->len = len;
+    c->reads_required = reads_required;
+    c->reads_current = 0;
+    return 0;
+}
+/* keep only byte counts, not the FASTQ text (long benchmark samples) */
+void orc_set_discard_output(orc_sim *s, int on) { s->discard = on; }
 void orc_set_philox(orc_sim *s, uint64_t seed, uint32_t sample) {
     s->mode = 1;
     s->seed = seed;
@@ -789,6 +812,11 @@ int orc_run(orc_sim *s) {
             if (s->sch[live[i]].reads_current < s->sch[live[i]].reads_required) live[w++] = live[i];
         n_live = w;
         g++;
+        if (s->discard) {
+            s->bytes_r1 += s->r1.n; s->bytes_r2 += s->r2.n;
+            s->r1.n = 0; s->r2.n = 0; s->n_ins = 0; s->n_mols = 0;
+        }
+        s->total_pairs = total_pairs;
         if (s->max_pairs > 0 && total_pairs >= s->max_pairs) break;
     }
     s->n_groups = (int64_t)g;
@@ -800,6 +828,8 @@ int orc_run(orc_sim *s) {
 const uint8_t *orc_r1(const orc_sim *s, size_t *n) { *n = s->r1.n; return s->r1.p; }
 const uint8_t *orc_r2(const orc_sim *s, size_t *n) { *n = s->r2.n; return s->r2.p; }
 int64_t orc_n_groups(const orc_sim *s) { return s->n_groups; }
+int64_t orc_total_pairs(const orc_sim *s) { return s->total_pairs; }
+uint64_t orc_total_bytes(const orc_sim *s) { return s->discard ? s->bytes_r1 + s->bytes_r2 : s->r1.n + s->r2.n; }
 int64_t orc_n_molecules(const orc_sim *s) { return (int64_t)s->n_mols; }
 int64_t orc_n_pairs(const orc_sim *s) { return (int64_t)s->n_ins; }
 const orc_mol *orc_molecules(const orc_sim *s) { return s->mols; }

@@ -103,6 +103,12 @@ def lib():
     L.orc_error_message.argtypes = [vp]
     L.orc_error_message.restype = C.c_char_p
     L.orc_add_schema.argtypes = [vp, C.c_char_p, i32, C.c_char_p, i64, i64]
+    L.orc_add_schema_borrowed.argtypes = [vp, C.c_char_p, i32, vp, i64, i64]
+    L.orc_set_discard_output.argtypes = [vp, i32]
+    L.orc_total_pairs.argtypes = [vp]
+    L.orc_total_pairs.restype = i64
+    L.orc_total_bytes.argtypes = [vp]
+    L.orc_total_bytes.restype = u64
     L.orc_set_philox.argtypes = [vp, u64, u32]
     L.orc_set_replay.argtypes = [vp, vp, sz]
     L.orc_set_record.argtypes = [vp, i32]
@@ -339,6 +345,21 @@ class Oracle:
     def add_schema(self, chrom: str, haplotype: int, seq: bytes, reads_required: int):
         lib().orc_add_schema(self.h, chrom.encode(), int(haplotype), seq, len(seq), int(reads_required))
         self.n_schema += 1
+
+    def add_schema_borrowed(self, chrom: str, haplotype: int, address: int, length: int, reads_required: int):
+        """No copy: `address` must point to upper-case IUPAC bytes that outlive the run."""
+        lib().orc_add_schema_borrowed(self.h, chrom.encode(), int(haplotype), C.c_void_p(address), int(length), int(reads_required))
+        self.n_schema += 1
+
+    def run_counting(self, max_pairs: int):
+        """Bench mode: run until `max_pairs`, discarding the text; returns (pairs, fastq_bytes)."""
+        L = lib()
+        L.orc_set_discard_output(self.h, 1)
+        L.orc_set_max_pairs(self.h, int(max_pairs))
+        rc = L.orc_run(self.h)
+        if rc:
+            raise OracleError(rc, L.orc_error_message(self.h).decode())
+        return int(L.orc_total_pairs(self.h)), int(L.orc_total_bytes(self.h))
 
     @staticmethod
     def mutate(master: bytes, variants):
