@@ -190,50 +190,61 @@ __device__ __forceinline__ uint4 expand16(uint32_t bits, uint32_t lut) {
     return v;
 }
 
-// Copy T bytes of the (4-byte aligned) scratch to stage offset sb: interior words through a
-// funnel shift, the <= 3 + 3 edge bytes one by one.
-__device__ __forceinline__ void copy_header(uint8_t *stage, uint32_t sb, uint32_t T, const uint8_t *scr, uint32_t lane) {
-    const uint32_t a = sb & 3u;
-    const uint32_t head_n = (4u - a) & 3u;
-    uint32_t *dstw = reinterpret_cast<uint32_t *>(stage + (sb - a));
-    const uint32_t *srcw = reinterpret_cast<const uint32_t *>(scr);
-    for (uint32_t w = lane; 4u * w < T + 4u; w += 32) {
-        int o = (int)(4u * w) - (int)a;
-        if (o >= 0 && (uint32_t)o + 4u <= T) {
-            uint32_t i0 = (uint32_t)o >> 2, sh = ((uint32_t)o & 3u) * 8u;
-            dstw[w] = __funnelshift_r(srcw[i0], srcw[i0 + 1], sh);
-        }
-    }
-    const uint32_t ts = T - ((sb + T) & 3u);
-    if (lane < 3) {
-        if (lane < head_n) stage[sb + lane] = scr[lane];
-    } else if (lane >= 4 && lane < 7) {
-        uint32_t i = ts + (lane - 4);
-        if (i < T && i >= head_n) stage[sb + i] = scr[i];
-    }
+// Per-pair parameters of the fast path, computed once by the pair's decode thread and read by the
+// emitting warp with three 16-byte shared-memory loads.
+struct __align__(16) FastDesc {
+    uint32_t sb1, sb2;       // stage byte offsets of the R1 / R2 record
+    uint32_t bstart, bend;
+    uint64_t wbase1, wbase2; // first packed word each half-warp loads (haplotype base + window word)
+    uint32_t mol;
+    uint16_t hdr;            // header length incl. '\n'
+    uint8_t P, SUF;
+    uint8_t d1, d2;
+    uint8_t rel1, rel2;      // window start relative to the first loaded word, in bases (0..30)
+    uint32_t pad;
+};
+static_assert(sizeof(FastDesc) == 48, "FastDesc layout");
+
+__device__ __forceinline__ void make_fast_desc(const EmitArgs &a, const PairDesc &d, uint32_t sb1, uint32_t sb2, FastDesc &f) {
+    f.sb1 = sb1;
+    f.sb2 = sb2;
+    f.bstart = d.bstart;
+    f.bend = d.bend;
+    const uint32_t ws1 = d.bstart - 1u, ws2 = d.bend - (uint32_t)a.r2;  // 0-based window starts
+    const uint32_t wb1 = ws1 >= 15u ? (ws1 - 15u) >> 4 : 0u, wb2 = ws2 >= 15u ? (ws2 - 15u) >> 4 : 0u;
+    f.wbase1 = d.word_off + wb1;
+    f.wbase2 = d.word_off + wb2;
+    f.rel1 = (uint8_t)(ws1 - 16u * wb1);
+    f.rel2 = (uint8_t)(ws2 - 16u * wb2);
+    f.mol = d.mol;
+    f.hdr = (uint16_t)d.hdr;
+    f.P = d.P;
+    f.SUF = d.SUF;
+    f.d1 = d.d1;
+    f.d2 = d.d2;
+    f.pad = 0;
 }
 
 // One read pair, one warp, 2-bit reference, regular pair.
-__device__ __forceinline__ void emit_pair_fast(const EmitArgs &a, const PairDesc &d, uint8_t *stage1, uint8_t *stage2,
-                                               uint32_t sb1, uint32_t sb2, uint8_t *scr, uint32_t lane,
-                                               unsigned long long magic) {
+__device__ __forceinline__ void emit_pair_fast(const EmitArgs &a, const FastDesc &f, uint8_t *stage1, uint8_t *stage2,
+                                               uint8_t *scr, uint32_t lane, unsigned long long magic, uint32_t rd_off) {
     const uint32_t half = lane >> 4, hl = lane & 15u;
     const uint32_t inl = (uint32_t)a.bclen_inline;
+    const uint32_t hdr = f.hdr;
+    const uint32_t S = half ? (uint32_t)a.r2 : (uint32_t)a.r1;
+    uint8_t *stage = half ? stage2 : stage1;
+    const uint32_t seq_off = (half ? f.sb2 : f.sb1 + inl) + hdr;
     // ---- sequences: half-warp 0 → R1 (reverse complement), half-warp 1 → R2 (forward) --------
     {
-        const uint32_t S = half ? (uint32_t)a.r2 : (uint32_t)a.r1;
-        uint8_t *stage = half ? stage2 : stage1;
-        const uint32_t seq_off = half ? sb2 + d.hdr : sb1 + d.hdr + inl;
-        const int ws = half ? (int)(d.bend - (uint32_t)a.r2) : (int)(d.bstart - 1u);  // 0-based window start
-        const int wb = ws >= 15 ? (ws - 15) >> 4 : 0;
-        const uint32_t W = __ldg(a.hap + d.word_off + (uint32_t)wb + hl);
-        const uint32_t c = (seq_off >> 4) + hl, c_last = (seq_off + S - 1u) >> 4;
-        const int k0 = (int)(16u * c) - (int)seq_off;
-        const int q = half ? ws + k0 : ws + (int)S - 1 - k0 - 15;
-        const int j = (q >> 4) - wb;
+        const uint32_t W = __ldg(a.hap + (half ? f.wbase2 : f.wbase1) + hl);
+        const int rel = half ? f.rel2 : f.rel1;
+        const uint32_t c = (seq_off >> 4) + hl;
+        const int k0 = (int)(16u * c) - (int)seq_off;                      // first base index of this chunk (>= -15)
+        const int q = half ? rel + k0 : rel + (int)S - 16 - k0;           // relative to the first loaded word
+        const int j = q >> 4;
         const uint32_t sh = ((uint32_t)q & 15u) * 2u;
-        uint32_t lo = __shfl_sync(0xffffffffu, W, (int)((half << 4) | (uint32_t)(j < 0 ? 0 : (j > 15 ? 15 : j))));
-        uint32_t hi = __shfl_sync(0xffffffffu, W, (int)((half << 4) | (uint32_t)(j + 1 < 0 ? 0 : (j + 1 > 15 ? 15 : j + 1))));
+        uint32_t lo = __shfl_sync(0xffffffffu, W, (int)((lane & 16u) | ((uint32_t)j & 15u)));
+        uint32_t hi = __shfl_sync(0xffffffffu, W, (int)((lane & 16u) | ((uint32_t)(j + 1) & 15u)));
         if (j < 0) lo = 0;
         uint32_t bits = __funnelshift_r(lo, hi, sh);
         if (!half) {
@@ -241,45 +252,44 @@ __device__ __forceinline__ void emit_pair_fast(const EmitArgs &a, const PairDesc
             bits = ((bits >> 1) & 0x55555555u) | ((bits & 0x55555555u) << 1);
         }
         const uint4 v = expand16(bits, half ? 0x54474341u /* "ACGT" */ : 0x41434754u /* "TGCA" */);
-        if (c <= c_last) *reinterpret_cast<uint4 *>(stage + 16u * c) = v;
+        if (16u * c < seq_off + S) *reinterpret_cast<uint4 *>(stage + 16u * c) = v;
     }
     // ---- header scratch: prefix words, digits, suffix bytes -----------------------------------
-    const uint8_t *tx = a.text + (uint64_t)d.mol * a.text_stride;
-    const uint32_t P = d.P, SUF = d.SUF;
-    if (lane < ((P + 3u) >> 2)) reinterpret_cast<uint32_t *>(scr)[lane] = __ldg(reinterpret_cast<const uint32_t *>(tx) + lane);
+    const uint8_t *tx = a.text + (uint64_t)f.mol * a.text_stride;
+    const uint32_t P = f.P, SUF = f.SUF, d1 = f.d1, d2 = f.d2;
+    if (lane < 16) reinterpret_cast<uint32_t *>(scr)[lane] = __ldg(reinterpret_cast<const uint32_t *>(tx) + lane);  // P <= 64
     __syncwarp();
     {
-        const uint32_t first = lane < 10;
-        const uint32_t v = first ? d.bstart : d.bend;
-        const uint32_t kk = first ? lane : lane - 10u;
-        const uint32_t qd = kk == 9u ? v : (uint32_t)__umul64hi((unsigned long long)v, magic);
+        const bool first = lane < 10;
+        const uint32_t v = first ? f.bstart : f.bend;
+        const uint32_t qd = (lane == 9 || lane >= 19) ? v : (uint32_t)__umul64hi((unsigned long long)v, magic);
         const uint32_t dig = qd - 10u * (__umulhi(qd, 0xCCCCCCCDu) >> 3);
-        const uint32_t D = first ? d.d1 : d.d2;
-        const uint32_t base = first ? P : P + d.d1 + 1u;
-        if (lane < 20 && kk + D >= 10u) scr[base + kk + D - 10u] = (uint8_t)('0' + dig);
-        if (lane == 20) scr[P + d.d1] = ':';
-        const uint32_t o = P + d.d1 + 1u + d.d2;
-        for (uint32_t jj = lane; jj < SUF; jj += 32) scr[o + jj] = __ldg(tx + P + jj);
-        if (inl && lane < inl) scr[o + SUF + lane] = __ldg(tx + P + 1u + lane);
+        // digit `lane` (most significant first, 10 wide) lands at base + lane - (10 - D)
+        const int pos = first ? (int)(P + d1 + lane) - 10 : (int)(P + d1 + 1u + d2 + lane) - 20;
+        const int lowest = first ? (int)P : (int)(P + d1 + 1u);
+        if (lane < 20 && pos >= lowest) scr[pos] = (uint8_t)('0' + dig);
+        if (lane == 20) scr[P + d1] = ':';
+        const uint32_t o = P + d1 + 1u + d2;
+        for (uint32_t jj = lane; jj < SUF + inl; jj += 32) scr[o + jj] = __ldg(tx + P + (jj < SUF ? jj : jj - SUF + 1u));
     }
     __syncwarp();
-    copy_header(stage1, sb1, d.hdr + inl, scr, lane);
-    copy_header(stage2, sb2, d.hdr, scr, lane);
-    // ---- bytes after each sequence ("\n+\n", the quality bytes the sequence stores spilled on,
-    //      the final newline) and the read digit of R2 -----------------------------------------
+    // header bytes to both records (consecutive bytes: conflict-free shared-memory traffic)
     {
-        const uint32_t S = half ? (uint32_t)a.r2 : (uint32_t)a.r1;
-        uint8_t *stage = half ? stage2 : stage1;
-        const uint32_t seq_end = (half ? sb2 + d.hdr : sb1 + d.hdr + inl) + S;
-        const uint32_t rec_end = half ? sb2 + d.len2 : sb1 + d.len1;
+        const uint32_t T1 = hdr + inl;
+        for (uint32_t i = lane; i < T1; i += 32) {
+            const uint8_t ch = scr[i];
+            stage1[f.sb1 + i] = ch;
+            if (i < hdr) stage2[f.sb2 + i] = (i == rd_off + P + d1 + 1u + d2) ? (uint8_t)'2' : ch;
+        }
+    }
+    // ---- bytes after each sequence: "\n+\n", the quality bytes the sequence stores spilled on,
+    //      the final newline ---------------------------------------------------------------------
+    {
+        const uint32_t seq_end = seq_off + S;
+        const uint32_t rec_end = seq_end + 3u + S + (half ? 0u : inl) + 1u;
         const uint32_t addr = hl < 15 ? seq_end + hl : rec_end - 1u;
         const uint8_t val = (hl == 0 || hl == 2 || hl == 15) ? '\n' : (hl == 1 ? '+' : 'I');
         stage[addr] = val;
-    }
-    __syncwarp();
-    if (lane == 0) {
-        const uint32_t rd_pos = (a.fq_format == MMK_FMT_HAPLOTAGGING || a.fq_format == MMK_FMT_STANDARD) ? 1u : SUF - 13u;
-        stage2[sb2 + P + d.d1 + 1u + d.d2 + rd_pos] = '2';
     }
     __syncwarp();
 }
@@ -302,6 +312,7 @@ template <int BPB>
 __global__ void __launch_bounds__(EMIT_THREADS, 4) k_emit(const __grid_constant__ EmitArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ PairDesc s_d[EMIT_MAX_TP];
+    __shared__ FastDesc s_f[EMIT_MAX_TP];
     __shared__ uint32_t s_off1[EMIT_MAX_TP + 1], s_off2[EMIT_MAX_TP + 1];
     const uint32_t tile = a.tile0 + blockIdx.x;
     const uint64_t p0 = (uint64_t)tile * a.tile_pairs;
@@ -359,11 +370,16 @@ __global__ void __launch_bounds__(EMIT_THREADS, 4) k_emit(const __grid_constant_
         for (uint32_t j = threadIdx.x; j < n1; j += EMIT_THREADS) reinterpret_cast<uint4 *>(stage1)[j] = fill;
         for (uint32_t j = threadIdx.x; j < n2; j += EMIT_THREADS) reinterpret_cast<uint4 *>(stage2)[j] = fill;
     }
+    if (threadIdx.x < np) make_fast_desc(a, s_d[threadIdx.x], A1 + s_off1[threadIdx.x], A2 + s_off2[threadIdx.x], s_f[threadIdx.x]);
     const uint32_t kk = lane < 10 ? lane : (lane < 20 ? lane - 10u : 9u);
     const unsigned long long magic = c_magic10[kk];
+    const uint32_t rd_off = (a.fq_format == MMK_FMT_HAPLOTAGGING || a.fq_format == MMK_FMT_STANDARD) ? 1u : 0x80000000u;
     __syncthreads();
-    for (uint32_t t = warp; t < np; t += EMIT_WARPS)
-        emit_pair_fast(a, s_d[t], stage1, stage2, A1 + s_off1[t], A2 + s_off2[t], scr, lane, magic);
+    for (uint32_t t = warp; t < np; t += EMIT_WARPS) {
+        const FastDesc f = s_f[t];
+        const uint32_t ro = rd_off == 1u ? 1u : (uint32_t)f.SUF - 13u;
+        emit_pair_fast(a, f, stage1, stage2, scr, lane, magic, ro);
+    }
     __syncthreads();
     copy_out(stage1, A1, bytes1, a.out1 + (g1 - A1));
     copy_out(stage2, A2, bytes2, a.out2 + (g2 - A2));
