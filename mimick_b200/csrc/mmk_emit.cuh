@@ -11,9 +11,9 @@
 //   3. per pair, one warp: each half-warp expands its read from the 2-bit reference — one
 //      32-bit word per lane, shuffles + funnel shift + PRMT lookup — as full 16-byte stores that
 //      may spill garbage up to 15 bytes either side of the sequence;
-//   4. the header (built once per pair in a per-warp scratch, copied with a funnel shift to the
-//      unaligned record start) and the "\n+\n" / first quality bytes are written AFTER the
-//      sequence, so write order — not masks — resolves the overlaps.
+//   4. header bytes are written afterwards, one thread per (pair, header piece), and the
+//      "\n+\n" / first quality bytes right after the sequence: write order — not masks — resolves
+//      every overlap.
 // Anything else (4-bit reference, literal circular wrap, reads outside 16..192, huge headers,
 // force_generic) goes through write_record_generic, straight to global memory.
 #pragma once
@@ -190,20 +190,21 @@ __device__ __forceinline__ uint4 expand16(uint32_t bits, uint32_t lut) {
     return v;
 }
 
-// Per-pair parameters of the fast path, computed once by the pair's decode thread and read by the
-// emitting warp with three 16-byte shared-memory loads.
+// Per-pair parameters of the fast path, computed once by the pair's decode thread and read back
+// with two 16-byte shared-memory loads.
 struct __align__(16) FastDesc {
-    uint32_t sb1, sb2;       // stage byte offsets of the R1 / R2 record
+    uint32_t sb1, sb2;       // stage byte offsets of the R1 / R2 record (stage2 offsets include stage_cap)
     uint32_t bstart, bend;
-    uint64_t wbase1, wbase2; // first packed word each half-warp loads (haplotype base + window word)
+    uint32_t wbase1, wbase2; // first packed word each half-warp loads (arena word index)
     uint32_t mol;
-    uint16_t hdr;            // header length incl. '\n'
-    uint8_t P, SUF;
-    uint8_t d1, d2;
-    uint8_t rel1, rel2;      // window start relative to the first loaded word, in bases (0..30)
-    uint32_t pad;
+    uint32_t pk;             // hdr | P << 8 | SUF << 16 | d1 << 22 | d2 << 26   (hdr <= 255, P <= 64, SUF <= 40)
 };
-static_assert(sizeof(FastDesc) == 48, "FastDesc layout");
+static_assert(sizeof(FastDesc) == 32, "FastDesc layout");
+#define FD_HDR(pk) ((pk) & 0xffu)
+#define FD_P(pk) (((pk) >> 8) & 0xffu)
+#define FD_SUF(pk) (((pk) >> 16) & 0x3fu)
+#define FD_D1(pk) (((pk) >> 22) & 0xfu)
+#define FD_D2(pk) (((pk) >> 26) & 0xfu)
 
 __device__ __forceinline__ void make_fast_desc(const EmitArgs &a, const PairDesc &d, uint32_t sb1, uint32_t sb2, FastDesc &f) {
     f.sb1 = sb1;
@@ -211,36 +212,37 @@ __device__ __forceinline__ void make_fast_desc(const EmitArgs &a, const PairDesc
     f.bstart = d.bstart;
     f.bend = d.bend;
     const uint32_t ws1 = d.bstart - 1u, ws2 = d.bend - (uint32_t)a.r2;  // 0-based window starts
-    const uint32_t wb1 = ws1 >= 15u ? (ws1 - 15u) >> 4 : 0u, wb2 = ws2 >= 15u ? (ws2 - 15u) >> 4 : 0u;
-    f.wbase1 = d.word_off + wb1;
-    f.wbase2 = d.word_off + wb2;
-    f.rel1 = (uint8_t)(ws1 - 16u * wb1);
-    f.rel2 = (uint8_t)(ws2 - 16u * wb2);
+    f.wbase1 = (uint32_t)d.word_off + (ws1 >= 15u ? (ws1 - 15u) >> 4 : 0u);
+    f.wbase2 = (uint32_t)d.word_off + (ws2 >= 15u ? (ws2 - 15u) >> 4 : 0u);
     f.mol = d.mol;
-    f.hdr = (uint16_t)d.hdr;
-    f.P = d.P;
-    f.SUF = d.SUF;
-    f.d1 = d.d1;
-    f.d2 = d.d2;
-    f.pad = 0;
+    f.pk = d.hdr | ((uint32_t)d.P << 8) | ((uint32_t)d.SUF << 16) | ((uint32_t)d.d1 << 22) | ((uint32_t)d.d2 << 26);
 }
 
-// One read pair, one warp, 2-bit reference, regular pair.
-__device__ __forceinline__ void emit_pair_fast(const EmitArgs &a, const FastDesc &f, uint8_t *stage1, uint8_t *stage2,
-                                               uint8_t *scr, uint32_t lane, unsigned long long magic, uint32_t rd_off) {
+// Phase 1 — one read pair, one warp (half-warp 0: R1, reverse complement; half-warp 1: R2, forward):
+// quality chunks, then sequence chunks, then the 15 bytes after the sequence + the final newline.
+// All 16-byte stores are aligned to the stream; what they spill on is rewritten later.
+__device__ __forceinline__ void emit_pair_seq(const EmitArgs &a, const FastDesc &f, uint8_t *smem, uint32_t lane) {
     const uint32_t half = lane >> 4, hl = lane & 15u;
-    const uint32_t inl = (uint32_t)a.bclen_inline;
-    const uint32_t hdr = f.hdr;
+    const uint32_t inl = half ? 0u : (uint32_t)a.bclen_inline;
     const uint32_t S = half ? (uint32_t)a.r2 : (uint32_t)a.r1;
-    uint8_t *stage = half ? stage2 : stage1;
-    const uint32_t seq_off = (half ? f.sb2 : f.sb1 + inl) + hdr;
-    // ---- sequences: half-warp 0 → R1 (reverse complement), half-warp 1 → R2 (forward) --------
+    const uint32_t seq_off = (half ? f.sb2 : f.sb1) + FD_HDR(f.pk) + inl;
+    const uint32_t seq_end = seq_off + S;
+    const uint32_t rec_end = seq_end + 3u + S + inl + 1u;
+    // reference window: one packed word per lane of the half-warp
+    const uint32_t ws = half ? f.bend - (uint32_t)a.r2 : f.bstart - 1u;
+    const int rel = (int)(ws >= 15u ? ((ws - 15u) & 15u) + 15u : ws);     // window start relative to the first word
+    const uint32_t W = __ldg(a.hap + (half ? f.wbase2 : f.wbase1) + hl);
+    // quality: 'I' over every 16-byte chunk that touches [seq_end + 3, rec_end)
     {
-        const uint32_t W = __ldg(a.hap + (half ? f.wbase2 : f.wbase1) + hl);
-        const int rel = half ? f.rel2 : f.rel1;
+        const uint32_t c = ((seq_end + 3u) >> 4) + hl;
+        const uint4 fill = make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u);
+        if (16u * c < rec_end) *reinterpret_cast<uint4 *>(smem + 16u * c) = fill;
+    }
+    __syncwarp();
+    {
         const uint32_t c = (seq_off >> 4) + hl;
-        const int k0 = (int)(16u * c) - (int)seq_off;                      // first base index of this chunk (>= -15)
-        const int q = half ? rel + k0 : rel + (int)S - 16 - k0;           // relative to the first loaded word
+        const int k0 = (int)(16u * c) - (int)seq_off;                     // first base index of this chunk (>= -15)
+        const int q = half ? rel + k0 : rel + (int)S - 16 - k0;          // in bases from the first loaded word
         const int j = q >> 4;
         const uint32_t sh = ((uint32_t)q & 15u) * 2u;
         uint32_t lo = __shfl_sync(0xffffffffu, W, (int)((lane & 16u) | ((uint32_t)j & 15u)));
@@ -252,59 +254,73 @@ __device__ __forceinline__ void emit_pair_fast(const EmitArgs &a, const FastDesc
             bits = ((bits >> 1) & 0x55555555u) | ((bits & 0x55555555u) << 1);
         }
         const uint4 v = expand16(bits, half ? 0x54474341u /* "ACGT" */ : 0x41434754u /* "TGCA" */);
-        if (16u * c < seq_off + S) *reinterpret_cast<uint4 *>(stage + 16u * c) = v;
-    }
-    // ---- header scratch: prefix words, digits, suffix bytes -----------------------------------
-    const uint8_t *tx = a.text + (uint64_t)f.mol * a.text_stride;
-    const uint32_t P = f.P, SUF = f.SUF, d1 = f.d1, d2 = f.d2;
-    if (lane < 16) reinterpret_cast<uint32_t *>(scr)[lane] = __ldg(reinterpret_cast<const uint32_t *>(tx) + lane);  // P <= 64
-    __syncwarp();
-    {
-        const bool first = lane < 10;
-        const uint32_t v = first ? f.bstart : f.bend;
-        const uint32_t qd = (lane == 9 || lane >= 19) ? v : (uint32_t)__umul64hi((unsigned long long)v, magic);
-        const uint32_t dig = qd - 10u * (__umulhi(qd, 0xCCCCCCCDu) >> 3);
-        // digit `lane` (most significant first, 10 wide) lands at base + lane - (10 - D)
-        const int pos = first ? (int)(P + d1 + lane) - 10 : (int)(P + d1 + 1u + d2 + lane) - 20;
-        const int lowest = first ? (int)P : (int)(P + d1 + 1u);
-        if (lane < 20 && pos >= lowest) scr[pos] = (uint8_t)('0' + dig);
-        if (lane == 20) scr[P + d1] = ':';
-        const uint32_t o = P + d1 + 1u + d2;
-        for (uint32_t jj = lane; jj < SUF + inl; jj += 32) scr[o + jj] = __ldg(tx + P + (jj < SUF ? jj : jj - SUF + 1u));
+        if (16u * c < seq_end) *reinterpret_cast<uint4 *>(smem + 16u * c) = v;
     }
     __syncwarp();
-    // header bytes to both records (consecutive bytes: conflict-free shared-memory traffic)
     {
-        const uint32_t T1 = hdr + inl;
-        for (uint32_t i = lane; i < T1; i += 32) {
-            const uint8_t ch = scr[i];
-            stage1[f.sb1 + i] = ch;
-            if (i < hdr) stage2[f.sb2 + i] = (i == rd_off + P + d1 + 1u + d2) ? (uint8_t)'2' : ch;
-        }
-    }
-    // ---- bytes after each sequence: "\n+\n", the quality bytes the sequence stores spilled on,
-    //      the final newline ---------------------------------------------------------------------
-    {
-        const uint32_t seq_end = seq_off + S;
-        const uint32_t rec_end = seq_end + 3u + S + (half ? 0u : inl) + 1u;
         const uint32_t addr = hl < 15 ? seq_end + hl : rec_end - 1u;
         const uint8_t val = (hl == 0 || hl == 2 || hl == 15) ? '\n' : (hl == 1 ? '+' : 'I');
-        stage[addr] = val;
+        smem[addr] = val;
     }
-    __syncwarp();
+}
+
+// Phase 2 — header bytes, one thread per (pair, piece), straight into both stages. Records are
+// ~93 words apart, so the 32 pairs of a warp hit 32 different banks.
+__device__ __forceinline__ void emit_header_piece(const EmitArgs &a, const FastDesc &f, uint8_t *smem, uint32_t role,
+                                                  uint32_t rd_off) {
+    const uint32_t P = FD_P(f.pk), SUF = FD_SUF(f.pk), d1 = FD_D1(f.pk), d2 = FD_D2(f.pk);
+    const uint8_t *tx = a.text + (uint64_t)f.mol * a.text_stride;
+    if (role == 0) {  // "@chrom:hap|start:end|"
+        const uint32_t *tw = reinterpret_cast<const uint32_t *>(tx);
+        for (uint32_t w = 0; 4u * w < P; ++w) {
+            uint32_t x = __ldg(tw + w);
+#pragma unroll
+            for (uint32_t b = 0; b < 4; ++b) {
+                if (4u * w + b < P) {
+                    smem[f.sb1 + 4u * w + b] = (uint8_t)x;
+                    smem[f.sb2 + 4u * w + b] = (uint8_t)x;
+                }
+                x >>= 8;
+            }
+        }
+    } else if (role == 3) {  // format tail, read digit patched for R2; inline barcode for 10x R1
+        const uint32_t o = P + d1 + 1u + d2;
+        for (uint32_t i = 0; i < SUF; ++i) {
+            const uint8_t ch = __ldg(tx + P + i);
+            smem[f.sb1 + o + i] = ch;
+            smem[f.sb2 + o + i] = i == rd_off ? (uint8_t)'2' : ch;
+        }
+        for (uint32_t i = 0; i < (uint32_t)a.bclen_inline; ++i) smem[f.sb1 + o + SUF + i] = __ldg(tx + P + 1u + i);
+    } else {  // decimal insert breakpoints and the ':' between them
+        uint32_t v = role == 1 ? f.bstart : f.bend;
+        const uint32_t D = role == 1 ? d1 : d2;
+        const uint32_t o = role == 1 ? P : P + d1 + 1u;
+        for (uint32_t k = D; k-- > 0;) {
+            const uint32_t q = __umulhi(v, 0xCCCCCCCDu) >> 3;
+            const uint8_t ch = (uint8_t)('0' + (v - 10u * q));
+            smem[f.sb1 + o + k] = ch;
+            smem[f.sb2 + o + k] = ch;
+            v = q;
+        }
+        if (role == 1) {
+            smem[f.sb1 + P + d1] = ':';
+            smem[f.sb2 + P + d1] = ':';
+        }
+    }
 }
 
 // stage → global: aligned 16-byte stores of the stream; the two partial chunks byte-wise
 __device__ __forceinline__ void copy_out(const uint8_t *stage, uint32_t A, uint32_t bytes, uint8_t *gbase) {
-    const uint32_t n16 = (A + bytes + 15u) >> 4;
-    for (uint32_t j = threadIdx.x; j < n16; j += EMIT_THREADS) {
-        const uint32_t lo = 16u * j, hi = lo + 16u;
-        if (lo >= A && hi <= A + bytes) {
-            __stcs(reinterpret_cast<uint4 *>(gbase + lo), *reinterpret_cast<const uint4 *>(stage + lo));
-        } else {
-            const uint32_t b0 = lo > A ? lo : A, b1 = hi < A + bytes ? hi : A + bytes;
-            for (uint32_t b = b0; b < b1; ++b) gbase[b] = stage[b];
-        }
+    const uint32_t end = A + bytes;
+    const uint32_t c0 = (A + 15u) >> 4, c1 = end >> 4;  // full chunks [c0, c1)
+    for (uint32_t j = c0 + threadIdx.x; j < c1; j += EMIT_THREADS)
+        __stcs(reinterpret_cast<uint4 *>(gbase + 16u * j), *reinterpret_cast<const uint4 *>(stage + 16u * j));
+    if (threadIdx.x < 16) {  // head bytes [A, min(16*c0, end))
+        const uint32_t b = A + threadIdx.x;
+        if (b < 16u * c0 && b < end) gbase[b] = stage[b];
+    } else if (threadIdx.x < 32) {  // tail bytes [max(16*c1, 16*c0), end)
+        const uint32_t b = 16u * c1 + (threadIdx.x - 16u);
+        if (c1 >= c0 && b < end) gbase[b] = stage[b];
     }
 }
 
@@ -353,7 +369,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 4) k_emit(const __grid_constant_
     const uint64_t g1 = a.tile_off1[tile] - a.chunk_off1, g2 = a.tile_off2[tile] - a.chunk_off2;
     const uint32_t bytes1 = s_off1[np], bytes2 = s_off2[np];
     const uint32_t A1 = (uint32_t)(g1 & 15u), A2 = (uint32_t)(g2 & 15u);
-    const bool fast = BPB == 2 && a.fast_ok && all_regular && A1 + bytes1 + 16u <= a.stage_cap && A2 + bytes2 + 16u <= a.stage_cap;
+    const bool fast = BPB == 2 && a.fast_ok && all_regular && A1 + bytes1 + 32u <= a.stage_cap && A2 + bytes2 + 32u <= a.stage_cap;
     if (!fast) {
         uint8_t *o1 = a.out1 + g1, *o2 = a.out2 + g2;
         for (uint32_t t = warp; t < np; t += EMIT_WARPS) {
@@ -363,26 +379,23 @@ __global__ void __launch_bounds__(EMIT_THREADS, 4) k_emit(const __grid_constant_
         }
         return;
     }
-    uint8_t *stage1 = smem, *stage2 = smem + a.stage_cap, *scr = smem + 2u * a.stage_cap + warp * EMIT_SCR;
-    {   // quality bytes for free: pre-fill both stages with 'I'
-        const uint4 fill = make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u);
-        const uint32_t n1 = (A1 + bytes1 + 15u) >> 4, n2 = (A2 + bytes2 + 15u) >> 4;
-        for (uint32_t j = threadIdx.x; j < n1; j += EMIT_THREADS) reinterpret_cast<uint4 *>(stage1)[j] = fill;
-        for (uint32_t j = threadIdx.x; j < n2; j += EMIT_THREADS) reinterpret_cast<uint4 *>(stage2)[j] = fill;
-    }
-    if (threadIdx.x < np) make_fast_desc(a, s_d[threadIdx.x], A1 + s_off1[threadIdx.x], A2 + s_off2[threadIdx.x], s_f[threadIdx.x]);
-    const uint32_t kk = lane < 10 ? lane : (lane < 20 ? lane - 10u : 9u);
-    const unsigned long long magic = c_magic10[kk];
-    const uint32_t rd_off = (a.fq_format == MMK_FMT_HAPLOTAGGING || a.fq_format == MMK_FMT_STANDARD) ? 1u : 0x80000000u;
+    // stage1 = smem[0, stage_cap), stage2 = smem[stage_cap, 2 stage_cap): record offsets index smem directly
+    if (threadIdx.x < np)
+        make_fast_desc(a, s_d[threadIdx.x], A1 + s_off1[threadIdx.x], a.stage_cap + A2 + s_off2[threadIdx.x], s_f[threadIdx.x]);
     __syncthreads();
-    for (uint32_t t = warp; t < np; t += EMIT_WARPS) {
-        const FastDesc f = s_f[t];
-        const uint32_t ro = rd_off == 1u ? 1u : (uint32_t)f.SUF - 13u;
-        emit_pair_fast(a, f, stage1, stage2, scr, lane, magic, ro);
+    for (uint32_t t = warp; t < np; t += EMIT_WARPS) emit_pair_seq(a, s_f[t], smem, lane);
+    __syncthreads();
+    {
+        const uint32_t role = threadIdx.x >> 6, t = threadIdx.x & 63u;  // 4 pieces x up to 64 pairs
+        if (t < np) {
+            const FastDesc f = s_f[t];
+            const uint32_t rd_off = (a.fq_format == MMK_FMT_HAPLOTAGGING || a.fq_format == MMK_FMT_STANDARD) ? 1u : FD_SUF(f.pk) - 13u;
+            emit_header_piece(a, f, smem, role, rd_off);
+        }
     }
     __syncthreads();
-    copy_out(stage1, A1, bytes1, a.out1 + (g1 - A1));
-    copy_out(stage2, A2, bytes2, a.out2 + (g2 - A2));
+    copy_out(smem, A1, bytes1, a.out1 + (g1 - A1));
+    copy_out(smem + a.stage_cap, A2, bytes2, a.out2 + (g2 - A2));
 }
 
 }  // namespace mmkdev
