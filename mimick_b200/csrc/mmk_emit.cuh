@@ -192,7 +192,7 @@ __device__ __forceinline__ uint4 expand16(uint32_t bits, uint32_t lut) {
 
 // Per-pair parameters of the fast path, computed once by the pair's decode thread and read back
 // with two 16-byte shared-memory loads.
-struct __align__(16) FastDesc {
+struct FastDesc {
     uint32_t sb1, sb2;       // stage byte offsets of the R1 / R2 record (stage2 offsets include stage_cap)
     uint32_t bstart, bend;
     uint32_t wbase1, wbase2; // first packed word each half-warp loads (arena word index)
@@ -200,6 +200,15 @@ struct __align__(16) FastDesc {
     uint32_t pk;             // hdr | P << 8 | SUF << 16 | d1 << 22 | d2 << 26   (hdr <= 255, P <= 64, SUF <= 40)
 };
 static_assert(sizeof(FastDesc) == 32, "FastDesc layout");
+// kept in shared memory as two uint4 arrays (16-byte stride: conflict-free writes, broadcast reads)
+__device__ __forceinline__ FastDesc load_fast_desc(const uint4 *fa, const uint4 *fb, uint32_t t) {
+    const uint4 x = fa[t], y = fb[t];
+    FastDesc f;
+    f.sb1 = x.x; f.sb2 = x.y; f.bstart = x.z; f.bend = x.w;
+    f.wbase1 = y.x; f.wbase2 = y.y; f.mol = y.z; f.pk = y.w;
+    return f;
+}
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #define FD_HDR(pk) ((pk) & 0xffu)
 #define FD_P(pk) (((pk) >> 8) & 0xffu)
 #define FD_SUF(pk) (((pk) >> 16) & 0x3fu)
@@ -327,27 +336,33 @@ __device__ __forceinline__ void copy_out(const uint8_t *stage, uint32_t A, uint3
 template <int BPB>
 __global__ void __launch_bounds__(EMIT_THREADS, 4) k_emit(const __grid_constant__ EmitArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ PairDesc s_d[EMIT_MAX_TP];
-    __shared__ FastDesc s_f[EMIT_MAX_TP];
+    __shared__ uint4 s_fa[EMIT_MAX_TP], s_fb[EMIT_MAX_TP];
     __shared__ uint32_t s_off1[EMIT_MAX_TP + 1], s_off2[EMIT_MAX_TP + 1];
     const uint32_t tile = a.tile0 + blockIdx.x;
     const uint64_t p0 = (uint64_t)tile * a.tile_pairs;
     const uint32_t np = (uint32_t)((a.n_pairs - p0) < a.tile_pairs ? (a.n_pairs - p0) : a.tile_pairs);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t regular = 1;
+    const uint32_t tile_m0 = a.tile_mol0[tile];
+    // ---- decode: one thread per pair, descriptor stays in registers ---------------------------
+    PairDesc d;
+    d.regular = 1;
+    d.len1 = d.len2 = 0;
     if (threadIdx.x < np) {
-        PairDesc d;
-        decode_pair(a, p0 + threadIdx.x, a.tile_mol0[tile], d);
-        s_d[threadIdx.x] = d;
-        regular = d.regular;
+        decode_pair(a, p0 + threadIdx.x, tile_m0, d);
+        if (BPB == 2 && d.regular) {  // start the loads phases 1 and 2 will need
+            const uint32_t ws1 = d.bstart - 1u, ws2 = d.bend - (uint32_t)a.r2;
+            const uint32_t *w1 = a.hap + d.word_off + (ws1 >= 15u ? (ws1 - 15u) >> 4 : 0u);
+            const uint32_t *w2 = a.hap + d.word_off + (ws2 >= 15u ? (ws2 - 15u) >> 4 : 0u);
+            prefetch_l1(w1);
+            prefetch_l1(w1 + 15);
+            prefetch_l1(w2);
+            prefetch_l1(w2 + 15);
+            prefetch_l1(a.text + (uint64_t)d.mol * a.text_stride);
+        }
     }
-    const int all_regular = __syncthreads_and((int)regular);
-    // exclusive scan of record lengths within the tile (np <= 64: two items per lane of warp 0)
-    if (warp == 0) {
-        uint32_t a1 = lane * 2 < np ? s_d[lane * 2].len1 : 0, b1 = lane * 2 + 1 < np ? s_d[lane * 2 + 1].len1 : 0;
-        uint32_t a2 = lane * 2 < np ? s_d[lane * 2].len2 : 0, b2 = lane * 2 + 1 < np ? s_d[lane * 2 + 1].len2 : 0;
-        uint32_t x1 = a1 + b1, x2 = a2 + b2;
-        uint32_t i1 = x1, i2 = x2;
+    // exclusive scan of record lengths within the tile (np <= 64: warps 0 and 1 hold the items)
+    if (threadIdx.x < EMIT_MAX_TP) {
+        uint32_t i1 = d.len1, i2 = d.len2;
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t y1 = __shfl_up_sync(0xffffffffu, i1, o), y2 = __shfl_up_sync(0xffffffffu, i2, o);
             if (lane >= o) {
@@ -355,40 +370,49 @@ __global__ void __launch_bounds__(EMIT_THREADS, 4) k_emit(const __grid_constant_
                 i2 += y2;
             }
         }
-        uint32_t e1 = i1 - x1, e2 = i2 - x2;
-        s_off1[lane * 2] = e1;
-        s_off2[lane * 2] = e2;
-        s_off1[lane * 2 + 1] = e1 + a1;
-        s_off2[lane * 2 + 1] = e2 + a2;
-        if (lane == 31) {
-            s_off1[64] = i1;
-            s_off2[64] = i2;
-        }
+        s_off1[threadIdx.x + 1] = i1;  // inclusive, per warp; warp 1 is rebased below
+        s_off2[threadIdx.x + 1] = i2;
+        if (threadIdx.x == 0) s_off1[0] = s_off2[0] = 0;
     }
-    __syncthreads();
+    const int all_regular = __syncthreads_and((int)d.regular);
+    const uint32_t base1 = threadIdx.x >= 32 ? s_off1[32] : 0u, base2 = threadIdx.x >= 32 ? s_off2[32] : 0u;
+    const uint32_t off1 = (threadIdx.x < EMIT_MAX_TP ? s_off1[threadIdx.x + 1] - d.len1 : 0u) + base1;
+    const uint32_t off2 = (threadIdx.x < EMIT_MAX_TP ? s_off2[threadIdx.x + 1] - d.len2 : 0u) + base2;
+    const uint32_t bytes1 = s_off1[32] + s_off1[64], bytes2 = s_off2[32] + s_off2[64];
     const uint64_t g1 = a.tile_off1[tile] - a.chunk_off1, g2 = a.tile_off2[tile] - a.chunk_off2;
-    const uint32_t bytes1 = s_off1[np], bytes2 = s_off2[np];
     const uint32_t A1 = (uint32_t)(g1 & 15u), A2 = (uint32_t)(g2 & 15u);
     const bool fast = BPB == 2 && a.fast_ok && all_regular && A1 + bytes1 + 32u <= a.stage_cap && A2 + bytes2 + 32u <= a.stage_cap;
     if (!fast) {
+        // general path: every record byte-wise, straight to global memory (warp per pair)
+        __syncthreads();
+        if (threadIdx.x < np) {
+            s_off1[threadIdx.x] = off1;
+            s_off2[threadIdx.x] = off2;
+        }
+        __syncthreads();
         uint8_t *o1 = a.out1 + g1, *o2 = a.out2 + g2;
         for (uint32_t t = warp; t < np; t += EMIT_WARPS) {
-            PairDesc d = s_d[t];
-            write_record_generic<BPB>(a, d, 1, o1 + s_off1[t], lane);
-            write_record_generic<BPB>(a, d, 2, o2 + s_off2[t], lane);
+            PairDesc e;
+            decode_pair(a, p0 + t, tile_m0, e);
+            write_record_generic<BPB>(a, e, 1, o1 + s_off1[t], lane);
+            write_record_generic<BPB>(a, e, 2, o2 + s_off2[t], lane);
         }
         return;
     }
     // stage1 = smem[0, stage_cap), stage2 = smem[stage_cap, 2 stage_cap): record offsets index smem directly
-    if (threadIdx.x < np)
-        make_fast_desc(a, s_d[threadIdx.x], A1 + s_off1[threadIdx.x], a.stage_cap + A2 + s_off2[threadIdx.x], s_f[threadIdx.x]);
+    if (threadIdx.x < np) {
+        FastDesc f;
+        make_fast_desc(a, d, A1 + off1, a.stage_cap + A2 + off2, f);
+        s_fa[threadIdx.x] = make_uint4(f.sb1, f.sb2, f.bstart, f.bend);
+        s_fb[threadIdx.x] = make_uint4(f.wbase1, f.wbase2, f.mol, f.pk);
+    }
     __syncthreads();
-    for (uint32_t t = warp; t < np; t += EMIT_WARPS) emit_pair_seq(a, s_f[t], smem, lane);
+    for (uint32_t t = warp; t < np; t += EMIT_WARPS) emit_pair_seq(a, load_fast_desc(s_fa, s_fb, t), smem, lane);
     __syncthreads();
     {
         const uint32_t role = threadIdx.x >> 6, t = threadIdx.x & 63u;  // 4 pieces x up to 64 pairs
         if (t < np) {
-            const FastDesc f = s_f[t];
+            const FastDesc f = load_fast_desc(s_fa, s_fb, t);
             const uint32_t rd_off = (a.fq_format == MMK_FMT_HAPLOTAGGING || a.fq_format == MMK_FMT_STANDARD) ? 1u : FD_SUF(f.pk) - 13u;
             emit_header_piece(a, f, smem, role, rd_off);
         }

@@ -1126,7 +1126,7 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
         uint32_t max_rec = max_hdr + inl + (uint32_t)std::max(q.length_r1, q.length_r2) * 2 + inl + 4;
         ctx->fast_ok = q.length_r1 >= 16 && q.length_r1 <= 192 && q.length_r2 >= 16 && q.length_r2 <= 192 && !q.force_generic &&
                        ctx->d_hap.cap < (1ull << 32);  // the fast path indexes the arena with 32-bit word offsets
-        uint32_t tp = 48;
+        uint32_t tp = 64;
         if (const char *e = getenv("MMK_TILE_PAIRS")) tp = (uint32_t)atoi(e);
         tp = std::max(8u, std::min(64u, tp));
         while (tp > 8 && (uint64_t)tp * max_rec + 32 > 40 * 1024) tp -= 8;
