@@ -167,26 +167,31 @@ __constant__ unsigned long long c_magic10[10] = {18446744074ull, 184467440738ull
                                                  184467440737096ull, 1844674407370956ull, 18446744073709552ull,
                                                  184467440737095517ull, 1844674407370955162ull, 0ull};
 
-// 16 bases (32 bits, base i in bits 2i..2i+1) → 16 ASCII bytes through a 4-entry byte LUT
+// 16 bases (32 bits, base i in bits 2i..2i+1) → 16 ASCII bytes through a 4-entry byte LUT.
+// `bits & 0x33333333` already has the even bases as PRMT selectors (one nibble each), `bits >> 2`
+// the odd ones; four lookups and four interleaving PRMTs give the 16 bytes in order.
 __device__ __forceinline__ uint4 expand16(uint32_t bits, uint32_t lut) {
+    const uint32_t ev = bits & 0x33333333u, od = (bits >> 2) & 0x33333333u;
+    const uint32_t e_lo = __byte_perm(lut, 0, ev), e_hi = __byte_perm(lut, 0, ev >> 16);  // bases 0,2,4,6 / 8,10,12,14
+    const uint32_t o_lo = __byte_perm(lut, 0, od), o_hi = __byte_perm(lut, 0, od >> 16);  // bases 1,3,5,7 / 9,11,13,15
     uint4 v;
-    uint32_t b, t;
-    b = bits & 0xffu;
-    t = (b | (b << 4)) & 0x0f0fu;
-    t = (t | (t << 2)) & 0x3333u;
-    v.x = __byte_perm(lut, 0, t);
-    b = (bits >> 8) & 0xffu;
-    t = (b | (b << 4)) & 0x0f0fu;
-    t = (t | (t << 2)) & 0x3333u;
-    v.y = __byte_perm(lut, 0, t);
-    b = (bits >> 16) & 0xffu;
-    t = (b | (b << 4)) & 0x0f0fu;
-    t = (t | (t << 2)) & 0x3333u;
-    v.z = __byte_perm(lut, 0, t);
-    b = bits >> 24;
-    t = (b | (b << 4)) & 0x0f0fu;
-    t = (t | (t << 2)) & 0x3333u;
-    v.w = __byte_perm(lut, 0, t);
+    v.x = __byte_perm(e_lo, o_lo, 0x5140);
+    v.y = __byte_perm(e_lo, o_lo, 0x7362);
+    v.z = __byte_perm(e_hi, o_hi, 0x5140);
+    v.w = __byte_perm(e_hi, o_hi, 0x7362);
+    return v;
+}
+
+// shared memory through 32-bit window addresses (computed once per kernel)
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
 
@@ -230,7 +235,7 @@ __device__ __forceinline__ void make_fast_desc(const EmitArgs &a, const PairDesc
 // Phase 1 — one read pair, one warp (half-warp 0: R1, reverse complement; half-warp 1: R2, forward):
 // quality chunks, then sequence chunks, then the 15 bytes after the sequence + the final newline.
 // All 16-byte stores are aligned to the stream; what they spill on is rewritten later.
-__device__ __forceinline__ void emit_pair_seq(const EmitArgs &a, const FastDesc &f, uint8_t *smem, uint32_t lane) {
+__device__ __forceinline__ void emit_pair_seq(const EmitArgs &a, const FastDesc &f, uint32_t smem, uint32_t lane) {
     const uint32_t half = lane >> 4, hl = lane & 15u;
     const uint32_t inl = half ? 0u : (uint32_t)a.bclen_inline;
     const uint32_t S = half ? (uint32_t)a.r2 : (uint32_t)a.r1;
@@ -245,7 +250,7 @@ __device__ __forceinline__ void emit_pair_seq(const EmitArgs &a, const FastDesc 
     {
         const uint32_t c = ((seq_end + 3u) >> 4) + hl;
         const uint4 fill = make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u);
-        if (16u * c < rec_end) *reinterpret_cast<uint4 *>(smem + 16u * c) = fill;
+        if (16u * c < rec_end) sts128(smem + 16u * c, fill);
     }
     __syncwarp();
     {
@@ -263,22 +268,23 @@ __device__ __forceinline__ void emit_pair_seq(const EmitArgs &a, const FastDesc 
             bits = ((bits >> 1) & 0x55555555u) | ((bits & 0x55555555u) << 1);
         }
         const uint4 v = expand16(bits, half ? 0x54474341u /* "ACGT" */ : 0x41434754u /* "TGCA" */);
-        if (16u * c < seq_end) *reinterpret_cast<uint4 *>(smem + 16u * c) = v;
+        if (16u * c < seq_end) sts128(smem + 16u * c, v);
     }
     __syncwarp();
     {
         const uint32_t addr = hl < 15 ? seq_end + hl : rec_end - 1u;
-        const uint8_t val = (hl == 0 || hl == 2 || hl == 15) ? '\n' : (hl == 1 ? '+' : 'I');
-        smem[addr] = val;
+        const uint32_t val = (hl == 0 || hl == 2 || hl == 15) ? '\n' : (hl == 1 ? '+' : 'I');
+        sts8(smem + addr, val);
     }
 }
 
 // Phase 2 — header bytes, one thread per (pair, piece), straight into both stages. Records are
 // ~93 words apart, so the 32 pairs of a warp hit 32 different banks.
-__device__ __forceinline__ void emit_header_piece(const EmitArgs &a, const FastDesc &f, uint8_t *smem, uint32_t role,
+__device__ __forceinline__ void emit_header_piece(const EmitArgs &a, const FastDesc &f, uint32_t smem, uint32_t role,
                                                   uint32_t rd_off) {
     const uint32_t P = FD_P(f.pk), SUF = FD_SUF(f.pk), d1 = FD_D1(f.pk), d2 = FD_D2(f.pk);
     const uint8_t *tx = a.text + (uint64_t)f.mol * a.text_stride;
+    const uint32_t s1 = smem + f.sb1, s2 = smem + f.sb2;
     if (role == 0) {  // "@chrom:hap|start:end|"
         const uint32_t *tw = reinterpret_cast<const uint32_t *>(tx);
         for (uint32_t w = 0; 4u * w < P; ++w) {
@@ -286,8 +292,8 @@ __device__ __forceinline__ void emit_header_piece(const EmitArgs &a, const FastD
 #pragma unroll
             for (uint32_t b = 0; b < 4; ++b) {
                 if (4u * w + b < P) {
-                    smem[f.sb1 + 4u * w + b] = (uint8_t)x;
-                    smem[f.sb2 + 4u * w + b] = (uint8_t)x;
+                    sts8(s1 + 4u * w + b, x);
+                    sts8(s2 + 4u * w + b, x);
                 }
                 x >>= 8;
             }
@@ -295,42 +301,50 @@ __device__ __forceinline__ void emit_header_piece(const EmitArgs &a, const FastD
     } else if (role == 3) {  // format tail, read digit patched for R2; inline barcode for 10x R1
         const uint32_t o = P + d1 + 1u + d2;
         for (uint32_t i = 0; i < SUF; ++i) {
-            const uint8_t ch = __ldg(tx + P + i);
-            smem[f.sb1 + o + i] = ch;
-            smem[f.sb2 + o + i] = i == rd_off ? (uint8_t)'2' : ch;
+            const uint32_t ch = __ldg(tx + P + i);
+            sts8(s1 + o + i, ch);
+            sts8(s2 + o + i, i == rd_off ? (uint32_t)'2' : ch);
         }
-        for (uint32_t i = 0; i < (uint32_t)a.bclen_inline; ++i) smem[f.sb1 + o + SUF + i] = __ldg(tx + P + 1u + i);
+        for (uint32_t i = 0; i < (uint32_t)a.bclen_inline; ++i) sts8(s1 + o + SUF + i, __ldg(tx + P + 1u + i));
     } else {  // decimal insert breakpoints and the ':' between them
         uint32_t v = role == 1 ? f.bstart : f.bend;
         const uint32_t D = role == 1 ? d1 : d2;
         const uint32_t o = role == 1 ? P : P + d1 + 1u;
         for (uint32_t k = D; k-- > 0;) {
             const uint32_t q = __umulhi(v, 0xCCCCCCCDu) >> 3;
-            const uint8_t ch = (uint8_t)('0' + (v - 10u * q));
-            smem[f.sb1 + o + k] = ch;
-            smem[f.sb2 + o + k] = ch;
+            const uint32_t ch = '0' + (v - 10u * q);
+            sts8(s1 + o + k, ch);
+            sts8(s2 + o + k, ch);
             v = q;
         }
         if (role == 1) {
-            smem[f.sb1 + P + d1] = ':';
-            smem[f.sb2 + P + d1] = ':';
+            sts8(s1 + P + d1, ':');
+            sts8(s2 + P + d1, ':');
         }
     }
 }
 
-// stage → global: aligned 16-byte stores of the stream; the two partial chunks byte-wise
-__device__ __forceinline__ void copy_out(const uint8_t *stage, uint32_t A, uint32_t bytes, uint8_t *gbase) {
+// stage → global.  The 16-byte aligned interior of the tile goes out as ONE bulk asynchronous copy
+// (TMA engine, cp.async.bulk shared::cta → global) issued by thread 0; the partial chunks at the two
+// ends, which neighbouring tiles share, are written byte-wise.
+__device__ __forceinline__ void bulk_store(uint8_t *gdst, uint32_t ssrc, uint32_t nbytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void copy_out_edges(uint32_t stage, uint32_t A, uint32_t bytes, uint8_t *gbase, uint32_t tid) {
     const uint32_t end = A + bytes;
     const uint32_t c0 = (A + 15u) >> 4, c1 = end >> 4;  // full chunks [c0, c1)
-    for (uint32_t j = c0 + threadIdx.x; j < c1; j += EMIT_THREADS)
-        __stcs(reinterpret_cast<uint4 *>(gbase + 16u * j), *reinterpret_cast<const uint4 *>(stage + 16u * j));
-    if (threadIdx.x < 16) {  // head bytes [A, min(16*c0, end))
-        const uint32_t b = A + threadIdx.x;
-        if (b < 16u * c0 && b < end) gbase[b] = stage[b];
-    } else if (threadIdx.x < 32) {  // tail bytes [max(16*c1, 16*c0), end)
-        const uint32_t b = 16u * c1 + (threadIdx.x - 16u);
-        if (c1 >= c0 && b < end) gbase[b] = stage[b];
+    if (tid < 16) {  // head bytes [A, min(16 c0, end))
+        const uint32_t b = A + tid;
+        if (b < 16u * c0 && b < end) gbase[b] = (uint8_t)lds8(stage + b);
+    } else if (tid < 32) {  // tail bytes [16 c1, end) when the tile reaches past its first chunk
+        const uint32_t b = 16u * c1 + (tid - 16u);
+        if (c1 >= c0 && b < end) gbase[b] = (uint8_t)lds8(stage + b);
     }
+}
+__device__ __forceinline__ void copy_out_bulk(uint32_t stage, uint32_t A, uint32_t bytes, uint8_t *gbase) {
+    const uint32_t end = A + bytes;
+    const uint32_t c0 = (A + 15u) >> 4, c1 = end >> 4;
+    if (c1 > c0) bulk_store(gbase + 16u * c0, stage + 16u * c0, 16u * (c1 - c0));
 }
 
 template <int BPB>
@@ -406,20 +420,29 @@ __global__ void __launch_bounds__(EMIT_THREADS, 4) k_emit(const __grid_constant_
         s_fa[threadIdx.x] = make_uint4(f.sb1, f.sb2, f.bstart, f.bend);
         s_fb[threadIdx.x] = make_uint4(f.wbase1, f.wbase2, f.mol, f.pk);
     }
+    const uint32_t sm = (uint32_t)__cvta_generic_to_shared(smem);
     __syncthreads();
-    for (uint32_t t = warp; t < np; t += EMIT_WARPS) emit_pair_seq(a, load_fast_desc(s_fa, s_fb, t), smem, lane);
+    for (uint32_t t = warp; t < np; t += EMIT_WARPS) emit_pair_seq(a, load_fast_desc(s_fa, s_fb, t), sm, lane);
     __syncthreads();
     {
         const uint32_t role = threadIdx.x >> 6, t = threadIdx.x & 63u;  // 4 pieces x up to 64 pairs
         if (t < np) {
             const FastDesc f = load_fast_desc(s_fa, s_fb, t);
             const uint32_t rd_off = (a.fq_format == MMK_FMT_HAPLOTAGGING || a.fq_format == MMK_FMT_STANDARD) ? 1u : FD_SUF(f.pk) - 13u;
-            emit_header_piece(a, f, smem, role, rd_off);
+            emit_header_piece(a, f, sm, role, rd_off);
         }
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes → visible to the bulk copy
     __syncthreads();
-    copy_out(smem, A1, bytes1, a.out1 + (g1 - A1));
-    copy_out(smem + a.stage_cap, A2, bytes2, a.out2 + (g2 - A2));
+    uint8_t *gb1 = a.out1 + (g1 - A1), *gb2 = a.out2 + (g2 - A2);
+    if (threadIdx.x == 0) {
+        copy_out_bulk(sm, A1, bytes1, gb1);
+        copy_out_bulk(sm + a.stage_cap, A2, bytes2, gb2);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    if (warp == 1) copy_out_edges(sm, A1, bytes1, gb1, lane);
+    if (warp == 2) copy_out_edges(sm + a.stage_cap, A2, bytes2, gb2, lane);
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // stage must outlive the copy
 }
 
 }  // namespace mmkdev
