@@ -289,12 +289,15 @@ def cuda_arm(args):
         ms = sim.emit_all()
         allc = exchange(place)
         state.update(plan=plan, place=place, all=allc)
+        state["plan_ms"] = state.get("plan_ms", 0.0) + plan.host_ms
+        state["place_ms"] = state.get("place_ms", 0.0) + place.host_ms
         return ms
 
     # ---- device-resident pass: `value` ------------------------------------------------------
     load_inputs()
     for _ in range(args.warmup):
         step_resident()
+    state["plan_ms"] = state["place_ms"] = 0.0
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -397,6 +400,8 @@ def cuda_arm(args):
             "wall_s_timed_region": wall,
             "plan": {"groups": int(state["plan"].n_groups), "epochs": int(state["plan"].n_epochs),
                      "batches": int(state["plan"].n_batches)},
+            "phase_ms_per_step": {"plan": state["plan_ms"] / args.steps, "place": state["place_ms"] / args.steps,
+                                  "emit": emit_ms / args.steps},
         }
         print(json.dumps(line))
     if world > 1:

@@ -174,6 +174,7 @@ typedef struct mmk_plan_info {
     int64_t n_pairs;
     int64_t n_epochs;        /* pruning points */
     int64_t n_batches;
+    double host_ms;          /* wall time of the call (kernels + control round trips) */
 } mmk_plan_info;
 int32_t mmk_plan(mmk_ctx *ctx, mmk_plan_info *out);
 
@@ -190,6 +191,8 @@ typedef struct mmk_place_info {
     int64_t first_pair, n_pairs;
     uint64_t r1_bytes, r2_bytes; /* total FASTQ bytes of this shard */
     uint64_t gather_bytes;       /* packed reference bytes the extraction reads (algorithmic) */
+    double host_ms;              /* wall time of the call */
+    double phase_ms[4];          /* device time: placement, tile sums + scans, chunk table, (unused) */
 } mmk_place_info;
 int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out);
 

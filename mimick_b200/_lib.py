@@ -45,12 +45,13 @@ class SchemaInfo(C.Structure):
 
 class PlanInfo(C.Structure):
     _fields_ = [("n_groups", C.c_int64), ("n_molecules", C.c_int64), ("n_pairs", C.c_int64),
-                ("n_epochs", C.c_int64), ("n_batches", C.c_int64)]
+                ("n_epochs", C.c_int64), ("n_batches", C.c_int64), ("host_ms", C.c_double)]
 
 
 class PlaceInfo(C.Structure):
     _fields_ = [("first_molecule", C.c_int64), ("n_molecules", C.c_int64), ("first_pair", C.c_int64),
-                ("n_pairs", C.c_int64), ("r1_bytes", C.c_uint64), ("r2_bytes", C.c_uint64), ("gather_bytes", C.c_uint64)]
+                ("n_pairs", C.c_int64), ("r1_bytes", C.c_uint64), ("r2_bytes", C.c_uint64), ("gather_bytes", C.c_uint64),
+                ("host_ms", C.c_double), ("phase_ms", C.c_double * 4)]
 
 
 class Chunk(C.Structure):

@@ -611,11 +611,43 @@ __global__ void k_tile_mol0(const uint64_t *__restrict__ roff_l, uint32_t n_mol,
     for (uint64_t t = (lo + tile_pairs - 1) / tile_pairs; t * tile_pairs < hi; ++t) tile_mol0[t] = m;
 }
 
-__global__ void k_place(SimConst sc, const SchemaDev *__restrict__ sch, PlanDev plan, uint64_t mol0, uint32_t n_mol,
-                        const uint64_t *__restrict__ roff_l, uint2 *ins, MolRec *mol, uint8_t *text, uint32_t text_stride,
-                        const uint32_t *__restrict__ tile_mol0, uint32_t tile_pairs, unsigned long long *err) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_mol) return;
+// Placement, step 1 — one thread per read pair: the insert length of redraw round 0 and the 64
+// random bits of the pair's gap draw.  Everything that needs a transcendental or a Philox block is
+// here, flat over pairs, so it runs without divergence.
+__global__ void k_insert_draws(SimConst sc, PlanDev plan, uint64_t mol0, uint32_t n_mol, const uint64_t *__restrict__ roff_l,
+                               const uint32_t *__restrict__ tile_mol0, uint32_t n_tiles, uint32_t tile_pairs, uint64_t pair_lo,
+                               uint64_t pair_hi, double *__restrict__ tmp_x, uint64_t *__restrict__ tmp_g, uint2 *ins) {
+    uint64_t p = pair_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pair_hi) return;
+    uint32_t tile = (uint32_t)(p / tile_pairs);
+    uint32_t m_lo = tile_mol0[tile], lo = m_lo, hi = tile + 1 < n_tiles ? tile_mol0[tile + 1] : n_mol - 1;
+    while (lo < hi) {  // largest m with roff_l[m] <= p
+        uint32_t mid = (lo + hi + 1) >> 1;
+        if (roff_l[mid] <= p) lo = mid; else hi = mid - 1;
+    }
+    uint32_t i = (uint32_t)(p - roff_l[lo]);
+    uint64_t g = plan.group[mol0 + lo];
+    uint32_t m = plan.slot[mol0 + lo];
+    NoRec rec;
+    double x = draw_insert(sc, g, m, 0, i, rec);
+    mmk_stream gs;
+    mmk_stream_init(&gs, sc.seed, sc.sample, MMK_P_GAP, g, m);
+    tmp_x[p - pair_lo] = x;
+    tmp_g[p - pair_lo] = mmk_stream_at(&gs, i);
+    uint32_t li = (uint32_t)(long long)x;
+    if (li > 0x00ffffffu) li = 0x00ffffffu;
+    ins[p].y = li | ((lo - m_lo) << 24);
+}
+
+// Placement, step 2 — one thread per molecule: the left-to-right float sum of the insert lengths and
+// its redraw rule (Breakpoints.jl:209-212), the start draw (:240), the serial gap chain (:27-33), the
+// window checks, the header text and the per-molecule record.
+__global__ void k_place_chain(SimConst sc, const SchemaDev *__restrict__ sch, PlanDev plan, uint64_t mol0, uint32_t m_lo,
+                              uint32_t m_hi, const uint64_t *__restrict__ roff_l, uint64_t pair_lo,
+                              const double *__restrict__ tmp_x, const uint64_t *__restrict__ tmp_g, uint2 *ins, MolRec *mol,
+                              uint8_t *text, uint32_t text_stride, unsigned long long *err) {
+    uint32_t i = m_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m_hi) return;
     uint64_t gi = mol0 + i;
     uint64_t ro = roff_l[i];
     uint64_t g = plan.group[gi];
@@ -623,13 +655,52 @@ __global__ void k_place(SimConst sc, const SchemaDev *__restrict__ sch, PlanDev 
     uint32_t t = plan.schema[gi];
     uint32_t molsize = plan.size[gi], nfrags = plan.nfrags[gi];
     const SchemaDev &S = sch[t];
+    const uint32_t n = S.len;
+    const double *xs = tmp_x + (ro - pair_lo);
+    const uint64_t *gb = tmp_g + (ro - pair_lo);
+    uint2 *in = ins + ro;
     NoRec rec;
-    int64_t start;
-    TileRef tr{tile_mol0, ro, i, tile_pairs};
-    uint32_t status = molecule_place(sc, g, m, S.len, molsize, nfrags, ins + ro, tr, start, rec);
-    uint32_t n = S.len;
+    // float sum in insert order; whole-vector redraws while it exceeds the molecule
+    double sum = 0.0;
+    uint64_t isum = 0;
+    for (uint32_t k = 0; k < nfrags; ++k) {
+        double x = xs[k];
+        sum = MMK_ADD(sum, x);
+        isum += (uint32_t)(long long)x;
+    }
+    int attempts = 0;
+    while (sum > (double)molsize && attempts < sc.attempts) {
+        ++attempts;
+        sum = 0.0;
+        isum = 0;
+        for (uint32_t k = 0; k < nfrags; ++k) {
+            double x = draw_insert(sc, g, m, (uint32_t)attempts, k, rec);
+            sum = MMK_ADD(sum, x);
+            uint32_t li = (uint32_t)(long long)x;
+            if (li > 0x00ffffffu) li = 0x00ffffffu;
+            in[k].y = li | (in[k].y & 0xff000000u);
+            isum += li;
+        }
+    }
+    uint32_t status = sum > (double)molsize ? (uint32_t)MMK_ERR_INSERTS_UNFITTABLE : 0u;
+    // start_pos = rand(1:adjusted_end)
+    uint64_t adjusted_end = sc.circular ? (uint64_t)n : (n > molsize + 1u ? (uint64_t)(n - molsize) : 1ull);
+    mmk_stream s;
+    mmk_stream_init(&s, sc.seed, sc.sample, MMK_P_START, g, m);
+    int64_t start = (int64_t)mmk_next_index(&s, adjusted_end) + 1;
     uint32_t q1 = 0, q2 = 0;
-    if (!status) status = check_windows(ins + ro, nfrags, start, n, sc.r1, sc.r2, sc.strict, q1, q2);
+    if (!status) {
+        uint64_t remaining = (uint64_t)molsize + 1 - isum, cursor = 0;
+        for (uint32_t k = 0; k < nfrags; ++k) {
+            uint64_t gap = mmk_bits_to_index(gb[k], remaining + 1);
+            uint64_t st = cursor + gap;
+            uint32_t li = MMK_INS_LEN(in[k].y);
+            in[k].x = (uint32_t)st;
+            cursor = st + li;
+            remaining -= gap;
+        }
+        status = check_windows(in, nfrags, start, n, sc.r1, sc.r2, sc.strict, q1, q2);
+    }
     if (sc.fq_format == MMK_FMT_TENX) q1 += 16;
     if (status) {
         atomicMin(&err[0], (unsigned long long)gi);
@@ -666,15 +737,26 @@ __global__ void k_place(SimConst sc, const SchemaDev *__restrict__ sch, PlanDev 
     r.qual2 = q2;
     mol[i] = r;
 }
-void place(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol,
-           const uint64_t *d_read_off_global, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
-           uint64_t *d_read_off_local, uint32_t *d_tile_mol0, uint32_t tile_pairs, unsigned long long *d_err,
-           cudaStream_t st) {
+
+void place_prepare(uint64_t mol0, uint32_t n_mol, const uint64_t *d_read_off_global, uint64_t *d_read_off_local,
+                   uint32_t *d_tile_mol0, uint32_t tile_pairs, cudaStream_t st) {
     LAUNCH(k_local_roff, (n_mol + 1 + 255) / 256, 256, 0, st, d_read_off_global, mol0, n_mol, d_read_off_local);
     if (n_mol == 0) return;
     LAUNCH(k_tile_mol0, (n_mol + 255) / 256, 256, 0, st, d_read_off_local, n_mol, tile_pairs, d_tile_mol0);
-    LAUNCH(k_place, (n_mol + 127) / 128, 128, 0, st, sc, d_sch, plan, mol0, n_mol, d_read_off_local, d_ins, d_mol, d_text,
-           text_stride, d_tile_mol0, tile_pairs, d_err);
+}
+
+// one segment: pairs [pair_lo, pair_hi) = the pairs of molecules [m_lo, m_hi)
+void place_segment(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint32_t m_lo,
+                   uint32_t m_hi, uint64_t pair_lo, uint64_t pair_hi, const uint64_t *d_read_off_local,
+                   const uint32_t *d_tile_mol0, uint32_t n_tiles, uint32_t tile_pairs, double *d_tmp_x, uint64_t *d_tmp_g,
+                   uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride, unsigned long long *d_err,
+                   cudaStream_t st) {
+    if (m_hi <= m_lo) return;
+    uint64_t np = pair_hi - pair_lo;
+    if (np) LAUNCH(k_insert_draws, (unsigned)((np + 255) / 256), 256, 0, st, sc, plan, mol0, n_mol, d_read_off_local, d_tile_mol0,
+                   n_tiles, tile_pairs, pair_lo, pair_hi, d_tmp_x, d_tmp_g, d_ins);
+    LAUNCH(k_place_chain, (m_hi - m_lo + 127) / 128, 128, 0, st, sc, d_sch, plan, mol0, m_lo, m_hi, d_read_off_local, pair_lo,
+           d_tmp_x, d_tmp_g, d_ins, d_mol, d_text, text_stride, d_err);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <random>
 #include <string>
@@ -113,6 +114,8 @@ struct mmk_ctx {
     DBuf<uint64_t> d_roff_l;
     DBuf<uint64_t> d_tile_off1, d_tile_off2;
     DBuf<uint32_t> d_tile_mol0;
+    DBuf<double> d_tmp_x;     // placement scratch: round-0 insert lengths of one segment
+    DBuf<uint64_t> d_tmp_g;   // placement scratch: gap-draw bits of one segment
     uint32_t text_stride = 0, tile_pairs = 64, n_tiles = 0, stage_cap = 0;
     int32_t fast_ok = 0;
     mmk_place_info place_info{};
@@ -919,8 +922,13 @@ static int32_t plan_reserve(mmk_ctx *ctx, uint64_t n, uint64_t keep) {
     return MMK_OK;
 }
 
+static inline double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 extern "C" int32_t mmk_plan(mmk_ctx *ctx, mmk_plan_info *out) {
     if (!ctx) return MMK_ERR_INVALID_ARG;
+    const double t_begin = now_ms();
     if (!ctx->st) return fail(ctx, MMK_ERR_STATE, "context was not created successfully");
     CU(cudaSetDevice(ctx->par.device));
     if (!ctx->multi_mode) {
@@ -1041,6 +1049,7 @@ extern "C" int32_t mmk_plan(mmk_ctx *ctx, mmk_plan_info *out) {
     ctx->plan_info.n_pairs = (int64_t)total;
     ctx->plan_info.n_epochs = n_epochs;
     ctx->plan_info.n_batches = n_batches;
+    ctx->plan_info.host_ms = now_ms() - t_begin;
     if (out) *out = ctx->plan_info;
     return MMK_OK;
 }
@@ -1091,9 +1100,11 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     if (!ctx) return MMK_ERR_INVALID_ARG;
     if (!ctx->planned) return fail(ctx, MMK_ERR_STATE, "mmk_plan has not run");
     CU(cudaSetDevice(ctx->par.device));
+    const double t_begin = now_ms();
+    double t_phase = t_begin;
     // shard bounds
     DBuf<uint64_t> d_bounds;
-    CU(d_bounds.ensure((size_t)ctx->world + 1));
+    CU(d_bounds.ensure((size_t)std::max(ctx->world, 1024) + 1));
     shard_bounds(ctx->d_read_off.p, ctx->n_mol, ctx->n_pairs, ctx->world, d_bounds.p, ctx->st);
     std::vector<uint64_t> bounds((size_t)ctx->world + 1);
     CU(cudaMemcpyAsync(bounds.data(), d_bounds.p, bounds.size() * 8, cudaMemcpyDeviceToHost, ctx->st));
@@ -1145,8 +1156,31 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     CU(cudaMemcpyAsync(d_err.p, init, sizeof init, cudaMemcpyHostToDevice, ctx->st));
     ctx->n_tiles = (uint32_t)((ctx->s_npairs + ctx->tile_pairs - 1) / ctx->tile_pairs);
     CU(ctx->d_tile_mol0.ensure((size_t)ctx->n_tiles + 1));
-    place(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->mol0, (uint32_t)ctx->s_nmol, ctx->d_read_off.p, ctx->d_ins.p, ctx->d_mol.p,
-          ctx->d_text.p, ctx->text_stride, ctx->d_roff_l.p, ctx->d_tile_mol0.p, ctx->tile_pairs, d_err.p, ctx->st);
+    place_prepare(ctx->mol0, (uint32_t)ctx->s_nmol, ctx->d_read_off.p, ctx->d_roff_l.p, ctx->d_tile_mol0.p, ctx->tile_pairs, ctx->st);
+    {   // segments of at most SEG pairs bound the scratch of the flat per-pair draws
+        const uint64_t SEG = 64ull << 20;
+        const int n_seg = (int)std::max<uint64_t>(1, (ctx->s_npairs + SEG - 1) / SEG);
+        if (n_seg > 1023) return fail(ctx, MMK_ERR_UNSUPPORTED, "shard too large: more than 2^36 read pairs");
+        std::vector<uint64_t> sb((size_t)n_seg + 1), sp((size_t)n_seg + 1);
+        if (ctx->s_nmol) {
+            shard_bounds(ctx->d_roff_l.p, ctx->s_nmol, ctx->s_npairs, n_seg, d_bounds.p, ctx->st);
+            if ((size_t)n_seg + 1 > d_bounds.cap) return fail(ctx, MMK_ERR_NOMEM, "segment table");
+            CU(cudaMemcpyAsync(sb.data(), d_bounds.p, sb.size() * 8, cudaMemcpyDeviceToHost, ctx->st));
+            CU(cudaStreamSynchronize(ctx->st));
+            uint64_t max_pairs = 0;
+            for (int k = 0; k <= n_seg; ++k)
+                CU(cudaMemcpyAsync(&sp[k], ctx->d_roff_l.p + sb[k], 8, cudaMemcpyDeviceToHost, ctx->st));
+            CU(cudaStreamSynchronize(ctx->st));
+            for (int k = 0; k < n_seg; ++k) max_pairs = std::max(max_pairs, sp[k + 1] - sp[k]);
+            CU(ctx->d_tmp_x.ensure(max_pairs + 1));
+            CU(ctx->d_tmp_g.ensure(max_pairs + 1));
+            for (int k = 0; k < n_seg; ++k)
+                place_segment(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->mol0, (uint32_t)ctx->s_nmol, (uint32_t)sb[k],
+                              (uint32_t)sb[k + 1], sp[k], sp[k + 1], ctx->d_roff_l.p, ctx->d_tile_mol0.p, ctx->n_tiles,
+                              ctx->tile_pairs, ctx->d_tmp_x.p, ctx->d_tmp_g.p, ctx->d_ins.p, ctx->d_mol.p, ctx->d_text.p,
+                              ctx->text_stride, d_err.p, ctx->st);
+        }
+    }
     unsigned long long herr[3];
     CU(cudaMemcpyAsync(herr, d_err.p, sizeof herr, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
@@ -1156,6 +1190,8 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
         CU(cudaMemcpy(&code, ctx->p_status.p + herr[0], 1, cudaMemcpyDeviceToHost));
         return fail(ctx, code, "molecule %llu: %s", herr[0], mmk_strerror(code));
     }
+    ctx->place_info.phase_ms[0] = now_ms() - t_phase;
+    t_phase = now_ms();
     // tile offsets
     DBuf<uint32_t> d_sum1, d_sum2;
     DBuf<uint64_t> d_tmp;
@@ -1184,8 +1220,12 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     ctx->place_info.gather_bytes = tot[2];
     ctx->tile_cursor = 0;
     ctx->slot = 0;
+    ctx->place_info.phase_ms[1] = now_ms() - t_phase;
+    t_phase = now_ms();
     int32_t rc_chunks = prepare_chunks(ctx);
     if (rc_chunks) return rc_chunks;
+    ctx->place_info.phase_ms[2] = now_ms() - t_phase;
+    ctx->place_info.host_ms = now_ms() - t_begin;
     ctx->placed = true;
     if (out) *out = ctx->place_info;
     return MMK_OK;

@@ -129,10 +129,13 @@ void plan_batch(const SimConst &sc, const SchemaDev *d_sch, const uint16_t *d_li
 void shard_bounds(const uint64_t *d_read_off, uint64_t n_mol, uint64_t n_pairs, int32_t world, uint64_t *d_bounds /*[world+1]*/,
                   cudaStream_t st);
 
-void place(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol,
-           const uint64_t *d_read_off_global, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
-           uint64_t *d_read_off_local, uint32_t *d_tile_mol0, uint32_t tile_pairs,
-           unsigned long long *d_err /*[0]: first bad molecule*/, cudaStream_t st);
+void place_prepare(uint64_t mol0, uint32_t n_mol, const uint64_t *d_read_off_global, uint64_t *d_read_off_local,
+                   uint32_t *d_tile_mol0, uint32_t tile_pairs, cudaStream_t st);
+void place_segment(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint32_t m_lo,
+                   uint32_t m_hi, uint64_t pair_lo, uint64_t pair_hi, const uint64_t *d_read_off_local,
+                   const uint32_t *d_tile_mol0, uint32_t n_tiles, uint32_t tile_pairs, double *d_tmp_x, uint64_t *d_tmp_g,
+                   uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride, unsigned long long *d_err,
+                   cudaStream_t st);
 
 void tile_sums(const EmitArgs &a, uint32_t n_tiles_total, uint32_t *d_sum1, uint32_t *d_sum2, unsigned long long *d_gather,
                cudaStream_t st);

@@ -144,6 +144,21 @@ __device__ __forceinline__ uint32_t molecule_shape(const SimConst &sc, uint64_t 
     return status;
 }
 
+// One insert length: rand(truncated(Normal(mu, sd), lower = 200)) — z = randn() until z >= lb, then
+// mu + sd z (Breakpoints.jl:207, Distributions' randnt rejection branch).  The normals of insert i
+// in redraw round r come from their own Philox stream (seed ^ (r << 32 | i)), so the draw can be
+// made by any thread; the replay order (insert 0's normals, then insert 1's, ...) is unchanged.
+template <class R>
+__device__ __forceinline__ double draw_insert(const SimConst &sc, uint64_t g, uint32_t m, uint32_t round, uint32_t i, R &rec) {
+    mmk_stream s;
+    mmk_stream_init(&s, sc.seed ^ (((uint64_t)round << 32) | (uint64_t)i), sc.sample, MMK_P_INSERT, g, m);
+    for (;;) {
+        double z = mmk_next_normal(&s);
+        rec.put(MMK_P_INSERT, 0, mmk_d2u(z));
+        if (!(z < sc.ins_lb)) return MMK_ADD(sc.ins_mu, MMK_MUL(sc.ins_sd, z));
+    }
+}
+
 // Insert lengths, molecule start, gap chain.  Plan entry of insert i:
 //   ins[i].x = start_i - molecule start
 //   ins[i].y = length (low 24 bits) | (molecule index - first molecule of the insert's tile) << 24
@@ -161,7 +176,6 @@ __device__ __forceinline__ uint32_t molecule_place(const SimConst &sc, uint64_t 
                                                    uint32_t molsize, uint32_t nfrags, uint2 *ins, const TileRef &tr,
                                                    int64_t &start, R &rec) {
     mmk_stream s;
-    mmk_stream_init(&s, sc.seed, sc.sample, MMK_P_INSERT, g, m);
     int attempts = 0;
     double sum;
     uint64_t isum;
@@ -169,15 +183,7 @@ __device__ __forceinline__ uint32_t molecule_place(const SimConst &sc, uint64_t 
         sum = 0.0;
         isum = 0;
         for (uint32_t i = 0; i < nfrags; ++i) {
-            double x;
-            for (;;) {
-                double z = mmk_next_normal(&s);
-                rec.put(MMK_P_INSERT, 0, mmk_d2u(z));
-                if (!(z < sc.ins_lb)) {
-                    x = MMK_ADD(sc.ins_mu, MMK_MUL(sc.ins_sd, z));
-                    break;
-                }
-            }
+            double x = draw_insert(sc, g, m, (uint32_t)attempts, i, rec);
             sum = MMK_ADD(sum, x);
             uint32_t li = (uint32_t)(long long)x;
             if (li > 0x00ffffffu) li = 0x00ffffffu;  // unreachable: mmk_create bounds insert_length + 13 sd below 2^24

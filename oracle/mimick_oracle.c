@@ -131,6 +131,7 @@ typedef struct orc_sim {
     int st_init[16];
     uint64_t cur_g;
     uint32_t cur_m;
+    uint32_t cur_round, cur_insert; /* insert-length normals: one Philox stream per (round, insert) */
     /* optional record of what was consumed */
     orc_variate *rec;
     size_t rec_n, rec_cap;
@@ -198,7 +199,9 @@ static mmk_stream *stream_for(orc_sim *s, uint32_t purpose) {
         uint64_t g = s->cur_g;
         uint32_t m = s->cur_m;
         if (purpose == MMK_P_NMOL || purpose == MMK_P_TARGET) m = 0;
-        mmk_stream_init(&s->st[purpose], s->seed, s->sample, purpose, g, m);
+        uint64_t seed = s->seed;
+        if (purpose == MMK_P_INSERT) seed ^= ((uint64_t)s->cur_round << 32) | (uint64_t)s->cur_insert;
+        mmk_stream_init(&s->st[purpose], seed, s->sample, purpose, g, m);
         s->st_init[purpose] = 1;
     }
     return &s->st[purpose];
@@ -211,6 +214,11 @@ static void src_begin_group(orc_sim *s, uint64_t g) {
 static void src_begin_molecule(orc_sim *s, uint32_t m) {
     s->cur_m = m;
     for (int p = MMK_P_MOLSIZE; p <= MMK_P_GAP; ++p) s->st_init[p] = 0;
+}
+static void src_begin_insert(orc_sim *s, uint32_t round, uint32_t i) {
+    s->cur_round = round;
+    s->cur_insert = i;
+    s->st_init[MMK_P_INSERT] = 0;
 }
 static const orc_variate *rp_pop(orc_sim *s, uint32_t tag) {
     if (s->rp_pos >= s->rp_n) {
@@ -602,6 +610,7 @@ static int64_t calculate_insert_sizes(orc_sim *s, int64_t molsize, int64_t **len
     for (;;) {
         sum = 0.0;
         for (int64_t i = 0; i < n; ++i) {
+            src_begin_insert(s, (uint32_t)attempts, (uint32_t)i);
             tmp[i] = trunc_normal_rand(s);
             sum = MMK_ADD(sum, tmp[i]);
         }
@@ -862,6 +871,6 @@ void orc_sample_insert(uint64_t seed, int32_t mu, int32_t sd, int64_t n, double 
     orc_params p; memset(&p, 0, sizeof p); p.insert_length = mu; p.insert_stdev = sd; p.mol_length = 80000; p.mol_coverage = 0.2; p.n_molecules = 2;
     orc_sim *s = orc_create(&p);
     orc_set_philox(s, seed, 0);
-    for (int64_t i = 0; i < n; ++i) { src_begin_group(s, (uint64_t)i); out[i] = trunc_normal_rand(s); }
+    for (int64_t i = 0; i < n; ++i) { src_begin_group(s, (uint64_t)i); src_begin_insert(s, 0, 0); out[i] = trunc_normal_rand(s); }
     orc_destroy(s);
 }

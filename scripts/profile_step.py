@@ -23,5 +23,6 @@ for it in range(2):
     place = sim.place()
     ms = sim.emit_all()
     print(f"step {it}: pairs={plan.n_pairs} molecules={plan.n_molecules} epochs={plan.n_epochs} batches={plan.n_batches} "
-          f"bytes={place.r1_bytes + place.r2_bytes} emit_ms={ms:.3f}")
+          f"bytes={place.r1_bytes + place.r2_bytes} emit_ms={ms:.3f} plan_ms={plan.host_ms:.2f} place_ms={place.host_ms:.2f} "
+          f"phases={[round(x, 2) for x in place.phase_ms]}")
 sim.close()
