@@ -698,17 +698,21 @@ __global__ void k_place_chain(SimConst sc, const SchemaDev *__restrict__ sch, Pl
             in[k].x = (uint32_t)st;
             cursor = st + li;
             remaining -= gap;
+            // R2 window bstop - r2 + 1 : bstop must start at >= 1 (Julia BoundsError otherwise)
+            if (!sc.strict && start + (int64_t)st + (int64_t)li - (int64_t)sc.r2 < 1) status = MMK_ERR_BOUNDS;
         }
-        status = check_windows(in, nfrags, start, n, sc.r1, sc.r2, sc.strict, q1, q2);
+        // quality lengths follow the molecule's FIRST reads (FormatFASTQ.jl:14)
+        if (!status) (void)check_windows(in, 1, start, n, sc.r1, sc.r2, sc.strict, q1, q2);
     }
     if (sc.fq_format == MMK_FMT_TENX) q1 += 16;
     if (status) {
         atomicMin(&err[0], (unsigned long long)gi);
         plan.status[gi] = (uint8_t)status;
     }
-    // header text: "@chrom:hap|start:end|" then the format's tail with read digit '1'
-    uint8_t *tp = text + (uint64_t)i * text_stride;
-    uint8_t *p = tp;
+    // header text: "@chrom:hap|start:end|" then the format's tail with read digit '1'; assembled in a
+    // thread-local buffer and written with 16-byte stores
+    uint8_t buf[208];
+    uint8_t *p = buf;
     *p++ = '@';
     for (int k = 0; k < S.name_len; ++k) *p++ = (uint8_t)S.name[k];
     *p++ = ':';
@@ -718,7 +722,7 @@ __global__ void k_place_chain(SimConst sc, const SchemaDev *__restrict__ sch, Pl
     *p++ = ':';
     p = put_dec(p, (uint64_t)(start + molsize));
     *p++ = '|';
-    uint32_t plen = (uint32_t)(p - tp);
+    uint32_t plen = (uint32_t)(p - buf);
     uint8_t *sp = p;
     switch (sc.fq_format) {
     case MMK_FMT_STLFR: *p++ = '#'; p = put_barcode(p, sc.bc_format, gi); p = put_str(p, " 1:N:0:ATGACA\n"); break;
@@ -726,6 +730,15 @@ __global__ void k_place_chain(SimConst sc, const SchemaDev *__restrict__ sch, Pl
     case MMK_FMT_TELLSEQ: *p++ = ':'; p = put_barcode(p, sc.bc_format, gi); p = put_str(p, " 1:N:0:ATGACA\n"); break;
     case MMK_FMT_TENX: *p++ = '|'; p = put_barcode(p, sc.bc_format, gi); p = put_str(p, " 1:N:0:ATGACA\n"); break;
     default: p = put_str(p, "/1\tVX:i:1\tBX:Z:"); p = put_barcode(p, sc.bc_format, gi); *p++ = '\n'; break;
+    }
+    {
+        uint4 *dst = reinterpret_cast<uint4 *>(text + (uint64_t)i * text_stride);
+        const uint32_t nb = (uint32_t)(p - buf);
+        for (uint32_t o = 0; o < nb; o += 16) {
+            uint4 v;
+            memcpy(&v, buf + o, 16);
+            dst[o >> 4] = v;
+        }
     }
     MolRec r;
     r.start = start;
