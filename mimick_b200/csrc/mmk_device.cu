@@ -275,7 +275,7 @@ __global__ void k_scan_spine(uint64_t *block_sums, uint64_t nb) {
     }
     if (threadIdx.x == 0) block_sums[nb] = carry;
 }
-__global__ void k_scan_apply(const uint32_t *in, uint64_t n, const uint64_t *block_sums, uint64_t *out) {
+__global__ void k_scan_apply(const uint32_t *in, uint64_t n, const uint64_t *block_sums, uint64_t *out, const uint64_t *base_ptr) {
     __shared__ uint64_t s_warp[33];
     uint64_t base = (uint64_t)blockIdx.x * SCAN_B + (uint64_t)threadIdx.x * SCAN_I;
     uint32_t it[SCAN_I];
@@ -286,23 +286,27 @@ __global__ void k_scan_apply(const uint32_t *in, uint64_t n, const uint64_t *blo
         v += it[j];
     }
     uint64_t total;
-    uint64_t ex = block_exclusive_u64(v, s_warp, total) + block_sums[blockIdx.x];
+    const uint64_t b0 = base_ptr ? *base_ptr : 0ull;  // out[0] may alias *base_ptr: read before any write below
+    __syncthreads();
+    uint64_t ex = block_exclusive_u64(v, s_warp, total) + block_sums[blockIdx.x] + b0;
 #pragma unroll
     for (int j = 0; j < SCAN_I; ++j) {
         if (base + j < n) out[base + j] = ex;
         ex += it[j];
     }
-    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = block_sums[gridDim.x];
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = block_sums[gridDim.x] + b0;
 }
-void exclusive_scan_u32(const uint32_t *in, uint64_t *out, uint64_t n, uint64_t *tmp, cudaStream_t s) {
+// out[i] = base + sum(in[0..i)), out[n] = base + total; base = *d_base (device) or 0
+void exclusive_scan_u32(const uint32_t *in, uint64_t *out, uint64_t n, uint64_t *tmp, cudaStream_t s, const uint64_t *d_base) {
     if (n == 0) {
-        cudaMemsetAsync(out, 0, 8, s);
+        if (!d_base) cudaMemsetAsync(out, 0, 8, s);
+        else if (out != d_base) cudaMemcpyAsync(out, d_base, 8, cudaMemcpyDeviceToDevice, s);
         return;
     }
     unsigned nb = (unsigned)((n + SCAN_B - 1) / SCAN_B);
     LAUNCH(k_scan_reduce, nb, SCAN_T, 0, s, in, n, tmp);
     LAUNCH(k_scan_spine, 1, 1024, 0, s, tmp, nb);
-    LAUNCH(k_scan_apply, nb, SCAN_T, 0, s, in, n, tmp, out);
+    LAUNCH(k_scan_apply, nb, SCAN_T, 0, s, in, n, tmp, out, d_base);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -315,31 +319,6 @@ __global__ void k_group_nmol(SimConst sc, uint64_t g0, uint32_t n_groups, uint32
     nmol[i] = draw_nmol(sc, g0 + i, rec);
 }
 
-__global__ void k_plan_groups(SimConst sc, const SchemaDev *__restrict__ sch, const uint16_t *__restrict__ live,
-                              uint32_t n_live, uint16_t epoch, uint64_t g0, uint32_t n_groups,
-                              const uint32_t *__restrict__ nmol, const uint64_t *__restrict__ off, PlanDev plan,
-                              uint64_t mol_base) {
-    uint32_t gl = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gl >= n_groups) return;
-    uint64_t g = g0 + gl;
-    uint32_t n = nmol[gl];
-    uint64_t o = mol_base + off[gl];
-    NoRec rec;
-    for (uint32_t m = 0; m < n; ++m) {
-        uint32_t t = live[draw_target(sc, g, m, n_live)];
-        uint32_t seq_len = sch[t].len;
-        uint32_t molsize, nfrags;
-        uint32_t status = molecule_shape(sc, g, m, seq_len, molsize, nfrags, rec);
-        plan.group[o + m] = g;
-        plan.slot[o + m] = m;
-        plan.schema[o + m] = (uint16_t)t;
-        plan.epoch[o + m] = epoch;
-        plan.size[o + m] = molsize;
-        plan.nfrags[o + m] = nfrags;
-        plan.status[o + m] = (uint8_t)status;
-    }
-}
-
 constexpr uint32_t HCH = 4096;  // molecules per histogram chunk
 
 __global__ void k_fill_lpos(const uint16_t *live, uint32_t n_live, uint16_t *lpos) {
@@ -347,163 +326,165 @@ __global__ void k_fill_lpos(const uint16_t *live, uint32_t n_live, uint16_t *lpo
     if (i < n_live) lpos[live[i]] = (uint16_t)i;
 }
 
-// hist[c * n_live + lpos] += nfrags of chunk c's molecules of that live schema. The number of
-// molecules in the batch is only known on the device (off[n_groups]).
-__global__ void k_hist(const uint16_t *__restrict__ schema, const uint32_t *__restrict__ nfrags,
-                       const uint64_t *__restrict__ off, uint32_t n_groups, const uint16_t *__restrict__ lpos,
-                       uint32_t n_live, unsigned long long *hist) {
-    uint64_t n_mol = off[n_groups];
-    uint64_t c = blockIdx.x;
-    uint64_t lo = c * HCH;
-    if (lo >= n_mol) return;
-    uint64_t hi = lo + HCH < n_mol ? lo + HCH : n_mol;
-    unsigned long long *row = hist + c * n_live;
-    for (uint64_t i = lo + threadIdx.x; i < hi; i += blockDim.x)
-        atomicAdd(&row[lpos[schema[i]]], (unsigned long long)nfrags[i]);
+// One thread per barcode group of the batch [g0, g0 + n_groups): target picks against the current live
+// list, molecule size and number of inserts for each of its molecules (whose indices off[g] + slot do
+// not depend on the live set).  Also: per-chunk histogram of inserts per live schema (for the
+// coverage tracker) and the first molecule with a non-zero status.
+__global__ void k_plan_groups(SimConst sc, const SchemaDev *__restrict__ sch, const uint16_t *__restrict__ live,
+                              const uint16_t *__restrict__ lpos, uint32_t n_live, uint16_t epoch, uint64_t g0, uint32_t n_groups,
+                              const uint32_t *__restrict__ nmol, const uint64_t *__restrict__ off, PlanDev plan,
+                              unsigned long long *hist, unsigned long long *first_err) {
+    uint32_t gl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gl >= n_groups) return;
+    const uint64_t g = g0 + gl;
+    const uint32_t n = nmol[g];
+    const uint64_t o = off[g], base = off[g0];
+    NoRec rec;
+    for (uint32_t m = 0; m < n; ++m) {
+        const uint32_t t = live[draw_target(sc, g, m, n_live)];
+        uint32_t molsize, nfrags;
+        const uint32_t status = molecule_shape(sc, g, m, sch[t].len, molsize, nfrags, rec);
+        const uint64_t i = o + m;
+        plan.group[i] = g;
+        plan.slot[i] = m;
+        plan.schema[i] = (uint16_t)t;
+        plan.epoch[i] = epoch;
+        plan.size[i] = molsize;
+        plan.nfrags[i] = nfrags;
+        plan.status[i] = (uint8_t)status;
+        atomicAdd(&hist[((i - base) / HCH) * n_live + lpos[t]], (unsigned long long)nfrags);
+        if (status) atomicMin(first_err, (unsigned long long)(i - base));
+    }
 }
 
-// One warp per live schema: the chunk in which its cumulative insert count reaches `need`, then
-// the molecule inside that chunk; reports that molecule's barcode group (Main.jl:54,58: a schema
-// is pruned at the END of the group in which it reaches reads_required).
-__global__ void k_cross(const uint16_t *__restrict__ schema, const uint32_t *__restrict__ nfrags,
-                        const uint64_t *__restrict__ group, const uint64_t *__restrict__ off, uint32_t n_groups,
-                        const uint16_t *__restrict__ live, uint32_t n_live, const unsigned long long *__restrict__ hist,
-                        const int64_t *__restrict__ need, uint64_t g0, unsigned long long *cross_group) {
-    uint64_t n_mol = off[n_groups];
-    uint32_t n_chunks = (uint32_t)((n_mol + HCH - 1) / HCH);
-    uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t lane = threadIdx.x & 31;
-    if (s >= n_live) return;
-    int64_t want = need[s];
-    if (want <= 0) {  // already complete: pruned at the end of the batch's first group
-        if (lane == 0) cross_group[s] = g0;
-        return;
-    }
-    uint16_t sid = live[s];
-    unsigned long long cum = 0;
-    uint32_t found_chunk = 0xffffffffu;
-    for (uint32_t c0 = 0; c0 < n_chunks && found_chunk == 0xffffffffu; c0 += 32) {
-        uint32_t c = c0 + lane;
-        unsigned long long v = c < n_chunks ? hist[(uint64_t)c * n_live + s] : 0ull;
-        unsigned long long inc = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += y;
-        }
-        unsigned ball = __ballot_sync(0xffffffffu, (long long)(cum + inc) >= want);
-        if (ball) {
-            int l = __ffs(ball) - 1;
-            unsigned long long before = __shfl_sync(0xffffffffu, inc - v, l);
-            found_chunk = c0 + l;
-            cum += before;
+// One block closes the batch: per live schema the barcode group in which its cumulative insert count
+// reaches the remaining need (a schema is pruned at the END of that group, Main.jl:54,58), the earliest
+// such group = the cut, the number of molecules kept, the inserts each schema received from them.
+__global__ void __launch_bounds__(1024) k_plan_finish(const uint16_t *__restrict__ schema, const uint32_t *__restrict__ nfrags,
+                                                      const uint64_t *__restrict__ group, const uint64_t *__restrict__ off,
+                                                      uint64_t g0, uint32_t n_groups, const uint16_t *__restrict__ live,
+                                                      uint32_t n_live, const unsigned long long *__restrict__ hist,
+                                                      const int64_t *__restrict__ need, const unsigned long long *first_err,
+                                                      const uint8_t *__restrict__ status, BatchResult *res) {
+    __shared__ unsigned long long s_cut;
+    __shared__ uint64_t s_commit;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const uint64_t base = off[g0];
+    const uint64_t n_mol = off[g0 + n_groups] - base;
+    const uint32_t n_chunks = (uint32_t)((n_mol + HCH - 1) / HCH);
+    schema += base;
+    nfrags += base;
+    group += base;
+    if (threadIdx.x == 0) s_cut = ~0ull;
+    __syncthreads();
+    constexpr uint32_t PER = HCH / 32;
+    for (uint32_t s = warp; s < n_live; s += n_warps) {
+        const long long want = need[s];
+        unsigned long long cg = ~0ull;
+        if (want <= 0) {
+            cg = g0;  // already complete: pruned at the end of the batch's first group
         } else {
-            cum += __shfl_sync(0xffffffffu, inc, 31);
-        }
-    }
-    if (found_chunk == 0xffffffffu) {
-        if (lane == 0) cross_group[s] = ~0ull;
-        return;
-    }
-    constexpr uint32_t PER = HCH / 32;  // each lane owns PER consecutive molecules of the chunk
-    uint64_t lo = (uint64_t)found_chunk * HCH + (uint64_t)lane * PER;
-    unsigned long long part = 0;
-    for (uint32_t j = 0; j < PER; ++j) {
-        uint64_t i = lo + j;
-        if (i < n_mol && schema[i] == sid) part += nfrags[i];
-    }
-    unsigned long long inc = part;
-    for (int o = 1; o < 32; o <<= 1) {
-        unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += y;
-    }
-    unsigned ball = __ballot_sync(0xffffffffu, (long long)(cum + inc) >= want);
-    int l = __ffs(ball) - 1;  // non-zero by construction
-    if ((int)lane == l) {
-        unsigned long long run = cum + inc - part;
-        for (uint32_t j = 0; j < PER; ++j) {
-            uint64_t i = lo + j;
-            if (i < n_mol && schema[i] == sid) {
-                run += nfrags[i];
-                if ((long long)run >= want) {
-                    cross_group[s] = group[i];
-                    break;
+            const uint16_t sid = live[s];
+            unsigned long long cum = 0;
+            uint32_t found = 0xffffffffu;
+            for (uint32_t c0 = 0; c0 < n_chunks && found == 0xffffffffu; c0 += 32) {
+                const uint32_t c = c0 + lane;
+                const unsigned long long v = c < n_chunks ? hist[(uint64_t)c * n_live + s] : 0ull;
+                unsigned long long inc = v;
+                for (int o = 1; o < 32; o <<= 1) {
+                    unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += y;
                 }
+                const unsigned ball = __ballot_sync(0xffffffffu, (long long)(cum + inc) >= want);
+                if (ball) {
+                    const int l = __ffs(ball) - 1;
+                    cum += __shfl_sync(0xffffffffu, inc - v, l);
+                    found = c0 + l;
+                } else
+                    cum += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (found != 0xffffffffu) {  // the molecule inside the chunk: each lane owns PER consecutive molecules
+                const uint64_t lo = (uint64_t)found * HCH + (uint64_t)lane * PER;
+                unsigned long long part = 0;
+                for (uint32_t j = 0; j < PER; ++j) {
+                    const uint64_t i = lo + j;
+                    if (i < n_mol && schema[i] == sid) part += nfrags[i];
+                }
+                unsigned long long inc = part;
+                for (int o = 1; o < 32; o <<= 1) {
+                    unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += y;
+                }
+                const unsigned ball = __ballot_sync(0xffffffffu, (long long)(cum + inc) >= want);
+                const int l = __ffs(ball) - 1;  // non-zero by construction
+                if ((int)lane == l) {
+                    unsigned long long run = cum + inc - part;
+                    for (uint32_t j = 0; j < PER; ++j) {
+                        const uint64_t i = lo + j;
+                        if (i < n_mol && schema[i] == sid) {
+                            run += nfrags[i];
+                            if ((long long)run >= want) {
+                                cg = group[i];
+                                break;
+                            }
+                        }
+                    }
+                }
+                cg = __shfl_sync(0xffffffffu, cg, l);
             }
         }
-    }
-}
-
-__global__ void k_cut(const unsigned long long *cross_group, uint32_t n_live, uint64_t g0, uint32_t n_groups,
-                      const uint64_t *off, const uint8_t *status, BatchResult *res) {
-    __shared__ unsigned long long s_cut, s_err;
-    __shared__ uint64_t s_commit;
-    if (threadIdx.x == 0) {
-        s_cut = ~0ull;
-        s_err = ~0ull;
+        if (lane == 0 && cg != ~0ull) atomicMin(&s_cut, cg);
     }
     __syncthreads();
-    unsigned long long mine = ~0ull;
-    for (uint32_t i = threadIdx.x; i < n_live; i += blockDim.x) mine = cross_group[i] < mine ? cross_group[i] : mine;
-    if (mine != ~0ull) atomicMin(&s_cut, mine);
+    if (threadIdx.x == 0) s_commit = (s_cut == ~0ull) ? n_mol : off[s_cut + 1] - base;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint64_t total = off[n_groups];
-        s_commit = (s_cut == ~0ull) ? total : off[(uint32_t)(s_cut - g0) + 1];
+    const uint64_t nc = s_commit;
+    // inserts per live schema among the kept molecules: whole chunks from the histogram, the last from the molecules
+    const uint32_t full = (uint32_t)(nc / HCH);
+    for (uint32_t s = warp; s < n_live; s += n_warps) {
+        const uint16_t sid = live[s];
+        unsigned long long acc = 0;
+        for (uint32_t c = lane; c < full; c += 32) acc += hist[(uint64_t)c * n_live + s];
+        for (uint64_t i = (uint64_t)full * HCH + lane; i < nc; i += 32)
+            if (schema[i] == sid) acc += nfrags[i];
+        for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (lane == 0) res->sums[s] = acc;
     }
-    __syncthreads();
-    uint64_t nc = s_commit;
-    unsigned long long e = ~0ull;
-    for (uint64_t i = threadIdx.x; i < nc; i += blockDim.x)
-        if (status[i] && i < e) e = i;
-    if (e != ~0ull) atomicMin(&s_err, e);
-    __syncthreads();
     if (threadIdx.x == 0) {
+        const unsigned long long fe = *first_err;
         res->cut_group = s_cut;
         res->n_commit = nc;
-        res->first_error = s_err;
-        res->error_code = s_err != ~0ull ? status[s_err] : 0;
-    }
-}
-
-__global__ void k_sums(const uint16_t *__restrict__ schema, const uint32_t *__restrict__ nfrags,
-                       const uint16_t *__restrict__ lpos, uint32_t n_live, BatchResult *res) {
-    uint64_t n = res->n_commit;
-    unsigned long long *sums = (unsigned long long *)res->sums;
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    extern __shared__ unsigned long long s_h[];
-    if (n_live <= 2048) {
-        for (uint32_t j = threadIdx.x; j < n_live; j += blockDim.x) s_h[j] = 0;
-        __syncthreads();
-        for (; i < n; i += stride) atomicAdd(&s_h[lpos[schema[i]]], (unsigned long long)nfrags[i]);
-        __syncthreads();
-        for (uint32_t j = threadIdx.x; j < n_live; j += blockDim.x)
-            if (s_h[j]) atomicAdd(&sums[j], s_h[j]);
-    } else {
-        for (; i < n; i += stride) atomicAdd(&sums[lpos[schema[i]]], (unsigned long long)nfrags[i]);
+        res->first_error = fe < nc ? fe : ~0ull;
+        res->error_code = fe < nc ? status[base + fe] : 0;
     }
 }
 
 uint32_t plan_hist_chunks(uint64_t max_molecules) { return (uint32_t)((max_molecules + HCH - 1) / HCH); }
 
-void plan_batch(const SimConst &sc, const SchemaDev *d_sch, const uint16_t *d_live, uint32_t n_live, uint16_t epoch,
-                uint64_t g0, uint32_t n_groups, uint32_t *d_nmol, uint64_t *d_off, uint64_t *d_scan_tmp, PlanDev plan,
-                uint64_t mol_base, uint64_t max_mol, const int64_t *d_need, unsigned long long *d_hist,
-                unsigned long long *d_cross, uint16_t *d_lpos, BatchResult *d_res, cudaStream_t st) {
-    LAUNCH(k_group_nmol, (n_groups + 255) / 256, 256, 0, st, sc, g0, n_groups, d_nmol);
-    exclusive_scan_u32(d_nmol, d_off, n_groups, d_scan_tmp, st);
-    LAUNCH(k_plan_groups, (n_groups + 127) / 128, 128, 0, st, sc, d_sch, d_live, n_live, epoch, g0, n_groups, d_nmol, d_off,
-                                                          plan, mol_base);
-    uint32_t n_chunks = plan_hist_chunks(max_mol);
-    cudaMemsetAsync(d_hist, 0, (size_t)n_chunks * n_live * sizeof(unsigned long long), st);
+// group table: n_mol of groups [g_lo, g_hi) and their molecule offsets (off[g_lo] must already be valid)
+void plan_extend_table(const SimConst &sc, uint64_t g_lo, uint64_t g_hi, uint32_t *d_nmol, uint64_t *d_off, uint64_t *d_scan_tmp,
+                       cudaStream_t st) {
+    if (g_hi <= g_lo) return;
+    const uint32_t n = (uint32_t)(g_hi - g_lo);
+    LAUNCH(k_group_nmol, (n + 255) / 256, 256, 0, st, sc, g_lo, n, d_nmol + g_lo);
+    exclusive_scan_u32(d_nmol + g_lo, d_off + g_lo, n, d_scan_tmp, st, d_off + g_lo);
+}
+
+void plan_set_live(const uint16_t *d_live, uint32_t n_live, uint16_t *d_lpos, cudaStream_t st) {
     LAUNCH(k_fill_lpos, (n_live + 255) / 256, 256, 0, st, d_live, n_live, d_lpos);
-    LAUNCH(k_hist, n_chunks, 256, 0, st, plan.schema + mol_base, plan.nfrags + mol_base, d_off, n_groups, d_lpos, n_live, d_hist);
-    LAUNCH(k_cross, (n_live * 32 + 127) / 128, 128, 0, st, plan.schema + mol_base, plan.nfrags + mol_base, plan.group + mol_base,
-                                                       d_off, n_groups, d_live, n_live, d_hist, d_need, g0, d_cross);
-    LAUNCH(k_cut, 1, 1024, 0, st, d_cross, n_live, g0, n_groups, d_off, plan.status + mol_base, d_res);
-    cudaMemsetAsync((char *)d_res + offsetof(BatchResult, sums), 0, (size_t)n_live * 8, st);
-    size_t sm = n_live <= 2048 ? (size_t)n_live * 8 : 0;
-    LAUNCH(k_sums, 148 * 4, 256, sm, st, plan.schema + mol_base, plan.nfrags + mol_base, d_lpos, n_live, d_res);
+}
+
+void plan_batch(const SimConst &sc, const SchemaDev *d_sch, const uint16_t *d_live, const uint16_t *d_lpos, uint32_t n_live,
+                uint16_t epoch, uint64_t g0, uint32_t n_groups, const uint32_t *d_nmol, const uint64_t *d_off, PlanDev plan,
+                uint64_t max_mol, const int64_t *d_need, unsigned long long *d_hist, unsigned long long *d_first_err,
+                BatchResult *d_res, cudaStream_t st) {
+    const uint32_t n_chunks = plan_hist_chunks(max_mol);
+    cudaMemsetAsync(d_hist, 0, (size_t)n_chunks * n_live * sizeof(unsigned long long), st);
+    cudaMemsetAsync(d_first_err, 0xff, 8, st);
+    LAUNCH(k_plan_groups, (n_groups + 127) / 128, 128, 0, st, sc, d_sch, d_live, d_lpos, n_live, epoch, g0, n_groups, d_nmol, d_off,
+           plan, d_hist, d_first_err);
+    LAUNCH(k_plan_finish, 1, 1024, 0, st, plan.schema, plan.nfrags, plan.group, d_off, g0, n_groups, d_live, n_live, d_hist, d_need,
+           d_first_err, plan.status, d_res);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -608,43 +589,74 @@ __global__ void k_tile_mol0(const uint64_t *__restrict__ roff_l, uint32_t n_mol,
     if (m >= n_mol) return;
     uint64_t lo = roff_l[m], hi = roff_l[m + 1];  // pairs [lo, hi)
     if (hi == lo) return;
-    for (uint64_t t = (lo + tile_pairs - 1) / tile_pairs; t * tile_pairs < hi; ++t) tile_mol0[t] = m;
+    const uint32_t sh = 31 - __clz(tile_pairs);  // tile_pairs is a power of two
+    for (uint64_t t = (lo + tile_pairs - 1) >> sh; (t << sh) < hi; ++t) tile_mol0[t] = m;
 }
 
 // Placement, step 1 — one thread per read pair: the insert length of redraw round 0 and the 64
 // random bits of the pair's gap draw.  Everything that needs a transcendental or a Philox block is
-// here, flat over pairs, so it runs without divergence.
+// here, flat over pairs, so it runs without divergence.  Per molecule it also accumulates the integer
+// sum of the lengths and a fixed-point (2^-16) lower bound of their real sum, one atomic per warp run.
+struct __align__(16) PairTmp {
+    uint64_t bits;  // gap draw: gap = mulhi64(bits, remaining + 1)
+    uint32_t len;   // trunc(Int, insert length)
+    uint32_t pad;
+};
 __global__ void k_insert_draws(SimConst sc, PlanDev plan, uint64_t mol0, uint32_t n_mol, const uint64_t *__restrict__ roff_l,
                                const uint32_t *__restrict__ tile_mol0, uint32_t n_tiles, uint32_t tile_pairs, uint64_t pair_lo,
-                               uint64_t pair_hi, double *__restrict__ tmp_x, uint64_t *__restrict__ tmp_g, uint2 *ins) {
-    uint64_t p = pair_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= pair_hi) return;
-    uint32_t tile = (uint32_t)(p / tile_pairs);
-    uint32_t m_lo = tile_mol0[tile], lo = m_lo, hi = tile + 1 < n_tiles ? tile_mol0[tile + 1] : n_mol - 1;
+                               uint64_t pair_hi, PairTmp *__restrict__ tmp, uint32_t *acc_i, unsigned long long *acc_f) {
+    const uint64_t p_raw = pair_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = p_raw < pair_hi;
+    const uint64_t p = valid ? p_raw : pair_hi - 1;
+    const uint32_t tile = (uint32_t)(p >> (31 - __clz(tile_pairs)));  // tile_pairs is a power of two
+    uint32_t lo = tile_mol0[tile], hi = tile + 1 < n_tiles ? tile_mol0[tile + 1] : n_mol - 1;
     while (lo < hi) {  // largest m with roff_l[m] <= p
         uint32_t mid = (lo + hi + 1) >> 1;
         if (roff_l[mid] <= p) lo = mid; else hi = mid - 1;
     }
-    uint32_t i = (uint32_t)(p - roff_l[lo]);
-    uint64_t g = plan.group[mol0 + lo];
-    uint32_t m = plan.slot[mol0 + lo];
+    const uint32_t i = (uint32_t)(p - roff_l[lo]);
+    const uint64_t g = plan.group[mol0 + lo];
+    const uint32_t m = plan.slot[mol0 + lo];
     NoRec rec;
-    double x = draw_insert(sc, g, m, 0, i, rec);
+    const double x = draw_insert(sc, g, m, 0, i, rec);
     mmk_stream gs;
     mmk_stream_init(&gs, sc.seed, sc.sample, MMK_P_GAP, g, m);
-    tmp_x[p - pair_lo] = x;
-    tmp_g[p - pair_lo] = mmk_stream_at(&gs, i);
     uint32_t li = (uint32_t)(long long)x;
     if (li > 0x00ffffffu) li = 0x00ffffffu;
-    ins[p].y = li | ((lo - m_lo) << 24);
+    if (valid) {
+        PairTmp t;
+        t.bits = mmk_stream_at(&gs, i);
+        t.len = li;
+        t.pad = 0;
+        tmp[p - pair_lo] = t;
+    }
+    // lanes of the same molecule are contiguous: one atomic per run
+    const unsigned peers = __match_any_sync(0xffffffffu, valid ? lo : 0xffffffffu);
+    const unsigned long long X = (unsigned long long)MMK_MUL(x, 65536.0);  // floor(x * 2^16), x > 0
+    const uint32_t s_len = __reduce_add_sync(peers, li);
+    const uint32_t s_lo = __reduce_add_sync(peers, (uint32_t)(X & 0xfffffu));
+    const uint32_t s_hi = __reduce_add_sync(peers, (uint32_t)(X >> 20));
+    if (valid && (threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1)) {
+        atomicAdd(&acc_i[lo], s_len);
+        atomicAdd(&acc_f[lo], ((unsigned long long)s_hi << 20) + s_lo);
+    }
 }
 
-// Placement, step 2 — one thread per molecule: the left-to-right float sum of the insert lengths and
-// its redraw rule (Breakpoints.jl:209-212), the start draw (:240), the serial gap chain (:27-33), the
-// window checks, the header text and the per-molecule record.
+// Placement, step 2 — one thread per molecule: the redraw rule on the float sum of the insert lengths
+// (Breakpoints.jl:209-212), the start draw (:240), the serial gap chain (:27-33), the window checks, the
+// header text and the per-molecule record.  `sum > molsize` is decided from the fixed-point bounds of
+// step 1; only when those straddle the molecule size is the left-to-right float sum (the oracle's
+// definition) evaluated.
+__device__ __noinline__ double sequential_sum(const SimConst &sc, uint64_t g, uint32_t m, uint32_t round, uint32_t nfrags) {
+    NoRec rec;
+    double sum = 0.0;
+    for (uint32_t k = 0; k < nfrags; ++k) sum = MMK_ADD(sum, draw_insert(sc, g, m, round, k, rec));
+    return sum;
+}
 __global__ void k_place_chain(SimConst sc, const SchemaDev *__restrict__ sch, PlanDev plan, uint64_t mol0, uint32_t m_lo,
-                              uint32_t m_hi, const uint64_t *__restrict__ roff_l, uint64_t pair_lo,
-                              const double *__restrict__ tmp_x, const uint64_t *__restrict__ tmp_g, uint2 *ins, MolRec *mol,
+                              uint32_t m_hi, const uint64_t *__restrict__ roff_l, uint64_t pair_lo, PairTmp *tmp,
+                              const uint32_t *__restrict__ acc_i, const unsigned long long *__restrict__ acc_f,
+                              const uint32_t *__restrict__ tile_mol0, uint32_t tile_pairs, uint2 *ins, MolRec *mol,
                               uint8_t *text, uint32_t text_stride, unsigned long long *err) {
     uint32_t i = m_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m_hi) return;
@@ -656,33 +668,33 @@ __global__ void k_place_chain(SimConst sc, const SchemaDev *__restrict__ sch, Pl
     uint32_t molsize = plan.size[gi], nfrags = plan.nfrags[gi];
     const SchemaDev &S = sch[t];
     const uint32_t n = S.len;
-    const double *xs = tmp_x + (ro - pair_lo);
-    const uint64_t *gb = tmp_g + (ro - pair_lo);
+    PairTmp *tp = tmp + (ro - pair_lo);
     uint2 *in = ins + ro;
     NoRec rec;
-    // float sum in insert order; whole-vector redraws while it exceeds the molecule
-    double sum = 0.0;
-    uint64_t isum = 0;
-    for (uint32_t k = 0; k < nfrags; ++k) {
-        double x = xs[k];
-        sum = MMK_ADD(sum, x);
-        isum += (uint32_t)(long long)x;
+    uint64_t isum = acc_i[i];
+    bool over;
+    {
+        const unsigned long long lo = acc_f[i], M = (unsigned long long)molsize << 16;  // sum * 2^16 in [lo, lo + nfrags)
+        if (lo > M) over = true;
+        else if (lo + nfrags + 1 <= M) over = false;
+        else over = sequential_sum(sc, g, m, 0, nfrags) > (double)molsize;
     }
     int attempts = 0;
-    while (sum > (double)molsize && attempts < sc.attempts) {
+    while (over && attempts < sc.attempts) {  // whole-vector redraw
         ++attempts;
-        sum = 0.0;
+        double sum = 0.0;
         isum = 0;
         for (uint32_t k = 0; k < nfrags; ++k) {
             double x = draw_insert(sc, g, m, (uint32_t)attempts, k, rec);
             sum = MMK_ADD(sum, x);
             uint32_t li = (uint32_t)(long long)x;
             if (li > 0x00ffffffu) li = 0x00ffffffu;
-            in[k].y = li | (in[k].y & 0xff000000u);
+            tp[k].len = li;
             isum += li;
         }
+        over = sum > (double)molsize;
     }
-    uint32_t status = sum > (double)molsize ? (uint32_t)MMK_ERR_INSERTS_UNFITTABLE : 0u;
+    uint32_t status = over ? (uint32_t)MMK_ERR_INSERTS_UNFITTABLE : 0u;
     // start_pos = rand(1:adjusted_end)
     uint64_t adjusted_end = sc.circular ? (uint64_t)n : (n > molsize + 1u ? (uint64_t)(n - molsize) : 1ull);
     mmk_stream s;
@@ -691,15 +703,23 @@ __global__ void k_place_chain(SimConst sc, const SchemaDev *__restrict__ sch, Pl
     uint32_t q1 = 0, q2 = 0;
     if (!status) {
         uint64_t remaining = (uint64_t)molsize + 1 - isum, cursor = 0;
+        const uint32_t tshift = 31 - __clz(tile_pairs);  // tile_pairs is a power of two
+        uint32_t tile = (uint32_t)(ro >> tshift), tm0 = tile_mol0[tile];
+        uint32_t to_next = tile_pairs - (uint32_t)(ro & (tile_pairs - 1));  // pairs left in the current tile
         for (uint32_t k = 0; k < nfrags; ++k) {
-            uint64_t gap = mmk_bits_to_index(gb[k], remaining + 1);
+            if (to_next == 0) {
+                tm0 = tile_mol0[++tile];
+                to_next = tile_pairs;
+            }
+            --to_next;
+            const PairTmp e = tp[k];
+            uint64_t gap = mmk_bits_to_index(e.bits, remaining + 1);
             uint64_t st = cursor + gap;
-            uint32_t li = MMK_INS_LEN(in[k].y);
-            in[k].x = (uint32_t)st;
-            cursor = st + li;
+            in[k] = make_uint2((uint32_t)st, e.len | ((i - tm0) << 24));
+            cursor = st + e.len;
             remaining -= gap;
             // R2 window bstop - r2 + 1 : bstop must start at >= 1 (Julia BoundsError otherwise)
-            if (!sc.strict && start + (int64_t)st + (int64_t)li - (int64_t)sc.r2 < 1) status = MMK_ERR_BOUNDS;
+            if (!sc.strict && start + (int64_t)st + (int64_t)e.len - (int64_t)sc.r2 < 1) status = MMK_ERR_BOUNDS;
         }
         // quality lengths follow the molecule's FIRST reads (FormatFASTQ.jl:14)
         if (!status) (void)check_windows(in, 1, start, n, sc.r1, sc.r2, sc.strict, q1, q2);
@@ -759,17 +779,18 @@ void place_prepare(uint64_t mol0, uint32_t n_mol, const uint64_t *d_read_off_glo
 }
 
 // one segment: pairs [pair_lo, pair_hi) = the pairs of molecules [m_lo, m_hi)
+size_t place_tmp_bytes(uint64_t max_pairs) { return (size_t)(max_pairs + 1) * sizeof(PairTmp); }
 void place_segment(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint32_t m_lo,
                    uint32_t m_hi, uint64_t pair_lo, uint64_t pair_hi, const uint64_t *d_read_off_local,
-                   const uint32_t *d_tile_mol0, uint32_t n_tiles, uint32_t tile_pairs, double *d_tmp_x, uint64_t *d_tmp_g,
-                   uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride, unsigned long long *d_err,
-                   cudaStream_t st) {
+                   const uint32_t *d_tile_mol0, uint32_t n_tiles, uint32_t tile_pairs, void *d_tmp, uint32_t *d_acc_i,
+                   unsigned long long *d_acc_f, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
+                   unsigned long long *d_err, cudaStream_t st) {
     if (m_hi <= m_lo) return;
     uint64_t np = pair_hi - pair_lo;
     if (np) LAUNCH(k_insert_draws, (unsigned)((np + 255) / 256), 256, 0, st, sc, plan, mol0, n_mol, d_read_off_local, d_tile_mol0,
-                   n_tiles, tile_pairs, pair_lo, pair_hi, d_tmp_x, d_tmp_g, d_ins);
+                   n_tiles, tile_pairs, pair_lo, pair_hi, (PairTmp *)d_tmp, d_acc_i, d_acc_f);
     LAUNCH(k_place_chain, (m_hi - m_lo + 127) / 128, 128, 0, st, sc, d_sch, plan, mol0, m_lo, m_hi, d_read_off_local, pair_lo,
-           d_tmp_x, d_tmp_g, d_ins, d_mol, d_text, text_stride, d_err);
+           (PairTmp *)d_tmp, d_acc_i, d_acc_f, d_tile_mol0, tile_pairs, d_ins, d_mol, d_text, text_stride, d_err);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(EMIT_THREADS, 4) k_emit(const __grid_constant_
     __shared__ uint4 s_fa[EMIT_MAX_TP], s_fb[EMIT_MAX_TP];
     __shared__ uint32_t s_off1[EMIT_MAX_TP + 1], s_off2[EMIT_MAX_TP + 1];
     const uint32_t tile = a.tile0 + blockIdx.x;
-    const uint64_t p0 = (uint64_t)tile * a.tile_pairs;
+    const uint64_t p0 = (uint64_t)tile * a.tile_pairs;  // tile_pairs is a power of two
     const uint32_t np = (uint32_t)((a.n_pairs - p0) < a.tile_pairs ? (a.n_pairs - p0) : a.tile_pairs);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t tile_m0 = a.tile_mol0[tile];

@@ -100,6 +100,19 @@ struct mmk_ctx {
     DBuf<uint32_t> p_nfrags;
     DBuf<uint8_t> p_status;
     DBuf<uint64_t> d_read_off;  // [n_mol + 1]
+    // planner scratch, kept between calls
+    DBuf<uint32_t> d_gnmol;     // group table: molecules per barcode group
+    DBuf<uint64_t> d_goff;      // group table: first molecule of every group
+    uint64_t g_tab = 0;         // groups covered by the table
+    DBuf<uint16_t> d_live, d_lpos;
+    DBuf<int64_t> d_need;
+    DBuf<unsigned long long> d_hist, d_first_err;
+    DBuf<uint8_t> d_res;
+    DBuf<uint64_t> d_scan_tmp;
+    // placement / chunking scratch, kept between calls
+    DBuf<uint64_t> s_bounds, s_b1, s_b2;
+    DBuf<unsigned long long> s_err;
+    DBuf<uint32_t> s_sum1, s_sum2, s_cb, s_cn;
     uint64_t n_mol = 0, n_pairs = 0, n_groups = 0;
     std::vector<uint32_t> epoch_nlive;
     mmk_plan_info plan_info{};
@@ -114,8 +127,9 @@ struct mmk_ctx {
     DBuf<uint64_t> d_roff_l;
     DBuf<uint64_t> d_tile_off1, d_tile_off2;
     DBuf<uint32_t> d_tile_mol0;
-    DBuf<double> d_tmp_x;     // placement scratch: round-0 insert lengths of one segment
-    DBuf<uint64_t> d_tmp_g;   // placement scratch: gap-draw bits of one segment
+    DBuf<uint8_t> d_tmp;      // placement scratch: (gap bits, insert length) per pair of one segment
+    DBuf<uint32_t> d_acc_i;   // placement scratch: sum of insert lengths per molecule
+    DBuf<unsigned long long> d_acc_f;  // ... and a 2^-16 fixed-point lower bound of their real sum
     uint32_t text_stride = 0, tile_pairs = 64, n_tiles = 0, stage_cap = 0;
     int32_t fast_ok = 0;
     mmk_place_info place_info{};
@@ -926,6 +940,23 @@ static inline double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// grow the group table to cover groups [0, g_need) and the plan arrays to hold their molecules
+static int32_t ensure_group_table(mmk_ctx *ctx, uint64_t g_need, uint64_t keep_mol) {
+    if (g_need <= ctx->g_tab) return MMK_OK;
+    uint64_t g_new = std::max<uint64_t>(g_need, ctx->g_tab + ctx->g_tab / 2);
+    g_new = (g_new + 1023) & ~1023ull;
+    CU(ctx->d_gnmol.ensure(g_new, ctx->g_tab, ctx->st));
+    CU(ctx->d_goff.ensure(g_new + 1, ctx->g_tab + 1, ctx->st));
+    CU(ctx->d_scan_tmp.ensure((g_new - ctx->g_tab) / 1024 + 8));
+    plan_extend_table(ctx->sc, ctx->g_tab, g_new, ctx->d_gnmol.p, ctx->d_goff.p, ctx->d_scan_tmp.p, ctx->st);
+    uint64_t total = 0;
+    CU(cudaMemcpyAsync(&total, ctx->d_goff.p + g_new, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaGetLastError());
+    ctx->g_tab = g_new;
+    return plan_reserve(ctx, total + 1, keep_mol);
+}
+
 extern "C" int32_t mmk_plan(mmk_ctx *ctx, mmk_plan_info *out) {
     if (!ctx) return MMK_ERR_INVALID_ARG;
     const double t_begin = now_ms();
@@ -939,6 +970,7 @@ extern "C" int32_t mmk_plan(mmk_ctx *ctx, mmk_plan_info *out) {
     const uint32_t K = (uint32_t)ctx->schemas.size();
     for (auto &s : ctx->schemas) s.current = 0;
     ctx->placed = false;
+    ctx->planned = false;
     ctx->tile_cursor = 0;
     ctx->epoch_nlive.clear();
 
@@ -949,59 +981,65 @@ extern "C" int32_t mmk_plan(mmk_ctx *ctx, mmk_plan_info *out) {
 
     std::vector<uint16_t> live(K);
     for (uint32_t i = 0; i < K; ++i) live[i] = (uint16_t)i;
-    DBuf<uint16_t> d_live, d_lpos;
-    DBuf<int64_t> d_need;
-    DBuf<uint32_t> d_nmol;
-    DBuf<uint64_t> d_off, d_tmp;
-    DBuf<unsigned long long> d_hist, d_cross;
-    DBuf<uint8_t> d_res;
-    CU(d_live.ensure(K ? K : 1));
-    CU(d_lpos.ensure(65536));
-    CU(d_need.ensure(K ? K : 1));
-    CU(d_cross.ensure(K ? K : 1));
-    size_t res_bytes = sizeof(BatchResult) + (size_t)K * 8;
-    CU(d_res.ensure(res_bytes));
+    CU(ctx->d_live.ensure(K ? K : 1));
+    CU(ctx->d_lpos.ensure(65536));
+    CU(ctx->d_need.ensure(K ? K : 1));
+    CU(ctx->d_first_err.ensure(1));
+    const size_t res_bytes = sizeof(BatchResult) + (size_t)K * 8;
+    CU(ctx->d_res.ensure(res_bytes));
     std::vector<uint8_t> h_res(res_bytes);
     std::vector<int64_t> need(K);
 
-    uint64_t g0 = 0, n_mol = 0;
+    // the group table is rebuilt by every call (no state is carried between runs)
+    ctx->g_tab = 0;
+    CU(ctx->d_goff.ensure(1));
+    CU(cudaMemsetAsync(ctx->d_goff.p, 0, 8, ctx->st));
+
+    uint64_t g0 = 0, n_mol = 0, total_need = 0;
+    for (auto &s : ctx->schemas) total_need += (uint64_t)std::max<int64_t>(s.required, 0);
     uint64_t B = Bmin;
     int64_t n_batches = 0, n_epochs = 0;
     bool live_dirty = true;
-    double inserts_per_group_schema = 0.0;  // running estimate, per live schema
+    double inserts_per_group = 0.0;  // running estimate, all live schemas together
     while (!live.empty()) {
         const uint32_t n_live = (uint32_t)live.size();
         if (live_dirty) {
-            CU(cudaMemcpyAsync(d_live.p, live.data(), n_live * 2, cudaMemcpyHostToDevice, ctx->st));
+            CU(cudaMemcpyAsync(ctx->d_live.p, live.data(), n_live * 2, cudaMemcpyHostToDevice, ctx->st));
+            plan_set_live(ctx->d_live.p, n_live, ctx->d_lpos.p, ctx->st);
             ctx->epoch_nlive.push_back(n_live);
             if (ctx->epoch_nlive.size() > 65535) return fail(ctx, MMK_ERR_UNSUPPORTED, "more than 65535 pruning epochs");
             live_dirty = false;
         }
         int64_t min_need = INT64_MAX;
+        uint64_t remaining_need = 0;
         for (uint32_t i = 0; i < n_live; ++i) {
             need[i] = ctx->schemas[live[i]].required - ctx->schemas[live[i]].current;
             min_need = std::min(min_need, need[i]);
+            remaining_need += (uint64_t)std::max<int64_t>(need[i], 0);
         }
         // size the batch to reach the next pruning point with a small overshoot
-        if (inserts_per_group_schema > 0.0 && min_need > 0) {
-            double est = (double)min_need / inserts_per_group_schema;
+        if (inserts_per_group > 0.0 && min_need > 0) {
+            double est = (double)min_need * (double)n_live / inserts_per_group;
             B = (uint64_t)std::min<double>((double)Bmax, std::max<double>((double)Bmin, est * 1.03 + 2048.0));
         } else if (min_need <= 0)
             B = Bmin;
         const uint32_t nb = (uint32_t)B;
+        {   // table: this batch, and — once the rate is known — the expected rest of the run in one extension
+            uint64_t want = g0 + nb;
+            if (inserts_per_group > 0.0) want = std::max<uint64_t>(want, g0 + (uint64_t)((double)remaining_need / inserts_per_group * 1.05) + 4096);
+            if (g0 + nb > ctx->g_tab) {
+                int32_t rc = ensure_group_table(ctx, want, n_mol);
+                if (rc) return rc;
+            }
+        }
         const uint64_t max_mol = (uint64_t)nb * max_nmol;
-        int32_t rc = plan_reserve(ctx, n_mol + max_mol, n_mol);
-        if (rc) return rc;
-        CU(d_nmol.ensure(nb));
-        CU(d_off.ensure((size_t)nb + 1));
-        CU(d_tmp.ensure((size_t)nb / 1024 + 8));
-        CU(d_hist.ensure((size_t)plan_hist_chunks(max_mol) * n_live));
-        CU(cudaMemcpyAsync(d_need.p, need.data(), n_live * 8, cudaMemcpyHostToDevice, ctx->st));
-        plan_batch(ctx->sc, ctx->d_sch.p, d_live.p, n_live, (uint16_t)(ctx->epoch_nlive.size() - 1), g0, nb, d_nmol.p, d_off.p,
-                   d_tmp.p, plan_dev(ctx), n_mol, max_mol, d_need.p, d_hist.p, d_cross.p, d_lpos.p, (BatchResult *)d_res.p,
-                   ctx->st);
-        size_t rb = sizeof(BatchResult) + (size_t)(n_live ? n_live - 1 : 0) * 8;
-        CU(cudaMemcpyAsync(h_res.data(), d_res.p, rb, cudaMemcpyDeviceToHost, ctx->st));
+        CU(ctx->d_hist.ensure((size_t)plan_hist_chunks(max_mol) * n_live));
+        CU(cudaMemcpyAsync(ctx->d_need.p, need.data(), n_live * 8, cudaMemcpyHostToDevice, ctx->st));
+        plan_batch(ctx->sc, ctx->d_sch.p, ctx->d_live.p, ctx->d_lpos.p, n_live, (uint16_t)(ctx->epoch_nlive.size() - 1), g0, nb,
+                   ctx->d_gnmol.p, ctx->d_goff.p, plan_dev(ctx), max_mol, ctx->d_need.p, ctx->d_hist.p, ctx->d_first_err.p,
+                   (BatchResult *)ctx->d_res.p, ctx->st);
+        const size_t rb = sizeof(BatchResult) + (size_t)(n_live ? n_live - 1 : 0) * 8;
+        CU(cudaMemcpyAsync(h_res.data(), ctx->d_res.p, rb, cudaMemcpyDeviceToHost, ctx->st));
         CU(cudaStreamSynchronize(ctx->st));
         CU(cudaGetLastError());
         ++n_batches;
@@ -1017,9 +1055,8 @@ extern "C" int32_t mmk_plan(mmk_ctx *ctx, mmk_plan_info *out) {
             batch_inserts += r->sums[i];
         }
         n_mol += r->n_commit;
-        uint64_t groups_done = (r->cut_group == ~0ull) ? nb : (r->cut_group - g0 + 1);
-        if (groups_done > 0 && batch_inserts > 0)
-            inserts_per_group_schema = (double)batch_inserts / (double)groups_done / (double)n_live;
+        const uint64_t groups_done = (r->cut_group == ~0ull) ? nb : (r->cut_group - g0 + 1);
+        if (groups_done > 0 && batch_inserts > 0) inserts_per_group = (double)batch_inserts / (double)groups_done;
         g0 += groups_done;
         if (r->cut_group != ~0ull) {  // filter!(is_incomplete, schema), Main.jl:58
             std::vector<uint16_t> nl;
@@ -1037,8 +1074,8 @@ extern "C" int32_t mmk_plan(mmk_ctx *ctx, mmk_plan_info *out) {
     ctx->n_groups = g0;
     // first pair of every molecule
     CU(ctx->d_read_off.ensure(n_mol + 1));
-    CU(d_tmp.ensure((size_t)n_mol / 1024 + 8));
-    exclusive_scan_u32(ctx->p_nfrags.p, ctx->d_read_off.p, n_mol, d_tmp.p, ctx->st);
+    CU(ctx->d_scan_tmp.ensure((size_t)n_mol / 1024 + 8));
+    exclusive_scan_u32(ctx->p_nfrags.p, ctx->d_read_off.p, n_mol, ctx->d_scan_tmp.p, ctx->st);
     uint64_t total = 0;
     CU(cudaMemcpyAsync(&total, ctx->d_read_off.p + n_mol, 8, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
@@ -1103,7 +1140,7 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     const double t_begin = now_ms();
     double t_phase = t_begin;
     // shard bounds
-    DBuf<uint64_t> d_bounds;
+    DBuf<uint64_t> &d_bounds = ctx->s_bounds;
     CU(d_bounds.ensure((size_t)std::max(ctx->world, 1024) + 1));
     shard_bounds(ctx->d_read_off.p, ctx->n_mol, ctx->n_pairs, ctx->world, d_bounds.p, ctx->st);
     std::vector<uint64_t> bounds((size_t)ctx->world + 1);
@@ -1140,7 +1177,8 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
         uint32_t tp = 64;
         if (const char *e = getenv("MMK_TILE_PAIRS")) tp = (uint32_t)atoi(e);
         tp = std::max(8u, std::min(64u, tp));
-        while (tp > 8 && (uint64_t)tp * max_rec + 32 > 40 * 1024) tp -= 8;
+        while (tp & (tp - 1)) tp &= tp - 1;  // power of two: kernels turn pair index → tile with a shift
+        while (tp > 8 && (uint64_t)tp * max_rec + 32 > 40 * 1024) tp >>= 1;
         ctx->tile_pairs = tp;
         ctx->stage_cap = (uint32_t)(((uint64_t)tp * max_rec + 32 + 15) & ~15ull);
         if (!ctx->fast_ok) ctx->stage_cap = 16;
@@ -1150,7 +1188,7 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     CU(ctx->d_mol.ensure(ctx->s_nmol + 1));
     CU(ctx->d_text.ensure((size_t)(ctx->s_nmol + 1) * ctx->text_stride));
     CU(ctx->d_roff_l.ensure(ctx->s_nmol + 2));
-    DBuf<unsigned long long> d_err;
+    DBuf<unsigned long long> &d_err = ctx->s_err;
     CU(d_err.ensure(3));
     unsigned long long init[3] = {~0ull, 0, 0};
     CU(cudaMemcpyAsync(d_err.p, init, sizeof init, cudaMemcpyHostToDevice, ctx->st));
@@ -1172,13 +1210,16 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
                 CU(cudaMemcpyAsync(&sp[k], ctx->d_roff_l.p + sb[k], 8, cudaMemcpyDeviceToHost, ctx->st));
             CU(cudaStreamSynchronize(ctx->st));
             for (int k = 0; k < n_seg; ++k) max_pairs = std::max(max_pairs, sp[k + 1] - sp[k]);
-            CU(ctx->d_tmp_x.ensure(max_pairs + 1));
-            CU(ctx->d_tmp_g.ensure(max_pairs + 1));
+            CU(ctx->d_tmp.ensure(place_tmp_bytes(max_pairs)));
+            CU(ctx->d_acc_i.ensure(ctx->s_nmol + 1));
+            CU(ctx->d_acc_f.ensure(ctx->s_nmol + 1));
+            CU(cudaMemsetAsync(ctx->d_acc_i.p, 0, (ctx->s_nmol + 1) * 4, ctx->st));
+            CU(cudaMemsetAsync(ctx->d_acc_f.p, 0, (ctx->s_nmol + 1) * 8, ctx->st));
             for (int k = 0; k < n_seg; ++k)
                 place_segment(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->mol0, (uint32_t)ctx->s_nmol, (uint32_t)sb[k],
                               (uint32_t)sb[k + 1], sp[k], sp[k + 1], ctx->d_roff_l.p, ctx->d_tile_mol0.p, ctx->n_tiles,
-                              ctx->tile_pairs, ctx->d_tmp_x.p, ctx->d_tmp_g.p, ctx->d_ins.p, ctx->d_mol.p, ctx->d_text.p,
-                              ctx->text_stride, d_err.p, ctx->st);
+                              ctx->tile_pairs, ctx->d_tmp.p, ctx->d_acc_i.p, ctx->d_acc_f.p, ctx->d_ins.p, ctx->d_mol.p,
+                              ctx->d_text.p, ctx->text_stride, d_err.p, ctx->st);
         }
     }
     unsigned long long herr[3];
@@ -1193,8 +1234,8 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     ctx->place_info.phase_ms[0] = now_ms() - t_phase;
     t_phase = now_ms();
     // tile offsets
-    DBuf<uint32_t> d_sum1, d_sum2;
-    DBuf<uint64_t> d_tmp;
+    DBuf<uint32_t> &d_sum1 = ctx->s_sum1, &d_sum2 = ctx->s_sum2;
+    DBuf<uint64_t> &d_tmp = ctx->d_scan_tmp;
     CU(d_sum1.ensure((size_t)ctx->n_tiles + 1));
     CU(d_sum2.ensure((size_t)ctx->n_tiles + 1));
     CU(d_tmp.ensure((size_t)ctx->n_tiles / 1024 + 8));
@@ -1255,8 +1296,8 @@ static int32_t prepare_chunks(mmk_ctx *ctx) {
         ctx->out_cap = want;
     }
     const uint32_t max_chunks = 1 << 16;
-    DBuf<uint32_t> d_bounds, d_n;
-    DBuf<uint64_t> d_b1, d_b2;
+    DBuf<uint32_t> &d_bounds = ctx->s_cb, &d_n = ctx->s_cn;
+    DBuf<uint64_t> &d_b1 = ctx->s_b1, &d_b2 = ctx->s_b2;
     CU(d_bounds.ensure(max_chunks + 1));
     CU(d_b1.ensure(max_chunks + 1));
     CU(d_b2.ensure(max_chunks + 1));

@@ -117,25 +117,32 @@ void pack_pieces(const char *d_master, const char *d_alt, const int64_t *d_dst, 
 void unpack(const uint32_t *d_words, int64_t len, int bpb, char *d_out, cudaStream_t st);
 
 void exclusive_scan_u32(const uint32_t *d_in, uint64_t *d_out /*[n+1]*/, uint64_t n, uint64_t *d_tmp /*[>= n/1024+2]*/,
-                        cudaStream_t st);
+                        cudaStream_t st, const uint64_t *d_base = nullptr);
 
-// d_hist needs plan_hist_chunks(max_mol) * n_live entries, d_cross n_live, d_lpos 65536.
+// Planning. The group table (n_mol per barcode group, molecule offsets) does not depend on the live
+// set, so molecule indices are final whatever the pruning epochs turn out to be.
 uint32_t plan_hist_chunks(uint64_t max_molecules);
-void plan_batch(const SimConst &sc, const SchemaDev *d_sch, const uint16_t *d_live, uint32_t n_live, uint16_t epoch,
-                uint64_t g0, uint32_t n_groups, uint32_t *d_nmol, uint64_t *d_off, uint64_t *d_scan_tmp,
-                PlanDev plan, uint64_t mol_base, uint64_t max_mol, const int64_t *d_need, unsigned long long *d_hist,
-                unsigned long long *d_cross, uint16_t *d_lpos, BatchResult *d_res, cudaStream_t st);
+void plan_extend_table(const SimConst &sc, uint64_t g_lo, uint64_t g_hi, uint32_t *d_nmol, uint64_t *d_off, uint64_t *d_scan_tmp,
+                       cudaStream_t st);
+void plan_set_live(const uint16_t *d_live, uint32_t n_live, uint16_t *d_lpos /*[65536]*/, cudaStream_t st);
+// d_hist needs plan_hist_chunks(max_mol) * n_live entries
+void plan_batch(const SimConst &sc, const SchemaDev *d_sch, const uint16_t *d_live, const uint16_t *d_lpos, uint32_t n_live,
+                uint16_t epoch, uint64_t g0, uint32_t n_groups, const uint32_t *d_nmol, const uint64_t *d_off, PlanDev plan,
+                uint64_t max_mol, const int64_t *d_need, unsigned long long *d_hist, unsigned long long *d_first_err,
+                BatchResult *d_res, cudaStream_t st);
 
 void shard_bounds(const uint64_t *d_read_off, uint64_t n_mol, uint64_t n_pairs, int32_t world, uint64_t *d_bounds /*[world+1]*/,
                   cudaStream_t st);
 
 void place_prepare(uint64_t mol0, uint32_t n_mol, const uint64_t *d_read_off_global, uint64_t *d_read_off_local,
                    uint32_t *d_tile_mol0, uint32_t tile_pairs, cudaStream_t st);
+size_t place_tmp_bytes(uint64_t max_pairs);
+// d_acc_i / d_acc_f: per shard molecule, zeroed by the caller before the first segment
 void place_segment(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint32_t m_lo,
                    uint32_t m_hi, uint64_t pair_lo, uint64_t pair_hi, const uint64_t *d_read_off_local,
-                   const uint32_t *d_tile_mol0, uint32_t n_tiles, uint32_t tile_pairs, double *d_tmp_x, uint64_t *d_tmp_g,
-                   uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride, unsigned long long *d_err,
-                   cudaStream_t st);
+                   const uint32_t *d_tile_mol0, uint32_t n_tiles, uint32_t tile_pairs, void *d_tmp, uint32_t *d_acc_i,
+                   unsigned long long *d_acc_f, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
+                   unsigned long long *d_err, cudaStream_t st);
 
 void tile_sums(const EmitArgs &a, uint32_t n_tiles_total, uint32_t *d_sum1, uint32_t *d_sum2, unsigned long long *d_gather,
                cudaStream_t st);

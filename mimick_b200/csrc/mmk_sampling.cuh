@@ -218,7 +218,7 @@ __device__ __forceinline__ uint32_t molecule_place(const SimConst &sc, uint64_t 
         rec.put(MMK_P_GAP, (uint32_t)(remaining + 1), gap);
         uint64_t st = cursor + gap;
         uint32_t li = MMK_INS_LEN(ins[i].y);
-        uint32_t dm = tr.mol - tr.tile_mol0[(tr.pair0 + i) / tr.tile_pairs];
+        uint32_t dm = tr.mol - tr.tile_mol0[(tr.pair0 + i) >> (31 - __clz(tr.tile_pairs))];  // power-of-two tiles
         ins[i] = make_uint2((uint32_t)st, li | (dm << 24));
         cursor = st + li;
         remaining -= gap;
