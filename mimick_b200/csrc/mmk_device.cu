@@ -706,20 +706,28 @@ __global__ void k_place_chain(SimConst sc, const SchemaDev *__restrict__ sch, Pl
         const uint32_t tshift = 31 - __clz(tile_pairs);  // tile_pairs is a power of two
         uint32_t tile = (uint32_t)(ro >> tshift), tm0 = tile_mol0[tile];
         uint32_t to_next = tile_pairs - (uint32_t)(ro & (tile_pairs - 1));  // pairs left in the current tile
+        // R2 window bstop - r2 + 1 : bstop must start at >= 1 (Julia BoundsError otherwise); only molecules that
+        // start within r2 of position 1 can violate it
+        const bool check_r2 = !sc.strict && start <= (int64_t)sc.r2;
+        // the loop is latency-bound on its own loads: keep two 128-byte lines of the scratch in flight
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(tp));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + 8));
+        PairTmp e = tp[0];
         for (uint32_t k = 0; k < nfrags; ++k) {
+            if ((k & 7u) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + k + 16));
+            const PairTmp nxt = tp[k + 1 < nfrags ? k + 1 : k];
             if (to_next == 0) {
                 tm0 = tile_mol0[++tile];
                 to_next = tile_pairs;
             }
             --to_next;
-            const PairTmp e = tp[k];
-            uint64_t gap = mmk_bits_to_index(e.bits, remaining + 1);
-            uint64_t st = cursor + gap;
-            in[k] = make_uint2((uint32_t)st, e.len | ((i - tm0) << 24));
+            const uint32_t gap = (uint32_t)mmk_bits_to_index(e.bits, remaining + 1);
+            const uint32_t st = (uint32_t)cursor + gap;
+            in[k] = make_uint2(st, e.len | ((i - tm0) << 24));
             cursor = st + e.len;
             remaining -= gap;
-            // R2 window bstop - r2 + 1 : bstop must start at >= 1 (Julia BoundsError otherwise)
-            if (!sc.strict && start + (int64_t)st + (int64_t)e.len - (int64_t)sc.r2 < 1) status = MMK_ERR_BOUNDS;
+            if (check_r2 && start + (int64_t)st + (int64_t)e.len - (int64_t)sc.r2 < 1) status = MMK_ERR_BOUNDS;
+            e = nxt;
         }
         // quality lengths follow the molecule's FIRST reads (FormatFASTQ.jl:14)
         if (!status) (void)check_windows(in, 1, start, n, sc.r1, sc.r2, sc.strict, q1, q2);
