@@ -269,16 +269,10 @@ def cuda_arm(args):
         for nm, hap, h in genome:
             sim.add_contig(nm, (h.data_ptr(), h.numel()), hap)
 
-    counts = torch.zeros(4, dtype=torch.int64, device=dev)
-    gathered = [torch.zeros(4, dtype=torch.int64, device=dev) for _ in range(world)]
-
     def exchange(place):
-        """the path's only collective: per-rank (bytes_R1, bytes_R2, n_pairs, first_read_id)"""
-        if world == 1:
-            return [(place.r1_bytes, place.r2_bytes, place.n_pairs, place.first_pair)]
-        counts.copy_(torch.tensor([place.r1_bytes, place.r2_bytes, place.n_pairs, place.first_pair], dtype=torch.int64))
-        dist.all_gather(gathered, counts)
-        return [tuple(int(x) for x in g.tolist()) for g in gathered]
+        """the path's only collective: per-rank (bytes_R1, bytes_R2, n_pairs, first_read_id) over NCCL"""
+        lay = M.exchange_counts(M.RankCounts(place.r1_bytes, place.r2_bytes, place.n_pairs, place.first_pair), device=dev)
+        return [(c.r1_bytes, c.r2_bytes, c.n_pairs, c.first_pair) for c in lay.counts]
 
     state = {}
 

@@ -7,6 +7,7 @@ reference's `mimick(...)` API; importing it requires the built library — there
 from . import _lib
 from ._lib import MimickError
 from .api import SampleOutput, Simulator, Vcf, interperet_format, mimick
+from .dist import RankCounts, ShardLayout, exchange_counts, layout_from_counts, samples_for_rank
 
 __all__ = ["mimick", "Simulator", "Vcf", "MimickError", "SampleOutput", "interperet_format"]
 

@@ -22,6 +22,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
+from .dist import samples_for_rank
 from ._lib import Chunk, MimickError, MolRecord, Params, PlaceInfo, PlanInfo, SchemaInfo
 
 VARIATE_DTYPE = np.dtype([("tag", "<u4"), ("aux", "<u4"), ("bits", "<u8")])
@@ -397,7 +398,7 @@ def mimick(*args, prefix: str = "simulated/SIM", outdir: str = "simulated", quie
     os.makedirs(outdir, exist_ok=True)
     with Simulator(fmt, **kw) as sim:
         sim.load_fasta(fasta, 1)  # master schema once, masking included (Main.jl:92)
-        for si in range(rank, len(v.samples), world):  # Threads.@threads over samples → samples over GPUs
+        for si in samples_for_rank(len(v.samples), rank, world):  # Threads.@threads over samples → samples over GPUs
             sim.apply_vcf_sample(v, si)
             plan = sim.plan()
             sim.set_shard(0, 1)

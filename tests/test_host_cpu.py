@@ -1,0 +1,131 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports exactly what include/*.h declares,
+the host-only entry points behave like the reference's, the text readers agree with the oracle's
+independent parsers, and the library refuses to run without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import mimick_b200
+    from mimick_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "mimick_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(mmk_[a-z0-9_]+)\s*\(", hdr)) - {"mmk_chunk_cb"}
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (mmk_[a-z0-9_]+)", out))
+    assert declared <= exported, declared - exported
+    L = _lib.load()
+    assert L.mmk_abi_version() == 1
+    # no torch / python types in the ABI: the library does not even link libpython or libtorch
+    ldd = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "python" not in ldd and "torch" not in ldd
+
+
+def test_error_codes_are_shared_with_the_oracle():
+    from mimick_b200 import _lib
+    src = open(os.path.join(ROOT, "oracle", "mimick_oracle.c")).read()
+    orc = {k: int(v) for k, v in re.findall(r"ORC_(ERR_[A-Z_]+|OK) = (\d+)", src)}
+    for code, name in _lib.STATUS_NAMES.items():
+        assert orc[name.replace("MMK_", "")] == code
+
+
+def test_params_default_and_formats():
+    import mimick_b200 as M
+    from mimick_b200 import _lib
+    L = _lib.load()
+    p = _lib.Params()
+    L.mmk_params_default(C.byref(p))
+    # Julia defaults of Main.jl:24
+    assert (p.coverage, p.n_molecules, p.mol_coverage, p.mol_length) == (30.0, 2, 0.2, 80000)
+    assert (p.insert_length, p.insert_stdev, p.length_r1, p.length_r2) == (500, 50, 150, 150)
+    assert (p.singletons, p.circular, p.attempts, p.seed, p.mask) == (0.70, 0, 25, -1, 0)
+    assert p.struct_size == C.sizeof(_lib.Params)
+    enum = {"stlfr": 0, "haplotagging": 1, "tellseq": 2, "tenx": 3, "standard": 4}
+    for fmt in ["haplotagging", "stlfr", "tellseq", "tenx", "10x", "standard", "standard:haplotagging", "standard:stlfr"]:
+        bc, fq = O.interperet_format(fmt)
+        assert M.interperet_format(fmt) == (enum[bc], enum[fq])
+    with pytest.raises(M.MimickError) as e:
+        M.interperet_format("pacbio")
+    assert e.value.status == 2
+    assert L.mmk_check_variant_path(b"calls.bcf") == 6 and L.mmk_check_variant_path(b"x.BCF") == 6
+    assert L.mmk_check_variant_path(b"calls.vcf.gz") == 0
+
+
+def test_vcf_reader_matches_the_oracle_parser(ref_vcf, tmp_path):
+    import mimick_b200 as M
+    v = M.Vcf(ref_vcf)
+    o = O.read_vcf(ref_vcf)
+    assert v.samples == o.samples and v.contigs == o.contigs and v.ploidy == o.ploidy and v.n_records == len(o.records)
+    with pytest.raises(M.MimickError) as e:
+        M.Vcf(str(tmp_path / "none.vcf"))
+    assert e.value.status == 9
+    bad = tmp_path / "bad.vcf"
+    bad.write_text("##fileformat=VCFv4.2\n##contig=<ID=c>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\ts0\n"
+                   "c\t5\t.\tA\tT\t.\t.\t.\tGT\t./.\n")
+    with pytest.raises(M.MimickError) as e:   # parse(UInt8, ".") throws in the reference too
+        M.Vcf(str(bad))
+    assert e.value.status == 10
+
+
+def test_no_cpu_fallback():
+    """On a machine without a CUDA device the product must fail loudly, not compute on the CPU."""
+    import torch
+    import mimick_b200 as M
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(M.MimickError) as e:
+        M.Simulator("haplotagging", seed=1)
+    assert e.value.status == 13 and "no CPU path" in str(e.value)
+    src = "".join(open(os.path.join(ROOT, "mimick_b200", f)).read() for f in ("api.py", "_lib.py", "dist.py", "__init__.py"))
+    assert "oracle" not in src.replace("the oracle", "")  # the product never imports the checker
+
+
+def test_shard_layout_logic():
+    import mimick_b200 as M
+    counts = [M.RankCounts(100, 90, 5, 0), M.RankCounts(40, 44, 2, 5), M.RankCounts(0, 0, 0, 7)]
+    lay = M.layout_from_counts(counts)
+    assert lay.r1_offset == [0, 100, 140] and lay.r2_offset == [0, 90, 134]
+    assert (lay.total_pairs, lay.total_r1_bytes, lay.total_r2_bytes) == (7, 140, 134)
+    with pytest.raises(ValueError):
+        M.layout_from_counts([M.RankCounts(1, 1, 5, 0), M.RankCounts(1, 1, 2, 4)])
+    assert M.samples_for_rank(7, 1, 4) == [1, 5] and M.samples_for_rank(7, 3, 8) == [3]
+    assert sorted(sum((M.samples_for_rank(7, r, 3) for r in range(3)), [])) == list(range(7))
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import mimick_b200 as M
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = M.RankCounts(1000 + rank, 2000 + rank, 10 * (rank + 1), 0 if rank == 0 else 10)
+    lay = M.exchange_counts(mine)
+    q.put((rank, lay.r1_offset, lay.r2_offset, lay.total_pairs, [c.first_pair for c in lay.counts]))
+    dist.destroy_process_group()
+
+
+def test_exchange_counts_world_size_2_gloo():
+    """The N>1 host path (the only collective of the hot path) on CPU: 2 processes, gloo."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, o1, o2, pairs, firsts in res:
+        assert o1 == [0, 1000] and o2 == [0, 2000] and pairs == 30 and firsts == [0, 10]

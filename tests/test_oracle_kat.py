@@ -1,0 +1,232 @@
+"""Pins the CPU oracle (oracle/mimick_oracle.c) to everything the reference offers that can be checked
+without running Julia: the literal format examples of its docs, hand-derived known answers on its own
+fixtures, Random123's Philox known-answer vectors, and the analytic laws of the
+distributions it samples.  The reference itself ships no golden outputs ("parity unpinned")."""
+import ctypes as C
+import re
+
+import numpy as np
+import pytest
+from scipy import stats
+
+import oracle as O
+from helpers import make_ci_haplotypes, random_bases, write_fasta
+
+
+def barcode(fmt, k):
+    buf = C.create_string_buffer(64)
+    n = O.lib().orc_barcode(O.FMT[fmt], k, buf)
+    return None if n < 0 else buf.value.decode()
+
+
+def test_philox_known_answers():
+    L = O.lib()
+    for ctr, key, want in [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+                           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+                           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+                            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]:
+        c = np.array(ctr, dtype=np.uint32)
+        k = np.array(key, dtype=np.uint32)
+        o = np.zeros(4, dtype=np.uint32)
+        L.orc_philox(c.ctypes.data, k.ctypes.data, o.ctypes.data)
+        assert tuple(int(x) for x in o) == want
+
+
+def test_deterministic_log_exp_accuracy():
+    L = O.lib()
+    rng = np.random.default_rng(0)
+    x = np.exp(rng.uniform(-700, 700, 20000))
+    got = np.array([L.orc_det_log(float(v)) for v in x])
+    assert np.max(np.abs(got - np.log(x)) / np.maximum(np.abs(np.log(x)), 1e-300)) < 1e-15
+    y = rng.uniform(-700, 700, 20000)
+    got = np.array([L.orc_det_exp(float(v)) for v in y])
+    assert np.max(np.abs(got - np.exp(y)) / np.exp(y)) < 1e-15
+
+
+def test_barcode_enumerators_match_docs_and_iterator_order():
+    # shapes from docs/algorithm.md:40-46; order = Iterators.product, first factor fastest (Barcodes.jl:12-34)
+    assert barcode("haplotagging", 0) == "A01C01B01D01"
+    assert barcode("haplotagging", 1) == "A02C01B01D01"
+    assert barcode("haplotagging", 95) == "A96C01B01D01"
+    assert barcode("haplotagging", 96) == "A01C02B01D01"
+    assert barcode("haplotagging", 96 ** 2) == "A01C01B02D01"
+    assert barcode("haplotagging", 96 ** 3) == "A01C01B01D02"
+    assert barcode("haplotagging", 96 ** 4 - 1) == "A96C96B96D96"
+    assert barcode("haplotagging", 96 ** 4) is None  # format_barcode(::Nothing) → error, Barcodes.jl:75
+    assert re.fullmatch(r"A\d\dC\d\dB\d\dD\d\d", barcode("haplotagging", 4242))  # like "A43C21B01D93"
+    assert barcode("stlfr", 0) == "1_1_1"
+    assert barcode("stlfr", 1999) == "2000_1_1"
+    assert barcode("stlfr", 2000) == "1_2_1"
+    assert barcode("stlfr", 4_000_000) == "1_1_2"
+    assert barcode("stlfr", 8_000_000_000) is None
+    assert barcode("tellseq", 0) == "A" * 18
+    assert barcode("tellseq", 1) == "T" + "A" * 17   # alphabet order A,T,G,C; leftmost fastest
+    assert barcode("tellseq", 2) == "G" + "A" * 17
+    assert barcode("tellseq", 3) == "C" + "A" * 17
+    assert barcode("tellseq", 4) == "AT" + "A" * 16
+    assert len(barcode("tenx", 12345)) == 16 and set(barcode("tenx", 12345)) <= set("ATGC")
+    assert barcode("tenx", 4 ** 16) is None
+
+
+def test_interperet_format_table():
+    # Common.jl:56-74
+    assert O.interperet_format("haplotagging") == ("haplotagging", "haplotagging")
+    assert O.interperet_format("stlfr") == ("stlfr", "stlfr")
+    assert O.interperet_format("tenx") == ("tenx", "tenx")
+    assert O.interperet_format("10x") == ("tenx", "tenx")
+    assert O.interperet_format("standard") == ("tellseq", "standard")
+    assert O.interperet_format("standard:haplotagging") == ("haplotagging", "standard")
+    assert O.interperet_format("standard:stlfr") == ("stlfr", "standard")
+    with pytest.raises(O.OracleError):
+        O.interperet_format("nanopore")
+
+
+def test_reads_required_on_reference_fixture(ref_fasta):
+    # -g 5 on the 1.5 Mbp contig → 25 000 pairs per haplotype
+    (name, seq), = O.read_fasta(ref_fasta)
+    assert name == "chr1" and len(seq) == 1_500_000 and seq.count(b"N") == 0
+    o = O.Oracle("haplotagging", coverage=5)
+    s, req = o.prepare_contig(seq, False, 0, 1)
+    assert req == 25000
+    o2 = O.Oracle("haplotagging", coverage=30, read_length=(150, 108))
+    assert o2.prepare_contig(seq, False, 0, 1)[1] == int((30 * 1_500_000 / ((150 + 108) // 2)) / 2)
+    with pytest.raises(O.OracleError) as e:  # fewer than round(0.95 * 300) unambiguous bases
+        o.prepare_contig(b"ACGT" * 50 + b"N" * 200, False, 0, 1)
+    assert e.value.code == 5
+
+
+def test_snp_painting_of_reference_vcf(ref_fasta, ref_vcf):
+    # per-sample-haplotype ALT counts and the first variants of tsk_0 / tsk_1
+    vcf = O.read_vcf(ref_vcf)
+    assert vcf.contigs == ["chr1"] and vcf.ploidy == 2 and len(vcf.records) == 13705
+    want = [(2069, 2123), (1997, 2134), (2046, 2110), (2102, 2057), (2071, 2082), (2116, 2150), (2082, 2117)]
+    master = O.read_fasta(ref_fasta)[0][1]
+    for si, (n1, n2) in enumerate(want):
+        v = O.sample_variants(vcf, si)
+        assert (len(v["chr1_1"]), len(v["chr1_2"])) == (n1, n2)
+    v1 = O.sample_variants(vcf, 1)["chr1_1"]
+    assert [(p, r, a) for p, t, r, a in v1[:2]] == [(187, "G", "A"), (192, "G", "A")]
+    v0 = O.sample_variants(vcf, 0)["chr1_1"]
+    assert v0[0][0] == 192
+    hap = O.Oracle.mutate(master, v1)
+    assert len(hap) == len(master) and hap[186:187] == b"A" and hap[191:192] == b"A" and master[186:187] == b"G"
+    diff = np.flatnonzero(np.frombuffer(hap, np.uint8) != np.frombuffer(master, np.uint8))
+    assert len(diff) == 1997  # every ALT differs from REF in the fixture
+
+
+def test_indel_splice_semantics():
+    # mutate!: all SNPs first, then non-SNPs in reverse file order on the current sequence (ProcessVariants.jl:170-176)
+    ref = b"AAAACCCCGGGGTTTT"
+    var = [(2, 0, "A", "T"), (5, 1, "CCC", "C"), (9, 1, "G", "GAT"), (13, 1, "TT", "AC")]
+    assert O.Oracle.mutate(ref, var) == b"ATAACCGATGGGACTT"
+    # REF span at the very end and an insertion at position 1
+    assert O.Oracle.mutate(b"ACGT", [(1, 1, "A", "TTA"), (4, 1, "T", "")]) == b"TTACG"
+
+
+def test_record_text_known_answers(ref_fasta, tmp_path):
+    """Hand-derived records (SURVEY §8c ii): every format's header for one molecule, R1 = revcomp of the
+    insert's left r1 bases, R2 = the insert's right r2 bases (Breakpoints.jl:99-100, FormatFASTQ.jl)."""
+    seq = O.read_fasta(ref_fasta)[0][1]
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    formats = {
+        "haplotagging": (b"/1\tBX:Z:A01C01B01D01", b"/2\tBX:Z:A01C01B01D01"),
+        "stlfr": (b"#1_1_1 1:N:0:ATGACA", b"#1_1_1 2:N:0:ATGACA"),
+        "tellseq": (b":AAAAAAAAAAAAAAAAAA 1:N:0:ATGACA", b":AAAAAAAAAAAAAAAAAA 2:N:0:ATGACA"),
+        "10x": (b"|AAAAAAAAAAAAAAAA 1:N:0:ATGACA", b"|AAAAAAAAAAAAAAAA 2:N:0:ATGACA"),
+        "standard": (b"/1\tVX:i:1\tBX:Z:AAAAAAAAAAAAAAAAAA", b"/2\tVX:i:1\tBX:Z:AAAAAAAAAAAAAAAAAA"),
+        "standard:stlfr": (b"/1\tVX:i:1\tBX:Z:1_1_1", b"/2\tVX:i:1\tBX:Z:1_1_1"),
+    }
+    for fmt, (t1, t2) in formats.items():
+        res = O.mimick_single([ref_fasta], fmt, seed=3, coverage=0.05, attempts=300, singletons=0.0)
+        m = res.molecules[0]
+        bs, be = int(res.insert_start[0]), int(res.insert_stop[0])
+        head = b"@chr1:1|%d:%d|%d:%d" % (m["start"], m["start"] + m["molsize"], bs, be)
+        l1 = res.r1.split(b"\n")[:4]
+        l2 = res.r2.split(b"\n")[:4]
+        assert l1[0] == head + t1 and l2[0] == head + t2
+        want_r1 = seq[bs - 1:bs - 1 + 150].translate(comp)[::-1]
+        want_r2 = seq[be - 150:be]
+        bc = b"AAAAAAAAAAAAAAAA" if fmt == "10x" else b""
+        assert l1[1] == bc + want_r1 and l2[1] == want_r2
+        assert l1[2] == b"+" and l1[3] == b"I" * (150 + len(bc)) and l2[3] == b"I" * 150
+
+
+def test_structural_invariants(tmp_path):
+    fastas = make_ci_haplotypes(tmp_path, seed=5, big=40000)
+    res = O.mimick_single(fastas, "haplotagging", seed=9, coverage=10, attempts=300, singletons=0.2)
+    m = res.molecules
+    assert np.all(np.diff(m["barcode_index"]) == 1) and m["barcode_index"][0] == 0  # one barcode per molecule (Main.jl:51)
+    for mol in m[:400]:
+        a, b = mol["first_read"], mol["first_read"] + mol["n_frags"]
+        st, en = res.insert_start[a:b], res.insert_stop[a:b]
+        assert np.all(st[1:] > en[:-1])                       # ordered, non-overlapping
+        assert st[0] >= mol["start"] and en[-1] <= mol["start"] + mol["molsize"]   # inside position = start:start+L
+        assert np.all(en - st + 1 >= 200)                     # truncated(Normal, lower = 200)
+    for cur, req in zip(res.reads_current, res.reads_required):
+        assert cur >= req                                      # every schema reaches its target ...
+    recs = res.r1.split(b"\n")
+    assert len(recs) == 4 * len(res.insert_start) + 1 and recs[-1] == b""
+    assert all(r.startswith(b"@") for r in recs[0:-1:4]) and all(r == b"+" for r in recs[2:-1:4])
+
+
+def test_truncated_exponential_law():
+    L = O.lib()
+    n = 200000
+    out = np.zeros(n)
+    # rejection branch (tp > 0.25): molecule length, Exponential(80000) truncated below at 4000
+    L.orc_sample_trunc_exp(1, 80000.0, 4000.0, 0, 0.0, n, out.ctypes.data)
+    assert out.min() >= 4000
+    assert stats.kstest(out - 4000, stats.expon(scale=80000).cdf).pvalue > 1e-3  # memoryless
+    # both bounds: n_molecules Exponential(2) on [1, 5]
+    L.orc_sample_trunc_exp(2, 2.0, 1.0, 1, 5.0, n, out.ctypes.data)
+    d = stats.truncexpon(b=(5 - 1) / 2.0, loc=1, scale=2.0)
+    assert out.min() >= 1 and out.max() <= 5 and stats.kstest(out, d.cdf).pvalue > 1e-3
+    # quantile branch (tp <= 0.25): the tiny-contig case truncated(Exponential(2), 2.0, 2.008)
+    info = np.zeros(4)
+    L.orc_trunc_exp_info(2.0, 2.0, 1, 2.008, info.ctypes.data)
+    assert info[0] == 0 and 1e-8 < info[3] < 0.25 and abs(info[3] - (np.exp(-1) - np.exp(-1.004))) < 1e-12
+    L.orc_sample_trunc_exp(3, 2.0, 2.0, 1, 2.008, n, out.ctypes.data)
+    d = stats.truncexpon(b=0.008 / 2.0, loc=2.0, scale=2.0)
+    assert out.min() >= 2.0 and out.max() <= 2.008 and stats.kstest(out, d.cdf).pvalue > 1e-3
+    # lower > upper is the reference's error site (Breakpoints.jl:191)
+    L.orc_trunc_exp_info(2.0, 2.0, 1, 1.4, info.ctypes.data)
+    assert info[0] == 7
+
+
+def test_insert_size_law():
+    L = O.lib()
+    n = 200000
+    out = np.zeros(n)
+    L.orc_sample_insert(5, 500, 50, n, out.ctypes.data)
+    assert out.min() >= 200 and stats.kstest(out, stats.norm(500, 50).cdf).pvalue > 1e-3
+    L.orc_sample_insert(6, 300, 100, n, out.ctypes.data)   # truncation at 200 is 1 sigma below the mean
+    d = stats.truncnorm(a=(200 - 300) / 100, b=np.inf, loc=300, scale=100)
+    assert out.min() >= 200 and stats.kstest(out, d.cdf).pvalue > 1e-3
+
+
+def test_free_running_distributions(tmp_path):
+    """Free-running (Philox) mode against the reference's laws: molecule length, inserts per molecule,
+    singleton fraction, schema choice (north_star: KS / chi-square checks)."""
+    rng = np.random.default_rng(1)
+    p = str(tmp_path / "g.fa")
+    write_fasta(p, [("a", random_bases(rng, 3_000_000)), ("b", random_bases(rng, 3_000_000))])
+    res = O.mimick_single([p], "stlfr", seed=12, coverage=6, attempts=300, singletons=0.25)
+    m = res.molecules
+    # molecule length: Exponential(80000) | >= 4000, redrawn while > contig (3 Mbp: negligible), then trunc
+    assert stats.kstest(m["molsize"] - 4000 + rng.uniform(0, 1, len(m)), stats.expon(scale=80000).cdf).pvalue > 1e-3
+    single = m["n_frags"] == 1
+    assert abs(single.mean() - 0.25) < 4 * np.sqrt(0.25 * 0.75 / len(m))
+    # targets: uniform over the two live schemas until one completes
+    first = m[: len(m) // 3]
+    cnt = np.bincount(first["schema"], minlength=2)
+    assert stats.chisquare(cnt).pvalue > 1e-3
+    # insert length = trunc(Normal(500, 50))
+    lens = (res.insert_stop - res.insert_start + 1).astype(float)
+    assert abs(lens.mean() + 0.5 - 500) < 1.0 and abs(lens.std() - 50) < 1.0
+    # gaps are uniform on the remaining leeway: the first gap of a molecule is U{0..leeway}
+    nf = m["n_frags"].astype(np.int64)
+    ok = ~single
+    tot = np.add.reduceat(res.insert_stop - res.insert_start + 1, m["first_read"])
+    leeway = m["molsize"] + 1 - tot
+    u = (res.insert_start[m["first_read"]] - m["start"] + rng.uniform(0, 1, len(m))) / (leeway + 1)
+    assert stats.kstest(u[ok], "uniform").pvalue > 1e-3
