@@ -808,11 +808,10 @@ void place_segment(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uin
 #include "mmk_emit.cuh"
 namespace mmkdev {
 
-void tile_sums(const EmitArgs &a, uint32_t n_tiles_total, uint32_t *d_sum1, uint32_t *d_sum2, unsigned long long *d_gather,
-               cudaStream_t st) {
+void tile_prepare(const EmitArgs &a, uint32_t n_tiles_total, uint32_t *d_sum1, uint32_t *d_sum2, uint4 *d_fdesc,
+                  uint8_t *d_tile_flags, unsigned long long *d_gather, cudaStream_t st) {
     if (n_tiles_total == 0) return;
-    uint32_t threads = (a.tile_pairs + 31) / 32 * 32;
-    LAUNCH(k_tile_sums, n_tiles_total, threads, 0, st, a, n_tiles_total, d_sum1, d_sum2, d_gather);
+    LAUNCH(k_tile_prepare, n_tiles_total, 64, 0, st, a, n_tiles_total, d_sum1, d_sum2, d_fdesc, d_tile_flags, d_gather);
 }
 
 __global__ void k_find_tile(const uint64_t *off1, const uint64_t *off2, uint32_t tile0, uint32_t n_tiles, uint64_t cap,
@@ -874,14 +873,22 @@ void emit(const EmitArgs &a, cudaStream_t st) {
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
-    size_t smem = 2 * (size_t)a.stage_cap + EMIT_WARPS * EMIT_SCR;
+    size_t smem = 2 * (size_t)a.stage_cap;
     if (!attr_set[dev & 63]) {
-        cudaFuncSetAttribute(k_emit<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(k_emit<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_emit<2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_emit<4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_emit<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_emit<4, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr_set[dev & 63] = true;
     }
-    if (a.bpb == 2) LAUNCH((k_emit<2>), a.n_tiles, EMIT_THREADS, smem, st, a);
-    else LAUNCH((k_emit<4>), a.n_tiles, EMIT_THREADS, smem, st, a);
+    // one thread per (pair, header piece): 64-pair tiles run 256 threads, 32-pair tiles 128
+    if (a.tile_pairs > 32) {
+        if (a.bpb == 2) LAUNCH((k_emit<2, 256>), a.n_tiles, 256, smem, st, a);
+        else LAUNCH((k_emit<4, 256>), a.n_tiles, 256, smem, st, a);
+    } else {
+        if (a.bpb == 2) LAUNCH((k_emit<2, 128>), a.n_tiles, 128, smem, st, a);
+        else LAUNCH((k_emit<4, 128>), a.n_tiles, 128, smem, st, a);
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -22,9 +22,7 @@
 
 namespace mmkdev {
 
-constexpr int EMIT_THREADS = 256;
-constexpr int EMIT_WARPS = EMIT_THREADS / 32;
-constexpr int EMIT_MAX_TP = 64;
+constexpr int EMIT_MAX_TP = 64;  // pairs per tile <= threads / 4 (one thread per header piece)
 constexpr int EMIT_SCR = 192;  // per-warp header scratch bytes
 
 struct PairDesc {
@@ -123,39 +121,54 @@ __device__ void write_record_generic(const EmitArgs &a, const PairDesc &d, int r
 }
 
 // ------------------------------------------------------------------------------------------
-// tile sums: record lengths of every tile → byte offsets (after a scan)
+// tile preparation: one decode of every pair → record lengths per tile (byte offsets after a scan),
+// a packed 16-byte descriptor per pair for the emit kernel, and the tile's fast/general flag
 // ------------------------------------------------------------------------------------------
-__global__ void k_tile_sums(EmitArgs a, uint32_t n_tiles, uint32_t *sum1, uint32_t *sum2, unsigned long long *gather) {
-    __shared__ uint32_t s_acc[3];
-    uint32_t tile = blockIdx.x;
+// x: bstart   y: insert length | dm << 24   z: sb1 | sb2 << 16 (tile-relative record offsets)
+// w: P | SUF << 7 | schema << 13
+__global__ void __launch_bounds__(64) k_tile_prepare(EmitArgs a, uint32_t n_tiles, uint32_t *sum1, uint32_t *sum2, uint4 *fdesc,
+                                                     uint8_t *tile_flags, unsigned long long *gather) {
+    __shared__ uint32_t s_w[4];
+    const uint32_t tile = blockIdx.x;
     if (tile >= n_tiles) return;
-    uint64_t p0 = (uint64_t)tile * a.tile_pairs;
-    uint32_t np = (uint32_t)((a.n_pairs - p0) < a.tile_pairs ? (a.n_pairs - p0) : a.tile_pairs);
-    if (threadIdx.x == 0) s_acc[0] = s_acc[1] = s_acc[2] = 0;
-    __syncthreads();
-    uint32_t l1 = 0, l2 = 0, gb = 0;
+    const uint64_t p0 = (uint64_t)tile * a.tile_pairs;
+    const uint32_t np = (uint32_t)((a.n_pairs - p0) < a.tile_pairs ? (a.n_pairs - p0) : a.tile_pairs);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    PairDesc d;
+    d.regular = 1;
+    d.len1 = d.len2 = d.sq1 = d.sq2 = 0;
+    uint32_t schema = 0, iny = 0;
     if (threadIdx.x < np) {
-        PairDesc d;
-        decode_pair(a, p0 + threadIdx.x, a.tile_mol0[tile], d);
-        l1 = d.len1;
-        l2 = d.len2;
-        gb = (d.sq1 * a.bpb + 7) / 8 + (d.sq2 * a.bpb + 7) / 8;
+        const uint32_t m0 = a.tile_mol0[tile];
+        decode_pair(a, p0 + threadIdx.x, m0, d);
+        schema = a.mol[d.mol].schema;
+        iny = a.ins[p0 + threadIdx.x].y;
     }
-    for (int o = 16; o; o >>= 1) {
-        l1 += __shfl_down_sync(0xffffffffu, l1, o);
-        l2 += __shfl_down_sync(0xffffffffu, l2, o);
-        gb += __shfl_down_sync(0xffffffffu, gb, o);
+    uint32_t i1 = d.len1, i2 = d.len2, gb = (d.sq1 * a.bpb + 7) / 8 + (d.sq2 * a.bpb + 7) / 8;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y1 = __shfl_up_sync(0xffffffffu, i1, o), y2 = __shfl_up_sync(0xffffffffu, i2, o);
+        if (lane >= o) {
+            i1 += y1;
+            i2 += y2;
+        }
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&s_acc[0], l1);
-        atomicAdd(&s_acc[1], l2);
-        atomicAdd(&s_acc[2], gb);
+    for (int o = 16; o; o >>= 1) gb += __shfl_down_sync(0xffffffffu, gb, o);
+    if (lane == 31) {
+        s_w[warp * 2] = i1;
+        s_w[warp * 2 + 1] = i2;
     }
-    __syncthreads();
+    const int all_regular = __syncthreads_and((int)d.regular);
+    const uint32_t off1 = i1 - d.len1 + (warp ? s_w[0] : 0u), off2 = i2 - d.len2 + (warp ? s_w[1] : 0u);
+    const uint32_t bytes1 = s_w[0] + s_w[2], bytes2 = s_w[1] + s_w[3];
+    if (threadIdx.x < np)
+        fdesc[p0 + threadIdx.x] = make_uint4(d.bstart, iny, (off1 & 0xffffu) | (off2 << 16),
+                                             (uint32_t)d.P | ((uint32_t)d.SUF << 7) | (schema << 13));
+    if (lane == 0 && gb) atomicAdd(gather, (unsigned long long)gb);
     if (threadIdx.x == 0) {
-        sum1[tile] = s_acc[0];
-        sum2[tile] = s_acc[1];
-        atomicAdd(gather, (unsigned long long)s_acc[2]);
+        sum1[tile] = bytes1;
+        sum2[tile] = bytes2;
+        tile_flags[tile] = (uint8_t)(all_regular && bytes1 + 48u <= a.stage_cap && bytes2 + 48u <= a.stage_cap && bytes1 < 65536u &&
+                                     bytes2 < 65536u);
     }
 }
 
@@ -220,16 +233,23 @@ __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefe
 #define FD_D1(pk) (((pk) >> 22) & 0xfu)
 #define FD_D2(pk) (((pk) >> 26) & 0xfu)
 
-__device__ __forceinline__ void make_fast_desc(const EmitArgs &a, const PairDesc &d, uint32_t sb1, uint32_t sb2, FastDesc &f) {
-    f.sb1 = sb1;
-    f.sb2 = sb2;
-    f.bstart = d.bstart;
-    f.bend = d.bend;
-    const uint32_t ws1 = d.bstart - 1u, ws2 = d.bend - (uint32_t)a.r2;  // 0-based window starts
-    f.wbase1 = (uint32_t)d.word_off + (ws1 >= 15u ? (ws1 - 15u) >> 4 : 0u);
-    f.wbase2 = (uint32_t)d.word_off + (ws2 >= 15u ? (ws2 - 15u) >> 4 : 0u);
-    f.mol = d.mol;
-    f.pk = d.hdr | ((uint32_t)d.P << 8) | ((uint32_t)d.SUF << 16) | ((uint32_t)d.d1 << 22) | ((uint32_t)d.d2 << 26);
+// unpack the 16-byte descriptor k_tile_prepare wrote (x: bstart, y: len | dm << 24, z: sb1 | sb2 << 16,
+// w: P | SUF << 7 | schema << 13) into the emit kernel's working form
+__device__ __forceinline__ void make_fast_desc(const EmitArgs &a, const uint4 &q, uint32_t tile_m0, uint32_t base1, uint32_t base2,
+                                               FastDesc &f) {
+    const uint32_t bstart = q.x, bend = q.x + MMK_INS_LEN(q.y) - 1u;
+    const uint32_t P = q.w & 0x7fu, SUF = (q.w >> 7) & 0x3fu, schema = q.w >> 13;
+    const uint32_t d1 = ndigits_u32(bstart), d2 = ndigits_u32(bend);
+    const uint32_t word_off = (uint32_t)a.sch[schema].word_off;
+    f.sb1 = base1 + (q.z & 0xffffu);
+    f.sb2 = base2 + (q.z >> 16);
+    f.bstart = bstart;
+    f.bend = bend;
+    const uint32_t ws1 = bstart - 1u, ws2 = bend - (uint32_t)a.r2;  // 0-based window starts
+    f.wbase1 = word_off + (ws1 >= 15u ? (ws1 - 15u) >> 4 : 0u);
+    f.wbase2 = word_off + (ws2 >= 15u ? (ws2 - 15u) >> 4 : 0u);
+    f.mol = tile_m0 + MMK_INS_DM(q.y);
+    f.pk = (P + d1 + 1u + d2 + SUF) | (P << 8) | (SUF << 16) | (d1 << 22) | (d2 << 26);
 }
 
 // Phase 1 — one read pair, one warp (half-warp 0: R1, reverse complement; half-warp 1: R2, forward):
@@ -347,8 +367,9 @@ __device__ __forceinline__ void copy_out_bulk(uint32_t stage, uint32_t A, uint32
     if (c1 > c0) bulk_store(gbase + 16u * c0, stage + 16u * c0, 16u * (c1 - c0));
 }
 
-template <int BPB>
-__global__ void __launch_bounds__(EMIT_THREADS, 4) k_emit(const __grid_constant__ EmitArgs a) {
+template <int BPB, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_emit(const __grid_constant__ EmitArgs a) {
+    constexpr uint32_t EMIT_WARPS = THREADS / 32;
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint4 s_fa[EMIT_MAX_TP], s_fb[EMIT_MAX_TP];
     __shared__ uint32_t s_off1[EMIT_MAX_TP + 1], s_off2[EMIT_MAX_TP + 1];
@@ -356,76 +377,67 @@ __global__ void __launch_bounds__(EMIT_THREADS, 4) k_emit(const __grid_constant_
     const uint64_t p0 = (uint64_t)tile * a.tile_pairs;  // tile_pairs is a power of two
     const uint32_t np = (uint32_t)((a.n_pairs - p0) < a.tile_pairs ? (a.n_pairs - p0) : a.tile_pairs);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // every load of the prologue is independent of the others: one memory latency, not a chain
     const uint32_t tile_m0 = a.tile_mol0[tile];
-    // ---- decode: one thread per pair, descriptor stays in registers ---------------------------
-    PairDesc d;
-    d.regular = 1;
-    d.len1 = d.len2 = 0;
-    if (threadIdx.x < np) {
-        decode_pair(a, p0 + threadIdx.x, tile_m0, d);
-        if (BPB == 2 && d.regular) {  // start the loads phases 1 and 2 will need
-            const uint32_t ws1 = d.bstart - 1u, ws2 = d.bend - (uint32_t)a.r2;
-            const uint32_t *w1 = a.hap + d.word_off + (ws1 >= 15u ? (ws1 - 15u) >> 4 : 0u);
-            const uint32_t *w2 = a.hap + d.word_off + (ws2 >= 15u ? (ws2 - 15u) >> 4 : 0u);
-            prefetch_l1(w1);
-            prefetch_l1(w1 + 15);
-            prefetch_l1(w2);
-            prefetch_l1(w2 + 15);
-            prefetch_l1(a.text + (uint64_t)d.mol * a.text_stride);
-        }
-    }
-    // exclusive scan of record lengths within the tile (np <= 64: warps 0 and 1 hold the items)
-    if (threadIdx.x < EMIT_MAX_TP) {
-        uint32_t i1 = d.len1, i2 = d.len2;
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t y1 = __shfl_up_sync(0xffffffffu, i1, o), y2 = __shfl_up_sync(0xffffffffu, i2, o);
-            if (lane >= o) {
-                i1 += y1;
-                i2 += y2;
-            }
-        }
-        s_off1[threadIdx.x + 1] = i1;  // inclusive, per warp; warp 1 is rebased below
-        s_off2[threadIdx.x + 1] = i2;
-        if (threadIdx.x == 0) s_off1[0] = s_off2[0] = 0;
-    }
-    const int all_regular = __syncthreads_and((int)d.regular);
-    const uint32_t base1 = threadIdx.x >= 32 ? s_off1[32] : 0u, base2 = threadIdx.x >= 32 ? s_off2[32] : 0u;
-    const uint32_t off1 = (threadIdx.x < EMIT_MAX_TP ? s_off1[threadIdx.x + 1] - d.len1 : 0u) + base1;
-    const uint32_t off2 = (threadIdx.x < EMIT_MAX_TP ? s_off2[threadIdx.x + 1] - d.len2 : 0u) + base2;
-    const uint32_t bytes1 = s_off1[32] + s_off1[64], bytes2 = s_off2[32] + s_off2[64];
-    const uint64_t g1 = a.tile_off1[tile] - a.chunk_off1, g2 = a.tile_off2[tile] - a.chunk_off2;
+    const uint64_t t1 = a.tile_off1[tile], t2 = a.tile_off2[tile];
+    const uint32_t bytes1 = (uint32_t)(a.tile_off1[tile + 1] - t1), bytes2 = (uint32_t)(a.tile_off2[tile + 1] - t2);
+    const bool fast = BPB == 2 && a.fast_ok && a.tile_flags[tile];
+    const uint64_t g1 = t1 - a.chunk_off1, g2 = t2 - a.chunk_off2;
     const uint32_t A1 = (uint32_t)(g1 & 15u), A2 = (uint32_t)(g2 & 15u);
-    const bool fast = BPB == 2 && a.fast_ok && all_regular && A1 + bytes1 + 32u <= a.stage_cap && A2 + bytes2 + 32u <= a.stage_cap;
     if (!fast) {
         // general path: every record byte-wise, straight to global memory (warp per pair)
+        PairDesc d;
+        d.len1 = d.len2 = 0;
+        if (threadIdx.x < np) decode_pair(a, p0 + threadIdx.x, tile_m0, d);
+        if (threadIdx.x < EMIT_MAX_TP) {
+            uint32_t i1 = d.len1, i2 = d.len2;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t y1 = __shfl_up_sync(0xffffffffu, i1, o), y2 = __shfl_up_sync(0xffffffffu, i2, o);
+                if (lane >= o) {
+                    i1 += y1;
+                    i2 += y2;
+                }
+            }
+            s_off1[threadIdx.x + 1] = i1;
+            s_off2[threadIdx.x + 1] = i2;
+            if (threadIdx.x == 0) s_off1[0] = s_off2[0] = 0;
+        }
         __syncthreads();
-        if (threadIdx.x < np) {
-            s_off1[threadIdx.x] = off1;
-            s_off2[threadIdx.x] = off2;
+        const uint32_t base1 = s_off1[32], base2 = s_off2[32];
+        __syncthreads();
+        if (threadIdx.x < np) {  // exclusive offsets of the pair's two records inside the tile
+            s_off1[threadIdx.x + 1] -= d.len1 - (threadIdx.x >= 32 ? base1 : 0u);
+            s_off2[threadIdx.x + 1] -= d.len2 - (threadIdx.x >= 32 ? base2 : 0u);
         }
         __syncthreads();
         uint8_t *o1 = a.out1 + g1, *o2 = a.out2 + g2;
         for (uint32_t t = warp; t < np; t += EMIT_WARPS) {
             PairDesc e;
             decode_pair(a, p0 + t, tile_m0, e);
-            write_record_generic<BPB>(a, e, 1, o1 + s_off1[t], lane);
-            write_record_generic<BPB>(a, e, 2, o2 + s_off2[t], lane);
+            write_record_generic<BPB>(a, e, 1, o1 + s_off1[t + 1], lane);
+            write_record_generic<BPB>(a, e, 2, o2 + s_off2[t + 1], lane);
         }
         return;
     }
     // stage1 = smem[0, stage_cap), stage2 = smem[stage_cap, 2 stage_cap): record offsets index smem directly
     if (threadIdx.x < np) {
         FastDesc f;
-        make_fast_desc(a, d, A1 + off1, a.stage_cap + A2 + off2, f);
+        make_fast_desc(a, a.fdesc[p0 + threadIdx.x], tile_m0, A1, a.stage_cap + A2, f);
         s_fa[threadIdx.x] = make_uint4(f.sb1, f.sb2, f.bstart, f.bend);
         s_fb[threadIdx.x] = make_uint4(f.wbase1, f.wbase2, f.mol, f.pk);
+        // start the loads phases 1 and 2 will need
+        prefetch_l1(a.hap + f.wbase1);
+        prefetch_l1(a.hap + f.wbase1 + 15);
+        prefetch_l1(a.hap + f.wbase2);
+        prefetch_l1(a.hap + f.wbase2 + 15);
+        prefetch_l1(a.text + (uint64_t)f.mol * a.text_stride);
     }
     const uint32_t sm = (uint32_t)__cvta_generic_to_shared(smem);
     __syncthreads();
     for (uint32_t t = warp; t < np; t += EMIT_WARPS) emit_pair_seq(a, load_fast_desc(s_fa, s_fb, t), sm, lane);
     __syncthreads();
     {
-        const uint32_t role = threadIdx.x >> 6, t = threadIdx.x & 63u;  // 4 pieces x up to 64 pairs
+        const uint32_t role = threadIdx.x / (THREADS / 4), t = threadIdx.x % (THREADS / 4);  // 4 pieces x up to THREADS/4 pairs
         if (t < np) {
             const FastDesc f = load_fast_desc(s_fa, s_fb, t);
             const uint32_t rd_off = (a.fq_format == MMK_FMT_HAPLOTAGGING || a.fq_format == MMK_FMT_STANDARD) ? 1u : FD_SUF(f.pk) - 13u;

@@ -127,6 +127,8 @@ struct mmk_ctx {
     DBuf<uint64_t> d_roff_l;
     DBuf<uint64_t> d_tile_off1, d_tile_off2;
     DBuf<uint32_t> d_tile_mol0;
+    DBuf<uint4> d_fdesc;
+    DBuf<uint8_t> d_tile_flags;
     DBuf<uint8_t> d_tmp;      // placement scratch: (gap bits, insert length) per pair of one segment
     DBuf<uint32_t> d_acc_i;   // placement scratch: sum of insert lengths per molecule
     DBuf<unsigned long long> d_acc_f;  // ... and a 2^-16 fixed-point lower bound of their real sum
@@ -1113,6 +1115,8 @@ static EmitArgs base_args(mmk_ctx *c) {
     a.text = c->d_text.p;
     a.ins = c->d_ins.p;
     a.tile_mol0 = c->d_tile_mol0.p;
+    a.fdesc = c->d_fdesc.p;
+    a.tile_flags = c->d_tile_flags.p;
     a.stage_cap = c->stage_cap;
     a.fast_ok = c->fast_ok;
     a.tile_off1 = c->d_tile_off1.p;
@@ -1174,7 +1178,7 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
         uint32_t max_rec = max_hdr + inl + (uint32_t)std::max(q.length_r1, q.length_r2) * 2 + inl + 4;
         ctx->fast_ok = q.length_r1 >= 16 && q.length_r1 <= 192 && q.length_r2 >= 16 && q.length_r2 <= 192 && !q.force_generic &&
                        ctx->d_hap.cap < (1ull << 32);  // the fast path indexes the arena with 32-bit word offsets
-        uint32_t tp = 64;
+        uint32_t tp = 32;
         if (const char *e = getenv("MMK_TILE_PAIRS")) tp = (uint32_t)atoi(e);
         tp = std::max(8u, std::min(64u, tp));
         while (tp & (tp - 1)) tp &= tp - 1;  // power of two: kernels turn pair index → tile with a shift
@@ -1243,7 +1247,10 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     CU(ctx->d_tile_off2.ensure((size_t)ctx->n_tiles + 1));
     CU(cudaMemsetAsync(d_err.p, 0, 8, ctx->st));
     EmitArgs a = base_args(ctx);
-    tile_sums(a, ctx->n_tiles, d_sum1.p, d_sum2.p, d_err.p, ctx->st);
+    CU(ctx->d_fdesc.ensure(ctx->s_npairs + 1));
+    CU(ctx->d_tile_flags.ensure((size_t)ctx->n_tiles + 1));
+    a = base_args(ctx);
+    tile_prepare(a, ctx->n_tiles, d_sum1.p, d_sum2.p, ctx->d_fdesc.p, ctx->d_tile_flags.p, d_err.p, ctx->st);
     exclusive_scan_u32(d_sum1.p, ctx->d_tile_off1.p, ctx->n_tiles, d_tmp.p, ctx->st);
     exclusive_scan_u32(d_sum2.p, ctx->d_tile_off2.p, ctx->n_tiles, d_tmp.p, ctx->st);
     uint64_t tot[3] = {0, 0, 0};

@@ -77,6 +77,8 @@ struct EmitArgs {
     const uint8_t *text;
     const uint2 *ins;          // (start - mol.start, length) per shard pair
     const uint32_t *tile_mol0; // [n_tiles] first shard molecule of every tile
+    const uint4 *fdesc;        // [n_pairs] packed per-pair descriptors written by k_tile_prepare
+    const uint8_t *tile_flags; // [n_tiles] 1: every pair regular and the tile fits the stage (fast path)
     const uint64_t *tile_off1; // [n_tiles + 1] shard-relative byte offsets
     const uint64_t *tile_off2;
     uint8_t *out1, *out2;
@@ -144,8 +146,8 @@ void place_segment(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uin
                    unsigned long long *d_acc_f, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
                    unsigned long long *d_err, cudaStream_t st);
 
-void tile_sums(const EmitArgs &a, uint32_t n_tiles_total, uint32_t *d_sum1, uint32_t *d_sum2, unsigned long long *d_gather,
-               cudaStream_t st);
+void tile_prepare(const EmitArgs &a, uint32_t n_tiles_total, uint32_t *d_sum1, uint32_t *d_sum2, uint4 *d_fdesc,
+                  uint8_t *d_tile_flags, unsigned long long *d_gather, cudaStream_t st);
 void find_tile(const uint64_t *d_off1, const uint64_t *d_off2, uint32_t tile0, uint32_t n_tiles, uint64_t cap,
                uint32_t *d_out, cudaStream_t st);
 void emit(const EmitArgs &a, cudaStream_t st);
