@@ -201,7 +201,7 @@ def reference_arm(args):
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     genome = make_genome(args.workload, args.scale, dev, pin=False)
     threads = args.cpu_threads or min(os.cpu_count() or 1, 64)
-    per = args.cpu_pairs or 150_000
+    per = args.cpu_pairs or 600_000
     for _ in range(args.warmup):
         cpu_run(genome, args.workload, max(per // 10, 1000), threads)
     pairs = byts = 0
@@ -364,7 +364,7 @@ def cuda_arm(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = args.cpu_threads or min(os.cpu_count() or 1, 64)
-        per = args.cpu_pairs or 150_000
+        per = args.cpu_pairs or 4_000_000
         p, b, dt = cpu_run(genome, args.workload, per, threads)
         cpu = {"value": p / dt, "unit": "read pairs/s", "cores": threads, "kind": "port",
                "sample": f"{threads} independent simulations (one per host thread, the reference's task-per-sample shape), "
