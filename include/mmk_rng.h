@@ -283,20 +283,47 @@ MMK_HD double mmk_next_exp(mmk_stream *s) { return mmk_bits_to_exp(mmk_stream_ne
 MMK_HD uint64_t mmk_next_index(mmk_stream *s, uint64_t n) {
     return mmk_bits_to_index(mmk_stream_next64(s), n);
 }
-/* standard normal, Marsaglia polar method; each attempt consumes two draws (one block when
- * the stream is block-aligned, which it is for MMK_P_INSERT). */
-MMK_HD double mmk_next_normal(mmk_stream *s) {
-    for (;;) {
-        double u1 = mmk_bits_to_u01(mmk_stream_next64(s));
-        double u2 = mmk_bits_to_u01(mmk_stream_next64(s));
-        double v1 = MMK_SUB(MMK_ADD(u1, u1), 1.0);
-        double v2 = MMK_SUB(MMK_ADD(u2, u2), 1.0);
-        double q = MMK_ADD(MMK_MUL(v1, v1), MMK_MUL(v2, v2));
-        if (q < 1.0 && q > 0.0) {
-            double f = MMK_SQRT(MMK_DIV(MMK_MUL(-2.0, mmk_log(q)), q));
-            return MMK_MUL(v1, f);
-        }
+/* standard normal by inversion: z = Phi^-1(p), p = (k + 1/2) 2^-52 from the top 52 bits (0 < p < 1,
+ * both p and 1 - p exact).  Phi^-1 is P. J. Acklam's rational approximation (relative error < 1.15e-9,
+ * |Phi(z) - p| < 3e-10 — checked against scipy in tests), evaluated with single-rounded operations so the
+ * host and the device agree bit for bit.  One draw per normal, no rejection; 95 % of the draws need no
+ * transcendental at all. */
+MMK_HD double mmk_bits_to_normal(uint64_t x) {
+    const double p = MMK_MUL(MMK_ADD((double)(x >> 12), 0.5), 2.220446049250313e-16); /* 2^-52 */
+    const double q0 = MMK_SUB(p, 0.5);
+    if (q0 >= -0.47575 && q0 <= 0.47575) {
+        const double r = MMK_MUL(q0, q0);
+        double n = -3.969683028665376e+01;
+        n = MMK_ADD(MMK_MUL(n, r), 2.209460984245205e+02);
+        n = MMK_ADD(MMK_MUL(n, r), -2.759285104469687e+02);
+        n = MMK_ADD(MMK_MUL(n, r), 1.383577518672690e+02);
+        n = MMK_ADD(MMK_MUL(n, r), -3.066479806614716e+01);
+        n = MMK_ADD(MMK_MUL(n, r), 2.506628277459239e+00);
+        double d = -5.447609879822406e+01;
+        d = MMK_ADD(MMK_MUL(d, r), 1.615858368580409e+02);
+        d = MMK_ADD(MMK_MUL(d, r), -1.556989798598866e+02);
+        d = MMK_ADD(MMK_MUL(d, r), 6.680131188771972e+01);
+        d = MMK_ADD(MMK_MUL(d, r), -1.328068155288572e+01);
+        d = MMK_ADD(MMK_MUL(d, r), 1.0);
+        return MMK_DIV(MMK_MUL(n, q0), d);
     }
+    const int upper = q0 > 0.0;
+    const double t = upper ? MMK_SUB(1.0, p) : p;
+    const double q = MMK_SQRT(MMK_MUL(-2.0, mmk_log(t)));
+    double n = -7.784894002430293e-03;
+    n = MMK_ADD(MMK_MUL(n, q), -3.223964580411365e-01);
+    n = MMK_ADD(MMK_MUL(n, q), -2.400758277161838e+00);
+    n = MMK_ADD(MMK_MUL(n, q), -2.549732539343734e+00);
+    n = MMK_ADD(MMK_MUL(n, q), 4.374664141464968e+00);
+    n = MMK_ADD(MMK_MUL(n, q), 2.938163982698783e+00);
+    double d = 7.784695709041462e-03;
+    d = MMK_ADD(MMK_MUL(d, q), 3.224671290700398e-01);
+    d = MMK_ADD(MMK_MUL(d, q), 2.445134137142996e+00);
+    d = MMK_ADD(MMK_MUL(d, q), 3.754408661907416e+00);
+    d = MMK_ADD(MMK_MUL(d, q), 1.0);
+    const double z = MMK_DIV(n, d);
+    return upper ? -z : z;
 }
+MMK_HD double mmk_next_normal(mmk_stream *s) { return mmk_bits_to_normal(mmk_stream_next64(s)); }
 
 #endif /* MMK_RNG_H */

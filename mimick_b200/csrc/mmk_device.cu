@@ -811,7 +811,9 @@ namespace mmkdev {
 void tile_prepare(const EmitArgs &a, uint32_t n_tiles_total, uint32_t *d_sum1, uint32_t *d_sum2, uint4 *d_fdesc,
                   uint8_t *d_tile_flags, unsigned long long *d_gather, cudaStream_t st) {
     if (n_tiles_total == 0) return;
-    LAUNCH(k_tile_prepare, n_tiles_total, 64, 0, st, a, n_tiles_total, d_sum1, d_sum2, d_fdesc, d_tile_flags, d_gather);
+    const uint32_t per_cta = 256u / a.tile_pairs;
+    LAUNCH(k_tile_prepare, (n_tiles_total + per_cta - 1) / per_cta, 256, 0, st, a, n_tiles_total, d_sum1, d_sum2, d_fdesc, d_tile_flags,
+           d_gather);
 }
 
 __global__ void k_find_tile(const uint64_t *off1, const uint64_t *off2, uint32_t tile0, uint32_t n_tiles, uint64_t cap,

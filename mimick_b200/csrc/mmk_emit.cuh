@@ -126,49 +126,68 @@ __device__ void write_record_generic(const EmitArgs &a, const PairDesc &d, int r
 // ------------------------------------------------------------------------------------------
 // x: bstart   y: insert length | dm << 24   z: sb1 | sb2 << 16 (tile-relative record offsets)
 // w: P | SUF << 7 | schema << 13
-__global__ void __launch_bounds__(64) k_tile_prepare(EmitArgs a, uint32_t n_tiles, uint32_t *sum1, uint32_t *sum2, uint4 *fdesc,
-                                                     uint8_t *tile_flags, unsigned long long *gather) {
-    __shared__ uint32_t s_w[4];
-    const uint32_t tile = blockIdx.x;
-    if (tile >= n_tiles) return;
-    const uint64_t p0 = (uint64_t)tile * a.tile_pairs;
-    const uint32_t np = (uint32_t)((a.n_pairs - p0) < a.tile_pairs ? (a.n_pairs - p0) : a.tile_pairs);
+__global__ void __launch_bounds__(256) k_tile_prepare(EmitArgs a, uint32_t n_tiles, uint32_t *sum1, uint32_t *sum2, uint4 *fdesc,
+                                                      uint8_t *tile_flags, unsigned long long *gather) {
+    // 256 threads = 256 / tile_pairs tiles; tile_pairs is a power of two in 8..64
+    __shared__ uint32_t s_w[8][2];
+    __shared__ uint32_t s_irr[8];
+    const uint32_t TP = a.tile_pairs, tsh = 31 - __clz(TP);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t tile = blockIdx.x * (256u >> tsh) + (threadIdx.x >> tsh), it = threadIdx.x & (TP - 1u);
+    const bool tile_ok = tile < n_tiles;
+    const uint64_t p0 = (uint64_t)tile << tsh;
+    const uint32_t np = tile_ok ? (uint32_t)((a.n_pairs - p0) < TP ? (a.n_pairs - p0) : TP) : 0u;
     PairDesc d;
     d.regular = 1;
     d.len1 = d.len2 = d.sq1 = d.sq2 = 0;
     uint32_t schema = 0, iny = 0;
-    if (threadIdx.x < np) {
+    if (it < np) {
         const uint32_t m0 = a.tile_mol0[tile];
-        decode_pair(a, p0 + threadIdx.x, m0, d);
+        decode_pair(a, p0 + it, m0, d);
         schema = a.mol[d.mol].schema;
-        iny = a.ins[p0 + threadIdx.x].y;
+        iny = a.ins[p0 + it].y;
     }
+    // inclusive scans inside the tile: segments of min(TP, 32) lanes, two warps combined for TP = 64
+    const uint32_t W = TP < 32u ? TP : 32u, il = lane & (W - 1u);
     uint32_t i1 = d.len1, i2 = d.len2, gb = (d.sq1 * a.bpb + 7) / 8 + (d.sq2 * a.bpb + 7) / 8;
-    for (int o = 1; o < 32; o <<= 1) {
+    for (uint32_t o = 1; o < W; o <<= 1) {
         uint32_t y1 = __shfl_up_sync(0xffffffffu, i1, o), y2 = __shfl_up_sync(0xffffffffu, i2, o);
-        if (lane >= o) {
+        if (il >= o) {
             i1 += y1;
             i2 += y2;
         }
     }
     for (int o = 16; o; o >>= 1) gb += __shfl_down_sync(0xffffffffu, gb, o);
-    if (lane == 31) {
-        s_w[warp * 2] = i1;
-        s_w[warp * 2 + 1] = i2;
+    const unsigned irr = __ballot_sync(0xffffffffu, !d.regular);
+    uint32_t tot1 = __shfl_sync(0xffffffffu, i1, (int)((lane & ~(W - 1u)) + W - 1u));
+    uint32_t tot2 = __shfl_sync(0xffffffffu, i2, (int)((lane & ~(W - 1u)) + W - 1u));
+    uint32_t off1 = i1 - d.len1, off2 = i2 - d.len2;
+    bool irregular = (irr & (W == 32u ? 0xffffffffu : (((1u << W) - 1u) << (lane & ~(W - 1u))))) != 0u;
+    if (TP == 64u) {
+        if (lane == 31) {
+            s_w[warp][0] = i1;
+            s_w[warp][1] = i2;
+            s_irr[warp] = irr;
+        }
+        __syncthreads();
+        const uint32_t w0 = warp & ~1u;
+        if (warp & 1u) {
+            off1 += s_w[w0][0];
+            off2 += s_w[w0][1];
+        }
+        tot1 = s_w[w0][0] + s_w[w0 + 1][0];
+        tot2 = s_w[w0][1] + s_w[w0 + 1][1];
+        irregular = (s_irr[w0] | s_irr[w0 + 1]) != 0u;
     }
-    const int all_regular = __syncthreads_and((int)d.regular);
-    const uint32_t off1 = i1 - d.len1 + (warp ? s_w[0] : 0u), off2 = i2 - d.len2 + (warp ? s_w[1] : 0u);
-    const uint32_t bytes1 = s_w[0] + s_w[2], bytes2 = s_w[1] + s_w[3];
-    if (threadIdx.x < np)
-        fdesc[p0 + threadIdx.x] = make_uint4(d.bstart, iny, (off1 & 0xffffu) | (off2 << 16),
-                                             (uint32_t)d.P | ((uint32_t)d.SUF << 7) | (schema << 13));
+    if (it < np)
+        fdesc[p0 + it] = make_uint4(d.bstart, iny, (off1 & 0xffffu) | (off2 << 16),
+                                    (uint32_t)d.P | ((uint32_t)d.SUF << 7) | (schema << 13));
     if (lane == 0 && gb) atomicAdd(gather, (unsigned long long)gb);
-    if (threadIdx.x == 0) {
-        sum1[tile] = bytes1;
-        sum2[tile] = bytes2;
-        tile_flags[tile] = (uint8_t)(all_regular && bytes1 + 48u <= a.stage_cap && bytes2 + 48u <= a.stage_cap && bytes1 < 65536u &&
-                                     bytes2 < 65536u);
+    if (tile_ok && it == 0) {
+        sum1[tile] = tot1;
+        sum2[tile] = tot2;
+        tile_flags[tile] = (uint8_t)(!irregular && tot1 + 48u <= a.stage_cap && tot2 + 48u <= a.stage_cap && tot1 < 65536u &&
+                                     tot2 < 65536u);
     }
 }
 

@@ -131,7 +131,19 @@ __device__ __forceinline__ uint32_t molecule_shape(const SimConst &sc, uint64_t 
             } else
                 n_mean = sc.mol_coverage;
             TruncExp d;
-            if (!trunc_exp_make(d, n_mean, 2.0, true, max_possible)) {
+            // Distributions.jl picks the sampler from the kept mass tp (> 0.25: rejection).  tp is
+            // exp(-2/n) - exp(-max/n) up to rounding; unless that is within 1e-9 of 0.25 the decision is
+            // the same as with the log-space tp of `truncated`, and the rejection sampler needs no cdf.
+            const double tp_quick = MMK_SUB(mmk_exp(-MMK_DIV(2.0, n_mean)), mmk_exp(-MMK_DIV(max_possible, n_mean)));
+            if (2.0 <= max_possible && tp_quick > 0.25 + 1e-9) {
+                d.theta = n_mean;
+                d.lower = 2.0;
+                d.upper = max_possible;
+                d.has_upper = 1;
+                d.tp = tp_quick;  // only compared with 0.25 from here on
+                mmk_stream_init(&s, sc.seed, sc.sample, MMK_P_NFRAGS, g, m);
+                N = trunc_exp_rand(s, d, MMK_P_NFRAGS, rec);
+            } else if (!trunc_exp_make(d, n_mean, 2.0, true, max_possible)) {
                 status = MMK_ERR_TRUNCATION_BOUNDS;
                 N = 1.0;
             } else {
