@@ -37,8 +37,12 @@ __device__ __forceinline__ uint32_t ndigits_u64(uint64_t v) {
     return d;
 }
 __device__ __forceinline__ uint32_t ndigits_u32(uint32_t v) {
-    return 1u + (v >= 10u) + (v >= 100u) + (v >= 1000u) + (v >= 10000u) + (v >= 100000u) + (v >= 1000000u) +
-           (v >= 10000000u) + (v >= 100000000u) + (v >= 1000000000u);
+    if (v >= 100000u) {
+        if (v >= 10000000u) return v >= 1000000000u ? 10u : (v >= 100000000u ? 9u : 8u);
+        return v >= 1000000u ? 7u : 6u;
+    }
+    if (v >= 1000u) return v >= 10000u ? 5u : 4u;
+    return v >= 100u ? 3u : (v >= 10u ? 2u : 1u);
 }
 __constant__ uint32_t c_pow10[10] = {1u, 10u, 100u, 1000u, 10000u, 100000u, 1000000u, 10000000u, 100000000u, 1000000000u};
 
@@ -653,6 +657,28 @@ __device__ __noinline__ double sequential_sum(const SimConst &sc, uint64_t g, ui
     for (uint32_t k = 0; k < nfrags; ++k) sum = MMK_ADD(sum, draw_insert(sc, g, m, round, k, rec));
     return sum;
 }
+// whole-vector redraws while the float sum exceeds the molecule (Breakpoints.jl:209-212); true if it still does
+__device__ __noinline__ bool redraw_rounds(const SimConst &sc, uint64_t g, uint32_t m, uint32_t nfrags, uint32_t molsize,
+                                           PairTmp *tp, uint64_t &isum) {
+    NoRec rec;
+    bool over = true;
+    int attempts = 0;
+    while (over && attempts < sc.attempts) {
+        ++attempts;
+        double sum = 0.0;
+        isum = 0;
+        for (uint32_t k = 0; k < nfrags; ++k) {
+            double x = draw_insert(sc, g, m, (uint32_t)attempts, k, rec);
+            sum = MMK_ADD(sum, x);
+            uint32_t li = (uint32_t)(long long)x;
+            if (li > 0x00ffffffu) li = 0x00ffffffu;
+            tp[k].len = li;
+            isum += li;
+        }
+        over = sum > (double)molsize;
+    }
+    return over;
+}
 __global__ void k_place_chain(SimConst sc, const SchemaDev *__restrict__ sch, PlanDev plan, uint64_t mol0, uint32_t m_lo,
                               uint32_t m_hi, const uint64_t *__restrict__ roff_l, uint64_t pair_lo, PairTmp *tmp,
                               const uint32_t *__restrict__ acc_i, const unsigned long long *__restrict__ acc_f,
@@ -679,21 +705,7 @@ __global__ void k_place_chain(SimConst sc, const SchemaDev *__restrict__ sch, Pl
         else if (lo + nfrags + 1 <= M) over = false;
         else over = sequential_sum(sc, g, m, 0, nfrags) > (double)molsize;
     }
-    int attempts = 0;
-    while (over && attempts < sc.attempts) {  // whole-vector redraw
-        ++attempts;
-        double sum = 0.0;
-        isum = 0;
-        for (uint32_t k = 0; k < nfrags; ++k) {
-            double x = draw_insert(sc, g, m, (uint32_t)attempts, k, rec);
-            sum = MMK_ADD(sum, x);
-            uint32_t li = (uint32_t)(long long)x;
-            if (li > 0x00ffffffu) li = 0x00ffffffu;
-            tp[k].len = li;
-            isum += li;
-        }
-        over = sum > (double)molsize;
-    }
+    if (over) over = redraw_rounds(sc, g, m, nfrags, molsize, tp, isum);  // rare: kept out of line
     uint32_t status = over ? (uint32_t)MMK_ERR_INSERTS_UNFITTABLE : 0u;
     // start_pos = rand(1:adjusted_end)
     uint64_t adjusted_end = sc.circular ? (uint64_t)n : (n > molsize + 1u ? (uint64_t)(n - molsize) : 1ull);
@@ -737,6 +749,27 @@ __global__ void k_place_chain(SimConst sc, const SchemaDev *__restrict__ sch, Pl
         atomicMin(&err[0], (unsigned long long)gi);
         plan.status[gi] = (uint8_t)status;
     }
+    MolRec r;
+    r.start = start;
+    r.size = molsize;
+    r.schema = (uint16_t)t;
+    r.prefix_len = 0;  // k_mol_text fills the two lengths
+    r.suffix_len = 0;
+    r.qual1 = q1;
+    r.qual2 = q2;
+    mol[i] = r;
+}
+
+// Placement, step 3 — one thread per molecule: the header text every record of the molecule shares.
+__global__ void k_mol_text(SimConst sc, const SchemaDev *__restrict__ sch, uint64_t mol0, uint32_t m_lo, uint32_t m_hi, MolRec *mol,
+                           uint8_t *text, uint32_t text_stride) {
+    uint32_t i = m_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m_hi) return;
+    const uint64_t gi = mol0 + i;
+    MolRec r = mol[i];
+    const SchemaDev &S = sch[r.schema];
+    const int64_t start = r.start;
+    const uint32_t molsize = r.size;
     // header text: "@chrom:hap|start:end|" then the format's tail with read digit '1'; assembled in a
     // thread-local buffer and written with 16-byte stores
     uint8_t buf[208];
@@ -768,14 +801,8 @@ __global__ void k_place_chain(SimConst sc, const SchemaDev *__restrict__ sch, Pl
             dst[o >> 4] = v;
         }
     }
-    MolRec r;
-    r.start = start;
-    r.size = molsize;
-    r.schema = (uint16_t)t;
     r.prefix_len = (uint8_t)plen;
     r.suffix_len = (uint8_t)(p - sp);
-    r.qual1 = q1;
-    r.qual2 = q2;
     mol[i] = r;
 }
 
@@ -799,6 +826,7 @@ void place_segment(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uin
                    n_tiles, tile_pairs, pair_lo, pair_hi, (PairTmp *)d_tmp, d_acc_i, d_acc_f);
     LAUNCH(k_place_chain, (m_hi - m_lo + 127) / 128, 128, 0, st, sc, d_sch, plan, mol0, m_lo, m_hi, d_read_off_local, pair_lo,
            (PairTmp *)d_tmp, d_acc_i, d_acc_f, d_tile_mol0, tile_pairs, d_ins, d_mol, d_text, text_stride, d_err);
+    LAUNCH(k_mol_text, (m_hi - m_lo + 127) / 128, 128, 0, st, sc, d_sch, mol0, m_lo, m_hi, d_mol, d_text, text_stride);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -49,7 +49,7 @@ __device__ __forceinline__ void decode_pair(const EmitArgs &a, uint64_t p, uint3
     d.word_off = S.word_off;
     d.n = S.len;
     d.mol = m;
-    d.bstart = (uint32_t)(mr.start + in.x);
+    d.bstart = (uint32_t)mr.start + in.x;
     d.bend = d.bstart + MMK_INS_LEN(in.y) - 1;
     d.d1 = (uint8_t)ndigits_u32(d.bstart);
     d.d2 = (uint8_t)ndigits_u32(d.bend);
@@ -57,8 +57,13 @@ __device__ __forceinline__ void decode_pair(const EmitArgs &a, uint64_t p, uint3
     d.SUF = mr.suffix_len;
     d.hdr = (uint32_t)d.P + d.d1 + 1 + d.d2 + d.SUF;
     int64_t a2 = (int64_t)d.bend - a.r2 + 1;
-    d.sq1 = window_len(d.bstart, (int64_t)d.bstart + a.r1 - 1, d.n, a.strict);
-    d.sq2 = window_len(a2, d.bend, d.n, a.strict);
+    if (d.bend <= d.n && d.bstart + (uint32_t)a.r1 - 1u <= d.n) {  // both windows inside the haplotype: nominal lengths
+        d.sq1 = (uint32_t)a.r1;
+        d.sq2 = (uint32_t)a.r2;
+    } else {
+        d.sq1 = window_len(d.bstart, (int64_t)d.bstart + a.r1 - 1, d.n, a.strict);
+        d.sq2 = window_len(a2, d.bend, d.n, a.strict);
+    }
     d.q1 = mr.qual1;
     d.q2 = mr.qual2;
     d.len1 = d.hdr + a.bclen_inline + d.sq1 + 3 + d.q1 + 1;
@@ -158,6 +163,8 @@ __global__ void __launch_bounds__(256) k_tile_prepare(EmitArgs a, uint32_t n_til
         }
     }
     for (int o = 16; o; o >>= 1) gb += __shfl_down_sync(0xffffffffu, gb, o);
+    // (accounting only) spread the per-warp totals over 256 counters: same-address atomics serialise in L2
+    if (lane == 0 && gb) atomicAdd(&gather[(blockIdx.x * 8u + warp) & 255u], (unsigned long long)gb);
     const unsigned irr = __ballot_sync(0xffffffffu, !d.regular);
     uint32_t tot1 = __shfl_sync(0xffffffffu, i1, (int)((lane & ~(W - 1u)) + W - 1u));
     uint32_t tot2 = __shfl_sync(0xffffffffu, i2, (int)((lane & ~(W - 1u)) + W - 1u));
@@ -182,7 +189,6 @@ __global__ void __launch_bounds__(256) k_tile_prepare(EmitArgs a, uint32_t n_til
     if (it < np)
         fdesc[p0 + it] = make_uint4(d.bstart, iny, (off1 & 0xffffu) | (off2 << 16),
                                     (uint32_t)d.P | ((uint32_t)d.SUF << 7) | (schema << 13));
-    if (lane == 0 && gb) atomicAdd(gather, (unsigned long long)gb);
     if (tile_ok && it == 0) {
         sum1[tile] = tot1;
         sum2[tile] = tot2;

@@ -111,7 +111,7 @@ struct mmk_ctx {
     DBuf<uint64_t> d_scan_tmp;
     // placement / chunking scratch, kept between calls
     DBuf<uint64_t> s_bounds, s_b1, s_b2;
-    DBuf<unsigned long long> s_err;
+    DBuf<unsigned long long> s_err, s_gather;
     DBuf<uint32_t> s_sum1, s_sum2, s_cb, s_cn;
     uint64_t n_mol = 0, n_pairs = 0, n_groups = 0;
     std::vector<uint32_t> epoch_nlive;
@@ -1245,19 +1245,23 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     CU(d_tmp.ensure((size_t)ctx->n_tiles / 1024 + 8));
     CU(ctx->d_tile_off1.ensure((size_t)ctx->n_tiles + 1));
     CU(ctx->d_tile_off2.ensure((size_t)ctx->n_tiles + 1));
-    CU(cudaMemsetAsync(d_err.p, 0, 8, ctx->st));
+    DBuf<unsigned long long> &d_gather = ctx->s_gather;
+    CU(d_gather.ensure(256));
+    CU(cudaMemsetAsync(d_gather.p, 0, 256 * 8, ctx->st));
     EmitArgs a = base_args(ctx);
     CU(ctx->d_fdesc.ensure(ctx->s_npairs + 1));
     CU(ctx->d_tile_flags.ensure((size_t)ctx->n_tiles + 1));
     a = base_args(ctx);
-    tile_prepare(a, ctx->n_tiles, d_sum1.p, d_sum2.p, ctx->d_fdesc.p, ctx->d_tile_flags.p, d_err.p, ctx->st);
+    tile_prepare(a, ctx->n_tiles, d_sum1.p, d_sum2.p, ctx->d_fdesc.p, ctx->d_tile_flags.p, d_gather.p, ctx->st);
     exclusive_scan_u32(d_sum1.p, ctx->d_tile_off1.p, ctx->n_tiles, d_tmp.p, ctx->st);
     exclusive_scan_u32(d_sum2.p, ctx->d_tile_off2.p, ctx->n_tiles, d_tmp.p, ctx->st);
     uint64_t tot[3] = {0, 0, 0};
     CU(cudaMemcpyAsync(&tot[0], ctx->d_tile_off1.p + ctx->n_tiles, 8, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaMemcpyAsync(&tot[1], ctx->d_tile_off2.p + ctx->n_tiles, 8, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaMemcpyAsync(&tot[2], d_err.p, 8, cudaMemcpyDeviceToHost, ctx->st));
+    unsigned long long h_gather[256];
+    CU(cudaMemcpyAsync(h_gather, d_gather.p, sizeof h_gather, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
+    for (int k = 0; k < 256; ++k) tot[2] += h_gather[k];
     CU(cudaGetLastError());
     ctx->place_info.first_molecule = (int64_t)ctx->mol0;
     ctx->place_info.n_molecules = (int64_t)ctx->s_nmol;
