@@ -604,7 +604,7 @@ __global__ void k_tile_mol0(const uint64_t *__restrict__ roff_l, uint32_t n_mol,
 struct __align__(16) PairTmp {
     uint64_t bits;  // gap draw: gap = mulhi64(bits, remaining + 1)
     uint32_t len;   // trunc(Int, insert length)
-    uint32_t pad;
+    uint32_t dm;    // molecule index - first molecule of the pair's tile
 };
 __global__ void k_insert_draws(SimConst sc, PlanDev plan, uint64_t mol0, uint32_t n_mol, const uint64_t *__restrict__ roff_l,
                                const uint32_t *__restrict__ tile_mol0, uint32_t n_tiles, uint32_t tile_pairs, uint64_t pair_lo,
@@ -613,7 +613,8 @@ __global__ void k_insert_draws(SimConst sc, PlanDev plan, uint64_t mol0, uint32_
     const bool valid = p_raw < pair_hi;
     const uint64_t p = valid ? p_raw : pair_hi - 1;
     const uint32_t tile = (uint32_t)(p >> (31 - __clz(tile_pairs)));  // tile_pairs is a power of two
-    uint32_t lo = tile_mol0[tile], hi = tile + 1 < n_tiles ? tile_mol0[tile + 1] : n_mol - 1;
+    const uint32_t tm0 = tile_mol0[tile];
+    uint32_t lo = tm0, hi = tile + 1 < n_tiles ? tile_mol0[tile + 1] : n_mol - 1;
     while (lo < hi) {  // largest m with roff_l[m] <= p
         uint32_t mid = (lo + hi + 1) >> 1;
         if (roff_l[mid] <= p) lo = mid; else hi = mid - 1;
@@ -631,7 +632,7 @@ __global__ void k_insert_draws(SimConst sc, PlanDev plan, uint64_t mol0, uint32_
         PairTmp t;
         t.bits = mmk_stream_at(&gs, i);
         t.len = li;
-        t.pad = 0;
+        t.dm = lo - tm0;
         tmp[p - pair_lo] = t;
     }
     // lanes of the same molecule are contiguous: one atomic per run
@@ -679,13 +680,11 @@ __device__ __noinline__ bool redraw_rounds(const SimConst &sc, uint64_t g, uint3
     }
     return over;
 }
-__global__ void k_place_chain(SimConst sc, const SchemaDev *__restrict__ sch, PlanDev plan, uint64_t mol0, uint32_t m_lo,
-                              uint32_t m_hi, const uint64_t *__restrict__ roff_l, uint64_t pair_lo, PairTmp *tmp,
-                              const uint32_t *__restrict__ acc_i, const unsigned long long *__restrict__ acc_f,
-                              const uint32_t *__restrict__ tile_mol0, uint32_t tile_pairs, uint2 *ins, MolRec *mol,
-                              uint8_t *text, uint32_t text_stride, unsigned long long *err) {
-    uint32_t i = m_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m_hi) return;
+__device__ __forceinline__ void place_chain_one(const SimConst &sc, const SchemaDev *__restrict__ sch, const PlanDev &plan,
+                                                uint64_t mol0, uint32_t i, const uint64_t *__restrict__ roff_l, uint64_t pair_lo,
+                                                PairTmp *tmp, const uint32_t *__restrict__ acc_i,
+                                                const unsigned long long *__restrict__ acc_f, uint2 *ins, MolRec *mol,
+                                                unsigned long long *err) {
     uint64_t gi = mol0 + i;
     uint64_t ro = roff_l[i];
     uint64_t g = plan.group[gi];
@@ -715,12 +714,8 @@ __global__ void k_place_chain(SimConst sc, const SchemaDev *__restrict__ sch, Pl
     uint32_t q1 = 0, q2 = 0;
     if (!status) {
         uint64_t remaining = (uint64_t)molsize + 1 - isum, cursor = 0;
-        const uint32_t tshift = 31 - __clz(tile_pairs);  // tile_pairs is a power of two
-        uint32_t tile = (uint32_t)(ro >> tshift), tm0 = tile_mol0[tile];
-        uint32_t to_next = tile_pairs - (uint32_t)(ro & (tile_pairs - 1));  // pairs left in the current tile
-        // R2 window bstop - r2 + 1 : bstop must start at >= 1 (Julia BoundsError otherwise); only molecules that
-        // start within r2 of position 1 can violate it
-        const bool check_r2 = !sc.strict && start <= (int64_t)sc.r2;
+        // R2 window bstop - r2 + 1 : bstop must start at >= 1 (Julia BoundsError otherwise): st + len >= r2 + 1 - start
+        const uint32_t need_end = (!sc.strict && start <= (int64_t)sc.r2) ? (uint32_t)((int64_t)sc.r2 + 1 - start) : 0u;
         // the loop is latency-bound on its own loads: keep two 128-byte lines of the scratch in flight
         asm volatile("prefetch.global.L1 [%0];" ::"l"(tp));
         asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + 8));
@@ -728,17 +723,12 @@ __global__ void k_place_chain(SimConst sc, const SchemaDev *__restrict__ sch, Pl
         for (uint32_t k = 0; k < nfrags; ++k) {
             if ((k & 7u) == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(tp + k + 16));
             const PairTmp nxt = tp[k + 1 < nfrags ? k + 1 : k];
-            if (to_next == 0) {
-                tm0 = tile_mol0[++tile];
-                to_next = tile_pairs;
-            }
-            --to_next;
             const uint32_t gap = (uint32_t)mmk_bits_to_index(e.bits, remaining + 1);
             const uint32_t st = (uint32_t)cursor + gap;
-            in[k] = make_uint2(st, e.len | ((i - tm0) << 24));
+            in[k] = make_uint2(st, e.len | (e.dm << 24));
             cursor = st + e.len;
             remaining -= gap;
-            if (check_r2 && start + (int64_t)st + (int64_t)e.len - (int64_t)sc.r2 < 1) status = MMK_ERR_BOUNDS;
+            if (st + e.len < need_end) status = MMK_ERR_BOUNDS;
             e = nxt;
         }
         // quality lengths follow the molecule's FIRST reads (FormatFASTQ.jl:14)
@@ -813,20 +803,76 @@ void place_prepare(uint64_t mol0, uint32_t n_mol, const uint64_t *d_read_off_glo
     LAUNCH(k_tile_mol0, (n_mol + 255) / 256, 256, 0, st, d_read_off_local, n_mol, tile_pairs, d_tile_mol0);
 }
 
+// One CTA places PLACE_BLOCK consecutive molecules.  It first orders them by insert count (counting sort
+// in shared memory), so that the lanes of a warp loop alike — with the raw order only ~6 of 32 lanes are
+// active on average (insert counts are exponentially distributed) — while keeping the block's memory
+// traffic local.
+constexpr uint32_t PLACE_BLOCK = 1024, SORT_BINS = 1024;
+__global__ void __launch_bounds__(256) k_place_chain(SimConst sc, const SchemaDev *__restrict__ sch, PlanDev plan, uint64_t mol0,
+                                                     uint32_t m_lo, uint32_t m_hi, const uint64_t *__restrict__ roff_l,
+                                                     uint64_t pair_lo, PairTmp *tmp, const uint32_t *__restrict__ acc_i,
+                                                     const unsigned long long *__restrict__ acc_f, uint2 *ins, MolRec *mol,
+                                                     unsigned long long *err) {
+    __shared__ uint32_t s_bins[SORT_BINS];
+    __shared__ uint32_t s_warp[9];
+    __shared__ uint16_t s_perm[PLACE_BLOCK];
+    const uint32_t base = m_lo + blockIdx.x * PLACE_BLOCK;
+    const uint32_t cnt = m_hi - base < PLACE_BLOCK ? m_hi - base : PLACE_BLOCK;
+    const uint32_t *nf = plan.nfrags + mol0 + base;
+    for (uint32_t b = threadIdx.x; b < SORT_BINS; b += 256) s_bins[b] = 0;
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < cnt; j += 256) atomicAdd(&s_bins[nf[j] < SORT_BINS ? nf[j] : SORT_BINS - 1], 1u);
+    __syncthreads();
+    {   // exclusive scan of the 1024 bins: 4 per thread
+        const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        uint32_t v[4], tsum = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            v[q] = s_bins[threadIdx.x * 4 + q];
+            tsum += v[q];
+        }
+        uint32_t inc = tsum;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) s_warp[warp + 1] = inc;
+        if (threadIdx.x == 0) s_warp[0] = 0;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int w = 1; w <= 8; ++w) s_warp[w] += s_warp[w - 1];
+        __syncthreads();
+        uint32_t ex = inc - tsum + s_warp[warp];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            s_bins[threadIdx.x * 4 + q] = ex;
+            ex += v[q];
+        }
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < cnt; j += 256) s_perm[atomicAdd(&s_bins[nf[j] < SORT_BINS ? nf[j] : SORT_BINS - 1], 1u)] = (uint16_t)j;
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < cnt; j += 256)
+        place_chain_one(sc, sch, plan, mol0, base + s_perm[j], roff_l, pair_lo, tmp, acc_i, acc_f, ins, mol, err);
+}
+
 // one segment: pairs [pair_lo, pair_hi) = the pairs of molecules [m_lo, m_hi)
 size_t place_tmp_bytes(uint64_t max_pairs) { return (size_t)(max_pairs + 1) * sizeof(PairTmp); }
 void place_segment(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint32_t m_lo,
                    uint32_t m_hi, uint64_t pair_lo, uint64_t pair_hi, const uint64_t *d_read_off_local,
                    const uint32_t *d_tile_mol0, uint32_t n_tiles, uint32_t tile_pairs, void *d_tmp, uint32_t *d_acc_i,
-                   unsigned long long *d_acc_f, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
-                   unsigned long long *d_err, cudaStream_t st) {
+                   unsigned long long *d_acc_f, uint32_t *d_perm, uint32_t *d_bins, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text,
+                   uint32_t text_stride, unsigned long long *d_err, cudaStream_t st) {
     if (m_hi <= m_lo) return;
-    uint64_t np = pair_hi - pair_lo;
+    const uint64_t np = pair_hi - pair_lo;
+    const uint32_t nm = m_hi - m_lo;
     if (np) LAUNCH(k_insert_draws, (unsigned)((np + 255) / 256), 256, 0, st, sc, plan, mol0, n_mol, d_read_off_local, d_tile_mol0,
                    n_tiles, tile_pairs, pair_lo, pair_hi, (PairTmp *)d_tmp, d_acc_i, d_acc_f);
-    LAUNCH(k_place_chain, (m_hi - m_lo + 127) / 128, 128, 0, st, sc, d_sch, plan, mol0, m_lo, m_hi, d_read_off_local, pair_lo,
-           (PairTmp *)d_tmp, d_acc_i, d_acc_f, d_tile_mol0, tile_pairs, d_ins, d_mol, d_text, text_stride, d_err);
-    LAUNCH(k_mol_text, (m_hi - m_lo + 127) / 128, 128, 0, st, sc, d_sch, mol0, m_lo, m_hi, d_mol, d_text, text_stride);
+    (void)d_perm;
+    (void)d_bins;
+    LAUNCH(k_place_chain, (nm + PLACE_BLOCK - 1) / PLACE_BLOCK, 256, 0, st, sc, d_sch, plan, mol0, m_lo, m_hi, d_read_off_local,
+           pair_lo, (PairTmp *)d_tmp, d_acc_i, d_acc_f, d_ins, d_mol, d_err);
+    LAUNCH(k_mol_text, (nm + 127) / 128, 128, 0, st, sc, d_sch, mol0, m_lo, m_hi, d_mol, d_text, text_stride);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -130,6 +130,7 @@ struct mmk_ctx {
     DBuf<uint4> d_fdesc;
     DBuf<uint8_t> d_tile_flags;
     DBuf<uint8_t> d_tmp;      // placement scratch: (gap bits, insert length) per pair of one segment
+    DBuf<uint32_t> d_perm, d_bins;  // placement scratch: molecules of a segment ordered by insert count
     DBuf<uint32_t> d_acc_i;   // placement scratch: sum of insert lengths per molecule
     DBuf<unsigned long long> d_acc_f;  // ... and a 2^-16 fixed-point lower bound of their real sum
     uint32_t text_stride = 0, tile_pairs = 64, n_tiles = 0, stage_cap = 0;
@@ -1217,13 +1218,15 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
             CU(ctx->d_tmp.ensure(place_tmp_bytes(max_pairs)));
             CU(ctx->d_acc_i.ensure(ctx->s_nmol + 1));
             CU(ctx->d_acc_f.ensure(ctx->s_nmol + 1));
+            CU(ctx->d_perm.ensure(ctx->s_nmol + 1));
+            CU(ctx->d_bins.ensure(1024));
             CU(cudaMemsetAsync(ctx->d_acc_i.p, 0, (ctx->s_nmol + 1) * 4, ctx->st));
             CU(cudaMemsetAsync(ctx->d_acc_f.p, 0, (ctx->s_nmol + 1) * 8, ctx->st));
             for (int k = 0; k < n_seg; ++k)
                 place_segment(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->mol0, (uint32_t)ctx->s_nmol, (uint32_t)sb[k],
                               (uint32_t)sb[k + 1], sp[k], sp[k + 1], ctx->d_roff_l.p, ctx->d_tile_mol0.p, ctx->n_tiles,
-                              ctx->tile_pairs, ctx->d_tmp.p, ctx->d_acc_i.p, ctx->d_acc_f.p, ctx->d_ins.p, ctx->d_mol.p,
-                              ctx->d_text.p, ctx->text_stride, d_err.p, ctx->st);
+                              ctx->tile_pairs, ctx->d_tmp.p, ctx->d_acc_i.p, ctx->d_acc_f.p, ctx->d_perm.p, ctx->d_bins.p,
+                              ctx->d_ins.p, ctx->d_mol.p, ctx->d_text.p, ctx->text_stride, d_err.p, ctx->st);
         }
     }
     unsigned long long herr[3];

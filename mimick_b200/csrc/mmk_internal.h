@@ -143,8 +143,8 @@ size_t place_tmp_bytes(uint64_t max_pairs);
 void place_segment(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint32_t m_lo,
                    uint32_t m_hi, uint64_t pair_lo, uint64_t pair_hi, const uint64_t *d_read_off_local,
                    const uint32_t *d_tile_mol0, uint32_t n_tiles, uint32_t tile_pairs, void *d_tmp, uint32_t *d_acc_i,
-                   unsigned long long *d_acc_f, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
-                   unsigned long long *d_err, cudaStream_t st);
+                   unsigned long long *d_acc_f, uint32_t *d_perm /*[>= m_hi - m_lo]*/, uint32_t *d_bins /*[1024]*/, uint2 *d_ins,
+                   MolRec *d_mol, uint8_t *d_text, uint32_t text_stride, unsigned long long *d_err, cudaStream_t st);
 
 void tile_prepare(const EmitArgs &a, uint32_t n_tiles_total, uint32_t *d_sum1, uint32_t *d_sum2, uint4 *d_fdesc,
                   uint8_t *d_tile_flags, unsigned long long *d_gather, cudaStream_t st);
