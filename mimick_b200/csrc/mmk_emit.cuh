@@ -280,7 +280,7 @@ __device__ __forceinline__ void make_fast_desc(const EmitArgs &a, const uint4 &q
 // Phase 1 — one read pair, one warp (half-warp 0: R1, reverse complement; half-warp 1: R2, forward):
 // quality chunks, then sequence chunks, then the 15 bytes after the sequence + the final newline.
 // All 16-byte stores are aligned to the stream; what they spill on is rewritten later.
-__device__ __forceinline__ void emit_pair_seq(const EmitArgs &a, const FastDesc &f, uint32_t smem, uint32_t lane) {
+__device__ __forceinline__ void emit_pair_seq(const EmitArgs &a, const FastDesc &f, uint32_t W, uint32_t smem, uint32_t lane) {
     const uint32_t half = lane >> 4, hl = lane & 15u;
     const uint32_t inl = half ? 0u : (uint32_t)a.bclen_inline;
     const uint32_t S = half ? (uint32_t)a.r2 : (uint32_t)a.r1;
@@ -290,7 +290,6 @@ __device__ __forceinline__ void emit_pair_seq(const EmitArgs &a, const FastDesc 
     // reference window: one packed word per lane of the half-warp
     const uint32_t ws = half ? f.bend - (uint32_t)a.r2 : f.bstart - 1u;
     const int rel = (int)(ws >= 15u ? ((ws - 15u) & 15u) + 15u : ws);     // window start relative to the first word
-    const uint32_t W = __ldg(a.hap + (half ? f.wbase2 : f.wbase1) + hl);
     // quality: 'I' over every 16-byte chunk that touches [seq_end + 3, rec_end)
     {
         const uint32_t c = ((seq_end + 3u) >> 4) + hl;
@@ -407,6 +406,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_emit(const __grid_c
     const uint64_t t1 = a.tile_off1[tile], t2 = a.tile_off2[tile];
     const uint32_t bytes1 = (uint32_t)(a.tile_off1[tile + 1] - t1), bytes2 = (uint32_t)(a.tile_off2[tile + 1] - t2);
     const bool fast = BPB == 2 && a.fast_ok && a.tile_flags[tile];
+    // warm L2 for a tile that a later wave of CTAs will run (descriptors are read exactly once)
+    if (threadIdx.x < 4 && blockIdx.x + 1184u < a.n_tiles)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(a.fdesc + (p0 + 1184ull * a.tile_pairs)) + 128u * threadIdx.x));
     const uint64_t g1 = t1 - a.chunk_off1, g2 = t2 - a.chunk_off2;
     const uint32_t A1 = (uint32_t)(g1 & 15u), A2 = (uint32_t)(g2 & 15u);
     if (!fast) {
@@ -459,7 +461,19 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_emit(const __grid_c
     }
     const uint32_t sm = (uint32_t)__cvta_generic_to_shared(smem);
     __syncthreads();
-    for (uint32_t t = warp; t < np; t += EMIT_WARPS) emit_pair_seq(a, load_fast_desc(s_fa, s_fb, t), sm, lane);
+    {   // the reference word of pair t + EMIT_WARPS is loaded while pair t is expanded
+        const uint32_t half = lane >> 4, hl = lane & 15u;
+        FastDesc f = load_fast_desc(s_fa, s_fb, warp < np ? warp : 0);
+        uint32_t W = __ldg(a.hap + (half ? f.wbase2 : f.wbase1) + hl);
+        for (uint32_t t = warp; t < np; t += EMIT_WARPS) {
+            const uint32_t tn = t + EMIT_WARPS < np ? t + EMIT_WARPS : t;
+            const FastDesc fn = load_fast_desc(s_fa, s_fb, tn);
+            const uint32_t Wn = __ldg(a.hap + (half ? fn.wbase2 : fn.wbase1) + hl);
+            emit_pair_seq(a, f, W, sm, lane);
+            f = fn;
+            W = Wn;
+        }
+    }
     __syncthreads();
     {
         const uint32_t role = threadIdx.x / (THREADS / 4), t = threadIdx.x % (THREADS / 4);  // 4 pieces x up to THREADS/4 pairs
