@@ -271,8 +271,9 @@ __device__ __forceinline__ void make_fast_desc(const EmitArgs &a, const uint4 &q
     f.bstart = bstart;
     f.bend = bend;
     const uint32_t ws1 = bstart - 1u, ws2 = bend - (uint32_t)a.r2;  // 0-based window starts
-    f.wbase1 = word_off + (ws1 >= 15u ? (ws1 - 15u) >> 4 : 0u);
-    f.wbase2 = word_off + (ws2 >= 15u ? (ws2 - 15u) >> 4 : 0u);
+    const uint32_t wsh = a.bpb == 2 ? 4u : 3u;                        // 16 or 8 bases per packed word
+    f.wbase1 = word_off + (ws1 >= 15u ? (ws1 - 15u) >> wsh : 0u);
+    f.wbase2 = word_off + (ws2 >= 15u ? (ws2 - 15u) >> wsh : 0u);
     f.mol = tile_m0 + MMK_INS_DM(q.y);
     f.pk = (P + d1 + 1u + d2 + SUF) | (P << 8) | (SUF << 16) | (d1 << 22) | (d2 << 26);
 }
@@ -312,6 +313,81 @@ __device__ __forceinline__ void emit_pair_seq(const EmitArgs &a, const FastDesc 
             bits = ((bits >> 1) & 0x55555555u) | ((bits & 0x55555555u) << 1);
         }
         const uint4 v = expand16(bits, half ? 0x54474341u /* "ACGT" */ : 0x41434754u /* "TGCA" */);
+        if (16u * c < seq_end) sts128(smem + 16u * c, v);
+    }
+    __syncwarp();
+    {
+        const uint32_t addr = hl < 15 ? seq_end + hl : rec_end - 1u;
+        const uint32_t val = (hl == 0 || hl == 2 || hl == 15) ? '\n' : (hl == 1 ? '+' : 'I');
+        sts8(smem + addr, val);
+    }
+}
+
+// 8 bases of a 4-bit word (BioSequences one-hot codes A=1 C=2 G=4 T=8) → 8 ASCII bytes; false if any of
+// the 8 symbols is not one of A, C, G, T (IUPAC ambiguity or gap: the caller converts those one by one).
+__device__ __forceinline__ bool expand8_onehot(uint32_t w, uint32_t &lo, uint32_t &hi) {
+    // popcount per nibble must be 1 everywhere
+    const uint32_t pc = w - ((w >> 1) & 0x77777777u) - ((w >> 2) & 0x33333333u) - ((w >> 3) & 0x11111111u);
+    // one-hot nibble → index 0..3: (n >> 1) - (n >> 3) gives 0, 1, 2, 3 for 1, 2, 4, 8 (no borrow between nibbles)
+    const uint32_t idx = ((w >> 1) & 0x77777777u) - ((w >> 3) & 0x11111111u);
+    lo = __byte_perm(0x54474341u /* "ACGT" */, 0, idx);
+    hi = __byte_perm(0x54474341u, 0, idx >> 16);
+    return pc == 0x11111111u;
+}
+__device__ __forceinline__ uint32_t expand4_any(uint32_t nib16) {  // 4 symbols, any IUPAC code
+    uint32_t r = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) r |= (uint32_t)(uint8_t)code4_to_ascii((nib16 >> (4 * b)) & 15u) << (8 * b);
+    return r;
+}
+
+// Phase 1 for a 4-bit reference: same structure as emit_pair_seq; each lane of a half-warp holds two packed
+// words (W0: word hl, W1: word hl + 16), a 16-base chunk is cut from three of them. Reverse complement of
+// 8 one-hot symbols is a plain bit reversal of the word (reversing a nibble complements it).
+__device__ __forceinline__ void emit_pair_seq4(const EmitArgs &a, const FastDesc &f, uint32_t W0, uint32_t W1, uint32_t smem,
+                                               uint32_t lane) {
+    const uint32_t half = lane >> 4, hl = lane & 15u;
+    const uint32_t inl = half ? 0u : (uint32_t)a.bclen_inline;
+    const uint32_t S = half ? (uint32_t)a.r2 : (uint32_t)a.r1;
+    const uint32_t seq_off = (half ? f.sb2 : f.sb1) + FD_HDR(f.pk) + inl;
+    const uint32_t seq_end = seq_off + S;
+    const uint32_t rec_end = seq_end + 3u + S + inl + 1u;
+    const uint32_t ws = half ? f.bend - (uint32_t)a.r2 : f.bstart - 1u;
+    const int rel = (int)(ws >= 15u ? ((ws - 15u) & 7u) + 15u : ws);  // window start relative to the first loaded word
+    {
+        const uint32_t c = ((seq_end + 3u) >> 4) + hl;
+        const uint4 fill = make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u);
+        if (16u * c < rec_end) sts128(smem + 16u * c, fill);
+    }
+    __syncwarp();
+    {
+        const uint32_t c = (seq_off >> 4) + hl;
+        const int k0 = (int)(16u * c) - (int)seq_off;
+        const int q = half ? rel + k0 : rel + (int)S - 16 - k0;  // first of 16 consecutive haplotype bases, from the first word
+        const int j = q >> 3;
+        const uint32_t sh = ((uint32_t)q & 7u) * 4u;
+        uint32_t w[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int jj = j + t;
+            const uint32_t x0 = __shfl_sync(0xffffffffu, W0, (int)((lane & 16u) | ((uint32_t)jj & 15u)));
+            const uint32_t x1 = __shfl_sync(0xffffffffu, W1, (int)((lane & 16u) | ((uint32_t)jj & 15u)));
+            w[t] = jj < 0 ? 0u : (jj < 16 ? x0 : x1);
+        }
+        uint32_t b0 = __funnelshift_r(w[0], w[1], sh), b1 = __funnelshift_r(w[1], w[2], sh);  // bases 0-7, 8-15 of the run
+        if (!half) {  // reverse complement: reverse the 16 symbols and complement each
+            const uint32_t t0 = __brev(b1), t1 = __brev(b0);
+            b0 = t0;
+            b1 = t1;
+        }
+        uint4 v;
+        const bool ok0 = expand8_onehot(b0, v.x, v.y), ok1 = expand8_onehot(b1, v.z, v.w);
+        if (!(ok0 && ok1)) {  // rare: ambiguity codes (reads outside the read are masked by the later stores)
+            v.x = expand4_any(b0);
+            v.y = expand4_any(b0 >> 16);
+            v.z = expand4_any(b1);
+            v.w = expand4_any(b1 >> 16);
+        }
         if (16u * c < seq_end) sts128(smem + 16u * c, v);
     }
     __syncwarp();
@@ -405,7 +481,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_emit(const __grid_c
     const uint32_t tile_m0 = a.tile_mol0[tile];
     const uint64_t t1 = a.tile_off1[tile], t2 = a.tile_off2[tile];
     const uint32_t bytes1 = (uint32_t)(a.tile_off1[tile + 1] - t1), bytes2 = (uint32_t)(a.tile_off2[tile + 1] - t2);
-    const bool fast = BPB == 2 && a.fast_ok && a.tile_flags[tile];
+    const bool fast = a.fast_ok && a.tile_flags[tile];
     // warm L2 for a tile that a later wave of CTAs will run (descriptors are read exactly once)
     if (threadIdx.x < 4 && blockIdx.x + 1184u < a.n_tiles)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(a.fdesc + (p0 + 1184ull * a.tile_pairs)) + 128u * threadIdx.x));
@@ -454,24 +530,28 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_emit(const __grid_c
         s_fb[threadIdx.x] = make_uint4(f.wbase1, f.wbase2, f.mol, f.pk);
         // start the loads phases 1 and 2 will need
         prefetch_l1(a.hap + f.wbase1);
-        prefetch_l1(a.hap + f.wbase1 + 15);
+        prefetch_l1(a.hap + f.wbase1 + (BPB == 2 ? 15 : 31));
         prefetch_l1(a.hap + f.wbase2);
-        prefetch_l1(a.hap + f.wbase2 + 15);
+        prefetch_l1(a.hap + f.wbase2 + (BPB == 2 ? 15 : 31));
         prefetch_l1(a.text + (uint64_t)f.mol * a.text_stride);
     }
     const uint32_t sm = (uint32_t)__cvta_generic_to_shared(smem);
     __syncthreads();
-    {   // the reference word of pair t + EMIT_WARPS is loaded while pair t is expanded
+    {   // the reference words of pair t + EMIT_WARPS are loaded while pair t is expanded
         const uint32_t half = lane >> 4, hl = lane & 15u;
         FastDesc f = load_fast_desc(s_fa, s_fb, warp < np ? warp : 0);
-        uint32_t W = __ldg(a.hap + (half ? f.wbase2 : f.wbase1) + hl);
+        const uint32_t *wp = a.hap + (half ? f.wbase2 : f.wbase1) + hl;
+        uint32_t W0 = __ldg(wp), W1 = BPB == 4 ? __ldg(wp + 16) : 0u;
         for (uint32_t t = warp; t < np; t += EMIT_WARPS) {
             const uint32_t tn = t + EMIT_WARPS < np ? t + EMIT_WARPS : t;
             const FastDesc fn = load_fast_desc(s_fa, s_fb, tn);
-            const uint32_t Wn = __ldg(a.hap + (half ? fn.wbase2 : fn.wbase1) + hl);
-            emit_pair_seq(a, f, W, sm, lane);
+            const uint32_t *wn = a.hap + (half ? fn.wbase2 : fn.wbase1) + hl;
+            const uint32_t W0n = __ldg(wn), W1n = BPB == 4 ? __ldg(wn + 16) : 0u;
+            if (BPB == 2) emit_pair_seq(a, f, W0, sm, lane);
+            else emit_pair_seq4(a, f, W0, W1, sm, lane);
             f = fn;
-            W = Wn;
+            W0 = W0n;
+            W1 = W1n;
         }
     }
     __syncthreads();

@@ -546,7 +546,7 @@ static int32_t upload_schemas(mmk_ctx *ctx) {
 
 static inline uint64_t words_for(int64_t len, int bpb) {
     uint64_t per = 32 / bpb;
-    uint64_t w = ((uint64_t)len + per - 1) / per + 32;  // pad words: the emit kernel's 16-word window loads over-read
+    uint64_t w = ((uint64_t)len + per - 1) / per + 48;  // pad words: the emit kernel's 16/32-word window loads over-read
     return (w + 3) & ~3ull;                            // 16-byte aligned starts
 }
 

@@ -15,6 +15,8 @@ desc, _, nhap, fmt, kw = bench.WORKLOADS[wl]
 simkw = dict(bench.COMMON_SIM)
 simkw.update(kw)
 genome = bench.make_genome(wl, scale, "cuda:0", pin=True)
+if os.environ.get("MMK_FORCE_4BIT"):  # one N makes the whole reference 4-bit
+    genome[0][2][12345] = ord("N")
 sim = M.Simulator(fmt, seed=42, device=0, max_chunk_bytes=2048 << 20, **simkw)
 for nm, hap, h in genome:
     sim.add_contig(nm, (h.data_ptr(), h.numel()), hap)

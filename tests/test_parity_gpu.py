@@ -158,6 +158,29 @@ def test_parameter_regions(tmp_path, kw):
     check_single([p1, p2], "tellseq", seed=77, coverage=8, **kw)
 
 
+def test_iupac_ambiguity_codes_4bit(tmp_path):
+    """IUPAC ambiguity codes, N runs, gaps and lower case: the 4-bit reference path (fast tiles convert
+    non-ACGT symbols one by one; complement of an ambiguity code is its bit-reversed mask)."""
+    rng = np.random.default_rng(10)
+    seqs = []
+    for L in (70000, 50000):
+        a = np.frombuffer(random_bases(rng, L), dtype=np.uint8).copy()
+        idx = rng.integers(0, L, size=L // 40)
+        a[idx] = np.frombuffer(b"MRWSYKVHDBN-", dtype=np.uint8)[rng.integers(0, 12, size=len(idx))]
+        a[1000:1400] = ord("N")
+        low = rng.integers(0, L, size=L // 10)
+        a[low] = np.where((a[low] >= 65) & (a[low] <= 90), a[low] + 32, a[low])
+        seqs.append(a.tobytes())
+    p = os.path.join(str(tmp_path), "amb.fa")
+    write_fasta(p, [("ctgA", seqs[0]), ("ctgB", seqs[1])])
+    gpu, orc = check_single([p], "haplotagging", seed=21, coverage=12, **CLI)
+    assert b"N" in gpu["r1"] and b"R" in gpu["r2"] and b"-" in gpu["r1"]
+    forced = gpu_single([p], "haplotagging", 21, coverage=12, variates=False, force_generic=True, **CLI)
+    assert forced["r1"] == gpu["r1"] and forced["r2"] == gpu["r2"]
+    masked = gpu_single([p], "haplotagging", 21, mask=True, coverage=12, variates=False, **CLI)
+    assert b"N" not in masked["r1"].replace(b"1:N:0", b"")  # mask_N! replaces exactly the N's (other codes stay)
+
+
 def test_many_schemas_many_epochs(tmp_path):
     """40 contigs × 2 haplotypes of very different lengths: dozens of pruning epochs, small batches."""
     rng = np.random.default_rng(8)
