@@ -323,7 +323,7 @@ __global__ void k_group_nmol(SimConst sc, uint64_t g0, uint32_t n_groups, uint32
     nmol[i] = draw_nmol(sc, g0 + i, rec);
 }
 
-constexpr uint32_t HCH = 4096;  // molecules per histogram chunk
+constexpr uint32_t HCH = 512;  // molecules per histogram chunk (the finish kernel walks one chunk serially)
 
 __global__ void k_fill_lpos(const uint16_t *live, uint32_t n_live, uint16_t *lpos) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

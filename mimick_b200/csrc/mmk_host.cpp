@@ -109,6 +109,8 @@ struct mmk_ctx {
     DBuf<unsigned long long> d_hist, d_first_err;
     DBuf<uint8_t> d_res;
     DBuf<uint64_t> d_scan_tmp;
+    uint8_t *h_res = nullptr;   // pinned: batch result + per-schema need
+    size_t h_res_cap = 0;
     // placement / chunking scratch, kept between calls
     DBuf<uint64_t> s_bounds, s_b1, s_b2;
     DBuf<unsigned long long> s_err, s_gather;
@@ -388,6 +390,7 @@ extern "C" void mmk_destroy(mmk_ctx *c) {
     if (c->h_stats) cudaFreeHost(c->h_stats);
     if (c->d_u32x2) cudaFree(c->d_u32x2);
     if (c->h_u32x2) cudaFreeHost(c->h_u32x2);
+    if (c->h_res) cudaFreeHost(c->h_res);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     for (int i = 0; i < 2; ++i) {
@@ -990,8 +993,14 @@ extern "C" int32_t mmk_plan(mmk_ctx *ctx, mmk_plan_info *out) {
     CU(ctx->d_first_err.ensure(1));
     const size_t res_bytes = sizeof(BatchResult) + (size_t)K * 8;
     CU(ctx->d_res.ensure(res_bytes));
-    std::vector<uint8_t> h_res(res_bytes);
-    std::vector<int64_t> need(K);
+    if (ctx->h_res_cap < res_bytes + (size_t)K * 8) {  // pinned: the per-batch control round trip is latency-bound
+        if (ctx->h_res) cudaFreeHost(ctx->h_res);
+        ctx->h_res = nullptr;
+        CU(cudaMallocHost((void **)&ctx->h_res, res_bytes + (size_t)K * 8 + 64));
+        ctx->h_res_cap = res_bytes + (size_t)K * 8;
+    }
+    uint8_t *h_res = ctx->h_res;
+    int64_t *need = (int64_t *)(ctx->h_res + ((res_bytes + 15) & ~(size_t)15));
 
     // the group table is rebuilt by every call (no state is carried between runs)
     ctx->g_tab = 0;
@@ -1037,16 +1046,16 @@ extern "C" int32_t mmk_plan(mmk_ctx *ctx, mmk_plan_info *out) {
         }
         const uint64_t max_mol = (uint64_t)nb * max_nmol;
         CU(ctx->d_hist.ensure((size_t)plan_hist_chunks(max_mol) * n_live));
-        CU(cudaMemcpyAsync(ctx->d_need.p, need.data(), n_live * 8, cudaMemcpyHostToDevice, ctx->st));
+        CU(cudaMemcpyAsync(ctx->d_need.p, need, n_live * 8, cudaMemcpyHostToDevice, ctx->st));
         plan_batch(ctx->sc, ctx->d_sch.p, ctx->d_live.p, ctx->d_lpos.p, n_live, (uint16_t)(ctx->epoch_nlive.size() - 1), g0, nb,
                    ctx->d_gnmol.p, ctx->d_goff.p, plan_dev(ctx), max_mol, ctx->d_need.p, ctx->d_hist.p, ctx->d_first_err.p,
                    (BatchResult *)ctx->d_res.p, ctx->st);
         const size_t rb = sizeof(BatchResult) + (size_t)(n_live ? n_live - 1 : 0) * 8;
-        CU(cudaMemcpyAsync(h_res.data(), ctx->d_res.p, rb, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaMemcpyAsync(h_res, ctx->d_res.p, rb, cudaMemcpyDeviceToHost, ctx->st));
         CU(cudaStreamSynchronize(ctx->st));
         CU(cudaGetLastError());
         ++n_batches;
-        const BatchResult *r = (const BatchResult *)h_res.data();
+        const BatchResult *r = (const BatchResult *)h_res;
         if (r->first_error != ~0ull) {
             ctx->n_mol = 0;
             return fail(ctx, (int32_t)r->error_code, "molecule %llu: %s", (unsigned long long)(n_mol + r->first_error),
