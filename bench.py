@@ -143,6 +143,23 @@ class ClockSampler:
         return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic():
+    """DRAM bytes (read + write) of one k_emit launch from the committed `ncu --set full` capture, with the
+    launch's algorithmic bytes for comparison (profiles/r01_k_emit_ncu_full.csv); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r01_k_emit_ncu_full.csv")
+    if not os.path.exists(p):
+        return None, None
+    vals = {}
+    for ln in open(p):
+        f = ln.strip().split(",")
+        if len(f) >= 3 and f[0].startswith("dram__bytes_"):
+            mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(f[-1], 1)
+            vals[f[0]] = float(f[1]) * mult
+    if len(vals) < 2:
+        return None, None
+    return sum(vals.values()), "profiles/r01_k_emit_ncu_full.csv (one 2 GiB-chunk launch: 4.35 GB algorithmic)"
+
+
 def peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -320,6 +337,7 @@ def cuda_arm(args):
     algo_bytes = place.r1_bytes + place.r2_bytes + place.gather_bytes  # this rank, per step
     achieved = algo_bytes * args.steps / (emit_ms / 1e3) / 1e9
     peak, peak_src = peak_hbm()
+    traffic, traffic_src = ncu_traffic()
 
     # ---- end to end through the C ABI with host buffers: `e2e` --------------------------------
     slot_bytes, n_chunks = sim.chunk_layout()
@@ -384,7 +402,7 @@ def cuda_arm(args):
                        "output_ring": f"2 x 2 x {args.chunk_mib} MiB device buffers, reused chunk after chunk"},
             "fastq_gb_per_s": total_bytes / (ms_per_step / 1e3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_emit", "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_emit", "peak_source": peak_src,
                          "algorithmic_bytes_per_step": int(algo_bytes), "kernel_ms_per_step": emit_ms / args.steps,
                          "kernel_share_of_step": (emit_ms / args.steps) / ms_per_step},
             "cpu_baseline": cpu,
