@@ -327,3 +327,29 @@ def test_error_sites(tmp_path):
         with pytest.raises(M.MimickError) as e:
             sim.place()
         assert e.value.status == 3
+
+
+def test_mimick_function_writes_the_reference_file_layout(tmp_path, ref_fasta, ref_vcf):
+    """The public function with the reference's two methods and keywords (Main.jl:24, :88): file naming
+    `<prefix>.R{1,2}.fq` and `<outdir>/<sample>.R{1,2}.fq`, contents identical to the oracle's."""
+    import mimick_b200 as M
+    fastas = make_ci_haplotypes(tmp_path, seed=41, big=30000)
+    prefix = os.path.join(str(tmp_path), "single", "SIM")
+    out = M.mimick(fastas, "stlfr", prefix=prefix, coverage=6, seed=5, mask=True, **CLI)
+    orc = O.mimick_single(fastas, "stlfr", seed=5, mask=True, coverage=6, **CLI)
+    assert open(prefix + ".R1.fq", "rb").read() == orc.r1 and open(prefix + ".R2.fq", "rb").read() == orc.r2
+    assert out[0].n_pairs == len(orc.insert_start)
+    # two "GPUs" on one device: the parts concatenate to the same files
+    for rank in range(2):
+        M.mimick(fastas, "stlfr", prefix=prefix + "_sh", coverage=6, seed=5, mask=True, rank=rank, world=2, **CLI)
+    cat1 = b"".join(open(f"{prefix}_sh.R1.fq.part{r}", "rb").read() for r in range(2))
+    assert cat1 == orc.r1
+    outdir = os.path.join(str(tmp_path), "multi")
+    outs = M.mimick(ref_fasta, ref_vcf, "standard:haplotagging", outdir=outdir, coverage=0.5, seed=9, rank=1, world=4, **CLI)
+    assert [o.name for o in outs] == ["tsk_1", "tsk_5"]   # samples round-robin over ranks
+    want = O.mimick_multi(ref_fasta, ref_vcf, "standard:haplotagging", seed=9, coverage=0.5, samples=["tsk_1", "tsk_5"], **CLI)
+    for o in outs:
+        assert open(o.r1_path, "rb").read() == want[o.name].r1 and open(o.r2_path, "rb").read() == want[o.name].r2
+        assert os.path.basename(o.r1_path) == o.name + ".R1.fq"
+    with pytest.raises(TypeError):
+        M.mimick(fastas, "stlfr", gzip=True)
