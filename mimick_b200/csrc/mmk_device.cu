@@ -28,14 +28,6 @@ unsigned long long launch_count() { return g_launches; }
 // ------------------------------------------------------------------------------------------
 // small device helpers
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t ndigits_u64(uint64_t v) {
-    uint32_t d = 1;
-    while (v >= 10) {
-        v /= 10;
-        ++d;
-    }
-    return d;
-}
 __device__ __forceinline__ uint32_t ndigits_u32(uint32_t v) {
     if (v >= 100000u) {
         if (v >= 10000000u) return v >= 1000000000u ? 10u : (v >= 100000000u ? 9u : 8u);
@@ -861,15 +853,13 @@ size_t place_tmp_bytes(uint64_t max_pairs) { return (size_t)(max_pairs + 1) * si
 void place_segment(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint32_t m_lo,
                    uint32_t m_hi, uint64_t pair_lo, uint64_t pair_hi, const uint64_t *d_read_off_local,
                    const uint32_t *d_tile_mol0, uint32_t n_tiles, uint32_t tile_pairs, void *d_tmp, uint32_t *d_acc_i,
-                   unsigned long long *d_acc_f, uint32_t *d_perm, uint32_t *d_bins, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text,
+                   unsigned long long *d_acc_f, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text,
                    uint32_t text_stride, unsigned long long *d_err, cudaStream_t st) {
     if (m_hi <= m_lo) return;
     const uint64_t np = pair_hi - pair_lo;
     const uint32_t nm = m_hi - m_lo;
     if (np) LAUNCH(k_insert_draws, (unsigned)((np + 255) / 256), 256, 0, st, sc, plan, mol0, n_mol, d_read_off_local, d_tile_mol0,
                    n_tiles, tile_pairs, pair_lo, pair_hi, (PairTmp *)d_tmp, d_acc_i, d_acc_f);
-    (void)d_perm;
-    (void)d_bins;
     LAUNCH(k_place_chain, (nm + PLACE_BLOCK - 1) / PLACE_BLOCK, 256, 0, st, sc, d_sch, plan, mol0, m_lo, m_hi, d_read_off_local,
            pair_lo, (PairTmp *)d_tmp, d_acc_i, d_acc_f, d_ins, d_mol, d_err);
     LAUNCH(k_mol_text, (nm + 127) / 128, 128, 0, st, sc, d_sch, mol0, m_lo, m_hi, d_mol, d_text, text_stride);
@@ -890,59 +880,59 @@ void tile_prepare(const EmitArgs &a, uint32_t n_tiles_total, uint32_t *d_sum1, u
            d_gather);
 }
 
-__global__ void k_find_tile(const uint64_t *off1, const uint64_t *off2, uint32_t tile0, uint32_t n_tiles, uint64_t cap,
-                            uint32_t *out) {
-    if (threadIdx.x >= 2) return;
-    const uint64_t *off = threadIdx.x ? off2 : off1;
-    uint64_t base = off[tile0];
-    uint32_t lo = tile0, hi = n_tiles;  // largest t with off[t] - base <= cap
-    while (lo < hi) {
-        uint32_t mid = (uint32_t)(((uint64_t)lo + hi + 1) >> 1);
-        if (off[mid] - base <= cap) lo = mid; else hi = mid - 1;
-    }
-    out[threadIdx.x] = lo;
-}
 // Chunk table: tile boundaries so that each chunk's R1 and R2 bytes both fit `cap`.
 // bounds[0] = 0, bounds[k+1] = end tile of chunk k; *n_out = number of chunks (0xffffffff if a
 // single tile exceeds cap).
+// One warp: 32-ary search (each lane probes one pivot) instead of 25 dependent loads per boundary.
+__device__ __forceinline__ uint32_t warp_upper_tile(const uint64_t *off, uint32_t lo, uint32_t hi, uint64_t limit, uint32_t lane) {
+    // largest t in [lo, hi] with off[t] <= limit, given off[lo] <= limit
+    while (hi > lo) {
+        const uint32_t span = hi - lo;
+        const uint32_t step = (span + 31u) / 32u;
+        const uint32_t t = lo + step * (lane + 1u);
+        const bool ok = t <= hi && off[t] <= limit;
+        const unsigned b = __ballot_sync(0xffffffffu, ok);
+        const uint32_t n_ok = __popc(b);  // pivots are increasing, so ok lanes form a prefix
+        const uint32_t nlo = lo + step * n_ok;
+        uint32_t nhi = lo + step * (n_ok + 1u) - 1u;
+        if (nhi > hi) nhi = hi;
+        lo = nlo;
+        hi = nhi;
+    }
+    return lo;
+}
 __global__ void k_chunk_table(const uint64_t *off1, const uint64_t *off2, uint32_t n_tiles, uint64_t cap, uint32_t *bounds,
                               uint64_t *boff1, uint64_t *boff2, uint32_t max_chunks, uint32_t *n_out) {
+    const uint32_t lane = threadIdx.x;
     uint32_t t0 = 0, k = 0;
-    bounds[0] = 0;
-    boff1[0] = off1[0];
-    boff2[0] = off2[0];
+    if (lane == 0) {
+        bounds[0] = 0;
+        boff1[0] = off1[0];
+        boff2[0] = off2[0];
+    }
     while (t0 < n_tiles && k < max_chunks) {
-        uint32_t best = n_tiles;
-        for (int r = 0; r < 2; ++r) {
-            const uint64_t *off = r ? off2 : off1;
-            uint64_t base = off[t0];
-            uint32_t lo = t0, hi = n_tiles;
-            while (lo < hi) {
-                uint32_t mid = (uint32_t)(((uint64_t)lo + hi + 1) >> 1);
-                if (off[mid] - base <= cap) lo = mid; else hi = mid - 1;
-            }
-            best = lo < best ? lo : best;
-        }
+        const uint32_t e1 = warp_upper_tile(off1, t0, n_tiles, off1[t0] + cap, lane);
+        const uint32_t e2 = warp_upper_tile(off2, t0, n_tiles, off2[t0] + cap, lane);
+        const uint32_t best = e1 < e2 ? e1 : e2;
         if (best <= t0) {
-            *n_out = 0xffffffffu;
+            if (lane == 0) *n_out = 0xffffffffu;
             return;
         }
-        bounds[++k] = best;
-        boff1[k] = off1[best];
-        boff2[k] = off2[best];
+        ++k;
+        if (lane == 0) {
+            bounds[k] = best;
+            boff1[k] = off1[best];
+            boff2[k] = off2[best];
+        }
         t0 = best;
     }
-    *n_out = (t0 < n_tiles) ? 0xfffffffeu : k;
+    if (lane == 0) *n_out = (t0 < n_tiles) ? 0xfffffffeu : k;
 }
 void chunk_table(const uint64_t *d_off1, const uint64_t *d_off2, uint32_t n_tiles, uint64_t cap, uint32_t *d_bounds,
                  uint64_t *d_boff1, uint64_t *d_boff2, uint32_t max_chunks, uint32_t *d_n, cudaStream_t st) {
-    LAUNCH(k_chunk_table, 1, 1, 0, st, d_off1, d_off2, n_tiles, cap, d_bounds, d_boff1, d_boff2, max_chunks, d_n);
+    LAUNCH(k_chunk_table, 1, 32, 0, st, d_off1, d_off2, n_tiles, cap, d_bounds, d_boff1, d_boff2, max_chunks, d_n);
 }
 
-void find_tile(const uint64_t *d_off1, const uint64_t *d_off2, uint32_t tile0, uint32_t n_tiles, uint64_t cap, uint32_t *d_out,
-               cudaStream_t st) {
-    LAUNCH(k_find_tile, 1, 32, 0, st, d_off1, d_off2, tile0, n_tiles, cap, d_out);
-}
 
 void emit(const EmitArgs &a, cudaStream_t st) {
     if (a.n_tiles == 0) return;

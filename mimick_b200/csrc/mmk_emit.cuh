@@ -23,7 +23,6 @@
 namespace mmkdev {
 
 constexpr int EMIT_MAX_TP = 64;  // pairs per tile <= threads / 4 (one thread per header piece)
-constexpr int EMIT_SCR = 192;  // per-warp header scratch bytes
 
 struct PairDesc {
     uint64_t word_off;   // packed haplotype start (32-bit words)
@@ -200,11 +199,6 @@ __global__ void __launch_bounds__(256) k_tile_prepare(EmitArgs a, uint32_t n_til
 // ------------------------------------------------------------------------------------------
 // fast path pieces
 // ------------------------------------------------------------------------------------------
-// ceil(2^64 / 10^(9-k)) for k = 0..8; k = 9 (divide by 1) is special-cased
-__constant__ unsigned long long c_magic10[10] = {18446744074ull, 184467440738ull, 1844674407371ull, 18446744073710ull,
-                                                 184467440737096ull, 1844674407370956ull, 18446744073709552ull,
-                                                 184467440737095517ull, 1844674407370955162ull, 0ull};
-
 // 16 bases (32 bits, base i in bits 2i..2i+1) → 16 ASCII bytes through a 4-entry byte LUT.
 // `bits & 0x33333333` already has the even bases as PRMT selectors (one nibble each), `bits >> 2`
 // the odd ones; four lookups and four interleaving PRMTs give the 16 bytes in order.
@@ -251,7 +245,16 @@ __device__ __forceinline__ FastDesc load_fast_desc(const uint4 *fa, const uint4 
     f.wbase1 = y.x; f.wbase2 = y.y; f.mol = y.z; f.pk = y.w;
     return f;
 }
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+#ifndef MMK_PREFETCH_MODE
+#define MMK_PREFETCH_MODE 1
+#endif
+__device__ __forceinline__ void prefetch_l1(const void *p) {
+#if MMK_PREFETCH_MODE == 1
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#elif MMK_PREFETCH_MODE == 2
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
 #define FD_HDR(pk) ((pk) & 0xffu)
 #define FD_P(pk) (((pk) >> 8) & 0xffu)
 #define FD_SUF(pk) (((pk) >> 16) & 0x3fu)

@@ -132,7 +132,6 @@ struct mmk_ctx {
     DBuf<uint4> d_fdesc;
     DBuf<uint8_t> d_tile_flags;
     DBuf<uint8_t> d_tmp;      // placement scratch: (gap bits, insert length) per pair of one segment
-    DBuf<uint32_t> d_perm, d_bins;  // placement scratch: molecules of a segment ordered by insert count
     DBuf<uint32_t> d_acc_i;   // placement scratch: sum of insert lengths per molecule
     DBuf<unsigned long long> d_acc_f;  // ... and a 2^-16 fixed-point lower bound of their real sum
     uint32_t text_stride = 0, tile_pairs = 64, n_tiles = 0, stage_cap = 0;
@@ -147,8 +146,6 @@ struct mmk_ctx {
     std::vector<uint32_t> chunk_tiles;          // [n_chunks + 1] tile boundaries
     std::vector<uint64_t> chunk_off1, chunk_off2;  // [n_chunks + 1] byte offsets at those boundaries
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_emit[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
-    uint32_t *d_u32x2 = nullptr;
-    uint32_t *h_u32x2 = nullptr;  // pinned
 };
 
 // ------------------------------------------------------------------------------------------
@@ -362,8 +359,6 @@ extern "C" int32_t mmk_create(const mmk_params *p, mmk_ctx **out) {
     }
     CU(cudaMalloc((void **)&ctx->d_stats, sizeof(ContigStats)));
     CU(cudaMallocHost((void **)&ctx->h_stats, sizeof(ContigStats)));
-    CU(cudaMalloc((void **)&ctx->d_u32x2, 16));
-    CU(cudaMallocHost((void **)&ctx->h_u32x2, 16));
     return MMK_OK;
 }
 
@@ -388,8 +383,6 @@ extern "C" void mmk_destroy(mmk_ctx *c) {
     free_outputs(c);
     if (c->d_stats) cudaFree(c->d_stats);
     if (c->h_stats) cudaFreeHost(c->h_stats);
-    if (c->d_u32x2) cudaFree(c->d_u32x2);
-    if (c->h_u32x2) cudaFreeHost(c->h_u32x2);
     if (c->h_res) cudaFreeHost(c->h_res);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
@@ -1227,14 +1220,12 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
             CU(ctx->d_tmp.ensure(place_tmp_bytes(max_pairs)));
             CU(ctx->d_acc_i.ensure(ctx->s_nmol + 1));
             CU(ctx->d_acc_f.ensure(ctx->s_nmol + 1));
-            CU(ctx->d_perm.ensure(ctx->s_nmol + 1));
-            CU(ctx->d_bins.ensure(1024));
             CU(cudaMemsetAsync(ctx->d_acc_i.p, 0, (ctx->s_nmol + 1) * 4, ctx->st));
             CU(cudaMemsetAsync(ctx->d_acc_f.p, 0, (ctx->s_nmol + 1) * 8, ctx->st));
             for (int k = 0; k < n_seg; ++k)
                 place_segment(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->mol0, (uint32_t)ctx->s_nmol, (uint32_t)sb[k],
                               (uint32_t)sb[k + 1], sp[k], sp[k + 1], ctx->d_roff_l.p, ctx->d_tile_mol0.p, ctx->n_tiles,
-                              ctx->tile_pairs, ctx->d_tmp.p, ctx->d_acc_i.p, ctx->d_acc_f.p, ctx->d_perm.p, ctx->d_bins.p,
+                              ctx->tile_pairs, ctx->d_tmp.p, ctx->d_acc_i.p, ctx->d_acc_f.p,
                               ctx->d_ins.p, ctx->d_mol.p, ctx->d_text.p, ctx->text_stride, d_err.p, ctx->st);
         }
     }

@@ -143,13 +143,11 @@ size_t place_tmp_bytes(uint64_t max_pairs);
 void place_segment(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint32_t m_lo,
                    uint32_t m_hi, uint64_t pair_lo, uint64_t pair_hi, const uint64_t *d_read_off_local,
                    const uint32_t *d_tile_mol0, uint32_t n_tiles, uint32_t tile_pairs, void *d_tmp, uint32_t *d_acc_i,
-                   unsigned long long *d_acc_f, uint32_t *d_perm /*[>= m_hi - m_lo]*/, uint32_t *d_bins /*[1024]*/, uint2 *d_ins,
+                   unsigned long long *d_acc_f, uint2 *d_ins,
                    MolRec *d_mol, uint8_t *d_text, uint32_t text_stride, unsigned long long *d_err, cudaStream_t st);
 
 void tile_prepare(const EmitArgs &a, uint32_t n_tiles_total, uint32_t *d_sum1, uint32_t *d_sum2, uint4 *d_fdesc,
                   uint8_t *d_tile_flags, unsigned long long *d_gather, cudaStream_t st);
-void find_tile(const uint64_t *d_off1, const uint64_t *d_off2, uint32_t tile0, uint32_t n_tiles, uint64_t cap,
-               uint32_t *d_out, cudaStream_t st);
 void emit(const EmitArgs &a, cudaStream_t st);
 void chunk_table(const uint64_t *d_off1, const uint64_t *d_off2, uint32_t n_tiles, uint64_t cap, uint32_t *d_bounds,
                  uint64_t *d_boff1, uint64_t *d_boff2, uint32_t max_chunks, uint32_t *d_n, cudaStream_t st);
