@@ -322,35 +322,44 @@ __global__ void k_fill_lpos(const uint16_t *live, uint32_t n_live, uint16_t *lpo
     if (i < n_live) lpos[live[i]] = (uint16_t)i;
 }
 
-// One thread per barcode group of the batch [g0, g0 + n_groups): target picks against the current live
-// list, molecule size and number of inserts for each of its molecules (whose indices off[g] + slot do
-// not depend on the live set).  Also: per-chunk histogram of inserts per live schema (for the
-// coverage tracker) and the first molecule with a non-zero status.
-__global__ void k_plan_groups(SimConst sc, const SchemaDev *__restrict__ sch, const uint16_t *__restrict__ live,
-                              const uint16_t *__restrict__ lpos, uint32_t n_live, uint16_t epoch, uint64_t g0, uint32_t n_groups,
-                              const uint32_t *__restrict__ nmol, const uint64_t *__restrict__ off, PlanDev plan,
-                              unsigned long long *hist, unsigned long long *first_err) {
+// group table, second half: (group, slot) of every molecule — independent of the live set
+__global__ void k_fill_slots(uint64_t g_lo, uint32_t n_groups, const uint32_t *__restrict__ nmol, const uint64_t *__restrict__ off,
+                             PlanDev plan) {
     uint32_t gl = blockIdx.x * blockDim.x + threadIdx.x;
     if (gl >= n_groups) return;
-    const uint64_t g = g0 + gl;
+    const uint64_t g = g_lo + gl, o = off[g];
     const uint32_t n = nmol[g];
-    const uint64_t o = off[g], base = off[g0];
-    NoRec rec;
     for (uint32_t m = 0; m < n; ++m) {
-        const uint32_t t = live[draw_target(sc, g, m, n_live)];
-        uint32_t molsize, nfrags;
-        const uint32_t status = molecule_shape(sc, g, m, sch[t].len, molsize, nfrags, rec);
-        const uint64_t i = o + m;
-        plan.group[i] = g;
-        plan.slot[i] = m;
-        plan.schema[i] = (uint16_t)t;
-        plan.epoch[i] = epoch;
-        plan.size[i] = molsize;
-        plan.nfrags[i] = nfrags;
-        plan.status[i] = (uint8_t)status;
-        atomicAdd(&hist[((i - base) / HCH) * n_live + lpos[t]], (unsigned long long)nfrags);
-        if (status) atomicMin(first_err, (unsigned long long)(i - base));
+        plan.group[o + m] = g;
+        plan.slot[o + m] = m;
     }
+}
+
+// One thread per molecule of the batch's groups [g0, g0 + n_groups): target pick against the current live
+// list, molecule size and number of inserts.  Also: per-chunk histogram of inserts per live schema (for the
+// coverage tracker, laid out [schema][chunk] so the finish kernel reads it coalesced) and the first molecule
+// with a non-zero status.
+__global__ void k_plan_molecules(SimConst sc, const SchemaDev *__restrict__ sch, const uint16_t *__restrict__ live,
+                                 const uint16_t *__restrict__ lpos, uint32_t n_live, uint16_t epoch, uint64_t g0, uint32_t n_groups,
+                                 const uint64_t *__restrict__ off, PlanDev plan, unsigned long long *hist, uint32_t hstride,
+                                 unsigned long long *first_err) {
+    const uint64_t base = off[g0], n_mol = off[g0 + n_groups] - base;
+    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_mol) return;
+    const uint64_t i = base + j;
+    const uint64_t g = plan.group[i];
+    const uint32_t m = plan.slot[i];
+    NoRec rec;
+    const uint32_t t = live[draw_target(sc, g, m, n_live)];
+    uint32_t molsize, nfrags;
+    const uint32_t status = molecule_shape(sc, g, m, sch[t].len, molsize, nfrags, rec);
+    plan.schema[i] = (uint16_t)t;
+    plan.epoch[i] = epoch;
+    plan.size[i] = molsize;
+    plan.nfrags[i] = nfrags;
+    plan.status[i] = (uint8_t)status;
+    atomicAdd(&hist[(uint64_t)lpos[t] * hstride + (uint32_t)(j / HCH)], (unsigned long long)nfrags);
+    if (status) atomicMin(first_err, (unsigned long long)j);
 }
 
 // One block closes the batch: per live schema the barcode group in which its cumulative insert count
@@ -359,7 +368,7 @@ __global__ void k_plan_groups(SimConst sc, const SchemaDev *__restrict__ sch, co
 __global__ void __launch_bounds__(1024) k_plan_finish(const uint16_t *__restrict__ schema, const uint32_t *__restrict__ nfrags,
                                                       const uint64_t *__restrict__ group, const uint64_t *__restrict__ off,
                                                       uint64_t g0, uint32_t n_groups, const uint16_t *__restrict__ live,
-                                                      uint32_t n_live, const unsigned long long *__restrict__ hist,
+                                                      uint32_t n_live, const unsigned long long *__restrict__ hist, uint32_t hstride,
                                                       const int64_t *__restrict__ need, const unsigned long long *first_err,
                                                       const uint8_t *__restrict__ status, BatchResult *res) {
     __shared__ unsigned long long s_cut;
@@ -385,7 +394,7 @@ __global__ void __launch_bounds__(1024) k_plan_finish(const uint16_t *__restrict
             uint32_t found = 0xffffffffu;
             for (uint32_t c0 = 0; c0 < n_chunks && found == 0xffffffffu; c0 += 32) {
                 const uint32_t c = c0 + lane;
-                const unsigned long long v = c < n_chunks ? hist[(uint64_t)c * n_live + s] : 0ull;
+                const unsigned long long v = c < n_chunks ? hist[(uint64_t)s * hstride + c] : 0ull;
                 unsigned long long inc = v;
                 for (int o = 1; o < 32; o <<= 1) {
                     unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
@@ -440,7 +449,7 @@ __global__ void __launch_bounds__(1024) k_plan_finish(const uint16_t *__restrict
     for (uint32_t s = warp; s < n_live; s += n_warps) {
         const uint16_t sid = live[s];
         unsigned long long acc = 0;
-        for (uint32_t c = lane; c < full; c += 32) acc += hist[(uint64_t)c * n_live + s];
+        for (uint32_t c = lane; c < full; c += 32) acc += hist[(uint64_t)s * hstride + c];
         for (uint64_t i = (uint64_t)full * HCH + lane; i < nc; i += 32)
             if (schema[i] == sid) acc += nfrags[i];
         for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
@@ -465,6 +474,12 @@ void plan_extend_table(const SimConst &sc, uint64_t g_lo, uint64_t g_hi, uint32_
     LAUNCH(k_group_nmol, (n + 255) / 256, 256, 0, st, sc, g_lo, n, d_nmol + g_lo);
     exclusive_scan_u32(d_nmol + g_lo, d_off + g_lo, n, d_scan_tmp, st, d_off + g_lo);
 }
+// after the plan arrays were sized for off[g_hi] molecules
+void plan_fill_slots(uint64_t g_lo, uint64_t g_hi, const uint32_t *d_nmol, const uint64_t *d_off, PlanDev plan, cudaStream_t st) {
+    if (g_hi <= g_lo) return;
+    const uint32_t n = (uint32_t)(g_hi - g_lo);
+    LAUNCH(k_fill_slots, (n + 255) / 256, 256, 0, st, g_lo, n, d_nmol, d_off, plan);
+}
 
 void plan_set_live(const uint16_t *d_live, uint32_t n_live, uint16_t *d_lpos, cudaStream_t st) {
     LAUNCH(k_fill_lpos, (n_live + 255) / 256, 256, 0, st, d_live, n_live, d_lpos);
@@ -474,13 +489,14 @@ void plan_batch(const SimConst &sc, const SchemaDev *d_sch, const uint16_t *d_li
                 uint16_t epoch, uint64_t g0, uint32_t n_groups, const uint32_t *d_nmol, const uint64_t *d_off, PlanDev plan,
                 uint64_t max_mol, const int64_t *d_need, unsigned long long *d_hist, unsigned long long *d_first_err,
                 BatchResult *d_res, cudaStream_t st) {
+    (void)d_nmol;
     const uint32_t n_chunks = plan_hist_chunks(max_mol);
     cudaMemsetAsync(d_hist, 0, (size_t)n_chunks * n_live * sizeof(unsigned long long), st);
     cudaMemsetAsync(d_first_err, 0xff, 8, st);
-    LAUNCH(k_plan_groups, (n_groups + 127) / 128, 128, 0, st, sc, d_sch, d_live, d_lpos, n_live, epoch, g0, n_groups, d_nmol, d_off,
-           plan, d_hist, d_first_err);
-    LAUNCH(k_plan_finish, 1, 1024, 0, st, plan.schema, plan.nfrags, plan.group, d_off, g0, n_groups, d_live, n_live, d_hist, d_need,
-           d_first_err, plan.status, d_res);
+    LAUNCH(k_plan_molecules, (unsigned)((max_mol + 127) / 128), 128, 0, st, sc, d_sch, d_live, d_lpos, n_live, epoch, g0, n_groups, d_off,
+           plan, d_hist, n_chunks, d_first_err);
+    LAUNCH(k_plan_finish, 1, 1024, 0, st, plan.schema, plan.nfrags, plan.group, d_off, g0, n_groups, d_live, n_live, d_hist, n_chunks,
+           d_need, d_first_err, plan.status, d_res);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -940,7 +940,7 @@ static inline double now_ms() {
 }
 
 // grow the group table to cover groups [0, g_need) and the plan arrays to hold their molecules
-static int32_t ensure_group_table(mmk_ctx *ctx, uint64_t g_need, uint64_t keep_mol) {
+static int32_t ensure_group_table(mmk_ctx *ctx, uint64_t g_need, uint64_t g_keep, uint64_t keep_mol) {
     if (g_need <= ctx->g_tab) return MMK_OK;
     uint64_t g_new = std::max<uint64_t>(g_need, ctx->g_tab + ctx->g_tab / 2);
     g_new = (g_new + 1023) & ~1023ull;
@@ -953,7 +953,11 @@ static int32_t ensure_group_table(mmk_ctx *ctx, uint64_t g_need, uint64_t keep_m
     CU(cudaStreamSynchronize(ctx->st));
     CU(cudaGetLastError());
     ctx->g_tab = g_new;
-    return plan_reserve(ctx, total + 1, keep_mol);
+    int32_t rc = plan_reserve(ctx, total + 1, keep_mol);
+    if (rc) return rc;
+    // a reallocation keeps only the committed molecules [0, keep_mol) = groups [0, g_keep): label the rest again
+    plan_fill_slots(g_keep, g_new, ctx->d_gnmol.p, ctx->d_goff.p, plan_dev(ctx), ctx->st);
+    return MMK_OK;
 }
 
 extern "C" int32_t mmk_plan(mmk_ctx *ctx, mmk_plan_info *out) {
@@ -1033,7 +1037,7 @@ extern "C" int32_t mmk_plan(mmk_ctx *ctx, mmk_plan_info *out) {
             uint64_t want = g0 + nb;
             if (inserts_per_group > 0.0) want = std::max<uint64_t>(want, g0 + (uint64_t)((double)remaining_need / inserts_per_group * 1.05) + 4096);
             if (g0 + nb > ctx->g_tab) {
-                int32_t rc = ensure_group_table(ctx, want, n_mol);
+                int32_t rc = ensure_group_table(ctx, want, g0, n_mol);
                 if (rc) return rc;
             }
         }

@@ -126,6 +126,7 @@ void exclusive_scan_u32(const uint32_t *d_in, uint64_t *d_out /*[n+1]*/, uint64_
 uint32_t plan_hist_chunks(uint64_t max_molecules);
 void plan_extend_table(const SimConst &sc, uint64_t g_lo, uint64_t g_hi, uint32_t *d_nmol, uint64_t *d_off, uint64_t *d_scan_tmp,
                        cudaStream_t st);
+void plan_fill_slots(uint64_t g_lo, uint64_t g_hi, const uint32_t *d_nmol, const uint64_t *d_off, PlanDev plan, cudaStream_t st);
 void plan_set_live(const uint16_t *d_live, uint32_t n_live, uint16_t *d_lpos /*[65536]*/, cudaStream_t st);
 // d_hist needs plan_hist_chunks(max_mol) * n_live entries
 void plan_batch(const SimConst &sc, const SchemaDev *d_sch, const uint16_t *d_live, const uint16_t *d_lpos, uint32_t n_live,
