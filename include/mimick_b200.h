@@ -230,6 +230,27 @@ int32_t mmk_emit_all(mmk_ctx *ctx, float *kernel_ms);
 typedef int32_t (*mmk_chunk_cb)(void *user, const mmk_chunk *chunk, const void *r1_host, const void *r2_host);
 int32_t mmk_emit_stream(mmk_ctx *ctx, void *const r1_host[2], void *const r2_host[2], uint64_t slot_cap,
                         mmk_chunk_cb cb, void *user);
+
+/* ---- BGZF output -----------------------------------------------------------------------------
+ * The reference writes <prefix>.R{1,2}.fq.gz through BGZFCompressorStream (src/Main.jl:42-43,
+ * 111-112).  These entry points deliver the same text as blocked gzip: every chunk is a whole number
+ * of BGZF members (one per tile of records, coded on the device), so chunks — and the shards of
+ * several ranks — concatenate into a valid file; the writer appends mmk_bgzf_eof() once at the end.
+ * In the mmk_chunk of these calls r*_dev / r*_bytes / r*_offset describe the CODED bytes.
+ *
+ * mmk_bgzf_bound       host (or device) capacity one coded chunk of one stream may need
+ * mmk_emit_chunk_bgzf  like mmk_emit_chunk; the device pointers stay valid until the next emit call
+ * mmk_emit_stream_bgzf like mmk_emit_stream (slot_cap >= mmk_bgzf_bound)
+ * mmk_bgzf_eof         writes the 28-byte BGZF end-of-file member, returns 28
+ * mmk_bgzf_table       the fixed deflate code (reversed code | length << 16 per symbol) and the constant
+ *                      block prefix bit string; host-only, for tests */
+int32_t mmk_bgzf_bound(mmk_ctx *ctx, uint64_t *slot_bytes);
+int32_t mmk_emit_chunk_bgzf(mmk_ctx *ctx, mmk_chunk *out);
+int32_t mmk_emit_stream_bgzf(mmk_ctx *ctx, void *const r1_host[2], void *const r2_host[2], uint64_t slot_cap,
+                             mmk_chunk_cb cb, void *user);
+int32_t mmk_bgzf_eof(void *out, uint32_t cap);
+int32_t mmk_bgzf_table(uint32_t *litlen_codes, uint32_t *dist_codes, uint8_t *prefix, uint32_t prefix_cap,
+                       uint32_t *prefix_bits);
 /* bytes each output slot holds for this shard (after mmk_place) and the number of chunks */
 int32_t mmk_chunk_layout(mmk_ctx *ctx, uint64_t *slot_bytes, int32_t *n_chunks);
 

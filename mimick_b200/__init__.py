@@ -6,9 +6,9 @@ reference's `mimick(...)` API; importing it requires the built library — there
 """
 from . import _lib
 from ._lib import MimickError
-from .api import SampleOutput, Simulator, Vcf, interperet_format, mimick
+from .api import SampleOutput, Simulator, Vcf, bgzf_eof, interperet_format, mimick
 from .dist import RankCounts, ShardLayout, exchange_counts, layout_from_counts, samples_for_rank
 
-__all__ = ["mimick", "Simulator", "Vcf", "MimickError", "SampleOutput", "interperet_format"]
+__all__ = ["mimick", "Simulator", "Vcf", "MimickError", "SampleOutput", "interperet_format", "bgzf_eof"]
 
 _lib.load()  # fail loudly at import time if libmimick_b200.so is missing

@@ -75,6 +75,7 @@ EXPORTS = [
     "mmk_place", "mmk_emit_chunk", "mmk_rewind", "mmk_copy_chunk", "mmk_emit_to_host", "mmk_dump_molecules",
     "mmk_dump_inserts", "mmk_dump_variates", "mmk_dump_mask_variates", "mmk_kat_philox", "mmk_kat_math",
     "mmk_emit_all", "mmk_emit_stream", "mmk_chunk_layout", "mmk_launch_count", "mmk_clear_contigs",
+    "mmk_bgzf_bound", "mmk_emit_chunk_bgzf", "mmk_emit_stream_bgzf", "mmk_bgzf_eof", "mmk_bgzf_table",
 ]
 
 CHUNK_CB = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.POINTER(Chunk), C.c_void_p, C.c_void_p)
@@ -138,6 +139,11 @@ def load():
     sig("mmk_emit_all", i32, vp, P(C.c_float))
     sig("mmk_emit_stream", i32, vp, P(vp), P(vp), u64, vp, vp)
     sig("mmk_chunk_layout", i32, vp, P(u64), P(i32))
+    sig("mmk_bgzf_bound", i32, vp, P(u64))
+    sig("mmk_emit_chunk_bgzf", i32, vp, P(Chunk))
+    sig("mmk_emit_stream_bgzf", i32, vp, P(vp), P(vp), u64, vp, vp)
+    sig("mmk_bgzf_eof", i32, vp, C.c_uint32)
+    sig("mmk_bgzf_table", i32, vp, vp, vp, C.c_uint32, P(C.c_uint32))
     sig("mmk_launch_count", u64)
     sig("mmk_dump_molecules", i32, vp, i64, i64, vp)
     sig("mmk_dump_inserts", i32, vp, i64, i64, vp, vp)

@@ -219,6 +219,17 @@ class Simulator:
         self._ck(self._L.mmk_emit_chunk(self._h, C.byref(ch)))
         return ch
 
+    def emit_chunk_bgzf(self) -> Chunk:
+        """Next chunk as BGZF members (device pointers and sizes describe the coded bytes)."""
+        ch = Chunk()
+        self._ck(self._L.mmk_emit_chunk_bgzf(self._h, C.byref(ch)))
+        return ch
+
+    def bgzf_bound(self) -> int:
+        n = C.c_uint64()
+        self._ck(self._L.mmk_bgzf_bound(self._h, C.byref(n)))
+        return int(n.value)
+
     def rewind(self):
         self._ck(self._L.mmk_rewind(self._h))
 
@@ -251,9 +262,10 @@ class Simulator:
         self._ck(self._L.mmk_chunk_layout(self._h, C.byref(sb), C.byref(n)))
         return int(sb.value), int(n.value)
 
-    def emit_stream(self, r1_slots, r2_slots, slot_cap, consumer=None):
+    def emit_stream(self, r1_slots, r2_slots, slot_cap, consumer=None, bgzf=False):
         """Whole shard through two host slots per read (addresses; pinned memory recommended).
-        `consumer(chunk, r1_addr, r2_addr)` is called per chunk once its bytes are in host memory."""
+        `consumer(chunk, r1_addr, r2_addr)` is called per chunk once its bytes are in host memory.
+        `bgzf=True` delivers BGZF members instead of text (slot_cap >= bgzf_bound())."""
         a1 = (C.c_void_p * 2)(*r1_slots)
         a2 = (C.c_void_p * 2)(*r2_slots)
         cb = None
@@ -267,7 +279,21 @@ class Simulator:
                     traceback.print_exc()
                     return 1
             cb = _lib.CHUNK_CB(_cb)
-        self._ck(self._L.mmk_emit_stream(self._h, a1, a2, int(slot_cap), C.cast(cb, C.c_void_p) if cb else None, None))
+        fn = self._L.mmk_emit_stream_bgzf if bgzf else self._L.mmk_emit_stream
+        self._ck(fn(self._h, a1, a2, int(slot_cap), C.cast(cb, C.c_void_p) if cb else None, None))
+
+    def emit_bgzf_to_host(self):
+        """Whole shard as BGZF members (no end-of-file member); returns (R1, R2) bytes."""
+        cap = self.bgzf_bound()
+        slots = [np.empty(cap, dtype=np.uint8) for _ in range(4)]
+        parts = ([], [])
+
+        def consume(ch, p1, p2):
+            parts[0].append(C.string_at(p1, ch.r1_bytes))
+            parts[1].append(C.string_at(p2, ch.r2_bytes))
+        self.emit_stream([slots[0].ctypes.data, slots[1].ctypes.data], [slots[2].ctypes.data, slots[3].ctypes.data],
+                         cap, consume, bgzf=True)
+        return b"".join(parts[0]), b"".join(parts[1])
 
     def run(self):
         """plan → place → emit everything to host; returns (R1 bytes, R2 bytes)."""
@@ -341,26 +367,40 @@ class SampleOutput:
     seed: int
 
 
-def _write_shard(sim: Simulator, r1_path: str, r2_path: str, mode: str):
-    """File writes of chunk k overlap the generation and copy-out of chunk k+1 (mmk_emit_stream)."""
-    slot_bytes, _ = sim.chunk_layout()
+def bgzf_eof() -> bytes:
+    buf = C.create_string_buffer(28)
+    n = _lib.load().mmk_bgzf_eof(buf, 28)
+    assert n == 28
+    return buf.raw
+
+
+def _write_shard(sim: Simulator, r1_path: str, r2_path: str, mode: str, bgzf: bool = False, eof: bool = True):
+    """File writes of chunk k overlap the generation and copy-out of chunk k+1 (mmk_emit_stream).
+    `bgzf`: the chunks are BGZF members coded on the device; `eof` appends the end-of-file member."""
+    slot_bytes = sim.bgzf_bound() if bgzf else sim.chunk_layout()[0]
     slots = [np.empty(slot_bytes, dtype=np.uint8) for _ in range(4)]
     with open(r1_path, mode) as f1, open(r2_path, mode) as f2:
         def consume(ch, p1, p2):
             f1.write((C.c_char * ch.r1_bytes).from_address(p1))
             f2.write((C.c_char * ch.r2_bytes).from_address(p2))
         sim.emit_stream([slots[0].ctypes.data, slots[1].ctypes.data], [slots[2].ctypes.data, slots[3].ctypes.data],
-                        slot_bytes, consume)
+                        slot_bytes, consume, bgzf=bgzf)
+        if bgzf and eof:
+            f1.write(bgzf_eof())
+            f2.write(bgzf_eof())
 
 
 def mimick(*args, prefix: str = "simulated/SIM", outdir: str = "simulated", quiet: bool = False,
-           rank: int = 0, world: int = 1, **kw):
+           rank: int = 0, world: int = 1, compress: bool = True, **kw):
     """mimick(fasta::Vector{String}, format; ...)            — src/Main.jl:24
     mimick(fasta::String, vcf::String, format; outdir, ...) — src/Main.jl:88
 
     `rank`/`world` shard one run over several GPUs: every rank plans the same schedule and
     writes its own contiguous part to `<...>.R1.fq.part<rank>` (concatenate in rank order), or —
     in VCF mode — takes samples `rank, rank+world, ...`.
+    `compress` (default, as the reference): files are BGZF `*.fq.gz`, coded on the device; the parts of a
+    sharded run are whole BGZF members and only the last rank's part carries the end-of-file member.
+    `compress=False` writes plain `*.fq`.
     """
     unknown = set(kw) - set(_SIM_KW)
     if unknown:
@@ -387,8 +427,9 @@ def mimick(*args, prefix: str = "simulated/SIM", outdir: str = "simulated", quie
             sim.set_shard(rank, world)
             place = sim.place()
             suffix = "" if world == 1 else f".part{rank}"
-            r1p, r2p = f"{prefix}.R1.fq{suffix}", f"{prefix}.R2.fq{suffix}"
-            _write_shard(sim, r1p, r2p, "wb")
+            ext = "fq.gz" if compress else "fq"
+            r1p, r2p = f"{prefix}.R1.{ext}{suffix}", f"{prefix}.R2.{ext}{suffix}"
+            _write_shard(sim, r1p, r2p, "wb", bgzf=compress, eof=rank == world - 1)
             outs.append(SampleOutput("", r1p, r2p, place.n_pairs, place.n_molecules, place.r1_bytes, place.r2_bytes, sim.seed))
         return outs
     rc = L.mmk_check_variant_path(os.fspath(vcf).encode())
@@ -403,9 +444,10 @@ def mimick(*args, prefix: str = "simulated/SIM", outdir: str = "simulated", quie
             plan = sim.plan()
             sim.set_shard(0, 1)
             place = sim.place()
-            r1p = os.path.join(outdir, f"{v.samples[si]}.R1.fq")
-            r2p = os.path.join(outdir, f"{v.samples[si]}.R2.fq")
-            _write_shard(sim, r1p, r2p, "wb")
+            ext = "fq.gz" if compress else "fq"
+            r1p = os.path.join(outdir, f"{v.samples[si]}.R1.{ext}")
+            r2p = os.path.join(outdir, f"{v.samples[si]}.R2.{ext}")
+            _write_shard(sim, r1p, r2p, "wb", bgzf=compress)
             outs.append(SampleOutput(v.samples[si], r1p, r2p, place.n_pairs, place.n_molecules, place.r1_bytes,
                                      place.r2_bytes, sim.seed))
     v.close()

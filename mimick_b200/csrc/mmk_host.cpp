@@ -146,6 +146,20 @@ struct mmk_ctx {
     std::vector<uint32_t> chunk_tiles;          // [n_chunks + 1] tile boundaries
     std::vector<uint64_t> chunk_off1, chunk_off2;  // [n_chunks + 1] byte offsets at those boundaries
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_emit[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+
+    // BGZF stage
+    uint32_t tile_bytes_bound = 0;   // upper bound of one tile's text in one stream
+    DBuf<uint32_t> d_bz_tab;         // codes, CRC table, block prefix
+    uint32_t bz_hdr_bits = 0;
+    uint32_t bz_tiles_per_block = 1, bz_in_cap = 0, bz_max_blocks = 0, bz_slot_shift = 1;
+    uint64_t bz_out_cap = 0;
+    DBuf<uint8_t> d_bz_slots;
+    DBuf<uint32_t> d_bz_sizes;
+    DBuf<uint64_t> d_bz_offs;
+    DBuf<uint8_t> bz_out[2][2];      // [slot][read] packed BGZF bytes of a chunk
+    uint64_t *h_bz_tot = nullptr;    // pinned [slot][read]
+    uint64_t bz_cum[2] = {0, 0};     // BGZF bytes handed out so far per stream
+    bool bz_ready = false;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -384,6 +398,7 @@ extern "C" void mmk_destroy(mmk_ctx *c) {
     if (c->d_stats) cudaFree(c->d_stats);
     if (c->h_stats) cudaFreeHost(c->h_stats);
     if (c->h_res) cudaFreeHost(c->h_res);
+    if (c->h_bz_tot) cudaFreeHost(c->h_bz_tot);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     for (int i = 0; i < 2; ++i) {
@@ -1191,6 +1206,8 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
         while (tp & (tp - 1)) tp &= tp - 1;  // power of two: kernels turn pair index → tile with a shift
         while (tp > 8 && (uint64_t)tp * max_rec + 32 > 40 * 1024) tp >>= 1;
         ctx->tile_pairs = tp;
+        ctx->tile_bytes_bound = tp * max_rec;
+        ctx->bz_ready = false;
         ctx->stage_cap = (uint32_t)(((uint64_t)tp * max_rec + 32 + 15) & ~15ull);
         if (!ctx->fast_ok) ctx->stage_cap = 16;
     }
@@ -1403,6 +1420,7 @@ extern "C" int32_t mmk_rewind(mmk_ctx *ctx) {
     if (!ctx) return MMK_ERR_INVALID_ARG;
     ctx->tile_cursor = 0;
     ctx->slot = 0;
+    ctx->bz_cum[0] = ctx->bz_cum[1] = 0;
     return MMK_OK;
 }
 extern "C" int32_t mmk_copy_chunk(mmk_ctx *ctx, const mmk_chunk *ch, void *r1_host, void *r2_host) {
@@ -1494,6 +1512,250 @@ extern "C" int32_t mmk_emit_stream(mmk_ctx *ctx, void *const r1_host[2], void *c
             if (rc) return fail(ctx, rc, "chunk consumer returned %d", rc);
             return (int32_t)MMK_OK;
         });
+}
+
+// ------------------------------------------------------------------------------------------
+// BGZF output (the reference's writers are BGZFCompressorStream, src/Main.jl:42-43,111-112)
+// ------------------------------------------------------------------------------------------
+#include "mmk_bgzf_table.h"
+
+static uint32_t bit_reverse(uint32_t v, int n) {
+    uint32_t r = 0;
+    for (int i = 0; i < n; ++i) r |= ((v >> i) & 1u) << (n - 1 - i);
+    return r;
+}
+// canonical Huffman codes (RFC 1951 3.2.2) of `n` code lengths, bit-reversed for LSB-first packing: code | len << 16
+static void canonical_codes(const uint8_t *len, int n, uint32_t *out) {
+    uint32_t count[16] = {0}, next[16] = {0};
+    for (int i = 0; i < n; ++i) count[len[i]]++;
+    count[0] = 0;
+    uint32_t code = 0;
+    for (int b = 1; b < 16; ++b) {
+        code = (code + count[b - 1]) << 1;
+        next[b] = code;
+    }
+    for (int i = 0; i < n; ++i) out[i] = len[i] ? (bit_reverse(next[len[i]]++, len[i]) | ((uint32_t)len[i] << 16)) : 0u;
+}
+static uint32_t gf_mul(uint32_t a, uint32_t b) {
+    uint32_t p = 0;
+    for (int i = 0; i < 32; ++i) {
+        if (a & 0x80000000u) p ^= b;
+        a <<= 1;
+        b = (b >> 1) ^ ((b & 1u) ? 0xEDB88320u : 0u);
+    }
+    return p;
+}
+static std::vector<uint32_t> bgzf_table_words() {
+    std::vector<uint32_t> t(BGZF_TAB_CODES + (MMK_BGZF_HDR_BITS + 31) / 32, 0u);
+    canonical_codes(MMK_BGZF_LL_LEN, 286, t.data());
+    canonical_codes(MMK_BGZF_D_LEN, 30, t.data() + 286);
+    for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1u) ? 0xEDB88320u : 0u);
+        t[286 + 30 + i] = c;
+    }
+    for (size_t i = 0; i < sizeof MMK_BGZF_HDR; ++i) t[BGZF_TAB_CODES + i / 4] |= (uint32_t)MMK_BGZF_HDR[i] << (8 * (i % 4));
+    return t;
+}
+
+extern "C" int32_t mmk_bgzf_table(uint32_t *litlen_codes, uint32_t *dist_codes, uint8_t *prefix, uint32_t prefix_cap,
+                                  uint32_t *prefix_bits) {
+    std::vector<uint32_t> t = bgzf_table_words();
+    if (litlen_codes) memcpy(litlen_codes, t.data(), 286 * 4);
+    if (dist_codes) memcpy(dist_codes, t.data() + 286, 30 * 4);
+    if (prefix) {
+        if (prefix_cap < sizeof MMK_BGZF_HDR) return MMK_ERR_INVALID_ARG;
+        memcpy(prefix, MMK_BGZF_HDR, sizeof MMK_BGZF_HDR);
+    }
+    if (prefix_bits) *prefix_bits = MMK_BGZF_HDR_BITS;
+    return MMK_OK;
+}
+
+extern "C" int32_t mmk_bgzf_eof(void *out, uint32_t cap) {
+    static const uint8_t eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 27, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (!out || cap < sizeof eof) return MMK_ERR_INVALID_ARG;
+    memcpy(out, eof, sizeof eof);
+    return (int32_t)sizeof eof;
+}
+
+// geometry and buffers of the BGZF stage for the placed shard
+static int32_t bgzf_prepare(mmk_ctx *ctx) {
+    if (ctx->bz_ready) return MMK_OK;
+    if (ctx->d_bz_tab.cap == 0) {
+        std::vector<uint32_t> t = bgzf_table_words();
+        CU(ctx->d_bz_tab.ensure(t.size()));
+        CU(cudaMemcpyAsync(ctx->d_bz_tab.p, t.data(), t.size() * 4, cudaMemcpyHostToDevice, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        ctx->bz_hdr_bits = MMK_BGZF_HDR_BITS;
+    }
+    if (!ctx->h_bz_tot) CU(cudaMallocHost((void **)&ctx->h_bz_tot, 4 * sizeof(uint64_t)));
+    const uint32_t bound = std::max(ctx->tile_bytes_bound, 64u);
+    if (bound > 65280u) return fail(ctx, MMK_ERR_UNSUPPORTED, "one tile of records exceeds a BGZF block");
+    uint32_t G = 1;
+    if (const char *e = getenv("MMK_BGZF_TILES")) G = (uint32_t)std::max(1, atoi(e));
+    G = std::min(G, 65280u / bound);
+    ctx->bz_tiles_per_block = G;
+    ctx->bz_in_cap = (G * bound + 15) & ~15u;
+    uint32_t max_tiles = 0;
+    for (size_t k = 0; k + 1 < ctx->chunk_tiles.size(); ++k) max_tiles = std::max(max_tiles, ctx->chunk_tiles[k + 1] - ctx->chunk_tiles[k]);
+    ctx->bz_max_blocks = (max_tiles + G - 1) / G;
+    ctx->bz_slot_shift = 0;
+    while ((64u << ctx->bz_slot_shift) <= ctx->bz_in_cap) ++ctx->bz_slot_shift;  // largest shift with 2^shift <= in_cap / 32
+    ctx->bz_out_cap = bgzf_slots_bytes(ctx->out_cap, ctx->bz_max_blocks, ctx->bz_slot_shift);
+    CU(ctx->d_bz_slots.ensure(ctx->bz_out_cap));
+    CU(ctx->d_bz_sizes.ensure((size_t)ctx->bz_max_blocks + 1));
+    CU(ctx->d_bz_offs.ensure((size_t)ctx->bz_max_blocks + 2));
+    CU(ctx->d_scan_tmp.ensure((size_t)ctx->bz_max_blocks / 1024 + 8));
+    const int slots = ctx->out[1][0] ? 2 : 1;
+    for (int s = 0; s < slots; ++s)
+        for (int r = 0; r < 2; ++r) CU(ctx->bz_out[s][r].ensure(ctx->bz_out_cap));
+    ctx->bz_ready = true;
+    return MMK_OK;
+}
+
+// enqueue: text of chunk k (already being written into out[slot] on the stream) -> bz_out[slot][*], totals -> h_bz_tot
+static int32_t bgzf_launch(mmk_ctx *ctx, uint32_t k, int slot) {
+    const uint32_t t0 = ctx->chunk_tiles[k], t1 = ctx->chunk_tiles[k + 1];
+    const uint32_t G = ctx->bz_tiles_per_block;
+    const uint32_t nblk = (t1 - t0 + G - 1) / G;
+    BgzfArgs a;
+    memset(&a, 0, sizeof a);
+    a.tile0 = t0;
+    a.n_tiles = t1 - t0;
+    a.tiles_per_block = G;
+    a.in_cap = ctx->bz_in_cap;
+    a.max_records = G * ctx->tile_pairs;
+    a.crc_chunk = (ctx->bz_in_cap + bgzf_threads() - 1) / bgzf_threads();
+    {
+        uint32_t v = 0x80000000u;  // x^0
+        for (uint32_t i = 0; i < 8 * a.crc_chunk; ++i) v = (v >> 1) ^ ((v & 1u) ? 0xEDB88320u : 0u);
+        for (int j = 0; j < 8; ++j) {
+            a.crc_shift[j] = v;
+            v = gf_mul(v, v);
+        }
+    }
+    a.tab = ctx->d_bz_tab.p;
+    a.hdr_bits = ctx->bz_hdr_bits;
+    a.slots = ctx->d_bz_slots.p;
+    a.slot_shift = ctx->bz_slot_shift;
+    a.sizes = ctx->d_bz_sizes.p;
+    for (int r = 0; r < 2; ++r) {
+        a.text = ctx->out[slot][r];
+        a.tile_off = r ? ctx->d_tile_off2.p : ctx->d_tile_off1.p;
+        a.chunk_off = r ? ctx->chunk_off2[k] : ctx->chunk_off1[k];
+        bgzf_encode(a, nblk, ctx->st);
+        exclusive_scan_u32(ctx->d_bz_sizes.p, ctx->d_bz_offs.p, nblk, ctx->d_scan_tmp.p, ctx->st);
+        bgzf_compact(a, ctx->d_bz_offs.p, ctx->bz_out[slot][r].p, nblk, ctx->st);
+        CU(cudaMemcpyAsync(&ctx->h_bz_tot[slot * 2 + r], ctx->d_bz_offs.p + nblk, 8, cudaMemcpyDeviceToHost, ctx->st));
+    }
+    return MMK_OK;
+}
+static void bgzf_fill(mmk_ctx *ctx, int slot, mmk_chunk *ch) {  // after the totals arrived
+    ch->r1_dev = ctx->bz_out[slot][0].p;
+    ch->r2_dev = ctx->bz_out[slot][1].p;
+    ch->r1_bytes = ctx->h_bz_tot[slot * 2 + 0];
+    ch->r2_bytes = ctx->h_bz_tot[slot * 2 + 1];
+    ch->r1_offset = ctx->bz_cum[0];
+    ch->r2_offset = ctx->bz_cum[1];
+    ctx->bz_cum[0] += ch->r1_bytes;
+    ctx->bz_cum[1] += ch->r2_bytes;
+}
+
+extern "C" int32_t mmk_bgzf_bound(mmk_ctx *ctx, uint64_t *slot_bytes) {
+    if (!ctx || !slot_bytes) return MMK_ERR_INVALID_ARG;
+    if (!ctx->placed) return fail(ctx, MMK_ERR_STATE, "mmk_place has not run");
+    CU(cudaSetDevice(ctx->par.device));
+    int32_t rc = bgzf_prepare(ctx);
+    if (rc) return rc;
+    *slot_bytes = ctx->bz_out_cap;
+    return MMK_OK;
+}
+
+extern "C" int32_t mmk_emit_chunk_bgzf(mmk_ctx *ctx, mmk_chunk *out) {
+    if (!ctx || !out) return MMK_ERR_INVALID_ARG;
+    if (!ctx->placed) return fail(ctx, MMK_ERR_STATE, "mmk_place has not run");
+    CU(cudaSetDevice(ctx->par.device));
+    int32_t rc = bgzf_prepare(ctx);
+    if (rc) return rc;
+    memset(out, 0, sizeof *out);
+    if (ctx->tile_cursor >= n_chunks_of(ctx)) {
+        out->done = 1;
+        return MMK_OK;
+    }
+    int slot = ctx->out[1][0] ? ctx->slot : 0;
+    CU(cudaEventRecord(ctx->ev_a, ctx->st));
+    rc = launch_chunk(ctx, ctx->tile_cursor, slot, out);
+    if (rc) return rc;
+    rc = bgzf_launch(ctx, ctx->tile_cursor, slot);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev_b, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaGetLastError());
+    CU(cudaEventElapsedTime(&out->kernel_ms, ctx->ev_a, ctx->ev_b));
+    bgzf_fill(ctx, slot, out);
+    ctx->tile_cursor++;
+    ctx->slot ^= 1;
+    return MMK_OK;
+}
+
+extern "C" int32_t mmk_emit_stream_bgzf(mmk_ctx *ctx, void *const r1_host[2], void *const r2_host[2], uint64_t slot_cap,
+                                        mmk_chunk_cb cb, void *user) {
+    if (!ctx || !r1_host || !r2_host || !r1_host[0] || !r1_host[1] || !r2_host[0] || !r2_host[1]) return MMK_ERR_INVALID_ARG;
+    if (!ctx->placed) return fail(ctx, MMK_ERR_STATE, "mmk_place has not run");
+    CU(cudaSetDevice(ctx->par.device));
+    int32_t rc = bgzf_prepare(ctx);
+    if (rc) return rc;
+    if (slot_cap < ctx->bz_out_cap) return fail(ctx, MMK_ERR_INVALID_ARG, "host slots are smaller than mmk_bgzf_bound");
+    ctx->bz_cum[0] = ctx->bz_cum[1] = 0;
+    const uint32_t n = n_chunks_of(ctx);
+    const bool ring = ctx->out[1][0] != nullptr;
+    std::vector<mmk_chunk> chunks(n);
+    auto slot_of = [&](uint32_t k) { return ring ? (int)(k & 1) : 0; };
+    // chunk j: its coded sizes are known once ev_emit fired; then the copy is queued on the copy stream
+    auto start_copy = [&](uint32_t j) -> int32_t {
+        const int sl = slot_of(j);
+        CU(cudaEventSynchronize(ctx->ev_emit[sl]));
+        bgzf_fill(ctx, sl, &chunks[j]);
+        const mmk_chunk &ch = chunks[j];
+        if (ch.r1_bytes) CU(cudaMemcpyAsync(r1_host[j & 1], ch.r1_dev, ch.r1_bytes, cudaMemcpyDeviceToHost, ctx->st_copy));
+        if (ch.r2_bytes) CU(cudaMemcpyAsync(r2_host[j & 1], ch.r2_dev, ch.r2_bytes, cudaMemcpyDeviceToHost, ctx->st_copy));
+        CU(cudaEventRecord(ctx->ev_copy[sl], ctx->st_copy));
+        return MMK_OK;
+    };
+    auto finish = [&](uint32_t j) -> int32_t {
+        CU(cudaEventSynchronize(ctx->ev_copy[slot_of(j)]));
+        if (!cb) return MMK_OK;
+        int32_t r = cb(user, &chunks[j], r1_host[j & 1], r2_host[j & 1]);
+        if (r) return fail(ctx, r, "chunk consumer returned %d", r);
+        return MMK_OK;
+    };
+    for (uint32_t k = 0; k < n; ++k) {
+        const int slot = slot_of(k);
+        if (!ring && k >= 1) {  // one device slot: strictly serial
+            if ((rc = start_copy(k - 1))) return rc;
+            if ((rc = finish(k - 1))) return rc;
+        }
+        // the coded buffers of this slot are free once the copy of chunk k-2 finished
+        if (ring && k >= 2) CU(cudaStreamWaitEvent(ctx->st, ctx->ev_copy[slot], 0));
+        if ((rc = launch_chunk(ctx, k, slot, &chunks[k]))) return rc;
+        if ((rc = bgzf_launch(ctx, k, slot))) return rc;
+        CU(cudaEventRecord(ctx->ev_emit[slot], ctx->st));
+        if (ring && k >= 1) {
+            // host slot (k-1)&1 was handed back by finish(k-3) one iteration ago; the consumer of chunk k-2 then
+            // runs while chunk k-1 crosses PCIe and chunk k is being generated
+            if ((rc = start_copy(k - 1))) return rc;
+            if (k >= 2 && (rc = finish(k - 2))) return rc;
+        }
+    }
+    if (n >= 1) {
+        if ((rc = start_copy(n - 1))) return rc;
+        if (ring && n >= 2 && (rc = finish(n - 2))) return rc;
+        if ((rc = finish(n - 1))) return rc;
+    }
+    CU(cudaStreamSynchronize(ctx->st_copy));
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaGetLastError());
+    return MMK_OK;
 }
 
 extern "C" uint64_t mmk_launch_count(void) { return (uint64_t)launch_count(); }

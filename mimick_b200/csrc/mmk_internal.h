@@ -167,4 +167,34 @@ void kat_math(int kind, const double *d_in, double *d_out, int64_t n, cudaStream
 }  // namespace mmkdev
 #ifdef __cplusplus
 }
+
+// ------------------------------------------------------------------------------------------
+// BGZF stage (mmk_bgzf.cuh)
+// ------------------------------------------------------------------------------------------
+struct BgzfArgs {
+    const uint8_t *text;       // device text of the chunk (stream offset chunk_off sits at text[0])
+    const uint64_t *tile_off;  // shard-wide stream offset of every tile
+    uint64_t chunk_off;
+    uint32_t tile0, n_tiles;   // tiles of the chunk
+    uint32_t tiles_per_block;
+    uint32_t in_cap;           // staging capacity in bytes (multiple of 16, <= 65280)
+    uint32_t max_records;      // records per block the line table can hold
+    uint32_t crc_chunk;        // bytes per thread in the CRC pass (BZ_THREADS * crc_chunk >= in_cap)
+    uint32_t crc_shift[8];     // x^(8 * crc_chunk * 2^k) mod P
+    const uint32_t *tab;       // [286 + 30 + 256 + hdr words]: codes, CRC table, block prefix
+    uint32_t hdr_bits;
+    uint8_t *slots;            // slot area; block b writes at bz_slot_off(its text offset, b, slot_shift)
+    uint32_t slot_shift;       // 2^slot_shift <= in_cap / 32
+    uint32_t *sizes;           // coded size of every block
+};
+
+namespace mmkdev {
+constexpr uint32_t BGZF_TAB_CODES = 286 + 30 + 256;  // literal/length codes, distance codes, CRC-32 table; block prefix words follow
+size_t bgzf_smem_bytes(uint32_t in_cap, uint32_t max_records);
+uint32_t bgzf_threads();
+void bgzf_encode(const BgzfArgs &a, uint32_t n_blocks, cudaStream_t st);
+void bgzf_compact(const BgzfArgs &a, const uint64_t *offs, uint8_t *dst, uint32_t n_blocks, cudaStream_t st);
+uint64_t bgzf_slots_bytes(uint64_t text_bytes, uint32_t n_blocks, uint32_t slot_shift);  // capacity of the slot area = bound of the coded chunk
+}  // namespace mmkdev
+
 #endif

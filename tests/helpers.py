@@ -49,3 +49,30 @@ def assert_same_bytes(got: bytes, want: bytes, what: str):
         raise AssertionError(
             f"{what}: first difference at byte {d} (len got {len(got)}, want {len(want)})\n"
             f"--- got ---\n{got[lo:d + 120]!r}\n--- want ---\n{want[lo:d + 120]!r}")
+
+
+def bgzf_members(z: bytes):
+    """Walks a BGZF stream; yields (offset, member size, ISIZE, CRC32) and checks every fixed header field."""
+    import struct
+    pos = 0
+    while pos < len(z):
+        assert z[pos:pos + 4] == b"\x1f\x8b\x08\x04", f"gzip magic / FEXTRA at {pos}"
+        xlen = struct.unpack_from("<H", z, pos + 10)[0]
+        assert xlen == 6 and z[pos + 12:pos + 16] == b"BC\x02\x00", f"BC subfield at {pos}"
+        bsize = struct.unpack_from("<H", z, pos + 16)[0] + 1
+        crc, isize = struct.unpack_from("<II", z, pos + bsize - 8)
+        assert isize <= 65536
+        yield pos, bsize, isize, crc
+        pos += bsize
+    assert pos == len(z)
+
+
+def bgzf_inflate(z: bytes) -> bytes:
+    """Member by member with zlib (checks CRC-32 and ISIZE of every member)."""
+    import zlib
+    out = []
+    for off, size, isize, crc in bgzf_members(z):
+        raw = zlib.decompress(z[off + 18:off + size - 8], wbits=-15)
+        assert len(raw) == isize and zlib.crc32(raw) == crc, f"member at {off}: CRC/ISIZE mismatch"
+        out.append(raw)
+    return b"".join(out)

@@ -5,6 +5,7 @@ import ctypes as C
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -129,3 +130,56 @@ def test_exchange_counts_world_size_2_gloo():
         assert p.exitcode == 0
     for rank, o1, o2, pairs, firsts in res:
         assert o1 == [0, 1000] and o2 == [0, 2000] and pairs == 30 and firsts == [0, 10]
+
+
+def test_bgzf_code_table_is_a_valid_deflate_code():
+    """The fixed deflate code of the BGZF stage (host side only, no GPU): the block prefix the kernel copies and the
+    canonical codes it packs must form a stream zlib accepts — a block of literals, one run and one back-reference
+    coded by hand from mmk_bgzf_table() inflates to the text; the codes equal those the generator script derives
+    from the same code lengths; the end-of-file member is the 28-byte BGZF constant."""
+    import ctypes as C
+    import gzip
+    import zlib
+
+    import numpy as np
+
+    import mimick_b200 as M
+    from mimick_b200 import _lib
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import bgzf_table as T
+
+    L = _lib.load()
+    ll = np.zeros(286, dtype=np.uint32)
+    dd = np.zeros(30, dtype=np.uint32)
+    prefix = C.create_string_buffer(256)
+    nbits = C.c_uint32()
+    assert L.mmk_bgzf_table(ll.ctypes.data, dd.ctypes.data, prefix, 256, C.byref(nbits)) == 0
+
+    def rev(code, n):
+        return int(format(code, f"0{n}b")[::-1], 2) if n else 0
+    ll_len = [int(v) >> 16 for v in ll]
+    d_len = [int(v) >> 16 for v in dd]
+    assert max(ll_len) <= 12 and max(d_len) <= 12 and all(ll_len[b] for b in T.SUPPORTED) and all(ll_len[256:]) and all(d_len)
+    assert [int(v) & 0xffff for v in ll] == [rev(c, n) for c, n in T.canonical(ll_len, 286)]
+    assert [int(v) & 0xffff for v in dd] == [rev(c, n) for c, n in T.canonical(d_len, 30)]
+    hdr = T.dynamic_header(ll_len, d_len)
+    assert hdr.n == nbits.value and hdr.tobytes() == prefix.raw[:(hdr.n + 7) // 8]
+
+    text = b"@chr1:1|100:90000|5000:5499/1\tBX:Z:A01C01B01D01\nACGTTGCANNACGT\n+\nIIIIIIIIIIIIII\n" * 3
+    w = T.BitWriter()
+    w.bits(int.from_bytes(prefix.raw[:(hdr.n + 7) // 8], "little"), hdr.n)
+    for t in T.tokenize(text):
+        if t[0] == "lit":
+            w.bits(int(ll[t[1]]) & 0xffff, int(ll[t[1]]) >> 16)
+        else:
+            s, e, x = T.length_symbol(t[1])
+            w.bits(int(ll[s]) & 0xffff, int(ll[s]) >> 16)
+            w.bits(x, e)
+            s, e, x = T.dist_symbol(t[2])
+            w.bits(int(dd[s]) & 0xffff, int(dd[s]) >> 16)
+            w.bits(x, e)
+    w.bits(int(ll[256]) & 0xffff, int(ll[256]) >> 16)
+    assert zlib.decompress(w.tobytes(), wbits=-15) == text
+    assert any(t[0] == "match" and t[2] == 1 for t in T.tokenize(text)) and any(t[0] == "match" and t[2] > 1 for t in T.tokenize(text))
+    eof = M.bgzf_eof()
+    assert eof == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000") and gzip.decompress(eof) == b""

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 import oracle as O
-from helpers import assert_same_bytes, make_ci_haplotypes, random_bases, write_fasta
+from helpers import assert_same_bytes, bgzf_inflate, bgzf_members, make_ci_haplotypes, random_bases, write_fasta
 
 pytestmark = pytest.mark.gpu
 
@@ -28,6 +28,12 @@ def gpu_single(fastas, fmt, seed, mask=False, variates=True, **kw):
         r1, r2 = sim.emit_to_host()
         out = dict(r1=r1.tobytes(), r2=r2.tobytes(), mol=sim.molecules(), ins=sim.inserts(), plan=plan, place=place,
                    schemas=sim.schemas())
+        # the BGZF stage on the same shard: blocked gzip that inflates to exactly the text above
+        sim.rewind()
+        z1, z2 = sim.emit_bgzf_to_host()
+        out["z1"], out["z2"] = z1, z2
+        assert_same_bytes(bgzf_inflate(z1), out["r1"], f"{fmt} BGZF R1")
+        assert_same_bytes(bgzf_inflate(z2), out["r2"], f"{fmt} BGZF R2")
         if variates:
             out["var"] = np.concatenate([sim.mask_variates(), sim.variates()])
         return out
@@ -331,25 +337,78 @@ def test_error_sites(tmp_path):
 
 def test_mimick_function_writes_the_reference_file_layout(tmp_path, ref_fasta, ref_vcf):
     """The public function with the reference's two methods and keywords (Main.jl:24, :88): file naming
-    `<prefix>.R{1,2}.fq` and `<outdir>/<sample>.R{1,2}.fq`, contents identical to the oracle's."""
+    `<prefix>.R{1,2}.fq.gz` and `<outdir>/<sample>.R{1,2}.fq.gz` (BGZF, as the reference's writers), contents
+    identical to the oracle's after inflation; `compress=False` gives the plain text."""
+    import gzip
+
     import mimick_b200 as M
     fastas = make_ci_haplotypes(tmp_path, seed=41, big=30000)
     prefix = os.path.join(str(tmp_path), "single", "SIM")
-    out = M.mimick(fastas, "stlfr", prefix=prefix, coverage=6, seed=5, mask=True, **CLI)
+    out = M.mimick(fastas, "stlfr", prefix=prefix, coverage=6, seed=5, mask=True, compress=False, **CLI)
     orc = O.mimick_single(fastas, "stlfr", seed=5, mask=True, coverage=6, **CLI)
     assert open(prefix + ".R1.fq", "rb").read() == orc.r1 and open(prefix + ".R2.fq", "rb").read() == orc.r2
     assert out[0].n_pairs == len(orc.insert_start)
+    out = M.mimick(fastas, "stlfr", prefix=prefix, coverage=6, seed=5, mask=True, **CLI)
+    assert out[0].r1_path == prefix + ".R1.fq.gz"
+    z = open(prefix + ".R1.fq.gz", "rb").read()
+    assert z.endswith(M.bgzf_eof()) and gzip.decompress(z) == orc.r1
+    assert gzip.decompress(open(prefix + ".R2.fq.gz", "rb").read()) == orc.r2
     # two "GPUs" on one device: the parts concatenate to the same files
     for rank in range(2):
         M.mimick(fastas, "stlfr", prefix=prefix + "_sh", coverage=6, seed=5, mask=True, rank=rank, world=2, **CLI)
-    cat1 = b"".join(open(f"{prefix}_sh.R1.fq.part{r}", "rb").read() for r in range(2))
-    assert cat1 == orc.r1
+    cat1 = b"".join(open(f"{prefix}_sh.R1.fq.gz.part{r}", "rb").read() for r in range(2))
+    assert cat1.endswith(M.bgzf_eof()) and cat1.count(M.bgzf_eof()) == 1 and gzip.decompress(cat1) == orc.r1
     outdir = os.path.join(str(tmp_path), "multi")
     outs = M.mimick(ref_fasta, ref_vcf, "standard:haplotagging", outdir=outdir, coverage=0.5, seed=9, rank=1, world=4, **CLI)
     assert [o.name for o in outs] == ["tsk_1", "tsk_5"]   # samples round-robin over ranks
     want = O.mimick_multi(ref_fasta, ref_vcf, "standard:haplotagging", seed=9, coverage=0.5, samples=["tsk_1", "tsk_5"], **CLI)
     for o in outs:
-        assert open(o.r1_path, "rb").read() == want[o.name].r1 and open(o.r2_path, "rb").read() == want[o.name].r2
-        assert os.path.basename(o.r1_path) == o.name + ".R1.fq"
+        assert gzip.decompress(open(o.r1_path, "rb").read()) == want[o.name].r1
+        assert gzip.decompress(open(o.r2_path, "rb").read()) == want[o.name].r2
+        assert os.path.basename(o.r1_path) == o.name + ".R1.fq.gz"
     with pytest.raises(TypeError):
         M.mimick(fastas, "stlfr", gzip=True)
+
+
+def test_bgzf_members_and_ratio(tmp_path):
+    """Structure of the coded stream (SAM spec 4.1: gzip member with the BC extra field, BSIZE, CRC-32, ISIZE), several
+    chunks through the ring, and the coding gain on the headline format: every member inflates on its own, sizes add
+    up, and haplotagging text shrinks at least 4.5x (A/C/G/T at 2-3 bits, headers and quality lines as matches)."""
+    import zlib
+
+    import mimick_b200 as M
+    rng = np.random.default_rng(77)
+    p = os.path.join(str(tmp_path), "a.fa")
+    write_fasta(p, [("chr1", random_bases(rng, 3_000_000))])
+    with M.Simulator("haplotagging", seed=3, coverage=2.0, max_chunk_bytes=3 << 20, **CLI) as sim:
+        sim.load_fasta(p)
+        sim.plan()
+        place = sim.place()
+        assert sim.chunk_layout()[1] >= 3
+        r1, r2 = (x.tobytes() for x in sim.emit_to_host())
+        sim.rewind()
+        z1, z2 = sim.emit_bgzf_to_host()
+        # chunk-at-a-time entry point gives the same coded bytes
+        sim.rewind()
+        parts = []
+        while True:
+            ch = sim.emit_chunk_bgzf()
+            if ch.n_pairs == 0 and ch.done:
+                break
+            a, b = sim.copy_chunk(ch)
+            parts.append((a.tobytes(), b.tobytes(), ch.r1_offset))
+            if ch.done:
+                break
+        assert b"".join(x[0] for x in parts) == z1 and b"".join(x[1] for x in parts) == z2
+        assert [x[2] for x in parts] == list(np.cumsum([0] + [len(x[0]) for x in parts[:-1]]))
+    for z, raw in ((z1, r1), (z2, r2)):
+        pos = 0
+        for off, size, isize, crc in bgzf_members(z):
+            payload = zlib.decompress(z[off + 18:off + size - 8], wbits=-15)
+            assert len(payload) == isize and zlib.crc32(payload) == crc
+            assert payload == raw[pos:pos + isize]
+            assert payload.count(b"\n") == 4 * 32 or pos + isize == len(raw)   # one tile of 32 records per member
+            pos += isize
+        assert pos == len(raw)
+        assert len(raw) / len(z) > 4.5, len(raw) / len(z)
+    assert place.r1_bytes == len(r1)
