@@ -977,11 +977,11 @@ void emit(const EmitArgs &a, cudaStream_t st) {
 // BGZF stage
 // ------------------------------------------------------------------------------------------
 #include "mmk_bgzf.cuh"
-uint32_t bgzf_threads() { return BZ_THREADS; }
-size_t bgzf_smem_bytes(uint32_t in_cap, uint32_t max_records) {
-    size_t off = (size_t)BGZF_TAB_CODES * 4 + (4 * (size_t)max_records + 4) * 4 + ((size_t)max_records + 4) * 4;
-    off = (off + 15) & ~(size_t)15;
-    return off + ((size_t)in_cap + 64) + (size_t)in_cap + 32;
+void bgzf_geometry(BgzfArgs &a) {
+    a.out_cap = (a.in_cap / 2 + 64 + 15) & ~15u;
+    a.crc_words = (a.in_cap / 4 + 2 + 31) / 32;
+    size_t w = ((size_t)a.in_cap + 32) + a.out_cap + (4 * (size_t)a.max_records + 4) * 4 + 2 * ((size_t)a.max_records + 4) * 4;
+    a.warp_smem = (uint32_t)((w + 15) & ~(size_t)15);
 }
 void bgzf_encode(const BgzfArgs &a, uint32_t n_blocks, cudaStream_t st) {
     if (!n_blocks) return;
@@ -989,14 +989,15 @@ void bgzf_encode(const BgzfArgs &a, uint32_t n_blocks, cudaStream_t st) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
-        cudaFuncSetAttribute(k_bgzf, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(k_bgzf, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_set[dev & 63] = true;
     }
-    LAUNCH(k_bgzf, n_blocks, BZ_THREADS, bgzf_smem_bytes(a.in_cap, a.max_records), st, a);
+    const size_t smem = ((BZ_T_SHIFT * 4 + 15) & ~(size_t)15) + (size_t)BZ_WARPS * a.warp_smem;
+    LAUNCH(k_bgzf, (n_blocks + BZ_WARPS - 1) / BZ_WARPS, BZ_THREADS, smem, st, a, n_blocks);
 }
 void bgzf_compact(const BgzfArgs &a, const uint64_t *offs, uint8_t *dst, uint32_t n_blocks, cudaStream_t st) {
     if (!n_blocks) return;
-    LAUNCH(k_bgzf_compact, n_blocks, 256, 0, st, a, offs, dst);
+    LAUNCH(k_bgzf_compact, (n_blocks + 7) / 8, 256, 0, st, a, n_blocks, offs, dst);
 }
 uint64_t bgzf_slots_bytes(uint64_t text_bytes, uint32_t n_blocks, uint32_t slot_shift) {
     return text_bytes + (text_bytes >> slot_shift) + 64ull * n_blocks + 512;

@@ -151,7 +151,7 @@ struct mmk_ctx {
     uint32_t tile_bytes_bound = 0;   // upper bound of one tile's text in one stream
     DBuf<uint32_t> d_bz_tab;         // codes, CRC table, block prefix
     uint32_t bz_hdr_bits = 0;
-    uint32_t bz_tiles_per_block = 1, bz_in_cap = 0, bz_max_blocks = 0, bz_slot_shift = 1;
+    uint32_t bz_tiles_per_block = 1, bz_in_cap = 0, bz_max_blocks = 0, bz_slot_shift = 1, bz_crc_words = 1;
     uint64_t bz_out_cap = 0;
     DBuf<uint8_t> d_bz_slots;
     DBuf<uint32_t> d_bz_sizes;
@@ -1545,14 +1545,29 @@ static uint32_t gf_mul(uint32_t a, uint32_t b) {
     }
     return p;
 }
-static std::vector<uint32_t> bgzf_table_words() {
+// crc_words: 32-bit words per thread of the kernel's CRC pass (0: leave the per-thread shifts out)
+static std::vector<uint32_t> bgzf_table_words(uint32_t crc_words) {
     std::vector<uint32_t> t(BGZF_TAB_CODES + (MMK_BGZF_HDR_BITS + 31) / 32, 0u);
     canonical_codes(MMK_BGZF_LL_LEN, 286, t.data());
     canonical_codes(MMK_BGZF_D_LEN, 30, t.data() + 286);
+    uint32_t *crc = t.data() + 286 + 30;  // slicing-by-4: table k = CRC of a byte followed by k zero bytes
     for (uint32_t i = 0; i < 256; ++i) {
         uint32_t c = i;
         for (int k = 0; k < 8; ++k) c = (c >> 1) ^ ((c & 1u) ? 0xEDB88320u : 0u);
-        t[286 + 30 + i] = c;
+        crc[i] = c;
+    }
+    for (int k = 1; k < 4; ++k)
+        for (uint32_t i = 0; i < 256; ++i) crc[k * 256 + i] = (crc[(k - 1) * 256 + i] >> 8) ^ crc[crc[(k - 1) * 256 + i] & 0xffu];
+    if (crc_words) {  // lane t of T: x^(32 * crc_words * (T - 1 - t)) mod P
+        const uint32_t T = 32;
+        uint32_t step = 0x80000000u;  // x^0
+        for (uint32_t i = 0; i < 32 * crc_words; ++i) step = (step >> 1) ^ ((step & 1u) ? 0xEDB88320u : 0u);
+        uint32_t v = 0x80000000u;
+        uint32_t *shift = crc + 1024;
+        for (uint32_t k = 0; k < T; ++k) {
+            shift[T - 1 - k] = v;
+            v = gf_mul(v, step);
+        }
     }
     for (size_t i = 0; i < sizeof MMK_BGZF_HDR; ++i) t[BGZF_TAB_CODES + i / 4] |= (uint32_t)MMK_BGZF_HDR[i] << (8 * (i % 4));
     return t;
@@ -1560,7 +1575,7 @@ static std::vector<uint32_t> bgzf_table_words() {
 
 extern "C" int32_t mmk_bgzf_table(uint32_t *litlen_codes, uint32_t *dist_codes, uint8_t *prefix, uint32_t prefix_cap,
                                   uint32_t *prefix_bits) {
-    std::vector<uint32_t> t = bgzf_table_words();
+    std::vector<uint32_t> t = bgzf_table_words(0);
     if (litlen_codes) memcpy(litlen_codes, t.data(), 286 * 4);
     if (dist_codes) memcpy(dist_codes, t.data() + 286, 30 * 4);
     if (prefix) {
@@ -1581,21 +1596,28 @@ extern "C" int32_t mmk_bgzf_eof(void *out, uint32_t cap) {
 // geometry and buffers of the BGZF stage for the placed shard
 static int32_t bgzf_prepare(mmk_ctx *ctx) {
     if (ctx->bz_ready) return MMK_OK;
-    if (ctx->d_bz_tab.cap == 0) {
-        std::vector<uint32_t> t = bgzf_table_words();
-        CU(ctx->d_bz_tab.ensure(t.size()));
-        CU(cudaMemcpyAsync(ctx->d_bz_tab.p, t.data(), t.size() * 4, cudaMemcpyHostToDevice, ctx->st));
-        CU(cudaStreamSynchronize(ctx->st));
-        ctx->bz_hdr_bits = MMK_BGZF_HDR_BITS;
-    }
     if (!ctx->h_bz_tot) CU(cudaMallocHost((void **)&ctx->h_bz_tot, 4 * sizeof(uint64_t)));
     const uint32_t bound = std::max(ctx->tile_bytes_bound, 64u);
     if (bound > 65280u) return fail(ctx, MMK_ERR_UNSUPPORTED, "one tile of records exceeds a BGZF block");
     uint32_t G = 1;
     if (const char *e = getenv("MMK_BGZF_TILES")) G = (uint32_t)std::max(1, atoi(e));
     G = std::min(G, 65280u / bound);
+    G = std::max(1u, std::min(G, 64u / ctx->tile_pairs));  // a lane codes at most two records
     ctx->bz_tiles_per_block = G;
     ctx->bz_in_cap = (G * bound + 15) & ~15u;
+    {
+        BgzfArgs g;
+        memset(&g, 0, sizeof g);
+        g.in_cap = ctx->bz_in_cap;
+        g.max_records = G * ctx->tile_pairs;
+        bgzf_geometry(g);
+        ctx->bz_crc_words = g.crc_words;
+        std::vector<uint32_t> t = bgzf_table_words(ctx->bz_crc_words);
+        CU(ctx->d_bz_tab.ensure(t.size()));
+        CU(cudaMemcpyAsync(ctx->d_bz_tab.p, t.data(), t.size() * 4, cudaMemcpyHostToDevice, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        ctx->bz_hdr_bits = MMK_BGZF_HDR_BITS;
+    }
     uint32_t max_tiles = 0;
     for (size_t k = 0; k + 1 < ctx->chunk_tiles.size(); ++k) max_tiles = std::max(max_tiles, ctx->chunk_tiles[k + 1] - ctx->chunk_tiles[k]);
     ctx->bz_max_blocks = (max_tiles + G - 1) / G;
@@ -1625,15 +1647,7 @@ static int32_t bgzf_launch(mmk_ctx *ctx, uint32_t k, int slot) {
     a.tiles_per_block = G;
     a.in_cap = ctx->bz_in_cap;
     a.max_records = G * ctx->tile_pairs;
-    a.crc_chunk = (ctx->bz_in_cap + bgzf_threads() - 1) / bgzf_threads();
-    {
-        uint32_t v = 0x80000000u;  // x^0
-        for (uint32_t i = 0; i < 8 * a.crc_chunk; ++i) v = (v >> 1) ^ ((v & 1u) ? 0xEDB88320u : 0u);
-        for (int j = 0; j < 8; ++j) {
-            a.crc_shift[j] = v;
-            v = gf_mul(v, v);
-        }
-    }
+    bgzf_geometry(a);
     a.tab = ctx->d_bz_tab.p;
     a.hdr_bits = ctx->bz_hdr_bits;
     a.slots = ctx->d_bz_slots.p;

@@ -179,9 +179,10 @@ struct BgzfArgs {
     uint32_t tiles_per_block;
     uint32_t in_cap;           // staging capacity in bytes (multiple of 16, <= 65280)
     uint32_t max_records;      // records per block the line table can hold
-    uint32_t crc_chunk;        // bytes per thread in the CRC pass (BZ_THREADS * crc_chunk >= in_cap)
-    uint32_t crc_shift[8];     // x^(8 * crc_chunk * 2^k) mod P
-    const uint32_t *tab;       // [286 + 30 + 256 + hdr words]: codes, CRC table, block prefix
+    uint32_t out_cap;          // bytes of the coded-member buffer (multiple of 16); larger members are stored
+    uint32_t warp_smem;        // shared-memory bytes of one warp's region (multiple of 16)
+    uint32_t crc_words;        // 32-bit words per lane in the CRC pass (32 * crc_words * 4 >= in_cap + 4)
+    const uint32_t *tab;       // codes, CRC-32 slicing tables, per-lane CRC shifts x^(32 * crc_words * (31 - lane)), block prefix
     uint32_t hdr_bits;
     uint8_t *slots;            // slot area; block b writes at bz_slot_off(its text offset, b, slot_shift)
     uint32_t slot_shift;       // 2^slot_shift <= in_cap / 32
@@ -189,9 +190,8 @@ struct BgzfArgs {
 };
 
 namespace mmkdev {
-constexpr uint32_t BGZF_TAB_CODES = 286 + 30 + 256;  // literal/length codes, distance codes, CRC-32 table; block prefix words follow
-size_t bgzf_smem_bytes(uint32_t in_cap, uint32_t max_records);
-uint32_t bgzf_threads();
+constexpr uint32_t BGZF_TAB_CODES = 286 + 30 + 4 * 256 + 32;  // words before the block prefix in BgzfArgs::tab
+void bgzf_geometry(BgzfArgs &a);  // fills out_cap, warp_smem, crc_words from in_cap and max_records
 void bgzf_encode(const BgzfArgs &a, uint32_t n_blocks, cudaStream_t st);
 void bgzf_compact(const BgzfArgs &a, const uint64_t *offs, uint8_t *dst, uint32_t n_blocks, cudaStream_t st);
 uint64_t bgzf_slots_bytes(uint64_t text_bytes, uint32_t n_blocks, uint32_t slot_shift);  // capacity of the slot area = bound of the coded chunk
