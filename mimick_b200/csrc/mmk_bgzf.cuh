@@ -25,7 +25,7 @@
 #pragma once
 #include "mmk_internal.h"
 
-constexpr uint32_t BZ_WARPS = 5;            // blocks per CTA
+constexpr uint32_t BZ_WARPS = 6;            // blocks per CTA
 constexpr uint32_t BZ_THREADS = BZ_WARPS * 32;
 constexpr uint32_t BZ_GZ_HDR = 18;
 constexpr uint32_t BZ_MIN_MATCH = 4, BZ_MAX_MATCH = 258;
@@ -74,31 +74,42 @@ __device__ __forceinline__ void bz_or_bits(uint32_t *buf, uint32_t pos, uint64_t
 
 // Lane-private bit writer into whole words [w, end)
 struct BzWriter {
-    uint32_t *w, *end;
-    uint64_t acc;
-    uint32_t nb, bits;
+    uint32_t *w, *w0, *end;
+    uint32_t acc, nb;
     bool bad;
-    __device__ __forceinline__ void put(uint32_t v, uint32_t n) {  // n <= 32
-        acc |= (uint64_t)v << nb;
+    __device__ __forceinline__ void init(uint32_t *begin, uint32_t *stop) { w = w0 = begin, end = stop, acc = 0, nb = 0, bad = false; }
+    __device__ __forceinline__ void put(uint32_t v, uint32_t n) {  // n <= 32 bits of v, nb < 32
+        acc |= v << nb;
+        const uint32_t room = 32 - nb;  // 1..32 bits went into the current word
         nb += n;
-        bits += n;
         if (nb >= 32) {
-            if (w < end) *w++ = (uint32_t)acc;
+            if (w < end) *w = acc;
             else bad = true;
-            acc >>= 32;
+            ++w;
             nb -= 32;
+            acc = __funnelshift_rc(v, 0u, room);  // the rest of v (0 when room == 32)
         }
     }
-    __device__ __forceinline__ void flush() {
+    __device__ __forceinline__ uint32_t finish() {  // returns the bits written
+        const uint32_t bits = (uint32_t)(w - w0) * 32 + nb;
         if (nb) {
-            if (w < end) *w++ = (uint32_t)acc;
+            if (w < end) *w = acc;
             else bad = true;
         }
+        return bits;
     }
 };
 
 __device__ __forceinline__ void bz_put_literals(const BzSmem &S, BzWriter &bw, uint32_t a, uint32_t b) {
-    for (uint32_t j = a; j < b; ++j) {
+    uint32_t j = a;
+#pragma unroll 4
+    for (; j + 2 <= b; j += 2) {  // two literals (<= 24 bits) per put
+        const uint32_t e0 = S.ll[S.in[j]], e1 = S.ll[S.in[j + 1]];
+        const uint32_t l0 = e0 >> 16, l1 = e1 >> 16;
+        if (!l0 || !l1) bw.bad = true;
+        bw.put((e0 & 0xffffu) | ((e1 & 0xffffu) << l0), l0 + l1);
+    }
+    if (j < b) {
         const uint32_t e = S.ll[S.in[j]];
         if (!(e >> 16)) bw.bad = true;
         bw.put(e & 0xffffu, e >> 16);
@@ -197,39 +208,56 @@ __device__ __forceinline__ uint32_t bz_member(const BgzfArgs &a, BzSmem S, const
     __syncwarp();
     const uint8_t *in = S.in;
 
-    // pass 1, word-wise: CRC of the lane's chunk and its newline count.  The message is taken from the word holding
-    // its first byte (`pad` bytes before it read as zero, which leaves a zero CRC state unchanged) and chunks are
-    // aligned to the END of the whole words, so the per-lane shift constants do not depend on n.
+    // pass 1, word-wise: CRC of the lane's chunk, its newline count and the newline positions (a queue of up to
+    // eight 16-bit offsets in registers).  The message is taken from the word holding its first byte — the `pad` bytes
+    // before it are zeroed, which leaves a zero CRC state unchanged — and chunks are aligned to the END of the whole
+    // words, so the per-lane shift constants do not depend on n.  The 0xFFFFFFFF preset is folded into the first four
+    // message bytes (complemented in place for the duration of the pass).
     const uint32_t pad = phase & 3, nv = n + pad;
-    const uint32_t *W = S.in_w + (phase >> 2);
+    uint32_t *W = S.in_w + (phase >> 2);
+    if (lane == 0) {
+        for (uint32_t k = 0; k < pad; ++k) ((uint8_t *)W)[k] = 0;
+        if (n >= 4)
+            for (uint32_t k = 0; k < 4; ++k) S.in[k] ^= 0xffu;
+    }
+    __syncwarp();
     const int wf = (int)(nv >> 2);  // whole words
     const int CW = (int)a.crc_words;
     const int w_lo = wf - (int)(32 - lane) * CW, w_hi = w_lo + CW;
     uint32_t crc = 0, nl = 0;
+    unsigned long long q_lo = 0, q_hi = 0;
+    auto push = [&](uint32_t pos) {
+        q_hi = (q_hi << 16) | (q_lo >> 48);
+        q_lo = (q_lo << 16) | pos;
+        ++nl;
+    };
+#pragma unroll 2
     for (int w = max(w_lo, 0); w < w_hi; ++w) {
-        uint32_t x = W[w];
-        if (w == 0) x &= 0xffffffffu << (8 * pad);
-        nl += __popc(__vcmpeq4(x, 0x0a0a0a0au)) >> 3;
-        if (w == 0) x ^= 0xffffffffu << (8 * pad);  // the 0xFFFFFFFF preset folded into the first four message bytes
-        if (w == 1 && pad) x ^= 0xffffffffu >> (8 * (4 - pad));
+        const uint32_t x = W[w];
+        uint32_t m = __vcmpeq4(x, 0x0a0a0a0au);
+        while (m) {  // about one word in twenty
+            const uint32_t b = (__ffs(m) - 1) >> 3;
+            push((uint32_t)w * 4 + b + 1 - pad);
+            m &= ~(0xffu << (8 * b));
+        }
         crc = bz_crc_word(S.crc_t, crc ^ x);
     }
     const uint32_t tail0 = (uint32_t)wf * 4;  // trailing bytes (virtual offsets) belong to the last lane
     if (lane == 31)
-        for (uint32_t v = tail0; v < nv; ++v) nl += in[v - pad] == 10;
+        for (uint32_t v = tail0; v < nv; ++v)
+            if (in[v - pad] == 10) push(v + 1 - pad);
     crc = bz_gf_mul(crc, a.tab[BZ_T_SHIFT + lane]);  // moved to the end of the whole words ...
     crc = __reduce_xor_sync(FULL, crc);              // ... and folded
     if (n >= 4) {
-        for (uint32_t v = tail0; v < nv; ++v) {
-            uint32_t b = in[v - pad];
-            if (v - pad < 4) b ^= 0xffu;
-            crc = S.crc_t[(crc ^ b) & 0xffu] ^ (crc >> 8);
-        }
+        for (uint32_t v = tail0; v < nv; ++v) crc = S.crc_t[(crc ^ in[v - pad]) & 0xffu] ^ (crc >> 8);
     } else {  // too short for the folded preset (last piece of an oversized block): plain bytewise CRC
         crc = 0xffffffffu;
         for (uint32_t i = 0; i < n; ++i) crc = S.crc_t[(crc ^ in[i]) & 0xffu] ^ (crc >> 8);
     }
     crc = ~crc;
+    __syncwarp();
+    if (lane == 0 && n >= 4)
+        for (uint32_t k = 0; k < 4; ++k) S.in[k] ^= 0xffu;
 
     // newline ranks -> line starts
     uint32_t inc = nl;
@@ -245,19 +273,25 @@ __device__ __forceinline__ uint32_t bz_member(const BgzfArgs &a, BzSmem S, const
     if (ok) {
         uint32_t before = inc - nl;
         if (lane == 0) S.ls[0] = 0;
-        for (int w = max(w_lo, 0); w < w_hi; ++w) {
-            uint32_t x = W[w];
-            if (w == 0) x &= 0xffffffffu << (8 * pad);
-            uint32_t m = __vcmpeq4(x, 0x0a0a0a0au);
-            while (m) {
-                const uint32_t b = (__ffs(m) - 1) >> 3;
-                S.ls[++before] = (uint32_t)w * 4 + b + 1 - pad;
-                m &= ~(0xffu << (8 * b));
+        if (!__any_sync(FULL, nl > 8)) {
+            for (uint32_t i = 0; i < nl; ++i) {  // oldest first
+                const uint32_t slot = nl - 1 - i;
+                const unsigned long long q = slot < 4 ? q_lo : q_hi;
+                S.ls[++before] = (uint32_t)(q >> (16 * (slot & 3))) & 0xffffu;
             }
+        } else {  // a lane met more newlines than its queue holds (very short lines): scan again
+            for (int w = max(w_lo, 0); w < w_hi; ++w) {
+                uint32_t m = __vcmpeq4(W[w], 0x0a0a0a0au);
+                while (m) {
+                    const uint32_t b = (__ffs(m) - 1) >> 3;
+                    S.ls[++before] = (uint32_t)w * 4 + b + 1 - pad;
+                    m &= ~(0xffu << (8 * b));
+                }
+            }
+            if (lane == 31)
+                for (uint32_t v = tail0; v < nv; ++v)
+                    if (in[v - pad] == 10) S.ls[++before] = v + 1 - pad;
         }
-        if (lane == 31)
-            for (uint32_t v = tail0; v < nv; ++v)
-                if (in[v - pad] == 10) S.ls[++before] = v + 1 - pad;
         __syncwarp();
 
         // pass 2a: quality class of every record
@@ -303,9 +337,7 @@ __device__ __forceinline__ uint32_t bz_member(const BgzfArgs &a, BzSmem S, const
             const uint32_t choice = S.rec2[r];
             const uint32_t P = choice & 0x1ffu, Sx = (choice >> 9) & 0x1ffu, same = (choice >> 18) & 1u, qchar = (choice >> 19) & 0xffu;
             BzWriter bw;
-            bw.w = S.in_w + ((phase + q0 + 3) >> 2);
-            bw.end = S.in_w + ((phase + e0 - 1) >> 2);
-            bw.acc = 0, bw.nb = 0, bw.bits = 0, bw.bad = false;
+            bw.init(S.in_w + ((phase + q0 + 3) >> 2), S.in_w + ((phase + e0 - 1) >> 2));
             if (P) bz_put_match(S, bw, P, h0 - S.ls[4 * r - 4]);
             bz_put_literals(S, bw, h0 + P, s0 - Sx);
             if (Sx) bz_put_match(S, bw, Sx, s0 - S.ls[4 * r - 3]);
@@ -320,9 +352,8 @@ __device__ __forceinline__ uint32_t bz_member(const BgzfArgs &a, BzSmem S, const
                 bz_put_long_match(S, bw, e0 - 1 - q0 - 1, 1);
                 bw.put(en & 0xffffu, en >> 16);
             }
-            bw.flush();
+            S.rec[r] = bw.finish();
             bad |= bw.bad;
-            S.rec[r] = bw.bits;
         }
         ok = !__any_sync(FULL, bad);
     }

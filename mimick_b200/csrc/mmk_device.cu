@@ -978,7 +978,7 @@ void emit(const EmitArgs &a, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------
 #include "mmk_bgzf.cuh"
 void bgzf_geometry(BgzfArgs &a) {
-    a.out_cap = (a.in_cap / 2 + 64 + 15) & ~15u;
+    a.out_cap = (a.in_cap / 3 + 64 + 15) & ~15u;  // members that do not shrink 3x are stored
     a.crc_words = (a.in_cap / 4 + 2 + 31) / 32;
     size_t w = ((size_t)a.in_cap + 32) + a.out_cap + (4 * (size_t)a.max_records + 4) * 4 + 2 * ((size_t)a.max_records + 4) * 4;
     a.warp_smem = (uint32_t)((w + 15) & ~(size_t)15);
