@@ -460,9 +460,15 @@ __global__ void __launch_bounds__(BZ_THREADS) k_bgzf(BgzfArgs a, uint32_t n_bloc
 }
 
 // Packs the coded blocks back to back: block b goes to dst[offs[b] ...).  One warp per block.
+// *total (pinned host memory, written over the bus: a copy-engine transfer would queue behind the bulk copy of the
+// previous chunk) receives the size of the packed chunk.
 __global__ void __launch_bounds__(256) k_bgzf_compact(BgzfArgs a, uint32_t n_blocks, const uint64_t *__restrict__ offs,
-                                                      uint8_t *__restrict__ dst) {
+                                                      uint8_t *__restrict__ dst, unsigned long long *total) {
     const uint32_t b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *total = offs[n_blocks];
+        __threadfence_system();
+    }
     if (b >= n_blocks) return;
     const uint32_t tb = a.tile0 + b * a.tiles_per_block;
     const uint8_t *src = a.slots + bz_slot_off(a.tile_off[tb] - a.chunk_off, b, a.slot_shift);

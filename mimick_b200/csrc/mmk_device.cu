@@ -995,9 +995,10 @@ void bgzf_encode(const BgzfArgs &a, uint32_t n_blocks, cudaStream_t st) {
     const size_t smem = ((BZ_T_SHIFT * 4 + 15) & ~(size_t)15) + (size_t)BZ_WARPS * a.warp_smem;
     LAUNCH(k_bgzf, (n_blocks + BZ_WARPS - 1) / BZ_WARPS, BZ_THREADS, smem, st, a, n_blocks);
 }
-void bgzf_compact(const BgzfArgs &a, const uint64_t *offs, uint8_t *dst, uint32_t n_blocks, cudaStream_t st) {
+void bgzf_compact(const BgzfArgs &a, const uint64_t *offs, uint8_t *dst, uint32_t n_blocks, unsigned long long *host_total,
+                  cudaStream_t st) {
     if (!n_blocks) return;
-    LAUNCH(k_bgzf_compact, (n_blocks + 7) / 8, 256, 0, st, a, n_blocks, offs, dst);
+    LAUNCH(k_bgzf_compact, (n_blocks + 7) / 8, 256, 0, st, a, n_blocks, offs, dst, host_total);
 }
 uint64_t bgzf_slots_bytes(uint64_t text_bytes, uint32_t n_blocks, uint32_t slot_shift) {
     return text_bytes + (text_bytes >> slot_shift) + 64ull * n_blocks + 512;

@@ -1659,8 +1659,8 @@ static int32_t bgzf_launch(mmk_ctx *ctx, uint32_t k, int slot) {
         a.chunk_off = r ? ctx->chunk_off2[k] : ctx->chunk_off1[k];
         bgzf_encode(a, nblk, ctx->st);
         exclusive_scan_u32(ctx->d_bz_sizes.p, ctx->d_bz_offs.p, nblk, ctx->d_scan_tmp.p, ctx->st);
-        bgzf_compact(a, ctx->d_bz_offs.p, ctx->bz_out[slot][r].p, nblk, ctx->st);
-        CU(cudaMemcpyAsync(&ctx->h_bz_tot[slot * 2 + r], ctx->d_bz_offs.p + nblk, 8, cudaMemcpyDeviceToHost, ctx->st));
+        ctx->h_bz_tot[slot * 2 + r] = 0;
+        bgzf_compact(a, ctx->d_bz_offs.p, ctx->bz_out[slot][r].p, nblk, (unsigned long long *)&ctx->h_bz_tot[slot * 2 + r], ctx->st);
     }
     return MMK_OK;
 }

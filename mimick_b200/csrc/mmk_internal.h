@@ -193,7 +193,8 @@ namespace mmkdev {
 constexpr uint32_t BGZF_TAB_CODES = 286 + 30 + 4 * 256 + 32;  // words before the block prefix in BgzfArgs::tab
 void bgzf_geometry(BgzfArgs &a);  // fills out_cap, warp_smem, crc_words from in_cap and max_records
 void bgzf_encode(const BgzfArgs &a, uint32_t n_blocks, cudaStream_t st);
-void bgzf_compact(const BgzfArgs &a, const uint64_t *offs, uint8_t *dst, uint32_t n_blocks, cudaStream_t st);
+void bgzf_compact(const BgzfArgs &a, const uint64_t *offs, uint8_t *dst, uint32_t n_blocks, unsigned long long *host_total,
+                  cudaStream_t st);  // host_total: pinned host memory
 uint64_t bgzf_slots_bytes(uint64_t text_bytes, uint32_t n_blocks, uint32_t slot_shift);  // capacity of the slot area = bound of the coded chunk
 }  // namespace mmkdev
 
