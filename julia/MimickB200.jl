@@ -80,8 +80,9 @@ function create(format::String; device=0, coverage=30, n_molecules=2, mol_covera
     return ctx[]
 end
 
-# plan → place → stream every chunk to the two files
-function simulate_to(ctx, r1_path::String, r2_path::String)
+# plan → place → stream every chunk to the two files.  `bgzf` (default, as the reference's BGZFCompressorStream
+# writers, src/Main.jl:42-43): chunks are whole BGZF members coded on the device; the end-of-file member closes each file.
+function simulate_to(ctx, r1_path::String, r2_path::String; bgzf::Bool=true)
     plan = Ref{PlanInfo}(); place = Ref{PlaceInfo}()
     check(ctx, ccall((:mmk_plan, LIB), Int32, (Ptr{Cvoid}, Ref{PlanInfo}), ctx, plan))
     check(ctx, ccall((:mmk_place, LIB), Int32, (Ptr{Cvoid}, Ref{PlaceInfo}), ctx, place))
@@ -89,7 +90,11 @@ function simulate_to(ctx, r1_path::String, r2_path::String)
         open(r2_path, "w") do f2
             while true
                 ch = Ref{Chunk}()
-                check(ctx, ccall((:mmk_emit_chunk, LIB), Int32, (Ptr{Cvoid}, Ref{Chunk}), ctx, ch))
+                if bgzf
+                    check(ctx, ccall((:mmk_emit_chunk_bgzf, LIB), Int32, (Ptr{Cvoid}, Ref{Chunk}), ctx, ch))
+                else
+                    check(ctx, ccall((:mmk_emit_chunk, LIB), Int32, (Ptr{Cvoid}, Ref{Chunk}), ctx, ch))
+                end
                 c = ch[]
                 if c.n_pairs > 0
                     b1 = Vector{UInt8}(undef, c.r1_bytes); b2 = Vector{UInt8}(undef, c.r2_bytes)
@@ -97,6 +102,11 @@ function simulate_to(ctx, r1_path::String, r2_path::String)
                     write(f1, b1); write(f2, b2)
                 end
                 c.done != 0 && break
+            end
+            if bgzf
+                eof = Vector{UInt8}(undef, 28)
+                ccall((:mmk_bgzf_eof, LIB), Int32, (Ptr{UInt8}, UInt32), eof, 28)
+                write(f1, eof); write(f2, eof)
             end
         end
     end
@@ -113,7 +123,7 @@ function mimick(fasta::Vector{String}, format::String; prefix::String="simulated
             check(ctx, ccall((:mmk_load_fasta, LIB), Int32, (Ptr{Cvoid}, Cstring, Int32), ctx, f, i))
         end
         mkpath(dirname(prefix))
-        simulate_to(ctx, "$prefix.R1.fq", "$prefix.R2.fq")
+        simulate_to(ctx, "$prefix.R1.fq.gz", "$prefix.R2.fq.gz")
     finally
         ccall((:mmk_destroy, LIB), Cvoid, (Ptr{Cvoid},), ctx)
     end
@@ -137,7 +147,7 @@ function mimick(fasta::String, vcf::String, format::String; outdir::String="simu
         for s in 0:(n - 1)      # the reference threads over samples; one context per GPU can split this range
             name = unsafe_string(ccall((:mmk_vcf_sample_name, LIB), Cstring, (Ptr{Cvoid}, Int32), v[], s))
             check(ctx, ccall((:mmk_apply_vcf_sample, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32), ctx, v[], s))
-            simulate_to(ctx, joinpath(outdir, "$name.R1.fq"), joinpath(outdir, "$name.R2.fq"))
+            simulate_to(ctx, joinpath(outdir, "$name.R1.fq.gz"), joinpath(outdir, "$name.R2.fq.gz"))
         end
     finally
         ccall((:mmk_destroy, LIB), Cvoid, (Ptr{Cvoid},), ctx)
