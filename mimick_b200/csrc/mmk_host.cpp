@@ -78,6 +78,7 @@ struct mmk_ctx {
     SimConst sc;
     uint64_t seed = 0;
     cudaStream_t st = nullptr, st_copy = nullptr;
+    cudaMemPool_t sym_pool = nullptr;  // contig symbols come and go per run: stream-ordered pool that keeps its memory
     std::string err;
 
     std::vector<Contig> contigs;
@@ -161,6 +162,18 @@ struct mmk_ctx {
     uint64_t bz_cum[2] = {0, 0};     // BGZF bytes handed out so far per stream
     bool bz_ready = false;
 };
+
+// contig symbol buffers (uploaded ASCII, released once packed): stream-ordered allocations from a pool that keeps
+// freed memory, so repeated runs on one context do not pay cudaMalloc / cudaFree (~1 ms each at these sizes)
+static cudaError_t sym_alloc(mmk_ctx *c, char **p, size_t bytes) {
+    if (c->sym_pool) return cudaMallocFromPoolAsync((void **)p, bytes, c->sym_pool, c->st);
+    return cudaMalloc((void **)p, bytes);
+}
+static void sym_free(mmk_ctx *c, char *p) {
+    if (!p) return;
+    if (c->sym_pool) cudaFreeAsync(p, c->st);
+    else cudaFree(p);
+}
 
 // ------------------------------------------------------------------------------------------
 // errors
@@ -365,6 +378,21 @@ extern "C" int32_t mmk_create(const mmk_params *p, mmk_ctx **out) {
     CU(cudaSetDevice(q.device));
     CU(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking));
+    {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof props);
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = q.device;
+        if (cudaMemPoolCreate(&ctx->sym_pool, &props) == cudaSuccess) {
+            uint64_t keep = 16ull << 30;  // freed symbol buffers stay with the context up to this much
+            cudaMemPoolSetAttribute(ctx->sym_pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            ctx->sym_pool = nullptr;  // plain cudaMalloc / cudaFree
+            cudaGetLastError();
+        }
+    }
     CU(cudaEventCreate(&ctx->ev_a));
     CU(cudaEventCreate(&ctx->ev_b));
     for (int i = 0; i < 2; ++i) {
@@ -392,8 +420,9 @@ extern "C" void mmk_destroy(mmk_ctx *c) {
         cudaSetDevice(c->par.device);
         cudaStreamSynchronize(c->st);
     }
-    for (auto &k : c->contigs)
-        if (k.d_ascii) cudaFree(k.d_ascii);
+    for (auto &k : c->contigs) sym_free(c, k.d_ascii);
+    if (c->st) cudaStreamSynchronize(c->st);
+    if (c->sym_pool) cudaMemPoolDestroy(c->sym_pool);
     free_outputs(c);
     if (c->d_stats) cudaFree(c->d_stats);
     if (c->h_stats) cudaFreeHost(c->h_stats);
@@ -436,12 +465,12 @@ extern "C" int32_t mmk_add_contig(mmk_ctx *ctx, const char *name, const char *ba
     k.name = name;
     k.haplotype = haplotype;
     k.len = len;
-    CU(cudaMalloc((void **)&k.d_ascii, (size_t)len + 64));
+    CU(sym_alloc(ctx, &k.d_ascii, (size_t)len + 64));
     ctx->contigs.push_back(k);
     Contig &c = ctx->contigs.back();
     const mmk_params &q = ctx->par;
     auto drop = [&]() {
-        cudaFree(c.d_ascii);
+        sym_free(ctx, c.d_ascii);
         ctx->contigs.pop_back();
     };
     cudaError_t e = cudaMemcpyAsync(c.d_ascii, bases, (size_t)len, cudaMemcpyHostToDevice, ctx->st);
@@ -528,8 +557,7 @@ extern "C" int32_t mmk_clear_contigs(mmk_ctx *ctx) {
         CU(cudaSetDevice(ctx->par.device));
         CU(cudaStreamSynchronize(ctx->st));
     }
-    for (auto &k : ctx->contigs)
-        if (k.d_ascii) cudaFree(k.d_ascii);
+    for (auto &k : ctx->contigs) sym_free(ctx, k.d_ascii);
     ctx->contigs.clear();
     ctx->multi_mode = false;
     ctx->sc.sample = 0;
@@ -609,7 +637,7 @@ static int32_t finalize_single(mmk_ctx *ctx) {
     if (rc) return rc;
     // the packed arena is now the only copy a single-sample run needs
     for (auto &c : ctx->contigs) {
-        cudaFree(c.d_ascii);
+        sym_free(ctx, c.d_ascii);
         c.d_ascii = nullptr;
     }
     ctx->schemas_ready = true;
