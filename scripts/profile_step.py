@@ -27,4 +27,14 @@ for it in range(2):
     print(f"step {it}: pairs={plan.n_pairs} molecules={plan.n_molecules} epochs={plan.n_epochs} batches={plan.n_batches} "
           f"bytes={place.r1_bytes + place.r2_bytes} emit_ms={ms:.3f} plan_ms={plan.host_ms:.2f} place_ms={place.host_ms:.2f} "
           f"phases={[round(x, 2) for x in place.phase_ms]}")
+if os.environ.get("MMK_PROFILE_BGZF", "1") != "0":  # the same shard once more, coded as BGZF members on the device
+    sim.rewind()
+    ms = z = 0
+    while True:
+        ch = sim.emit_chunk_bgzf()
+        ms += ch.kernel_ms
+        z += ch.r1_bytes + ch.r2_bytes
+        if ch.done:
+            break
+    print(f"bgzf: coded={z} ratio={(place.r1_bytes + place.r2_bytes) / z:.2f} emit+code_ms={ms:.2f}")
 sim.close()
