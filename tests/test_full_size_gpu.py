@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
@@ -59,6 +60,19 @@ def check_chunk(fmt, r1, r2, haps, r1_len, r2_len, circular_n=None):
     return n, out
 
 
+def check_bgzf_chunk(coded: bytes, text: bytes):
+    import zlib
+    from helpers import bgzf_members
+    members = list(bgzf_members(coded))
+    assert sum(m[2] for m in members) == len(text)
+    pos = 0
+    for i, (off, size, isize, crc) in enumerate(members):
+        if i < 300 or i >= len(members) - 300 or i % 997 == 0:
+            raw = zlib.decompress(coded[off + 18:off + size - 8], wbits=-15)
+            assert len(raw) == isize and zlib.crc32(raw) == crc and raw == text[pos:pos + isize], f"member {i}"
+        pos += isize
+
+
 def run_config(wl, max_chunk_mib, sample_chunks):
     import bench
     import mimick_b200 as M
@@ -75,6 +89,7 @@ def run_config(wl, max_chunk_mib, sample_chunks):
         schemas = sim.schemas()
         slot_bytes, n_chunks = sim.chunk_layout()
         got_pairs, b1, b2, checked, k = 0, 0, 0, [], 0
+        texts = {}
         while True:
             ch = sim.emit_chunk()
             got_pairs += ch.n_pairs
@@ -95,10 +110,27 @@ def run_config(wl, max_chunk_mib, sample_chunks):
                 circ = simkw.get("circular")
                 n, recs = check_chunk(fmt, head1, r2[:cut2], haps, 150, 150, circular_n=True if circ else None)
                 checked.append((n, recs))
+                texts[k] = (r1, r2)
             k += 1
             if ch.done:
                 break
         assert k == n_chunks and got_pairs == plan.n_pairs == place.n_pairs and b1 == place.r1_bytes and b2 == place.r2_bytes
+        # the same shard through the BGZF stage: coded offsets chain, every member of the sampled chunks has a valid
+        # frame whose ISIZEs add up to the text chunk, and a sample of members inflates to exactly that text
+        sim.rewind()
+        z1 = z2 = k = 0
+        while True:
+            ch = sim.emit_chunk_bgzf()
+            assert ch.r1_offset == z1 and ch.r2_offset == z2
+            z1 += ch.r1_bytes
+            z2 += ch.r2_bytes
+            if k in texts:
+                for coded, text in zip(sim.copy_chunk(ch), texts[k]):
+                    check_bgzf_chunk(coded.tobytes(), text)
+            k += 1
+            if ch.done:
+                break
+        assert k == n_chunks and 4.5 < (b1 + b2) / (z1 + z2) < 7.0
         mols = sim.molecules(0, min(plan.n_molecules, 200000))
     return plan, place, schemas, checked, mols
 

@@ -183,3 +183,31 @@ def test_bgzf_code_table_is_a_valid_deflate_code():
     assert any(t[0] == "match" and t[2] == 1 for t in T.tokenize(text)) and any(t[0] == "match" and t[2] > 1 for t in T.tokenize(text))
     eof = M.bgzf_eof()
     assert eof == bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000") and gzip.decompress(eof) == b""
+
+
+def test_cli_maps_the_reference_options():
+    """`python -m mimick_b200` takes the reference's options (mimick/__main__.py:36-60: names, short flags, defaults,
+    ranges) and maps them to the mimick(...) keywords exactly as the reference's Julia command line does (:73-83)."""
+    from mimick_b200.__main__ import plan_call
+
+    args, kw = plan_call(["hap1.fa", "hap2.fa"])
+    assert args == (["hap1.fa", "hap2.fa"], "standard:haplotagging")
+    assert kw["prefix"] == "simulated/" and kw["coverage"] == 30.0 and kw["n_molecules"] == 2 and kw["mol_coverage"] == 0.2
+    assert kw["mol_length"] == 80000 and kw["insert_length"] == 500 and kw["insert_stdev"] == 50 and kw["read_length"] == [150, 150]
+    assert kw["singletons"] == 0 and kw["circular"] is False and kw["attempts"] == 300 and kw["seed"] == -1 and kw["mask"] is False
+    assert kw["compress"] is True
+
+    args, kw = plan_call("-c -m -q -o out/x -s 7 -f 10x -g 12.5 -i 400 -d 30 -A 20 -C 3 -L 50000 -N -2 -l 134,150 -S 0.25 a.fa".split())
+    assert args == (["a.fa"], "tenx")
+    assert kw == dict(prefix="out/x", coverage=12.5, n_molecules=-2, mol_coverage=3.0, mol_length=50000, insert_length=400,
+                      insert_stdev=30, read_length=[134, 150], singletons=0.25, circular=True, attempts=20, seed=7, mask=True,
+                      quiet=True, device=0, compress=True, rank=0, world=1)
+    args, kw = plan_call(["--vcf", "calls.vcf.gz", "--format", "STLFR", "--plain", "ref.fa", "-s", "-9"])
+    assert args == ("ref.fa", "calls.vcf.gz", "stlfr") and kw["outdir"] == "simulated/" and "prefix" not in kw
+    assert kw["seed"] == -1 and kw["compress"] is False          # seed is clamped at -1 like click.IntRange(min=-1, clamp=True)
+    for bad in (["-g", "0.01", "a.fa"], ["-f", "bgi", "a.fa"], ["-l", "150", "a.fa"], ["-l", "5,150", "a.fa"], ["-A", "2", "a.fa"], []):
+        with pytest.raises(SystemExit):
+            plan_call(bad)
+    with pytest.raises(SystemExit) as e:   # __main__.py:84-86
+        plan_call(["-l", "200,200", "-L", "300", "a.fa"])
+    assert "cannot exceed the average molecule length" in str(e.value)

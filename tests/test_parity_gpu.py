@@ -412,3 +412,25 @@ def test_bgzf_members_and_ratio(tmp_path):
         assert pos == len(raw)
         assert len(raw) / len(z) > 4.5, len(raw) / len(z)
     assert place.r1_bytes == len(r1)
+
+
+def test_command_line_runs_like_the_reference_cli(tmp_path):
+    """`python -m mimick_b200` with the reference's options (mimick/__main__.py): exit code 0, the two .fq.gz files of the
+    single-sample mode, contents equal to the oracle run with the same parameters; a Julia-side error (here: a contig
+    too short for the reads) gives exit code 1 like the reference."""
+    import gzip
+    import subprocess
+    import sys
+    fastas = make_ci_haplotypes(tmp_path, seed=21, big=40000)
+    prefix = os.path.join(str(tmp_path), "cli", "S")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "mimick_b200", "-o", prefix, "-s", "11", "-f", "stlfr", "-g", "4", "-l", "150,108", "-q", "-m"] + fastas
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    orc = O.mimick_single(fastas, "stlfr", seed=11, mask=True, coverage=4, read_length=[150, 108], **CLI)
+    assert gzip.decompress(open(prefix + ".R1.fq.gz", "rb").read()) == orc.r1
+    assert gzip.decompress(open(prefix + ".R2.fq.gz", "rb").read()) == orc.r2
+    tiny = os.path.join(str(tmp_path), "tiny.fa")
+    write_fasta(tiny, [("t", b"ACGT" * 20)])
+    r = subprocess.run([sys.executable, "-m", "mimick_b200", "-o", prefix + "2", tiny], cwd=root, capture_output=True, text=True)
+    assert r.returncode == 1 and "ERROR" in r.stderr
