@@ -282,8 +282,8 @@ __device__ __forceinline__ void make_fast_desc(const EmitArgs &a, const uint4 &q
 }
 
 // Phase 1 — one read pair, one warp (half-warp 0: R1, reverse complement; half-warp 1: R2, forward):
-// quality chunks, then sequence chunks, then the 15 bytes after the sequence + the final newline.
-// All 16-byte stores are aligned to the stream; what they spill on is rewritten later.
+// sequence chunks, then the 15 bytes after the sequence + the final newline (the stage already holds the quality
+// character everywhere).  All 16-byte stores are aligned to the stream; what they spill on is rewritten later.
 __device__ __forceinline__ void emit_pair_seq(const EmitArgs &a, const FastDesc &f, uint32_t W, uint32_t smem, uint32_t lane) {
     const uint32_t half = lane >> 4, hl = lane & 15u;
     const uint32_t inl = half ? 0u : (uint32_t)a.bclen_inline;
@@ -294,13 +294,7 @@ __device__ __forceinline__ void emit_pair_seq(const EmitArgs &a, const FastDesc 
     // reference window: one packed word per lane of the half-warp
     const uint32_t ws = half ? f.bend - (uint32_t)a.r2 : f.bstart - 1u;
     const int rel = (int)(ws >= 15u ? ((ws - 15u) & 15u) + 15u : ws);     // window start relative to the first word
-    // quality: 'I' over every 16-byte chunk that touches [seq_end + 3, rec_end)
-    {
-        const uint32_t c = ((seq_end + 3u) >> 4) + hl;
-        const uint4 fill = make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u);
-        if (16u * c < rec_end) sts128(smem + 16u * c, fill);
-    }
-    __syncwarp();
+    // (the whole stage was filled with the quality character before the first pass)
     {
         const uint32_t c = (seq_off >> 4) + hl;
         const int k0 = (int)(16u * c) - (int)seq_off;                     // first base index of this chunk (>= -15)
@@ -311,11 +305,10 @@ __device__ __forceinline__ void emit_pair_seq(const EmitArgs &a, const FastDesc 
         uint32_t hi = __shfl_sync(0xffffffffu, W, (int)((lane & 16u) | ((uint32_t)(j + 1) & 15u)));
         if (j < 0) lo = 0;
         uint32_t bits = __funnelshift_r(lo, hi, sh);
-        if (!half) {
-            bits = __brev(bits);
-            bits = ((bits >> 1) & 0x55555555u) | ((bits & 0x55555555u) << 1);
-        }
-        const uint4 v = expand16(bits, half ? 0x54474341u /* "ACGT" */ : 0x41434754u /* "TGCA" */);
+        // reverse complement: brev mirrors the 16 bases and also swaps the two bits of every base; the lookup is
+        // indexed by the swapped code (00 A -> 'T', 10 = swapped C -> 'G', 01 = swapped G -> 'C', 11 T -> 'A')
+        if (!half) bits = __brev(bits);
+        const uint4 v = expand16(bits, half ? 0x54474341u /* "ACGT" */ : 0x41474354u /* "TCGA" */);
         if (16u * c < seq_end) sts128(smem + 16u * c, v);
     }
     __syncwarp();
@@ -357,12 +350,6 @@ __device__ __forceinline__ void emit_pair_seq4(const EmitArgs &a, const FastDesc
     const uint32_t rec_end = seq_end + 3u + S + inl + 1u;
     const uint32_t ws = half ? f.bend - (uint32_t)a.r2 : f.bstart - 1u;
     const int rel = (int)(ws >= 15u ? ((ws - 15u) & 7u) + 15u : ws);  // window start relative to the first loaded word
-    {
-        const uint32_t c = ((seq_end + 3u) >> 4) + hl;
-        const uint4 fill = make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u);
-        if (16u * c < rec_end) sts128(smem + 16u * c, fill);
-    }
-    __syncwarp();
     {
         const uint32_t c = (seq_off >> 4) + hl;
         const int k0 = (int)(16u * c) - (int)seq_off;
@@ -488,6 +475,12 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_emit(const __grid_c
     // warm L2 for a tile that a later wave of CTAs will run (descriptors are read exactly once)
     if (threadIdx.x < 4 && blockIdx.x + 1184u < a.n_tiles)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(a.fdesc + (p0 + 1184ull * a.tile_pairs)) + 128u * threadIdx.x));
+    {   // the quality character over both stages while the loads above are in flight: sequence chunks, separators and
+        // headers overwrite everything that is not quality
+        const uint4 fill = make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u);
+        uint4 *st = reinterpret_cast<uint4 *>(smem);
+        for (uint32_t i = threadIdx.x; i < a.stage_cap / 8u; i += THREADS) st[i] = fill;
+    }
     const uint64_t g1 = t1 - a.chunk_off1, g2 = t2 - a.chunk_off2;
     const uint32_t A1 = (uint32_t)(g1 & 15u), A2 = (uint32_t)(g2 & 15u);
     if (!fast) {

@@ -401,6 +401,23 @@ def test_bgzf_members_and_ratio(tmp_path):
                 break
         assert b"".join(x[0] for x in parts) == z1 and b"".join(x[1] for x in parts) == z2
         assert [x[2] for x in parts] == list(np.cumsum([0] + [len(x[0]) for x in parts[:-1]]))
+    # the kernel's token choice and bit packing are specified by scripts/bgzf_table.py (tokenize / deflate_block, a
+    # bit-exact Python model built on the same code lengths): the first members must equal the model byte for byte
+    import re
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "scripts"))
+    import bgzf_table as T
+    txt = open(os.path.join(root, "mimick_b200", "csrc", "mmk_bgzf_table.h")).read()
+    ll_len = [int(x) for x in re.search(r"LL_LEN\[286\] = \{([^}]*)\}", txt).group(1).split(",")]
+    d_len = [int(x) for x in re.search(r"D_LEN\[30\] = \{([^}]*)\}", txt).group(1).split(",")]
+    for z, raw in ((z1, r1), (z2, r2)):
+        pos = 0
+        for i, (off, size, isize, crc) in enumerate(bgzf_members(z)):
+            if i >= 12:
+                break
+            assert z[off + 18:off + size - 8] == T.deflate_block(raw[pos:pos + isize], ll_len, d_len), f"member {i} differs from the model"
+            pos += isize
     for z, raw in ((z1, r1), (z2, r2)):
         pos = 0
         for off, size, isize, crc in bgzf_members(z):
