@@ -238,11 +238,12 @@ struct FastDesc {
 };
 static_assert(sizeof(FastDesc) == 32, "FastDesc layout");
 // kept in shared memory as two uint4 arrays (16-byte stride: conflict-free writes, broadcast reads)
-__device__ __forceinline__ FastDesc load_fast_desc(const uint4 *fa, const uint4 *fb, uint32_t t) {
-    const uint4 x = fa[t], y = fb[t];
+__device__ __forceinline__ FastDesc load_fast_desc(const uint4 *fa, const uint2 *fb, uint32_t t) {  // header phase (no window words)
+    const uint4 x = fa[t];
+    const uint2 y = fb[t];
     FastDesc f;
     f.sb1 = x.x; f.sb2 = x.y; f.bstart = x.z; f.bend = x.w;
-    f.wbase1 = y.x; f.wbase2 = y.y; f.mol = y.z; f.pk = y.w;
+    f.wbase1 = f.wbase2 = 0; f.mol = y.x; f.pk = y.y;
     return f;
 }
 #ifndef MMK_PREFETCH_MODE
@@ -284,16 +285,14 @@ __device__ __forceinline__ void make_fast_desc(const EmitArgs &a, const uint4 &q
 // Phase 1 — one read pair, one warp (half-warp 0: R1, reverse complement; half-warp 1: R2, forward):
 // sequence chunks, then the 15 bytes after the sequence + the final newline (the stage already holds the quality
 // character everywhere).  All 16-byte stores are aligned to the stream; what they spill on is rewritten later.
-__device__ __forceinline__ void emit_pair_seq(const EmitArgs &a, const FastDesc &f, uint32_t W, uint32_t smem, uint32_t lane) {
+__device__ __forceinline__ void emit_pair_seq(const EmitArgs &a, const uint2 rdesc, uint32_t W, uint32_t smem, uint32_t lane) {
     const uint32_t half = lane >> 4, hl = lane & 15u;
     const uint32_t inl = half ? 0u : (uint32_t)a.bclen_inline;
     const uint32_t S = half ? (uint32_t)a.r2 : (uint32_t)a.r1;
-    const uint32_t seq_off = (half ? f.sb2 : f.sb1) + FD_HDR(f.pk) + inl;
+    const uint32_t seq_off = rdesc.x & 0xfffffu;   // stage byte offset of the read's first base
+    const int rel = (int)(rdesc.x >> 20);           // window start relative to the first loaded word
     const uint32_t seq_end = seq_off + S;
     const uint32_t rec_end = seq_end + 3u + S + inl + 1u;
-    // reference window: one packed word per lane of the half-warp
-    const uint32_t ws = half ? f.bend - (uint32_t)a.r2 : f.bstart - 1u;
-    const int rel = (int)(ws >= 15u ? ((ws - 15u) & 15u) + 15u : ws);     // window start relative to the first word
     // (the whole stage was filled with the quality character before the first pass)
     {
         const uint32_t c = (seq_off >> 4) + hl;
@@ -340,16 +339,15 @@ __device__ __forceinline__ uint32_t expand4_any(uint32_t nib16) {  // 4 symbols,
 // Phase 1 for a 4-bit reference: same structure as emit_pair_seq; each lane of a half-warp holds two packed
 // words (W0: word hl, W1: word hl + 16), a 16-base chunk is cut from three of them. Reverse complement of
 // 8 one-hot symbols is a plain bit reversal of the word (reversing a nibble complements it).
-__device__ __forceinline__ void emit_pair_seq4(const EmitArgs &a, const FastDesc &f, uint32_t W0, uint32_t W1, uint32_t smem,
+__device__ __forceinline__ void emit_pair_seq4(const EmitArgs &a, const uint2 rdesc, uint32_t W0, uint32_t W1, uint32_t smem,
                                                uint32_t lane) {
     const uint32_t half = lane >> 4, hl = lane & 15u;
     const uint32_t inl = half ? 0u : (uint32_t)a.bclen_inline;
     const uint32_t S = half ? (uint32_t)a.r2 : (uint32_t)a.r1;
-    const uint32_t seq_off = (half ? f.sb2 : f.sb1) + FD_HDR(f.pk) + inl;
+    const uint32_t seq_off = rdesc.x & 0xfffffu;
+    const int rel = (int)(rdesc.x >> 20);  // window start relative to the first loaded word
     const uint32_t seq_end = seq_off + S;
     const uint32_t rec_end = seq_end + 3u + S + inl + 1u;
-    const uint32_t ws = half ? f.bend - (uint32_t)a.r2 : f.bstart - 1u;
-    const int rel = (int)(ws >= 15u ? ((ws - 15u) & 7u) + 15u : ws);  // window start relative to the first loaded word
     {
         const uint32_t c = (seq_off >> 4) + hl;
         const int k0 = (int)(16u * c) - (int)seq_off;
@@ -461,8 +459,11 @@ template <int BPB, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_emit(const __grid_constant__ EmitArgs a) {
     constexpr uint32_t EMIT_WARPS = THREADS / 32;
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ uint4 s_fa[EMIT_MAX_TP], s_fb[EMIT_MAX_TP];
-    __shared__ uint32_t s_off1[EMIT_MAX_TP + 1], s_off2[EMIT_MAX_TP + 1];
+    constexpr uint32_t MAXP = THREADS / 4;                   // pairs per tile this instantiation serves
+    __shared__ uint4 s_fa[MAXP];                             // per pair, for the header phase: sb1, sb2, bstart, bend
+    __shared__ uint2 s_fb[MAXP];                             // ... mol, pk
+    __shared__ uint2 s_rd[2 * MAXP];                         // per read, for the sequence phase: seq_off | rel << 20, first word
+    __shared__ uint32_t s_off1[MAXP + 1], s_off2[MAXP + 1];
     const uint32_t tile = a.tile0 + blockIdx.x;
     const uint64_t p0 = (uint64_t)tile * a.tile_pairs;  // tile_pairs is a power of two
     const uint32_t np = (uint32_t)((a.n_pairs - p0) < a.tile_pairs ? (a.n_pairs - p0) : a.tile_pairs);
@@ -488,7 +489,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_emit(const __grid_c
         PairDesc d;
         d.len1 = d.len2 = 0;
         if (threadIdx.x < np) decode_pair(a, p0 + threadIdx.x, tile_m0, d);
-        if (threadIdx.x < EMIT_MAX_TP) {
+        if (threadIdx.x < MAXP) {
             uint32_t i1 = d.len1, i2 = d.len2;
             for (int o = 1; o < 32; o <<= 1) {
                 uint32_t y1 = __shfl_up_sync(0xffffffffu, i1, o), y2 = __shfl_up_sync(0xffffffffu, i2, o);
@@ -523,7 +524,14 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_emit(const __grid_c
         FastDesc f;
         make_fast_desc(a, a.fdesc[p0 + threadIdx.x], tile_m0, A1, a.stage_cap + A2, f);
         s_fa[threadIdx.x] = make_uint4(f.sb1, f.sb2, f.bstart, f.bend);
-        s_fb[threadIdx.x] = make_uint4(f.wbase1, f.wbase2, f.mol, f.pk);
+        s_fb[threadIdx.x] = make_uint2(f.mol, f.pk);
+        {   // what phase 1 needs of each read, so that its lanes load 8 bytes and select nothing
+            constexpr uint32_t WM = BPB == 2 ? 15u : 7u;
+            const uint32_t ws1 = f.bstart - 1u, ws2 = f.bend - (uint32_t)a.r2;
+            const uint32_t rel1 = ws1 >= 15u ? ((ws1 - 15u) & WM) + 15u : ws1, rel2 = ws2 >= 15u ? ((ws2 - 15u) & WM) + 15u : ws2;
+            s_rd[2 * threadIdx.x] = make_uint2((f.sb1 + FD_HDR(f.pk) + (uint32_t)a.bclen_inline) | (rel1 << 20), f.wbase1);
+            s_rd[2 * threadIdx.x + 1] = make_uint2((f.sb2 + FD_HDR(f.pk)) | (rel2 << 20), f.wbase2);
+        }
         // start the loads phases 1 and 2 will need
         prefetch_l1(a.hap + f.wbase1);
         prefetch_l1(a.hap + f.wbase1 + (BPB == 2 ? 15 : 31));
@@ -535,17 +543,16 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_emit(const __grid_c
     __syncthreads();
     {   // the reference words of pair t + EMIT_WARPS are loaded while pair t is expanded
         const uint32_t half = lane >> 4, hl = lane & 15u;
-        FastDesc f = load_fast_desc(s_fa, s_fb, warp < np ? warp : 0);
-        const uint32_t *wp = a.hap + (half ? f.wbase2 : f.wbase1) + hl;
-        uint32_t W0 = __ldg(wp), W1 = BPB == 4 ? __ldg(wp + 16) : 0u;
+        const uint32_t *hap_lane = a.hap + hl;
+        uint2 rd = s_rd[2 * (warp < np ? warp : 0) + half];
+        uint32_t W0 = __ldg(hap_lane + rd.y), W1 = BPB == 4 ? __ldg(hap_lane + rd.y + 16) : 0u;
         for (uint32_t t = warp; t < np; t += EMIT_WARPS) {
             const uint32_t tn = t + EMIT_WARPS < np ? t + EMIT_WARPS : t;
-            const FastDesc fn = load_fast_desc(s_fa, s_fb, tn);
-            const uint32_t *wn = a.hap + (half ? fn.wbase2 : fn.wbase1) + hl;
-            const uint32_t W0n = __ldg(wn), W1n = BPB == 4 ? __ldg(wn + 16) : 0u;
-            if (BPB == 2) emit_pair_seq(a, f, W0, sm, lane);
-            else emit_pair_seq4(a, f, W0, W1, sm, lane);
-            f = fn;
+            const uint2 rn = s_rd[2 * tn + half];
+            const uint32_t W0n = __ldg(hap_lane + rn.y), W1n = BPB == 4 ? __ldg(hap_lane + rn.y + 16) : 0u;
+            if (BPB == 2) emit_pair_seq(a, rd, W0, sm, lane);
+            else emit_pair_seq4(a, rd, W0, W1, sm, lane);
+            rd = rn;
             W0 = W0n;
             W1 = W1n;
         }
