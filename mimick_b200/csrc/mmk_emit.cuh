@@ -480,7 +480,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_emit(const __grid_c
         // headers overwrite everything that is not quality
         const uint4 fill = make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u);
         uint4 *st = reinterpret_cast<uint4 *>(smem);
-        for (uint32_t i = threadIdx.x; i < a.stage_cap / 8u; i += THREADS) st[i] = fill;
+        const uint32_t n16 = a.stage_cap / 8u;  // 16-byte units of both stages
+#pragma unroll 4
+        for (uint32_t i = threadIdx.x; i < n16; i += THREADS) st[i] = fill;
     }
     const uint64_t g1 = t1 - a.chunk_off1, g2 = t2 - a.chunk_off2;
     const uint32_t A1 = (uint32_t)(g1 & 15u), A2 = (uint32_t)(g2 & 15u);
