@@ -108,7 +108,9 @@ void *mmk_cuda_stream(const mmk_ctx *ctx);
 
 /* ---- inputs ------------------------------------------------------------------------------
  * process_fasta / setup_schema, src/ProcessFASTA.jl:45-95.  `bases` is ASCII IUPAC (either
- * case), host memory, `len` symbols; `haplotype` is the 1-based FASTA file index.  The contig
+ * case), `len` symbols, in host memory or in device memory of the context's GPU (unified
+ * addressing tells them apart; a multi-GPU caller can upload each contig once and replicate it
+ * over NVLink); `haplotype` is the 1-based FASTA file index.  The contig
  * is uploaded, validated, optionally N-masked (mask_N!, :29-36) and counted on the device;
  * reads_required follows :47-61.  Contigs become schemas in the order they are added. */
 int32_t mmk_add_contig(mmk_ctx *ctx, const char *name, const char *bases, int64_t len, int32_t haplotype);

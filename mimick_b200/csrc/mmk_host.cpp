@@ -473,7 +473,8 @@ extern "C" int32_t mmk_add_contig(mmk_ctx *ctx, const char *name, const char *ba
         sym_free(ctx, c.d_ascii);
         ctx->contigs.pop_back();
     };
-    cudaError_t e = cudaMemcpyAsync(c.d_ascii, bases, (size_t)len, cudaMemcpyHostToDevice, ctx->st);
+    // `bases` may be host memory (pageable or pinned) or device memory, e.g. symbols another rank broadcast over NVLink
+    cudaError_t e = cudaMemcpyAsync(c.d_ascii, bases, (size_t)len, cudaMemcpyDefault, ctx->st);
     ContigStats zero{~0ull, 0, 0};
     if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->d_stats, &zero, sizeof zero, cudaMemcpyHostToDevice, ctx->st);
     if (e == cudaSuccess) {

@@ -451,3 +451,29 @@ def test_command_line_runs_like_the_reference_cli(tmp_path):
     write_fasta(tiny, [("t", b"ACGT" * 20)])
     r = subprocess.run([sys.executable, "-m", "mimick_b200", "-o", prefix + "2", tiny], cwd=root, capture_output=True, text=True)
     assert r.returncode == 1 and "ERROR" in r.stderr
+
+
+def test_contig_symbols_may_already_be_on_the_device(tmp_path):
+    """mmk_add_contig takes host or device memory: a multi-GPU caller uploads each contig once and replicates it over
+    NVLink (bench.py does); the output must not depend on where the symbols came from."""
+    import torch
+
+    import mimick_b200 as M
+    rng = np.random.default_rng(12)
+    seqs = [("c1", random_bases(rng, 300000)), ("c2", random_bases(rng, 200000, b"ACGTN"))]
+    outs = []
+    for on_device in (False, True):
+        with M.Simulator("tellseq", seed=4, coverage=3, mask=True, **CLI) as sim:
+            keep = []
+            for name, seq in seqs:
+                t = torch.frombuffer(bytearray(seq), dtype=torch.uint8)
+                if on_device:
+                    t = t.cuda()
+                keep.append(t)
+                sim.add_contig(name, (t.data_ptr(), t.numel()), 1)
+            outs.append(sim.run())
+    assert outs[0] == outs[1]
+    p = os.path.join(str(tmp_path), "a.fa")
+    write_fasta(p, seqs)
+    orc = O.mimick_single([p], "tellseq", seed=4, mask=True, coverage=3, **CLI)
+    assert outs[0][0] == orc.r1 and outs[0][1] == orc.r2
