@@ -254,6 +254,31 @@ def reference_arm(args):
 # ------------------------------------------------------------------------------------------
 # CUDA arm
 # ------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that the pinned host buffers it allocates
+    (first touch) and the threads that consume them sit next to the GPU's PCIe root.  With one process per GPU and all
+    buffers on one socket, eight concurrent D2H streams share that socket's memory and the inter-socket link.
+    Best effort: returns the node, or None when the topology cannot be read."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(f"{base}/numa_node").read())
+        cpus = set()
+        for part in open(f"{base}/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node >= 0 and cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
+
 def cuda_arm(args):
     import torch
     import torch.distributed as dist
@@ -267,6 +292,7 @@ def cuda_arm(args):
         raise SystemExit("bench.py: no CUDA device (the CUDA arm has no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
+    numa = bind_to_gpu_numa_node(local)   # before any pinned allocation: host rings next to the GPU's PCIe root
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(dev))
@@ -474,6 +500,7 @@ def cuda_arm(args):
             "e2e": e2e,
             "e2e_text": e2e_text,
             "gpu_launches": int(launches),
+            "host_numa_node": numa,
             "clocks": clocks,
             "wall_s_timed_region": wall,
             "plan": {"groups": int(state["plan"].n_groups), "epochs": int(state["plan"].n_epochs),
