@@ -368,8 +368,8 @@ __global__ void k_plan_molecules(SimConst sc, const SchemaDev *__restrict__ sch,
 __global__ void __launch_bounds__(1024) k_plan_finish(const uint16_t *__restrict__ schema, const uint32_t *__restrict__ nfrags,
                                                       const uint64_t *__restrict__ group, const uint64_t *__restrict__ off,
                                                       uint64_t g0, uint32_t n_groups, const uint16_t *__restrict__ live,
-                                                      uint32_t n_live, const unsigned long long *__restrict__ hist, uint32_t hstride,
-                                                      const int64_t *__restrict__ need, const unsigned long long *first_err,
+                                                      uint32_t n_live, unsigned long long *hist, uint32_t hstride,
+                                                      const int64_t *__restrict__ need, unsigned long long *first_err,
                                                       const uint8_t *__restrict__ status, BatchResult *res) {
     __shared__ unsigned long long s_cut;
     __shared__ uint64_t s_commit;
@@ -392,9 +392,17 @@ __global__ void __launch_bounds__(1024) k_plan_finish(const uint16_t *__restrict
             const uint16_t sid = live[s];
             unsigned long long cum = 0;
             uint32_t found = 0xffffffffu;
+            // four rounds of loads in flight: the scan below is a chain of L2 latencies otherwise
+            const unsigned long long *hs = hist + (uint64_t)s * hstride;
+            unsigned long long pre[4];
+#pragma unroll
+            for (uint32_t u = 0; u < 4; ++u) pre[u] = 32 * u + lane < n_chunks ? hs[32 * u + lane] : 0ull;
             for (uint32_t c0 = 0; c0 < n_chunks && found == 0xffffffffu; c0 += 32) {
-                const uint32_t c = c0 + lane;
-                const unsigned long long v = c < n_chunks ? hist[(uint64_t)s * hstride + c] : 0ull;
+                const unsigned long long v = pre[0];
+                pre[0] = pre[1];
+                pre[1] = pre[2];
+                pre[2] = pre[3];
+                pre[3] = c0 + 128 + lane < n_chunks ? hs[c0 + 128 + lane] : 0ull;
                 unsigned long long inc = v;
                 for (int o = 1; o < 32; o <<= 1) {
                     unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
@@ -461,7 +469,12 @@ __global__ void __launch_bounds__(1024) k_plan_finish(const uint16_t *__restrict
         res->n_commit = nc;
         res->first_error = fe < nc ? fe : ~0ull;
         res->error_code = fe < nc ? status[base + fe] : 0;
+        *first_err = ~0ull;  // ready for the next batch
     }
+    // leave the histogram all-zero for the next batch (this batch dirtied n_chunks columns of n_live rows)
+    __syncthreads();
+    for (uint32_t s = warp; s < n_live; s += n_warps)
+        for (uint32_t c = lane; c < n_chunks; c += 32) hist[(uint64_t)s * hstride + c] = 0ull;
 }
 
 uint32_t plan_hist_chunks(uint64_t max_molecules) { return (uint32_t)((max_molecules + HCH - 1) / HCH); }
@@ -490,9 +503,7 @@ void plan_batch(const SimConst &sc, const SchemaDev *d_sch, const uint16_t *d_li
                 uint64_t max_mol, const int64_t *d_need, unsigned long long *d_hist, unsigned long long *d_first_err,
                 BatchResult *d_res, cudaStream_t st) {
     (void)d_nmol;
-    const uint32_t n_chunks = plan_hist_chunks(max_mol);
-    cudaMemsetAsync(d_hist, 0, (size_t)n_chunks * n_live * sizeof(unsigned long long), st);
-    cudaMemsetAsync(d_first_err, 0xff, 8, st);
+    const uint32_t n_chunks = plan_hist_chunks(max_mol);  // d_hist is all-zero and *d_first_err all-ones on entry (k_plan_finish restores both)
     LAUNCH(k_plan_molecules, (unsigned)((max_mol + 127) / 128), 128, 0, st, sc, d_sch, d_live, d_lpos, n_live, epoch, g0, n_groups, d_off,
            plan, d_hist, n_chunks, d_first_err);
     LAUNCH(k_plan_finish, 1, 1024, 0, st, plan.schema, plan.nfrags, plan.group, d_off, g0, n_groups, d_live, n_live, d_hist, n_chunks,

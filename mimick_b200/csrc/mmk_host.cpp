@@ -1053,6 +1053,7 @@ extern "C" int32_t mmk_plan(mmk_ctx *ctx, mmk_plan_info *out) {
     uint64_t B = Bmin;
     int64_t n_batches = 0, n_epochs = 0;
     bool live_dirty = true;
+    bool hist_clean = false;  // a failed earlier call may have left the scratch dirty: clean it once per plan
     double inserts_per_group = 0.0;  // running estimate, all live schemas together
     while (!live.empty()) {
         const uint32_t n_live = (uint32_t)live.size();
@@ -1086,7 +1087,15 @@ extern "C" int32_t mmk_plan(mmk_ctx *ctx, mmk_plan_info *out) {
             }
         }
         const uint64_t max_mol = (uint64_t)nb * max_nmol;
-        CU(ctx->d_hist.ensure((size_t)plan_hist_chunks(max_mol) * n_live));
+        {   // the batch kernels keep the histogram all-zero and the first-error slot all-ones between batches
+            const size_t want_hist = (size_t)plan_hist_chunks(max_mol) * n_live;
+            if (want_hist > ctx->d_hist.cap || !hist_clean) {
+                CU(ctx->d_hist.ensure(want_hist));
+                CU(cudaMemsetAsync(ctx->d_hist.p, 0, ctx->d_hist.cap * sizeof(unsigned long long), ctx->st));
+                CU(cudaMemsetAsync(ctx->d_first_err.p, 0xff, 8, ctx->st));
+                hist_clean = true;
+            }
+        }
         CU(cudaMemcpyAsync(ctx->d_need.p, need, n_live * 8, cudaMemcpyHostToDevice, ctx->st));
         plan_batch(ctx->sc, ctx->d_sch.p, ctx->d_live.p, ctx->d_lpos.p, n_live, (uint16_t)(ctx->epoch_nlive.size() - 1), g0, nb,
                    ctx->d_gnmol.p, ctx->d_goff.p, plan_dev(ctx), max_mol, ctx->d_need.p, ctx->d_hist.p, ctx->d_first_err.p,
