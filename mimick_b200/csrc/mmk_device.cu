@@ -362,119 +362,130 @@ __global__ void k_plan_molecules(SimConst sc, const SchemaDev *__restrict__ sch,
     if (status) atomicMin(first_err, (unsigned long long)j);
 }
 
-// One block closes the batch: per live schema the barcode group in which its cumulative insert count
-// reaches the remaining need (a schema is pruned at the END of that group, Main.jl:54,58), the earliest
-// such group = the cut, the number of molecules kept, the inserts each schema received from them.
-__global__ void __launch_bounds__(1024) k_plan_finish(const uint16_t *__restrict__ schema, const uint32_t *__restrict__ nfrags,
-                                                      const uint64_t *__restrict__ group, const uint64_t *__restrict__ off,
-                                                      uint64_t g0, uint32_t n_groups, const uint16_t *__restrict__ live,
-                                                      uint32_t n_live, unsigned long long *hist, uint32_t hstride,
-                                                      const int64_t *__restrict__ need, unsigned long long *first_err,
-                                                      const uint8_t *__restrict__ status, BatchResult *res) {
-    __shared__ unsigned long long s_cut;
-    __shared__ uint64_t s_commit;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+// Two small kernels close the batch, one warp per live schema in both.
+// k_plan_cut: the barcode group in which the schema's cumulative insert count reaches its remaining need (a schema
+// is pruned at the END of that group, Main.jl:54,58); the earliest over all schemas = the cut (atomicMin).
+// k_plan_sums: the number of molecules kept and the inserts each schema received from them; leaves the scratch
+// (histogram, first-error slot, the other batch parity's cut slot) clean for the next batch.
+// scratch[0] = first molecule with a non-zero status, scratch[1 + parity] = cut group of the batch.
+constexpr uint32_t PLAN_FIN_THREADS = 256;
+__global__ void __launch_bounds__(PLAN_FIN_THREADS) k_plan_cut(const uint16_t *__restrict__ schema, const uint32_t *__restrict__ nfrags,
+                                                               const uint64_t *__restrict__ group, const uint64_t *__restrict__ off,
+                                                               uint64_t g0, uint32_t n_groups, const uint16_t *__restrict__ live,
+                                                               uint32_t n_live, const unsigned long long *__restrict__ hist,
+                                                               uint32_t hstride, const int64_t *__restrict__ need,
+                                                               unsigned long long *cut) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t s = blockIdx.x * (PLAN_FIN_THREADS / 32) + (threadIdx.x >> 5);
+    if (s >= n_live) return;
     const uint64_t base = off[g0];
     const uint64_t n_mol = off[g0 + n_groups] - base;
     const uint32_t n_chunks = (uint32_t)((n_mol + HCH - 1) / HCH);
     schema += base;
     nfrags += base;
     group += base;
-    if (threadIdx.x == 0) s_cut = ~0ull;
-    __syncthreads();
     constexpr uint32_t PER = HCH / 32;
-    for (uint32_t s = warp; s < n_live; s += n_warps) {
-        const long long want = need[s];
-        unsigned long long cg = ~0ull;
-        if (want <= 0) {
-            cg = g0;  // already complete: pruned at the end of the batch's first group
-        } else {
-            const uint16_t sid = live[s];
-            unsigned long long cum = 0;
-            uint32_t found = 0xffffffffu;
-            // four rounds of loads in flight: the scan below is a chain of L2 latencies otherwise
-            const unsigned long long *hs = hist + (uint64_t)s * hstride;
-            unsigned long long pre[4];
+    const long long want = need[s];
+    unsigned long long cg = ~0ull;
+    if (want <= 0) {
+        cg = g0;  // already complete: pruned at the end of the batch's first group
+    } else {
+        const uint16_t sid = live[s];
+        unsigned long long cum = 0;
+        uint32_t found = 0xffffffffu;
+        // four rounds of loads in flight: the scan below is a chain of L2 latencies otherwise
+        const unsigned long long *hs = hist + (uint64_t)s * hstride;
+        unsigned long long pre[4];
 #pragma unroll
-            for (uint32_t u = 0; u < 4; ++u) pre[u] = 32 * u + lane < n_chunks ? hs[32 * u + lane] : 0ull;
-            for (uint32_t c0 = 0; c0 < n_chunks && found == 0xffffffffu; c0 += 32) {
-                const unsigned long long v = pre[0];
-                pre[0] = pre[1];
-                pre[1] = pre[2];
-                pre[2] = pre[3];
-                pre[3] = c0 + 128 + lane < n_chunks ? hs[c0 + 128 + lane] : 0ull;
-                unsigned long long inc = v;
-                for (int o = 1; o < 32; o <<= 1) {
-                    unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += y;
-                }
-                const unsigned ball = __ballot_sync(0xffffffffu, (long long)(cum + inc) >= want);
-                if (ball) {
-                    const int l = __ffs(ball) - 1;
-                    cum += __shfl_sync(0xffffffffu, inc - v, l);
-                    found = c0 + l;
-                } else
-                    cum += __shfl_sync(0xffffffffu, inc, 31);
+        for (uint32_t u = 0; u < 4; ++u) pre[u] = 32 * u + lane < n_chunks ? hs[32 * u + lane] : 0ull;
+        for (uint32_t c0 = 0; c0 < n_chunks && found == 0xffffffffu; c0 += 32) {
+            const unsigned long long v = pre[0];
+            pre[0] = pre[1];
+            pre[1] = pre[2];
+            pre[2] = pre[3];
+            pre[3] = c0 + 128 + lane < n_chunks ? hs[c0 + 128 + lane] : 0ull;
+            unsigned long long inc = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += y;
             }
-            if (found != 0xffffffffu) {  // the molecule inside the chunk: each lane owns PER consecutive molecules
-                const uint64_t lo = (uint64_t)found * HCH + (uint64_t)lane * PER;
-                unsigned long long part = 0;
+            const unsigned ball = __ballot_sync(0xffffffffu, (long long)(cum + inc) >= want);
+            if (ball) {
+                const int l = __ffs(ball) - 1;
+                cum += __shfl_sync(0xffffffffu, inc - v, l);
+                found = c0 + l;
+            } else
+                cum += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (found != 0xffffffffu) {  // the molecule inside the chunk: each lane owns PER consecutive molecules
+            const uint64_t lo = (uint64_t)found * HCH + (uint64_t)lane * PER;
+            unsigned long long part = 0;
+            for (uint32_t j = 0; j < PER; ++j) {
+                const uint64_t i = lo + j;
+                if (i < n_mol && schema[i] == sid) part += nfrags[i];
+            }
+            unsigned long long inc = part;
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += y;
+            }
+            const unsigned ball = __ballot_sync(0xffffffffu, (long long)(cum + inc) >= want);
+            const int l = __ffs(ball) - 1;  // non-zero by construction
+            if ((int)lane == l) {
+                unsigned long long run = cum + inc - part;
                 for (uint32_t j = 0; j < PER; ++j) {
                     const uint64_t i = lo + j;
-                    if (i < n_mol && schema[i] == sid) part += nfrags[i];
-                }
-                unsigned long long inc = part;
-                for (int o = 1; o < 32; o <<= 1) {
-                    unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += y;
-                }
-                const unsigned ball = __ballot_sync(0xffffffffu, (long long)(cum + inc) >= want);
-                const int l = __ffs(ball) - 1;  // non-zero by construction
-                if ((int)lane == l) {
-                    unsigned long long run = cum + inc - part;
-                    for (uint32_t j = 0; j < PER; ++j) {
-                        const uint64_t i = lo + j;
-                        if (i < n_mol && schema[i] == sid) {
-                            run += nfrags[i];
-                            if ((long long)run >= want) {
-                                cg = group[i];
-                                break;
-                            }
+                    if (i < n_mol && schema[i] == sid) {
+                        run += nfrags[i];
+                        if ((long long)run >= want) {
+                            cg = group[i];
+                            break;
                         }
                     }
                 }
-                cg = __shfl_sync(0xffffffffu, cg, l);
             }
+            cg = __shfl_sync(0xffffffffu, cg, l);
         }
-        if (lane == 0 && cg != ~0ull) atomicMin(&s_cut, cg);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) s_commit = (s_cut == ~0ull) ? n_mol : off[s_cut + 1] - base;
-    __syncthreads();
-    const uint64_t nc = s_commit;
-    // inserts per live schema among the kept molecules: whole chunks from the histogram, the last from the molecules
-    const uint32_t full = (uint32_t)(nc / HCH);
-    for (uint32_t s = warp; s < n_live; s += n_warps) {
-        const uint16_t sid = live[s];
-        unsigned long long acc = 0;
-        for (uint32_t c = lane; c < full; c += 32) acc += hist[(uint64_t)s * hstride + c];
-        for (uint64_t i = (uint64_t)full * HCH + lane; i < nc; i += 32)
-            if (schema[i] == sid) acc += nfrags[i];
-        for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-        if (lane == 0) res->sums[s] = acc;
-    }
-    if (threadIdx.x == 0) {
-        const unsigned long long fe = *first_err;
-        res->cut_group = s_cut;
+    if (lane == 0 && cg != ~0ull) atomicMin(cut, cg);
+}
+__global__ void __launch_bounds__(PLAN_FIN_THREADS) k_plan_sums(const uint16_t *__restrict__ schema, const uint32_t *__restrict__ nfrags,
+                                                                const uint64_t *__restrict__ off, uint64_t g0, uint32_t n_groups,
+                                                                const uint16_t *__restrict__ live, uint32_t n_live,
+                                                                unsigned long long *hist, uint32_t hstride,
+                                                                unsigned long long *scratch, uint32_t parity,
+                                                                const uint8_t *__restrict__ status, BatchResult *res) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t s = blockIdx.x * (PLAN_FIN_THREADS / 32) + (threadIdx.x >> 5);
+    const uint64_t base = off[g0];
+    const uint64_t n_mol = off[g0 + n_groups] - base;
+    const uint32_t n_chunks = (uint32_t)((n_mol + HCH - 1) / HCH);
+    const unsigned long long cutv = scratch[1 + parity];
+    const uint64_t nc = (cutv == ~0ull) ? n_mol : off[cutv + 1] - base;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned long long fe = scratch[0];
+        res->cut_group = cutv;
         res->n_commit = nc;
         res->first_error = fe < nc ? fe : ~0ull;
         res->error_code = fe < nc ? status[base + fe] : 0;
-        *first_err = ~0ull;  // ready for the next batch
+        scratch[0] = ~0ull;            // ready for the next batch
+        scratch[1 + (parity ^ 1u)] = ~0ull;  // ... which uses the other cut slot (nobody reads it any more)
     }
+    if (s >= n_live) return;
+    schema += base;
+    nfrags += base;
+    // inserts of this schema among the kept molecules: whole chunks from the histogram, the last from the molecules
+    const uint32_t full = (uint32_t)(nc / HCH);
+    const uint16_t sid = live[s];
+    unsigned long long *hs = hist + (uint64_t)s * hstride;
+    unsigned long long acc = 0;
+    for (uint32_t c = lane; c < full; c += 32) acc += hs[c];
+    for (uint64_t i = (uint64_t)full * HCH + lane; i < nc; i += 32)
+        if (schema[i] == sid) acc += nfrags[i];
+    for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) res->sums[s] = acc;
     // leave the histogram all-zero for the next batch (this batch dirtied n_chunks columns of n_live rows)
-    __syncthreads();
-    for (uint32_t s = warp; s < n_live; s += n_warps)
-        for (uint32_t c = lane; c < n_chunks; c += 32) hist[(uint64_t)s * hstride + c] = 0ull;
+    for (uint32_t c = lane; c < n_chunks; c += 32) hs[c] = 0ull;
 }
 
 uint32_t plan_hist_chunks(uint64_t max_molecules) { return (uint32_t)((max_molecules + HCH - 1) / HCH); }
@@ -500,14 +511,18 @@ void plan_set_live(const uint16_t *d_live, uint32_t n_live, uint16_t *d_lpos, cu
 
 void plan_batch(const SimConst &sc, const SchemaDev *d_sch, const uint16_t *d_live, const uint16_t *d_lpos, uint32_t n_live,
                 uint16_t epoch, uint64_t g0, uint32_t n_groups, const uint32_t *d_nmol, const uint64_t *d_off, PlanDev plan,
-                uint64_t max_mol, const int64_t *d_need, unsigned long long *d_hist, unsigned long long *d_first_err,
+                uint64_t max_mol, const int64_t *d_need, unsigned long long *d_hist, unsigned long long *d_scratch, uint32_t parity,
                 BatchResult *d_res, cudaStream_t st) {
     (void)d_nmol;
-    const uint32_t n_chunks = plan_hist_chunks(max_mol);  // d_hist is all-zero and *d_first_err all-ones on entry (k_plan_finish restores both)
+    // d_hist is all-zero, d_scratch[0] (first error) and d_scratch[1 + parity] (cut) all-ones on entry: k_plan_sums restores them
+    const uint32_t n_chunks = plan_hist_chunks(max_mol);
     LAUNCH(k_plan_molecules, (unsigned)((max_mol + 127) / 128), 128, 0, st, sc, d_sch, d_live, d_lpos, n_live, epoch, g0, n_groups, d_off,
-           plan, d_hist, n_chunks, d_first_err);
-    LAUNCH(k_plan_finish, 1, 1024, 0, st, plan.schema, plan.nfrags, plan.group, d_off, g0, n_groups, d_live, n_live, d_hist, n_chunks,
-           d_need, d_first_err, plan.status, d_res);
+           plan, d_hist, n_chunks, d_scratch);
+    const unsigned fin_blocks = (n_live + PLAN_FIN_THREADS / 32 - 1) / (PLAN_FIN_THREADS / 32);
+    LAUNCH(k_plan_cut, fin_blocks, PLAN_FIN_THREADS, 0, st, plan.schema, plan.nfrags, plan.group, d_off, g0, n_groups, d_live, n_live,
+           d_hist, n_chunks, d_need, d_scratch + 1 + parity);
+    LAUNCH(k_plan_sums, fin_blocks, PLAN_FIN_THREADS, 0, st, plan.schema, plan.nfrags, d_off, g0, n_groups, d_live, n_live, d_hist,
+           n_chunks, d_scratch, parity, plan.status, d_res);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -1031,7 +1031,7 @@ extern "C" int32_t mmk_plan(mmk_ctx *ctx, mmk_plan_info *out) {
     CU(ctx->d_live.ensure(K ? K : 1));
     CU(ctx->d_lpos.ensure(65536));
     CU(ctx->d_need.ensure(K ? K : 1));
-    CU(ctx->d_first_err.ensure(1));
+    CU(ctx->d_first_err.ensure(3));  // first error, cut of even / odd batches
     const size_t res_bytes = sizeof(BatchResult) + (size_t)K * 8;
     CU(ctx->d_res.ensure(res_bytes));
     if (ctx->h_res_cap < res_bytes + (size_t)K * 8) {  // pinned: the per-batch control round trip is latency-bound
@@ -1092,7 +1092,7 @@ extern "C" int32_t mmk_plan(mmk_ctx *ctx, mmk_plan_info *out) {
             if (want_hist > ctx->d_hist.cap || !hist_clean) {
                 CU(ctx->d_hist.ensure(want_hist));
                 CU(cudaMemsetAsync(ctx->d_hist.p, 0, ctx->d_hist.cap * sizeof(unsigned long long), ctx->st));
-                CU(cudaMemsetAsync(ctx->d_first_err.p, 0xff, 8, ctx->st));
+                CU(cudaMemsetAsync(ctx->d_first_err.p, 0xff, 3 * 8, ctx->st));
                 hist_clean = true;
             }
         }
@@ -1100,7 +1100,7 @@ extern "C" int32_t mmk_plan(mmk_ctx *ctx, mmk_plan_info *out) {
         // operations on the critical path of every batch
         plan_batch(ctx->sc, ctx->d_sch.p, ctx->d_live.p, ctx->d_lpos.p, n_live, (uint16_t)(ctx->epoch_nlive.size() - 1), g0, nb,
                    ctx->d_gnmol.p, ctx->d_goff.p, plan_dev(ctx), max_mol, need, ctx->d_hist.p, ctx->d_first_err.p,
-                   (BatchResult *)h_res, ctx->st);
+                   (uint32_t)(n_batches & 1), (BatchResult *)h_res, ctx->st);
         CU(cudaStreamSynchronize(ctx->st));
         CU(cudaGetLastError());
         ++n_batches;

@@ -131,8 +131,8 @@ void plan_set_live(const uint16_t *d_live, uint32_t n_live, uint16_t *d_lpos /*[
 // d_hist needs plan_hist_chunks(max_mol) * n_live entries
 void plan_batch(const SimConst &sc, const SchemaDev *d_sch, const uint16_t *d_live, const uint16_t *d_lpos, uint32_t n_live,
                 uint16_t epoch, uint64_t g0, uint32_t n_groups, const uint32_t *d_nmol, const uint64_t *d_off, PlanDev plan,
-                uint64_t max_mol, const int64_t *d_need, unsigned long long *d_hist, unsigned long long *d_first_err,
-                BatchResult *d_res, cudaStream_t st);
+                uint64_t max_mol, const int64_t *d_need, unsigned long long *d_hist, unsigned long long *d_scratch, uint32_t parity,
+                BatchResult *d_res, cudaStream_t st);  // d_scratch: 3 words (first error, cut of even / odd batches)
 
 void shard_bounds(const uint64_t *d_read_off, uint64_t n_mol, uint64_t n_pairs, int32_t world, uint64_t *d_bounds /*[world+1]*/,
                   cudaStream_t st);
