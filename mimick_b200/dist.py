@@ -55,10 +55,17 @@ def exchange_counts(mine: RankCounts, device=None) -> ShardLayout:
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return layout_from_counts([mine])
+    world = dist.get_world_size()
     t = torch.tensor([mine.r1_bytes, mine.r2_bytes, mine.n_pairs, mine.first_pair], dtype=torch.int64, device=device)
-    out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
-    dist.all_gather(out, t)
-    return layout_from_counts([RankCounts(*[int(x) for x in o.tolist()]) for o in out])
+    if t.is_cuda:   # one collective into one tensor, one device-to-host read
+        out = torch.empty(world * 4, dtype=torch.int64, device=t.device)
+        dist.all_gather_into_tensor(out, t)
+        rows = out.cpu().view(world, 4).tolist()
+    else:           # gloo
+        parts = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        rows = [p.tolist() for p in parts]
+    return layout_from_counts([RankCounts(*[int(x) for x in r]) for r in rows])
 
 
 def samples_for_rank(n_samples: int, rank: int, world: int) -> List[int]:
