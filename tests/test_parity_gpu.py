@@ -477,3 +477,38 @@ def test_contig_symbols_may_already_be_on_the_device(tmp_path):
     write_fasta(p, seqs)
     orc = O.mimick_single([p], "tellseq", seed=4, mask=True, coverage=3, **CLI)
     assert outs[0][0] == orc.r1 and outs[0][1] == orc.r2
+
+
+def test_bgzf_fallbacks_and_consumer_errors(tmp_path):
+    """BGZF edge cases: (i) text with a byte the fixed code has no symbol for (a contig name with a non-ASCII
+    character) must come out as stored members that still inflate to the oracle's text; (ii) very short reads
+    (more newlines per lane than the register queue holds) still code correctly; (iii) a consumer that fails
+    aborts the stream with its status."""
+    import mimick_b200 as M
+    rng = np.random.default_rng(31)
+    p = os.path.join(str(tmp_path), "u.fa")
+    write_fasta(p, [("chré", random_bases(rng, 120000))])
+    gpu = gpu_single([p], "haplotagging", 6, coverage=4, variates=False, **CLI)   # checks inflate(BGZF) == text inside
+    orc = O.mimick_single([p], "haplotagging", seed=6, coverage=4, **CLI)
+    assert gpu["r1"] == orc.r1 and gpu["r2"] == orc.r2 and "chré".encode() in orc.r1[:40]
+    stored = sum(1 for off, size, isize, crc in bgzf_members(gpu["z1"]) if size == isize + 18 + 5 + 8)
+    assert stored == sum(1 for _ in bgzf_members(gpu["z1"]))          # every member is a stored block
+    q = os.path.join(str(tmp_path), "s.fa")
+    write_fasta(q, [("c", random_bases(rng, 90000))])
+    short = dict(read_length=[16, 20], insert_length=260, insert_stdev=10, mol_length=5000)
+    gpu = gpu_single([q], "stlfr", 8, coverage=3, variates=False, **short, **CLI)
+    orc = O.mimick_single([q], "stlfr", seed=8, coverage=3, **short, **CLI)
+    assert gpu["r1"] == orc.r1 and gpu["r2"] == orc.r2 and len(gpu["r1"]) / len(gpu["z1"]) > 2.0
+    with M.Simulator("stlfr", seed=8, coverage=3, **short, **CLI) as sim:
+        sim.load_fasta(q)
+        sim.plan()
+        sim.place()
+        cap = sim.bgzf_bound()
+        slots = [np.empty(cap, dtype=np.uint8) for _ in range(4)]
+
+        def boom(ch, p1, p2):
+            raise RuntimeError("disk full")
+        with pytest.raises(M.MimickError):
+            sim.emit_stream([slots[0].ctypes.data, slots[1].ctypes.data], [slots[2].ctypes.data, slots[3].ctypes.data], cap, boom, bgzf=True)
+        with pytest.raises(M.MimickError):   # slots smaller than the bound are refused before anything runs
+            sim.emit_stream([slots[0].ctypes.data, slots[1].ctypes.data], [slots[2].ctypes.data, slots[3].ctypes.data], 1024, None, bgzf=True)
