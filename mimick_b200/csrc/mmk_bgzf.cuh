@@ -20,7 +20,8 @@
 // bit packing are serial byte loops per record, so a warp instruction advances 32 records at once and nothing needs
 // a CTA barrier.  A record's bits are first packed into the shared-memory bytes of its own quality line (nobody
 // reads those again once the token choice is made), then — after a warp scan of the bit counts — shifted to their
-// final position in the member.  Only quality lines that are a run of one character are coded (this library writes
+// final position in the member (quality lines too short for that — short reads — switch the warp to a direct mode:
+// count, scan, write in place).  Only quality lines that are a run of one character are coded (this library writes
 // no other kind); anything else falls back to a stored block.
 #pragma once
 #include "mmk_internal.h"
@@ -100,7 +101,37 @@ struct BzWriter {
     }
 };
 
-__device__ __forceinline__ void bz_put_literals(const BzSmem &S, BzWriter &bw, uint32_t a, uint32_t b) {
+// Same interface, counting only (sizing pass of the direct mode)
+struct BzCounter {
+    uint32_t bits;
+    bool bad;
+    __device__ __forceinline__ void put(uint32_t, uint32_t n) { bits += n; }
+};
+// Same interface, writing at an arbitrary bit position of the zeroed member buffer: words are OR-ed in because the
+// first and the last one are shared with the neighbouring records
+struct BzDirect {
+    uint32_t *w;
+    uint32_t acc, nb;
+    bool bad;
+    __device__ __forceinline__ void init(uint32_t *buf, uint32_t bitpos) { w = buf + (bitpos >> 5), nb = bitpos & 31u, acc = 0, bad = false; }
+    __device__ __forceinline__ void put(uint32_t v, uint32_t n) {
+        acc |= v << nb;
+        const uint32_t room = 32 - nb;
+        nb += n;
+        if (nb >= 32) {
+            atomicOr(w, acc);
+            ++w;
+            nb -= 32;
+            acc = __funnelshift_rc(v, 0u, room);
+        }
+    }
+    __device__ __forceinline__ void finish() {
+        if (nb) atomicOr(w, acc);
+    }
+};
+
+template <class Wr>
+__device__ __forceinline__ void bz_put_literals(const BzSmem &S, Wr &bw, uint32_t a, uint32_t b) {
     uint32_t j = a;
 #pragma unroll 4
     for (; j + 2 <= b; j += 2) {  // two literals (<= 24 bits) per put
@@ -116,7 +147,8 @@ __device__ __forceinline__ void bz_put_literals(const BzSmem &S, BzWriter &bw, u
     }
 }
 // One match token (length 3..258, distance 1..32768)
-__device__ __forceinline__ void bz_put_match(const BzSmem &S, BzWriter &bw, uint32_t len, uint32_t dist) {
+template <class Wr>
+__device__ __forceinline__ void bz_put_match(const BzSmem &S, Wr &bw, uint32_t len, uint32_t dist) {
     uint32_t sym, eb, ev;
     const uint32_t l = len - 3;
     if (len == 258) {
@@ -145,13 +177,35 @@ __device__ __forceinline__ void bz_put_match(const BzSmem &S, BzWriter &bw, uint
     bw.put((e2 & 0xffffu) | (dev << (e2 >> 16)), (e2 >> 16) + deb);
 }
 // A match longer than 258 is cut into pieces of 3..258 (scripts/bgzf_table.py:split_match)
-__device__ __forceinline__ void bz_put_long_match(const BzSmem &S, BzWriter &bw, uint32_t total, uint32_t dist) {
+template <class Wr>
+__device__ __forceinline__ void bz_put_long_match(const BzSmem &S, Wr &bw, uint32_t total, uint32_t dist) {
     uint32_t rem = total;
     while (rem) {
         uint32_t take = min(BZ_MAX_MATCH, rem);
         if (rem - take > 0 && rem - take < 3) take = rem - 3;
         bz_put_match(S, bw, take, dist);
         rem -= take;
+    }
+}
+
+// The tokens of record r, in stream order, given the choices of pass 2b (scripts/bgzf_table.py:tokenize).
+template <class Wr>
+__device__ __forceinline__ void bz_record_tokens(const BzSmem &S, uint32_t r, uint32_t choice, Wr &bw) {
+    const uint32_t h0 = S.ls[4 * r], s0 = S.ls[4 * r + 1], p0 = S.ls[4 * r + 2], q0 = S.ls[4 * r + 3], e0 = S.ls[4 * r + 4];
+    const uint32_t P = choice & 0x1ffu, Sx = (choice >> 9) & 0x1ffu, same = (choice >> 18) & 1u, qchar = (choice >> 19) & 0xffu;
+    if (P) bz_put_match(S, bw, P, h0 - S.ls[4 * r - 4]);
+    bz_put_literals(S, bw, h0 + P, s0 - Sx);
+    if (Sx) bz_put_match(S, bw, Sx, s0 - S.ls[4 * r - 3]);
+    bz_put_literals(S, bw, s0, p0);
+    if (same) {
+        bz_put_long_match(S, bw, e0 - p0, p0 - S.ls[4 * r - 2]);
+    } else {
+        bz_put_literals(S, bw, p0, q0);
+        const uint32_t eq = S.ll[qchar], en = S.ll[10];
+        if (!(eq >> 16) || !(en >> 16)) bw.bad = true;
+        bw.put(eq & 0xffffu, eq >> 16);
+        bz_put_long_match(S, bw, e0 - 1 - q0 - 1, 1);
+        bw.put(en & 0xffffu, en >> 16);
     }
 }
 
@@ -269,6 +323,7 @@ __device__ __forceinline__ uint32_t bz_member(const BgzfArgs &a, BzSmem S, const
     const uint32_t n_lines = __shfl_sync(FULL, inc, 31);
     const uint32_t n_rec = n_lines >> 2;
     bool ok = may_code && n >= 8 && (n_lines & 3) == 0 && n_rec <= a.max_records && in[n - 1] == 10;
+    bool staged = true;
     uint32_t total_bits = 0;
     if (ok) {
         uint32_t before = inc - nl;
@@ -331,29 +386,33 @@ __device__ __forceinline__ uint32_t bz_member(const BgzfArgs &a, BzSmem S, const
             if (r < n_rec) S.rec2[r] = choice | (qc_of(r) & 0x1feu) << 18;  // the run character in bits 19..26
         }
         __syncwarp();
-        // pass 2c: tokens of the lane's records, packed into the words of their own quality lines
-        for (uint32_t r = lane; r < n_rec && !bad; r += 32) {
-            const uint32_t h0 = S.ls[4 * r], s0 = S.ls[4 * r + 1], p0 = S.ls[4 * r + 2], q0 = S.ls[4 * r + 3], e0 = S.ls[4 * r + 4];
+        // pass 2c: tokens of the lane's records.  Staged mode packs them into the words of the record's own quality
+        // line (no sizing pass); when a quality line looks too short for that (short reads), direct mode sizes the
+        // records first and writes them at their final positions after the scan.
+        for (uint32_t r = lane; r < n_rec; r += 32) {
             const uint32_t choice = S.rec2[r];
-            const uint32_t P = choice & 0x1ffu, Sx = (choice >> 9) & 0x1ffu, same = (choice >> 18) & 1u, qchar = (choice >> 19) & 0xffu;
-            BzWriter bw;
-            bw.init(S.in_w + ((phase + q0 + 3) >> 2), S.in_w + ((phase + e0 - 1) >> 2));
-            if (P) bz_put_match(S, bw, P, h0 - S.ls[4 * r - 4]);
-            bz_put_literals(S, bw, h0 + P, s0 - Sx);
-            if (Sx) bz_put_match(S, bw, Sx, s0 - S.ls[4 * r - 3]);
-            bz_put_literals(S, bw, s0, p0);
-            if (same) {
-                bz_put_long_match(S, bw, e0 - p0, p0 - S.ls[4 * r - 2]);
+            const uint32_t h0 = S.ls[4 * r], s0 = S.ls[4 * r + 1], p0 = S.ls[4 * r + 2], q0 = S.ls[4 * r + 3], e0 = S.ls[4 * r + 4];
+            const uint32_t lits = (s0 - h0) - (choice & 0x1ffu) - ((choice >> 9) & 0x1ffu);
+            const uint32_t est = 8u * lits + 3u * (p0 - s0) + 128u;   // digits cost <= 8 bits, bases <= 3, three matches
+            const int cap = 32 * ((int)((phase + e0 - 1) >> 2) - (int)((phase + q0 + 3) >> 2));
+            if ((int)est > cap) staged = false;
+        }
+        staged = !__any_sync(FULL, !staged);
+        for (uint32_t r = lane; r < n_rec && !bad; r += 32) {
+            const uint32_t choice = S.rec2[r];
+            if (staged) {
+                BzWriter bw;
+                bw.init(S.in_w + ((phase + S.ls[4 * r + 3] + 3) >> 2), S.in_w + ((phase + S.ls[4 * r + 4] - 1) >> 2));
+                bz_record_tokens(S, r, choice, bw);
+                S.rec[r] = bw.finish();
+                bad |= bw.bad;
             } else {
-                bz_put_literals(S, bw, p0, q0);
-                const uint32_t eq = S.ll[qchar], en = S.ll[10];
-                if (!(eq >> 16) || !(en >> 16)) bw.bad = true;
-                bw.put(eq & 0xffffu, eq >> 16);
-                bz_put_long_match(S, bw, e0 - 1 - q0 - 1, 1);
-                bw.put(en & 0xffffu, en >> 16);
+                BzCounter cw;
+                cw.bits = 0, cw.bad = false;
+                bz_record_tokens(S, r, choice, cw);
+                S.rec[r] = cw.bits;
+                bad |= cw.bad;
             }
-            S.rec[r] = bw.finish();
-            bad |= bw.bad;
         }
         ok = !__any_sync(FULL, bad);
     }
@@ -372,7 +431,10 @@ __device__ __forceinline__ uint32_t bz_member(const BgzfArgs &a, BzSmem S, const
                 const uint32_t y = __shfl_up_sync(FULL, x, o);
                 if ((int)lane >= o) x += y;
             }
-            if (r < n_rec) S.rec2[r] = carry + x - v;
+            if (r < n_rec) {
+                if (staged) S.rec2[r] = carry + x - v;  // staged: rec = bits, rec2 = position
+                else S.rec[r] = carry + x - v;          // direct: rec = position, rec2 keeps the token choice
+            }
             carry += __shfl_sync(FULL, x, 31);
         }
         total_bits = carry;
@@ -384,7 +446,13 @@ __device__ __forceinline__ uint32_t bz_member(const BgzfArgs &a, BzSmem S, const
             const uint32_t *hdr = a.tab + BZ_T_HDR;
             for (uint32_t i = lane; i * 32 < a.hdr_bits; i += 32)
                 bz_or_bits(S.out, BZ_GZ_HDR * 8 + i * 32, hdr[i], min(32u, a.hdr_bits - i * 32));
-            for (uint32_t r = lane; r < n_rec; r += 32) {
+            for (uint32_t r = lane; r < n_rec && !staged; r += 32) {
+                BzDirect dw;
+                dw.init(S.out, S.rec[r]);
+                bz_record_tokens(S, r, S.rec2[r], dw);
+                dw.finish();
+            }
+            for (uint32_t r = lane; r < n_rec && staged; r += 32) {
                 const uint32_t *src = S.in_w + ((phase + S.ls[4 * r + 3] + 3) >> 2);
                 const uint32_t d0 = S.rec2[r], nb = S.rec[r];
                 for (uint32_t b = 0; b < nb; b += 32) {
