@@ -206,3 +206,81 @@ def test_config5_full_size_sharded():
         assert mols["barcode_index"][0] == place.first_molecule and mols["first_read"][0] == place.first_pair
         sing = sim.molecules(0, 500000)["n_frags"] == 1
         assert abs(sing.mean() - 0.1) < 0.01
+
+
+def test_config4_full_size_vcf_sample_tellseq():
+    """BASELINE configs[3], one of its 8 samples (one sample per GPU): 100 Mbp master contig, 100 k SNPs and 10 k
+    indels (1-20 bp, VCF-anchored), genotypes Bernoulli(0.3) per haplotype, TELLseq, 20x.  The two haplotypes built on
+    the device equal a numpy construction (SNPs painted, indel pieces spliced), reads_required is inherited from the
+    master (ProcessVariants.jl:157-185), and sampled records are windows of those haplotypes."""
+    import mimick_b200 as M
+    HDR["tellseq"] = re.compile(rb"^@(\S+?):(\d+)\|(\d+):(\d+)\|(\d+):(\d+):([ATGC]{18}) ([12]):N:0:ATGACA$")
+    rng = np.random.default_rng(1004)
+    n = 100_000_000
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    master = acgt[rng.integers(0, 4, size=n)]
+    n_var = 110_000
+    cells = np.sort(rng.choice(n // 64 - 2, size=n_var, replace=False)) + 1
+    pos = cells.astype(np.int64) * 64 + rng.integers(0, 16, size=n_var)          # 1-based, >= 48 apart
+    is_indel = np.zeros(n_var, dtype=bool)
+    is_indel[rng.choice(n_var, size=10_000, replace=False)] = True
+    ent_pos, ent_type, ent_reflen, ent_alt, ent_hap = [], [], [], [], []
+    per_hap = {1: [], 2: []}
+    snp_pos = {1: [], 2: []}
+    snp_alt = {1: [], 2: []}
+    for i in range(n_var):
+        p = int(pos[i])
+        ref = master[p - 1]
+        if is_indel[i]:
+            k = int(rng.integers(1, 21))
+            if rng.random() < 0.5:   # deletion: REF = k + 1 bases, ALT = the anchor base
+                ref_len, alt = k + 1, bytes([ref])
+            else:                    # insertion: REF = anchor, ALT = anchor + k bases
+                ref_len, alt = 1, bytes([ref]) + acgt[rng.integers(0, 4, size=k)].tobytes()
+            typ = 1
+        else:
+            ref_len, alt, typ = 1, bytes([acgt[(np.searchsorted(acgt, ref) + int(rng.integers(1, 4))) % 4]]), 0
+        for hap in (1, 2):
+            if rng.random() < 0.3:
+                ent_pos.append(p), ent_type.append(typ), ent_reflen.append(ref_len), ent_alt.append(alt), ent_hap.append(hap)
+                if typ:
+                    per_hap[hap].append((p, ref_len, alt))
+                else:
+                    snp_pos[hap].append(p - 1), snp_alt[hap].append(alt[0])
+    want = {}
+    for hap in (1, 2):
+        seq = master.copy()
+        seq[np.array(snp_pos[hap], dtype=np.int64)] = np.array(snp_alt[hap], dtype=np.uint8)
+        raw = seq.tobytes()
+        out, prev = [], 0
+        for p, ref_len, alt in per_hap[hap]:
+            out.append(raw[prev:p - 1])
+            out.append(alt)
+            prev = p - 1 + ref_len
+        out.append(raw[prev:])
+        want[hap] = b"".join(out)
+    simkw = dict(coverage=20, n_molecules=2, mol_coverage=0.2, mol_length=80000, insert_length=500, insert_stdev=50,
+                 read_length=[150, 150], singletons=0.0, attempts=300)
+    with M.Simulator("tellseq", seed=42, device=0, max_chunk_bytes=1024 << 20, **simkw) as sim:
+        sim.add_contig("chr1", master.tobytes(), 1)
+        sim.set_sample_variants(3, 2, [0], np.zeros(len(ent_pos), dtype=np.int32), ent_pos, ent_type, ent_reflen, ent_alt, ent_hap)
+        schemas = sim.schemas()
+        assert [s["reads_required"] for s in schemas] == [6_666_666, 6_666_666] and [s["haplotype"] for s in schemas] == [1, 2]
+        for i, hap in enumerate((1, 2)):
+            got = sim.schema_bases(i)
+            assert len(got) == len(want[hap]) == schemas[i]["length"]
+            assert got == want[hap], f"haplotype {hap} differs from the numpy construction"
+        plan = sim.plan()
+        place = sim.place()
+        assert 13_333_332 <= plan.n_pairs < 13_343_332 and plan.n_epochs == 2
+        ch = sim.emit_chunk()
+        r1, r2 = sim.copy_chunk(ch)
+        r1 = r1.tobytes()[: 1 << 20]
+        r1 = r1[: r1.rfind(b"\n@") + 1]
+        nrec = r1.count(b"\n") // 4
+        r2b = r2.tobytes()
+        cut = 0
+        for _ in range(nrec * 4):
+            cut = r2b.index(b"\n", cut) + 1
+        nchk, recs = check_chunk("tellseq", r1, r2b[:cut], {("chr1", 1): want[1], ("chr1", 2): want[2]}, 150, 150)
+        assert nchk > 1000 and {k[0][1] for k in recs} == {b"1", b"2"}
