@@ -56,21 +56,39 @@ __device__ __forceinline__ uint32_t comp4(uint32_t k) { return (__brev(k) >> 28)
 // ------------------------------------------------------------------------------------------
 // FASTA symbols
 // ------------------------------------------------------------------------------------------
+// all four bytes of w are upper-case A, C, G or T
+__device__ __forceinline__ bool word_is_acgt(uint32_t w) {
+    const uint32_t m = __vcmpeq4(w, 0x41414141u) | __vcmpeq4(w, 0x43434343u) | __vcmpeq4(w, 0x47474747u) | __vcmpeq4(w, 0x54545454u);
+    return m == 0xffffffffu;
+}
+__device__ __forceinline__ void normalize_one(char *bases, int64_t i, unsigned long long &nN, unsigned long long &nX,
+                                              unsigned long long &bad) {
+    uint32_t c = (uint8_t)bases[i];
+    uint32_t k = (c == '-') ? 0u : ascii_to_code4(c);
+    if (k == 0xffu || ((c & 0xdfu) < 'A' && c != '-')) {
+        if ((unsigned long long)i < bad) bad = (unsigned long long)i;
+        return;
+    }
+    bases[i] = code4_to_ascii(k);
+    nN += (k == 15u);
+    nX += !(k == 1u || k == 2u || k == 4u || k == 8u);
+}
+// Upper-cases, validates and counts.  16 symbols per thread and iteration; runs that are already upper-case ACGT
+// (nearly all of a real genome) are only read.  `bases` is 16-byte aligned.
 __global__ void k_normalize(char *bases, int64_t len, ContigStats *stats) {
+    const int64_t n16 = len >> 4;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     unsigned long long nN = 0, nX = 0, bad = ~0ull;
-    for (; i < len; i += stride) {
-        uint32_t c = (uint8_t)bases[i];
-        uint32_t k = (c == '-') ? 0u : ascii_to_code4(c);
-        if (k == 0xffu || ((c & 0xdfu) < 'A' && c != '-')) {
-            if ((unsigned long long)i < bad) bad = (unsigned long long)i;
-            continue;
-        }
-        char u = code4_to_ascii(k);
-        bases[i] = u;
-        nN += (k == 15u);
-        nX += !(k == 1u || k == 2u || k == 4u || k == 8u);
+    const uint4 *v = reinterpret_cast<const uint4 *>(bases);
+    for (; i < n16; i += stride) {
+        const uint4 x = v[i];
+        if (word_is_acgt(x.x) && word_is_acgt(x.y) && word_is_acgt(x.z) && word_is_acgt(x.w)) continue;
+        for (int j = 0; j < 16; ++j) normalize_one(bases, 16 * i + j, nN, nX, bad);
+    }
+    {   // the last len % 16 symbols
+        const int64_t t = (n16 << 4) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (t < len) normalize_one(bases, t, nN, nX, bad);
     }
     for (int o = 16; o; o >>= 1) {
         nN += __shfl_down_sync(0xffffffffu, nN, o);
@@ -168,6 +186,37 @@ __global__ void k_pack_pieces(const char *__restrict__ master, const char *__res
     if (bad) atomicMin(&stats->first_bad, (unsigned long long)o);
 }
 
+// One unmodified contig, 2 bits per base: 16 upper-case ACGT symbols (one 16-byte load) -> one word.
+// 'A' 0x41, 'C' 0x43, 'G' 0x47, 'T' 0x54: t = (c >> 1) & 3 gives 0, 1, 3, 2 and t ^ (t >> 1) the codes 0, 1, 2, 3;
+// the multiplication gathers the four 2-bit fields of a word into its top byte.
+__device__ __forceinline__ uint32_t pack4_acgt(uint32_t w) {
+    const uint32_t t = (w >> 1) & 0x03030303u;
+    const uint32_t c = t ^ ((t >> 1) & 0x01010101u);
+    return (c * 0x01041040u) >> 24;
+}
+__global__ void k_pack_plain2(const char *__restrict__ ascii, int64_t len, uint32_t *__restrict__ words, ContigStats *stats) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t o = w * 16;
+    if (o >= len) return;
+    if (o + 16 <= len) {
+        const uint4 x = reinterpret_cast<const uint4 *>(ascii)[w];
+        if (!(word_is_acgt(x.x) && word_is_acgt(x.y) && word_is_acgt(x.z) && word_is_acgt(x.w)))
+            atomicMin(&stats->first_bad, (unsigned long long)o);
+        words[w] = pack4_acgt(x.x) | (pack4_acgt(x.y) << 8) | (pack4_acgt(x.z) << 16) | (pack4_acgt(x.w) << 24);
+        return;
+    }
+    uint32_t word = 0;
+    bool bad = false;
+    for (int j = 0; o + j < len; ++j) {
+        const uint32_t c = (uint8_t)ascii[o + j];
+        const uint32_t k4 = ascii_to_code4(c);
+        bad |= !(k4 == 1u || k4 == 2u || k4 == 4u || k4 == 8u);
+        word |= code4_to_code2(k4) << (2 * j);
+    }
+    words[w] = word;
+    if (bad) atomicMin(&stats->first_bad, (unsigned long long)o);
+}
+
 template <int BPB>
 __global__ void k_unpack(const uint32_t *__restrict__ words, int64_t len, char *__restrict__ out) {
     constexpr int PER = 32 / BPB;
@@ -207,6 +256,12 @@ void pack_pieces(const char *master, const char *alt, const int64_t *dst, const 
         LAUNCH((k_pack_pieces<2>), g, 256, 0, s, master, alt, dst, src, kind, n_pieces, out_len, words, st);
     else
         LAUNCH((k_pack_pieces<4>), g, 256, 0, s, master, alt, dst, src, kind, n_pieces, out_len, words, st);
+}
+// one whole contig as it is (upper-case ACGT only), 2 bits per base; `ascii` 16-byte aligned
+void pack_plain2(const char *ascii, int64_t len, uint32_t *words, ContigStats *st, cudaStream_t s) {
+    if (len <= 0) return;
+    const int64_t nw = (len + 15) / 16;
+    LAUNCH(k_pack_plain2, (unsigned)((nw + 255) / 256), 256, 0, s, ascii, len, words, st);
 }
 void unpack(const uint32_t *words, int64_t len, int bpb, char *out, cudaStream_t s) {
     if (len <= 0) return;

@@ -628,8 +628,11 @@ static int32_t finalize_single(mmk_ctx *ctx) {
     CU(cudaMemsetAsync(kind.p, 0, 1, ctx->st));
     for (size_t i = 0; i < ctx->contigs.size(); ++i) {
         Contig &c = ctx->contigs[i];
-        pack_pieces(c.d_ascii, c.d_ascii, piece.p, piece.p + 1, kind.p, 1, c.len, ctx->d_hap.p + ctx->schemas[i].word_off,
-                    ctx->bpb, ctx->d_stats, ctx->st);
+        if (ctx->bpb == 2)  // whole contigs of upper-case ACGT: 16 symbols per thread, no piece search
+            pack_plain2(c.d_ascii, c.len, ctx->d_hap.p + ctx->schemas[i].word_off, ctx->d_stats, ctx->st);
+        else
+            pack_pieces(c.d_ascii, c.d_ascii, piece.p, piece.p + 1, kind.p, 1, c.len, ctx->d_hap.p + ctx->schemas[i].word_off,
+                        ctx->bpb, ctx->d_stats, ctx->st);
     }
     CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, sizeof zero, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));

@@ -113,6 +113,7 @@ void count_bases(const char *d_bases, int64_t len, ContigStats *d_stats, cudaStr
 void scatter_snps(char *d_bases, const int64_t *d_pos, const char *d_alt, int64_t n, cudaStream_t st);
 // segmented gather + pack: output base o comes from piece p = last piece with dst[p] <= o:
 // src_kind 0 → d_master[src[p] + (o - dst[p])], 1 → d_alt[src[p] + (o - dst[p])]
+void pack_plain2(const char *ascii, int64_t len, uint32_t *words, ContigStats *st, cudaStream_t s);
 void pack_pieces(const char *d_master, const char *d_alt, const int64_t *d_dst, const int64_t *d_src,
                  const uint8_t *d_kind, int32_t n_pieces, int64_t out_len, uint32_t *d_words, int bpb,
                  ContigStats *d_stats, cudaStream_t st);
