@@ -1,14 +1,17 @@
 // mmk_device.cu — sm_100a kernels of the simulation core and their launchers.
 //
-// Kernel inventory (DESIGN.md §4 has the data layout and the roofline of each):
-//   k_normalize / k_mask_n / k_count      FASTA symbols → validated upper-case, N masking   ProcessFASTA.jl:29-36,52-57
-//   k_scatter_snps / k_pack_pieces        haplotype construction: SNP scatter + segmented    ProcessVariants.jl:143-176
-//                                         gather of indel pieces, packed to 2 or 4 bits/base
-//   k_group_nmol / k_plan_groups          barcode groups → molecules (target, size, #inserts) Main.jl:44-51, Breakpoints.jl:149-196
-//   k_hist / k_cross_* / k_cut / k_sums   coverage tracker + pruning point of a batch          Main.jl:54,58
-//   k_place                               insert sizes, start, gap chain, header text          Breakpoints.jl:205-251,21-35
-//   k_tile_sums                           record lengths per tile → byte offsets (with scan)   FormatFASTQ.jl
-//   k_emit                                extraction, reverse complement, FASTQ text           Breakpoints.jl:95-140, FormatFASTQ.jl
+// Kernel inventory (DESIGN.md §5 describes each and the roofline that bounds it):
+//   k_normalize / k_mask_n / k_count        FASTA symbols → validated upper-case, N masking        ProcessFASTA.jl:29-36,52-57
+//   k_scatter_snps / k_pack_pieces /        haplotype construction: SNP scatter + segmented gather  ProcessVariants.jl:143-176
+//   k_pack_plain2                           of indel pieces, packed to 2 or 4 bits per base
+//   k_group_nmol / k_fill_slots             group table: molecules per barcode group, their labels  Common.jl:89-91, Main.jl:44-47
+//   k_plan_molecules                        target, size and insert count of every molecule         Main.jl:47, Breakpoints.jl:149-196
+//   k_plan_cut / k_plan_sums                coverage tracker + pruning point of a batch             Main.jl:54,58
+//   k_insert_draws / k_place_chain /        insert sizes, start, gap chain, header text             Breakpoints.jl:205-251,21-35
+//   k_mol_text
+//   k_tile_prepare / k_chunk_table          record lengths per tile → byte offsets, chunk bounds     FormatFASTQ.jl
+//   k_emit (mmk_emit.cuh)                   extraction, reverse complement, FASTQ text              Breakpoints.jl:95-140, FormatFASTQ.jl
+//   k_bgzf / k_bgzf_compact (mmk_bgzf.cuh)  FASTQ text → BGZF members                               Main.jl:42-43,111-112
 #include <cstddef>
 #include <cstdio>
 
@@ -784,7 +787,6 @@ __device__ __forceinline__ void place_chain_one(const SimConst &sc, const Schema
     const uint32_t n = S.len;
     PairTmp *tp = tmp + (ro - pair_lo);
     uint2 *in = ins + ro;
-    NoRec rec;
     uint64_t isum = acc_i[i];
     bool over;
     {
