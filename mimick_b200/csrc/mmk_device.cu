@@ -13,6 +13,7 @@
 //   k_emit (mmk_emit.cuh)                   extraction, reverse complement, FASTQ text              Breakpoints.jl:95-140, FormatFASTQ.jl
 //   k_bgzf / k_bgzf_compact (mmk_bgzf.cuh)  FASTQ text → BGZF members                               Main.jl:42-43,111-112
 #include <cstddef>
+#include <cstdlib>
 #include <cstdio>
 
 #include "mmk_internal.h"
@@ -1039,6 +1040,7 @@ void emit(const EmitArgs &a, cudaStream_t st) {
     int dev = 0;
     cudaGetDevice(&dev);
     size_t smem = 2 * (size_t)a.stage_cap;
+    if (const char *e = getenv("MMK_EMIT_PAD")) smem += (size_t)atoi(e);  // occupancy probe (profiling only)
     if (!attr_set[dev & 63]) {
         cudaFuncSetAttribute(k_emit<2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         cudaFuncSetAttribute(k_emit<4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
