@@ -728,39 +728,53 @@ extern "C" int32_t mmk_set_sample_variants(mmk_ctx *ctx, uint32_t sample_stream,
                 b.snp_pos.push_back(kv.first);
                 b.snp_alt.push_back(kv.second);
             }
-            // spliceinto!(seq, pos:pos+len(ref)-1, alt) in REVERSE file order on the current sequence
-            std::vector<Piece> &pc = b.pieces;
-            pc.push_back(Piece{0, 0, mc.len});
+            // spliceinto!(seq, pos:pos+len(ref)-1, alt) in REVERSE file order on the current sequence.
+            // The list is kept back to front (rev.back() is the FIRST piece).  A VCF is sorted by position, so in
+            // reverse order nearly every splice falls inside the still untouched master prefix [0, L0): that is three
+            // pushes.  Anything else (unsorted or overlapping records) replays the splice on the whole list.
+            std::vector<Piece> rev;
+            rev.push_back(Piece{0, 0, mc.len});
             int64_t cur_len = mc.len;
             for (size_t r = indels.size(); r-- > 0;) {
                 int64_t i = indels[r];
                 int64_t a = pos[i] - 1, e = a + ref_len[i];  // [a, e) 0-based in current coordinates
                 if (a < 0 || e > cur_len || ref_len[i] < 0) return fail(ctx, MMK_ERR_BOUNDS, "indel at %lld outside contig %s", (long long)pos[i], mc.name.c_str());
-                std::vector<Piece> np;
-                np.reserve(pc.size() + 2);
-                int64_t o = 0;
-                bool inserted = false;
-                for (const Piece &p : pc) {
-                    int64_t lo = o, hi = o + p.len;
-                    o = hi;
-                    if (hi <= a) {  // entirely before
-                        np.push_back(p);
-                        continue;
+                const Piece head = rev.back();
+                if (head.kind == 0 && head.src == 0 && e <= head.len) {
+                    rev.pop_back();
+                    if (head.len > e) rev.push_back(Piece{0, e, head.len - e});
+                    if (alt_len[i] > 0) rev.push_back(Piece{1, alt_off[i], alt_len[i]});
+                    rev.push_back(Piece{0, 0, a});  // possibly empty: keeps the "untouched prefix first" form
+                } else {
+                    std::vector<Piece> np;
+                    np.reserve(rev.size() + 2);
+                    int64_t o = 0;
+                    bool inserted = false;
+                    for (size_t k = rev.size(); k-- > 0;) {
+                        const Piece &p = rev[k];
+                        int64_t lo = o, hi = o + p.len;
+                        o = hi;
+                        if (hi <= a) {  // entirely before
+                            np.push_back(p);
+                            continue;
+                        }
+                        if (lo < a) np.push_back(Piece{p.kind, p.src, a - lo});  // head survives
+                        if (!inserted) {
+                            if (alt_len[i] > 0) np.push_back(Piece{1, alt_off[i], alt_len[i]});
+                            inserted = true;
+                        }
+                        if (hi > e) {  // tail survives
+                            int64_t cut = std::max(e, lo) - lo;
+                            np.push_back(Piece{p.kind, p.src + cut, p.len - cut});
+                        }
                     }
-                    if (lo < a) np.push_back(Piece{p.kind, p.src, a - lo});  // head survives
-                    if (!inserted) {
-                        if (alt_len[i] > 0) np.push_back(Piece{1, alt_off[i], alt_len[i]});
-                        inserted = true;
-                    }
-                    if (hi > e) {  // tail survives
-                        int64_t cut = std::max(e, lo) - lo;
-                        np.push_back(Piece{p.kind, p.src + cut, p.len - cut});
-                    }
+                    if (!inserted && alt_len[i] > 0) np.push_back(Piece{1, alt_off[i], alt_len[i]});  // a == cur_len
+                    rev.assign(np.rbegin(), np.rend());
                 }
-                if (!inserted && alt_len[i] > 0) np.push_back(Piece{1, alt_off[i], alt_len[i]});  // a == cur_len
-                pc.swap(np);
                 cur_len += alt_len[i] - ref_len[i];
             }
+            std::vector<Piece> &pc = b.pieces;
+            pc.assign(rev.rbegin(), rev.rend());
             b.out_len = cur_len;
             if (cur_len >= (1ll << 31)) return fail(ctx, MMK_ERR_UNSUPPORTED, "haplotype has >= 2^31 bases");
             Schema s;
