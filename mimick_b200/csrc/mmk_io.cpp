@@ -111,7 +111,8 @@ int read_vcf(const char *path, VcfData &v, std::string &err) {
         return MMK_ERR_IO;
     }
     std::string line;
-    std::vector<std::string> f, keys, sub;
+    std::vector<std::string> f;
+    std::vector<const char *> fb, fe;
     v.ploidy = 0;
     while (lr.next(line)) {
         if (line.empty()) continue;
@@ -130,54 +131,92 @@ int read_vcf(const char *path, VcfData &v, std::string &err) {
             }
             continue;
         }
-        split(line, '\t', f);
-        if (f.size() < 10 || f.size() != 9 + v.samples.size()) {
+        // tab-separated fields as (begin, end) views into the line: no per-field allocations
+        const char *L0 = line.data(), *Lend = L0 + line.size();
+        fb.clear();
+        fe.clear();
+        for (const char *p = L0;;) {
+            const char *t = (const char *)memchr(p, '\t', (size_t)(Lend - p));
+            fb.push_back(p);
+            fe.push_back(t ? t : Lend);
+            if (!t) break;
+            p = t + 1;
+        }
+        if (fb.size() < 10 || fb.size() != 9 + v.samples.size()) {
             err = "malformed VCF record (column count)";
             return MMK_ERR_VCF;
         }
         VcfRecord r;
-        r.chrom = f[0];
-        r.pos = strtoll(f[1].c_str(), nullptr, 10);
-        r.ref = f[3];
-        split(f[4], ',', r.alts);
+        r.chrom.assign(fb[0], fe[0]);
+        const std::string pos_text(fb[1], fe[1]);
+        r.pos = strtoll(pos_text.c_str(), nullptr, 10);
+        r.ref.assign(fb[3], fe[3]);
+        {
+            const std::string alt_text(fb[4], fe[4]);
+            split(alt_text, ',', r.alts);
+        }
         // vartype, ProcessVariants.jl:61-69
         bool snp = r.ref.size() == 1;
         for (auto &a : r.alts) snp = snp && a.size() == 1;
         r.type = snp ? 0 : 1;
-        split(f[8], ':', keys);
         int gi = -1;
-        for (size_t i = 0; i < keys.size(); ++i)
-            if (keys[i] == "GT") gi = (int)i;
+        {   // index of GT among the ':'-separated FORMAT keys
+            int k = 0;
+            for (const char *p = fb[8];; ++k) {
+                const char *t = (const char *)memchr(p, ':', (size_t)(fe[8] - p));
+                const char *e = t ? t : fe[8];
+                if (e - p == 2 && p[0] == 'G' && p[1] == 'T') gi = k;
+                if (!t) break;
+                p = t + 1;
+            }
+        }
         if (gi < 0) {
             err = "VCF record without GT";
             return MMK_ERR_VCF;
         }
+        r.alleles.reserve(v.samples.size() * (v.ploidy > 0 ? (size_t)v.ploidy : 2u));
+        r.ploidy_of.reserve(v.samples.size());
         for (size_t s = 0; s < v.samples.size(); ++s) {
-            split(f[9 + s], ':', sub);
-            if ((size_t)gi >= sub.size()) {
+            // the gi-th ':'-separated subfield of the sample column
+            const char *p = fb[9 + s], *fend = fe[9 + s];
+            int k = 0;
+            while (k < gi) {
+                const char *t = (const char *)memchr(p, ':', (size_t)(fend - p));
+                if (!t) break;
+                p = t + 1;
+                ++k;
+            }
+            if (k < gi) {
                 err = "VCF sample field without GT";
                 return MMK_ERR_VCF;
             }
-            const std::string &gt = sub[gi];
+            const char *gend = (const char *)memchr(p, ':', (size_t)(fend - p));
+            if (!gend) gend = fend;
             // split(gt, ['/', '|']) then parse(UInt8, ·) — a missing allele "." is an error there too
             int n = 0;
-            size_t b = 0;
-            for (;;) {
-                size_t e = gt.find_first_of("/|", b);
-                std::string tok = gt.substr(b, e == std::string::npos ? std::string::npos : e - b);
-                if (tok.empty() || tok.find_first_not_of("0123456789") != std::string::npos) {
-                    err = "cannot parse genotype '" + gt + "' at " + r.chrom + ":" + f[1];
+            for (const char *q = p;;) {
+                const char *e = q;
+                long a = 0;
+                while (e < gend && *e >= '0' && *e <= '9') {
+                    a = a < 100000 ? a * 10 + (*e - '0') : a;
+                    ++e;
+                }
+                if (e == q || (e < gend && *e != '/' && *e != '|')) {
+                    err = "cannot parse genotype '" + std::string(p, gend) + "' at " + r.chrom + ":" + pos_text;
                     return MMK_ERR_VCF;
                 }
-                long a = strtol(tok.c_str(), nullptr, 10);
                 if (a < 0 || a > (long)r.alts.size() || a > 255) {
-                    err = "allele index out of range at " + r.chrom + ":" + f[1];
+                    err = "allele index out of range at " + r.chrom + ":" + pos_text;
                     return MMK_ERR_VCF;
                 }
                 r.alleles.push_back((uint8_t)a);
                 ++n;
-                if (e == std::string::npos) break;
-                b = e + 1;
+                if (e == gend) break;
+                q = e + 1;
+                if (q == gend) {  // trailing separator: an empty allele
+                    err = "cannot parse genotype '" + std::string(p, gend) + "' at " + r.chrom + ":" + pos_text;
+                    return MMK_ERR_VCF;
+                }
             }
             if (v.ploidy == 0) v.ploidy = n;  // get_ploidy_and_contigs: sample 1 of the first record
             if (s == 0 && v.records.empty()) v.ploidy = n;
