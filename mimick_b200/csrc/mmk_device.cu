@@ -950,16 +950,22 @@ __global__ void __launch_bounds__(256) k_place_chain(SimConst sc, const SchemaDe
 
 // one segment: pairs [pair_lo, pair_hi) = the pairs of molecules [m_lo, m_hi)
 size_t place_tmp_bytes(uint64_t max_pairs) { return (size_t)(max_pairs + 1) * sizeof(PairTmp); }
-void place_segment(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint32_t m_lo,
-                   uint32_t m_hi, uint64_t pair_lo, uint64_t pair_hi, const uint64_t *d_read_off_local,
-                   const uint32_t *d_tile_mol0, uint32_t n_tiles, uint32_t tile_pairs, void *d_tmp, uint32_t *d_acc_i,
-                   unsigned long long *d_acc_f, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text,
-                   uint32_t text_stride, unsigned long long *d_err, cudaStream_t st) {
-    if (m_hi <= m_lo) return;
+// st_draws: the flat per-pair draws; st_chain: the per-molecule chain and the header text (the caller orders the two
+// streams with events when they differ: the chain of a segment needs its draws, the draws of segment k + 2 the
+// scratch of segment k)
+void place_segment_draws(const SimConst &sc, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint64_t pair_lo, uint64_t pair_hi,
+                         const uint64_t *d_read_off_local, const uint32_t *d_tile_mol0, uint32_t n_tiles, uint32_t tile_pairs,
+                         void *d_tmp, uint32_t *d_acc_i, unsigned long long *d_acc_f, cudaStream_t st) {
     const uint64_t np = pair_hi - pair_lo;
-    const uint32_t nm = m_hi - m_lo;
     if (np) LAUNCH(k_insert_draws, (unsigned)((np + 255) / 256), 256, 0, st, sc, plan, mol0, n_mol, d_read_off_local, d_tile_mol0,
                    n_tiles, tile_pairs, pair_lo, pair_hi, (PairTmp *)d_tmp, d_acc_i, d_acc_f);
+}
+void place_segment_chain(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t m_lo, uint32_t m_hi,
+                         uint64_t pair_lo, const uint64_t *d_read_off_local, void *d_tmp, uint32_t *d_acc_i,
+                         unsigned long long *d_acc_f, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
+                         unsigned long long *d_err, cudaStream_t st) {
+    if (m_hi <= m_lo) return;
+    const uint32_t nm = m_hi - m_lo;
     LAUNCH(k_place_chain, (nm + PLACE_BLOCK - 1) / PLACE_BLOCK, 256, 0, st, sc, d_sch, plan, mol0, m_lo, m_hi, d_read_off_local,
            pair_lo, (PairTmp *)d_tmp, d_acc_i, d_acc_f, d_ins, d_mol, d_err);
     LAUNCH(k_mol_text, (nm + 127) / 128, 128, 0, st, sc, d_sch, mol0, m_lo, m_hi, d_mol, d_text, text_stride);

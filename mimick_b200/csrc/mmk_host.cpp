@@ -132,7 +132,7 @@ struct mmk_ctx {
     DBuf<uint32_t> d_tile_mol0;
     DBuf<uint4> d_fdesc;
     DBuf<uint8_t> d_tile_flags;
-    DBuf<uint8_t> d_tmp;      // placement scratch: (gap bits, insert length) per pair of one segment
+    DBuf<uint8_t> d_tmp, d_tmp2;  // placement scratch: (gap bits, insert length) per pair of one segment (two alternate)
     DBuf<uint32_t> d_acc_i;   // placement scratch: sum of insert lengths per molecule
     DBuf<unsigned long long> d_acc_f;  // ... and a 2^-16 fixed-point lower bound of their real sum
     uint32_t text_stride = 0, tile_pairs = 64, n_tiles = 0, stage_cap = 0;
@@ -147,6 +147,7 @@ struct mmk_ctx {
     std::vector<uint32_t> chunk_tiles;          // [n_chunks + 1] tile boundaries
     std::vector<uint64_t> chunk_off1, chunk_off2;  // [n_chunks + 1] byte offsets at those boundaries
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_emit[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+    cudaEvent_t ev_draw[2] = {nullptr, nullptr}, ev_chain[2] = {nullptr, nullptr};  // placement: draws / chain per scratch buffer
 
     // BGZF stage
     uint32_t tile_bytes_bound = 0;   // upper bound of one tile's text in one stream
@@ -398,6 +399,8 @@ extern "C" int32_t mmk_create(const mmk_params *p, mmk_ctx **out) {
     for (int i = 0; i < 2; ++i) {
         CU(cudaEventCreateWithFlags(&ctx->ev_emit[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_draw[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_chain[i], cudaEventDisableTiming));
     }
     CU(cudaMalloc((void **)&ctx->d_stats, sizeof(ContigStats)));
     CU(cudaMallocHost((void **)&ctx->h_stats, sizeof(ContigStats)));
@@ -433,6 +436,8 @@ extern "C" void mmk_destroy(mmk_ctx *c) {
     for (int i = 0; i < 2; ++i) {
         if (c->ev_emit[i]) cudaEventDestroy(c->ev_emit[i]);
         if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
+        if (c->ev_draw[i]) cudaEventDestroy(c->ev_draw[i]);
+        if (c->ev_chain[i]) cudaEventDestroy(c->ev_chain[i]);
     }
     if (c->st_copy) cudaStreamDestroy(c->st_copy);
     if (c->st) cudaStreamDestroy(c->st);
@@ -1277,10 +1282,14 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     ctx->n_tiles = (uint32_t)((ctx->s_npairs + ctx->tile_pairs - 1) / ctx->tile_pairs);
     CU(ctx->d_tile_mol0.ensure((size_t)ctx->n_tiles + 1));
     place_prepare(ctx->mol0, (uint32_t)ctx->s_nmol, ctx->d_read_off.p, ctx->d_roff_l.p, ctx->d_tile_mol0.p, ctx->tile_pairs, ctx->st);
-    {   // segments of at most SEG pairs bound the scratch of the flat per-pair draws
-        const uint64_t SEG = 64ull << 20;
+    {   // Segments of at most SEG pairs bound the scratch of the flat per-pair draws.  The draws of segment k + 1
+        // (compute-bound) run on the main stream while the chain of segment k (latency-bound) runs on the second
+        // stream; two scratch buffers alternate.
+        uint64_t SEG = 100ull << 20;  // larger segments have shorter tails in the chain kernel; 100 M pairs = 1.6 GB of scratch each
+        if (const char *e = getenv("MMK_PLACE_SEG_MPAIRS")) SEG = (uint64_t)std::max(1, atoi(e)) << 20;
+        const bool overlap = !(getenv("MMK_PLACE_OVERLAP") && atoi(getenv("MMK_PLACE_OVERLAP")) == 0);
         const int n_seg = (int)std::max<uint64_t>(1, (ctx->s_npairs + SEG - 1) / SEG);
-        if (n_seg > 1023) return fail(ctx, MMK_ERR_UNSUPPORTED, "shard too large: more than 2^36 read pairs");
+        if (n_seg > 1023) return fail(ctx, MMK_ERR_UNSUPPORTED, "shard too large: more than 2^34 read pairs");
         std::vector<uint64_t> sb((size_t)n_seg + 1), sp((size_t)n_seg + 1);
         if (ctx->s_nmol) {
             shard_bounds(ctx->d_roff_l.p, ctx->s_nmol, ctx->s_npairs, n_seg, d_bounds.p, ctx->st);
@@ -1293,15 +1302,36 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
             CU(cudaStreamSynchronize(ctx->st));
             for (int k = 0; k < n_seg; ++k) max_pairs = std::max(max_pairs, sp[k + 1] - sp[k]);
             CU(ctx->d_tmp.ensure(place_tmp_bytes(max_pairs)));
+            if (overlap && n_seg > 1) CU(ctx->d_tmp2.ensure(place_tmp_bytes(max_pairs)));
             CU(ctx->d_acc_i.ensure(ctx->s_nmol + 1));
             CU(ctx->d_acc_f.ensure(ctx->s_nmol + 1));
             CU(cudaMemsetAsync(ctx->d_acc_i.p, 0, (ctx->s_nmol + 1) * 4, ctx->st));
             CU(cudaMemsetAsync(ctx->d_acc_f.p, 0, (ctx->s_nmol + 1) * 8, ctx->st));
-            for (int k = 0; k < n_seg; ++k)
-                place_segment(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->mol0, (uint32_t)ctx->s_nmol, (uint32_t)sb[k],
-                              (uint32_t)sb[k + 1], sp[k], sp[k + 1], ctx->d_roff_l.p, ctx->d_tile_mol0.p, ctx->n_tiles,
-                              ctx->tile_pairs, ctx->d_tmp.p, ctx->d_acc_i.p, ctx->d_acc_f.p,
-                              ctx->d_ins.p, ctx->d_mol.p, ctx->d_text.p, ctx->text_stride, d_err.p, ctx->st);
+            const bool two = overlap && n_seg > 1;
+            cudaStream_t s_draw = ctx->st, s_chain = two ? ctx->st_copy : ctx->st;
+            if (two) {  // the second stream starts after everything queued so far (error slot, prepare kernels)
+                CU(cudaEventRecord(ctx->ev_draw[0], ctx->st));
+                CU(cudaStreamWaitEvent(s_chain, ctx->ev_draw[0], 0));
+            }
+            for (int k = 0; k < n_seg; ++k) {
+                const int b = two ? (k & 1) : 0;
+                void *tmp = b ? (void *)ctx->d_tmp2.p : (void *)ctx->d_tmp.p;
+                if (two && k >= 2) CU(cudaStreamWaitEvent(s_draw, ctx->ev_chain[b], 0));  // scratch b free again
+                place_segment_draws(ctx->sc, plan_dev(ctx), ctx->mol0, (uint32_t)ctx->s_nmol, sp[k], sp[k + 1], ctx->d_roff_l.p,
+                                    ctx->d_tile_mol0.p, ctx->n_tiles, ctx->tile_pairs, tmp, ctx->d_acc_i.p, ctx->d_acc_f.p, s_draw);
+                if (two) {
+                    CU(cudaEventRecord(ctx->ev_draw[b], s_draw));
+                    CU(cudaStreamWaitEvent(s_chain, ctx->ev_draw[b], 0));
+                }
+                place_segment_chain(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->mol0, (uint32_t)sb[k], (uint32_t)sb[k + 1], sp[k],
+                                    ctx->d_roff_l.p, tmp, ctx->d_acc_i.p, ctx->d_acc_f.p, ctx->d_ins.p, ctx->d_mol.p, ctx->d_text.p,
+                                    ctx->text_stride, d_err.p, s_chain);
+                if (two) CU(cudaEventRecord(ctx->ev_chain[b], s_chain));
+            }
+            if (two) {  // join: the main stream continues after the last chains
+                CU(cudaStreamWaitEvent(ctx->st, ctx->ev_chain[0], 0));
+                CU(cudaStreamWaitEvent(ctx->st, ctx->ev_chain[1], 0));
+            }
         }
     }
     unsigned long long herr[3];

@@ -142,11 +142,13 @@ void place_prepare(uint64_t mol0, uint32_t n_mol, const uint64_t *d_read_off_glo
                    uint32_t *d_tile_mol0, uint32_t tile_pairs, cudaStream_t st);
 size_t place_tmp_bytes(uint64_t max_pairs);
 // d_acc_i / d_acc_f: per shard molecule, zeroed by the caller before the first segment
-void place_segment(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint32_t m_lo,
-                   uint32_t m_hi, uint64_t pair_lo, uint64_t pair_hi, const uint64_t *d_read_off_local,
-                   const uint32_t *d_tile_mol0, uint32_t n_tiles, uint32_t tile_pairs, void *d_tmp, uint32_t *d_acc_i,
-                   unsigned long long *d_acc_f, uint2 *d_ins,
-                   MolRec *d_mol, uint8_t *d_text, uint32_t text_stride, unsigned long long *d_err, cudaStream_t st);
+void place_segment_draws(const SimConst &sc, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint64_t pair_lo, uint64_t pair_hi,
+                         const uint64_t *d_read_off_local, const uint32_t *d_tile_mol0, uint32_t n_tiles, uint32_t tile_pairs,
+                         void *d_tmp, uint32_t *d_acc_i, unsigned long long *d_acc_f, cudaStream_t st);
+void place_segment_chain(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t m_lo, uint32_t m_hi,
+                         uint64_t pair_lo, const uint64_t *d_read_off_local, void *d_tmp, uint32_t *d_acc_i,
+                         unsigned long long *d_acc_f, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
+                         unsigned long long *d_err, cudaStream_t st);
 
 void tile_prepare(const EmitArgs &a, uint32_t n_tiles_total, uint32_t *d_sum1, uint32_t *d_sum2, uint4 *d_fdesc,
                   uint8_t *d_tile_flags, unsigned long long *d_gather, cudaStream_t st);
