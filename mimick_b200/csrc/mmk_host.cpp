@@ -378,7 +378,11 @@ extern "C" int32_t mmk_create(const mmk_params *p, mmk_ctx **out) {
     if (q.device < 0 || q.device >= ndev) return fail(ctx, MMK_ERR_INVALID_ARG, "device %d out of range", q.device);
     CU(cudaSetDevice(q.device));
     CU(cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking));
+    {   // second stream at the highest priority: in placement it runs the latency-bound chain kernel beside the draws
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&ctx->st_copy, cudaStreamNonBlocking, hi));
+    }
     {
         cudaMemPoolProps props;
         memset(&props, 0, sizeof props);
