@@ -978,12 +978,12 @@ void place_segment_chain(const SimConst &sc, const SchemaDev *d_sch, PlanDev pla
 #include "mmk_emit.cuh"
 namespace mmkdev {
 
-void tile_prepare(const EmitArgs &a, uint32_t n_tiles_total, uint32_t *d_sum1, uint32_t *d_sum2, uint4 *d_fdesc,
+void tile_prepare(const EmitArgs &a, uint32_t tile_lo, uint32_t tile_hi, uint32_t *d_sum1, uint32_t *d_sum2, uint4 *d_fdesc,
                   uint8_t *d_tile_flags, unsigned long long *d_gather, cudaStream_t st) {
-    if (n_tiles_total == 0) return;
+    if (tile_hi <= tile_lo) return;
     const uint32_t per_cta = 256u / a.tile_pairs;
-    LAUNCH(k_tile_prepare, (n_tiles_total + per_cta - 1) / per_cta, 256, 0, st, a, n_tiles_total, d_sum1, d_sum2, d_fdesc, d_tile_flags,
-           d_gather);
+    LAUNCH(k_tile_prepare, (tile_hi - tile_lo + per_cta - 1) / per_cta, 256, 0, st, a, tile_lo, tile_hi, d_sum1, d_sum2, d_fdesc,
+           d_tile_flags, d_gather);
 }
 
 // Chunk table: tile boundaries so that each chunk's R1 and R2 bytes both fit `cap`.

@@ -130,14 +130,14 @@ __device__ void write_record_generic(const EmitArgs &a, const PairDesc &d, int r
 // ------------------------------------------------------------------------------------------
 // x: bstart   y: insert length | dm << 24   z: sb1 | sb2 << 16 (tile-relative record offsets)
 // w: P | SUF << 7 | schema << 13
-__global__ void __launch_bounds__(256) k_tile_prepare(EmitArgs a, uint32_t n_tiles, uint32_t *sum1, uint32_t *sum2, uint4 *fdesc,
-                                                      uint8_t *tile_flags, unsigned long long *gather) {
+__global__ void __launch_bounds__(256) k_tile_prepare(EmitArgs a, uint32_t tile_lo, uint32_t n_tiles, uint32_t *sum1, uint32_t *sum2,
+                                                      uint4 *fdesc, uint8_t *tile_flags, unsigned long long *gather) {
     // 256 threads = 256 / tile_pairs tiles; tile_pairs is a power of two in 8..64
     __shared__ uint32_t s_w[8][2];
     __shared__ uint32_t s_irr[8];
     const uint32_t TP = a.tile_pairs, tsh = 31 - __clz(TP);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t tile = blockIdx.x * (256u >> tsh) + (threadIdx.x >> tsh), it = threadIdx.x & (TP - 1u);
+    const uint32_t tile = tile_lo + blockIdx.x * (256u >> tsh) + (threadIdx.x >> tsh), it = threadIdx.x & (TP - 1u);  // tiles [tile_lo, n_tiles)
     const bool tile_ok = tile < n_tiles;
     const uint64_t p0 = (uint64_t)tile << tsh;
     const uint32_t np = tile_ok ? (uint32_t)((a.n_pairs - p0) < TP ? (a.n_pairs - p0) : TP) : 0u;

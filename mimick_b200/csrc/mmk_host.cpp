@@ -1286,6 +1286,19 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     ctx->n_tiles = (uint32_t)((ctx->s_npairs + ctx->tile_pairs - 1) / ctx->tile_pairs);
     CU(ctx->d_tile_mol0.ensure((size_t)ctx->n_tiles + 1));
     place_prepare(ctx->mol0, (uint32_t)ctx->s_nmol, ctx->d_read_off.p, ctx->d_roff_l.p, ctx->d_tile_mol0.p, ctx->tile_pairs, ctx->st);
+    // per-tile outputs of k_tile_prepare, launched per segment below
+    DBuf<uint32_t> &d_sum1 = ctx->s_sum1, &d_sum2 = ctx->s_sum2;
+    CU(d_sum1.ensure((size_t)ctx->n_tiles + 1));
+    CU(d_sum2.ensure((size_t)ctx->n_tiles + 1));
+    CU(ctx->d_scan_tmp.ensure((size_t)ctx->n_tiles / 1024 + 8));
+    CU(ctx->d_tile_off1.ensure((size_t)ctx->n_tiles + 1));
+    CU(ctx->d_tile_off2.ensure((size_t)ctx->n_tiles + 1));
+    DBuf<unsigned long long> &d_gather = ctx->s_gather;
+    CU(d_gather.ensure(256));
+    CU(cudaMemsetAsync(d_gather.p, 0, 256 * 8, ctx->st));
+    CU(ctx->d_fdesc.ensure(ctx->s_npairs + 1));
+    CU(ctx->d_tile_flags.ensure((size_t)ctx->n_tiles + 1));
+    const EmitArgs targs = base_args(ctx);
     {   // Segments of at most SEG pairs bound the scratch of the flat per-pair draws.  The draws of segment k + 1
         // (compute-bound) run on the main stream while the chain of segment k (latency-bound) runs on the second
         // stream; two scratch buffers alternate.
@@ -1317,10 +1330,17 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
                 CU(cudaEventRecord(ctx->ev_draw[0], ctx->st));
                 CU(cudaStreamWaitEvent(s_chain, ctx->ev_draw[0], 0));
             }
+            // tiles whose pairs are all placed: record lengths, descriptors
+            uint32_t tiles_done = 0;
+            auto prepare_upto = [&](int k_done, cudaStream_t st) {  // segments 0..k_done are placed before this point of `st`
+                const uint32_t t_hi = k_done + 1 == n_seg ? ctx->n_tiles : (uint32_t)(sp[k_done + 1] / ctx->tile_pairs);
+                tile_prepare(targs, tiles_done, t_hi, d_sum1.p, d_sum2.p, ctx->d_fdesc.p, ctx->d_tile_flags.p, d_gather.p, st);
+                tiles_done = std::max(tiles_done, t_hi);
+            };
             for (int k = 0; k < n_seg; ++k) {
                 const int b = two ? (k & 1) : 0;
                 void *tmp = b ? (void *)ctx->d_tmp2.p : (void *)ctx->d_tmp.p;
-                if (two && k >= 2) CU(cudaStreamWaitEvent(s_draw, ctx->ev_chain[b], 0));  // scratch b free again
+                if (two && k >= 2) CU(cudaStreamWaitEvent(s_draw, ctx->ev_chain[b], 0));  // chain k - 2 done: scratch b free again
                 place_segment_draws(ctx->sc, plan_dev(ctx), ctx->mol0, (uint32_t)ctx->s_nmol, sp[k], sp[k + 1], ctx->d_roff_l.p,
                                     ctx->d_tile_mol0.p, ctx->n_tiles, ctx->tile_pairs, tmp, ctx->d_acc_i.p, ctx->d_acc_f.p, s_draw);
                 if (two) {
@@ -1330,12 +1350,16 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
                 place_segment_chain(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->mol0, (uint32_t)sb[k], (uint32_t)sb[k + 1], sp[k],
                                     ctx->d_roff_l.p, tmp, ctx->d_acc_i.p, ctx->d_acc_f.p, ctx->d_ins.p, ctx->d_mol.p, ctx->d_text.p,
                                     ctx->text_stride, d_err.p, s_chain);
-                if (two) CU(cudaEventRecord(ctx->ev_chain[b], s_chain));
+                if (two) {
+                    CU(cudaEventRecord(ctx->ev_chain[b], s_chain));
+                    prepare_upto(k, s_chain);  // memory-bound; behind the chain it overlaps the next segment's draws
+                }
             }
-            if (two) {  // join: the main stream continues after the last chains
-                CU(cudaStreamWaitEvent(ctx->st, ctx->ev_chain[0], 0));
-                CU(cudaStreamWaitEvent(ctx->st, ctx->ev_chain[1], 0));
+            if (two) {  // join: the main stream continues after everything queued on the second stream
+                CU(cudaEventRecord(ctx->ev_draw[0], s_chain));
+                CU(cudaStreamWaitEvent(ctx->st, ctx->ev_draw[0], 0));
             }
+            prepare_upto(n_seg - 1, ctx->st);  // what is left (everything when there is one stream)
         }
     }
     unsigned long long herr[3];
@@ -1349,22 +1373,8 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     }
     ctx->place_info.phase_ms[0] = now_ms() - t_phase;
     t_phase = now_ms();
-    // tile offsets
-    DBuf<uint32_t> &d_sum1 = ctx->s_sum1, &d_sum2 = ctx->s_sum2;
+    // tile offsets (the per-tile record lengths were computed segment by segment above)
     DBuf<uint64_t> &d_tmp = ctx->d_scan_tmp;
-    CU(d_sum1.ensure((size_t)ctx->n_tiles + 1));
-    CU(d_sum2.ensure((size_t)ctx->n_tiles + 1));
-    CU(d_tmp.ensure((size_t)ctx->n_tiles / 1024 + 8));
-    CU(ctx->d_tile_off1.ensure((size_t)ctx->n_tiles + 1));
-    CU(ctx->d_tile_off2.ensure((size_t)ctx->n_tiles + 1));
-    DBuf<unsigned long long> &d_gather = ctx->s_gather;
-    CU(d_gather.ensure(256));
-    CU(cudaMemsetAsync(d_gather.p, 0, 256 * 8, ctx->st));
-    EmitArgs a = base_args(ctx);
-    CU(ctx->d_fdesc.ensure(ctx->s_npairs + 1));
-    CU(ctx->d_tile_flags.ensure((size_t)ctx->n_tiles + 1));
-    a = base_args(ctx);
-    tile_prepare(a, ctx->n_tiles, d_sum1.p, d_sum2.p, ctx->d_fdesc.p, ctx->d_tile_flags.p, d_gather.p, ctx->st);
     exclusive_scan_u32(d_sum1.p, ctx->d_tile_off1.p, ctx->n_tiles, d_tmp.p, ctx->st);
     exclusive_scan_u32(d_sum2.p, ctx->d_tile_off2.p, ctx->n_tiles, d_tmp.p, ctx->st);
     uint64_t tot[3] = {0, 0, 0};

@@ -150,7 +150,7 @@ void place_segment_chain(const SimConst &sc, const SchemaDev *d_sch, PlanDev pla
                          unsigned long long *d_acc_f, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
                          unsigned long long *d_err, cudaStream_t st);
 
-void tile_prepare(const EmitArgs &a, uint32_t n_tiles_total, uint32_t *d_sum1, uint32_t *d_sum2, uint4 *d_fdesc,
+void tile_prepare(const EmitArgs &a, uint32_t tile_lo, uint32_t tile_hi, uint32_t *d_sum1, uint32_t *d_sum2, uint4 *d_fdesc,
                   uint8_t *d_tile_flags, unsigned long long *d_gather, cudaStream_t st);
 void emit(const EmitArgs &a, cudaStream_t st);
 void chunk_table(const uint64_t *d_off1, const uint64_t *d_off2, uint32_t n_tiles, uint64_t cap, uint32_t *d_bounds,
