@@ -211,3 +211,39 @@ def test_cli_maps_the_reference_options():
     with pytest.raises(SystemExit) as e:   # __main__.py:84-86
         plan_call(["-l", "200,200", "-L", "300", "a.fa"])
     assert "cannot exceed the average molecule length" in str(e.value)
+
+
+def test_bgzf_parse_model_round_trips_arbitrary_records():
+    """scripts/bgzf_table.py is the specification of the device's FASTQ-aware deflate parse (the GPU tests require the
+    kernel's members to equal the model's bytes).  The model itself must be a valid deflate coder for ANY 4-line
+    text: random headers (shared prefixes / suffixes of every length, including none), sequences and quality lines
+    that are runs, non-runs or empty, and lines longer than the 258-byte match limit."""
+    import random
+    import re
+    import zlib
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import bgzf_table as T
+    txt = open(os.path.join(ROOT, "mimick_b200", "csrc", "mmk_bgzf_table.h")).read()
+    ll_len = [int(x) for x in re.search(r"LL_LEN\[286\] = \{([^}]*)\}", txt).group(1).split(",")]
+    d_len = [int(x) for x in re.search(r"D_LEN\[30\] = \{([^}]*)\}", txt).group(1).split(",")]
+    rnd = random.Random(5)
+    alphabet = bytes(T.SUPPORTED).replace(b"\n", b"")
+
+    def word(lo, hi, chars=alphabet):
+        return bytes(rnd.choice(chars) for _ in range(rnd.randint(lo, hi)))
+    for trial in range(60):
+        recs = []
+        stem, tail = word(0, 40), word(0, 30)
+        for _ in range(rnd.randint(1, 12)):
+            if rnd.random() < 0.2:
+                stem, tail = word(0, 300), word(0, 20)
+            hdr = b"@" + stem + word(0, 12, b"0123456789:") + tail
+            seq = word(0, 400, b"ACGTN")
+            qual = rnd.choice([b"I" * len(seq), word(0, 50), b"", b"#" * rnd.randint(1, 700)])
+            recs.append(hdr + b"\n" + seq + b"\n+" + word(0, 3) + b"\n" + qual + b"\n")
+        block = b"".join(recs)
+        z = T.deflate_block(block, ll_len, d_len)
+        assert z is not None and zlib.decompress(z, wbits=-15) == block, f"trial {trial}"
+    assert T.tokenize(b"@a\nAC\n+\n") is None and T.tokenize(b"") is None            # not whole 4-line records
+    assert T.deflate_block(b"@a\n\xff\n+\nI\n", ll_len, d_len) is None                 # a byte without a code -> stored on the device
+    assert T.split_match(259) == [256, 3] and T.split_match(260) == [257, 3] and sum(T.split_match(1000)) == 1000
