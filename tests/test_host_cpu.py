@@ -247,3 +247,34 @@ def test_bgzf_parse_model_round_trips_arbitrary_records():
     assert T.tokenize(b"@a\nAC\n+\n") is None and T.tokenize(b"") is None            # not whole 4-line records
     assert T.deflate_block(b"@a\n\xff\n+\nI\n", ll_len, d_len) is None                 # a byte without a code -> stored on the device
     assert T.split_match(259) == [256, 3] and T.split_match(260) == [257, 3] and sum(T.split_match(1000)) == 1000
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/mimick_b200.h must compile as strict C99 (no C++ or CUDA types) and a
+    C program linked against libmimick_b200.so must be able to call it (host-only entry points; no GPU here)."""
+    src = tmp_path / "abi.c"
+    src.write_text('''#include <stdio.h>
+#include <string.h>
+#include "mimick_b200.h"
+int main(void) {
+    mmk_params p;
+    int32_t bc = -1, fq = -1;
+    unsigned char eof[28];
+    mmk_params_default(&p);
+    if (mmk_abi_version() != MMK_ABI_VERSION) return 1;
+    if (mmk_interpret_format("standard:stlfr", &bc, &fq) != 0) return 2;
+    if (mmk_interpret_format("bgi", &bc, &fq) == 0) return 3;
+    if (mmk_bgzf_eof(eof, sizeof eof) != 28 || eof[0] != 0x1f || eof[1] != 0x8b) return 4;
+    if (strlen(mmk_strerror(3)) == 0) return 5;
+    printf("%d %d %g\\n", (int)bc, (int)fq, p.coverage);
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    lib_dir = os.path.join(ROOT, "mimick_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                        "-o", str(exe), "-L", lib_dir, "-l:libmimick_b200.so", f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert r.stdout.split()[2] == "30"
