@@ -426,6 +426,7 @@ extern "C" void mmk_destroy(mmk_ctx *c) {
     if (c->st) {
         cudaSetDevice(c->par.device);
         cudaStreamSynchronize(c->st);
+        if (c->st_copy) cudaStreamSynchronize(c->st_copy);  // placement and the streamed emission also queue work there
     }
     for (auto &k : c->contigs) sym_free(c, k.d_ascii);
     if (c->st) cudaStreamSynchronize(c->st);
