@@ -1,11 +1,11 @@
 """Offline generator of the fixed deflate code tables used by the BGZF stage (mimick_b200/csrc/mmk_bgzf_table.h).
 
-    python scripts/bgzf_table.py            # prints the statistics and rewrites the header
+    python tests/golden/make_bgzf_table.py  # builds the fitting corpus, prints the statistics, rewrites the header
 
 The BGZF kernel codes every block with ONE pre-agreed "dynamic Huffman" table (so the block header is a constant
 bit string and no per-block histogram / tree construction runs on the device).  The table is fitted here to the token
-stream the kernel's FASTQ-aware parse produces on FASTQ text of every barcode format, as written by the CPU
-oracle (test infrastructure; this script is a development tool, not part of the product path).
+stream the kernel's FASTQ-aware parse produces on FASTQ text of every barcode format (the corpus is produced by
+tests/golden/make_bgzf_table.py; this module is a development tool and test-side model, not part of the product path).
 
 `tokenize()` below is the specification of that parse (the CUDA kernel k_bgzf follows it token for token) and
 `deflate_block()` a bit-exact Python model of the encoder; tests use them to cross-check compressed sizes.
@@ -249,31 +249,10 @@ def deflate_block(block: bytes, ll_len, d_len, header: BitWriter | None = None):
 
 
 # ---------------------------------------------------------------------------------------------- fitting
-def sample_texts():
-    sys.path.insert(0, ROOT)
-    from oracle import oracle as orc
-
-    rng = np.random.default_rng(2024)
-    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
-    tmp = "/tmp/bgzf_table_inputs"
-    os.makedirs(tmp, exist_ok=True)
-    # a contig whose coordinates mix 6..8 digits, two haplotypes
-    seqs = [acgt[rng.integers(0, 4, size=12_000_000)].tobytes() for _ in range(2)]
-    paths = []
-    for i, s in enumerate(seqs):
-        p = os.path.join(tmp, f"h{i}.fa")
-        with open(p, "wb") as fh:
-            fh.write(b">chr7\n" + s + b"\n")
-        paths.append(p)
-    texts = []
-    for fmt in ["haplotagging", "stlfr", "tellseq", "10x", "standard:haplotagging", "standard"]:
-        res = orc.mimick_single(paths, fmt, seed=3, coverage=0.12, singletons=0.1)
-        texts.append((fmt, res.r1, res.r2))
-    return texts
-
-
-def main():
-    texts = sample_texts()
+def fit(texts):
+    """texts: list of (format name, R1 text, R2 text).  Fits the code lengths to the token stream of 32-record blocks,
+    checks the resulting coder against zlib, prints the statistics and rewrites mmk_bgzf_table.h.
+    The corpus comes from tests/golden/make_bgzf_table.py (which runs the CPU oracle — test infrastructure)."""
     ll_f = {s: 0 for s in SUPPORTED + list(range(256, 286))}
     d_f = {s: 0 for s in range(30)}
     total_in = 0
@@ -326,7 +305,7 @@ def main():
     out = os.path.join(ROOT, "mimick_b200", "csrc", "mmk_bgzf_table.h")
     hb = hdr.tobytes()
     with open(out, "w") as fh:
-        fh.write("// Generated by scripts/bgzf_table.py — do not edit.\n")
+        fh.write("// Generated by tests/golden/make_bgzf_table.py (scripts/bgzf_table.py:fit) — do not edit.\n")
         fh.write("// Fixed deflate code of the BGZF stage: code lengths of the literal/length and distance alphabets and the\n")
         fh.write("// constant block prefix (BFINAL=1, BTYPE=2, code-length section) as a little-endian bit string.\n")
         fh.write("#pragma once\n#include <stdint.h>\n")
@@ -338,5 +317,7 @@ def main():
     print("wrote", out)
 
 
+
+
 if __name__ == "__main__":
-    main()
+    raise SystemExit("run tests/golden/make_bgzf_table.py: it builds the fitting corpus and calls fit()")
