@@ -215,9 +215,24 @@ MMK_HD void mmk_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint
 }
 
 /* ---- stream addressing ----------------------------------------------------------------
- * key     = (seed low 32, seed high 32)
- * counter = (block, purpose | sample<<8 | g[39:32]<<24, g[31:0], m)
+ * key     = (seed low 32, seed high 32) — always the user's seed, except in the redraw rounds of the
+ *           insert-length vector (below); nothing is ever XORed into it, so runs with different seeds
+ *           share no stream
+ * counter = (c0 + (block << sh), purpose | sample<<8 | g[39:32]<<24, g[31:0], m)
  * One Philox block yields two 64-bit draws: draw 2b is words (0,1), draw 2b+1 is words (2,3).
+ * Ordinary streams have c0 = 0, sh = 0: the block index is the whole first counter word.
+ *
+ * Insert streams (purpose MMK_P_INSERT) — one per (redraw round r, insert i) of a molecule, so that any
+ * thread can make the draws of any read pair:
+ *     c0 = i (inserts per molecule < 2^24: each is >= 200 bases of a contig < 2^31), sh = 24
+ *     key = seed in round 0; in round r >= 1 the round key mmk_round_key(seed, r): words (0,1) of
+ *           Philox(key = seed; counter = (r, MMK_P_ROUNDKEY, 0, 0))
+ *     draw 0      first variate of the insert-length sampler
+ *     draw 1      (round 0 only) the 64 bits of the insert's gap draw (Breakpoints.jl:28): length and gap
+ *                 of a pair come from ONE Philox block
+ *     draw 2, ... further variates of the length sampler (rejected proposals)
+ * (after 256 blocks the block index wraps onto the insert index bits: unreachable, the samplers accept
+ * with probability > 0.3 per proposal.)
  */
 enum mmk_purpose {
     MMK_P_MASK = 1,     /* N masking: g = contig index, m = haplotype file index, draw = position */
@@ -226,13 +241,17 @@ enum mmk_purpose {
     MMK_P_MOLSIZE = 4,  /* molecule: molecule length draw(s)                      Breakpoints.jl:155-158 */
     MMK_P_SINGLETON = 5,/* molecule: singleton test                               Breakpoints.jl:173 */
     MMK_P_NFRAGS = 6,   /* molecule: number of inserts draw(s)                    Breakpoints.jl:191-192 */
-    MMK_P_INSERT = 7,   /* molecule: insert length normals                        Breakpoints.jl:207,211 */
+    MMK_P_INSERT = 7,   /* insert: length sampler variates + gap draw             Breakpoints.jl:207,211 */
     MMK_P_START = 8,    /* molecule: start position                               Breakpoints.jl:240 */
-    MMK_P_GAP = 9       /* molecule: draw i = gap before insert i                 Breakpoints.jl:28 */
+    MMK_P_GAP = 9,      /* (tag of the replay stream only) gap before insert i    Breakpoints.jl:28 */
+    MMK_P_ROUNDKEY = 10,/* key derivation of redraw round r >= 1 */
+    MMK_P_ERROR = 11,   /* read: substitution / indel / quality draws of the sequencing-error model */
+    MMK_P_ERRPOS = 12   /* read: per-base draws of the sequencing-error model */
 };
 
 typedef struct mmk_stream {
     uint32_t key[2];
+    uint32_t c0, sh;
     uint32_t c1, c2, c3;
     uint32_t next; /* index of the next 64-bit draw */
     uint32_t blk;  /* Philox block currently held in buf (0xffffffff = none) */
@@ -243,6 +262,8 @@ MMK_HD void mmk_stream_init(mmk_stream *s, uint64_t seed, uint32_t sample, uint3
                             uint64_t g, uint32_t m) {
     s->key[0] = (uint32_t)seed;
     s->key[1] = (uint32_t)(seed >> 32);
+    s->c0 = 0;
+    s->sh = 0;
     s->c1 = (purpose & 0xffu) | ((sample & 0xffffu) << 8) | ((uint32_t)((g >> 32) & 0xffu) << 24);
     s->c2 = (uint32_t)g;
     s->c3 = m;
@@ -250,22 +271,47 @@ MMK_HD void mmk_stream_init(mmk_stream *s, uint64_t seed, uint32_t sample, uint3
     s->blk = 0xffffffffu;
 }
 MMK_HD void mmk_stream_seek(mmk_stream *s, uint32_t draw) { s->next = draw; }
+MMK_HD void mmk_stream_block(const mmk_stream *s, uint32_t block, uint32_t out[4]) {
+    uint32_t ctr[4] = {s->c0 + (block << s->sh), s->c1, s->c2, s->c3};
+    mmk_philox4x32_10(ctr, s->key, out);
+}
 MMK_HD uint64_t mmk_stream_at(const mmk_stream *s, uint32_t draw) {
-    uint32_t ctr[4] = {draw >> 1, s->c1, s->c2, s->c3};
     uint32_t o[4];
-    mmk_philox4x32_10(ctr, s->key, o);
+    mmk_stream_block(s, draw >> 1, o);
     return (draw & 1u) ? (((uint64_t)o[3] << 32) | o[2]) : (((uint64_t)o[1] << 32) | o[0]);
 }
 MMK_HD uint64_t mmk_stream_next64(mmk_stream *s) {
     uint32_t d = s->next++;
     if ((d >> 1) != s->blk) {
-        uint32_t ctr[4] = {d >> 1, s->c1, s->c2, s->c3};
-        mmk_philox4x32_10(ctr, s->key, s->buf);
+        mmk_stream_block(s, d >> 1, s->buf);
         s->blk = d >> 1;
     }
     return (d & 1u) ? (((uint64_t)s->buf[3] << 32) | s->buf[2])
                     : (((uint64_t)s->buf[1] << 32) | s->buf[0]);
 }
+
+/* key of redraw round r (r >= 1) of the insert-length vector; round 0 uses the seed itself */
+MMK_HD uint64_t mmk_round_key(uint64_t seed, uint32_t round) {
+    if (round == 0) return seed;
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t ctr[4] = {round, MMK_P_ROUNDKEY, 0u, 0u};
+    uint32_t o[4];
+    mmk_philox4x32_10(ctr, key, o);
+    return ((uint64_t)o[1] << 32) | o[0];
+}
+/* stream of insert i of molecule (g, m) under `key` = mmk_round_key(seed, round) */
+MMK_HD void mmk_insert_stream_init(mmk_stream *s, uint64_t key, uint32_t sample, uint64_t g, uint32_t m, uint32_t i) {
+    mmk_stream_init(s, key, sample, MMK_P_INSERT, g, m);
+    s->c0 = i;
+    s->sh = 24;
+}
+/* next variate of the length sampler: draws 0, 2, 3, 4, ... (draw 1 is the gap draw) */
+MMK_HD uint64_t mmk_insert_next64(mmk_stream *s) {
+    uint64_t v = mmk_stream_next64(s);
+    if (s->next == 1) s->next = 2;
+    return v;
+}
+#define MMK_INSERT_GAP_DRAW 1u
 
 /* ---- variates ---------------------------------------------------------------------------- */
 /* u01 in [0,1): 53 random bits */

@@ -716,14 +716,17 @@ __global__ void k_insert_draws(SimConst sc, PlanDev plan, uint64_t mol0, uint32_
     const uint64_t g = plan.group[mol0 + lo];
     const uint32_t m = plan.slot[mol0 + lo];
     NoRec rec;
-    const double x = draw_insert(sc, g, m, 0, i, rec);
-    mmk_stream gs;
-    mmk_stream_init(&gs, sc.seed, sc.sample, MMK_P_GAP, g, m);
-    uint32_t li = (uint32_t)(long long)x;
-    if (li > 0x00ffffffu) li = 0x00ffffffu;
+    // ONE Philox block per pair: words (0,1) feed the length sampler, words (2,3) are the gap draw
+    mmk_stream is;
+    mmk_insert_stream_init(&is, sc.seed, sc.sample, g, m, i);
+    mmk_stream_block(&is, 0, is.buf);
+    is.blk = 0;
+    const uint64_t gbits = ((uint64_t)is.buf[3] << 32) | is.buf[2];
+    const double x = draw_insert_from(sc, is, rec);
+    const uint32_t li = insert_len_of(x);
     if (valid) {
         PairTmp t;
-        t.bits = mmk_stream_at(&gs, i);
+        t.bits = gbits;
         t.len = li;
         t.dm = lo - tm0;
         tmp[p - pair_lo] = t;
@@ -748,7 +751,8 @@ __global__ void k_insert_draws(SimConst sc, PlanDev plan, uint64_t mol0, uint32_
 __device__ __noinline__ double sequential_sum(const SimConst &sc, uint64_t g, uint32_t m, uint32_t round, uint32_t nfrags) {
     NoRec rec;
     double sum = 0.0;
-    for (uint32_t k = 0; k < nfrags; ++k) sum = MMK_ADD(sum, draw_insert(sc, g, m, round, k, rec));
+    const uint64_t key = mmk_round_key(sc.seed, round);
+    for (uint32_t k = 0; k < nfrags; ++k) sum = MMK_ADD(sum, draw_insert(sc, key, g, m, k, rec));
     return sum;
 }
 // whole-vector redraws while the float sum exceeds the molecule (Breakpoints.jl:209-212); true if it still does
@@ -761,11 +765,11 @@ __device__ __noinline__ bool redraw_rounds(const SimConst &sc, uint64_t g, uint3
         ++attempts;
         double sum = 0.0;
         isum = 0;
+        const uint64_t key = mmk_round_key(sc.seed, (uint32_t)attempts);
         for (uint32_t k = 0; k < nfrags; ++k) {
-            double x = draw_insert(sc, g, m, (uint32_t)attempts, k, rec);
+            double x = draw_insert(sc, key, g, m, k, rec);
             sum = MMK_ADD(sum, x);
-            uint32_t li = (uint32_t)(long long)x;
-            if (li > 0x00ffffffu) li = 0x00ffffffu;
+            const uint32_t li = insert_len_of(x);
             tp[k].len = li;
             isum += li;
         }
@@ -1189,7 +1193,7 @@ __global__ void k_kat_math(int kind, const double *in, double *out, int64_t n) {
     else if (kind == 2) out[i] = mmk_bits_to_exp(mmk_d2u(x));
     else {
         mmk_stream s;
-        mmk_stream_init(&s, mmk_d2u(x), 0, MMK_P_INSERT, (uint64_t)i, 0);
+        mmk_insert_stream_init(&s, mmk_d2u(x), 0, (uint64_t)i, 0, 0);
         out[i] = mmk_next_normal(&s);
     }
 }

@@ -351,12 +351,15 @@ extern "C" int32_t mmk_create(const mmk_params *p, mmk_ctx **out) {
     sc.ins_mu = (double)q.insert_length;
     sc.ins_sd = (double)q.insert_stdev;
     sc.ins_lb = MMK_DIV(MMK_SUB(200.0, sc.ins_mu), sc.ins_sd);
-    {
-        double lcdf = 0.5 * erfc(-sc.ins_lb / sqrt(2.0));
-        if (sc.ins_lb != sc.ins_lb) lcdf = 200.0 > sc.ins_mu ? 1.0 : 0.0;
-        if (!(1.0 - lcdf > 0.3))
+    {   // the kept mass tp = 1 - cdf(lb) picks the sampler (Distributions.jl src/truncated/normal.jl: tp > 0.3 rejection)
+        const double tp = 0.5 * erfc(sc.ins_lb / sqrt(2.0));
+        if (sc.ins_lb != sc.ins_lb || sc.ins_lb == INFINITY)  // sd = 0 and mu <= 200
             return fail(ctx, MMK_ERR_UNSUPPORTED,
-                        "insert-size truncation keeps <= 30%% of the normal law (insert_length far below 200): not implemented");
+                        "insert-size truncation at 200 keeps no mass of Normal(%d, %d): the reference's sampler never returns",
+                        q.insert_length, q.insert_stdev);
+        sc.ins_robert = tp > 0.3 ? 0 : 1;
+        sc.ins_a = MMK_DIV(MMK_ADD(sc.ins_lb, MMK_SQRT(MMK_ADD(MMK_MUL(sc.ins_lb, sc.ins_lb), 4.0))), 2.0);
+        sc.ins_theta = MMK_DIV(1.0, sc.ins_a);
     }
     if ((double)q.insert_length + 13.0 * (double)q.insert_stdev >= 16777215.0)
         return fail(ctx, MMK_ERR_UNSUPPORTED, "insert lengths of 2^24 bases or more");

@@ -21,6 +21,8 @@ struct SimConst {
     TruncExp mollen;     // truncated(Exponential(mol_length), lower = lowerbound)
     TruncExp nmol;       // truncated(Exponential(N), 1, 2.5N)
     double ins_mu, ins_sd, ins_lb;  // truncated(Normal(mu, sd), lower = 200), lb standardised
+    double ins_a, ins_theta;        // Robert's exponential proposal (kept mass <= 0.3): a = (lb + sqrt(lb^2 + 4)) / 2, theta = 1 / a
+    int32_t ins_robert, pad0;       // 1: kept mass tp <= 0.3 (Distributions.jl randnt switches samplers there)
     double singletons, mol_coverage;
     int32_t insert_length, attempts;
     int32_t r1, r2;

@@ -156,19 +156,50 @@ __device__ __forceinline__ uint32_t molecule_shape(const SimConst &sc, uint64_t 
     return status;
 }
 
-// One insert length: rand(truncated(Normal(mu, sd), lower = 200)) — z = randn() until z >= lb, then
-// mu + sd z (Breakpoints.jl:207, Distributions' randnt rejection branch).  The normals of insert i
-// in redraw round r come from their own Philox stream (seed ^ (r << 32 | i)), so the draw can be
-// made by any thread; the replay order (insert 0's normals, then insert 1's, ...) is unchanged.
+// One insert length: rand(truncated(Normal(mu, sd), lower = 200)) (Breakpoints.jl:207; Distributions.jl
+// src/truncated/normal.jl `randnt`, lower bound only, ub = Inf):
+//   tp > 0.3   z = randn() until z >= lb                                     (plain rejection)
+//   tp <= 0.3  Robert (1995), exponential proposal (lb > 0 follows from tp <= 0.3; the branch test
+//              `span > ...` is always true for an infinite span): a = (lb + sqrt(lb^2 + 4)) / 2;
+//              r = randexp() / a + lb, u = rand() until u < exp(-(r - a)^2 / 2)
+//   result     mu + sd * z
+// `s` is the insert's own stream (mmk_insert_stream_init), positioned at its first variate, so any thread
+// can make the draw; the replay order (insert 0's variates, then insert 1's, ...) is the reference's.
 template <class R>
-__device__ __forceinline__ double draw_insert(const SimConst &sc, uint64_t g, uint32_t m, uint32_t round, uint32_t i, R &rec) {
-    mmk_stream s;
-    mmk_stream_init(&s, sc.seed ^ (((uint64_t)round << 32) | (uint64_t)i), sc.sample, MMK_P_INSERT, g, m);
+__device__ __forceinline__ double draw_insert_from(const SimConst &sc, mmk_stream &s, R &rec) {
+    if (sc.ins_robert) {
+        for (;;) {
+            const double e = mmk_bits_to_exp(mmk_insert_next64(&s));
+            rec.put(MMK_P_INSERT, 0, mmk_d2u(e));
+            const double r = MMK_ADD(MMK_MUL(sc.ins_theta, e), sc.ins_lb);
+            const double u = mmk_bits_to_u01(mmk_insert_next64(&s));
+            rec.put(MMK_P_INSERT, 0, mmk_d2u(u));
+            const double t = MMK_SUB(r, sc.ins_a);
+            if (u < mmk_exp(MMK_MUL(-0.5, MMK_MUL(t, t)))) return MMK_ADD(sc.ins_mu, MMK_MUL(sc.ins_sd, r));
+        }
+    }
     for (;;) {
-        double z = mmk_next_normal(&s);
+        const double z = mmk_bits_to_normal(mmk_insert_next64(&s));
         rec.put(MMK_P_INSERT, 0, mmk_d2u(z));
         if (!(z < sc.ins_lb)) return MMK_ADD(sc.ins_mu, MMK_MUL(sc.ins_sd, z));
     }
+}
+// `key` = mmk_round_key(seed, redraw round)
+template <class R>
+__device__ __forceinline__ double draw_insert(const SimConst &sc, uint64_t key, uint64_t g, uint32_t m, uint32_t i, R &rec) {
+    mmk_stream s;
+    mmk_insert_stream_init(&s, key, sc.sample, g, m, i);
+    return draw_insert_from(sc, s, rec);
+}
+// the 64 bits of insert i's gap draw: draw 1 of its round-0 stream
+__device__ __forceinline__ uint64_t gap_bits(const SimConst &sc, uint64_t g, uint32_t m, uint32_t i) {
+    mmk_stream s;
+    mmk_insert_stream_init(&s, sc.seed, sc.sample, g, m, i);
+    return mmk_stream_at(&s, MMK_INSERT_GAP_DRAW);
+}
+__device__ __forceinline__ uint32_t insert_len_of(double x) {
+    uint32_t li = (uint32_t)(long long)x;
+    return li > 0x00ffffffu ? 0x00ffffffu : li;  // unreachable: mmk_create bounds insert_length + 13 sd below 2^24
 }
 
 // Insert lengths, molecule start, gap chain.  Plan entry of insert i:
@@ -194,11 +225,11 @@ __device__ __forceinline__ uint32_t molecule_place(const SimConst &sc, uint64_t 
     for (;;) {
         sum = 0.0;
         isum = 0;
+        const uint64_t key = mmk_round_key(sc.seed, (uint32_t)attempts);
         for (uint32_t i = 0; i < nfrags; ++i) {
-            double x = draw_insert(sc, g, m, (uint32_t)attempts, i, rec);
+            double x = draw_insert(sc, key, g, m, i, rec);
             sum = MMK_ADD(sum, x);
-            uint32_t li = (uint32_t)(long long)x;
-            if (li > 0x00ffffffu) li = 0x00ffffffu;  // unreachable: mmk_create bounds insert_length + 13 sd below 2^24
+            uint32_t li = insert_len_of(x);
             ins[i].y = li;
             isum += li;
         }
@@ -224,9 +255,8 @@ __device__ __forceinline__ uint32_t molecule_place(const SimConst &sc, uint64_t 
     // gap chain
     uint64_t remaining = (uint64_t)molsize + 1 - isum;
     uint64_t cursor = 0;  // relative to start
-    mmk_stream_init(&s, sc.seed, sc.sample, MMK_P_GAP, g, m);
     for (uint32_t i = 0; i < nfrags; ++i) {
-        uint64_t gap = mmk_next_index(&s, remaining + 1);
+        uint64_t gap = mmk_bits_to_index(gap_bits(sc, g, m, i), remaining + 1);
         rec.put(MMK_P_GAP, (uint32_t)(remaining + 1), gap);
         uint64_t st = cursor + gap;
         uint32_t li = MMK_INS_LEN(ins[i].y);

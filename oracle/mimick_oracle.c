@@ -117,6 +117,7 @@ typedef struct orc_sim {
     trunc_exp d_mollen, d_nmol;
     int nmol_fixed;
     double ins_mu, ins_sd, ins_lb; /* truncated Normal, standardised lower bound */
+    double ins_tp;                 /* kept mass 1 - cdf(lb): picks the sampler of randnt */
 
     orc_schema *sch;
     int n_sch, cap_sch;
@@ -199,9 +200,10 @@ static mmk_stream *stream_for(orc_sim *s, uint32_t purpose) {
         uint64_t g = s->cur_g;
         uint32_t m = s->cur_m;
         if (purpose == MMK_P_NMOL || purpose == MMK_P_TARGET) m = 0;
-        uint64_t seed = s->seed;
-        if (purpose == MMK_P_INSERT) seed ^= ((uint64_t)s->cur_round << 32) | (uint64_t)s->cur_insert;
-        mmk_stream_init(&s->st[purpose], seed, s->sample, purpose, g, m);
+        if (purpose == MMK_P_INSERT) /* one stream per (redraw round, insert): include/mmk_rng.h "Insert streams" */
+            mmk_insert_stream_init(&s->st[purpose], mmk_round_key(s->seed, s->cur_round), s->sample, g, m, s->cur_insert);
+        else
+            mmk_stream_init(&s->st[purpose], s->seed, s->sample, purpose, g, m);
         s->st_init[purpose] = 1;
     }
     return &s->st[purpose];
@@ -255,15 +257,36 @@ static double src_randexp(orc_sim *s, uint32_t purpose) {
     rec_push(s, purpose, 0, d, 0, 0);
     return d;
 }
-static double src_randn(orc_sim *s, uint32_t purpose) {
+/* variates of the insert-length sampler (tag INSERT): kind 0 randn, 1 randexp, 2 rand */
+static double src_insert_variate(orc_sim *s, int kind) {
     double d;
     if (s->mode == 0) {
-        const orc_variate *v = rp_pop(s, purpose);
-        d = v ? v->v.d : 0.0;
-    } else
-        d = mmk_next_normal(stream_for(s, purpose));
-    rec_push(s, purpose, 0, d, 0, 0);
+        const orc_variate *v = rp_pop(s, MMK_P_INSERT);
+        d = v ? v->v.d : (kind == 1 ? 1.0 : kind == 2 ? 0.5 : 0.0);
+    } else {
+        uint64_t bits = mmk_insert_next64(stream_for(s, MMK_P_INSERT));
+        d = kind == 0 ? mmk_bits_to_normal(bits) : kind == 1 ? mmk_bits_to_exp(bits) : mmk_bits_to_u01(bits);
+    }
+    rec_push(s, MMK_P_INSERT, 0, d, 0, 0);
     return d;
+}
+/* gap before insert i, uniform in [0, n): Philox mode reads draw 1 of the insert's round-0 stream */
+static int64_t src_gap(orc_sim *s, uint32_t i, uint64_t n) {
+    int64_t r;
+    if (s->mode == 0) {
+        const orc_variate *v = rp_pop(s, MMK_P_GAP);
+        r = v ? v->v.i : 0;
+        if (v && (v->aux != (uint32_t)n || r < 0 || (uint64_t)r >= n)) {
+            fail(s, ORC_ERR_REPLAY, "replay gap variate outside the range the logic asked for");
+            r = 0;
+        }
+    } else {
+        mmk_stream st;
+        mmk_insert_stream_init(&st, s->seed, s->sample, s->cur_g, s->cur_m, i);
+        r = (int64_t)mmk_bits_to_index(mmk_stream_at(&st, MMK_INSERT_GAP_DRAW), n);
+    }
+    rec_push(s, MMK_P_GAP, (uint32_t)n, 0, r, 1);
+    return r;
 }
 /* uniform integer in [0, n) */
 static int64_t src_index(orc_sim *s, uint32_t purpose, uint64_t n) {
@@ -327,11 +350,28 @@ static double trunc_exp_rand(orc_sim *s, const trunc_exp *d, uint32_t purpose) {
         return -MMK_MUL(mmk_log1mexp(lp), d->theta);
     }
 }
-/* rand(::Truncated{Normal}) with tp > 0.3: z = randn() until lb <= z (<= ub = Inf); μ + σ·z */
+/* rand(::Truncated{Normal}) — Distributions.jl src/truncated/normal.jl: z = randnt(lb, ub, tp); mu + sigma z.
+ * Only a lower bound here (src/Structs.jl:68), so ub = Inf:
+ *   tp > 0.3: r = randn() until lb <= r;
+ *   else (then lb > 0, and `span > 2/(lb + sqrt(lb^2+4)) exp(...)` holds for an infinite span):
+ *     Robert (1995) exponential proposal: a = (lb + sqrt(lb^2 + 4))/2; repeat r = rand(Exponential(1/a)) + lb,
+ *     u = rand() until u < exp(-0.5 (r - a)^2) (and r < ub). */
 static double trunc_normal_rand(orc_sim *s) {
+    if (s->ins_tp > 0.3) {
+        for (;;) {
+            double z = src_insert_variate(s, 0);
+            if (!(z < s->ins_lb)) return MMK_ADD(s->ins_mu, MMK_MUL(s->ins_sd, z));
+            if (s->err) return s->ins_mu;
+        }
+    }
+    const double lb = s->ins_lb;
+    const double a = MMK_DIV(MMK_ADD(lb, MMK_SQRT(MMK_ADD(MMK_MUL(lb, lb), 4.0))), 2.0);
+    const double theta = MMK_DIV(1.0, a);
     for (;;) {
-        double z = src_randn(s, MMK_P_INSERT);
-        if (!(z < s->ins_lb)) return MMK_ADD(s->ins_mu, MMK_MUL(s->ins_sd, z));
+        double r = MMK_ADD(MMK_MUL(theta, src_insert_variate(s, 1)), lb);
+        double u = src_insert_variate(s, 2);
+        double t = MMK_SUB(r, a);
+        if (u < mmk_exp(MMK_MUL(-0.5, MMK_MUL(t, t)))) return MMK_ADD(s->ins_mu, MMK_MUL(s->ins_sd, r));
         if (s->err) return s->ins_mu;
     }
 }
@@ -364,12 +404,9 @@ orc_sim *orc_create(const orc_params *p) {
     s->ins_mu = (double)p->insert_length;
     s->ins_sd = (double)p->insert_stdev;
     s->ins_lb = MMK_DIV(MMK_SUB(200.0, s->ins_mu), s->ins_sd);
-    {
-        double lcdf = 0.5 * erfc(-s->ins_lb / sqrt(2.0));
-        if (s->ins_lb != s->ins_lb) lcdf = 200.0 > s->ins_mu ? 1.0 : 0.0; /* sd = 0 and mu = 200 */
-        if (!(1.0 - lcdf > 0.3))
-            fail(s, ORC_ERR_UNSUPPORTED, "insert-size truncation keeps <= 30% of the normal law; Robert-style sampler not restated");
-    }
+    s->ins_tp = 0.5 * erfc(s->ins_lb / sqrt(2.0)); /* used only to pick the sampler (tp > 0.3) */
+    if (s->ins_lb != s->ins_lb || s->ins_lb == INFINITY) /* sd = 0 and mu <= 200: randnt never returns */
+        fail(s, ORC_ERR_UNSUPPORTED, "insert-size truncation at 200 keeps no mass of the normal law");
     s->mode = 1;
     s->seed = 0;
     return s;
@@ -687,7 +724,7 @@ static void simulate_molecule(orc_sim *s, int schema_idx, int64_t molsize, const
     }
     int64_t *bs = s->ins_start + s->n_ins, *be = s->ins_stop + s->n_ins;
     for (int64_t i = 0; i < n_frags; ++i) {
-        int64_t gap = src_index(s, MMK_P_GAP, (uint64_t)remaining + 1);
+        int64_t gap = src_gap(s, (uint32_t)i, (uint64_t)remaining + 1);
         int64_t st = cursor + gap;
         bs[i] = st;
         be[i] = st + lens[i] - 1;
@@ -871,6 +908,6 @@ void orc_sample_insert(uint64_t seed, int32_t mu, int32_t sd, int64_t n, double 
     orc_params p; memset(&p, 0, sizeof p); p.insert_length = mu; p.insert_stdev = sd; p.mol_length = 80000; p.mol_coverage = 0.2; p.n_molecules = 2;
     orc_sim *s = orc_create(&p);
     orc_set_philox(s, seed, 0);
-    for (int64_t i = 0; i < n; ++i) { src_begin_group(s, (uint64_t)i); src_begin_insert(s, 0, 0); out[i] = trunc_normal_rand(s); }
+    for (int64_t i = 0; i < n; ++i) { src_begin_group(s, (uint64_t)i); src_begin_insert(s, 0, (uint32_t)(i & 0xffff)); out[i] = trunc_normal_rand(s); }
     orc_destroy(s);
 }

@@ -202,6 +202,35 @@ def test_insert_size_law():
     L.orc_sample_insert(6, 300, 100, n, out.ctypes.data)   # truncation at 200 is 1 sigma below the mean
     d = stats.truncnorm(a=(200 - 300) / 100, b=np.inf, loc=300, scale=100)
     assert out.min() >= 200 and stats.kstest(out, d.cdf).pvalue > 1e-3
+    # kept mass <= 0.3: Distributions.jl's randnt switches to Robert's exponential proposal (-i 150 -d 50: lb = 1, tp = 0.159)
+    L.orc_sample_insert(7, 150, 50, n, out.ctypes.data)
+    d = stats.truncnorm(a=1.0, b=np.inf, loc=150, scale=50)
+    assert out.min() >= 200 and stats.kstest(out, d.cdf).pvalue > 1e-3
+    L.orc_sample_insert(8, 100, 20, n, out.ctypes.data)     # lb = 5: tp = 2.9e-7
+    d = stats.truncnorm(a=5.0, b=np.inf, loc=100, scale=20)
+    assert out.min() >= 200 and stats.kstest(out, d.cdf).pvalue > 1e-3
+    L.orc_sample_insert(9, 210, 200, n, out.ctypes.data)    # tp = 0.52: rejection with half the normals rejected
+    d = stats.truncnorm(a=-0.05, b=np.inf, loc=210, scale=200)
+    assert out.min() >= 200 and stats.kstest(out, d.cdf).pvalue > 1e-3
+
+
+def test_seeds_share_no_insert_variates(tmp_path):
+    """Nothing is mixed into the Philox key: runs whose seeds differ in any bit (0/1, bit 32, the old
+    round/insert XOR pattern) consume disjoint insert-length and gap variates."""
+    rng = np.random.default_rng(3)
+    p = str(tmp_path / "g.fa")
+    write_fasta(p, [("a", random_bases(rng, 400_000))])
+    seen = {}
+    for seed in (0, 1, 2, 3, 1 << 32, (1 << 32) | 5, 7 ^ 5):
+        res = O.mimick_single([p], "haplotagging", seed=seed, coverage=4, attempts=300, singletons=0.0, record=True)
+        v = res.variates
+        sel = v[(v["tag"] == O.P_INSERT) | (v["tag"] == O.P_GAP)]
+        assert len(sel) > 5000
+        seen[seed] = set(sel["bits"][sel["tag"] == O.P_INSERT].tolist())
+    seeds = list(seen)
+    for i in range(len(seeds)):
+        for j in range(i + 1, len(seeds)):
+            assert not (seen[seeds[i]] & seen[seeds[j]]), (seeds[i], seeds[j])
 
 
 def test_free_running_distributions(tmp_path):

@@ -154,6 +154,10 @@ def test_circular(tmp_path, strict):
     dict(read_length=(150, 108), mol_length=20000, mol_coverage=0.5, singletons=0.0, attempts=300),
     dict(mol_length=300, singletons=0.0, attempts=300),   # molecule-length law in its quantile branch (tp = e^-10)
     dict(read_length=(250, 250), insert_length=600, insert_stdev=150, singletons=0.0, attempts=300),
+    # truncated(Normal(ins, sd), lower = 200) outside plain rejection (src/Structs.jl:68; the CLI admits -i 0.., mimick/__main__.py:44):
+    dict(insert_length=150, insert_stdev=50, read_length=(100, 100), singletons=0.0, attempts=300),   # kept mass 0.16: Robert's exponential proposal
+    dict(insert_length=210, insert_stdev=200, read_length=(100, 100), singletons=0.0, attempts=300),  # kept mass 0.52: rejection, half the normals rejected
+    dict(insert_length=100, insert_stdev=20, read_length=(75, 75), singletons=0.0, attempts=300),     # 5 sigma into the tail
 ])
 def test_parameter_regions(tmp_path, kw):
     rng = np.random.default_rng(4)
