@@ -294,6 +294,15 @@ int32_t mmk_dump_mask_variates(mmk_ctx *ctx, mmk_variate *out, uint64_t cap, uin
 int32_t mmk_kat_philox(mmk_ctx *ctx, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* kind 0: mmk_log, 1: mmk_exp, 2: bits→exp variate, 3: polar normal from stream (seed=x bits) */
 int32_t mmk_kat_math(mmk_ctx *ctx, int32_t kind, const double *in, double *out, int64_t n);
+/* Insert lengths the placement kernels derive from raw 64-bit draws (threshold table with its exact fallback):
+ * len[i] = trunc(Int, mu + sd * z(bits[i])), 0 where the truncation at 200 rejects the draw; slow[i] = 1 where
+ * the double-precision fallback ran (near a threshold, outside the table, table disabled). */
+/* Host-only: the threshold table mmk_create builds for Normal(insert_length, insert_stdev) truncated at 200 (needs no
+ * device).  thr[k] = top 32 of the 52 draw bits of the smallest draw whose length is base_len + k + 1; the table answers
+ * for top-32 draws in [u_lo, u_hi] farther than `guard` from every threshold.  *enabled = 0: no table (exact path only). */
+int32_t mmk_insert_table(int32_t insert_length, int32_t insert_stdev, uint32_t *enabled, uint32_t *n_thr, uint32_t *base_len,
+                         uint32_t *u_lo, uint32_t *u_hi, uint32_t *guard, uint32_t *thr, uint32_t thr_cap);
+int32_t mmk_kat_insert_len(mmk_ctx *ctx, const uint64_t *bits, uint32_t *len, uint8_t *slow, int64_t n);
 
 #ifdef __cplusplus
 }

@@ -76,6 +76,7 @@ EXPORTS = [
     "mmk_dump_inserts", "mmk_dump_variates", "mmk_dump_mask_variates", "mmk_kat_philox", "mmk_kat_math",
     "mmk_emit_all", "mmk_emit_stream", "mmk_chunk_layout", "mmk_launch_count", "mmk_clear_contigs",
     "mmk_bgzf_bound", "mmk_emit_chunk_bgzf", "mmk_emit_stream_bgzf", "mmk_bgzf_eof", "mmk_bgzf_table",
+    "mmk_kat_insert_len", "mmk_insert_table",
 ]
 
 CHUNK_CB = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.POINTER(Chunk), C.c_void_p, C.c_void_p)
@@ -151,5 +152,7 @@ def load():
     sig("mmk_dump_mask_variates", i32, vp, vp, u64, P(u64))
     sig("mmk_kat_philox", i32, vp, vp, vp, vp)
     sig("mmk_kat_math", i32, vp, i32, vp, vp, i64)
+    sig("mmk_kat_insert_len", i32, vp, vp, vp, vp, i64)
+    sig("mmk_insert_table", i32, i32, i32, P(u32), P(u32), P(u32), P(u32), P(u32), P(u32), vp, u32)
     _LIB = L
     return L

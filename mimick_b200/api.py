@@ -341,6 +341,14 @@ class Simulator:
         self._ck(self._L.mmk_kat_philox(self._h, c.ctypes.data, k.ctypes.data, o.ctypes.data))
         return o
 
+    def kat_insert_len(self, bits: np.ndarray):
+        """Insert lengths the placement kernels derive from raw 64-bit draws; returns (len, took_exact_path)."""
+        bits = np.ascontiguousarray(bits, dtype=np.uint64)
+        ln = np.zeros(bits.size, dtype=np.uint32)
+        slow = np.zeros(bits.size, dtype=np.uint8)
+        self._ck(self._L.mmk_kat_insert_len(self._h, bits.ctypes.data, ln.ctypes.data, slow.ctypes.data, bits.size))
+        return ln, slow
+
     def kat_math(self, kind: int, x: np.ndarray) -> np.ndarray:
         x = np.ascontiguousarray(x, dtype=np.float64)
         o = np.zeros_like(x)

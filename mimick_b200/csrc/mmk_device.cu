@@ -12,6 +12,7 @@
 //   k_tile_prepare / k_chunk_table          record lengths per tile → byte offsets, chunk bounds     FormatFASTQ.jl
 //   k_emit (mmk_emit.cuh)                   extraction, reverse complement, FASTQ text              Breakpoints.jl:95-140, FormatFASTQ.jl
 //   k_bgzf / k_bgzf_compact (mmk_bgzf.cuh)  FASTQ text → BGZF members                               Main.jl:42-43,111-112
+#include <algorithm>
 #include <cstddef>
 #include <cstdlib>
 #include <cstdio>
@@ -374,13 +375,6 @@ __global__ void k_group_nmol(SimConst sc, uint64_t g0, uint32_t n_groups, uint32
     nmol[i] = draw_nmol(sc, g0 + i, rec);
 }
 
-constexpr uint32_t HCH = 512;  // molecules per histogram chunk (the finish kernel walks one chunk serially)
-
-__global__ void k_fill_lpos(const uint16_t *live, uint32_t n_live, uint16_t *lpos) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_live) lpos[live[i]] = (uint16_t)i;
-}
-
 // group table, second half: (group, slot) of every molecule — independent of the live set
 __global__ void k_fill_slots(uint64_t g_lo, uint32_t n_groups, const uint32_t *__restrict__ nmol, const uint64_t *__restrict__ off,
                              PlanDev plan) {
@@ -394,158 +388,10 @@ __global__ void k_fill_slots(uint64_t g_lo, uint32_t n_groups, const uint32_t *_
     }
 }
 
-// One thread per molecule of the batch's groups [g0, g0 + n_groups): target pick against the current live
-// list, molecule size and number of inserts.  Also: per-chunk histogram of inserts per live schema (for the
-// coverage tracker, laid out [schema][chunk] so the finish kernel reads it coalesced) and the first molecule
-// with a non-zero status.
-__global__ void k_plan_molecules(SimConst sc, const SchemaDev *__restrict__ sch, const uint16_t *__restrict__ live,
-                                 const uint16_t *__restrict__ lpos, uint32_t n_live, uint16_t epoch, uint64_t g0, uint32_t n_groups,
-                                 const uint64_t *__restrict__ off, PlanDev plan, unsigned long long *hist, uint32_t hstride,
-                                 unsigned long long *first_err) {
-    const uint64_t base = off[g0], n_mol = off[g0 + n_groups] - base;
-    const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_mol) return;
-    const uint64_t i = base + j;
-    const uint64_t g = plan.group[i];
-    const uint32_t m = plan.slot[i];
-    NoRec rec;
-    const uint32_t t = live[draw_target(sc, g, m, n_live)];
-    uint32_t molsize, nfrags;
-    const uint32_t status = molecule_shape(sc, g, m, sch[t].len, molsize, nfrags, rec);
-    plan.schema[i] = (uint16_t)t;
-    plan.epoch[i] = epoch;
-    plan.size[i] = molsize;
-    plan.nfrags[i] = nfrags;
-    plan.status[i] = (uint8_t)status;
-    atomicAdd(&hist[(uint64_t)lpos[t] * hstride + (uint32_t)(j / HCH)], (unsigned long long)nfrags);
-    if (status) atomicMin(first_err, (unsigned long long)j);
-}
 
-// Two small kernels close the batch, one warp per live schema in both.
-// k_plan_cut: the barcode group in which the schema's cumulative insert count reaches its remaining need (a schema
-// is pruned at the END of that group, Main.jl:54,58); the earliest over all schemas = the cut (atomicMin).
-// k_plan_sums: the number of molecules kept and the inserts each schema received from them; leaves the scratch
-// (histogram, first-error slot, the other batch parity's cut slot) clean for the next batch.
-// scratch[0] = first molecule with a non-zero status, scratch[1 + parity] = cut group of the batch.
-constexpr uint32_t PLAN_FIN_THREADS = 256;
-__global__ void __launch_bounds__(PLAN_FIN_THREADS) k_plan_cut(const uint16_t *__restrict__ schema, const uint32_t *__restrict__ nfrags,
-                                                               const uint64_t *__restrict__ group, const uint64_t *__restrict__ off,
-                                                               uint64_t g0, uint32_t n_groups, const uint16_t *__restrict__ live,
-                                                               uint32_t n_live, const unsigned long long *__restrict__ hist,
-                                                               uint32_t hstride, const int64_t *__restrict__ need,
-                                                               unsigned long long *cut) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t s = blockIdx.x * (PLAN_FIN_THREADS / 32) + (threadIdx.x >> 5);
-    if (s >= n_live) return;
-    const uint64_t base = off[g0];
-    const uint64_t n_mol = off[g0 + n_groups] - base;
-    const uint32_t n_chunks = (uint32_t)((n_mol + HCH - 1) / HCH);
-    schema += base;
-    nfrags += base;
-    group += base;
-    constexpr uint32_t PER = HCH / 32;
-    const long long want = need[s];
-    unsigned long long cg = ~0ull;
-    if (want <= 0) {
-        cg = g0;  // already complete: pruned at the end of the batch's first group
-    } else {
-        const uint16_t sid = live[s];
-        unsigned long long cum = 0;
-        uint32_t found = 0xffffffffu;
-        // four rounds of loads in flight: the scan below is a chain of L2 latencies otherwise
-        const unsigned long long *hs = hist + (uint64_t)s * hstride;
-        unsigned long long pre[4];
-#pragma unroll
-        for (uint32_t u = 0; u < 4; ++u) pre[u] = 32 * u + lane < n_chunks ? hs[32 * u + lane] : 0ull;
-        for (uint32_t c0 = 0; c0 < n_chunks && found == 0xffffffffu; c0 += 32) {
-            const unsigned long long v = pre[0];
-            pre[0] = pre[1];
-            pre[1] = pre[2];
-            pre[2] = pre[3];
-            pre[3] = c0 + 128 + lane < n_chunks ? hs[c0 + 128 + lane] : 0ull;
-            unsigned long long inc = v;
-            for (int o = 1; o < 32; o <<= 1) {
-                unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += y;
-            }
-            const unsigned ball = __ballot_sync(0xffffffffu, (long long)(cum + inc) >= want);
-            if (ball) {
-                const int l = __ffs(ball) - 1;
-                cum += __shfl_sync(0xffffffffu, inc - v, l);
-                found = c0 + l;
-            } else
-                cum += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        if (found != 0xffffffffu) {  // the molecule inside the chunk: each lane owns PER consecutive molecules
-            const uint64_t lo = (uint64_t)found * HCH + (uint64_t)lane * PER;
-            unsigned long long part = 0;
-            for (uint32_t j = 0; j < PER; ++j) {
-                const uint64_t i = lo + j;
-                if (i < n_mol && schema[i] == sid) part += nfrags[i];
-            }
-            unsigned long long inc = part;
-            for (int o = 1; o < 32; o <<= 1) {
-                unsigned long long y = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += y;
-            }
-            const unsigned ball = __ballot_sync(0xffffffffu, (long long)(cum + inc) >= want);
-            const int l = __ffs(ball) - 1;  // non-zero by construction
-            if ((int)lane == l) {
-                unsigned long long run = cum + inc - part;
-                for (uint32_t j = 0; j < PER; ++j) {
-                    const uint64_t i = lo + j;
-                    if (i < n_mol && schema[i] == sid) {
-                        run += nfrags[i];
-                        if ((long long)run >= want) {
-                            cg = group[i];
-                            break;
-                        }
-                    }
-                }
-            }
-            cg = __shfl_sync(0xffffffffu, cg, l);
-        }
-    }
-    if (lane == 0 && cg != ~0ull) atomicMin(cut, cg);
-}
-__global__ void __launch_bounds__(PLAN_FIN_THREADS) k_plan_sums(const uint16_t *__restrict__ schema, const uint32_t *__restrict__ nfrags,
-                                                                const uint64_t *__restrict__ off, uint64_t g0, uint32_t n_groups,
-                                                                const uint16_t *__restrict__ live, uint32_t n_live,
-                                                                unsigned long long *hist, uint32_t hstride,
-                                                                unsigned long long *scratch, uint32_t parity,
-                                                                const uint8_t *__restrict__ status, BatchResult *res) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t s = blockIdx.x * (PLAN_FIN_THREADS / 32) + (threadIdx.x >> 5);
-    const uint64_t base = off[g0];
-    const uint64_t n_mol = off[g0 + n_groups] - base;
-    const uint32_t n_chunks = (uint32_t)((n_mol + HCH - 1) / HCH);
-    const unsigned long long cutv = scratch[1 + parity];
-    const uint64_t nc = (cutv == ~0ull) ? n_mol : off[cutv + 1] - base;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const unsigned long long fe = scratch[0];
-        res->cut_group = cutv;
-        res->n_commit = nc;
-        res->first_error = fe < nc ? fe : ~0ull;
-        res->error_code = fe < nc ? status[base + fe] : 0;
-        scratch[0] = ~0ull;            // ready for the next batch
-        scratch[1 + (parity ^ 1u)] = ~0ull;  // ... which uses the other cut slot (nobody reads it any more)
-    }
-    if (s >= n_live) return;
-    schema += base;
-    nfrags += base;
-    // inserts of this schema among the kept molecules: whole chunks from the histogram, the last from the molecules
-    const uint32_t full = (uint32_t)(nc / HCH);
-    const uint16_t sid = live[s];
-    unsigned long long *hs = hist + (uint64_t)s * hstride;
-    unsigned long long acc = 0;
-    for (uint32_t c = lane; c < full; c += 32) acc += hs[c];
-    for (uint64_t i = (uint64_t)full * HCH + lane; i < nc; i += 32)
-        if (schema[i] == sid) acc += nfrags[i];
-    for (int o = 16; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-    if (lane == 0) res->sums[s] = acc;
-    // leave the histogram all-zero for the next batch (this batch dirtied n_chunks columns of n_live rows)
-    for (uint32_t c = lane; c < n_chunks; c += 32) hs[c] = 0ull;
-}
+}  // namespace mmkdev
+#include "mmk_plan.cuh"
+namespace mmkdev {
 
 uint32_t plan_hist_chunks(uint64_t max_molecules) { return (uint32_t)((max_molecules + HCH - 1) / HCH); }
 
@@ -564,24 +410,24 @@ void plan_fill_slots(uint64_t g_lo, uint64_t g_hi, const uint32_t *d_nmol, const
     LAUNCH(k_fill_slots, (n + 255) / 256, 256, 0, st, g_lo, n, d_nmol, d_off, plan);
 }
 
-void plan_set_live(const uint16_t *d_live, uint32_t n_live, uint16_t *d_lpos, cudaStream_t st) {
-    LAUNCH(k_fill_lpos, (n_live + 255) / 256, 256, 0, st, d_live, n_live, d_lpos);
+void plan_init(PlanState *d_st, const PlanArrays &pa, uint32_t K, cudaStream_t st) {
+    LAUNCH(k_plan_init, (K + 255) / 256, 256, 0, st, d_st, pa, K);
 }
-
-void plan_batch(const SimConst &sc, const SchemaDev *d_sch, const uint16_t *d_live, const uint16_t *d_lpos, uint32_t n_live,
-                uint16_t epoch, uint64_t g0, uint32_t n_groups, const uint32_t *d_nmol, const uint64_t *d_off, PlanDev plan,
-                uint64_t max_mol, const int64_t *d_need, unsigned long long *d_hist, unsigned long long *d_scratch, uint32_t parity,
-                BatchResult *d_res, cudaStream_t st) {
-    (void)d_nmol;
-    // d_hist is all-zero, d_scratch[0] (first error) and d_scratch[1 + parity] (cut) all-ones on entry: k_plan_sums restores them
-    const uint32_t n_chunks = plan_hist_chunks(max_mol);
-    LAUNCH(k_plan_molecules, (unsigned)((max_mol + 127) / 128), 128, 0, st, sc, d_sch, d_live, d_lpos, n_live, epoch, g0, n_groups, d_off,
-           plan, d_hist, n_chunks, d_scratch);
-    const unsigned fin_blocks = (n_live + PLAN_FIN_THREADS / 32 - 1) / (PLAN_FIN_THREADS / 32);
-    LAUNCH(k_plan_cut, fin_blocks, PLAN_FIN_THREADS, 0, st, plan.schema, plan.nfrags, plan.group, d_off, g0, n_groups, d_live, n_live,
-           d_hist, n_chunks, d_need, d_scratch + 1 + parity);
-    LAUNCH(k_plan_sums, fin_blocks, PLAN_FIN_THREADS, 0, st, plan.schema, plan.nfrags, d_off, g0, n_groups, d_live, n_live, d_hist,
-           n_chunks, d_scratch, parity, plan.status, d_res);
+void plan_batches(const SimConst &sc, const SchemaDev *d_sch, PlanState *d_st, const PlanArrays &pa, const uint64_t *d_off, PlanDev plan,
+                  unsigned long long *d_first_err, int n_batches, cudaStream_t st) {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    const unsigned grid = (unsigned)sms * 8u;  // 2048 threads per SM: every batch is one wave, grid-stride inside
+    for (int k = 0; k < n_batches; ++k) {
+        LAUNCH(k_plan_molecules, grid, PLAN_THREADS, 0, st, sc, d_sch, d_st, pa, d_off, plan, d_first_err);
+        LAUNCH(k_plan_cut, (unsigned)sms, PLAN_THREADS, 0, st, d_st, pa, plan.schema, plan.nfrags, plan.group, d_off);
+        LAUNCH(k_plan_close, (unsigned)sms, PLAN_THREADS, 0, st, d_st, pa, plan.schema, plan.nfrags, d_off, plan.status, d_first_err);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -973,6 +819,104 @@ void place_segment_chain(const SimConst &sc, const SchemaDev *d_sch, PlanDev pla
     LAUNCH(k_place_chain, (nm + PLACE_BLOCK - 1) / PLACE_BLOCK, 256, 0, st, sc, d_sch, plan, mol0, m_lo, m_hi, d_read_off_local,
            pair_lo, (PairTmp *)d_tmp, d_acc_i, d_acc_f, d_ins, d_mol, d_err);
     LAUNCH(k_mol_text, (nm + 127) / 128, 128, 0, st, sc, d_sch, mol0, m_lo, m_hi, d_mol, d_text, text_stride);
+}
+
+// ------------------------------------------------------------------------------------------
+// fused placement: mmk_place.cuh
+// ------------------------------------------------------------------------------------------
+}  // namespace mmkdev
+#include "mmk_place.cuh"
+namespace mmkdev {
+
+static int place_tb() {  // tiles per block of k_place_block: 64 (default) or 32 (MMK_PLACE_TB, profiling)
+    const char *e = getenv("MMK_PLACE_TB");
+    return (e && atoi(e) == 32) ? 32 : 64;
+}
+uint32_t place_big_threshold() { return place_tb() == 32 ? PlbGeom<32>::BIG : PlbGeom<64>::BIG; }
+
+void place_local_roff(uint64_t mol0, uint32_t n_mol, const uint64_t *d_read_off_global, uint64_t *d_read_off_local, cudaStream_t st) {
+    LAUNCH(k_local_roff, (n_mol + 1 + 255) / 256, 256, 0, st, d_read_off_global, mol0, n_mol, d_read_off_local);
+}
+
+template <int TB>
+static void launch_place_block(const PlaceArgs &a, cudaStream_t st) {
+    static int ctas_per_sm[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t smem = PlbGeom<TB>::SMEM;
+    if (!ctas_per_sm[dev & 63]) {
+        cudaFuncSetAttribute(k_place_block<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int n = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_place_block<TB>, PLB_THREADS, smem);
+        ctas_per_sm[dev & 63] = n > 0 ? n : 1;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(a.n_blocks, (uint64_t)sms * ctas_per_sm[dev & 63]);
+    LAUNCH((k_place_block<TB>), grid, PLB_THREADS, smem, st, a);
+}
+
+void place_fused(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint64_t n_pairs,
+                 uint32_t n_tiles, const uint64_t *d_roff_l, uint32_t *d_tile_mol0, const InsTable *d_tab, uint32_t *d_big_list,
+                 uint32_t *d_big_count, uint32_t big_cap, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
+                 uint4 *d_fdesc, uint32_t *d_sum1, uint32_t *d_sum2, uint8_t *d_tile_flags, unsigned long long *d_gather,
+                 unsigned long long *d_err, uint32_t stage_cap, int bpb, cudaStream_t st) {
+    if (n_mol == 0 || n_pairs == 0) return;
+    const int tb = place_tb();
+    const uint32_t big = place_big_threshold();
+    cudaMemsetAsync(d_big_count, 0, 4, st);
+    LAUNCH(k_tile_mol0_big, (n_mol + 255) / 256, 256, 0, st, d_roff_l, n_mol, 32u, d_tile_mol0, big, d_big_list, d_big_count, big_cap);
+    PlaceArgs a;
+    a.sc = sc;
+    a.sch = d_sch;
+    a.plan = plan;
+    a.mol0 = mol0;
+    a.n_mol = n_mol;
+    a.n_tiles = n_tiles;
+    a.n_pairs = n_pairs;
+    a.roff = d_roff_l;
+    a.tile_mol0 = d_tile_mol0;
+    a.tab = d_tab;
+    a.big_list = d_big_list;
+    a.big_count = d_big_count;
+    a.ins = d_ins;
+    a.mol = d_mol;
+    a.fdesc = d_fdesc;
+    a.sum1 = d_sum1;
+    a.sum2 = d_sum2;
+    a.tile_flags = d_tile_flags;
+    a.gather = d_gather;
+    a.err = d_err;
+    a.stage_cap = stage_cap;
+    a.bpb = bpb;
+    a.n_blocks = (n_tiles + (uint32_t)tb - 1) / (uint32_t)tb;
+    // molecules too long for a block's shared-memory window first (the count lives on the device: fixed grid, grid-stride loop)
+    LAUNCH(k_place_big, (unsigned)std::min<uint32_t>(big_cap, 148u * 4u), PLB_THREADS, 0, st, a);
+    if (tb == 32) launch_place_block<32>(a, st);
+    else launch_place_block<64>(a, st);
+    LAUNCH(k_mol_text, (n_mol + 127) / 128, 128, 0, st, sc, d_sch, mol0, 0u, n_mol, d_mol, d_text, text_stride);
+}
+
+__global__ void k_kat_insert_len(const __grid_constant__ SimConst sc, const InsTable *__restrict__ gtab, const uint64_t *__restrict__ bits,
+                                 uint32_t *len, uint8_t *slow, int64_t n) {
+    __shared__ InsTable tab;
+    stage_table(&tab, gtab);
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t x = bits[i];
+    uint32_t l = 0;
+    uint8_t sl = 0;
+    if (!(tab.enabled && ins_len_fast(tab, (uint32_t)(x >> 32), l))) {  // the exact definition; 0 = rejected by the truncation
+        sl = 1;
+        const double z = mmk_bits_to_normal(x);
+        l = (sc.ins_robert || z < sc.ins_lb) ? 0u : insert_len_of(MMK_ADD(sc.ins_mu, MMK_MUL(sc.ins_sd, z)));
+    }
+    len[i] = l;
+    slow[i] = sl;
+}
+void kat_insert_len(const SimConst &sc, const InsTable *d_tab, const uint64_t *d_bits, uint32_t *d_len, uint8_t *d_slow, int64_t n, cudaStream_t st) {
+    if (n > 0) LAUNCH(k_kat_insert_len, (unsigned)((n + 255) / 256), 256, 0, st, sc, d_tab, d_bits, d_len, d_slow, n);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -7,6 +7,7 @@
 // file only sequences kernels and moves small control values.
 #include <math.h>
 #include <stdarg.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -106,12 +107,12 @@ struct mmk_ctx {
     DBuf<uint64_t> d_goff;      // group table: first molecule of every group
     uint64_t g_tab = 0;         // groups covered by the table
     DBuf<uint16_t> d_live, d_lpos;
-    DBuf<int64_t> d_need;
-    DBuf<unsigned long long> d_hist, d_first_err;
-    DBuf<uint8_t> d_res;
+    DBuf<int64_t> d_need, d_required, d_current;
+    DBuf<unsigned long long> d_hist, d_first_err, d_sums;
+    DBuf<uint32_t> d_epoch_nlive;
+    DBuf<PlanState> d_pstate;   // the planner's control block (mmk_plan.cuh)
+    PlanState *h_pstate = nullptr;  // pinned mirror, read once per round of batches
     DBuf<uint64_t> d_scan_tmp;
-    uint8_t *h_res = nullptr;   // pinned: batch result + per-schema need
-    size_t h_res_cap = 0;
     // placement / chunking scratch, kept between calls
     DBuf<uint64_t> s_bounds, s_b1, s_b2;
     DBuf<unsigned long long> s_err, s_gather;
@@ -133,6 +134,9 @@ struct mmk_ctx {
     DBuf<uint4> d_fdesc;
     DBuf<uint8_t> d_tile_flags;
     DBuf<uint8_t> d_tmp, d_tmp2;  // placement scratch: (gap bits, insert length) per pair of one segment (two alternate)
+    DBuf<InsTable> d_instab;  // insert-length threshold table (built by mmk_create)
+    InsTable *h_instab = nullptr;
+    DBuf<uint32_t> d_big_list, d_big_count;  // molecules too long for the fused placement's shared-memory window
     DBuf<uint32_t> d_acc_i;   // placement scratch: sum of insert lengths per molecule
     DBuf<unsigned long long> d_acc_f;  // ... and a 2^-16 fixed-point lower bound of their real sum
     uint32_t text_stride = 0, tile_pairs = 64, n_tiles = 0, stage_cap = 0;
@@ -306,6 +310,87 @@ static uint64_t barcode_capacity(int bc) {
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// insert-length threshold table (mmk_place.cuh explains the scheme)
+// ------------------------------------------------------------------------------------------
+static const uint32_t INS_GUARD_HOST = 16;  // must equal INS_GUARD in mmk_place.cuh
+// trunc(Int, mu + sd z(u)) of the 52-bit draw u, 0 when the truncation at 200 rejects it (z < lb)
+static uint32_t exact_insert_len(const SimConst &sc, uint64_t u52) {
+    const double z = mmk_bits_to_normal(u52 << 12);
+    if (z < sc.ins_lb) return 0;
+    const double x = MMK_ADD(sc.ins_mu, MMK_MUL(sc.ins_sd, z));
+    uint32_t li = x > 0 ? (uint32_t)(long long)x : 0u;
+    return li > 0x00ffffffu ? 0x00ffffffu : li;
+}
+static bool table_insert_len(const InsTable &t, uint32_t u32, uint32_t &len) {  // host twin of ins_len_fast
+    const uint32_t c = u32 >> (32 - INS_CELL_BITS);
+    uint32_t lo = t.cell[c], hi = t.cell[c + 1];
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (t.thr[mid] <= u32) lo = mid + 1; else hi = mid;
+    }
+    len = t.base_len + lo;
+    const bool below_ok = lo == 0 || u32 - t.thr[lo - 1] > INS_GUARD_HOST;
+    const bool above_ok = lo == t.n_thr || t.thr[lo] - u32 > INS_GUARD_HOST;
+    return below_ok && above_ok && u32 >= t.u_lo && u32 <= t.u_hi;
+}
+template <class Pred>
+static uint64_t first_u52(uint64_t lo, uint64_t hi, Pred pred) {  // smallest u in [lo, hi] with pred(u), hi + 1 if none (pred monotone)
+    if (!pred(hi)) return hi + 1;
+    while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        if (pred(mid)) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+static void build_insert_table(const SimConst &sc, InsTable &t) {
+    memset(&t, 0, sizeof t);
+    if (sc.ins_robert || !(sc.ins_sd > 0.0)) return;  // the table tabulates the rejection sampler's first (accepted) normal
+    const uint64_t U = (1ull << 52) - 1;
+    const double zmax = std::min(7.9, 990.0 / sc.ins_sd);
+    const double zmin = std::max(-zmax, sc.ins_lb);
+    if (!(zmin < zmax)) return;
+    const uint64_t ua = first_u52(0, U, [&](uint64_t u) { return mmk_bits_to_normal(u << 12) >= zmin; });
+    const uint64_t ub = first_u52(0, U, [&](uint64_t u) { return mmk_bits_to_normal(u << 12) > zmax; }) - 1;
+    if (ua > U || ub <= ua || (ub >> 20) < (ua >> 20) + 4 * INS_GUARD_HOST + 8) return;
+    const uint32_t base = exact_insert_len(sc, ua), top = exact_insert_len(sc, ub);
+    if (base == 0 || top < base || top - base > (uint32_t)INS_MAX_THR) return;
+    t.base_len = base;
+    t.n_thr = top - base;
+    for (uint32_t k = 0; k < t.n_thr; ++k) {
+        const uint32_t L = base + k + 1;
+        const uint64_t T = first_u52(ua, ub, [&](uint64_t u) { return exact_insert_len(sc, u) >= L; });
+        t.thr[k] = (uint32_t)(T >> 20);
+    }
+    t.u_lo = (uint32_t)(ua >> 20) + 1 + INS_GUARD_HOST;
+    t.u_hi = (uint32_t)(ub >> 20) - 1 - INS_GUARD_HOST;
+    {
+        uint32_t k = 0;
+        for (uint32_t c = 0; c <= (uint32_t)INS_CELLS; ++c) {
+            const uint64_t edge = (uint64_t)c << (32 - INS_CELL_BITS);
+            while (k < t.n_thr && (uint64_t)t.thr[k] < edge) ++k;
+            t.cell[c] = (uint16_t)k;
+        }
+    }
+    t.enabled = 1;
+    // self-check against the definition: both edges of the guard band of every threshold, the range ends, and a sweep
+    auto agrees = [&](uint32_t u32) {
+        uint32_t fast;
+        if (!table_insert_len(t, u32, fast)) return true;  // exact path on the device
+        return fast == exact_insert_len(sc, (uint64_t)u32 << 20) && fast == exact_insert_len(sc, ((uint64_t)u32 << 20) | 0xfffffu);
+    };
+    bool ok = true;
+    for (uint32_t k = 0; k < t.n_thr && ok; ++k)
+        for (uint32_t d = INS_GUARD_HOST + 1; d <= INS_GUARD_HOST + 2 && ok; ++d) ok = agrees(t.thr[k] - d) && agrees(t.thr[k] + d);
+    ok = ok && agrees(t.u_lo) && agrees(t.u_hi);
+    uint64_t x = 0x9E3779B97F4A7C15ull;
+    for (int i = 0; i < 20000 && ok; ++i) {
+        x ^= x << 13, x ^= x >> 7, x ^= x << 17;
+        ok = agrees((uint32_t)(x >> 32));
+    }
+    if (!ok) t.enabled = 0;  // never observed; the exact path is always correct
+}
+
 extern "C" int32_t mmk_create(const mmk_params *p, mmk_ctx **out) {
     if (!p || !out) return MMK_ERR_INVALID_ARG;
     *out = nullptr;
@@ -411,6 +496,11 @@ extern "C" int32_t mmk_create(const mmk_params *p, mmk_ctx **out) {
     }
     CU(cudaMalloc((void **)&ctx->d_stats, sizeof(ContigStats)));
     CU(cudaMallocHost((void **)&ctx->h_stats, sizeof(ContigStats)));
+    ctx->h_instab = new InsTable();
+    build_insert_table(sc, *ctx->h_instab);
+    CU(ctx->d_instab.ensure(1));
+    CU(cudaMemcpyAsync(ctx->d_instab.p, ctx->h_instab, sizeof(InsTable), cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
     return MMK_OK;
 }
 
@@ -437,8 +527,9 @@ extern "C" void mmk_destroy(mmk_ctx *c) {
     free_outputs(c);
     if (c->d_stats) cudaFree(c->d_stats);
     if (c->h_stats) cudaFreeHost(c->h_stats);
-    if (c->h_res) cudaFreeHost(c->h_res);
+    if (c->h_pstate) cudaFreeHost(c->h_pstate);
     if (c->h_bz_tot) cudaFreeHost(c->h_bz_tot);
+    delete c->h_instab;
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     for (int i = 0; i < 2; ++i) {
@@ -1045,124 +1136,116 @@ extern "C" int32_t mmk_plan(mmk_ctx *ctx, mmk_plan_info *out) {
     }
     if (!ctx->schemas_ready) return fail(ctx, MMK_ERR_STATE, "schemas not built");
     const uint32_t K = (uint32_t)ctx->schemas.size();
+    if (K == 0) return fail(ctx, MMK_ERR_STATE, "no schemas");
     for (auto &s : ctx->schemas) s.current = 0;
     ctx->placed = false;
     ctx->planned = false;
     ctx->tile_cursor = 0;
     ctx->epoch_nlive.clear();
+    ctx->n_mol = 0;
 
     const uint32_t max_nmol = ctx->sc.nmol_fixed > 0 ? (uint32_t)ctx->sc.nmol_fixed
                                                      : (uint32_t)nearbyint(2.5 * (double)ctx->par.n_molecules) + 1;
-    const uint64_t Bmax = ctx->par.plan_batch_groups > 0 ? (uint64_t)ctx->par.plan_batch_groups : (1ull << 20);
-    const uint64_t Bmin = std::min<uint64_t>(Bmax, 8192);
-
-    std::vector<uint16_t> live(K);
-    for (uint32_t i = 0; i < K; ++i) live[i] = (uint16_t)i;
-    CU(ctx->d_live.ensure(K ? K : 1));
-    CU(ctx->d_lpos.ensure(65536));
-    CU(ctx->d_need.ensure(K ? K : 1));
-    CU(ctx->d_first_err.ensure(3));  // first error, cut of even / odd batches
-    const size_t res_bytes = sizeof(BatchResult) + (size_t)K * 8;
-    CU(ctx->d_res.ensure(res_bytes));
-    if (ctx->h_res_cap < res_bytes + (size_t)K * 8) {  // pinned: the per-batch control round trip is latency-bound
-        if (ctx->h_res) cudaFreeHost(ctx->h_res);
-        ctx->h_res = nullptr;
-        CU(cudaMallocHost((void **)&ctx->h_res, res_bytes + (size_t)K * 8 + 64));
-        ctx->h_res_cap = res_bytes + (size_t)K * 8;
+    uint64_t Bmax = ctx->par.plan_batch_groups > 0 ? (uint64_t)ctx->par.plan_batch_groups : (1ull << 20);
+    {   // the insert histogram holds one row per live schema and one column per 512 molecules of a batch: bound it to 256 MB
+        const uint64_t max_cols = std::max<uint64_t>((256ull << 20) / 8 / K, 64);
+        Bmax = std::max<uint64_t>(1, std::min<uint64_t>(Bmax, max_cols * 512 / max_nmol));
     }
-    uint8_t *h_res = ctx->h_res;
-    int64_t *need = (int64_t *)(ctx->h_res + ((res_bytes + 15) & ~(size_t)15));
+    const uint64_t Bmin = std::min<uint64_t>(Bmax, 8192);
+    const uint32_t hstride = plan_hist_chunks(Bmax * max_nmol) + 1;
+
+    // control block, trackers, scratch
+    CU(ctx->d_live.ensure(K));
+    CU(ctx->d_lpos.ensure(65536));
+    CU(ctx->d_need.ensure(K));
+    CU(ctx->d_required.ensure(K));
+    CU(ctx->d_current.ensure(K));
+    CU(ctx->d_sums.ensure(K));
+    CU(ctx->d_epoch_nlive.ensure(65536));
+    CU(ctx->d_first_err.ensure(1));
+    CU(ctx->d_pstate.ensure(1));
+    CU(ctx->d_hist.ensure((size_t)hstride * K));
+    if (!ctx->h_pstate) CU(cudaMallocHost((void **)&ctx->h_pstate, sizeof(PlanState)));
+    CU(cudaMemsetAsync(ctx->d_hist.p, 0, (size_t)hstride * K * sizeof(unsigned long long), ctx->st));
+    CU(cudaMemsetAsync(ctx->d_first_err.p, 0xff, 8, ctx->st));
+    std::vector<int64_t> required(K);
+    for (uint32_t i = 0; i < K; ++i) required[i] = ctx->schemas[i].required;
+    CU(cudaMemcpyAsync(ctx->d_required.p, required.data(), (size_t)K * 8, cudaMemcpyHostToDevice, ctx->st));
+    PlanArrays pa;
+    pa.live = ctx->d_live.p;
+    pa.lpos = ctx->d_lpos.p;
+    pa.required = ctx->d_required.p;
+    pa.current = ctx->d_current.p;
+    pa.need = ctx->d_need.p;
+    pa.sums = ctx->d_sums.p;
+    pa.hist = ctx->d_hist.p;
+    pa.epoch_nlive = ctx->d_epoch_nlive.p;
 
     // the group table is rebuilt by every call (no state is carried between runs)
     ctx->g_tab = 0;
     CU(ctx->d_goff.ensure(1));
     CU(cudaMemsetAsync(ctx->d_goff.p, 0, 8, ctx->st));
+    {
+        int32_t rc = ensure_group_table(ctx, Bmin, 0, 0);
+        if (rc) return rc;
+    }
+    PlanState &hs = *ctx->h_pstate;
+    memset(&hs, 0, sizeof hs);
+    hs.B = Bmin;
+    hs.Bmin = Bmin;
+    hs.Bmax = Bmax;
+    hs.g_tab = ctx->g_tab;
+    hs.barcode_cap = barcode_capacity(ctx->par.bc_format);
+    hs.cut = ~0ull;
+    hs.n_live = K;
+    hs.hstride = hstride;
+    CU(cudaMemcpyAsync(ctx->d_pstate.p, &hs, sizeof hs, cudaMemcpyHostToDevice, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));  // `required` and the staged state are host temporaries
+    plan_init(ctx->d_pstate.p, pa, K, ctx->st);
 
-    uint64_t g0 = 0, n_mol = 0, total_need = 0;
-    for (auto &s : ctx->schemas) total_need += (uint64_t)std::max<int64_t>(s.required, 0);
-    uint64_t B = Bmin;
-    int64_t n_batches = 0, n_epochs = 0;
-    bool live_dirty = true;
-    bool hist_clean = false;  // a failed earlier call may have left the scratch dirty: clean it once per plan
-    double inserts_per_group = 0.0;  // running estimate, all live schemas together
-    while (!live.empty()) {
-        const uint32_t n_live = (uint32_t)live.size();
-        if (live_dirty) {
-            CU(cudaMemcpyAsync(ctx->d_live.p, live.data(), n_live * 2, cudaMemcpyHostToDevice, ctx->st));
-            plan_set_live(ctx->d_live.p, n_live, ctx->d_lpos.p, ctx->st);
-            ctx->epoch_nlive.push_back(n_live);
-            if (ctx->epoch_nlive.size() > 65535) return fail(ctx, MMK_ERR_UNSUPPORTED, "more than 65535 pruning epochs");
-            live_dirty = false;
-        }
-        int64_t min_need = INT64_MAX;
-        uint64_t remaining_need = 0;
-        for (uint32_t i = 0; i < n_live; ++i) {
-            need[i] = ctx->schemas[live[i]].required - ctx->schemas[live[i]].current;
-            min_need = std::min(min_need, need[i]);
-            remaining_need += (uint64_t)std::max<int64_t>(need[i], 0);
-        }
-        // size the batch to reach the next pruning point with a small overshoot
-        if (inserts_per_group > 0.0 && min_need > 0) {
-            double est = (double)min_need * (double)n_live / inserts_per_group;
-            B = (uint64_t)std::min<double>((double)Bmax, std::max<double>((double)Bmin, est * 1.03 + 2048.0));
-        } else if (min_need <= 0)
-            B = Bmin;
-        const uint32_t nb = (uint32_t)B;
-        {   // table: this batch, and — once the rate is known — the expected rest of the run in one extension
-            uint64_t want = g0 + nb;
-            if (inserts_per_group > 0.0) want = std::max<uint64_t>(want, g0 + (uint64_t)((double)remaining_need / inserts_per_group * 1.05) + 4096);
-            if (g0 + nb > ctx->g_tab) {
-                int32_t rc = ensure_group_table(ctx, want, g0, n_mol);
-                if (rc) return rc;
-            }
-        }
-        const uint64_t max_mol = (uint64_t)nb * max_nmol;
-        {   // the batch kernels keep the histogram all-zero and the first-error slot all-ones between batches
-            const size_t want_hist = (size_t)plan_hist_chunks(max_mol) * n_live;
-            if (want_hist > ctx->d_hist.cap || !hist_clean) {
-                CU(ctx->d_hist.ensure(want_hist));
-                CU(cudaMemsetAsync(ctx->d_hist.p, 0, ctx->d_hist.cap * sizeof(unsigned long long), ctx->st));
-                CU(cudaMemsetAsync(ctx->d_first_err.p, 0xff, 3 * 8, ctx->st));
-                hist_clean = true;
-            }
-        }
-        // `need` and the batch result live in pinned host memory the kernel reads / writes directly: two fewer copy
-        // operations on the critical path of every batch
-        plan_batch(ctx->sc, ctx->d_sch.p, ctx->d_live.p, ctx->d_lpos.p, n_live, (uint16_t)(ctx->epoch_nlive.size() - 1), g0, nb,
-                   ctx->d_gnmol.p, ctx->d_goff.p, plan_dev(ctx), max_mol, need, ctx->d_hist.p, ctx->d_first_err.p,
-                   (uint32_t)(n_batches & 1), (BatchResult *)h_res, ctx->st);
+    // rounds of batches: the first batch alone (it measures the insert rate that sizes the group table), then 16 at a time
+    int round_batches = 1;
+    for (int round = 0;; ++round) {
+        if (round > 100000) return fail(ctx, MMK_ERR_CUDA, "planner does not terminate (internal error)");
+        plan_batches(ctx->sc, ctx->d_sch.p, ctx->d_pstate.p, pa, ctx->d_goff.p, plan_dev(ctx), ctx->d_first_err.p, round_batches, ctx->st);
+        CU(cudaMemcpyAsync(&hs, ctx->d_pstate.p, sizeof hs, cudaMemcpyDeviceToHost, ctx->st));
         CU(cudaStreamSynchronize(ctx->st));
         CU(cudaGetLastError());
-        ++n_batches;
-        const BatchResult *r = (const BatchResult *)h_res;
-        if (r->first_error != ~0ull) {
-            ctx->n_mol = 0;
-            return fail(ctx, (int32_t)r->error_code, "molecule %llu: %s", (unsigned long long)(n_mol + r->first_error),
-                        mmk_strerror((int32_t)r->error_code));
+        if (hs.error_code)
+            return fail(ctx, (int32_t)hs.error_code, hs.error_code == MMK_ERR_BARCODES_EXHAUSTED
+                                                         ? "There are no more barcodes available for the selected barcode type (molecule %llu)."
+                                                         : "molecule %llu: %s",
+                        (unsigned long long)hs.error_mol, mmk_strerror((int32_t)hs.error_code));
+        if (hs.done) break;
+        // table for the expected rest of the run in one extension (5 % margin); a run that outlives it asks again
+        uint64_t want = hs.g0 + hs.B;
+        if (hs.rate > 0.0) want = std::max<uint64_t>(want, hs.g0 + (uint64_t)((double)hs.remaining_need / hs.rate * 1.05) + 4096);
+        if (hs.need_table || want > ctx->g_tab) {
+            int32_t rc = ensure_group_table(ctx, want, hs.g0, hs.n_mol);
+            if (rc) return rc;
+            uint64_t patch[1] = {ctx->g_tab};
+            uint32_t zero = 0;
+            CU(cudaMemcpyAsync((char *)ctx->d_pstate.p + offsetof(PlanState, g_tab), patch, 8, cudaMemcpyHostToDevice, ctx->st));
+            CU(cudaMemcpyAsync((char *)ctx->d_pstate.p + offsetof(PlanState, need_table), &zero, 4, cudaMemcpyHostToDevice, ctx->st));
+            if (hs.need_table) {  // the device stopped with nothing left to plan: give the next batch its size back
+                uint64_t nb = std::min<uint64_t>(std::max<uint64_t>(hs.B, Bmin), ctx->g_tab - hs.g0);
+                CU(cudaMemcpyAsync((char *)ctx->d_pstate.p + offsetof(PlanState, B), &nb, 8, cudaMemcpyHostToDevice, ctx->st));
+            }
+            CU(cudaStreamSynchronize(ctx->st));
         }
-        uint64_t batch_inserts = 0;
-        for (uint32_t i = 0; i < n_live; ++i) {
-            ctx->schemas[live[i]].current += (int64_t)r->sums[i];
-            batch_inserts += r->sums[i];
-        }
-        n_mol += r->n_commit;
-        const uint64_t groups_done = (r->cut_group == ~0ull) ? nb : (r->cut_group - g0 + 1);
-        if (groups_done > 0 && batch_inserts > 0) inserts_per_group = (double)batch_inserts / (double)groups_done;
-        g0 += groups_done;
-        if (r->cut_group != ~0ull) {  // filter!(is_incomplete, schema), Main.jl:58
-            std::vector<uint16_t> nl;
-            for (uint16_t s : live)
-                if (ctx->schemas[s].current < ctx->schemas[s].required) nl.push_back(s);
-            if (nl.size() == live.size()) return fail(ctx, MMK_ERR_CUDA, "planner cut without a completed schema (internal error)");
-            live.swap(nl);
-            live_dirty = true;
-            ++n_epochs;
-        }
-        if (n_mol > barcode_capacity(ctx->par.bc_format))
-            return fail(ctx, MMK_ERR_BARCODES_EXHAUSTED, "There are no more barcodes available for the selected barcode type.");
+        round_batches = 16;
     }
+    const uint64_t n_mol = hs.n_mol;
     ctx->n_mol = n_mol;
-    ctx->n_groups = g0;
+    ctx->n_groups = hs.g0;
+    {   // trackers and the live-set size of every epoch back to the host
+        std::vector<int64_t> cur(K);
+        ctx->epoch_nlive.resize((size_t)hs.epoch + 1);
+        CU(cudaMemcpyAsync(cur.data(), ctx->d_current.p, (size_t)K * 8, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaMemcpyAsync(ctx->epoch_nlive.data(), ctx->d_epoch_nlive.p, ctx->epoch_nlive.size() * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        for (uint32_t i = 0; i < K; ++i) ctx->schemas[i].current = cur[i];
+    }
     // first pair of every molecule
     CU(ctx->d_read_off.ensure(n_mol + 1));
     CU(ctx->d_scan_tmp.ensure((size_t)n_mol / 1024 + 8));
@@ -1172,11 +1255,11 @@ extern "C" int32_t mmk_plan(mmk_ctx *ctx, mmk_plan_info *out) {
     CU(cudaStreamSynchronize(ctx->st));
     ctx->n_pairs = total;
     ctx->planned = true;
-    ctx->plan_info.n_groups = (int64_t)g0;
+    ctx->plan_info.n_groups = (int64_t)hs.g0;
     ctx->plan_info.n_molecules = (int64_t)n_mol;
     ctx->plan_info.n_pairs = (int64_t)total;
-    ctx->plan_info.n_epochs = n_epochs;
-    ctx->plan_info.n_batches = n_batches;
+    ctx->plan_info.n_epochs = (int64_t)hs.n_epochs;
+    ctx->plan_info.n_batches = (int64_t)hs.n_batches;
     ctx->plan_info.host_ms = now_ms() - t_begin;
     if (out) *out = ctx->plan_info;
     return MMK_OK;
@@ -1194,6 +1277,8 @@ extern "C" int32_t mmk_set_shard(mmk_ctx *ctx, int32_t rank, int32_t world) {
 // ------------------------------------------------------------------------------------------
 // placement + tile offsets for this shard
 // ------------------------------------------------------------------------------------------
+static const bool PLACE_FUSED_DEFAULT = false;  // MMK_PLACE_MODE=fused|legacy overrides (tests run both)
+
 static EmitArgs base_args(mmk_ctx *c) {
     EmitArgs a;
     memset(&a, 0, sizeof a);
@@ -1289,8 +1374,13 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     CU(cudaMemcpyAsync(d_err.p, init, sizeof init, cudaMemcpyHostToDevice, ctx->st));
     ctx->n_tiles = (uint32_t)((ctx->s_npairs + ctx->tile_pairs - 1) / ctx->tile_pairs);
     CU(ctx->d_tile_mol0.ensure((size_t)ctx->n_tiles + 1));
-    place_prepare(ctx->mol0, (uint32_t)ctx->s_nmol, ctx->d_read_off.p, ctx->d_roff_l.p, ctx->d_tile_mol0.p, ctx->tile_pairs, ctx->st);
-    // per-tile outputs of k_tile_prepare, launched per segment below
+    // Fused placement (mmk_place.cuh) needs 32-pair tiles; MMK_PLACE_LEGACY=1 keeps the three-kernel path (draws → chain →
+    // tile preparation through global scratch), which also serves other tile sizes.
+    bool fused = ctx->tile_pairs == 32 && PLACE_FUSED_DEFAULT;
+    if (const char *e = getenv("MMK_PLACE_MODE")) fused = ctx->tile_pairs == 32 && strcmp(e, "fused") == 0;
+    if (fused) place_local_roff(ctx->mol0, (uint32_t)ctx->s_nmol, ctx->d_read_off.p, ctx->d_roff_l.p, ctx->st);
+    else place_prepare(ctx->mol0, (uint32_t)ctx->s_nmol, ctx->d_read_off.p, ctx->d_roff_l.p, ctx->d_tile_mol0.p, ctx->tile_pairs, ctx->st);
+    // per-tile outputs of the placement, launched per segment below
     DBuf<uint32_t> &d_sum1 = ctx->s_sum1, &d_sum2 = ctx->s_sum2;
     CU(d_sum1.ensure((size_t)ctx->n_tiles + 1));
     CU(d_sum2.ensure((size_t)ctx->n_tiles + 1));
@@ -1303,6 +1393,15 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     CU(ctx->d_fdesc.ensure(ctx->s_npairs + 1));
     CU(ctx->d_tile_flags.ensure((size_t)ctx->n_tiles + 1));
     const EmitArgs targs = base_args(ctx);
+    if (fused) {
+        const uint32_t big_cap = (uint32_t)(ctx->s_npairs / place_big_threshold() + 1);
+        CU(ctx->d_big_list.ensure(big_cap));
+        CU(ctx->d_big_count.ensure(1));
+        place_fused(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->mol0, (uint32_t)ctx->s_nmol, ctx->s_npairs, ctx->n_tiles, ctx->d_roff_l.p,
+                    ctx->d_tile_mol0.p, ctx->d_instab.p, ctx->d_big_list.p, ctx->d_big_count.p, big_cap, ctx->d_ins.p, ctx->d_mol.p,
+                    ctx->d_text.p, ctx->text_stride, ctx->d_fdesc.p, d_sum1.p, d_sum2.p, ctx->d_tile_flags.p, d_gather.p, d_err.p,
+                    ctx->stage_cap, ctx->bpb, ctx->st);
+    } else
     {   // Segments of at most SEG pairs bound the scratch of the flat per-pair draws.  The draws of segment k + 1
         // (compute-bound) run on the main stream while the chain of segment k (latency-bound) runs on the second
         // stream; two scratch buffers alternate.
@@ -2011,4 +2110,46 @@ extern "C" int32_t mmk_kat_math(mmk_ctx *ctx, int32_t kind, const double *in, do
     CU(cudaStreamSynchronize(ctx->st));
     CU(cudaGetLastError());
     return MMK_OK;
+}
+extern "C" int32_t mmk_kat_insert_len(mmk_ctx *ctx, const uint64_t *bits, uint32_t *len, uint8_t *slow, int64_t n) {
+    if (!ctx || !bits || !len || !slow || n < 0) return MMK_ERR_INVALID_ARG;
+    CU(cudaSetDevice(ctx->par.device));
+    DBuf<uint64_t> d_bits;
+    DBuf<uint32_t> d_len;
+    DBuf<uint8_t> d_slow;
+    CU(d_bits.ensure((size_t)n + 1));
+    CU(d_len.ensure((size_t)n + 1));
+    CU(d_slow.ensure((size_t)n + 1));
+    CU(cudaMemcpyAsync(d_bits.p, bits, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->st));
+    kat_insert_len(ctx->sc, ctx->d_instab.p, d_bits.p, d_len.p, d_slow.p, n, ctx->st);
+    CU(cudaMemcpyAsync(len, d_len.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaMemcpyAsync(slow, d_slow.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaGetLastError());
+    return MMK_OK;
+}
+extern "C" int32_t mmk_insert_table(int32_t insert_length, int32_t insert_stdev, uint32_t *enabled, uint32_t *n_thr, uint32_t *base_len,
+                                    uint32_t *u_lo, uint32_t *u_hi, uint32_t *guard, uint32_t *thr, uint32_t thr_cap) {
+    if (!enabled || !n_thr || !base_len || !u_lo || !u_hi || !guard) return MMK_ERR_INVALID_ARG;
+    SimConst sc;
+    memset(&sc, 0, sizeof sc);
+    sc.ins_mu = (double)insert_length;
+    sc.ins_sd = (double)insert_stdev;
+    sc.ins_lb = MMK_DIV(MMK_SUB(200.0, sc.ins_mu), sc.ins_sd);
+    sc.ins_robert = (0.5 * erfc(sc.ins_lb / sqrt(2.0)) > 0.3) ? 0 : 1;
+    InsTable *t = new InsTable();
+    build_insert_table(sc, *t);
+    *enabled = t->enabled;
+    *n_thr = t->n_thr;
+    *base_len = t->base_len;
+    *u_lo = t->u_lo;
+    *u_hi = t->u_hi;
+    *guard = INS_GUARD_HOST;
+    int32_t rc = MMK_OK;
+    if (thr) {
+        if (thr_cap < t->n_thr) rc = MMK_ERR_INVALID_ARG;
+        else memcpy(thr, t->thr, (size_t)t->n_thr * 4);
+    }
+    delete t;
+    return rc;
 }

@@ -30,6 +30,19 @@ struct SimConst {
     int32_t fq_format, bc_format;
 };
 
+// Insert-length table (mmk_place.cuh): trunc(mu + sd * Phi^-1) of the top 32 bits of a draw by search among thresholds.
+constexpr int INS_CELL_BITS = 9, INS_CELLS = 1 << INS_CELL_BITS, INS_MAX_THR = 2048;
+struct InsTable {
+    uint32_t enabled;   // 0: every draw takes the double-precision path
+    uint32_t n_thr;     // thresholds in thr[]
+    uint32_t base_len;  // length of a draw below thr[0]
+    uint32_t u_lo, u_hi;  // table valid for top-32 draws in [u_lo, u_hi] (accepted by the truncation, inside the tabulated range)
+    uint32_t pad[3];
+    uint32_t thr[INS_MAX_THR];     // top 32 of the 52 bits of the smallest draw whose length is base_len + k + 1, ascending
+    uint16_t cell[INS_CELLS + 8];  // cell[c] = #thresholds below c << (32 - INS_CELL_BITS); cell[INS_CELLS] = n_thr
+};
+static_assert(sizeof(InsTable) % 16 == 0, "InsTable is staged with 16-byte copies");
+
 // One (contig, haplotype) unit as the kernels see it.
 struct SchemaDev {
     uint64_t word_off;  // first 32-bit word of the packed haplotype in the arena
@@ -62,13 +75,29 @@ struct PlanDev {
     uint8_t *status;
 };
 
-struct BatchResult {  // device→host after every speculative batch
-    uint64_t cut_group;   // first group at whose end a live schema reaches its target, or ~0
-    uint64_t n_commit;    // molecules of the batch to keep
-    uint64_t first_error; // batch-local index of the first molecule with status != 0 among kept, or ~0
-    uint32_t error_code;
-    uint32_t pad;
-    uint64_t sums[1];     // [n_live] inserts added per live schema by the kept molecules
+// Control block of the planner, in device memory (mmk_plan.cuh); the host reads it back once per round of batches.
+struct PlanState {
+    uint64_t g0;              // first barcode group of the next batch
+    uint64_t n_mol;           // molecules committed so far
+    uint64_t g_tab;           // groups the group table covers (host-maintained)
+    uint64_t B;               // groups in the next batch
+    uint64_t Bmin, Bmax;
+    uint64_t barcode_cap;     // barcodes the enumerator can produce (Barcodes.jl:75)
+    uint64_t remaining_need;  // inserts still missing over all live schemas
+    uint64_t error_mol;
+    double rate;              // inserts per barcode group, running estimate
+    unsigned long long cut;   // scratch: cut group of the batch in flight (atomicMin), ~0 = none
+    uint32_t n_live, epoch, done, need_table, error_code, n_batches, n_epochs, warps_done, hstride, pad;
+};
+struct PlanArrays {
+    uint16_t *live;            // [K] live schemas in first-seen order
+    uint16_t *lpos;            // [65536] schema -> position in `live`
+    const int64_t *required;   // [K] by schema
+    int64_t *current;          // [K] by schema
+    int64_t *need;             // [K] by live position: required - current
+    unsigned long long *sums;  // [K] by live position: scratch of k_plan_close
+    unsigned long long *hist;  // [n_live][hstride] inserts per (live schema, chunk); all-zero between batches
+    uint32_t *epoch_nlive;     // [65536] live schemas in every pruning epoch (replay needs the range of each target draw)
 };
 
 struct EmitArgs {
@@ -130,12 +159,10 @@ uint32_t plan_hist_chunks(uint64_t max_molecules);
 void plan_extend_table(const SimConst &sc, uint64_t g_lo, uint64_t g_hi, uint32_t *d_nmol, uint64_t *d_off, uint64_t *d_scan_tmp,
                        cudaStream_t st);
 void plan_fill_slots(uint64_t g_lo, uint64_t g_hi, const uint32_t *d_nmol, const uint64_t *d_off, PlanDev plan, cudaStream_t st);
-void plan_set_live(const uint16_t *d_live, uint32_t n_live, uint16_t *d_lpos /*[65536]*/, cudaStream_t st);
-// d_hist needs plan_hist_chunks(max_mol) * n_live entries
-void plan_batch(const SimConst &sc, const SchemaDev *d_sch, const uint16_t *d_live, const uint16_t *d_lpos, uint32_t n_live,
-                uint16_t epoch, uint64_t g0, uint32_t n_groups, const uint32_t *d_nmol, const uint64_t *d_off, PlanDev plan,
-                uint64_t max_mol, const int64_t *d_need, unsigned long long *d_hist, unsigned long long *d_scratch, uint32_t parity,
-                BatchResult *d_res, cudaStream_t st);  // d_scratch: 3 words (first error, cut of even / odd batches)
+void plan_init(PlanState *d_st, const PlanArrays &pa, uint32_t K, cudaStream_t st);
+// enqueues `n_batches` batches back to back; each reads its parameters from *d_st (a batch after the end of the plan is three empty launches)
+void plan_batches(const SimConst &sc, const SchemaDev *d_sch, PlanState *d_st, const PlanArrays &pa, const uint64_t *d_off, PlanDev plan,
+                  unsigned long long *d_first_err, int n_batches, cudaStream_t st);
 
 void shard_bounds(const uint64_t *d_read_off, uint64_t n_mol, uint64_t n_pairs, int32_t world, uint64_t *d_bounds /*[world+1]*/,
                   cudaStream_t st);
@@ -151,6 +178,17 @@ void place_segment_chain(const SimConst &sc, const SchemaDev *d_sch, PlanDev pla
                          uint64_t pair_lo, const uint64_t *d_read_off_local, void *d_tmp, uint32_t *d_acc_i,
                          unsigned long long *d_acc_f, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
                          unsigned long long *d_err, cudaStream_t st);
+
+// fused placement (mmk_place.cuh): needs 32-pair tiles. d_big_list: capacity n_pairs / place_big_threshold() + 1
+uint32_t place_big_threshold();
+void place_fused(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint64_t n_pairs,
+                 uint32_t n_tiles, const uint64_t *d_roff_l, uint32_t *d_tile_mol0, const InsTable *d_tab, uint32_t *d_big_list,
+                 uint32_t *d_big_count, uint32_t big_cap, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
+                 uint4 *d_fdesc, uint32_t *d_sum1, uint32_t *d_sum2, uint8_t *d_tile_flags, unsigned long long *d_gather,
+                 unsigned long long *d_err, uint32_t stage_cap, int bpb, cudaStream_t st);
+void place_local_roff(uint64_t mol0, uint32_t n_mol, const uint64_t *d_read_off_global, uint64_t *d_read_off_local, cudaStream_t st);
+// KAT: lengths the kernels derive from raw 64-bit draws (table path with its exact fallback); slow[i] = 1 where the fallback ran
+void kat_insert_len(const SimConst &sc, const InsTable *d_tab, const uint64_t *d_bits, uint32_t *d_len, uint8_t *d_slow, int64_t n, cudaStream_t st);
 
 void tile_prepare(const EmitArgs &a, uint32_t tile_lo, uint32_t tile_hi, uint32_t *d_sum1, uint32_t *d_sum2, uint4 *d_fdesc,
                   uint8_t *d_tile_flags, unsigned long long *d_gather, cudaStream_t st);

@@ -1,7 +1,7 @@
 /* mimick_oracle.c — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
  *
  * A sequential CPU restatement of the simulation core of pdimens/mimick
- * (mimick/MimickLinkedReads.jl/src/*.jl), used only as the checker for the CUDA path:
+ * (the .jl files under mimick/MimickLinkedReads.jl/src), used only as the checker for the CUDA path:
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
  * Nothing under mimick_b200/ links, imports or executes this file.
  *
@@ -28,6 +28,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+
+#include <zlib.h> /* crc32: digest mode only */
 
 #include "mmk_rng.h"
 
@@ -110,6 +112,15 @@ typedef struct {
     int64_t barcode_index;
 } orc_mol;
 
+/* Digest mode (full-size parity runs, where the text would not fit in host memory): a running CRC-32
+ * of each stream, sampled at the first barcode-group boundary at or after every `window` read pairs. */
+typedef struct {
+    int64_t pairs;          /* read pairs emitted so far */
+    uint64_t bytes1, bytes2; /* R1 / R2 bytes emitted so far */
+    uint32_t crc1, crc2;    /* CRC-32 (zlib) of R1[0:bytes1], R2[0:bytes2] */
+    uint32_t pad[2];
+} orc_checkpoint;
+
 typedef struct orc_sim {
     orc_params par;
     /* derived: src/Structs.jl:54-70 */
@@ -148,6 +159,11 @@ typedef struct orc_sim {
     int64_t n_groups;
     int64_t max_pairs; /* optional stop (bench sampling): 0 = run to completion */
     int discard;       /* bench: recycle the output buffers after every group, count bytes only */
+    int64_t digest_window; /* > 0: digest mode (text discarded after every group, molecules and inserts kept) */
+    int64_t next_cp;
+    uint32_t crc1, crc2;
+    orc_checkpoint *cps;
+    size_t n_cps, cap_cps;
     uint64_t bytes_r1, bytes_r2;
     int64_t total_pairs;
     int err;
@@ -424,6 +440,7 @@ void orc_destroy(orc_sim *s) {
     free(s->ins_start);
     free(s->ins_stop);
     free(s->rec);
+    free(s->cps);
     free(s);
 }
 int orc_error(const orc_sim *s) { return s->err; }
@@ -477,6 +494,24 @@ void orc_set_replay(orc_sim *s, const orc_variate *stream, size_t n) {
 }
 void orc_set_record(orc_sim *s, int on) { s->record = on; }
 void orc_set_max_pairs(orc_sim *s, int64_t n) { s->max_pairs = n; }
+void orc_set_digest(orc_sim *s, int64_t window_pairs) {
+    s->digest_window = window_pairs;
+    s->next_cp = window_pairs;
+}
+static void push_checkpoint(orc_sim *s, int64_t pairs) {
+    if (s->n_cps == s->cap_cps) {
+        s->cap_cps = s->cap_cps ? 2 * s->cap_cps : 64;
+        s->cps = (orc_checkpoint *)realloc(s->cps, s->cap_cps * sizeof(orc_checkpoint));
+    }
+    orc_checkpoint *c = &s->cps[s->n_cps++];
+    memset(c, 0, sizeof *c);
+    c->pairs = pairs;
+    c->bytes1 = s->bytes_r1;
+    c->bytes2 = s->bytes_r2;
+    c->crc1 = s->crc1;
+    c->crc2 = s->crc2;
+}
+const orc_checkpoint *orc_checkpoints(const orc_sim *s, size_t *n) { *n = s->n_cps; return s->cps; }
 
 /* ---------- src/ProcessFASTA.jl --------------------------------------------------------- */
 static const char IUPAC[] = "ACMGRSVTWYHKDBN";
@@ -861,10 +896,20 @@ int orc_run(orc_sim *s) {
         if (s->discard) {
             s->bytes_r1 += s->r1.n; s->bytes_r2 += s->r2.n;
             s->r1.n = 0; s->r2.n = 0; s->n_ins = 0; s->n_mols = 0;
+        } else if (s->digest_window > 0) {
+            for (size_t o = 0; o < s->r1.n; o += 1u << 30) s->crc1 = (uint32_t)crc32(s->crc1, s->r1.p + o, (uInt)(s->r1.n - o < (1u << 30) ? s->r1.n - o : (1u << 30)));
+            for (size_t o = 0; o < s->r2.n; o += 1u << 30) s->crc2 = (uint32_t)crc32(s->crc2, s->r2.p + o, (uInt)(s->r2.n - o < (1u << 30) ? s->r2.n - o : (1u << 30)));
+            s->bytes_r1 += s->r1.n; s->bytes_r2 += s->r2.n;
+            s->r1.n = 0; s->r2.n = 0;
+            if (total_pairs >= s->next_cp) {
+                push_checkpoint(s, total_pairs);
+                s->next_cp = (total_pairs / s->digest_window + 1) * s->digest_window;
+            }
         }
         s->total_pairs = total_pairs;
         if (s->max_pairs > 0 && total_pairs >= s->max_pairs) break;
     }
+    if (s->digest_window > 0 && !s->err && (s->n_cps == 0 || s->cps[s->n_cps - 1].pairs != total_pairs)) push_checkpoint(s, total_pairs);
     s->n_groups = (int64_t)g;
     free(live); free(lens); free(targets); free(t1.p); free(t2.p);
     return s->err;
@@ -875,7 +920,7 @@ const uint8_t *orc_r1(const orc_sim *s, size_t *n) { *n = s->r1.n; return s->r1.
 const uint8_t *orc_r2(const orc_sim *s, size_t *n) { *n = s->r2.n; return s->r2.p; }
 int64_t orc_n_groups(const orc_sim *s) { return s->n_groups; }
 int64_t orc_total_pairs(const orc_sim *s) { return s->total_pairs; }
-uint64_t orc_total_bytes(const orc_sim *s) { return s->discard ? s->bytes_r1 + s->bytes_r2 : s->r1.n + s->r2.n; }
+uint64_t orc_total_bytes(const orc_sim *s) { return (s->discard || s->digest_window > 0) ? s->bytes_r1 + s->bytes_r2 : s->r1.n + s->r2.n; }
 int64_t orc_n_molecules(const orc_sim *s) { return (int64_t)s->n_mols; }
 int64_t orc_n_pairs(const orc_sim *s) { return (int64_t)s->n_ins; }
 const orc_mol *orc_molecules(const orc_sim *s) { return s->mols; }
@@ -903,6 +948,14 @@ void orc_sample_trunc_exp(uint64_t seed, double theta, double lower, int has_upp
     trunc_exp d; trunc_exp_make(&d, theta, lower, has_upper, upper);
     for (int64_t i = 0; i < n; ++i) { src_begin_group(s, (uint64_t)i); out[i] = trunc_exp_rand(s, &d, MMK_P_NFRAGS); }
     orc_destroy(s);
+}
+/* the definition the device's threshold table must reproduce: trunc(Int, mu + sd * z(bits)), 0 when z < lb */
+void orc_insert_len_from_bits(int32_t mu, int32_t sd, const uint64_t *bits, uint32_t *out, int64_t n) {
+    const double dmu = (double)mu, dsd = (double)sd, lb = MMK_DIV(MMK_SUB(200.0, dmu), dsd);
+    for (int64_t i = 0; i < n; ++i) {
+        const double z = mmk_bits_to_normal(bits[i]);
+        out[i] = z < lb ? 0u : (uint32_t)(int64_t)MMK_ADD(dmu, MMK_MUL(dsd, z));
+    }
 }
 void orc_sample_insert(uint64_t seed, int32_t mu, int32_t sd, int64_t n, double *out) {
     orc_params p; memset(&p, 0, sizeof p); p.insert_length = mu; p.insert_stdev = sd; p.mol_length = 80000; p.mol_coverage = 0.2; p.n_molecules = 2;

@@ -64,6 +64,9 @@ class OrcMol(C.Structure):
     ]
 
 
+CHECKPOINT_DTYPE = np.dtype([("pairs", "<i8"), ("bytes1", "<u8"), ("bytes2", "<u8"), ("crc1", "<u4"), ("crc2", "<u4"),
+                             ("pad", "<u4", (2,))])
+
 MOL_DTYPE = np.dtype(
     [("group", "<i8"), ("slot", "<i4"), ("schema", "<i4"), ("start", "<i8"), ("molsize", "<i8"),
      ("n_frags", "<i8"), ("first_read", "<i8"), ("barcode_index", "<i8")]
@@ -113,6 +116,9 @@ def lib():
     L.orc_set_replay.argtypes = [vp, vp, sz]
     L.orc_set_record.argtypes = [vp, i32]
     L.orc_set_max_pairs.argtypes = [vp, i64]
+    L.orc_set_digest.argtypes = [vp, i64]
+    L.orc_checkpoints.argtypes = [vp, C.POINTER(sz)]
+    L.orc_checkpoints.restype = vp
     L.orc_normalize_bases.argtypes = [vp, i64]
     L.orc_normalize_bases.restype = i64
     L.orc_mask_n.argtypes = [vp, vp, i64, u32, u32]
@@ -156,8 +162,17 @@ def lib():
     L.orc_trunc_exp_info.argtypes = [dbl, dbl, i32, dbl, vp]
     L.orc_sample_trunc_exp.argtypes = [u64, dbl, dbl, i32, dbl, i64, vp]
     L.orc_sample_insert.argtypes = [u64, i32, i32, i64, vp]
+    L.orc_insert_len_from_bits.argtypes = [i32, i32, vp, vp, i64]
     _LIB = L
     return L
+
+
+def insert_len_from_bits(mu: int, sd: int, bits: np.ndarray) -> np.ndarray:
+    """trunc(Int, mu + sd * z(bits)) per raw 64-bit draw, 0 where the truncation at 200 rejects it."""
+    bits = np.ascontiguousarray(bits, dtype=np.uint64)
+    out = np.zeros(bits.size, dtype=np.uint32)
+    lib().orc_insert_len_from_bits(int(mu), int(sd), bits.ctypes.data, out.ctypes.data, bits.size)
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -277,6 +292,7 @@ class SimResult:
     reads_current: list
     reads_required: list
     variates: np.ndarray | None = None
+    checkpoints: np.ndarray | None = None   # digest mode: running CRC-32 of R1 / R2 at group boundaries
 
 
 class Oracle:
@@ -325,6 +341,11 @@ class Oracle:
 
     def set_max_pairs(self, n):
         lib().orc_set_max_pairs(self.h, int(n))
+
+    def set_digest(self, window_pairs):
+        """Digest mode: the text is folded into running CRC-32s (checkpoint every `window_pairs` read pairs, at the
+        next barcode-group boundary) and discarded; molecules and inserts are kept.  For full-size parity runs."""
+        lib().orc_set_digest(self.h, int(window_pairs))
 
     # ---- schema construction ------------------------------------------------------------
     def prepare_contig(self, seq: bytes, mask: bool, contig_index: int, hap_index: int):
@@ -404,7 +425,9 @@ class Oracle:
             req.append(int(r.value))
         p = L.orc_recorded(self.h, C.byref(n))
         var = np.frombuffer(C.string_at(p, n.value * 16), dtype=VARIATE_DTYPE).copy() if n.value else None
-        return SimResult(r1, r2, mols, st, en, int(L.orc_n_groups(self.h)), cur, req, var)
+        p = L.orc_checkpoints(self.h, C.byref(n))
+        cps = np.frombuffer(C.string_at(p, n.value * CHECKPOINT_DTYPE.itemsize), dtype=CHECKPOINT_DTYPE).copy() if n.value else None
+        return SimResult(r1, r2, mols, st, en, int(L.orc_n_groups(self.h)), cur, req, var, cps)
 
 
 # ------------------------------------------------------------------------------------------

@@ -32,7 +32,8 @@ for l in dis[start + 1:]:
         continue
     if re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+.*?;", l):
         lines.append(cur)
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--launch-count", "1"], capture_output=True, text=True).stdout
+skip = os.environ.get("NCU_SKIP", "0")
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--launch-skip", skip, "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.split("\n")))
 hdr = rows[1]
 data = [r for r in rows[2:] if r and r[0].startswith("0x")][: len(lines)]

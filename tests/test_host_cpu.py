@@ -278,3 +278,41 @@ int main(void) {
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert r.stdout.split()[2] == "30"
+
+
+@pytest.mark.parametrize("mu,sd", [(500, 50), (350, 80), (600, 150), (300, 100), (210, 200), (500, 1), (1000, 400)])
+def test_insert_length_table_reproduces_the_definition(mu, sd):
+    """The placement kernels find trunc(mu + sd z(u)) by searching a threshold table on the top 32 bits of the draw and
+    fall back to the double-precision definition inside a guard band around every threshold (mmk_place.cuh).  Host twin
+    of that lookup on the table mmk_create builds, against the oracle's evaluation of the definition: random draws and
+    draws on both edges of every guard band."""
+    import ctypes as C
+    from mimick_b200 import _lib
+    L = _lib.load()
+    en, n, base, ulo, uhi, guard = (C.c_uint32() for _ in range(6))
+    thr = np.zeros(4096, dtype=np.uint32)
+    assert L.mmk_insert_table(mu, sd, C.byref(en), C.byref(n), C.byref(base), C.byref(ulo), C.byref(uhi), C.byref(guard),
+                              thr.ctypes.data, thr.size) == 0
+    assert en.value == 1 and n.value > 0.9 * min(15.8 * sd, 1980) - 2 * sd - 400 and np.all(np.diff(thr[:n.value].astype(np.int64)) >= 0)
+    thr = thr[:n.value].astype(np.int64)
+    g = guard.value
+
+    def lookup(u32):
+        k = np.searchsorted(thr, u32, side="right")           # thresholds <= u32
+        below = np.where(k > 0, u32 - thr[np.maximum(k - 1, 0)], 1 << 40)
+        above = np.where(k < len(thr), thr[np.minimum(k, len(thr) - 1)] - u32, 1 << 40)
+        fast = (below > g) & (above > g) & (u32 >= ulo.value) & (u32 <= uhi.value)
+        return base.value + k, fast
+    rng = np.random.default_rng(mu * 1000 + sd)
+    bits = rng.integers(0, 1 << 64, size=400_000, dtype=np.uint64)
+    edges = np.concatenate([thr + d for d in (-g - 2, -g - 1, g + 1, g + 2)])
+    edges = edges[(edges >= 0) & (edges < (1 << 32))].astype(np.uint64)
+    adv = np.concatenate([(edges << np.uint64(32)), (edges << np.uint64(32)) | np.uint64(0xffffffff)])
+    bits = np.concatenate([bits, adv])
+    want = O.insert_len_from_bits(mu, sd, bits)
+    got, fast = lookup((bits >> np.uint64(32)).astype(np.int64))
+    assert np.array_equal(got[fast], want[fast].astype(np.int64))
+    from scipy import stats
+    zmax = min(7.9, 990.0 / sd)
+    covered = stats.norm.cdf(zmax) - stats.norm.cdf(max(-zmax, (200 - mu) / sd))   # accepted by the truncation, inside the table
+    assert fast[:400_000].mean() > covered - 0.005                                   # the exact path is the exception

@@ -155,9 +155,11 @@ def test_circular(tmp_path, strict):
     dict(mol_length=300, singletons=0.0, attempts=300),   # molecule-length law in its quantile branch (tp = e^-10)
     dict(read_length=(250, 250), insert_length=600, insert_stdev=150, singletons=0.0, attempts=300),
     # truncated(Normal(ins, sd), lower = 200) outside plain rejection (src/Structs.jl:68; the CLI admits -i 0.., mimick/__main__.py:44):
-    dict(insert_length=150, insert_stdev=50, read_length=(100, 100), singletons=0.0, attempts=300),   # kept mass 0.16: Robert's exponential proposal
-    dict(insert_length=210, insert_stdev=200, read_length=(100, 100), singletons=0.0, attempts=300),  # kept mass 0.52: rejection, half the normals rejected
-    dict(insert_length=100, insert_stdev=20, read_length=(75, 75), singletons=0.0, attempts=300),     # 5 sigma into the tail
+    # (the truncated mean exceeds insert_length there, so molecules whose insert count comes out near molsize / insert_length
+    # cannot fit — in the reference too; mol_coverage 0.02 keeps the counts far from that bound)
+    dict(insert_length=150, insert_stdev=50, read_length=(100, 100), mol_coverage=0.02, singletons=0.0, attempts=300),   # kept mass 0.16: Robert's exponential proposal
+    dict(insert_length=210, insert_stdev=200, read_length=(100, 100), mol_coverage=0.02, singletons=0.0, attempts=300),  # kept mass 0.52: rejection, half the normals rejected
+    dict(insert_length=100, insert_stdev=20, read_length=(75, 75), mol_coverage=0.02, singletons=0.0, attempts=300),     # 5 sigma into the tail
 ])
 def test_parameter_regions(tmp_path, kw):
     rng = np.random.default_rng(4)
@@ -166,6 +168,23 @@ def test_parameter_regions(tmp_path, kw):
     write_fasta(p1, [("chrA", random_bases(rng, 90000)), ("chrB", random_bases(rng, 30000))])
     write_fasta(p2, [("chrA", random_bases(rng, 90100)), ("chrB", random_bases(rng, 29000))])
     check_single([p1, p2], "tellseq", seed=77, coverage=8, **kw)
+
+
+def test_unfittable_inserts_fail_like_the_reference(tmp_path):
+    """-i 150 -d 50 at the default molecule coverage: the truncated insert law has mean 226 > 150, so a molecule whose insert
+    count lands near molsize / 150 can never fit: "FAILED TO FIND PRACTICAL READ SIZES" (Breakpoints.jl:214-216) after
+    `attempts` whole-vector redraws — same status, same molecule as the oracle."""
+    import mimick_b200 as M
+    rng = np.random.default_rng(4)
+    p = os.path.join(str(tmp_path), "a.fa")
+    write_fasta(p, [("chrA", random_bases(rng, 200000))])
+    kw = dict(insert_length=150, insert_stdev=50, read_length=(100, 100), singletons=0.0, attempts=5, coverage=8)
+    with pytest.raises(O.OracleError) as eo:
+        O.mimick_single([p], "tellseq", seed=77, **kw)
+    assert eo.value.code == 3
+    with pytest.raises(M.MimickError) as eg:
+        gpu_single([p], "tellseq", 77, variates=False, **kw)
+    assert eg.value.status == 3
 
 
 def test_iupac_ambiguity_codes_4bit(tmp_path):
@@ -516,3 +535,78 @@ def test_bgzf_fallbacks_and_consumer_errors(tmp_path):
             sim.emit_stream([slots[0].ctypes.data, slots[1].ctypes.data], [slots[2].ctypes.data, slots[3].ctypes.data], cap, boom, bgzf=True)
         with pytest.raises(M.MimickError):   # slots smaller than the bound are refused before anything runs
             sim.emit_stream([slots[0].ctypes.data, slots[1].ctypes.data], [slots[2].ctypes.data, slots[3].ctypes.data], 1024, None, bgzf=True)
+
+
+# ------------------------------------------------------------------------------------------
+# placement: the fused kernel (mmk_place.cuh), its long-molecule side kernel, the legacy three-kernel path
+# ------------------------------------------------------------------------------------------
+def test_device_insert_length_table():
+    """mmk_kat_insert_len: the kernels' table lookup (with its exact fallback) against the oracle's evaluation of the
+    definition, on random draws and on both edges of the guard band of every threshold."""
+    import ctypes as C
+    import mimick_b200 as M
+    from mimick_b200 import _lib
+    L = _lib.load()
+    for mu, sd in [(500, 50), (350, 80), (600, 150), (210, 200)]:
+        en, n, base, ulo, uhi, guard = (C.c_uint32() for _ in range(6))
+        thr = np.zeros(4096, dtype=np.uint32)
+        assert L.mmk_insert_table(mu, sd, C.byref(en), C.byref(n), C.byref(base), C.byref(ulo), C.byref(uhi), C.byref(guard),
+                                  thr.ctypes.data, thr.size) == 0 and en.value == 1
+        t = thr[:n.value].astype(np.int64)
+        g = guard.value
+        rng = np.random.default_rng(mu + sd)
+        edges = np.concatenate([t + d for d in (-g - 2, -g - 1, -g, -1, 0, 1, g, g + 1, g + 2)])
+        edges = edges[(edges >= 0) & (edges < (1 << 32))].astype(np.uint64)
+        bits = np.concatenate([rng.integers(0, 1 << 64, size=1_000_000, dtype=np.uint64), edges << np.uint64(32),
+                               (edges << np.uint64(32)) | np.uint64(0xffffffff)])
+        with M.Simulator("haplotagging", seed=1, insert_length=mu, insert_stdev=sd) as sim:
+            got, slow = sim.kat_insert_len(bits)
+        want = O.insert_len_from_bits(mu, sd, bits)
+        assert np.array_equal(got, want), (mu, sd, int(np.flatnonzero(got != want)[0]))
+        from scipy import stats
+        rejected = stats.norm.cdf((200 - mu) / sd)   # draws the truncation at 200 rejects always take the exact path
+        assert slow[:1_000_000].mean() < rejected + 0.01 and slow[1_000_000:].mean() > 0.3   # the fallback is rare, except where we aimed at it
+
+
+def _env(**kv):
+    import contextlib
+
+    @contextlib.contextmanager
+    def cm():
+        old = {k: os.environ.get(k) for k in kv}
+        os.environ.update({k: str(v) for k, v in kv.items()})
+        try:
+            yield
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    return cm()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(coverage=30, singletons=0.1),                                  # blocks of 2048 pairs, molecules straddling their boundaries
+    dict(coverage=30, singletons=1.0),                                  # every molecule one pair: 2048 molecules per block
+    dict(coverage=40, mol_length=2_000_000, mol_coverage=0.5, singletons=0.0),   # molecules of 1000s of pairs: k_place_big
+    dict(coverage=30, mol_length=400_000, mol_coverage=0.6, singletons=0.3, n_molecules=4),   # a mix around the 512-pair limit
+])
+def test_placement_paths_agree_with_the_oracle(tmp_path, kw):
+    """The default placement path, the fused kernel (64- and 32-tile blocks) and the three-kernel path give the oracle's bytes,
+    plan and inserts."""
+    rng = np.random.default_rng(14)
+    p1 = os.path.join(str(tmp_path), "a.fa")
+    p2 = os.path.join(str(tmp_path), "b.fa")
+    write_fasta(p1, [("chrA", random_bases(rng, 5_000_000)), ("chrB", random_bases(rng, 700_000))])
+    write_fasta(p2, [("chrA", random_bases(rng, 5_000_100)), ("chrB", random_bases(rng, 699_000))])
+    okw = dict(kw, attempts=300)
+    gpu, orc = check_single([p1, p2], "haplotagging", seed=31, **okw)
+    nf = gpu["mol"]["n_frags"]
+    if kw.get("mol_length", 0) >= 400_000:
+        assert (nf > 512).sum() > 3 and (nf <= 512).sum() > 3
+    for env in (dict(MMK_PLACE_MODE="fused"), dict(MMK_PLACE_MODE="fused", MMK_PLACE_TB=32), dict(MMK_PLACE_MODE="legacy")):
+        with _env(**env):
+            alt = gpu_single([p1, p2], "haplotagging", 31, variates=False, **okw)
+        assert alt["r1"] == gpu["r1"] and alt["r2"] == gpu["r2"], env
+        assert np.array_equal(alt["ins"][0], gpu["ins"][0]) and np.array_equal(alt["ins"][1], gpu["ins"][1]), env
