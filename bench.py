@@ -42,7 +42,13 @@ WORKLOADS = {
            [250_000_000], 2, "10x", dict(coverage=30, singletons=0.0, mol_length=50000)),
     "c2": ("5 Mbp synthetic circular prokaryote genome, stLFR, 1 haplotype, 50x (strict wrap)",
            [5_000_000], 1, "stlfr", dict(coverage=50, singletons=0.0, mol_length=80000, circular=True, strict_wrap=True)),
+    # BASELINE configs[3]: one FASTA + one VCF, every sample an independent simulation (src/Main.jl:104-130); samples go
+    # round-robin to ranks.  nhap = 1 here means "one master FASTA"; each sample builds two haplotypes from it.
+    "c4": ("100 Mbp synthetic FASTA + VCF with 8 samples (1e-3 SNPs, 1e-4 indels of 1-20 bp, genotypes Bernoulli(0.3) per haplotype), "
+           "TELLseq, 20x per sample, sharded by sample",
+           [100_000_000], 1, "tellseq", dict(coverage=20, singletons=0.0, mol_length=80000)),
 }
+C4_SAMPLES = 8
 COMMON_SIM = dict(n_molecules=2, mol_coverage=0.2, insert_length=500, insert_stdev=50, read_length=(150, 150),
                   attempts=300)
 
@@ -91,6 +97,43 @@ def make_genome(name, scale, device, pin):
         torch.cuda.synchronize()
         torch.cuda.empty_cache()
     return out
+
+
+def make_c4_variants(master, n_samples=C4_SAMPLES, seed=1004, snp_rate=1e-3, indel_rate=1e-4, p_alt=0.3):
+    """Synthetic phased multi-sample VCF content for configs[3], as the SoA mmk_set_sample_variants takes (one entry per
+    record and haplotype slot with a non-zero allele, file order).  Sites are shared by all samples, >= 48 bases apart;
+    indels are VCF-anchored (deletion: REF = anchor + k bases, ALT = anchor; insertion: REF = anchor, ALT = anchor + k
+    random bases; k in 1..20).  Returns (per-sample dict of numpy arrays, shared ALT blob)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    n = master.size
+    n_snp, n_ind = int(n * snp_rate), int(n * indel_rate)
+    n_var = n_snp + n_ind
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    cells = np.sort(rng.choice(n // 64 - 2, size=n_var, replace=False)) + 1
+    pos = cells.astype(np.int64) * 64 + rng.integers(0, 16, size=n_var)          # 1-based
+    is_indel = np.zeros(n_var, dtype=bool)
+    is_indel[rng.choice(n_var, size=n_ind, replace=False)] = True
+    k = rng.integers(1, 21, size=n_var)
+    is_del = rng.random(n_var) < 0.5
+    ref = master[pos - 1]
+    code = np.searchsorted(acgt, ref)
+    snp_alt = acgt[(code + rng.integers(1, 4, size=n_var)) % 4]
+    ref_len = np.where(is_indel & is_del, k + 1, 1).astype(np.int32)
+    alt_len = np.where(is_indel & ~is_del, k + 1, 1).astype(np.int32)
+    alt_off = np.zeros(n_var, dtype=np.int64)
+    alt_off[1:] = np.cumsum(alt_len[:-1])
+    blob = acgt[rng.integers(0, 4, size=int(alt_len.sum()))].copy()               # insertion tails; first bytes fixed below
+    blob[alt_off] = np.where(is_indel, ref, snp_alt)
+    typ = is_indel.astype(np.uint8)
+    out = []
+    for _ in range(n_samples):
+        g = rng.random((n_var, 2)) < p_alt                                        # [site, haplotype slot]
+        idx = np.flatnonzero(g.reshape(-1))
+        v, h = idx // 2, (idx % 2 + 1).astype(np.uint8)
+        out.append(dict(contig=np.zeros(len(v), dtype=np.int32), pos=pos[v].copy(), type=typ[v].copy(), ref_len=ref_len[v].copy(),
+                        alt_off=alt_off[v].copy(), alt_len=alt_len[v].copy(), hap=h))
+    return out, blob.tobytes()
 
 
 class ClockSampler:
@@ -185,10 +228,13 @@ def cpu_run(genome, wl, pairs_per_thread, threads, seed=42):
     cov = okw["coverage"]
     r1, r2 = okw["read_length"]
     sims = []
+    schemas = list(genome)
+    if wl == "c4":   # a sample = two haplotypes of the master; the bounded CPU sample simulates on the unmutated master
+        schemas = [(genome[0][0], 1, genome[0][2]), (genome[0][0], 2, genome[0][2])]   # (mutate! is O(len) per indel on the CPU)
     for t in range(threads):
-        o = O.Oracle(fmt, **okw)
+        o = O.Oracle("tenx" if fmt == "10x" else fmt, **okw)
         o.set_philox(seed, t)
-        for nm, hap, h in genome:
+        for nm, hap, h in schemas:
             n = h.numel()
             req = int((cov * n / ((r1 + r2) // 2)) / 2)
             o.add_schema_borrowed(nm, hap, h.data_ptr(), n, req)
@@ -221,6 +267,8 @@ def reference_arm(args):
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     genome = make_genome(args.workload, args.scale, dev, pin=False)
     threads = args.cpu_threads or min(os.cpu_count() or 1, 64)
+    if args.workload == "c4":
+        threads = min(threads, C4_SAMPLES)   # the reference's threading shape in VCF mode: one task per sample (src/Main.jl:104)
     per = args.cpu_pairs or 600_000
     for _ in range(args.warmup):
         cpu_run(genome, args.workload, max(per // 10, 1000), threads)
@@ -256,26 +304,36 @@ def reference_arm(args):
 # ------------------------------------------------------------------------------------------
 def bind_to_gpu_numa_node(index):
     """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that the pinned host buffers it allocates
-    (first touch) and the threads that consume them sit next to the GPU's PCIe root.  With one process per GPU and all
-    buffers on one socket, eight concurrent D2H streams share that socket's memory and the inter-socket link.
-    Best effort: returns the node, or None when the topology cannot be read."""
+    (first touch) and the threads that consume them sit next to the GPU's PCIe root.  Only meaningful on multi-node
+    hosts: returns what was found and whether anything was bound (the boxes of this pool are single-node VMs whose
+    PCI devices report node -1 — nothing to bind, and the report says so instead of a silent null)."""
+    info = {"bound": False, "gpu_node": None, "host_nodes": None, "why": ""}
     try:
         import torch
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")]
+        info["host_nodes"] = len(nodes)
         p = torch.cuda.get_device_properties(index)
         bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
         base = f"/sys/bus/pci/devices/{bdf}"
         node = int(open(f"{base}/numa_node").read())
+        info["gpu_node"] = node
+        if len(nodes) < 2 or node < 0:
+            info["why"] = "single NUMA node (or the GPU reports no node): nothing to bind"
+            return info
         cpus = set()
         for part in open(f"{base}/local_cpulist").read().strip().split(","):
             lo, _, hi = part.partition("-")
             cpus.update(range(int(lo), int(hi or lo) + 1))
         cpus &= os.sched_getaffinity(0)
-        if node >= 0 and cpus:
+        if cpus:
             os.sched_setaffinity(0, cpus)
-            return node
-    except Exception:
-        pass
-    return None
+            info["bound"] = True
+            info["why"] = f"bound to the {len(cpus)} CPUs of node {node}"
+        else:
+            info["why"] = "no allowed CPU on the GPU's node"
+    except Exception as e:  # noqa: BLE001
+        info["why"] = f"topology unreadable: {type(e).__name__}"
+    return info
 
 
 
@@ -312,6 +370,18 @@ def cuda_arm(args):
     sim = M.Simulator(fmt, seed=42, device=local, max_chunk_bytes=args.chunk_mib << 20, **simkw)
     stream = torch.cuda.ExternalStream(sim.cuda_stream, device=dev)
 
+    # Units of work of this rank.  Single-sample workloads: ONE job, this rank's molecule range of the one simulation.
+    # c4 (FASTA + VCF): one job per sample of this rank (samples round-robin over ranks, src/Main.jl:104); each job builds the
+    # sample's haplotypes from the resident master (north_star subsystem 1), then plans, places and emits the whole sample.
+    is_vcf = args.workload == "c4"
+    if is_vcf:
+        from mimick_b200.dist import samples_for_rank
+        variants, alt_blob = make_c4_variants(genome[0][2].numpy())
+        jobs = samples_for_rank(C4_SAMPLES, rank, world)
+        n_master = genome[0][2].numel()
+    else:
+        jobs = [None]
+
     dev_syms = {}
 
     def load_inputs():
@@ -338,29 +408,61 @@ def cuda_arm(args):
                 sim.add_contig(nm, (dev_syms[i].data_ptr(), h.numel()), hap)
         return mine
 
-    def exchange(place):
+    def exchange(tot):
         """the path's only collective: per-rank (bytes_R1, bytes_R2, n_pairs, first_read_id) over NCCL"""
-        lay = M.exchange_counts(M.RankCounts(place.r1_bytes, place.r2_bytes, place.n_pairs, place.first_pair), device=dev)
+        if is_vcf:   # samples are separate files: ranks only need each other's totals, nothing chains
+            t = torch.tensor(list(tot), dtype=torch.int64, device=dev)
+            if world == 1:
+                return [tuple(tot)]
+            out = torch.empty(world * 4, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(out, t)
+            return [tuple(r) for r in out.cpu().view(world, 4).tolist()]
+        lay = M.exchange_counts(M.RankCounts(*tot), device=dev)
         return [(c.r1_bytes, c.r2_bytes, c.n_pairs, c.first_pair) for c in lay.counts]
 
     state = {}
 
+    def run_jobs(emit):
+        """plan + place (+ haplotype construction) of every job of this rank, `emit(place)` for its text; returns this rank's
+        (bytes_R1, bytes_R2, n_pairs, first_read_id) and adds the phase times to `state`."""
+        tot = [0, 0, 0, 0]
+        algo = mols = 0
+        for job in jobs:
+            if is_vcf:
+                t0 = time.perf_counter()
+                sim.set_sample_variants_raw(job, 2, [0], variants[job], alt_blob)   # synchronous
+                state["hap_ms"] = state.get("hap_ms", 0.0) + 1e3 * (time.perf_counter() - t0)
+                state["hap_bytes"] = n_master // 4 * 2 + sum(sc["length"] for sc in sim.schemas()) // 4 + len(variants[job]["pos"]) * 30
+            plan = sim.plan()
+            sim.set_shard(*((0, 1) if is_vcf else (rank, world)))
+            place = sim.place()
+            emit(place)
+            tot[0] += place.r1_bytes
+            tot[1] += place.r2_bytes
+            tot[2] += place.n_pairs
+            tot[3] = 0 if is_vcf else place.first_pair
+            algo += place.r1_bytes + place.r2_bytes + place.gather_bytes
+            mols += plan.n_molecules
+            state["plan_ms"] = state.get("plan_ms", 0.0) + plan.host_ms
+            state["place_ms"] = state.get("place_ms", 0.0) + place.host_ms
+            state.update(plan=plan, place=place)
+        state.update(algo=algo, mols=mols)
+        return tot
+
     def step_resident():
-        plan = sim.plan()
-        sim.set_shard(rank, world)
-        place = sim.place()
-        ms = sim.emit_all()
-        allc = exchange(place)
-        state.update(plan=plan, place=place, all=allc)
-        state["plan_ms"] = state.get("plan_ms", 0.0) + plan.host_ms
-        state["place_ms"] = state.get("place_ms", 0.0) + place.host_ms
-        return ms
+        ms = [0.0]
+
+        def emit(place):
+            ms[0] += sim.emit_all()
+        tot = run_jobs(emit)
+        state["all"] = exchange(tot)
+        return ms[0]
 
     # ---- device-resident pass: `value` ------------------------------------------------------
     load_inputs()
     for _ in range(args.warmup):
         step_resident()
-    state["plan_ms"] = state["place_ms"] = 0.0
+    state["plan_ms"] = state["place_ms"] = state["hap_ms"] = 0.0
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -385,8 +487,8 @@ def cuda_arm(args):
     total_pairs = sum(c[2] for c in state["all"])
     total_bytes = sum(c[0] + c[1] for c in state["all"])
     value = total_pairs / (ms_per_step / 1e3)
-    place = state["place"]
-    algo_bytes = place.r1_bytes + place.r2_bytes + place.gather_bytes  # this rank, per step
+    algo_bytes = state["algo"]  # this rank, per step: FASTQ bytes written + packed reference bytes gathered
+    hap_ms_per_sample = state["hap_ms"] / args.steps / max(len(jobs), 1) if is_vcf else None
     achieved = algo_bytes * args.steps / (emit_ms / 1e3) / 1e9
     peak, peak_src = peak_hbm()
     traffic, traffic_src = ncu_traffic()
@@ -397,33 +499,37 @@ def cuda_arm(args):
     # is the same with uncompressed text crossing PCIe instead.
     def make_e2e(bgzf):
         slot_bytes = sim.bgzf_bound() if bgzf else sim.chunk_layout()[0]
+        if is_vcf:   # every sample goes through the same host ring; their bounds differ by a few members per chunk
+            slot_bytes = int(slot_bytes * 1.05) + (1 << 20)
         ring = [torch.empty(slot_bytes, dtype=torch.uint8, pin_memory=True) for _ in range(4)]
         d2h = {"bytes": 0, "step": 0, "h2d": 0}
 
         def consume(ch, p1, p2):
             d2h["step"] += ch.r1_bytes + ch.r2_bytes
 
-        phases = {"load": 0.0, "plan": 0.0, "place": 0.0, "stream": 0.0}
+        phases = {"load": 0.0, "haplotypes": 0.0, "plan": 0.0, "place": 0.0, "stream": 0.0}
 
         def step():
-            t = [time.perf_counter()]
+            t0 = time.perf_counter()
             sim.clear_contigs()
             d2h["h2d"] = load_inputs()         # H2D of every FASTA symbol from pinned memory
-            t.append(time.perf_counter())
-            sim.plan()
-            t.append(time.perf_counter())
-            sim.set_shard(rank, world)
-            pl = sim.place()
-            t.append(time.perf_counter())
+            t1 = time.perf_counter()
             d2h["step"] = 0
-            sim.emit_stream([ring[0].data_ptr(), ring[1].data_ptr()], [ring[2].data_ptr(), ring[3].data_ptr()], slot_bytes,
-                            consume, bgzf=bgzf)
-            exchange(pl)
-            t.append(time.perf_counter())
+            for k in ("plan_ms", "place_ms", "hap_ms"):
+                state[k] = 0.0
+
+            def emit(place):
+                sim.emit_stream([ring[0].data_ptr(), ring[1].data_ptr()], [ring[2].data_ptr(), ring[3].data_ptr()], slot_bytes,
+                                consume, bgzf=bgzf)
+            tot = run_jobs(emit)
+            exchange(tot)
+            t2 = time.perf_counter()
             d2h["bytes"] = d2h["step"]
-            for k, name in enumerate(("load", "plan", "place", "stream")):
-                phases[name] += 1e3 * (t[k + 1] - t[k])
-            return pl
+            phases["load"] += 1e3 * (t1 - t0)
+            phases["plan"] += state["plan_ms"]
+            phases["place"] += state["place_ms"]
+            phases["haplotypes"] += state["hap_ms"]
+            phases["stream"] += 1e3 * (t2 - t1) - state["plan_ms"] - state["place_ms"] - state["hap_ms"]
         return step, d2h, slot_bytes, phases
 
     def run_e2e(bgzf, steps, warmup):
@@ -473,9 +579,16 @@ def cuda_arm(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = args.cpu_threads or min(os.cpu_count() or 1, 64)
+        if is_vcf:
+            threads = min(threads, C4_SAMPLES)
         per = args.cpu_pairs or 4_000_000
+        p1, b1, dt1 = cpu_run(genome, args.workload, max(per // 2, 1000), 1)
         p, b, dt = cpu_run(genome, args.workload, per, threads)
         cpu = {"value": p / dt, "unit": "read pairs/s", "cores": threads, "kind": "port",
+               "reference_threading_shape": {
+                   "value": p1 / dt1, "unit": "read pairs/s", "cores": 1,
+                   "sample": f"ONE simulation thread (the reference's single-sample loop, src/Main.jl:44-59, is sequential; its "
+                             f"other threads only compress), stopped after {max(per // 2, 1000)} read pairs; {dt1:.1f} s"},
                "sample": f"{threads} independent simulations (one per host thread, the reference's task-per-sample shape), "
                          f"each stopped after {per} read pairs of the same workload; C restatement of the reference "
                          f"(Julia absent), text to memory, gzip off; {dt:.1f} s",
@@ -487,8 +600,12 @@ def cuda_arm(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}" + (f" (scale {args.scale})" if args.scale != 1.0 else ""),
-                       "read_pairs": int(total_pairs), "molecules": int(state["plan"].n_molecules),
-                       "fastq_bytes": int(total_bytes), "sharding": f"molecule ranges over {world} rank(s), replicated planning",
+                       "read_pairs": int(total_pairs),
+                       "molecules": int(state["mols"]) if is_vcf else int(state["plan"].n_molecules),
+                       "fastq_bytes": int(total_bytes),
+                       "sharding": (f"{C4_SAMPLES} samples round-robin over {world} rank(s), {len(jobs)} on rank 0; haplotypes built "
+                                    "from the resident master inside every step") if is_vcf
+                       else f"molecule ranges over {world} rank(s), replicated planning",
                        "l2": "outputs (GBs per step) far exceed the 126 MB L2; no flush needed",
                        "output_ring": f"2 x 2 x {args.chunk_mib} MiB device buffers, reused chunk after chunk"},
             "fastq_gb_per_s": total_bytes / (ms_per_step / 1e3) / 1e9,
@@ -500,11 +617,18 @@ def cuda_arm(args):
             "e2e": e2e,
             "e2e_text": e2e_text,
             "gpu_launches": int(launches),
-            "host_numa_node": numa,
+            "host_numa": numa,
             "clocks": clocks,
             "wall_s_timed_region": wall,
             "plan": {"groups": int(state["plan"].n_groups), "epochs": int(state["plan"].n_epochs),
                      "batches": int(state["plan"].n_batches)},
+            "haplotype_construction": None if not is_vcf else {
+                "ms_per_sample": hap_ms_per_sample, "ms_per_step_rank0": hap_ms_per_sample * len(jobs),
+                "algorithmic_bytes_per_sample": int(state["hap_bytes"]),
+                "bytes": "packed master read once per haplotype + packed haplotypes written + 30 B per variant entry (SURVEY 8d)",
+                "achieved_gb_per_s": state["hap_bytes"] / (hap_ms_per_sample / 1e3) / 1e9,
+                "frac_of_hbm_peak": state["hap_bytes"] / (hap_ms_per_sample / 1e3) / 1e9 / peak,
+                "note": "wall time of mmk_set_sample_variants (host piece list + H2D of the variant arrays + device kernels)"},
             "phase_ms_per_step": {"plan": state["plan_ms"] / args.steps, "place": state["place_ms"] / args.steps,
                                   "emit": emit_ms / args.steps},
         }

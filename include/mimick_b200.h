@@ -83,6 +83,12 @@ typedef struct mmk_params {
     int32_t force_generic;  /* 1: emit every record through the general byte-wise path (testing) */
     uint64_t max_chunk_bytes; /* capacity of each device output buffer (R1 and R2 each); 0 = default */
     int64_t plan_batch_groups; /* barcode groups planned per speculative batch; 0 = default */
+    /* Sequencing-error / quality model.  The reference has none (docs/algorithm.md:11: reads are verbatim copies,
+     * quality constant 'I', src/FormatFASTQ.jl:14); with all four rates 0 (the default) the output is the reference's.
+     * DESIGN.md "Error model" specifies the draws; every read of nominal length gets, per cycle c of its S cycles:
+     *   substitution with probability err_sub_start + (err_sub_end - err_sub_start) c / (S - 1),
+     *   insertion / deletion with probabilities err_ins / err_del, and a Phred quality drawn around the cycle's error rate. */
+    double err_sub_start, err_sub_end, err_ins, err_del;
 } mmk_params;
 
 typedef struct mmk_ctx mmk_ctx;
@@ -253,6 +259,12 @@ int32_t mmk_emit_stream_bgzf(mmk_ctx *ctx, void *const r1_host[2], void *const r
 int32_t mmk_bgzf_eof(void *out, uint32_t cap);
 int32_t mmk_bgzf_table(uint32_t *litlen_codes, uint32_t *dist_codes, uint8_t *prefix, uint32_t prefix_cap,
                        uint32_t *prefix_bits);
+/* Whole shard into two files, as the reference's writers do (src/Main.jl:42-43,111-112): BGZF members coded on the
+ * device when `bgzf` != 0 (then `append_eof` != 0 appends the end-of-file member: the last rank of a sharded run), plain
+ * FASTQ text otherwise.  `append` != 0 opens the files for appending.  The library owns a pinned host ring; the writes of
+ * chunk k (one thread per file) overlap the generation and copy-out of chunk k + 1.  bytes_written[2]: R1, R2 (may be NULL). */
+int32_t mmk_emit_files(mmk_ctx *ctx, const char *r1_path, const char *r2_path, int32_t bgzf, int32_t append_eof, int32_t append,
+                       uint64_t bytes_written[2]);
 /* bytes each output slot holds for this shard (after mmk_place) and the number of chunks */
 int32_t mmk_chunk_layout(mmk_ctx *ctx, uint64_t *slot_bytes, int32_t *n_chunks);
 

@@ -245,8 +245,7 @@ enum mmk_purpose {
     MMK_P_START = 8,    /* molecule: start position                               Breakpoints.jl:240 */
     MMK_P_GAP = 9,      /* (tag of the replay stream only) gap before insert i    Breakpoints.jl:28 */
     MMK_P_ROUNDKEY = 10,/* key derivation of redraw round r >= 1 */
-    MMK_P_ERROR = 11,   /* read: substitution / indel / quality draws of the sequencing-error model */
-    MMK_P_ERRPOS = 12   /* read: per-base draws of the sequencing-error model */
+    MMK_P_ERROR = 11    /* read cycle: event / replacement / quality draw of the sequencing-error model */
 };
 
 typedef struct mmk_stream {
@@ -312,6 +311,19 @@ MMK_HD uint64_t mmk_insert_next64(mmk_stream *s) {
     return v;
 }
 #define MMK_INSERT_GAP_DRAW 1u
+
+/* Sequencing-error model (optional, default off): one 64-bit draw per (read pair, read, cycle).
+ *   key = seed; counter = (cycle >> 1 | (read - 1) << 24, MMK_P_ERROR | sample << 8, pair[31:0], pair[63:32]);
+ *   even cycles take words (0,1) of the block, odd cycles words (2,3).  `pair` is the run-wide index of the read pair
+ *   (it fixes barcode, molecule and insert), `read` 1 or 2, cycle < 2^25.
+ * Low word: the event uniform; high word: bits 0-1 replacement selector, bits 2-4 quality jitter. */
+MMK_HD uint64_t mmk_error_draw(uint64_t seed, uint32_t sample, uint64_t pair, uint32_t read, uint32_t cycle) {
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t ctr[4] = {(cycle >> 1) | ((read - 1u) << 24), (uint32_t)MMK_P_ERROR | ((sample & 0xffffu) << 8), (uint32_t)pair, (uint32_t)(pair >> 32)};
+    uint32_t o[4];
+    mmk_philox4x32_10(ctr, key, o);
+    return (cycle & 1u) ? (((uint64_t)o[3] << 32) | o[2]) : (((uint64_t)o[1] << 32) | o[0]);
+}
 
 /* ---- variates ---------------------------------------------------------------------------- */
 /* u01 in [0,1): 53 random bits */

@@ -9,6 +9,7 @@ for Julia threads over samples; here samples are spread over ranks).
 from __future__ import annotations
 
 import argparse
+import os
 import sys
 
 FORMATS = ["10x", "stlfr", "standard", "standard:haplotagging", "standard:stlfr", "haplotagging", "tellseq"]
@@ -92,9 +93,12 @@ def plan_call(argv):
               mol_length=ns.molecule_length, insert_length=ns.insert_size, insert_stdev=ns.insert_stdev,
               read_length=ns.read_lengths, singletons=ns.singletons, circular=ns.circular, attempts=ns.molecule_attempts,
               seed=ns.seed, mask=ns.mask_n, quiet=ns.quiet, device=ns.device, compress=not ns.plain, rank=ns.rank, world=ns.world)
+    # click resolves -o with resolve_path=True (mimick/__main__.py:37): the default "simulated/" becomes <cwd>/simulated, so the
+    # files are simulated.R1.fq.gz (not hidden files inside simulated/), and the VCF mode's outdir is the resolved directory
+    out = os.path.realpath(ns.output_prefix)
     if ns.vcf:
-        return (ns.fasta[0], ns.vcf, fmt), dict(kw, outdir=ns.output_prefix)
-    return (list(ns.fasta), fmt), dict(kw, prefix=ns.output_prefix)
+        return (ns.fasta[0], ns.vcf, fmt), dict(kw, outdir=out)
+    return (list(ns.fasta), fmt), dict(kw, prefix=out)
 
 
 def main(argv=None) -> int:

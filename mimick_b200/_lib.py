@@ -35,6 +35,7 @@ class Params(C.Structure):
         ("length_r1", C.c_int32), ("length_r2", C.c_int32), ("singletons", C.c_double), ("circular", C.c_int32),
         ("mask", C.c_int32), ("seed", C.c_int64), ("strict_wrap", C.c_int32), ("force_generic", C.c_int32),
         ("max_chunk_bytes", C.c_uint64), ("plan_batch_groups", C.c_int64),
+        ("err_sub_start", C.c_double), ("err_sub_end", C.c_double), ("err_ins", C.c_double), ("err_del", C.c_double),
     ]
 
 
@@ -76,7 +77,7 @@ EXPORTS = [
     "mmk_dump_inserts", "mmk_dump_variates", "mmk_dump_mask_variates", "mmk_kat_philox", "mmk_kat_math",
     "mmk_emit_all", "mmk_emit_stream", "mmk_chunk_layout", "mmk_launch_count", "mmk_clear_contigs",
     "mmk_bgzf_bound", "mmk_emit_chunk_bgzf", "mmk_emit_stream_bgzf", "mmk_bgzf_eof", "mmk_bgzf_table",
-    "mmk_kat_insert_len", "mmk_insert_table",
+    "mmk_kat_insert_len", "mmk_insert_table", "mmk_emit_files",
 ]
 
 CHUNK_CB = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.POINTER(Chunk), C.c_void_p, C.c_void_p)
@@ -153,6 +154,7 @@ def load():
     sig("mmk_kat_philox", i32, vp, vp, vp, vp)
     sig("mmk_kat_math", i32, vp, i32, vp, vp, i64)
     sig("mmk_kat_insert_len", i32, vp, vp, vp, vp, i64)
+    sig("mmk_emit_files", i32, vp, cp, cp, i32, i32, i32, vp)
     sig("mmk_insert_table", i32, i32, i32, P(u32), P(u32), P(u32), P(u32), P(u32), P(u32), vp, u32)
     _LIB = L
     return L

@@ -180,6 +180,15 @@ class Simulator:
             pos.ctypes.data, typ.ctypes.data, ref_len.ctypes.data, alt_off.ctypes.data, alt_len.ctypes.data,
             hap.ctypes.data, blob, len(blob)))
 
+    def set_sample_variants_raw(self, sample_stream, ploidy, vcf_contigs, v, blob: bytes):
+        """Same, from ready-made arrays: `v` holds contig (i32), pos (i64), type (u8), ref_len (i32), alt_off (i64), alt_len (i32),
+        hap (u8); `blob` the ALT bytes the offsets point into."""
+        vc = np.ascontiguousarray(vcf_contigs, dtype=np.int32)
+        self._ck(self._L.mmk_set_sample_variants(
+            self._h, int(sample_stream), int(ploidy), vc.ctypes.data, len(vc), len(v["pos"]), v["contig"].ctypes.data,
+            v["pos"].ctypes.data, v["type"].ctypes.data, v["ref_len"].ctypes.data, v["alt_off"].ctypes.data,
+            v["alt_len"].ctypes.data, v["hap"].ctypes.data, blob, len(blob)))
+
     def schemas(self):
         out = []
         for i in range(self._L.mmk_n_schemas(self._h)):
@@ -383,19 +392,17 @@ def bgzf_eof() -> bytes:
 
 
 def _write_shard(sim: Simulator, r1_path: str, r2_path: str, mode: str, bgzf: bool = False, eof: bool = True):
-    """File writes of chunk k overlap the generation and copy-out of chunk k+1 (mmk_emit_stream).
-    `bgzf`: the chunks are BGZF members coded on the device; `eof` appends the end-of-file member."""
-    slot_bytes = sim.bgzf_bound() if bgzf else sim.chunk_layout()[0]
-    slots = [np.empty(slot_bytes, dtype=np.uint8) for _ in range(4)]
-    with open(r1_path, mode) as f1, open(r2_path, mode) as f2:
-        def consume(ch, p1, p2):
-            f1.write((C.c_char * ch.r1_bytes).from_address(p1))
-            f2.write((C.c_char * ch.r2_bytes).from_address(p2))
-        sim.emit_stream([slots[0].ctypes.data, slots[1].ctypes.data], [slots[2].ctypes.data, slots[3].ctypes.data],
-                        slot_bytes, consume, bgzf=bgzf)
-        if bgzf and eof:
-            f1.write(bgzf_eof())
-            f2.write(bgzf_eof())
+    """mmk_emit_files: the library streams the placed shard through its own pinned host ring into the two files (file writes of
+    chunk k overlap the generation and copy-out of chunk k+1).  `bgzf`: BGZF members coded on the device; `eof` appends the
+    end-of-file member."""
+    n = (C.c_uint64 * 2)()
+    sim._ck(sim._L.mmk_emit_files(sim._h, os.fspath(r1_path).encode(), os.fspath(r2_path).encode(), int(bool(bgzf)), int(bool(eof)),
+                                  int("a" in mode), n))
+    return int(n[0]), int(n[1])
+
+
+# device chunk of the file-writing path: the pinned host ring is 4 x this (text) or ~4 x this / 5 (BGZF); 8 GiB chunks are a bench setting
+FILE_CHUNK_BYTES = 256 << 20
 
 
 def mimick(*args, prefix: str = "simulated/SIM", outdir: str = "simulated", quiet: bool = False,
@@ -424,6 +431,7 @@ def mimick(*args, prefix: str = "simulated/SIM", outdir: str = "simulated", quie
         raise TypeError("mimick(fasta_list, format, ...) or mimick(fasta, vcf, format, ...)")
     L = _lib.load()
     outs = []
+    kw.setdefault("max_chunk_bytes", FILE_CHUNK_BYTES)
     if vcf is None:
         with Simulator(fmt, **kw) as sim:
             for hap, path in enumerate(fasta, start=1):

@@ -536,18 +536,26 @@ __global__ void k_tile_mol0(const uint64_t *__restrict__ roff_l, uint32_t n_mol,
     for (uint64_t t = (lo + tile_pairs - 1) >> sh; (t << sh) < hi; ++t) tile_mol0[t] = m;
 }
 
+}  // namespace mmkdev
+#include "mmk_place.cuh"  // threshold-table draws (pair_draw), sum_over, the fused placement kernels
+namespace mmkdev {
+
 // Placement, step 1 — one thread per read pair: the insert length of redraw round 0 and the 64
 // random bits of the pair's gap draw.  Everything that needs a transcendental or a Philox block is
 // here, flat over pairs, so it runs without divergence.  Per molecule it also accumulates the integer
-// sum of the lengths and a fixed-point (2^-16) lower bound of their real sum, one atomic per warp run.
+// sum of the lengths, one atomic per warp run.
 struct __align__(16) PairTmp {
     uint64_t bits;  // gap draw: gap = mulhi64(bits, remaining + 1)
     uint32_t len;   // trunc(Int, insert length)
     uint32_t dm;    // molecule index - first molecule of the pair's tile
 };
-__global__ void k_insert_draws(SimConst sc, PlanDev plan, uint64_t mol0, uint32_t n_mol, const uint64_t *__restrict__ roff_l,
-                               const uint32_t *__restrict__ tile_mol0, uint32_t n_tiles, uint32_t tile_pairs, uint64_t pair_lo,
-                               uint64_t pair_hi, PairTmp *__restrict__ tmp, uint32_t *acc_i, unsigned long long *acc_f) {
+__global__ void __launch_bounds__(256) k_insert_draws(const __grid_constant__ SimConst sc, PlanDev plan, uint64_t mol0, uint32_t n_mol,
+                                                      const uint64_t *__restrict__ roff_l, const uint32_t *__restrict__ tile_mol0, uint32_t n_tiles,
+                                                      uint32_t tile_pairs, uint64_t pair_lo, uint64_t pair_hi, PairTmp *__restrict__ tmp,
+                                                      uint32_t *acc_i, const InsTable *__restrict__ gtab) {
+    __shared__ InsTable tab;
+    stage_table(&tab, gtab);
+    __syncthreads();
     const uint64_t p_raw = pair_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = p_raw < pair_hi;
     const uint64_t p = valid ? p_raw : pair_hi - 1;
@@ -561,32 +569,20 @@ __global__ void k_insert_draws(SimConst sc, PlanDev plan, uint64_t mol0, uint32_
     const uint32_t i = (uint32_t)(p - roff_l[lo]);
     const uint64_t g = plan.group[mol0 + lo];
     const uint32_t m = plan.slot[mol0 + lo];
-    NoRec rec;
-    // ONE Philox block per pair: words (0,1) feed the length sampler, words (2,3) are the gap draw
-    mmk_stream is;
-    mmk_insert_stream_init(&is, sc.seed, sc.sample, g, m, i);
-    mmk_stream_block(&is, 0, is.buf);
-    is.blk = 0;
-    const uint64_t gbits = ((uint64_t)is.buf[3] << 32) | is.buf[2];
-    const double x = draw_insert_from(sc, is, rec);
-    const uint32_t li = insert_len_of(x);
+    // ONE Philox block per pair: words (0,1) feed the length sampler (threshold table), words (2,3) are the gap draw
+    uint32_t blo, bhi;
+    const uint32_t li = pair_draw(sc, tab, g, m, i, blo, bhi);
     if (valid) {
         PairTmp t;
-        t.bits = gbits;
+        t.bits = ((uint64_t)bhi << 32) | blo;
         t.len = li;
         t.dm = lo - tm0;
         tmp[p - pair_lo] = t;
     }
     // lanes of the same molecule are contiguous: one atomic per run
     const unsigned peers = __match_any_sync(0xffffffffu, valid ? lo : 0xffffffffu);
-    const unsigned long long X = (unsigned long long)MMK_MUL(x, 65536.0);  // floor(x * 2^16), x > 0
     const uint32_t s_len = __reduce_add_sync(peers, li);
-    const uint32_t s_lo = __reduce_add_sync(peers, (uint32_t)(X & 0xfffffu));
-    const uint32_t s_hi = __reduce_add_sync(peers, (uint32_t)(X >> 20));
-    if (valid && (threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1)) {
-        atomicAdd(&acc_i[lo], s_len);
-        atomicAdd(&acc_f[lo], ((unsigned long long)s_hi << 20) + s_lo);
-    }
+    if (valid && (threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&acc_i[lo], s_len);
 }
 
 // Placement, step 2 — one thread per molecule: the redraw rule on the float sum of the insert lengths
@@ -594,13 +590,6 @@ __global__ void k_insert_draws(SimConst sc, PlanDev plan, uint64_t mol0, uint32_
 // header text and the per-molecule record.  `sum > molsize` is decided from the fixed-point bounds of
 // step 1; only when those straddle the molecule size is the left-to-right float sum (the oracle's
 // definition) evaluated.
-__device__ __noinline__ double sequential_sum(const SimConst &sc, uint64_t g, uint32_t m, uint32_t round, uint32_t nfrags) {
-    NoRec rec;
-    double sum = 0.0;
-    const uint64_t key = mmk_round_key(sc.seed, round);
-    for (uint32_t k = 0; k < nfrags; ++k) sum = MMK_ADD(sum, draw_insert(sc, key, g, m, k, rec));
-    return sum;
-}
 // whole-vector redraws while the float sum exceeds the molecule (Breakpoints.jl:209-212); true if it still does
 __device__ __noinline__ bool redraw_rounds(const SimConst &sc, uint64_t g, uint32_t m, uint32_t nfrags, uint32_t molsize,
                                            PairTmp *tp, uint64_t &isum) {
@@ -625,8 +614,7 @@ __device__ __noinline__ bool redraw_rounds(const SimConst &sc, uint64_t g, uint3
 }
 __device__ __forceinline__ void place_chain_one(const SimConst &sc, const SchemaDev *__restrict__ sch, const PlanDev &plan,
                                                 uint64_t mol0, uint32_t i, const uint64_t *__restrict__ roff_l, uint64_t pair_lo,
-                                                PairTmp *tmp, const uint32_t *__restrict__ acc_i,
-                                                const unsigned long long *__restrict__ acc_f, uint2 *ins, MolRec *mol,
+                                                PairTmp *tmp, const uint32_t *__restrict__ acc_i, uint2 *ins, MolRec *mol,
                                                 unsigned long long *err) {
     uint64_t gi = mol0 + i;
     uint64_t ro = roff_l[i];
@@ -639,13 +627,7 @@ __device__ __forceinline__ void place_chain_one(const SimConst &sc, const Schema
     PairTmp *tp = tmp + (ro - pair_lo);
     uint2 *in = ins + ro;
     uint64_t isum = acc_i[i];
-    bool over;
-    {
-        const unsigned long long lo = acc_f[i], M = (unsigned long long)molsize << 16;  // sum * 2^16 in [lo, lo + nfrags)
-        if (lo > M) over = true;
-        else if (lo + nfrags + 1 <= M) over = false;
-        else over = sequential_sum(sc, g, m, 0, nfrags) > (double)molsize;
-    }
+    bool over = sum_over(sc, sc.seed, g, m, nfrags, molsize, isum);  // from the integer sum unless it straddles the molecule size
     if (over) over = redraw_rounds(sc, g, m, nfrags, molsize, tp, isum);  // rare: kept out of line
     uint32_t status = over ? (uint32_t)MMK_ERR_INSERTS_UNFITTABLE : 0u;
     // start_pos = rand(1:adjusted_end)
@@ -752,8 +734,7 @@ void place_prepare(uint64_t mol0, uint32_t n_mol, const uint64_t *d_read_off_glo
 constexpr uint32_t PLACE_BLOCK = 1024, SORT_BINS = 1024;
 __global__ void __launch_bounds__(256) k_place_chain(SimConst sc, const SchemaDev *__restrict__ sch, PlanDev plan, uint64_t mol0,
                                                      uint32_t m_lo, uint32_t m_hi, const uint64_t *__restrict__ roff_l,
-                                                     uint64_t pair_lo, PairTmp *tmp, const uint32_t *__restrict__ acc_i,
-                                                     const unsigned long long *__restrict__ acc_f, uint2 *ins, MolRec *mol,
+                                                     uint64_t pair_lo, PairTmp *tmp, const uint32_t *__restrict__ acc_i, uint2 *ins, MolRec *mol,
                                                      unsigned long long *err) {
     __shared__ uint32_t s_bins[SORT_BINS];
     __shared__ uint32_t s_warp[9];
@@ -795,7 +776,7 @@ __global__ void __launch_bounds__(256) k_place_chain(SimConst sc, const SchemaDe
     for (uint32_t j = threadIdx.x; j < cnt; j += 256) s_perm[atomicAdd(&s_bins[nf[j] < SORT_BINS ? nf[j] : SORT_BINS - 1], 1u)] = (uint16_t)j;
     __syncthreads();
     for (uint32_t j = threadIdx.x; j < cnt; j += 256)
-        place_chain_one(sc, sch, plan, mol0, base + s_perm[j], roff_l, pair_lo, tmp, acc_i, acc_f, ins, mol, err);
+        place_chain_one(sc, sch, plan, mol0, base + s_perm[j], roff_l, pair_lo, tmp, acc_i, ins, mol, err);
 }
 
 // one segment: pairs [pair_lo, pair_hi) = the pairs of molecules [m_lo, m_hi)
@@ -805,67 +786,45 @@ size_t place_tmp_bytes(uint64_t max_pairs) { return (size_t)(max_pairs + 1) * si
 // scratch of segment k)
 void place_segment_draws(const SimConst &sc, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint64_t pair_lo, uint64_t pair_hi,
                          const uint64_t *d_read_off_local, const uint32_t *d_tile_mol0, uint32_t n_tiles, uint32_t tile_pairs,
-                         void *d_tmp, uint32_t *d_acc_i, unsigned long long *d_acc_f, cudaStream_t st) {
+                         void *d_tmp, uint32_t *d_acc_i, const InsTable *d_tab, cudaStream_t st) {
     const uint64_t np = pair_hi - pair_lo;
     if (np) LAUNCH(k_insert_draws, (unsigned)((np + 255) / 256), 256, 0, st, sc, plan, mol0, n_mol, d_read_off_local, d_tile_mol0,
-                   n_tiles, tile_pairs, pair_lo, pair_hi, (PairTmp *)d_tmp, d_acc_i, d_acc_f);
+                   n_tiles, tile_pairs, pair_lo, pair_hi, (PairTmp *)d_tmp, d_acc_i, d_tab);
 }
 void place_segment_chain(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t m_lo, uint32_t m_hi,
-                         uint64_t pair_lo, const uint64_t *d_read_off_local, void *d_tmp, uint32_t *d_acc_i,
-                         unsigned long long *d_acc_f, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
+                         uint64_t pair_lo, const uint64_t *d_read_off_local, void *d_tmp, uint32_t *d_acc_i, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
                          unsigned long long *d_err, cudaStream_t st) {
     if (m_hi <= m_lo) return;
     const uint32_t nm = m_hi - m_lo;
     LAUNCH(k_place_chain, (nm + PLACE_BLOCK - 1) / PLACE_BLOCK, 256, 0, st, sc, d_sch, plan, mol0, m_lo, m_hi, d_read_off_local,
-           pair_lo, (PairTmp *)d_tmp, d_acc_i, d_acc_f, d_ins, d_mol, d_err);
+           pair_lo, (PairTmp *)d_tmp, d_acc_i, d_ins, d_mol, d_err);
     LAUNCH(k_mol_text, (nm + 127) / 128, 128, 0, st, sc, d_sch, mol0, m_lo, m_hi, d_mol, d_text, text_stride);
 }
 
 // ------------------------------------------------------------------------------------------
-// fused placement: mmk_place.cuh
+// fused placement: launchers (kernels in mmk_place.cuh, included above)
 // ------------------------------------------------------------------------------------------
-}  // namespace mmkdev
-#include "mmk_place.cuh"
-namespace mmkdev {
-
-static int place_tb() {  // tiles per block of k_place_block: 64 (default) or 32 (MMK_PLACE_TB, profiling)
-    const char *e = getenv("MMK_PLACE_TB");
-    return (e && atoi(e) == 32) ? 32 : 64;
-}
-uint32_t place_big_threshold() { return place_tb() == 32 ? PlbGeom<32>::BIG : PlbGeom<64>::BIG; }
 
 void place_local_roff(uint64_t mol0, uint32_t n_mol, const uint64_t *d_read_off_global, uint64_t *d_read_off_local, cudaStream_t st) {
     LAUNCH(k_local_roff, (n_mol + 1 + 255) / 256, 256, 0, st, d_read_off_global, mol0, n_mol, d_read_off_local);
 }
 
-template <int TB>
-static void launch_place_block(const PlaceArgs &a, cudaStream_t st) {
-    static int ctas_per_sm[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const size_t smem = PlbGeom<TB>::SMEM;
-    if (!ctas_per_sm[dev & 63]) {
-        cudaFuncSetAttribute(k_place_block<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int n = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_place_block<TB>, PLB_THREADS, smem);
-        ctas_per_sm[dev & 63] = n > 0 ? n : 1;
-    }
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(a.n_blocks, (uint64_t)sms * ctas_per_sm[dev & 63]);
-    LAUNCH((k_place_block<TB>), grid, PLB_THREADS, smem, st, a);
-}
-
 void place_fused(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint64_t n_pairs,
-                 uint32_t n_tiles, const uint64_t *d_roff_l, uint32_t *d_tile_mol0, const InsTable *d_tab, uint32_t *d_big_list,
-                 uint32_t *d_big_count, uint32_t big_cap, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
-                 uint4 *d_fdesc, uint32_t *d_sum1, uint32_t *d_sum2, uint8_t *d_tile_flags, unsigned long long *d_gather,
-                 unsigned long long *d_err, uint32_t stage_cap, int bpb, cudaStream_t st) {
+                 uint32_t n_tiles, const uint64_t *d_roff_l, uint32_t *d_tile_mol0, const InsTable *d_tab, uint2 *d_ins, MolRec *d_mol,
+                 uint8_t *d_text, uint32_t text_stride, uint4 *d_fdesc, uint32_t *d_sum1, uint32_t *d_sum2, uint8_t *d_tile_flags,
+                 unsigned long long *d_gather, unsigned long long *d_err, unsigned long long *d_msum, uint32_t stage_cap, int bpb,
+                 cudaStream_t st) {
     if (n_mol == 0 || n_pairs == 0) return;
-    const int tb = place_tb();
-    const uint32_t big = place_big_threshold();
-    cudaMemsetAsync(d_big_count, 0, 4, st);
-    LAUNCH(k_tile_mol0_big, (n_mol + 255) / 256, 256, 0, st, d_roff_l, n_mol, 32u, d_tile_mol0, big, d_big_list, d_big_count, big_cap);
+    int dev = 0, sms = 0, ctas_sum = 0, ctas_chain = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_sum, k_mol_sum, PLM_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_chain, k_mol_chain, PLM_THREADS, 0);
+    cudaMemsetAsync(d_sum1, 0, (size_t)n_tiles * 4, st);
+    cudaMemsetAsync(d_sum2, 0, (size_t)n_tiles * 4, st);
+    cudaMemsetAsync(d_tile_flags, 0, (size_t)n_tiles, st);
+    LAUNCH(k_tile_mol0, (n_mol + 255) / 256, 256, 0, st, d_roff_l, n_mol, 32u, d_tile_mol0);
     PlaceArgs a;
     a.sc = sc;
     a.sch = d_sch;
@@ -877,8 +836,6 @@ void place_fused(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint6
     a.roff = d_roff_l;
     a.tile_mol0 = d_tile_mol0;
     a.tab = d_tab;
-    a.big_list = d_big_list;
-    a.big_count = d_big_count;
     a.ins = d_ins;
     a.mol = d_mol;
     a.fdesc = d_fdesc;
@@ -887,13 +844,20 @@ void place_fused(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint6
     a.tile_flags = d_tile_flags;
     a.gather = d_gather;
     a.err = d_err;
-    a.stage_cap = stage_cap;
+    a.msum = d_msum;
     a.bpb = bpb;
-    a.n_blocks = (n_tiles + (uint32_t)tb - 1) / (uint32_t)tb;
-    // molecules too long for a block's shared-memory window first (the count lives on the device: fixed grid, grid-stride loop)
-    LAUNCH(k_place_big, (unsigned)std::min<uint32_t>(big_cap, 148u * 4u), PLB_THREADS, 0, st, a);
-    if (tb == 32) launch_place_block<32>(a, st);
-    else launch_place_block<64>(a, st);
+    // one resident wave per kernel (a warp owns 1 / n_warps of the pairs, at least a few hundred)
+    const uint32_t wpc = PLM_THREADS / 32;
+    auto warps_for = [&](int ctas) {
+        uint32_t w = (uint32_t)sms * (uint32_t)(ctas > 0 ? ctas : 4) * wpc;
+        if (const char *e = getenv("MMK_PLACE_WAVES")) w *= (uint32_t)std::max(1, atoi(e));  // more, smaller shares (profiling)
+        return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(w, n_pairs / 256 + 1));
+    };
+    a.n_warps = warps_for(ctas_sum);
+    LAUNCH(k_mol_sum, (a.n_warps + wpc - 1) / wpc, PLM_THREADS, 0, st, a);
+    a.n_warps = warps_for(ctas_chain);
+    LAUNCH(k_mol_chain, (a.n_warps + wpc - 1) / wpc, PLM_THREADS, 0, st, a);
+    LAUNCH(k_tile_flags, (n_tiles + 255) / 256, 256, 0, st, d_sum1, d_sum2, n_tiles, stage_cap, d_tile_flags);
     LAUNCH(k_mol_text, (n_mol + 127) / 128, 128, 0, st, sc, d_sch, mol0, 0u, n_mol, d_mol, d_text, text_stride);
 }
 

@@ -128,8 +128,9 @@ __device__ void write_record_generic(const EmitArgs &a, const PairDesc &d, int r
 // tile preparation: one decode of every pair → record lengths per tile (byte offsets after a scan),
 // a packed 16-byte descriptor per pair for the emit kernel, and the tile's fast/general flag
 // ------------------------------------------------------------------------------------------
-// x: bstart   y: insert length | dm << 24   z: sb1 | sb2 << 16 (tile-relative record offsets)
-// w: P | SUF << 7 | schema << 13
+// x: bstart   y: insert length | dm << 24   w: P | SUF << 7 | schema << 13
+// z: 32-pair tiles: first arena word of the pair's haplotype (the emit kernel scans the record lengths itself and
+//    needs no dependent load for the window address); other tile sizes: sb1 | sb2 << 16 (tile-relative record offsets)
 __global__ void __launch_bounds__(256) k_tile_prepare(EmitArgs a, uint32_t tile_lo, uint32_t n_tiles, uint32_t *sum1, uint32_t *sum2,
                                                       uint4 *fdesc, uint8_t *tile_flags, unsigned long long *gather) {
     // 256 threads = 256 / tile_pairs tiles; tile_pairs is a power of two in 8..64
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(256) k_tile_prepare(EmitArgs a, uint32_t tile_
         irregular = (s_irr[w0] | s_irr[w0 + 1]) != 0u;
     }
     if (it < np)
-        fdesc[p0 + it] = make_uint4(d.bstart, iny, (off1 & 0xffffu) | (off2 << 16),
+        fdesc[p0 + it] = make_uint4(d.bstart, iny, TP == 32u ? (uint32_t)d.word_off : ((off1 & 0xffffu) | (off2 << 16)),
                                     (uint32_t)d.P | ((uint32_t)d.SUF << 7) | (schema << 13));
     if (tile_ok && it == 0) {
         sum1[tile] = tot1;
@@ -262,16 +263,18 @@ __device__ __forceinline__ void prefetch_l1(const void *p) {
 #define FD_D1(pk) (((pk) >> 22) & 0xfu)
 #define FD_D2(pk) (((pk) >> 26) & 0xfu)
 
-// unpack the 16-byte descriptor k_tile_prepare wrote (x: bstart, y: len | dm << 24, z: sb1 | sb2 << 16,
-// w: P | SUF << 7 | schema << 13) into the emit kernel's working form
+// unpack the 16-byte descriptor the placement wrote (x: bstart, y: len | dm << 24, z: see k_tile_prepare,
+// w: P | SUF << 7 | schema << 13) into the emit kernel's working form.  ZWORD: z is the haplotype's first arena word and
+// the caller fills sb1 / sb2 from its own scan of the record lengths.
+template <bool ZWORD>
 __device__ __forceinline__ void make_fast_desc(const EmitArgs &a, const uint4 &q, uint32_t tile_m0, uint32_t base1, uint32_t base2,
                                                FastDesc &f) {
     const uint32_t bstart = q.x, bend = q.x + MMK_INS_LEN(q.y) - 1u;
     const uint32_t P = q.w & 0x7fu, SUF = (q.w >> 7) & 0x3fu, schema = q.w >> 13;
     const uint32_t d1 = ndigits_u32(bstart), d2 = ndigits_u32(bend);
-    const uint32_t word_off = (uint32_t)a.sch[schema].word_off;
-    f.sb1 = base1 + (q.z & 0xffffu);
-    f.sb2 = base2 + (q.z >> 16);
+    const uint32_t word_off = ZWORD ? q.z : (uint32_t)a.sch[schema].word_off;
+    f.sb1 = ZWORD ? base1 : base1 + (q.z & 0xffffu);
+    f.sb2 = ZWORD ? base2 : base2 + (q.z >> 16);
     f.bstart = bstart;
     f.bend = bend;
     const uint32_t ws1 = bstart - 1u, ws2 = bend - (uint32_t)a.r2;  // 0-based window starts
@@ -293,7 +296,6 @@ __device__ __forceinline__ void emit_pair_seq(const EmitArgs &a, const uint2 rde
     const int rel = (int)(rdesc.x >> 20);           // window start relative to the first loaded word
     const uint32_t seq_end = seq_off + S;
     const uint32_t rec_end = seq_end + 3u + S + inl + 1u;
-    // (the whole stage was filled with the quality character before the first pass)
     {
         const uint32_t c = (seq_off >> 4) + hl;
         const int k0 = (int)(16u * c) - (int)seq_off;                     // first base index of this chunk (>= -15)
@@ -477,7 +479,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_emit(const __grid_c
     if (threadIdx.x < 4 && blockIdx.x + 1184u < a.n_tiles)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(a.fdesc + (p0 + 1184ull * a.tile_pairs)) + 128u * threadIdx.x));
     {   // the quality character over both stages while the loads above are in flight: sequence chunks, separators and
-        // headers overwrite everything that is not quality
+        // headers overwrite everything that is not quality (writing only the quality lines, per read, measured 6 % slower)
         const uint4 fill = make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u);
         uint4 *st = reinterpret_cast<uint4 *>(smem);
         const uint32_t n16 = a.stage_cap / 8u;  // 16-byte units of both stages
@@ -522,24 +524,40 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_emit(const __grid_c
         return;
     }
     // stage1 = smem[0, stage_cap), stage2 = smem[stage_cap, 2 stage_cap): record offsets index smem directly
-    if (threadIdx.x < np) {
+    constexpr bool ZWORD = THREADS == 128;  // 32-pair tiles: one warp holds the tile's pairs and scans their record lengths
+    if (ZWORD ? threadIdx.x < 32u : threadIdx.x < np) {
+        const bool have = threadIdx.x < np;
         FastDesc f;
-        make_fast_desc(a, a.fdesc[p0 + threadIdx.x], tile_m0, A1, a.stage_cap + A2, f);
-        s_fa[threadIdx.x] = make_uint4(f.sb1, f.sb2, f.bstart, f.bend);
-        s_fb[threadIdx.x] = make_uint2(f.mol, f.pk);
-        {   // what phase 1 needs of each read, so that its lanes load 8 bytes and select nothing
-            constexpr uint32_t WM = BPB == 2 ? 15u : 7u;
-            const uint32_t ws1 = f.bstart - 1u, ws2 = f.bend - (uint32_t)a.r2;
-            const uint32_t rel1 = ws1 >= 15u ? ((ws1 - 15u) & WM) + 15u : ws1, rel2 = ws2 >= 15u ? ((ws2 - 15u) & WM) + 15u : ws2;
-            s_rd[2 * threadIdx.x] = make_uint2((f.sb1 + FD_HDR(f.pk) + (uint32_t)a.bclen_inline) | (rel1 << 20), f.wbase1);
-            s_rd[2 * threadIdx.x + 1] = make_uint2((f.sb2 + FD_HDR(f.pk)) | (rel2 << 20), f.wbase2);
+        make_fast_desc<ZWORD>(a, have ? a.fdesc[p0 + threadIdx.x] : make_uint4(1u, 1u, 0u, 0u), tile_m0, A1, a.stage_cap + A2, f);
+        if (ZWORD) {  // record offsets in the tile: exclusive scan of (len1 | len2 << 16); both totals are < 2^16 (tile flag)
+            const uint32_t hdr = FD_HDR(f.pk);
+            const uint32_t lens = have ? ((hdr + 2u * (uint32_t)a.bclen_inline + 2u * (uint32_t)a.r1 + 4u) | ((hdr + 2u * (uint32_t)a.r2 + 4u) << 16)) : 0u;
+            uint32_t inc = lens;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= (uint32_t)o) inc += y;
+            }
+            f.sb1 += (inc - lens) & 0xffffu;
+            f.sb2 += (inc - lens) >> 16;
         }
-        // start the loads phases 1 and 2 will need
-        prefetch_l1(a.hap + f.wbase1);
-        prefetch_l1(a.hap + f.wbase1 + (BPB == 2 ? 15 : 31));
-        prefetch_l1(a.hap + f.wbase2);
-        prefetch_l1(a.hap + f.wbase2 + (BPB == 2 ? 15 : 31));
-        prefetch_l1(a.text + (uint64_t)f.mol * a.text_stride);
+        if (have) {
+            s_fa[threadIdx.x] = make_uint4(f.sb1, f.sb2, f.bstart, f.bend);
+            s_fb[threadIdx.x] = make_uint2(f.mol, f.pk);
+            {   // what phase 1 needs of each read, so that its lanes load 8 bytes and select nothing
+                constexpr uint32_t WM = BPB == 2 ? 15u : 7u;
+                const uint32_t ws1 = f.bstart - 1u, ws2 = f.bend - (uint32_t)a.r2;
+                const uint32_t rel1 = ws1 >= 15u ? ((ws1 - 15u) & WM) + 15u : ws1, rel2 = ws2 >= 15u ? ((ws2 - 15u) & WM) + 15u : ws2;
+                s_rd[2 * threadIdx.x] = make_uint2((f.sb1 + FD_HDR(f.pk) + (uint32_t)a.bclen_inline) | (rel1 << 20), f.wbase1);
+                s_rd[2 * threadIdx.x + 1] = make_uint2((f.sb2 + FD_HDR(f.pk)) | (rel2 << 20), f.wbase2);
+            }
+            // start the loads phases 1 and 2 will need
+            prefetch_l1(a.hap + f.wbase1);
+            prefetch_l1(a.hap + f.wbase1 + (BPB == 2 ? 15 : 31));
+            prefetch_l1(a.hap + f.wbase2);
+            prefetch_l1(a.hap + f.wbase2 + (BPB == 2 ? 15 : 31));
+            prefetch_l1(a.text + (uint64_t)f.mol * a.text_stride);
+        }
     }
     const uint32_t sm = (uint32_t)__cvta_generic_to_shared(smem);
     __syncthreads();

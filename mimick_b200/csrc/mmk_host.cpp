@@ -6,17 +6,21 @@
 // (sample haplotypes).  All sampling, extraction and formatting happens in mmk_device.cu; this
 // file only sequences kernels and moves small control values.
 #include <math.h>
+#include <errno.h>
+#include <fcntl.h>
 #include <stdarg.h>
 #include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
 #include <map>
 #include <random>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -134,11 +138,14 @@ struct mmk_ctx {
     DBuf<uint4> d_fdesc;
     DBuf<uint8_t> d_tile_flags;
     DBuf<uint8_t> d_tmp, d_tmp2;  // placement scratch: (gap bits, insert length) per pair of one segment (two alternate)
+    // haplotype construction scratch, kept between samples (a 100 Mbp master: cudaMalloc + cudaFree of these cost more than the kernels)
+    DBuf<char> v_alt, v_tmp, v_snp_alt;
+    DBuf<int64_t> v_snp_pos, v_dst, v_src;
+    DBuf<uint8_t> v_kind;
     DBuf<InsTable> d_instab;  // insert-length threshold table (built by mmk_create)
     InsTable *h_instab = nullptr;
-    DBuf<uint32_t> d_big_list, d_big_count;  // molecules too long for the fused placement's shared-memory window
+    DBuf<unsigned long long> d_msum;  // placement: per molecule, length sum | accepted redraw round << 32 (k_place_sum -> k_place_chain)
     DBuf<uint32_t> d_acc_i;   // placement scratch: sum of insert lengths per molecule
-    DBuf<unsigned long long> d_acc_f;  // ... and a 2^-16 fixed-point lower bound of their real sum
     uint32_t text_stride = 0, tile_pairs = 64, n_tiles = 0, stage_cap = 0;
     int32_t fast_ok = 0;
     mmk_place_info place_info{};
@@ -163,6 +170,8 @@ struct mmk_ctx {
     DBuf<uint32_t> d_bz_sizes;
     DBuf<uint64_t> d_bz_offs;
     DBuf<uint8_t> bz_out[2][2];      // [slot][read] packed BGZF bytes of a chunk
+    void *h_ring[4] = {nullptr, nullptr, nullptr, nullptr};  // pinned host ring of mmk_emit_files
+    uint64_t h_ring_cap = 0;
     uint64_t *h_bz_tot = nullptr;    // pinned [slot][read]
     uint64_t bz_cum[2] = {0, 0};     // BGZF bytes handed out so far per stream
     bool bz_ready = false;
@@ -347,7 +356,7 @@ static void build_insert_table(const SimConst &sc, InsTable &t) {
     memset(&t, 0, sizeof t);
     if (sc.ins_robert || !(sc.ins_sd > 0.0)) return;  // the table tabulates the rejection sampler's first (accepted) normal
     const uint64_t U = (1ull << 52) - 1;
-    const double zmax = std::min(7.9, 990.0 / sc.ins_sd);
+    const double zmax = std::min(7.9, 0.48 * INS_MAX_THR / sc.ins_sd);
     const double zmin = std::max(-zmax, sc.ins_lb);
     if (!(zmin < zmax)) return;
     const uint64_t ua = first_u52(0, U, [&](uint64_t u) { return mmk_bits_to_normal(u << 12) >= zmin; });
@@ -529,6 +538,8 @@ extern "C" void mmk_destroy(mmk_ctx *c) {
     if (c->h_stats) cudaFreeHost(c->h_stats);
     if (c->h_pstate) cudaFreeHost(c->h_pstate);
     if (c->h_bz_tot) cudaFreeHost(c->h_bz_tot);
+    for (auto &p : c->h_ring)
+        if (p) cudaFreeHost(p);
     delete c->h_instab;
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
@@ -819,18 +830,30 @@ extern "C" int32_t mmk_set_sample_variants(mmk_ctx *ctx, uint32_t sample_stream,
         const Contig &mc = ctx->contigs[vcf_contigs[ci]];
         for (int h = 0; h < ploidy; ++h) {
             Build &b = builds[(size_t)ci * ploidy + h];
-            std::map<int64_t, char> snps;
             std::vector<int64_t> indels;
+            bool sorted_unique = true;  // a VCF is sorted: one SNP per position, ascending
             for (int64_t i : by[(size_t)ci * ploidy + h]) {
                 if (type[i] == 0) {
                     if (pos[i] < 1 || pos[i] > mc.len) return fail(ctx, MMK_ERR_BOUNDS, "SNP position %lld outside contig %s", (long long)pos[i], mc.name.c_str());
-                    snps[pos[i]] = alts[(size_t)alt_off[i]];
+                    if (!b.snp_pos.empty() && pos[i] <= b.snp_pos.back()) sorted_unique = false;
+                    b.snp_pos.push_back(pos[i]);
+                    b.snp_alt.push_back(alts[(size_t)alt_off[i]]);
                 } else
                     indels.push_back(i);
             }
-            for (auto &kv : snps) {
-                b.snp_pos.push_back(kv.first);
-                b.snp_alt.push_back(kv.second);
+            if (!sorted_unique) {  // several SNPs on one position: the last in file order wins (seq[pos] = alt, one after the other)
+                std::vector<size_t> ord(b.snp_pos.size());
+                for (size_t k = 0; k < ord.size(); ++k) ord[k] = k;
+                std::stable_sort(ord.begin(), ord.end(), [&](size_t x, size_t y) { return b.snp_pos[x] < b.snp_pos[y]; });
+                std::vector<int64_t> up;
+                std::string ua;
+                for (size_t k = 0; k < ord.size(); ++k) {
+                    if (k + 1 < ord.size() && b.snp_pos[ord[k + 1]] == b.snp_pos[ord[k]]) continue;  // a later record overwrites this one
+                    up.push_back(b.snp_pos[ord[k]]);
+                    ua.push_back(b.snp_alt[ord[k]]);
+                }
+                b.snp_pos.swap(up);
+                b.snp_alt.swap(ua);
             }
             // spliceinto!(seq, pos:pos+len(ref)-1, alt) in REVERSE file order on the current sequence.
             // The list is kept back to front (rev.back() is the FIRST piece).  A VCF is sorted by position, so in
@@ -894,9 +917,9 @@ extern "C" int32_t mmk_set_sample_variants(mmk_ctx *ctx, uint32_t sample_stream,
     }
     CU(ctx->d_hap.ensure(woff ? woff : 4));
     CU(cudaMemsetAsync(ctx->d_hap.p, 0, woff * 4, ctx->st));
-    DBuf<char> d_alt, d_tmp, d_snp_alt;
-    DBuf<int64_t> d_snp_pos, d_dst, d_src;
-    DBuf<uint8_t> d_kind;
+    DBuf<char> &d_alt = ctx->v_alt, &d_tmp = ctx->v_tmp, &d_snp_alt = ctx->v_snp_alt;
+    DBuf<int64_t> &d_snp_pos = ctx->v_snp_pos, &d_dst = ctx->v_dst, &d_src = ctx->v_src;
+    DBuf<uint8_t> &d_kind = ctx->v_kind;
     CU(d_alt.ensure(alts.size() + 16));
     if (!alts.empty()) CU(cudaMemcpyAsync(d_alt.p, alts.data(), alts.size(), cudaMemcpyHostToDevice, ctx->st));
     ContigStats zero{~0ull, 0, 0};
@@ -938,7 +961,7 @@ extern "C" int32_t mmk_set_sample_variants(mmk_ctx *ctx, uint32_t sample_stream,
         CU(cudaMemcpyAsync(d_kind.p, h_kind.data(), h_kind.size(), cudaMemcpyHostToDevice, ctx->st));
         pack_pieces(src_ascii, d_alt.p, d_dst.p, d_src.p, d_kind.p, (int32_t)h_dst.size(), b.out_len, ctx->d_hap.p + s.word_off,
                     ctx->bpb, ctx->d_stats, ctx->st);
-        CU(cudaStreamSynchronize(ctx->st));  // host staging vectors are reused next iteration
+        // (copies from pageable host memory return once the source has been staged: the vectors may be reused)
     }
     CU(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats, sizeof zero, cudaMemcpyDeviceToHost, ctx->st));
     CU(cudaStreamSynchronize(ctx->st));
@@ -1393,15 +1416,14 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     CU(ctx->d_fdesc.ensure(ctx->s_npairs + 1));
     CU(ctx->d_tile_flags.ensure((size_t)ctx->n_tiles + 1));
     const EmitArgs targs = base_args(ctx);
-    if (fused) {
-        const uint32_t big_cap = (uint32_t)(ctx->s_npairs / place_big_threshold() + 1);
-        CU(ctx->d_big_list.ensure(big_cap));
-        CU(ctx->d_big_count.ensure(1));
+    auto run_fused = [&]() -> int32_t {
+        CU(ctx->d_msum.ensure(ctx->s_nmol + 1));
         place_fused(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->mol0, (uint32_t)ctx->s_nmol, ctx->s_npairs, ctx->n_tiles, ctx->d_roff_l.p,
-                    ctx->d_tile_mol0.p, ctx->d_instab.p, ctx->d_big_list.p, ctx->d_big_count.p, big_cap, ctx->d_ins.p, ctx->d_mol.p,
-                    ctx->d_text.p, ctx->text_stride, ctx->d_fdesc.p, d_sum1.p, d_sum2.p, ctx->d_tile_flags.p, d_gather.p, d_err.p,
-                    ctx->stage_cap, ctx->bpb, ctx->st);
-    } else
+                    ctx->d_tile_mol0.p, ctx->d_instab.p, ctx->d_ins.p, ctx->d_mol.p, ctx->d_text.p, ctx->text_stride, ctx->d_fdesc.p,
+                    d_sum1.p, d_sum2.p, ctx->d_tile_flags.p, d_gather.p, d_err.p, ctx->d_msum.p, ctx->stage_cap, ctx->bpb, ctx->st);
+        return MMK_OK;
+    };
+    auto run_legacy = [&]() -> int32_t
     {   // Segments of at most SEG pairs bound the scratch of the flat per-pair draws.  The draws of segment k + 1
         // (compute-bound) run on the main stream while the chain of segment k (latency-bound) runs on the second
         // stream; two scratch buffers alternate.
@@ -1424,9 +1446,7 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
             CU(ctx->d_tmp.ensure(place_tmp_bytes(max_pairs)));
             if (overlap && n_seg > 1) CU(ctx->d_tmp2.ensure(place_tmp_bytes(max_pairs)));
             CU(ctx->d_acc_i.ensure(ctx->s_nmol + 1));
-            CU(ctx->d_acc_f.ensure(ctx->s_nmol + 1));
             CU(cudaMemsetAsync(ctx->d_acc_i.p, 0, (ctx->s_nmol + 1) * 4, ctx->st));
-            CU(cudaMemsetAsync(ctx->d_acc_f.p, 0, (ctx->s_nmol + 1) * 8, ctx->st));
             const bool two = overlap && n_seg > 1;
             cudaStream_t s_draw = ctx->st, s_chain = two ? ctx->st_copy : ctx->st;
             if (two) {  // the second stream starts after everything queued so far (error slot, prepare kernels)
@@ -1445,13 +1465,13 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
                 void *tmp = b ? (void *)ctx->d_tmp2.p : (void *)ctx->d_tmp.p;
                 if (two && k >= 2) CU(cudaStreamWaitEvent(s_draw, ctx->ev_chain[b], 0));  // chain k - 2 done: scratch b free again
                 place_segment_draws(ctx->sc, plan_dev(ctx), ctx->mol0, (uint32_t)ctx->s_nmol, sp[k], sp[k + 1], ctx->d_roff_l.p,
-                                    ctx->d_tile_mol0.p, ctx->n_tiles, ctx->tile_pairs, tmp, ctx->d_acc_i.p, ctx->d_acc_f.p, s_draw);
+                                    ctx->d_tile_mol0.p, ctx->n_tiles, ctx->tile_pairs, tmp, ctx->d_acc_i.p, ctx->d_instab.p, s_draw);
                 if (two) {
                     CU(cudaEventRecord(ctx->ev_draw[b], s_draw));
                     CU(cudaStreamWaitEvent(s_chain, ctx->ev_draw[b], 0));
                 }
                 place_segment_chain(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->mol0, (uint32_t)sb[k], (uint32_t)sb[k + 1], sp[k],
-                                    ctx->d_roff_l.p, tmp, ctx->d_acc_i.p, ctx->d_acc_f.p, ctx->d_ins.p, ctx->d_mol.p, ctx->d_text.p,
+                                    ctx->d_roff_l.p, tmp, ctx->d_acc_i.p, ctx->d_ins.p, ctx->d_mol.p, ctx->d_text.p,
                                     ctx->text_stride, d_err.p, s_chain);
                 if (two) {
                     CU(cudaEventRecord(ctx->ev_chain[b], s_chain));
@@ -1464,11 +1484,17 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
             }
             prepare_upto(n_seg - 1, ctx->st);  // what is left (everything when there is one stream)
         }
-    }
+        return MMK_OK;
+    };
     unsigned long long herr[3];
-    CU(cudaMemcpyAsync(herr, d_err.p, sizeof herr, cudaMemcpyDeviceToHost, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
-    CU(cudaGetLastError());
+    for (;;) {
+        int32_t rc = fused ? run_fused() : run_legacy();
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(herr, d_err.p, sizeof herr, cudaMemcpyDeviceToHost, ctx->st));
+        CU(cudaStreamSynchronize(ctx->st));
+        CU(cudaGetLastError());
+        break;
+    }
     if (herr[0] != ~0ull) {
         uint8_t code = 0;
         CU(cudaMemcpy(&code, ctx->p_status.p + herr[0], 1, cudaMemcpyDeviceToHost));
@@ -1971,6 +1997,93 @@ extern "C" int32_t mmk_emit_stream_bgzf(mmk_ctx *ctx, void *const r1_host[2], vo
     CU(cudaStreamSynchronize(ctx->st));
     CU(cudaGetLastError());
     return MMK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// files
+// ------------------------------------------------------------------------------------------
+namespace {
+struct FileSink {
+    int fd[2] = {-1, -1};
+    uint64_t written[2] = {0, 0};
+    int err = 0;
+};
+bool write_all(int fd, const char *p, uint64_t n) {
+    while (n) {
+        const ssize_t w = ::write(fd, p, (size_t)std::min<uint64_t>(n, 1u << 30));
+        if (w < 0) {
+            if (errno == EINTR) continue;
+            return false;
+        }
+        p += w;
+        n -= (uint64_t)w;
+    }
+    return true;
+}
+int32_t file_sink_cb(void *user, const mmk_chunk *ch, const void *r1, const void *r2) {
+    FileSink *s = (FileSink *)user;
+    bool ok2 = true;
+    std::thread t2([&] { ok2 = write_all(s->fd[1], (const char *)r2, ch->r2_bytes); });  // R2 beside R1
+    const bool ok1 = write_all(s->fd[0], (const char *)r1, ch->r1_bytes);
+    t2.join();
+    if (!ok1 || !ok2) {
+        s->err = errno ? errno : EIO;
+        return MMK_ERR_IO;
+    }
+    s->written[0] += ch->r1_bytes;
+    s->written[1] += ch->r2_bytes;
+    return MMK_OK;
+}
+}  // namespace
+
+extern "C" int32_t mmk_emit_files(mmk_ctx *ctx, const char *r1_path, const char *r2_path, int32_t bgzf, int32_t append_eof,
+                                  int32_t append, uint64_t bytes_written[2]) {
+    if (!ctx || !r1_path || !r2_path) return MMK_ERR_INVALID_ARG;
+    if (!ctx->placed) return fail(ctx, MMK_ERR_STATE, "mmk_place has not run");
+    CU(cudaSetDevice(ctx->par.device));
+    uint64_t slot = 0;
+    if (bgzf) {
+        int32_t rc = mmk_bgzf_bound(ctx, &slot);
+        if (rc) return rc;
+    } else
+        slot = ctx->out_cap;
+    slot = std::max<uint64_t>(slot, 4096);
+    if (ctx->h_ring_cap < slot) {  // pinned ring, kept with the context
+        for (auto &p : ctx->h_ring) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+        }
+        ctx->h_ring_cap = 0;
+        for (auto &p : ctx->h_ring) CU(cudaMallocHost((void **)&p, slot));
+        ctx->h_ring_cap = slot;
+    }
+    FileSink sink;
+    const int flags = O_WRONLY | O_CREAT | (append ? O_APPEND : O_TRUNC);
+    sink.fd[0] = ::open(r1_path, flags, 0644);
+    sink.fd[1] = ::open(r2_path, flags, 0644);
+    if (sink.fd[0] < 0 || sink.fd[1] < 0) {
+        const int e = errno;
+        if (sink.fd[0] >= 0) ::close(sink.fd[0]);
+        if (sink.fd[1] >= 0) ::close(sink.fd[1]);
+        return fail(ctx, MMK_ERR_IO, "cannot open %s / %s for writing: %s", r1_path, r2_path, strerror(e));
+    }
+    void *const s1[2] = {ctx->h_ring[0], ctx->h_ring[1]}, *const s2[2] = {ctx->h_ring[2], ctx->h_ring[3]};
+    int32_t rc = bgzf ? mmk_emit_stream_bgzf(ctx, s1, s2, slot, file_sink_cb, &sink) : mmk_emit_stream(ctx, s1, s2, slot, file_sink_cb, &sink);
+    if (!rc && bgzf && append_eof) {
+        uint8_t eof[28];
+        mmk_bgzf_eof(eof, sizeof eof);
+        for (int r = 0; r < 2; ++r) {
+            if (!write_all(sink.fd[r], (const char *)eof, sizeof eof)) rc = MMK_ERR_IO;
+            else sink.written[r] += sizeof eof;
+        }
+    }
+    const bool c1 = ::close(sink.fd[0]) == 0, c2 = ::close(sink.fd[1]) == 0;
+    if (rc == MMK_ERR_IO || (!rc && !(c1 && c2))) return fail(ctx, MMK_ERR_IO, "write to %s / %s failed: %s", r1_path, r2_path, strerror(sink.err ? sink.err : errno));
+    if (bytes_written) {
+        bytes_written[0] = sink.written[0];
+        bytes_written[1] = sink.written[1];
+    }
+    return rc;
 }
 
 extern "C" uint64_t mmk_launch_count(void) { return (uint64_t)launch_count(); }

@@ -31,7 +31,7 @@ struct SimConst {
 };
 
 // Insert-length table (mmk_place.cuh): trunc(mu + sd * Phi^-1) of the top 32 bits of a draw by search among thresholds.
-constexpr int INS_CELL_BITS = 9, INS_CELLS = 1 << INS_CELL_BITS, INS_MAX_THR = 2048;
+constexpr int INS_CELL_BITS = 9, INS_CELLS = 1 << INS_CELL_BITS, INS_MAX_THR = 1024;
 struct InsTable {
     uint32_t enabled;   // 0: every draw takes the double-precision path
     uint32_t n_thr;     // thresholds in thr[]
@@ -170,22 +170,20 @@ void shard_bounds(const uint64_t *d_read_off, uint64_t n_mol, uint64_t n_pairs, 
 void place_prepare(uint64_t mol0, uint32_t n_mol, const uint64_t *d_read_off_global, uint64_t *d_read_off_local,
                    uint32_t *d_tile_mol0, uint32_t tile_pairs, cudaStream_t st);
 size_t place_tmp_bytes(uint64_t max_pairs);
-// d_acc_i / d_acc_f: per shard molecule, zeroed by the caller before the first segment
+// d_acc_i: per shard molecule, zeroed by the caller before the first segment
 void place_segment_draws(const SimConst &sc, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint64_t pair_lo, uint64_t pair_hi,
                          const uint64_t *d_read_off_local, const uint32_t *d_tile_mol0, uint32_t n_tiles, uint32_t tile_pairs,
-                         void *d_tmp, uint32_t *d_acc_i, unsigned long long *d_acc_f, cudaStream_t st);
+                         void *d_tmp, uint32_t *d_acc_i, const InsTable *d_tab, cudaStream_t st);
 void place_segment_chain(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t m_lo, uint32_t m_hi,
-                         uint64_t pair_lo, const uint64_t *d_read_off_local, void *d_tmp, uint32_t *d_acc_i,
-                         unsigned long long *d_acc_f, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
+                         uint64_t pair_lo, const uint64_t *d_read_off_local, void *d_tmp, uint32_t *d_acc_i, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
                          unsigned long long *d_err, cudaStream_t st);
 
-// fused placement (mmk_place.cuh): needs 32-pair tiles. d_big_list: capacity n_pairs / place_big_threshold() + 1
-uint32_t place_big_threshold();
+// fused placement (mmk_place.cuh): needs 32-pair tiles
 void place_fused(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint64_t n_pairs,
-                 uint32_t n_tiles, const uint64_t *d_roff_l, uint32_t *d_tile_mol0, const InsTable *d_tab, uint32_t *d_big_list,
-                 uint32_t *d_big_count, uint32_t big_cap, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
-                 uint4 *d_fdesc, uint32_t *d_sum1, uint32_t *d_sum2, uint8_t *d_tile_flags, unsigned long long *d_gather,
-                 unsigned long long *d_err, uint32_t stage_cap, int bpb, cudaStream_t st);
+                 uint32_t n_tiles, const uint64_t *d_roff_l, uint32_t *d_tile_mol0, const InsTable *d_tab, uint2 *d_ins, MolRec *d_mol,
+                 uint8_t *d_text, uint32_t text_stride, uint4 *d_fdesc, uint32_t *d_sum1, uint32_t *d_sum2, uint8_t *d_tile_flags,
+                 unsigned long long *d_gather, unsigned long long *d_err, unsigned long long *d_msum, uint32_t stage_cap, int bpb,
+                 cudaStream_t st);
 void place_local_roff(uint64_t mol0, uint32_t n_mol, const uint64_t *d_read_off_global, uint64_t *d_read_off_local, cudaStream_t st);
 // KAT: lengths the kernels derive from raw 64-bit draws (table path with its exact fallback); slow[i] = 1 where the fallback ran
 void kat_insert_len(const SimConst &sc, const InsTable *d_tab, const uint64_t *d_bits, uint32_t *d_len, uint8_t *d_slow, int64_t n, cudaStream_t st);

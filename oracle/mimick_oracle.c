@@ -79,6 +79,8 @@ typedef struct {
     int32_t fq_format;       /* ORC_FMT_* (output style)   src/Common.jl:56-74 */
     int32_t bc_format;       /* ORC_FMT_* (barcode style) */
     int32_t strict_wrap;     /* 0 = literal reference wrap (D5), 1 = modular wrap */
+    int32_t pad;
+    double err_sub_start, err_sub_end, err_ins, err_del; /* sequencing-error model (not in the reference; all 0 = off) */
 } orc_params;
 
 typedef struct {
@@ -166,6 +168,11 @@ typedef struct orc_sim {
     size_t n_cps, cap_cps;
     uint64_t bytes_r1, bytes_r2;
     int64_t total_pairs;
+    /* sequencing-error model: per-cycle substitution thresholds and base qualities of R1 / R2 (DESIGN.md "Error model") */
+    int err_on;
+    uint32_t *err_thr[2];
+    uint8_t *err_qb[2];
+    uint32_t err_tins, err_tdel;
     int err;
     char errmsg[256];
 } orc_sim;
@@ -425,6 +432,27 @@ orc_sim *orc_create(const orc_params *p) {
         fail(s, ORC_ERR_UNSUPPORTED, "insert-size truncation at 200 keeps no mass of the normal law");
     s->mode = 1;
     s->seed = 0;
+    s->err_on = p->err_sub_start > 0.0 || p->err_sub_end > 0.0 || p->err_ins > 0.0 || p->err_del > 0.0;
+    if (s->err_on) {
+        if (p->err_sub_start < 0 || p->err_sub_end < 0 || p->err_ins < 0 || p->err_del < 0 ||
+            (p->err_sub_start > p->err_sub_end ? p->err_sub_start : p->err_sub_end) + p->err_ins + p->err_del > 0.5)
+            fail(s, ORC_ERR_INVALID_ARG, "error rates must be >= 0 and sum to at most 0.5");
+        for (int r = 0; r < 2; ++r) {
+            const int S = r ? p->length_r2 : p->length_r1;
+            s->err_thr[r] = (uint32_t *)malloc((size_t)S * 4);
+            s->err_qb[r] = (uint8_t *)malloc((size_t)S);
+            for (int c = 0; c < S; ++c) {
+                const double e = S > 1 ? p->err_sub_start + (p->err_sub_end - p->err_sub_start) * (double)c / (double)(S - 1) : p->err_sub_start;
+                s->err_thr[r][c] = (uint32_t)floor(e * 4294967296.0);
+                double et = e + p->err_ins + p->err_del;
+                if (et < 1e-4) et = 1e-4;
+                int q = (int)floor(-10.0 * log10(et) + 0.5);
+                s->err_qb[r][c] = (uint8_t)(q < 2 ? 2 : q > 40 ? 40 : q);
+            }
+        }
+        s->err_tins = (uint32_t)floor(p->err_ins * 4294967296.0);
+        s->err_tdel = (uint32_t)floor(p->err_del * 4294967296.0);
+    }
     return s;
 }
 void orc_destroy(orc_sim *s) {
@@ -441,6 +469,7 @@ void orc_destroy(orc_sim *s) {
     free(s->ins_stop);
     free(s->rec);
     free(s->cps);
+    for (int r = 0; r < 2; ++r) { free(s->err_thr[r]); free(s->err_qb[r]); }
     free(s);
 }
 int orc_error(const orc_sim *s) { return s->err; }
@@ -735,10 +764,56 @@ static int64_t circular_index(const orc_schema *c, int64_t a, int64_t b, int str
 
 static int dec(char *o, int64_t v) { return sprintf(o, "%lld", (long long)v); }
 
+/* Sequencing-error model (NOT in the reference: docs/algorithm.md:11 lists it as future work; specified in DESIGN.md
+ * "Error model").  One read of nominal length S: cycle c takes one 64-bit draw (mmk_error_draw: seed, sample, run-wide
+ * pair index, read, cycle).  Low word u: u < thr_sub[c] substitution; next t_ins insertion; next t_del deletion.  High
+ * word: bits 0-1 replacement selector, bits 2-4 quality jitter.  The template is walked from the read's first base
+ * (R2: a2 upwards; R1: bs + r1 - 1 downwards, complemented): an insertion emits ACGT[sel] and consumes no template base; a
+ * deletion skips one template base first; positions past the contig ends are clamped (strict circular wrap: modular).
+ * A substitution replaces an A/C/G/T by ACGT[(code + 1 + sel % 3) % 4] (other IUPAC symbols stay).  Quality of cycle c:
+ * 33 + clamp(qbase[c] + jitter[-2,-1,0,0,0,0,1,2] - 10 [substituted or inserted], 2, 41). */
+static void erroneous_read(orc_sim *s, const orc_schema *c, int rd, int64_t first_pos, uint64_t pair, char *seq_out, char *qual_out) {
+    static const int JIT[8] = {-2, -1, 0, 0, 0, 0, 1, 2};
+    static const char ACGT[4] = {'A', 'C', 'G', 'T'};
+    const int S = rd == 1 ? s->par.length_r1 : s->par.length_r2;
+    const uint32_t *thr = s->err_thr[rd - 1];
+    const uint8_t *qb = s->err_qb[rd - 1];
+    const int64_t n = c->len;
+    int64_t r = 0; /* template bases consumed */
+    for (int cyc = 0; cyc < S; ++cyc) {
+        const uint64_t d = mmk_error_draw(s->seed, s->sample, pair, (uint32_t)rd, (uint32_t)cyc);
+        const uint32_t u = (uint32_t)d, aux = (uint32_t)(d >> 32);
+        const uint32_t sel = aux & 3u, jit = (aux >> 2) & 7u;
+        const int is_sub = u < thr[cyc];
+        const int is_ins = !is_sub && (u - thr[cyc]) < s->err_tins;
+        const int is_del = !is_sub && !is_ins && (u - thr[cyc] - s->err_tins) < s->err_tdel;
+        char b;
+        if (is_ins) {
+            b = ACGT[sel];
+        } else {
+            if (is_del) r++;
+            int64_t pos = rd == 1 ? first_pos - r : first_pos + r; /* 1-based */
+            if (s->par.strict_wrap) pos = ((pos - 1) % n + n) % n + 1;
+            else pos = pos < 1 ? 1 : pos > n ? n : pos;
+            b = c->seq[pos - 1];
+            if (rd == 1) b = comp(b);
+            r++;
+            if (is_sub) {
+                const char *at = b ? strchr("ACGT", b) : NULL;
+                if (at) b = ACGT[((int)(at - "ACGT") + 1 + (int)(sel % 3u)) % 4];
+            }
+        }
+        seq_out[cyc] = b;
+        int q = (int)qb[cyc] + JIT[jit] - ((is_sub || is_ins) ? 10 : 0);
+        q = q < 2 ? 2 : q > 41 ? 41 : q;
+        qual_out[cyc] = (char)(33 + q);
+    }
+}
+
 /* One molecule: get_sequences (:227-251) + seq_breakpoints! (:21-35) + extract_sequences!
  * (:95-109) + format_R1/format_R2 (src/FormatFASTQ.jl). */
 static void simulate_molecule(orc_sim *s, int schema_idx, int64_t molsize, const int64_t *lens, int64_t n_frags,
-                              const char *barcode, int bclen, bytebuf *t1, bytebuf *t2) {
+                              const char *barcode, int bclen, bytebuf *t1, bytebuf *t2, uint64_t pair_base) {
     const orc_params *p = &s->par;
     orc_schema *c = &s->sch[schema_idx];
     int64_t seq_len = c->len;
@@ -820,11 +895,25 @@ static void simulate_molecule(orc_sim *s, int schema_idx, int64_t molsize, const
                 bb_put(out, "/", 1); bb_put(out, &rc, 1); bb_put(out, "\tVX:i:1\tBX:Z:", 13); bb_put(out, barcode, (size_t)bclen); bb_put(out, "\n", 1);
                 break;
             }
-            if (rd == 1) { bb_put(out, t1->p + o1, (size_t)l1[i]); o1 += (size_t)l1[i]; }
-            else { bb_put(out, t2->p + o2, (size_t)l2[i]); o2 += (size_t)l2[i]; }
-            bb_put(out, "\n+\n", 3);
-            bb_fill(out, 'I', (size_t)(rd == 1 ? q1 : q2));
-            bb_put(out, "\n", 1);
+            const int64_t li = rd == 1 ? l1[i] : l2[i], qi = rd == 1 ? q1 : q2;
+            const int S = rd == 1 ? p->length_r1 : p->length_r2;
+            const int inl = (rd == 1 && p->fq_format == ORC_FMT_TENX) ? bclen : 0;
+            if (s->err_on && li == S && qi == S + inl) { /* the model covers reads of nominal length (others: the literal-wrap artefacts) */
+                char *es = (char *)malloc((size_t)S * 2), *eq = es + S;
+                erroneous_read(s, c, rd, rd == 1 ? bs[i] + p->length_r1 - 1 : be[i] - p->length_r2 + 1, pair_base + (uint64_t)i, es, eq);
+                bb_put(out, es, (size_t)S);
+                bb_put(out, "\n+\n", 3);
+                bb_fill(out, 'I', (size_t)inl); /* the inline barcode is not sequenced template: constant quality */
+                bb_put(out, eq, (size_t)S);
+                bb_put(out, "\n", 1);
+                free(es);
+            } else {
+                bb_put(out, (rd == 1 ? t1->p + o1 : t2->p + o2), (size_t)li);
+                bb_put(out, "\n+\n", 3);
+                bb_fill(out, 'I', (size_t)qi);
+                bb_put(out, "\n", 1);
+            }
+            if (rd == 1) o1 += (size_t)l1[i]; else o2 += (size_t)l2[i];
         }
     }
     free(l1);
@@ -883,7 +972,7 @@ int orc_run(orc_sim *s) {
             m->group = (int64_t)g; m->slot = (int32_t)j; m->schema = target; m->molsize = molsize;
             m->n_frags = nf; m->first_read = (int64_t)s->n_ins; m->barcode_index = (int64_t)bc_counter; m->start = 0;
             bc_counter++;
-            simulate_molecule(s, target, molsize, lens, nf, bc, bclen, &t1, &t2); /* :51-53 */
+            simulate_molecule(s, target, molsize, lens, nf, bc, bclen, &t1, &t2, (uint64_t)total_pairs); /* :51-53 */
             s->sch[target].reads_current += nf;                                /* :54 */
             total_pairs += nf;
         }

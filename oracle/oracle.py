@@ -48,6 +48,8 @@ class OrcParams(C.Structure):
         ("fq_format", C.c_int32),
         ("bc_format", C.c_int32),
         ("strict_wrap", C.c_int32),
+        ("pad", C.c_int32),
+        ("err_sub_start", C.c_double), ("err_sub_end", C.c_double), ("err_ins", C.c_double), ("err_del", C.c_double),
     ]
 
 
@@ -298,14 +300,15 @@ class SimResult:
 class Oracle:
     def __init__(self, fmt="standard:haplotagging", coverage=30, n_molecules=2, mol_coverage=0.2,
                  mol_length=80000, insert_length=500, insert_stdev=50, read_length=(150, 150),
-                 singletons=0.0, circular=False, attempts=25, strict_wrap=False):
+                 singletons=0.0, circular=False, attempts=25, strict_wrap=False, error_rate=(0.0, 0.0), indel_error=(0.0, 0.0)):
         L = lib()
         bc, out = interperet_format(fmt)
         self.coverage = float(coverage)
         self.read_length = tuple(read_length)
         self.par = OrcParams(int(insert_length), int(insert_stdev), int(read_length[0]), int(read_length[1]),
                              int(n_molecules), int(attempts), int(mol_length), float(mol_coverage),
-                             float(singletons), int(bool(circular)), FMT[out], FMT[bc], int(bool(strict_wrap)))
+                             float(singletons), int(bool(circular)), FMT[out], FMT[bc], int(bool(strict_wrap)), 0,
+                             float(error_rate[0]), float(error_rate[1]), float(indel_error[0]), float(indel_error[1]))
         self.h = L.orc_create(C.byref(self.par))
         self._keep = []
         self.n_schema = 0
@@ -435,7 +438,7 @@ class Oracle:
 # ------------------------------------------------------------------------------------------
 def _common_kwargs(kw):
     keys = ("coverage", "n_molecules", "mol_coverage", "mol_length", "insert_length", "insert_stdev",
-            "read_length", "singletons", "circular", "attempts", "strict_wrap")
+            "read_length", "singletons", "circular", "attempts", "strict_wrap", "error_rate", "indel_error")
     return {k: kw[k] for k in keys if k in kw}
 
 

@@ -87,7 +87,7 @@ def oracle_digest(fmt, schemas, seed, sample, window, max_pairs=0, **kw):
     borrowed, not copied."""
     import oracle as O
     keys = ("coverage", "n_molecules", "mol_coverage", "mol_length", "insert_length", "insert_stdev", "read_length",
-            "singletons", "circular", "attempts", "strict_wrap")
+            "singletons", "circular", "attempts", "strict_wrap", "error_rate", "indel_error")
     o = O.Oracle(fmt, **{k: kw[k] for k in keys if k in kw})
     o.set_philox(seed, sample)
     L = O.lib()

@@ -587,14 +587,14 @@ def _env(**kv):
 
 
 @pytest.mark.parametrize("kw", [
-    dict(coverage=30, singletons=0.1),                                  # blocks of 2048 pairs, molecules straddling their boundaries
-    dict(coverage=30, singletons=1.0),                                  # every molecule one pair: 2048 molecules per block
-    dict(coverage=40, mol_length=2_000_000, mol_coverage=0.5, singletons=0.0),   # molecules of 1000s of pairs: k_place_big
-    dict(coverage=30, mol_length=400_000, mol_coverage=0.6, singletons=0.3, n_molecules=4),   # a mix around the 512-pair limit
+    dict(coverage=30, singletons=0.1),
+    dict(coverage=30, singletons=1.0),                                  # every molecule one pair
+    dict(coverage=40, mol_length=2_000_000, mol_coverage=0.5, singletons=0.0),   # molecules of 1000s of pairs
+    dict(coverage=30, mol_length=400_000, mol_coverage=0.6, singletons=0.3, n_molecules=4),   # a mix of short and long molecules
 ])
 def test_placement_paths_agree_with_the_oracle(tmp_path, kw):
-    """The default placement path, the fused kernel (64- and 32-tile blocks) and the three-kernel path give the oracle's bytes,
-    plan and inserts."""
+    """The default placement path, the lane-per-molecule kernels (also with other warp shares) and the three-kernel
+    path give the oracle's bytes, plan and inserts."""
     rng = np.random.default_rng(14)
     p1 = os.path.join(str(tmp_path), "a.fa")
     p2 = os.path.join(str(tmp_path), "b.fa")
@@ -605,7 +605,8 @@ def test_placement_paths_agree_with_the_oracle(tmp_path, kw):
     nf = gpu["mol"]["n_frags"]
     if kw.get("mol_length", 0) >= 400_000:
         assert (nf > 512).sum() > 3 and (nf <= 512).sum() > 3
-    for env in (dict(MMK_PLACE_MODE="fused"), dict(MMK_PLACE_MODE="fused", MMK_PLACE_TB=32), dict(MMK_PLACE_MODE="legacy")):
+    for env in (dict(MMK_PLACE_MODE="fused"), dict(MMK_PLACE_MODE="fused", MMK_PLACE_WAVES=7),
+                dict(MMK_PLACE_MODE="legacy")):
         with _env(**env):
             alt = gpu_single([p1, p2], "haplotagging", 31, variates=False, **okw)
         assert alt["r1"] == gpu["r1"] and alt["r2"] == gpu["r2"], env
