@@ -312,18 +312,26 @@ MMK_HD uint64_t mmk_insert_next64(mmk_stream *s) {
 }
 #define MMK_INSERT_GAP_DRAW 1u
 
-/* Sequencing-error model (optional, default off): one 64-bit draw per (read pair, read, cycle).
- *   key = seed; counter = (cycle >> 1 | (read - 1) << 24, MMK_P_ERROR | sample << 8, pair[31:0], pair[63:32]);
- *   even cycles take words (0,1) of the block, odd cycles words (2,3).  `pair` is the run-wide index of the read pair
- *   (it fixes barcode, molecule and insert), `read` 1 or 2, cycle < 2^25.
- * Low word: the event uniform; high word: bits 0-1 replacement selector, bits 2-4 quality jitter. */
-MMK_HD uint64_t mmk_error_draw(uint64_t seed, uint32_t sample, uint64_t pair, uint32_t read, uint32_t cycle) {
+/* Sequencing-error model (optional, default off): one 32-bit draw per (read pair, read, cycle), four cycles per block.
+ *   key = seed; counter = (cycle >> 2 | (read - 1) << 24, MMK_P_ERROR | sample << 8, pair[31:0], pair[63:32]);
+ *   cycle c takes word c & 3 of the block.  `pair` is the run-wide index of the read pair (it fixes barcode, molecule
+ *   and insert), `read` 1 or 2, cycle < 2^26.
+ * Bits 0-23: the event uniform (thresholds are probabilities scaled by 2^24); bits 24-25: replacement selector;
+ * bits 26-28: quality jitter. */
+MMK_HD void mmk_error_block(uint64_t seed, uint32_t sample, uint64_t pair, uint32_t read, uint32_t block, uint32_t o[4]) {
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
-    uint32_t ctr[4] = {(cycle >> 1) | ((read - 1u) << 24), (uint32_t)MMK_P_ERROR | ((sample & 0xffffu) << 8), (uint32_t)pair, (uint32_t)(pair >> 32)};
-    uint32_t o[4];
+    uint32_t ctr[4] = {block | ((read - 1u) << 24), (uint32_t)MMK_P_ERROR | ((sample & 0xffffu) << 8), (uint32_t)pair, (uint32_t)(pair >> 32)};
     mmk_philox4x32_10(ctr, key, o);
-    return (cycle & 1u) ? (((uint64_t)o[3] << 32) | o[2]) : (((uint64_t)o[1] << 32) | o[0]);
 }
+MMK_HD uint32_t mmk_error_draw(uint64_t seed, uint32_t sample, uint64_t pair, uint32_t read, uint32_t cycle) {
+    uint32_t o[4];
+    mmk_error_block(seed, sample, pair, read, cycle >> 2, o);
+    return o[cycle & 3u];
+}
+#define MMK_ERR_U(w) ((w) & 0xffffffu)
+#define MMK_ERR_SEL(w) (((w) >> 24) & 3u)
+#define MMK_ERR_JIT(w) (((w) >> 26) & 7u)
+#define MMK_ERR_SCALE 16777216.0 /* 2^24 */
 
 /* ---- variates ---------------------------------------------------------------------------- */
 /* u01 in [0,1): 53 random bits */

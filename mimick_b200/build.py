@@ -26,7 +26,7 @@ HOST_FLAGS = "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall,-Wno-unused-function"
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", HOST_FLAGS, "-I", INCLUDE, "-I", CSRC]
 
 SOURCES = ["mmk_device.cu", "mmk_host.cpp", "mmk_io.cpp"]
-HEADERS = ["mmk_internal.h", "mmk_sampling.cuh", "mmk_host.h", "mmk_emit.cuh", "mmk_bgzf.cuh", "mmk_bgzf_table.h"]
+HEADERS = ["mmk_internal.h", "mmk_sampling.cuh", "mmk_host.h", "mmk_emit.cuh", "mmk_bgzf.cuh", "mmk_bgzf_table.h", "mmk_place.cuh", "mmk_plan.cuh"]
 
 
 def _nvcc() -> str:

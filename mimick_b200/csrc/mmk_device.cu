@@ -802,29 +802,34 @@ void place_segment_chain(const SimConst &sc, const SchemaDev *d_sch, PlanDev pla
 }
 
 // ------------------------------------------------------------------------------------------
-// fused placement: launchers (kernels in mmk_place.cuh, included above)
+// block placement: launcher (kernels in mmk_place.cuh, included above)
 // ------------------------------------------------------------------------------------------
-
 void place_local_roff(uint64_t mol0, uint32_t n_mol, const uint64_t *d_read_off_global, uint64_t *d_read_off_local, cudaStream_t st) {
     LAUNCH(k_local_roff, (n_mol + 1 + 255) / 256, 256, 0, st, d_read_off_global, mol0, n_mol, d_read_off_local);
 }
+uint32_t place_block_count(uint64_t n_pairs, uint32_t n_mol) { return (uint32_t)((n_pairs + (uint64_t)PB_W * n_mol) / PB_TARGET + 1); }
+uint32_t place_big_cap(uint64_t n_pairs) { return (uint32_t)(n_pairs / PB_BIG + 1); }
+bool place_block_supports(const SimConst &sc) { return (double)sc.insert_length + 9.0 * sc.ins_sd < 65000.0; }
 
-void place_fused(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint64_t n_pairs,
+void place_block(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint64_t n_pairs,
                  uint32_t n_tiles, const uint64_t *d_roff_l, uint32_t *d_tile_mol0, const InsTable *d_tab, uint2 *d_ins, MolRec *d_mol,
                  uint8_t *d_text, uint32_t text_stride, uint4 *d_fdesc, uint32_t *d_sum1, uint32_t *d_sum2, uint8_t *d_tile_flags,
-                 unsigned long long *d_gather, unsigned long long *d_err, unsigned long long *d_msum, uint32_t stage_cap, int bpb,
-                 cudaStream_t st) {
+                 unsigned long long *d_gather, unsigned long long *d_err, uint32_t *d_weight, uint64_t *d_woff, uint64_t *d_scan_tmp,
+                 uint32_t *d_blk, uint32_t *d_big_list, uint32_t *d_big_count, uint32_t stage_cap, int bpb, cudaStream_t st) {
     if (n_mol == 0 || n_pairs == 0) return;
-    int dev = 0, sms = 0, ctas_sum = 0, ctas_chain = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_sum, k_mol_sum, PLM_THREADS, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_chain, k_mol_chain, PLM_THREADS, 0);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_place_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PB_SMEM);
+        attr_set = true;
+    }
+    const uint32_t n_blocks = place_block_count(n_pairs, n_mol), big_cap = place_big_cap(n_pairs);
     cudaMemsetAsync(d_sum1, 0, (size_t)n_tiles * 4, st);
     cudaMemsetAsync(d_sum2, 0, (size_t)n_tiles * 4, st);
     cudaMemsetAsync(d_tile_flags, 0, (size_t)n_tiles, st);
-    LAUNCH(k_tile_mol0, (n_mol + 255) / 256, 256, 0, st, d_roff_l, n_mol, 32u, d_tile_mol0);
+    cudaMemsetAsync(d_big_count, 0, 4, st);
+    LAUNCH(k_mol_weights, (n_mol + 255) / 256, 256, 0, st, d_roff_l, n_mol, d_tile_mol0, d_weight, d_big_list, d_big_count, big_cap);
+    exclusive_scan_u32(d_weight, d_woff, n_mol, d_scan_tmp, st);
+    LAUNCH(k_place_blocks, (n_blocks + 1 + 255) / 256, 256, 0, st, d_woff, n_mol, n_blocks, d_blk);
     PlaceArgs a;
     a.sc = sc;
     a.sch = d_sch;
@@ -834,8 +839,14 @@ void place_fused(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint6
     a.n_tiles = n_tiles;
     a.n_pairs = n_pairs;
     a.roff = d_roff_l;
+    a.woff = d_woff;
+    a.blk = d_blk;
+    a.n_blocks = n_blocks;
     a.tile_mol0 = d_tile_mol0;
     a.tab = d_tab;
+    a.big_list = d_big_list;
+    a.big_count = d_big_count;
+    a.big_cap = big_cap;
     a.ins = d_ins;
     a.mol = d_mol;
     a.fdesc = d_fdesc;
@@ -844,19 +855,9 @@ void place_fused(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint6
     a.tile_flags = d_tile_flags;
     a.gather = d_gather;
     a.err = d_err;
-    a.msum = d_msum;
     a.bpb = bpb;
-    // one resident wave per kernel (a warp owns 1 / n_warps of the pairs, at least a few hundred)
-    const uint32_t wpc = PLM_THREADS / 32;
-    auto warps_for = [&](int ctas) {
-        uint32_t w = (uint32_t)sms * (uint32_t)(ctas > 0 ? ctas : 4) * wpc;
-        if (const char *e = getenv("MMK_PLACE_WAVES")) w *= (uint32_t)std::max(1, atoi(e));  // more, smaller shares (profiling)
-        return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(w, n_pairs / 256 + 1));
-    };
-    a.n_warps = warps_for(ctas_sum);
-    LAUNCH(k_mol_sum, (a.n_warps + wpc - 1) / wpc, PLM_THREADS, 0, st, a);
-    a.n_warps = warps_for(ctas_chain);
-    LAUNCH(k_mol_chain, (a.n_warps + wpc - 1) / wpc, PLM_THREADS, 0, st, a);
+    LAUNCH(k_place_big, std::min<uint32_t>(big_cap, 592u), PB_THREADS, 0, st, a);  // exits at once when there are no big molecules
+    LAUNCH(k_place_block, n_blocks, PB_THREADS, PB_SMEM, st, a);
     LAUNCH(k_tile_flags, (n_tiles + 255) / 256, 256, 0, st, d_sum1, d_sum2, n_tiles, stage_cap, d_tile_flags);
     LAUNCH(k_mol_text, (n_mol + 127) / 128, 128, 0, st, sc, d_sch, mol0, 0u, n_mol, d_mol, d_text, text_stride);
 }
@@ -964,7 +965,16 @@ void emit(const EmitArgs &a, cudaStream_t st) {
         cudaFuncSetAttribute(k_emit<4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         cudaFuncSetAttribute(k_emit<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         cudaFuncSetAttribute(k_emit<4, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_emit_w<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_emit_w<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr_set[dev & 63] = true;
+    }
+    // 32-pair tiles: autonomous warps, stage fill by bulk copy (MMK_EMIT_MODE=cta keeps the CTA-synchronous kernel)
+    static const bool warp_mode = !(getenv("MMK_EMIT_MODE") && strcmp(getenv("MMK_EMIT_MODE"), "cta") == 0);
+    if (a.tile_pairs == 32 && a.qfill && warp_mode) {
+        if (a.bpb == 2) LAUNCH((k_emit_w<2>), a.n_tiles, 128, smem, st, a);
+        else LAUNCH((k_emit_w<4>), a.n_tiles, 128, smem, st, a);
+        return;
     }
     // one thread per (pair, header piece): 64-pair tiles run 256 threads, 32-pair tiles 128
     if (a.tile_pairs > 32) {

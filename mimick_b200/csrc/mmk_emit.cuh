@@ -599,4 +599,244 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_emit(const __grid_c
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // stage must outlive the copy
 }
 
+
+// ------------------------------------------------------------------------------------------
+// k_emit_w — the same fast path with autonomous warps (32-pair tiles, 4 warps, 8 consecutive pairs each)
+// ------------------------------------------------------------------------------------------
+// What differs from k_emit:
+//   * the quality character arrives in both stages by ONE bulk asynchronous copy (TMA, global -> shared, from an
+//     L2-resident buffer of 'I'), issued by thread 0 before anything else and awaited on an mbarrier: no fill loop, no
+//     shared-memory store wavefronts for 40 % of the text;
+//   * every warp loads the tile's 32 descriptors and scans the record lengths itself, then owns pairs [8w, 8w + 8):
+//     sequences, headers and the copy-out of that sub-range (its own bulk store + edge bytes).  After the barrier that
+//     publishes the mbarrier there is no CTA-wide synchronisation: a warp waiting on memory stalls nobody else.
+//   * header bytes: four lanes per pair — text pieces as 32-bit words of the molecule's header text (funnel-shifted for
+//     the format tail), the two decimal numbers split in a low and a high half.
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t sdst, const void *gsrc, uint32_t nbytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sdst), "l"(gsrc), "r"(nbytes),
+                 "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MMK_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MMK_DONE_%=;\n"
+        "bra MMK_WAIT_%=;\n"
+        "MMK_DONE_%=:\n"
+        "}\n" ::"r"(mbar),
+        "r"(parity)
+        : "memory");
+}
+
+// header bytes of the warp's 8 pairs, 4 lanes per pair
+__device__ __forceinline__ void emit_headers_warp(const EmitArgs &a, const uint4 *s_fa, const uint2 *s_fb, uint32_t smem, uint32_t t, uint32_t sub) {
+    const FastDesc f = load_fast_desc(s_fa, s_fb, t);
+    const uint32_t P = FD_P(f.pk), SUF = FD_SUF(f.pk), d1 = FD_D1(f.pk), d2 = FD_D2(f.pk);
+    const uint8_t *tx = a.text + (uint64_t)f.mol * a.text_stride;
+    const uint32_t *tw = reinterpret_cast<const uint32_t *>(tx);
+    const uint32_t s1 = smem + f.sb1, s2 = smem + f.sb2;
+    // "@chrom:hap|start:end|": word w of the text, lanes take words sub, sub + 4, ...
+    for (uint32_t w = sub; 4u * w < P; w += 4u) {
+        uint32_t x = __ldg(tw + w);
+#pragma unroll
+        for (uint32_t b = 0; b < 4; ++b) {
+            if (4u * w + b < P) {
+                sts8(s1 + 4u * w + b, x);
+                sts8(s2 + 4u * w + b, x);
+            }
+            x >>= 8;
+        }
+    }
+    {   // format tail (starts at text byte P: two words funnel-shifted); the read digit of R2 is patched below
+        const uint32_t o = P + d1 + 1u + d2, w0 = P >> 2, sh = (P & 3u) * 8u;
+        for (uint32_t w = sub; 4u * w < SUF; w += 4u) {
+            uint32_t x = __funnelshift_r(__ldg(tw + w0 + w), __ldg(tw + w0 + w + 1u), sh);
+#pragma unroll
+            for (uint32_t b = 0; b < 4; ++b) {
+                const uint32_t i = 4u * w + b;
+                if (i < SUF) {
+                    sts8(s1 + o + i, x);
+                    sts8(s2 + o + i, x);
+                }
+                x >>= 8;
+            }
+        }
+        for (uint32_t i = sub; i < (uint32_t)a.bclen_inline; i += 4u) sts8(s1 + o + SUF + i, __ldg(tx + P + 1u + i));  // 10x: barcode before the R1 read
+    }
+    {   // decimal insert breakpoints: lanes 0/1 the low / high five digits of bstart, lanes 2/3 those of bend
+        const uint32_t v = (sub & 2u) ? f.bend : f.bstart, D = (sub & 2u) ? d2 : d1, o = (sub & 2u) ? P + d1 + 1u : P;
+        const uint32_t hi = v / 100000u, lo = v - hi * 100000u;
+        uint32_t x = (sub & 1u) ? hi : lo;
+        uint32_t n = (sub & 1u) ? (D > 5u ? D - 5u : 0u) : (D < 5u ? D : 5u);
+        uint32_t pos = (sub & 1u) ? o + n : o + D;  // one past the last digit this lane writes
+        while (n--) {
+            const uint32_t q = __umulhi(x, 0xCCCCCCCDu) >> 3;
+            const uint32_t ch = '0' + (x - 10u * q);
+            --pos;
+            sts8(s1 + pos, ch);
+            sts8(s2 + pos, ch);
+            x = q;
+        }
+        if (sub == 1u) {
+            sts8(s1 + P + d1, ':');
+            sts8(s2 + P + d1, ':');
+        }
+    }
+    __syncwarp(__activemask());
+    if (sub == 0u) {  // R2's read digit, after the lane that wrote the tail's '1'
+        const uint32_t rd_off = (a.fq_format == MMK_FMT_HAPLOTAGGING || a.fq_format == MMK_FMT_STANDARD) ? 1u : SUF - 13u;
+        sts8(s2 + P + d1 + 1u + d2 + rd_off, '2');
+    }
+}
+
+template <int BPB>
+__global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    __shared__ uint4 s_fa[32];
+    __shared__ uint2 s_fb[32];
+    __shared__ uint2 s_rd[64];
+    __shared__ uint32_t s_off1[33], s_off2[33];
+    __shared__ uint32_t s_done;
+    __shared__ __align__(8) unsigned long long s_mbar;
+    const uint32_t sm = (uint32_t)__cvta_generic_to_shared(smem), mb = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+    if (threadIdx.x == 0) {  // the quality character over both stages, by the copy engine
+        mbar_init(mb, 1u);
+        mbar_expect_tx(mb, 2u * a.stage_cap);
+        bulk_load(sm, a.qfill, 2u * a.stage_cap, mb);
+        s_done = 0;
+    }
+    const uint32_t tile = a.tile0 + blockIdx.x;
+    const uint64_t p0 = (uint64_t)tile * 32u;
+    const uint32_t np = (uint32_t)((a.n_pairs - p0) < 32u ? (a.n_pairs - p0) : 32u);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool fast = a.fast_ok && a.tile_flags[tile];
+    if (warp == 0) {  // descriptors of the whole tile: every load is independent of the others (one memory latency)
+        const uint32_t tile_m0 = a.tile_mol0[tile];
+        const uint32_t A1 = (uint32_t)((a.tile_off1[tile] - a.chunk_off1) & 15u), A2 = (uint32_t)((a.tile_off2[tile] - a.chunk_off2) & 15u);
+        const bool have = lane < np;
+        const uint4 q = have ? a.fdesc[p0 + lane] : make_uint4(1u, 1u, 0u, 0u);
+        if (lane < 4 && blockIdx.x + 1184u < a.n_tiles)  // warm L2 for a tile that a later wave of CTAs will run
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(a.fdesc + (p0 + 1184ull * 32u)) + 128u * lane));
+        if (fast) {
+            // stage1 = smem[0, stage_cap), stage2 = smem[stage_cap, 2 stage_cap): record offsets index smem directly
+            FastDesc f;
+            make_fast_desc<true>(a, q, tile_m0, A1, a.stage_cap + A2, f);
+            {   // record offsets in the tile: exclusive scan of (len1 | len2 << 16); both totals are < 2^16 (tile flag)
+                const uint32_t hdr = FD_HDR(f.pk);
+                const uint32_t lens = have ? ((hdr + 2u * (uint32_t)a.bclen_inline + 2u * (uint32_t)a.r1 + 4u) | ((hdr + 2u * (uint32_t)a.r2 + 4u) << 16)) : 0u;
+                uint32_t inc = lens;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= (uint32_t)o) inc += y;
+                }
+                f.sb1 += (inc - lens) & 0xffffu;
+                f.sb2 += (inc - lens) >> 16;
+            }
+            if (have) {
+                s_fa[lane] = make_uint4(f.sb1, f.sb2, f.bstart, f.bend);
+                s_fb[lane] = make_uint2(f.mol, f.pk);
+                constexpr uint32_t WM = BPB == 2 ? 15u : 7u;
+                const uint32_t ws1 = f.bstart - 1u, ws2 = f.bend - (uint32_t)a.r2;
+                const uint32_t rel1 = ws1 >= 15u ? ((ws1 - 15u) & WM) + 15u : ws1, rel2 = ws2 >= 15u ? ((ws2 - 15u) & WM) + 15u : ws2;
+                s_rd[2 * lane] = make_uint2((f.sb1 + FD_HDR(f.pk) + (uint32_t)a.bclen_inline) | (rel1 << 20), f.wbase1);
+                s_rd[2 * lane + 1] = make_uint2((f.sb2 + FD_HDR(f.pk)) | (rel2 << 20), f.wbase2);
+                // start the loads the next phases will need
+                prefetch_l1(a.hap + f.wbase1);
+                prefetch_l1(a.hap + f.wbase1 + (BPB == 2 ? 15 : 31));
+                prefetch_l1(a.hap + f.wbase2);
+                prefetch_l1(a.hap + f.wbase2 + (BPB == 2 ? 15 : 31));
+                prefetch_l1(a.text + (uint64_t)f.mol * a.text_stride);
+            }
+        }
+    }
+    __syncthreads();  // descriptors and the mbarrier are published; nothing below synchronises the CTA on the fast path
+    if (!fast) {
+        // general path: every record byte-wise, straight to global memory (warp per pair)
+        const uint32_t tile_m0 = a.tile_mol0[tile];
+        PairDesc d;
+        d.len1 = d.len2 = 0;
+        if (threadIdx.x < np) decode_pair(a, p0 + threadIdx.x, tile_m0, d);
+        if (threadIdx.x < 32) {
+            uint32_t i1 = d.len1, i2 = d.len2;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t y1 = __shfl_up_sync(0xffffffffu, i1, o), y2 = __shfl_up_sync(0xffffffffu, i2, o);
+                if (lane >= o) {
+                    i1 += y1;
+                    i2 += y2;
+                }
+            }
+            s_off1[threadIdx.x + 1] = i1 - d.len1;  // exclusive offsets of the pair's two records inside the tile
+            s_off2[threadIdx.x + 1] = i2 - d.len2;
+        }
+        __syncthreads();
+        uint8_t *o1 = a.out1 + (a.tile_off1[tile] - a.chunk_off1), *o2 = a.out2 + (a.tile_off2[tile] - a.chunk_off2);
+        for (uint32_t t = warp; t < np; t += 4) {
+            PairDesc e;
+            decode_pair(a, p0 + t, tile_m0, e);
+            write_record_generic<BPB>(a, e, 1, o1 + s_off1[t + 1], lane);
+            write_record_generic<BPB>(a, e, 2, o2 + s_off2[t + 1], lane);
+        }
+        mbar_wait(mb, 0u);  // the stage must outlive the copy into it
+        return;
+    }
+    // this warp's pairs [w0, w1)
+    const uint32_t w0 = 8u * warp, w1 = (w0 + 8u < np) ? w0 + 8u : np;
+    if (w0 < w1) {
+        {   // sequences: the reference words of the next pair are loaded while this one is expanded
+            const uint32_t half = lane >> 4, hl = lane & 15u;
+            const uint32_t *hap_lane = a.hap + hl;
+            uint2 rd = s_rd[2 * w0 + half];
+            uint32_t W0 = __ldg(hap_lane + rd.y), W1 = BPB == 4 ? __ldg(hap_lane + rd.y + 16) : 0u;
+            mbar_wait(mb, 0u);  // the quality fill has landed
+            for (uint32_t t = w0; t < w1; ++t) {
+                const uint32_t tn = t + 1u < w1 ? t + 1u : t;
+                const uint2 rn = s_rd[2 * tn + half];
+                const uint32_t W0n = __ldg(hap_lane + rn.y), W1n = BPB == 4 ? __ldg(hap_lane + rn.y + 16) : 0u;
+                if (BPB == 2) emit_pair_seq(a, rd, W0, sm, lane);
+                else emit_pair_seq4(a, rd, W0, W1, sm, lane);
+                rd = rn;
+                W0 = W0n;
+                W1 = W1n;
+            }
+        }
+        __syncwarp();
+        if (w0 + (lane >> 2) < w1) emit_headers_warp(a, s_fa, s_fb, sm, w0 + (lane >> 2), lane & 3u);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes → visible to the bulk copy
+    } else
+        mbar_wait(mb, 0u);
+    __syncwarp();
+    // the last warp to get here copies the tile out (the others are done: no barrier, nobody waits)
+    uint32_t ticket = 0;
+    if (lane == 0) {
+        __threadfence_block();
+        ticket = atomicAdd(&s_done, 1u);
+        __threadfence_block();
+    }
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket != 3u) return;
+    const uint64_t g1 = a.tile_off1[tile] - a.chunk_off1, g2 = a.tile_off2[tile] - a.chunk_off2;
+    const uint32_t bytes1 = (uint32_t)(a.tile_off1[tile + 1] - a.tile_off1[tile]), bytes2 = (uint32_t)(a.tile_off2[tile + 1] - a.tile_off2[tile]);
+    const uint32_t A1 = (uint32_t)(g1 & 15u), A2 = (uint32_t)(g2 & 15u);
+    uint8_t *gb1 = a.out1 + (g1 - A1), *gb2 = a.out2 + (g2 - A2);
+    if (lane == 0) {
+        copy_out_bulk(sm, A1, bytes1, gb1);
+        copy_out_bulk(sm + a.stage_cap, A2, bytes2, gb2);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    copy_out_edges(sm, A1, bytes1, gb1, lane);
+    copy_out_edges(sm + a.stage_cap, A2, bytes2, gb2, lane);
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // stage must outlive the copy
+}
+
 }  // namespace mmkdev

@@ -137,6 +137,7 @@ struct mmk_ctx {
     DBuf<uint32_t> d_tile_mol0;
     DBuf<uint4> d_fdesc;
     DBuf<uint8_t> d_tile_flags;
+    DBuf<uint8_t> d_qfill;        // 2 * stage_cap bytes of 'I': source of the emit kernel's stage fill (bulk copy)
     DBuf<uint8_t> d_tmp, d_tmp2;  // placement scratch: (gap bits, insert length) per pair of one segment (two alternate)
     // haplotype construction scratch, kept between samples (a 100 Mbp master: cudaMalloc + cudaFree of these cost more than the kernels)
     DBuf<char> v_alt, v_tmp, v_snp_alt;
@@ -144,7 +145,8 @@ struct mmk_ctx {
     DBuf<uint8_t> v_kind;
     DBuf<InsTable> d_instab;  // insert-length threshold table (built by mmk_create)
     InsTable *h_instab = nullptr;
-    DBuf<unsigned long long> d_msum;  // placement: per molecule, length sum | accepted redraw round << 32 (k_place_sum -> k_place_chain)
+    DBuf<uint32_t> d_weight, d_blk, d_big_list, d_big_count;  // block placement: molecule weights, block table, big molecules
+    DBuf<uint64_t> d_woff;                                    // ... weight prefix
     DBuf<uint32_t> d_acc_i;   // placement scratch: sum of insert lengths per molecule
     uint32_t text_stride = 0, tile_pairs = 64, n_tiles = 0, stage_cap = 0;
     int32_t fast_ok = 0;
@@ -1300,7 +1302,7 @@ extern "C" int32_t mmk_set_shard(mmk_ctx *ctx, int32_t rank, int32_t world) {
 // ------------------------------------------------------------------------------------------
 // placement + tile offsets for this shard
 // ------------------------------------------------------------------------------------------
-static const bool PLACE_FUSED_DEFAULT = false;  // MMK_PLACE_MODE=fused|legacy overrides (tests run both)
+static const bool PLACE_BLOCK_DEFAULT = true;  // MMK_PLACE_MODE=block|legacy overrides (tests run both)
 
 static EmitArgs base_args(mmk_ctx *c) {
     EmitArgs a;
@@ -1316,6 +1318,7 @@ static EmitArgs base_args(mmk_ctx *c) {
     a.tile_flags = c->d_tile_flags.p;
     a.stage_cap = c->stage_cap;
     a.fast_ok = c->fast_ok;
+    a.qfill = c->d_qfill.p;
     a.tile_off1 = c->d_tile_off1.p;
     a.tile_off2 = c->d_tile_off2.p;
     a.n_pairs = c->s_npairs;
@@ -1385,6 +1388,8 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
         ctx->bz_ready = false;
         ctx->stage_cap = (uint32_t)(((uint64_t)tp * max_rec + 32 + 15) & ~15ull);
         if (!ctx->fast_ok) ctx->stage_cap = 16;
+        CU(ctx->d_qfill.ensure(2 * (size_t)ctx->stage_cap));
+        CU(cudaMemsetAsync(ctx->d_qfill.p, 'I', 2 * (size_t)ctx->stage_cap, ctx->st));
     }
 
     CU(ctx->d_ins.ensure(ctx->s_npairs + 1));
@@ -1397,10 +1402,11 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     CU(cudaMemcpyAsync(d_err.p, init, sizeof init, cudaMemcpyHostToDevice, ctx->st));
     ctx->n_tiles = (uint32_t)((ctx->s_npairs + ctx->tile_pairs - 1) / ctx->tile_pairs);
     CU(ctx->d_tile_mol0.ensure((size_t)ctx->n_tiles + 1));
-    // Fused placement (mmk_place.cuh) needs 32-pair tiles; MMK_PLACE_LEGACY=1 keeps the three-kernel path (draws → chain →
-    // tile preparation through global scratch), which also serves other tile sizes.
-    bool fused = ctx->tile_pairs == 32 && PLACE_FUSED_DEFAULT;
-    if (const char *e = getenv("MMK_PLACE_MODE")) fused = ctx->tile_pairs == 32 && strcmp(e, "fused") == 0;
+    // Block placement (mmk_place.cuh) needs 32-pair tiles and insert lengths that fit 16 bits; MMK_PLACE_MODE=legacy keeps the
+    // three-kernel path (draws → chain → tile preparation through global scratch), which also serves the other cases.
+    const bool block_ok = ctx->tile_pairs == 32 && place_block_supports(ctx->sc);
+    bool fused = block_ok && PLACE_BLOCK_DEFAULT;
+    if (const char *e = getenv("MMK_PLACE_MODE")) fused = block_ok && strcmp(e, "legacy") != 0;
     if (fused) place_local_roff(ctx->mol0, (uint32_t)ctx->s_nmol, ctx->d_read_off.p, ctx->d_roff_l.p, ctx->st);
     else place_prepare(ctx->mol0, (uint32_t)ctx->s_nmol, ctx->d_read_off.p, ctx->d_roff_l.p, ctx->d_tile_mol0.p, ctx->tile_pairs, ctx->st);
     // per-tile outputs of the placement, launched per segment below
@@ -1417,10 +1423,17 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     CU(ctx->d_tile_flags.ensure((size_t)ctx->n_tiles + 1));
     const EmitArgs targs = base_args(ctx);
     auto run_fused = [&]() -> int32_t {
-        CU(ctx->d_msum.ensure(ctx->s_nmol + 1));
-        place_fused(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->mol0, (uint32_t)ctx->s_nmol, ctx->s_npairs, ctx->n_tiles, ctx->d_roff_l.p,
+        const uint32_t nm = (uint32_t)ctx->s_nmol;
+        CU(ctx->d_weight.ensure((size_t)nm + 1));
+        CU(ctx->d_woff.ensure((size_t)nm + 2));
+        CU(ctx->d_scan_tmp.ensure((size_t)std::max<uint64_t>(nm, ctx->n_tiles) / 1024 + 8));
+        CU(ctx->d_blk.ensure((size_t)place_block_count(ctx->s_npairs, nm) + 2));
+        CU(ctx->d_big_list.ensure((size_t)place_big_cap(ctx->s_npairs) + 1));
+        CU(ctx->d_big_count.ensure(1));
+        place_block(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->mol0, nm, ctx->s_npairs, ctx->n_tiles, ctx->d_roff_l.p,
                     ctx->d_tile_mol0.p, ctx->d_instab.p, ctx->d_ins.p, ctx->d_mol.p, ctx->d_text.p, ctx->text_stride, ctx->d_fdesc.p,
-                    d_sum1.p, d_sum2.p, ctx->d_tile_flags.p, d_gather.p, d_err.p, ctx->d_msum.p, ctx->stage_cap, ctx->bpb, ctx->st);
+                    d_sum1.p, d_sum2.p, ctx->d_tile_flags.p, d_gather.p, d_err.p, ctx->d_weight.p, ctx->d_woff.p, ctx->d_scan_tmp.p,
+                    ctx->d_blk.p, ctx->d_big_list.p, ctx->d_big_count.p, ctx->stage_cap, ctx->bpb, ctx->st);
         return MMK_OK;
     };
     auto run_legacy = [&]() -> int32_t

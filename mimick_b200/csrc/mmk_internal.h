@@ -125,6 +125,7 @@ struct EmitArgs {
     int32_t force_generic;
     uint32_t stage_cap;        // bytes of shared-memory stage per stream (fast path)
     int32_t fast_ok;           // host-level eligibility of the fast path (read lengths, format)
+    const uint8_t *qfill;      // >= 2 * stage_cap bytes of the quality character (source of the stage fill by bulk copy); null: k_emit
 };
 
 #ifdef __cplusplus
@@ -178,12 +179,15 @@ void place_segment_chain(const SimConst &sc, const SchemaDev *d_sch, PlanDev pla
                          uint64_t pair_lo, const uint64_t *d_read_off_local, void *d_tmp, uint32_t *d_acc_i, uint2 *d_ins, MolRec *d_mol, uint8_t *d_text, uint32_t text_stride,
                          unsigned long long *d_err, cudaStream_t st);
 
-// fused placement (mmk_place.cuh): needs 32-pair tiles
-void place_fused(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint64_t n_pairs,
+// block placement (mmk_place.cuh): needs 32-pair tiles and insert lengths below 2^16
+uint32_t place_block_count(uint64_t n_pairs, uint32_t n_mol);  // entries of d_blk - 1
+uint32_t place_big_cap(uint64_t n_pairs);                      // entries of d_big_list
+bool place_block_supports(const SimConst &sc);
+void place_block(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint64_t n_pairs,
                  uint32_t n_tiles, const uint64_t *d_roff_l, uint32_t *d_tile_mol0, const InsTable *d_tab, uint2 *d_ins, MolRec *d_mol,
                  uint8_t *d_text, uint32_t text_stride, uint4 *d_fdesc, uint32_t *d_sum1, uint32_t *d_sum2, uint8_t *d_tile_flags,
-                 unsigned long long *d_gather, unsigned long long *d_err, unsigned long long *d_msum, uint32_t stage_cap, int bpb,
-                 cudaStream_t st);
+                 unsigned long long *d_gather, unsigned long long *d_err, uint32_t *d_weight, uint64_t *d_woff, uint64_t *d_scan_tmp,
+                 uint32_t *d_blk, uint32_t *d_big_list, uint32_t *d_big_count, uint32_t stage_cap, int bpb, cudaStream_t st);
 void place_local_roff(uint64_t mol0, uint32_t n_mol, const uint64_t *d_read_off_global, uint64_t *d_read_off_local, cudaStream_t st);
 // KAT: lengths the kernels derive from raw 64-bit draws (table path with its exact fallback); slow[i] = 1 where the fallback ran
 void kat_insert_len(const SimConst &sc, const InsTable *d_tab, const uint64_t *d_bits, uint32_t *d_len, uint8_t *d_slow, int64_t n, cudaStream_t st);

@@ -1,18 +1,18 @@
-// mmk_place.cuh — read-pair placement in one pass over the shard.
+// mmk_place.cuh — read-pair placement of a shard, block by block, in shared memory.
 //
 // Reference behaviour: calculate_insert_sizes (Breakpoints.jl:205-218), get_sequences (:227-251),
 // seq_breakpoints! (:21-35), and the record lengths of format_R1 / format_R2 (FormatFASTQ.jl).
 //
-// k_place_block — one CTA places a block of TB tiles (32 read pairs each):
-//   A. one thread per read pair of every molecule that touches the block: ONE Philox block gives the insert
-//      length (through a threshold table: no floating point) and the 64 bits of the gap draw; both stay in
-//      shared memory; the integer length sum of every molecule is accumulated with shared-memory atomics;
-//   B. one thread per molecule: redraw rule on the sum, start draw, the serial gap chain over shared memory;
-//   C. one warp per tile: record lengths, intra-tile scan, the 16-byte pair descriptors the emit kernel reads,
-//      tile totals and the fast/general flag.
-// Molecules that straddle a block boundary are placed by both blocks (identical results; the block holding the
-// molecule's first pair writes its record).  Molecules with more than BIG pairs would not fit the shared-memory
-// window: k_place_big places them first, one CTA each, and the blocks read their inserts back from global memory.
+// A block is a run of consecutive molecules of bounded weight (pairs + PB_W per molecule: at most PB_CAP pairs and
+// PB_MAXM molecules, found by k_place_blocks with a search over the weight prefix).  One CTA per block (k_place_block):
+//   A. one thread per read pair: ONE Philox block gives the insert length (through a threshold table: no floating
+//      point) and the 64 bits of the gap draw; both stay in shared memory;
+//   B. one thread per molecule: integer length sum, redraw rule (Breakpoints.jl:209-212), start draw (:240), the
+//      serial gap chain over shared memory (:27-33), header-piece lengths, the molecule record;
+//   C. one warp per 32-pair tile (aligned to the tiles of the emit kernel): breakpoints, record lengths, the 16-byte
+//      pair descriptors the emit kernel reads, record bytes per tile and stream, the tile's irregular flag.
+// Nothing per pair goes through global scratch.  Molecules with more than PB_BIG pairs do not fit a block's window:
+// k_place_big places them first, one CTA each, and phase C reads their inserts back from global memory.
 //
 // The insert-length table.  trunc(mu + sd * Phi^-1(p(u))) is a non-decreasing step function of the 52-bit uniform
 // u up to rounding noise, so "which integer" is a search among ~16 sd thresholds.  The table keeps the top 32 bits of
@@ -66,6 +66,17 @@ __device__ __forceinline__ uint32_t pair_len(const SimConst &sc, const InsTable 
     NoRec rec;
     return insert_len_of(draw_insert_from(sc, is, rec));
 }
+// the table path alone: false when the draw needs the exact (double-precision) definition — 1e-5 of the draws
+__device__ __forceinline__ bool pair_draw_fast(const SimConst &sc, const InsTable &tab, uint64_t g, uint32_t m, uint32_t i, uint32_t &len,
+                                               uint32_t &bits_lo, uint32_t &bits_hi) {
+    mmk_stream is;
+    mmk_insert_stream_init(&is, sc.seed, sc.sample, g, m, i);
+    uint32_t o[4];
+    mmk_stream_block(&is, 0, o);
+    bits_lo = o[2];
+    bits_hi = o[3];
+    return tab.enabled && ins_len_fast(tab, o[1], len);
+}
 
 // Does the float sum of the molecule's insert lengths exceed the molecule (Breakpoints.jl:209)?  The sum lies in
 // [isum, isum + n): decided from the integers unless they straddle the molecule size (then: the left-to-right sum).
@@ -114,6 +125,19 @@ __device__ __forceinline__ void first_read_quals(const SimConst &sc, int64_t sta
     if (sc.fq_format == MMK_FMT_TENX) q1 += 16u;
 }
 
+constexpr uint32_t PB_THREADS = 256;
+constexpr uint32_t PB_W = 8;          // weight of a molecule besides its pairs (bounds the molecules of a block)
+constexpr uint32_t PB_BIG = 1024;     // molecules with more pairs go through k_place_big
+constexpr uint32_t PB_EXACT = 0xffffu; // phase A: length to be drawn by the exact definition (lengths are < 65000: place_block_supports)
+#ifndef MMK_PB_TARGET
+#define MMK_PB_TARGET 2496
+#endif
+constexpr uint32_t PB_TARGET = MMK_PB_TARGET;                 // weight of a block
+constexpr uint32_t PB_CAP = PB_TARGET + PB_BIG;               // pairs in shared memory: < TARGET + W + BIG - W * molecules
+constexpr uint32_t PB_MAXM = (PB_TARGET + PB_BIG) / PB_W + 2; // molecules of a block: each weighs >= W
+constexpr uint32_t PB_SORT_MAX = 160;  // blocks with more molecules run phase B in molecule order
+constexpr size_t PB_SMEM = sizeof(InsTable) + (size_t)PB_CAP * 12u + (size_t)(PB_MAXM + 1u) * 16u + (size_t)PB_SORT_MAX * 2u + 16u;
+
 struct PlaceArgs {
     SimConst sc;
     const SchemaDev *sch;
@@ -123,8 +147,14 @@ struct PlaceArgs {
     uint32_t n_tiles;
     uint64_t n_pairs;           // pairs in the shard
     const uint64_t *roff;       // [n_mol + 1] shard-relative first pair of every molecule
+    const uint64_t *woff;       // [n_mol + 1] weight prefix: PB_W per molecule + its pairs unless it is big
+    const uint32_t *blk;        // [n_blocks + 1] first molecule of every block
+    uint32_t n_blocks;
     const uint32_t *tile_mol0;  // [n_tiles] molecule holding the first pair of every tile
     const InsTable *tab;
+    const uint32_t *big_list;   // shard molecules with more than PB_BIG pairs
+    const uint32_t *big_count;
+    uint32_t big_cap;
     uint2 *ins;
     MolRec *mol;
     uint4 *fdesc;
@@ -132,10 +162,16 @@ struct PlaceArgs {
     uint8_t *tile_flags;         // [n_tiles] zero on entry; 1 = the tile holds a pair the fast emit path cannot take
     unsigned long long *gather;  // [256]
     unsigned long long *err;     // [0]: first molecule (plan index) with a non-zero status
-    unsigned long long *msum;    // [n_mol] k_mol_sum -> k_mol_chain: length sum | accepted round << 32 | PLM_OVER
     int32_t bpb;
-    uint32_t n_warps;            // warps of the launch; warp w places an equal share of the pairs
 };
+
+// packed per-molecule word of phases B -> C
+#define MPK(schema, P, SUF, qreg, big) ((schema) | ((P) << 16) | ((SUF) << 24) | ((qreg) << 30) | ((big) << 31))
+#define MPK_SCHEMA(w) ((w) & 0xffffu)
+#define MPK_P(w) (((w) >> 16) & 0xffu)
+#define MPK_SUF(w) (((w) >> 24) & 0x3fu)
+#define MPK_QREG(w) (((w) >> 30) & 1u)
+#define MPK_BIG(w) ((w) >> 31)
 
 __device__ __forceinline__ void stage_table(InsTable *dst, const InsTable *src) {
     const uint4 *s = reinterpret_cast<const uint4 *>(src);
@@ -148,248 +184,198 @@ __device__ __forceinline__ uint32_t need_end_of(const SimConst &sc, int64_t star
     return (!sc.strict && start <= (int64_t)sc.r2) ? (uint32_t)((int64_t)sc.r2 + 1 - start) : 0u;
 }
 
-// Placement of a shard, one LANE per molecule, in two kernels.
-// A warp owns a contiguous run of molecules holding 1/n_warps of the shard's pairs; its lanes pull molecules from that
-// run one after the other, so all 32 lanes stay busy whatever the molecules' insert counts (they are exponentially
-// distributed: a lane per molecule without refill leaves ~6 of 32 lanes active).
-//   k_mol_sum    insert k of the lane's molecule: one Philox block -> length (threshold table); integer sum of the
-//                  lengths; at the end the redraw rule of Breakpoints.jl:209-212 (whole-vector redraws under the next
-//                  round key while the sum exceeds the molecule).  Leaves (sum, accepted round, fits?) per molecule.
-//   k_mol_chain  start draw (Breakpoints.jl:240), header-piece lengths, then insert k: length and the 64 bits of the
-//                  gap draw (the Philox block again); gap = mulhi64(bits, leeway + 1) (Breakpoints.jl:27-33);
-//                  the pair's breakpoints, record lengths and the 16-byte descriptor for the emit kernel; record bytes
-//                  accumulated per tile and flushed with one atomic per (molecule, tile) run.
-// No shared memory beyond the 5 KB table, no scratch besides 8 bytes per molecule.
-constexpr uint32_t PLM_THREADS = 128;
-constexpr unsigned long long PLM_OVER = 1ull << 63;  // msum: the length vector never fitted (Breakpoints.jl:214-216)
-
-// molecules [first with roff >= share * gw, first with roff >= share * (gw + 1)): lanes 0 and 1 search the two bounds
-__device__ __forceinline__ void warp_molecule_run(const PlaceArgs &a, uint32_t gw, uint32_t lane, uint32_t &m_begin, uint32_t &m_end) {
-    uint32_t bnd = 0;
-    if (lane < 2) {
-        const uint32_t w = gw + lane;
-        if (w >= a.n_warps) bnd = a.n_mol;
-        else {
-            const uint64_t target = (uint64_t)(((unsigned __int128)a.n_pairs * w) / a.n_warps);
-            uint32_t lo = 0, hi = a.n_mol;
-            while (lo < hi) {
-                const uint32_t mid = lo + ((hi - lo) >> 1);
-                if (a.roff[mid] >= target) hi = mid; else lo = mid + 1;
-            }
-            bnd = lo;
-        }
+// per molecule: weight for the block partition, the tiles whose first pair it holds, the list of big molecules
+__global__ void k_mol_weights(const uint64_t *__restrict__ roff_l, uint32_t n_mol, uint32_t *tile_mol0, uint32_t *weight, uint32_t *big_list,
+                              uint32_t *big_count, uint32_t big_cap) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_mol) return;
+    const uint64_t lo = roff_l[m], hi = roff_l[m + 1];  // pairs [lo, hi)
+    const uint32_t n = (uint32_t)(hi - lo);
+    weight[m] = PB_W + (n > PB_BIG ? 0u : n);
+    for (uint64_t t = (lo + 31u) >> 5; (t << 5) < hi; ++t) tile_mol0[t] = m;
+    if (n > PB_BIG) {
+        const uint32_t k = atomicAdd(big_count, 1u);
+        if (k < big_cap) big_list[k] = m;
     }
-    m_begin = __shfl_sync(0xffffffffu, bnd, 0);
-    m_end = __shfl_sync(0xffffffffu, bnd, 1);
+}
+// blk[b] = first molecule whose weight prefix is >= b * PB_TARGET (blocks past the total weight are empty)
+__global__ void k_place_blocks(const uint64_t *__restrict__ woff, uint32_t n_mol, uint32_t n_blocks, uint32_t *blk) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > n_blocks) return;
+    const uint64_t target = (uint64_t)b * PB_TARGET;
+    uint32_t lo = 0, hi = n_mol;
+    while (lo < hi) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (woff[mid] >= target) hi = mid; else lo = mid + 1;
+    }
+    blk[b] = b == n_blocks ? n_mol : lo;
 }
 
-__global__ void __launch_bounds__(PLM_THREADS, 8) k_mol_sum(const __grid_constant__ PlaceArgs a) {
-    __shared__ InsTable tab;
-    stage_table(&tab, a.tab);
-    __syncthreads();
+// whole-vector redraws of one molecule's lengths in shared memory while the sum exceeds the molecule
+// (Breakpoints.jl:209-212); true if it still does after `attempts` rounds.  Rare: kept out of line.
+__device__ __noinline__ bool redraw_in_smem(const SimConst &sc, const InsTable &tab, uint64_t g, uint32_t m, uint32_t nfrags, uint32_t molsize,
+                                            uint16_t *s_len, uint64_t &isum) {
+    bool over = true;
+    for (int attempts = 1; over && attempts <= sc.attempts; ++attempts) {
+        const uint64_t key = mmk_round_key(sc.seed, (uint32_t)attempts);
+        isum = 0;
+        for (uint32_t k = 0; k < nfrags; ++k) {
+            const uint32_t li = pair_len(sc, tab, key, g, m, k);
+            s_len[k] = (uint16_t)li;
+            isum += li;
+        }
+        over = sum_over(sc, key, g, m, nfrags, molsize, isum);
+    }
+    return over;
+}
+
+__global__ void __launch_bounds__(PB_THREADS, 4) k_place_block(const __grid_constant__ PlaceArgs a) {
+    extern __shared__ __align__(16) uint8_t pb_smem[];
+    InsTable *tab = reinterpret_cast<InsTable *>(pb_smem);
+    uint2 *s_bits = reinterpret_cast<uint2 *>(pb_smem + sizeof(InsTable));  // gap bits; after phase B: .x = insert offset in the molecule
+    uint32_t *s_ro = reinterpret_cast<uint32_t *>(s_bits + PB_CAP);          // [nm + 1] first pair of every molecule, block-relative
+    uint32_t *s_so = s_ro + PB_MAXM + 1;                                     // [nm + 1] first shared-memory slot (big molecules have none)
+    uint32_t *s_start = s_so + PB_MAXM + 1;                                  // molecule start
+    uint32_t *s_meta = s_start + PB_MAXM + 1;                                // MPK word
+    uint16_t *s_len = reinterpret_cast<uint16_t *>(s_meta + PB_MAXM + 1);    // [PB_CAP]
+    uint16_t *s_mj = s_len + PB_CAP;                                         // [PB_CAP] block-local molecule of every slot
+    uint16_t *s_perm = s_mj + PB_CAP;                                        // [PB_SORT_MAX] molecules by decreasing insert count
     const SimConst &sc = a.sc;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t gw = blockIdx.x * (PLM_THREADS / 32u) + (threadIdx.x >> 5);
-    if (gw >= a.n_warps) return;
-    uint32_t m_next, m_end;
-    warp_molecule_run(a, gw, lane, m_next, m_end);
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    bool idle = true, done = false;
-    uint32_t ml = 0, ms = 0, n = 0, k = 0, molsize = 0, round = 0;
-    uint64_t g = 0, ro = 0, key = sc.seed, isum = 0;
-    for (;;) {
-        const unsigned need = __ballot_sync(0xffffffffu, idle && !done);
-        if (need) {
-            if (idle && !done) {
-                const uint32_t idx = m_next + __popc(need & lt_mask);
-                if (idx < m_end) {
-                    ml = idx;
-                    const uint64_t gi = a.mol0 + ml;
-                    g = a.plan.group[gi];
-                    ms = a.plan.slot[gi];
-                    molsize = a.plan.size[gi];
-                    ro = a.roff[ml];
-                    n = (uint32_t)(a.roff[ml + 1u] - ro);
-                    k = 0;
-                    isum = 0;
-                    round = 0;
-                    key = sc.seed;
-                    idle = false;
-                } else
-                    done = true;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t m_lo = a.blk[blockIdx.x], m_hi = a.blk[blockIdx.x + 1u];
+    if (m_hi <= m_lo) return;
+    const uint32_t nm = m_hi - m_lo;  // <= PB_MAXM
+    stage_table(tab, a.tab);
+    const uint64_t R0 = a.roff[m_lo];
+    const uint64_t W0 = a.woff[m_lo];
+    for (uint32_t j = tid; j <= nm; j += PB_THREADS) {
+        s_ro[j] = (uint32_t)(a.roff[m_lo + j] - R0);
+        s_so[j] = (uint32_t)(a.woff[m_lo + j] - W0) - PB_W * j;
+        s_start[j] = 0;  // phase A: integer sum of the molecule's insert lengths
+    }
+    __syncthreads();
+    const uint32_t np = s_ro[nm];        // pairs of the block, big molecules included
+    const uint32_t ns = s_so[nm];        // ... in shared memory (big molecules have no slots)
+    const bool any_big = ns != np;       // otherwise slot == block-relative pair
+    // ---- phase A: the draws; a thread takes `spt` consecutive slots (odd: conflict-free shared-memory stores) ---------
+    {
+        const uint32_t spt = ((ns + PB_THREADS - 1u) / PB_THREADS) | 1u;
+        const uint32_t s_begin = tid * spt, s_end = min(s_begin + spt, ns);
+        if (s_begin < ns) {
+            uint32_t lo = 0, hi = nm - 1u;
+            while (lo < hi) {  // largest j with s_so[j] <= s_begin (molecules without slots share their successor's: skipped)
+                const uint32_t mid = (lo + hi + 1u) >> 1;
+                if (s_so[mid] <= s_begin) lo = mid; else hi = mid - 1u;
             }
-            m_next += __popc(need);
+            uint32_t j = lo, next = s_so[j + 1u], first = s_so[j], acc = 0;
+            uint64_t g = a.plan.group[a.mol0 + m_lo + j];
+            uint32_t ms = a.plan.slot[a.mol0 + m_lo + j];
+            for (uint32_t slot = s_begin; slot < s_end; ++slot) {
+                if (slot >= next) {  // the next molecule that has slots
+                    if (acc) atomicAdd(&s_start[j], acc);
+                    acc = 0;
+                    do {
+                        ++j;
+                        first = next;
+                        next = s_so[j + 1u];
+                    } while (slot >= next);
+                    g = a.plan.group[a.mol0 + m_lo + j];
+                    ms = a.plan.slot[a.mol0 + m_lo + j];
+                }
+                uint32_t blo, bhi, li;
+                if (pair_draw_fast(sc, *tab, g, ms, slot - first, li, blo, bhi)) acc += li;
+                else li = PB_EXACT;
+                s_bits[slot] = make_uint2(blo, bhi);
+                s_len[slot] = (uint16_t)li;
+                s_mj[slot] = (uint16_t)j;
+            }
+            if (acc) atomicAdd(&s_start[j], acc);
+            for (uint32_t slot = s_begin; slot < s_end; ++slot) {  // draws off the table: the exact definition (1e-5 of them)
+                if (s_len[slot] != PB_EXACT) continue;
+                const uint32_t jj = s_mj[slot];
+                const uint64_t gi = a.mol0 + m_lo + jj;
+                NoRec rec;
+                const uint32_t li = insert_len_of(draw_insert(sc, sc.seed, a.plan.group[gi], a.plan.slot[gi], slot - s_so[jj], rec));
+                s_len[slot] = (uint16_t)li;
+                atomicAdd(&s_start[jj], li);
+            }
         }
-        if (__all_sync(0xffffffffu, done)) break;
-        if (done) continue;
-        mmk_stream is;
-        mmk_insert_stream_init(&is, key, sc.sample, g, ms, k);
-        mmk_stream_block(&is, 0, is.buf);
-        is.blk = 0;
-        uint32_t li;
-        if (!(tab.enabled && ins_len_fast(tab, is.buf[1], li))) {
-            NoRec rec;
-            li = insert_len_of(draw_insert_from(sc, is, rec));
+    }
+    // molecules by decreasing insert count, so that the lanes of a warp chain alike (the counts are exponentially distributed)
+    const bool sorted = nm <= PB_SORT_MAX;
+    if (sorted && tid < nm) {
+        const uint32_t n_mine = s_ro[tid + 1u] - s_ro[tid];
+        uint32_t rank = 0;
+        for (uint32_t i = 0; i < nm; ++i) {
+            const uint32_t n_i = s_ro[i + 1u] - s_ro[i];
+            rank += (n_i > n_mine) || (n_i == n_mine && i < tid);
         }
-        isum += li;
-        if (++k < n) continue;
-        // the vector is drawn: does it fit (Breakpoints.jl:209-212)?
-        const bool over = sum_over(sc, key, g, ms, n, molsize, isum);
-        if (over && round < (uint32_t)sc.attempts) {  // whole-vector redraw under the next round's key
-            ++round;
-            key = mmk_round_key(sc.seed, round);
-            k = 0;
-            isum = 0;
+        s_perm[rank] = (uint16_t)tid;
+    }
+    __syncthreads();
+    // ---- phase B: one thread per molecule ----------------------------------------------------------------------------
+    const uint32_t inl = sc.fq_format == MMK_FMT_TENX ? 16u : 0u;
+    for (uint32_t jt = tid; jt < nm; jt += PB_THREADS) {
+        const uint32_t j = sorted ? s_perm[jt] : jt;
+        const uint32_t ml = m_lo + j;  // shard-relative molecule
+        const uint64_t gi = a.mol0 + ml;
+        const uint32_t nfrags = s_ro[j + 1u] - s_ro[j];
+        if (nfrags > PB_BIG) {  // already placed: fetch what phase C needs
+            const MolRec r = a.mol[ml];
+            const uint32_t qreg = r.qual1 == (uint32_t)sc.r1 + inl && r.qual2 == (uint32_t)sc.r2;
+            s_start[j] = (uint32_t)r.start;
+            s_meta[j] = MPK((uint32_t)r.schema, (uint32_t)r.prefix_len, (uint32_t)r.suffix_len, qreg, 1u);
             continue;
         }
-        a.msum[ml] = (over ? PLM_OVER : 0ull) | ((unsigned long long)round << 32) | (unsigned long long)(uint32_t)isum;
-        idle = true;
-    }
-}
-
-__global__ void __launch_bounds__(PLM_THREADS, 5) k_mol_chain(const __grid_constant__ PlaceArgs a) {
-    __shared__ InsTable tab;
-    stage_table(&tab, a.tab);
-    __syncthreads();
-    const SimConst &sc = a.sc;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t gw = blockIdx.x * (PLM_THREADS / 32u) + (threadIdx.x >> 5);
-    if (gw >= a.n_warps) return;
-    uint32_t m_next, m_end;
-    warp_molecule_run(a, gw, lane, m_next, m_end);
-    const uint32_t inl = sc.fq_format == MMK_FMT_TENX ? 16u : 0u;
-    const uint32_t lt_mask = (1u << lane) - 1u;
-    bool idle = true, done = false;
-    // the molecule in hand
-    uint32_t ml = 0, ms = 0, n = 0, k = 0, t = 0, molsize = 0, n_hap = 0, word_off = 0, round = 0;
-    uint64_t g = 0, ro = 0, key = sc.seed;
-    uint32_t start = 0, remaining = 0, cursor = 0, need_end = 0, P = 0, SUF = 0, q1 = 0, q2 = 0, qreg = 0, status = 0;
-    // per-tile run
-    uint32_t cur_tile = 0, tm0 = 0, acc1 = 0, acc2 = 0, irr = 0;
-    unsigned long long gacc = 0;
-    const uint32_t gb_nominal = (uint32_t)((sc.r1 * a.bpb + 7) / 8 + (sc.r2 * a.bpb + 7) / 8);
-    for (;;) {
-        const unsigned need = __ballot_sync(0xffffffffu, idle && !done);
-        if (need) {
-            if (idle && !done) {
-                const uint32_t idx = m_next + __popc(need & lt_mask);
-                if (idx < m_end) {
-                    ml = idx;
-                    const uint64_t gi = a.mol0 + ml;
-                    g = a.plan.group[gi];
-                    ms = a.plan.slot[gi];
-                    t = a.plan.schema[gi];
-                    molsize = a.plan.size[gi];
-                    ro = a.roff[ml];
-                    n = (uint32_t)(a.roff[ml + 1u] - ro);
-                    n_hap = a.sch[t].len;
-                    word_off = (uint32_t)a.sch[t].word_off;
-                    const unsigned long long sm = a.msum[ml];
-                    round = (uint32_t)(sm >> 32) & 0x7fffffffu;
-                    key = mmk_round_key(sc.seed, round);
-                    // start_pos = rand(1:adjusted_end) (Breakpoints.jl:240)
-                    const uint64_t adjusted_end = sc.circular ? (uint64_t)n_hap : (n_hap > molsize + 1u ? (uint64_t)(n_hap - molsize) : 1ull);
-                    mmk_stream st;
-                    mmk_stream_init(&st, sc.seed, sc.sample, MMK_P_START, g, ms);
-                    start = (uint32_t)mmk_next_index(&st, adjusted_end) + 1u;
-                    header_lens(sc, a.sch[t], (int64_t)start, molsize, gi, P, SUF);
-                    need_end = need_end_of(sc, (int64_t)start);
-                    status = (sm & PLM_OVER) ? (uint32_t)MMK_ERR_INSERTS_UNFITTABLE : 0u;
-                    q1 = inl;
-                    q2 = 0;
-                    qreg = 0;
-                    remaining = (uint32_t)((uint64_t)molsize + 1 - (uint32_t)sm);
-                    cursor = 0;
-                    k = 0;
-                    idle = false;
-                    if (status) {  // Breakpoints.jl:214-216: nothing to chain
-                        atomicMin(&a.err[0], (unsigned long long)gi);
-                        a.plan.status[gi] = (uint8_t)status;
-                        MolRec r;
-                        r.start = (int64_t)start;
-                        r.size = molsize;
-                        r.schema = (uint16_t)t;
-                        r.prefix_len = (uint8_t)P;
-                        r.suffix_len = (uint8_t)SUF;
-                        r.qual1 = q1;
-                        r.qual2 = q2;
-                        a.mol[ml] = r;
-                        idle = true;  // next molecule on the next pass of the loop
-                    }
-                } else
-                    done = true;
+        const uint64_t g = a.plan.group[gi];
+        const uint32_t ms = a.plan.slot[gi];
+        const uint32_t t = a.plan.schema[gi];
+        const uint32_t molsize = a.plan.size[gi];
+        const SchemaDev &S = a.sch[t];
+        const uint32_t n_hap = S.len;
+        const uint32_t s0 = s_so[j];
+        uint64_t isum = s_start[j];
+        bool over = sum_over(sc, sc.seed, g, ms, nfrags, molsize, isum);
+        if (over) over = redraw_in_smem(sc, *tab, g, ms, nfrags, molsize, s_len + s0, isum);
+        // start_pos = rand(1:adjusted_end) (Breakpoints.jl:240)
+        const uint64_t adjusted_end = sc.circular ? (uint64_t)n_hap : (n_hap > molsize + 1u ? (uint64_t)(n_hap - molsize) : 1ull);
+        mmk_stream st;
+        mmk_stream_init(&st, sc.seed, sc.sample, MMK_P_START, g, ms);
+        const uint32_t start = (uint32_t)mmk_next_index(&st, adjusted_end) + 1u;
+        uint32_t status = over ? (uint32_t)MMK_ERR_INSERTS_UNFITTABLE : 0u;
+        uint32_t q1 = inl, q2 = 0;
+        if (!status) {
+            const uint32_t need_end = need_end_of(sc, (int64_t)start);
+            uint32_t remaining = (uint32_t)((uint64_t)molsize + 1u - isum), cursor = 0;
+            uint2 bits = s_bits[s0];
+            uint32_t len = s_len[s0];
+            for (uint32_t k = 0; k < nfrags; ++k) {
+                const uint32_t kn = k + 1u < nfrags ? k + 1u : k;  // next step's operands do not depend on the chain
+                const uint2 nbits = s_bits[s0 + kn];
+                const uint32_t nlen = s_len[s0 + kn];
+                // gap = mulhi64(bits, remaining + 1) with a 32-bit multiplier: two 32 x 32 -> 64 products
+                const uint32_t n1 = remaining + 1u;  // <= molsize + 1 < 2^32
+                const uint64_t lo64 = (uint64_t)bits.x * n1;
+                const uint64_t hi64 = (uint64_t)bits.y * n1 + (lo64 >> 32);
+                const uint32_t gap = (uint32_t)(hi64 >> 32);
+                const uint32_t so = cursor + gap;
+                s_bits[s0 + k].x = so;
+                cursor = so + len;
+                remaining -= gap;
+                if (so + len < need_end) status = MMK_ERR_BOUNDS;
+                bits = nbits;
+                len = nlen;
             }
-            m_next += __popc(need);
+            if (!status) first_read_quals(sc, (int64_t)start, s_bits[s0].x, s_len[s0], n_hap, q1, q2);
         }
-        if (__all_sync(0xffffffffu, done)) break;
-        if (done || idle) continue;
-        const uint64_t p = ro + k;
-        uint32_t blo, bhi, li;
-        {   // the insert's Philox block again (carrying 12 bytes per pair through memory instead measured 40 % slower)
-            mmk_stream is;
-            mmk_insert_stream_init(&is, key, sc.sample, g, ms, k);
-            mmk_stream_block(&is, 0, is.buf);
-            is.blk = 0;
-            blo = is.buf[2];
-            bhi = is.buf[3];
-            if (!(tab.enabled && ins_len_fast(tab, is.buf[1], li))) {
-                NoRec rec;
-                li = insert_len_of(draw_insert_from(sc, is, rec));
-            }
-            if (round) {  // lengths of the accepted redraw round; the gap bits are always those of round 0 (rare)
-                mmk_stream gs;
-                mmk_insert_stream_init(&gs, sc.seed, sc.sample, g, ms, k);
-                uint32_t o[4];
-                mmk_stream_block(&gs, 0, o);
-                blo = o[2];
-                bhi = o[3];
-            }
-        }
-        const uint32_t tile = (uint32_t)(p >> 5);
-        if (k == 0 || tile != cur_tile) {
-            if (k != 0) {  // the run in the previous tile
-                atomicAdd(&a.sum1[cur_tile], acc1);
-                atomicAdd(&a.sum2[cur_tile], acc2);
-                if (irr) a.tile_flags[cur_tile] = 1;
-            }
-            cur_tile = tile;
-            tm0 = a.tile_mol0[tile];
-            acc1 = acc2 = irr = 0;
-        }
-        const uint32_t gap = (uint32_t)mmk_bits_to_index(((uint64_t)bhi << 32) | blo, (uint64_t)remaining + 1);
-        const uint32_t st = cursor + gap;
-        cursor = st + li;
-        remaining -= gap;
-        if (st + li < need_end) status = MMK_ERR_BOUNDS;
-        if (k == 0) {  // quality lengths follow the molecule's FIRST reads (FormatFASTQ.jl:14)
-            first_read_quals(sc, (int64_t)start, st, li, n_hap, q1, q2);
-            qreg = q1 == (uint32_t)sc.r1 + inl && q2 == (uint32_t)sc.r2;
-        }
-        const uint32_t dm = ml - tm0;
-        const uint32_t bstart = start + st, bend = bstart + li - 1u;
-        const uint32_t hdr = P + ndigits_u32(bstart) + 1u + ndigits_u32(bend) + SUF;
-        uint32_t sq1 = (uint32_t)sc.r1, sq2 = (uint32_t)sc.r2;
-        const bool inside = bend <= n_hap && bstart + sq1 - 1u <= n_hap;  // both windows inside the haplotype: nominal lengths
-        const bool a2ok = bend >= sq2;                                   // the R2 window starts at >= 1
-        if (!inside) {
-            sq1 = window_len(bstart, (int64_t)bstart + sc.r1 - 1, n_hap, sc.strict);
-            sq2 = window_len((int64_t)bend - sc.r2 + 1, bend, n_hap, sc.strict);
-            gacc += (sq1 * a.bpb + 7) / 8 + (sq2 * a.bpb + 7) / 8;
-        } else
-            gacc += gb_nominal;
-        acc1 += hdr + inl + sq1 + 3u + q1 + 1u;
-        acc2 += hdr + sq2 + 3u + q2 + 1u;
-        irr |= !(inside && a2ok && qreg && P <= 64u && SUF <= 40u);
-        a.ins[p] = make_uint2(st, li | (dm << 24));
-        a.fdesc[p] = make_uint4(bstart, li | (dm << 24), word_off, (P & 0x7fu) | (SUF << 7) | (t << 13));
-        if (++k < n) continue;
-        // the molecule is placed
-        atomicAdd(&a.sum1[cur_tile], acc1);
-        atomicAdd(&a.sum2[cur_tile], acc2);
-        if (irr) a.tile_flags[cur_tile] = 1;
+        uint32_t P, SUF;
+        header_lens(sc, S, (int64_t)start, molsize, gi, P, SUF);
+        const uint32_t qreg = q1 == (uint32_t)sc.r1 + inl && q2 == (uint32_t)sc.r2;
+        s_start[j] = start;
+        s_meta[j] = MPK(t, P, SUF, qreg, 0u);
         if (status) {
-            atomicMin(&a.err[0], (unsigned long long)(a.mol0 + ml));
-            a.plan.status[a.mol0 + ml] = (uint8_t)status;
+            atomicMin(&a.err[0], (unsigned long long)gi);
+            a.plan.status[gi] = (uint8_t)status;
         }
         MolRec r;
         r.start = (int64_t)start;
@@ -397,15 +383,217 @@ __global__ void __launch_bounds__(PLM_THREADS, 5) k_mol_chain(const __grid_const
         r.schema = (uint16_t)t;
         r.prefix_len = (uint8_t)P;
         r.suffix_len = (uint8_t)SUF;
-        r.qual1 = status ? inl : q1;
-        r.qual2 = status ? 0u : q2;
+        r.qual1 = q1;
+        r.qual2 = q2;
         a.mol[ml] = r;
-        idle = true;
     }
-    if (gacc) atomicAdd(&a.gather[gw & 255u], gacc);
+    __syncthreads();
+    // ---- phase C: one warp per tile of the emit kernel ---------------------------------------------------------------
+    const uint64_t P1 = R0 + np;
+    const uint32_t t_lo = (uint32_t)(R0 >> 5), t_hi = (uint32_t)((P1 + 31u) >> 5);
+    const uint32_t gb_nominal = (uint32_t)((sc.r1 * a.bpb + 7) / 8 + (sc.r2 * a.bpb + 7) / 8);
+    unsigned long long gsum = 0;
+    for (uint32_t tile = t_lo + warp; tile < t_hi; tile += PB_THREADS / 32u) {
+        const uint64_t p = (uint64_t)tile * 32u + lane;
+        const bool valid = p >= R0 && p < P1;
+        uint32_t len1 = 0, len2 = 0, gb = 0, irr = 0;
+        if (valid) {
+            const uint32_t i = (uint32_t)(p - R0);
+            uint32_t j;
+            if (!any_big) j = s_mj[i];
+            else {
+                uint32_t lo = 0, hi = nm - 1u;
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi + 1u) >> 1;
+                    if (s_ro[mid] <= i) lo = mid; else hi = mid - 1u;
+                }
+                j = lo;
+            }
+            const uint32_t pk = s_meta[j];
+            const uint32_t ml = m_lo + j;
+            const uint32_t dm = ml - a.tile_mol0[tile];
+            const uint32_t start = s_start[j];
+            uint32_t so, li;
+            if (MPK_BIG(pk)) {
+                const uint2 q = a.ins[p];
+                so = q.x;
+                li = MMK_INS_LEN(q.y);
+            } else {
+                const uint32_t slot = s_so[j] + (i - s_ro[j]);
+                so = s_bits[slot].x;
+                li = s_len[slot];
+                a.ins[p] = make_uint2(so, li | (dm << 24));
+            }
+            const SchemaDev &S = a.sch[MPK_SCHEMA(pk)];
+            const uint32_t n_hap = S.len;
+            const uint32_t bstart = start + so, bend = bstart + li - 1u;
+            const uint32_t P = MPK_P(pk), SUF = MPK_SUF(pk);
+            const uint32_t hdr = P + ndigits_u32(bstart) + 1u + ndigits_u32(bend) + SUF;
+            uint32_t sq1 = (uint32_t)sc.r1, sq2 = (uint32_t)sc.r2;
+            const bool inside = bend <= n_hap && bstart + sq1 - 1u <= n_hap;  // both windows inside the haplotype: nominal lengths
+            const bool a2ok = bend >= sq2;                                    // the R2 window starts at >= 1
+            if (!inside) {
+                sq1 = window_len(bstart, (int64_t)bstart + sc.r1 - 1, n_hap, sc.strict);
+                sq2 = window_len((int64_t)bend - sc.r2 + 1, bend, n_hap, sc.strict);
+                gb = (sq1 * a.bpb + 7) / 8 + (sq2 * a.bpb + 7) / 8;
+            } else
+                gb = gb_nominal;
+            uint32_t q1 = (uint32_t)sc.r1 + inl, q2 = (uint32_t)sc.r2;
+            if (!MPK_QREG(pk)) {  // quality lengths of the molecule's first reads (FormatFASTQ.jl:14): from its record
+                const MolRec r = a.mol[ml];
+                q1 = r.qual1;
+                q2 = r.qual2;
+            }
+            len1 = hdr + inl + sq1 + 3u + q1 + 1u;
+            len2 = hdr + sq2 + 3u + q2 + 1u;
+            irr = !(inside && a2ok && MPK_QREG(pk) && P <= 64u && SUF <= 40u);
+            a.fdesc[p] = make_uint4(bstart, li | (dm << 24), (uint32_t)S.word_off, (P & 0x7fu) | (SUF << 7) | (MPK_SCHEMA(pk) << 13));
+        }
+        const uint32_t tot1 = __reduce_add_sync(0xffffffffu, len1), tot2 = __reduce_add_sync(0xffffffffu, len2);
+        gsum += __reduce_add_sync(0xffffffffu, gb);
+        const bool irregular = __any_sync(0xffffffffu, irr != 0u);
+        if (lane == 0) {
+            const bool whole = (uint64_t)tile * 32u >= R0 && ((uint64_t)tile * 32u + 32u <= P1 || P1 == a.n_pairs);
+            if (whole) {
+                a.sum1[tile] = tot1;
+                a.sum2[tile] = tot2;
+            } else {  // a tile shared with the neighbouring block
+                atomicAdd(&a.sum1[tile], tot1);
+                atomicAdd(&a.sum2[tile], tot2);
+            }
+            if (irregular) a.tile_flags[tile] = 1;
+        }
+    }
+    if (lane == 0 && gsum) atomicAdd(&a.gather[(blockIdx.x * 8u + warp) & 255u], gsum);
 }
 
-// tile_flags: 1 = irregular (from k_place_mol) -> 1 = every pair regular and the tile fits the emit kernel's stage
+// One CTA per molecule with more than PB_BIG pairs: lengths and gap bits in chunks through shared memory, the chain by
+// one thread.  Writes the molecule's inserts and its record.
+constexpr uint32_t BIGC = 1024;  // pairs per chunk
+__global__ void __launch_bounds__(PB_THREADS) k_place_big(const __grid_constant__ PlaceArgs a) {
+    __shared__ InsTable tab;
+    __shared__ uint32_t s_lo[BIGC], s_hi[BIGC], s_len[BIGC];
+    __shared__ unsigned long long s_red[PB_THREADS / 32];
+    __shared__ unsigned long long s_isum;
+    __shared__ uint32_t s_flag;
+    __shared__ unsigned long long s_state[3];  // remaining, cursor, status
+    const SimConst &sc = a.sc;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t count = min(*a.big_count, a.big_cap);
+    if (blockIdx.x >= count) return;
+    stage_table(&tab, a.tab);
+    __syncthreads();
+    for (uint32_t bi = blockIdx.x; bi < count; bi += gridDim.x) {
+        const uint32_t ml = a.big_list[bi];
+        const uint64_t gi = a.mol0 + ml;
+        const uint64_t ro = a.roff[ml];
+        const uint32_t nfrags = (uint32_t)(a.roff[ml + 1u] - ro);
+        const uint64_t g = a.plan.group[gi];
+        const uint32_t ms = a.plan.slot[gi];
+        const uint32_t t = a.plan.schema[gi];
+        const uint32_t molsize = a.plan.size[gi];
+        const SchemaDev &S = a.sch[t];
+        const uint32_t n = S.len;
+        // the round whose length vector fits (Breakpoints.jl:209-212)
+        uint64_t key = sc.seed, isum = 0;
+        bool over = true;
+        int round = 0;
+        for (int attempts = 0; attempts <= sc.attempts; ++attempts) {
+            round = attempts;
+            key = mmk_round_key(sc.seed, (uint32_t)attempts);
+            unsigned long long part = 0;
+            for (uint32_t k = tid; k < nfrags; k += PB_THREADS) part += pair_len(sc, tab, key, g, ms, k);
+            for (int o = 16; o; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+            __syncthreads();  // s_red / s_flag of the previous round are consumed
+            if (lane == 0) s_red[warp] = part;
+            __syncthreads();
+            if (tid == 0) {
+                unsigned long long tot = 0;
+                for (uint32_t w = 0; w < PB_THREADS / 32; ++w) tot += s_red[w];
+                s_isum = tot;
+                s_flag = sum_over(sc, key, g, ms, nfrags, molsize, tot) ? 1u : 0u;
+            }
+            __syncthreads();
+            isum = s_isum;
+            over = s_flag != 0u;
+            if (!over) break;
+        }
+        const uint64_t adjusted_end = sc.circular ? (uint64_t)n : (n > molsize + 1u ? (uint64_t)(n - molsize) : 1ull);
+        mmk_stream s;
+        mmk_stream_init(&s, sc.seed, sc.sample, MMK_P_START, g, ms);
+        const int64_t start = (int64_t)mmk_next_index(&s, adjusted_end) + 1;
+        uint32_t status = over ? (uint32_t)MMK_ERR_INSERTS_UNFITTABLE : 0u;
+        uint32_t q1 = 0, q2 = 0;
+        if (!status) {
+            const uint32_t need_end = need_end_of(sc, start);
+            if (tid == 0) {
+                s_state[0] = (uint64_t)molsize + 1 - isum;
+                s_state[1] = 0;
+                s_state[2] = 0;
+            }
+            for (uint32_t c0 = 0; c0 < nfrags; c0 += BIGC) {
+                const uint32_t cn = min(BIGC, nfrags - c0);
+                __syncthreads();  // previous chunk written out
+                for (uint32_t k = tid; k < cn; k += PB_THREADS) {
+                    uint32_t blo, bhi;
+                    uint32_t li = pair_draw(sc, tab, g, ms, c0 + k, blo, bhi);
+                    if (round) li = pair_len(sc, tab, key, g, ms, c0 + k);  // lengths of the accepted round, gap bits of round 0
+                    s_lo[k] = blo;
+                    s_hi[k] = bhi;
+                    s_len[k] = li;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    uint64_t remaining = s_state[0];
+                    uint32_t cursor = (uint32_t)s_state[1];
+                    uint32_t st_bad = (uint32_t)s_state[2];
+                    for (uint32_t k = 0; k < cn; ++k) {
+                        const uint32_t gap = (uint32_t)mmk_bits_to_index(((uint64_t)s_hi[k] << 32) | s_lo[k], remaining + 1);
+                        const uint32_t st = cursor + gap;
+                        s_lo[k] = st;
+                        cursor = st + s_len[k];
+                        remaining -= gap;
+                        if (st + s_len[k] < need_end) st_bad = MMK_ERR_BOUNDS;
+                    }
+                    s_state[0] = remaining;
+                    s_state[1] = cursor;
+                    s_state[2] = st_bad;
+                }
+                __syncthreads();
+                if (c0 == 0) first_read_quals(sc, start, s_lo[0], s_len[0], n, q1, q2);
+                for (uint32_t k = tid; k < cn; k += PB_THREADS) {
+                    const uint64_t p = ro + c0 + k;
+                    const uint32_t dm = ml - a.tile_mol0[p >> 5];
+                    a.ins[p] = make_uint2(s_lo[k], s_len[k] | (dm << 24));
+                }
+            }
+            __syncthreads();
+            status = (uint32_t)s_state[2];
+            if (status) q1 = q2 = 0;
+        }
+        if (status && sc.fq_format == MMK_FMT_TENX) q1 = 16u;
+        if (tid == 0) {
+            if (status) {
+                atomicMin(&a.err[0], (unsigned long long)gi);
+                a.plan.status[gi] = (uint8_t)status;
+            }
+            uint32_t P, SUF;
+            header_lens(sc, S, start, molsize, gi, P, SUF);
+            MolRec r;
+            r.start = start;
+            r.size = molsize;
+            r.schema = (uint16_t)t;
+            r.prefix_len = (uint8_t)P;
+            r.suffix_len = (uint8_t)SUF;
+            r.qual1 = q1;
+            r.qual2 = q2;
+            a.mol[ml] = r;
+        }
+        __syncthreads();
+    }
+}
+
+// tile_flags: 1 = irregular (from k_place_block) -> 1 = every pair regular and the tile fits the emit kernel's stage
 __global__ void k_tile_flags(const uint32_t *__restrict__ sum1, const uint32_t *__restrict__ sum2, uint32_t n_tiles, uint32_t stage_cap,
                              uint8_t *tile_flags) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

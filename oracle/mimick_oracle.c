@@ -443,15 +443,15 @@ orc_sim *orc_create(const orc_params *p) {
             s->err_qb[r] = (uint8_t *)malloc((size_t)S);
             for (int c = 0; c < S; ++c) {
                 const double e = S > 1 ? p->err_sub_start + (p->err_sub_end - p->err_sub_start) * (double)c / (double)(S - 1) : p->err_sub_start;
-                s->err_thr[r][c] = (uint32_t)floor(e * 4294967296.0);
+                s->err_thr[r][c] = (uint32_t)floor(e * MMK_ERR_SCALE);
                 double et = e + p->err_ins + p->err_del;
                 if (et < 1e-4) et = 1e-4;
                 int q = (int)floor(-10.0 * log10(et) + 0.5);
                 s->err_qb[r][c] = (uint8_t)(q < 2 ? 2 : q > 40 ? 40 : q);
             }
         }
-        s->err_tins = (uint32_t)floor(p->err_ins * 4294967296.0);
-        s->err_tdel = (uint32_t)floor(p->err_del * 4294967296.0);
+        s->err_tins = (uint32_t)floor(p->err_ins * MMK_ERR_SCALE);
+        s->err_tdel = (uint32_t)floor(p->err_del * MMK_ERR_SCALE);
     }
     return s;
 }
@@ -765,9 +765,9 @@ static int64_t circular_index(const orc_schema *c, int64_t a, int64_t b, int str
 static int dec(char *o, int64_t v) { return sprintf(o, "%lld", (long long)v); }
 
 /* Sequencing-error model (NOT in the reference: docs/algorithm.md:11 lists it as future work; specified in DESIGN.md
- * "Error model").  One read of nominal length S: cycle c takes one 64-bit draw (mmk_error_draw: seed, sample, run-wide
- * pair index, read, cycle).  Low word u: u < thr_sub[c] substitution; next t_ins insertion; next t_del deletion.  High
- * word: bits 0-1 replacement selector, bits 2-4 quality jitter.  The template is walked from the read's first base
+ * "Error model").  One read of nominal length S: cycle c takes one 32-bit draw (mmk_error_draw: seed, sample, run-wide
+ * pair index, read, cycle).  Bits 0-23 u: u < thr_sub[c] substitution; next t_ins insertion; next t_del deletion (thresholds
+ * are probabilities scaled by 2^24).  Bits 24-25: replacement selector, bits 26-28: quality jitter.  The template is walked from the read's first base
  * (R2: a2 upwards; R1: bs + r1 - 1 downwards, complemented): an insertion emits ACGT[sel] and consumes no template base; a
  * deletion skips one template base first; positions past the contig ends are clamped (strict circular wrap: modular).
  * A substitution replaces an A/C/G/T by ACGT[(code + 1 + sel % 3) % 4] (other IUPAC symbols stay).  Quality of cycle c:
@@ -781,9 +781,8 @@ static void erroneous_read(orc_sim *s, const orc_schema *c, int rd, int64_t firs
     const int64_t n = c->len;
     int64_t r = 0; /* template bases consumed */
     for (int cyc = 0; cyc < S; ++cyc) {
-        const uint64_t d = mmk_error_draw(s->seed, s->sample, pair, (uint32_t)rd, (uint32_t)cyc);
-        const uint32_t u = (uint32_t)d, aux = (uint32_t)(d >> 32);
-        const uint32_t sel = aux & 3u, jit = (aux >> 2) & 7u;
+        const uint32_t d = mmk_error_draw(s->seed, s->sample, pair, (uint32_t)rd, (uint32_t)cyc);
+        const uint32_t u = MMK_ERR_U(d), sel = MMK_ERR_SEL(d), jit = MMK_ERR_JIT(d);
         const int is_sub = u < thr[cyc];
         const int is_ins = !is_sub && (u - thr[cyc]) < s->err_tins;
         const int is_del = !is_sub && !is_ins && (u - thr[cyc] - s->err_tins) < s->err_tdel;

@@ -593,8 +593,8 @@ def _env(**kv):
     dict(coverage=30, mol_length=400_000, mol_coverage=0.6, singletons=0.3, n_molecules=4),   # a mix of short and long molecules
 ])
 def test_placement_paths_agree_with_the_oracle(tmp_path, kw):
-    """The default placement path, the lane-per-molecule kernels (also with other warp shares) and the three-kernel
-    path give the oracle's bytes, plan and inserts."""
+    """The default placement path (one CTA per block of molecules, big molecules through their own kernel) and the
+    three-kernel path give the oracle's bytes, plan and inserts."""
     rng = np.random.default_rng(14)
     p1 = os.path.join(str(tmp_path), "a.fa")
     p2 = os.path.join(str(tmp_path), "b.fa")
@@ -604,9 +604,8 @@ def test_placement_paths_agree_with_the_oracle(tmp_path, kw):
     gpu, orc = check_single([p1, p2], "haplotagging", seed=31, **okw)
     nf = gpu["mol"]["n_frags"]
     if kw.get("mol_length", 0) >= 400_000:
-        assert (nf > 512).sum() > 3 and (nf <= 512).sum() > 3
-    for env in (dict(MMK_PLACE_MODE="fused"), dict(MMK_PLACE_MODE="fused", MMK_PLACE_WAVES=7),
-                dict(MMK_PLACE_MODE="legacy")):
+        assert (nf > 1024).sum() > 3 and (nf <= 1024).sum() > 3   # both sides of PB_BIG (mmk_place.cuh)
+    for env in (dict(MMK_PLACE_MODE="block"), dict(MMK_PLACE_MODE="legacy")):
         with _env(**env):
             alt = gpu_single([p1, p2], "haplotagging", 31, variates=False, **okw)
         assert alt["r1"] == gpu["r1"] and alt["r2"] == gpu["r2"], env
