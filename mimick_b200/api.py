@@ -73,7 +73,10 @@ class Simulator:
     def __init__(self, format="standard:haplotagging", *, coverage=30, n_molecules=2, mol_coverage=0.2,
                  mol_length=80000, insert_length=500, insert_stdev=50, read_length=(150, 150), singletons=0.70,
                  circular=False, attempts=25, seed=-1, mask=False, device=0, strict_wrap=False,
-                 force_generic=False, max_chunk_bytes=0, plan_batch_groups=0):
+                 force_generic=False, max_chunk_bytes=0, plan_batch_groups=0, error_rate=(0.0, 0.0), indel_error=(0.0, 0.0)):
+        """`error_rate` = substitution probability at the first and the last cycle of a read (linear in between),
+        `indel_error` = insertion and deletion probability per cycle: the optional sequencing-error model (not in the
+        reference, whose reads are verbatim copies with constant quality; all zero = off, the parity default)."""
         L = _lib.load()
         self._L = L
         bc, fq = interperet_format(format)
@@ -100,6 +103,8 @@ class Simulator:
         p.force_generic = int(bool(force_generic))
         p.max_chunk_bytes = int(max_chunk_bytes)
         p.plan_batch_groups = int(plan_batch_groups)
+        p.err_sub_start, p.err_sub_end = float(error_rate[0]), float(error_rate[1])
+        p.err_ins, p.err_del = float(indel_error[0]), float(indel_error[1])
         self.params = p
         self._h = C.c_void_p()
         rc = L.mmk_create(C.byref(p), C.byref(self._h))
@@ -369,7 +374,7 @@ class Simulator:
 # the reference's public function
 # ------------------------------------------------------------------------------------------
 _SIM_KW = ("coverage", "n_molecules", "mol_coverage", "mol_length", "insert_length", "insert_stdev", "read_length",
-           "singletons", "circular", "attempts", "seed", "mask", "device", "strict_wrap", "max_chunk_bytes")
+           "singletons", "circular", "attempts", "seed", "mask", "device", "strict_wrap", "max_chunk_bytes", "error_rate", "indel_error")
 
 
 @dataclass

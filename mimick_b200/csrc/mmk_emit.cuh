@@ -27,6 +27,7 @@ constexpr int EMIT_MAX_TP = 64;  // pairs per tile <= threads / 4 (one thread pe
 struct PairDesc {
     uint64_t word_off;   // packed haplotype start (32-bit words)
     uint32_t mol;        // shard-relative molecule index
+    uint64_t pair;       // shard-relative pair index
     uint32_t bstart, bend;   // 1-based inclusive insert breakpoints (contigs < 2^31 bases)
     uint32_t hdr;        // header line length incl. '\n' (without an inline barcode)
     uint32_t sq1, sq2;   // sequence lengths
@@ -48,6 +49,7 @@ __device__ __forceinline__ void decode_pair(const EmitArgs &a, uint64_t p, uint3
     d.word_off = S.word_off;
     d.n = S.len;
     d.mol = m;
+    d.pair = p;
     d.bstart = (uint32_t)mr.start + in.x;
     d.bend = d.bstart + MMK_INS_LEN(in.y) - 1;
     d.d1 = (uint8_t)ndigits_u32(d.bstart);
@@ -89,6 +91,73 @@ __device__ __forceinline__ uint32_t fetch_code(const uint32_t *__restrict__ w, u
     return (__ldg(&w[pos / PER]) >> (BPB * (pos % PER))) & ((1u << BPB) - 1u);
 }
 
+// Sequencing-error model (optional, off by default; the reference has none: docs/algorithm.md:11 lists it as future
+// work).  Definition: oracle/mimick_oracle.c erroneous_read.  One warp per read of nominal length: a lane takes 4
+// consecutive cycles of a round of 128 (one Philox block, mmk_error_block); an insertion consumes no template base, a
+// deletion two, anything else one, so the template offset of a lane's first cycle is a warp scan away.
+// put(cycle, base character, quality character) stores the two bytes.
+template <int BPB, class Put>
+__device__ __forceinline__ void err_read_warp(const EmitArgs &a, const uint32_t *__restrict__ hw, uint32_t n, uint32_t rd, int64_t first_pos,
+                                              uint64_t pair, uint32_t lane, Put put) {
+    const uint32_t S = rd == 1u ? (uint32_t)a.r1 : (uint32_t)a.r2;
+    const uint32_t *thr = a.err_thr + (rd == 1u ? 0u : (uint32_t)a.r1);
+    const uint8_t *qb = a.err_qb + (rd == 1u ? 0u : (uint32_t)a.r1);
+    uint32_t consumed = 0;  // template bases consumed by the cycles of earlier rounds
+    for (uint32_t c0 = 0; c0 < S; c0 += 128u) {
+        const uint32_t cb = c0 + 4u * lane;
+        uint32_t o[4];
+        mmk_error_block(a.seed, a.sample, pair, rd, cb >> 2, o);
+        uint32_t ev = 0, cons = 0;  // 2 bits per cycle: 0 none, 1 substitution, 2 insertion, 3 deletion
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) {
+            if (cb + k < S) {
+                const uint32_t u = MMK_ERR_U(o[k]), t = __ldg(thr + cb + k);
+                const uint32_t e = u < t ? 1u : (u - t < a.err_tins ? 2u : (u - t - a.err_tins < a.err_tdel ? 3u : 0u));
+                ev |= e << (2u * k);
+                cons += e == 2u ? 0u : (e == 3u ? 2u : 1u);
+            }
+        }
+        uint32_t inc = cons;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= (uint32_t)d) inc += y;
+        }
+        uint32_t r = consumed + inc - cons;
+        consumed += __shfl_sync(0xffffffffu, inc, 31);
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) {
+            const uint32_t c = cb + k;
+            if (c >= S) break;
+            const uint32_t e = (ev >> (2u * k)) & 3u, sel = MMK_ERR_SEL(o[k]), jit = MMK_ERR_JIT(o[k]);
+            uint32_t ch;
+            if (e == 2u) {
+                ch = (0x54474341u >> (8u * sel)) & 0xffu;  // "ACGT"[sel]
+            } else {
+                if (e == 3u) ++r;
+                int64_t pos = rd == 1u ? first_pos - (int64_t)r : first_pos + (int64_t)r;  // 1-based
+                if (a.strict) pos = ((pos - 1) % (int64_t)n + (int64_t)n) % (int64_t)n + 1;
+                else pos = pos < 1 ? 1 : (pos > (int64_t)n ? (int64_t)n : pos);
+                const uint32_t code = fetch_code<BPB>(hw, (uint32_t)(pos - 1));
+                ++r;
+                uint32_t idx;  // index in "ACGT", 4 = another IUPAC symbol
+                if (BPB == 2) {
+                    idx = rd == 1u ? 3u - code : code;
+                    ch = (0x54474341u >> (8u * idx)) & 0xffu;
+                } else {
+                    const uint32_t c4 = rd == 1u ? comp4(code) : code;
+                    ch = (uint32_t)(uint8_t)code4_to_ascii(c4);
+                    idx = c4 == 1u ? 0u : (c4 == 2u ? 1u : (c4 == 4u ? 2u : (c4 == 8u ? 3u : 4u)));
+                }
+                if (e == 1u && idx < 4u) ch = (0x54474341u >> (8u * ((idx + 1u + sel % 3u) & 3u))) & 0xffu;
+            }
+            int q = (int)__ldg(qb + c) + (int)((0x43222210u >> (4u * jit)) & 15u) - 2 - ((e == 1u || e == 2u) ? 10 : 0);
+            q = q < 2 ? 2 : (q > 41 ? 41 : q);
+            put(c, ch, (uint32_t)(33 + q));
+        }
+    }
+}
+
 // General byte-wise record writer: any read length, wrap mode, quality length. One warp per record.
 template <int BPB>
 __device__ void write_record_generic(const EmitArgs &a, const PairDesc &d, int rd, uint8_t *out, uint32_t lane) {
@@ -121,6 +190,15 @@ __device__ void write_record_generic(const EmitArgs &a, const PairDesc &d, int r
         else if ((k -= 3) < q) c = 'I';
         else c = '\n';
         out[k0] = c;
+    }
+    if (a.err_on && sq == (rd == 1 ? (uint32_t)a.r1 : (uint32_t)a.r2) && q == sq + inl) {  // nominal read: the error model rewrites bases and qualities
+        __syncwarp();
+        const uint32_t hdr_all = P + d.d1 + 1u + d.d2 + SUF + inl;
+        uint8_t *seq = out + hdr_all, *qual = out + hdr_all + sq + 3u + inl;
+        err_read_warp<BPB>(a, hw, n, (uint32_t)rd, rd == 1 ? wb : wa, a.pair_base + d.pair, lane, [&](uint32_t c, uint32_t ch, uint32_t qc) {
+            seq[c] = (uint8_t)ch;
+            qual[c] = (uint8_t)qc;
+        });
     }
 }
 
@@ -222,6 +300,12 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
 __device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+// the same stores without the compiler-level memory barrier: the stage is only touched through volatile asm statements,
+// whose mutual order is kept, so loads and arithmetic of a second read pair may be scheduled across them (k_emit_w)
+__device__ __forceinline__ void sts128_nb(uint32_t addr, const uint4 &v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+__device__ __forceinline__ void sts8_nb(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v)); }
 __device__ __forceinline__ uint32_t lds8(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
@@ -318,6 +402,49 @@ __device__ __forceinline__ void emit_pair_seq(const EmitArgs &a, const uint2 rde
         const uint32_t val = (hl == 0 || hl == 2 || hl == 15) ? '\n' : (hl == 1 ? '+' : 'I');
         sts8(smem + addr, val);
     }
+}
+
+// Two read pairs per pass (k_emit_w): the two bodies share no data, so their shuffles, permutes and stores interleave
+// and a warp has twice the independent work in flight.
+struct SeqChunk {
+    uint4 v;
+    uint32_t addr, seq_end, rec_end;
+    bool store;
+};
+__device__ __forceinline__ SeqChunk seq_chunk(const EmitArgs &a, const uint2 rdesc, uint32_t W, uint32_t lane) {
+    const uint32_t half = lane >> 4, hl = lane & 15u;
+    const uint32_t inl = half ? 0u : (uint32_t)a.bclen_inline;
+    const uint32_t S = half ? (uint32_t)a.r2 : (uint32_t)a.r1;
+    const uint32_t seq_off = rdesc.x & 0xfffffu;
+    const int rel = (int)(rdesc.x >> 20);
+    SeqChunk r;
+    r.seq_end = seq_off + S;
+    r.rec_end = r.seq_end + 3u + S + inl + 1u;
+    const uint32_t c = (seq_off >> 4) + hl;
+    const int k0 = (int)(16u * c) - (int)seq_off;
+    const int q = half ? rel + k0 : rel + (int)S - 16 - k0;
+    const int j = q >> 4;
+    const uint32_t sh = ((uint32_t)q & 15u) * 2u;
+    uint32_t lo = __shfl_sync(0xffffffffu, W, (int)((lane & 16u) | ((uint32_t)j & 15u)));
+    const uint32_t hi = __shfl_sync(0xffffffffu, W, (int)((lane & 16u) | ((uint32_t)(j + 1) & 15u)));
+    if (j < 0) lo = 0;
+    uint32_t bits = __funnelshift_r(lo, hi, sh);
+    if (!half) bits = __brev(bits);
+    r.v = expand16(bits, half ? 0x54474341u /* "ACGT" */ : 0x41474354u /* "TCGA" */);
+    r.addr = 16u * c;
+    r.store = 16u * c < r.seq_end;
+    return r;
+}
+__device__ __forceinline__ void emit_pair_seq2(const EmitArgs &a, const uint2 rdA, uint32_t WA, const uint2 rdB, uint32_t WB, bool haveB,
+                                               uint32_t smem, uint32_t lane) {
+    const uint32_t hl = lane & 15u;
+    const SeqChunk A = seq_chunk(a, rdA, WA, lane), B = seq_chunk(a, rdB, WB, lane);
+    if (A.store) sts128_nb(smem + A.addr, A.v);
+    if (B.store && haveB) sts128_nb(smem + B.addr, B.v);
+    __syncwarp();
+    const uint32_t val = (hl == 0 || hl == 2 || hl == 15) ? '\n' : (hl == 1 ? '+' : 'I');
+    sts8_nb(smem + (hl < 15 ? A.seq_end + hl : A.rec_end - 1u), val);
+    if (haveB) sts8_nb(smem + (hl < 15 ? B.seq_end + hl : B.rec_end - 1u), val);
 }
 
 // 8 bases of a 4-bit word (BioSequences one-hot codes A=1 C=2 G=4 T=8) → 8 ASCII bytes; false if any of
@@ -699,12 +826,13 @@ __device__ __forceinline__ void emit_headers_warp(const EmitArgs &a, const uint4
     }
 }
 
-template <int BPB>
+template <int BPB, bool ERR, int ILP>
 __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint4 s_fa[32];
     __shared__ uint2 s_fb[32];
     __shared__ uint2 s_rd[64];
+    __shared__ uint2 s_er[ERR ? 32 : 1];  // error model: first arena word and length of the pair's haplotype
     __shared__ uint32_t s_off1[33], s_off2[33];
     __shared__ uint32_t s_done;
     __shared__ __align__(8) unsigned long long s_mbar;
@@ -751,6 +879,7 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
                 const uint32_t rel1 = ws1 >= 15u ? ((ws1 - 15u) & WM) + 15u : ws1, rel2 = ws2 >= 15u ? ((ws2 - 15u) & WM) + 15u : ws2;
                 s_rd[2 * lane] = make_uint2((f.sb1 + FD_HDR(f.pk) + (uint32_t)a.bclen_inline) | (rel1 << 20), f.wbase1);
                 s_rd[2 * lane + 1] = make_uint2((f.sb2 + FD_HDR(f.pk)) | (rel2 << 20), f.wbase2);
+                if (ERR) s_er[lane] = make_uint2(q.z, a.sch[q.w >> 13].len);
                 // start the loads the next phases will need
                 prefetch_l1(a.hap + f.wbase1);
                 prefetch_l1(a.hap + f.wbase1 + (BPB == 2 ? 15 : 31));
@@ -793,6 +922,23 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
     // this warp's pairs [w0, w1)
     const uint32_t w0 = 8u * warp, w1 = (w0 + 8u < np) ? w0 + 8u : np;
     if (w0 < w1) {
+        if (BPB == 2 && !ERR && ILP == 2) {  // two pairs per pass; the words of the next two are loaded meanwhile
+            const uint32_t half = lane >> 4, hl = lane & 15u;
+            const uint32_t *hap_lane = a.hap + hl;
+            uint2 rdA = s_rd[2 * w0 + half], rdB = s_rd[2 * (w0 + 1u < w1 ? w0 + 1u : w0) + half];
+            uint32_t WA = __ldg(hap_lane + rdA.y), WB = __ldg(hap_lane + rdB.y);
+            mbar_wait(mb, 0u);  // the quality fill has landed
+            for (uint32_t t = w0; t < w1; t += 2u) {
+                const uint32_t ta = t + 2u < w1 ? t + 2u : t, tb = t + 3u < w1 ? t + 3u : ta;
+                const uint2 rnA = s_rd[2 * ta + half], rnB = s_rd[2 * tb + half];
+                const uint32_t WnA = __ldg(hap_lane + rnA.y), WnB = __ldg(hap_lane + rnB.y);
+                emit_pair_seq2(a, rdA, WA, rdB, WB, t + 1u < w1, sm, lane);
+                rdA = rnA;
+                rdB = rnB;
+                WA = WnA;
+                WB = WnB;
+            }
+        } else
         {   // sequences: the reference words of the next pair are loaded while this one is expanded
             const uint32_t half = lane >> 4, hl = lane & 15u;
             const uint32_t *hap_lane = a.hap + hl;
@@ -805,6 +951,21 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
                 const uint32_t W0n = __ldg(hap_lane + rn.y), W1n = BPB == 4 ? __ldg(hap_lane + rn.y + 16) : 0u;
                 if (BPB == 2) emit_pair_seq(a, rd, W0, sm, lane);
                 else emit_pair_seq4(a, rd, W0, W1, sm, lane);
+                if (ERR) {  // bases and qualities again, through the error model (every pair of a fast tile has nominal reads)
+                    __syncwarp();
+                    const uint4 fa = s_fa[t];
+                    const uint2 er = s_er[t];
+                    const uint32_t so1 = sm + (s_rd[2 * t].x & 0xfffffu), so2 = sm + (s_rd[2 * t + 1].x & 0xfffffu);
+                    const uint32_t qo1 = so1 + (uint32_t)a.r1 + 3u + (uint32_t)a.bclen_inline, qo2 = so2 + (uint32_t)a.r2 + 3u;
+                    err_read_warp<BPB>(a, a.hap + er.x, er.y, 1u, (int64_t)fa.z + a.r1 - 1, a.pair_base + p0 + t, lane, [&](uint32_t c, uint32_t ch, uint32_t qc) {
+                        sts8(so1 + c, ch);
+                        sts8(qo1 + c, qc);
+                    });
+                    err_read_warp<BPB>(a, a.hap + er.x, er.y, 2u, (int64_t)fa.w - a.r2 + 1, a.pair_base + p0 + t, lane, [&](uint32_t c, uint32_t ch, uint32_t qc) {
+                        sts8(so2 + c, ch);
+                        sts8(qo2 + c, qc);
+                    });
+                }
                 rd = rn;
                 W0 = W0n;
                 W1 = W1n;

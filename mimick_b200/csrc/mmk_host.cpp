@@ -138,6 +138,11 @@ struct mmk_ctx {
     DBuf<uint4> d_fdesc;
     DBuf<uint8_t> d_tile_flags;
     DBuf<uint8_t> d_qfill;        // 2 * stage_cap bytes of 'I': source of the emit kernel's stage fill (bulk copy)
+    // sequencing-error model (optional): per-cycle substitution thresholds and base qualities, R1 cycles then R2
+    bool err_on = false;
+    uint32_t err_tins = 0, err_tdel = 0;
+    DBuf<uint32_t> d_err_thr;
+    DBuf<uint8_t> d_err_qb;
     DBuf<uint8_t> d_tmp, d_tmp2;  // placement scratch: (gap bits, insert length) per pair of one segment (two alternate)
     // haplotype construction scratch, kept between samples (a 100 Mbp master: cudaMalloc + cudaFree of these cost more than the kernels)
     DBuf<char> v_alt, v_tmp, v_snp_alt;
@@ -507,6 +512,32 @@ extern "C" int32_t mmk_create(const mmk_params *p, mmk_ctx **out) {
     }
     CU(cudaMalloc((void **)&ctx->d_stats, sizeof(ContigStats)));
     CU(cudaMallocHost((void **)&ctx->h_stats, sizeof(ContigStats)));
+    ctx->err_on = q.err_sub_start > 0.0 || q.err_sub_end > 0.0 || q.err_ins > 0.0 || q.err_del > 0.0;
+    if (q.err_sub_start < 0 || q.err_sub_end < 0 || q.err_ins < 0 || q.err_del < 0 ||
+        (ctx->err_on && std::max(q.err_sub_start, q.err_sub_end) + q.err_ins + q.err_del > 0.5))
+        return fail(ctx, MMK_ERR_INVALID_ARG, "error rates must be >= 0 and sum to at most 0.5");
+    if (ctx->err_on) {  // same expressions as the oracle (oracle/mimick_oracle.c orc_create): thresholds scaled by 2^24, Phred of the cycle's rate
+        const int S1 = q.length_r1, S2 = q.length_r2;
+        std::vector<uint32_t> thr((size_t)S1 + S2);
+        std::vector<uint8_t> qb((size_t)S1 + S2);
+        for (int r = 0; r < 2; ++r) {
+            const int S = r ? S2 : S1, o = r ? S1 : 0;
+            for (int c = 0; c < S; ++c) {
+                const double e = S > 1 ? q.err_sub_start + (q.err_sub_end - q.err_sub_start) * (double)c / (double)(S - 1) : q.err_sub_start;
+                thr[(size_t)o + c] = (uint32_t)floor(e * MMK_ERR_SCALE);
+                double et = e + q.err_ins + q.err_del;
+                if (et < 1e-4) et = 1e-4;
+                const int ph = (int)floor(-10.0 * log10(et) + 0.5);
+                qb[(size_t)o + c] = (uint8_t)(ph < 2 ? 2 : ph > 40 ? 40 : ph);
+            }
+        }
+        ctx->err_tins = (uint32_t)floor(q.err_ins * MMK_ERR_SCALE);
+        ctx->err_tdel = (uint32_t)floor(q.err_del * MMK_ERR_SCALE);
+        CU(ctx->d_err_thr.ensure(thr.size()));
+        CU(ctx->d_err_qb.ensure(qb.size()));
+        CU(cudaMemcpy(ctx->d_err_thr.p, thr.data(), thr.size() * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(ctx->d_err_qb.p, qb.data(), qb.size(), cudaMemcpyHostToDevice));
+    }
     ctx->h_instab = new InsTable();
     build_insert_table(sc, *ctx->h_instab);
     CU(ctx->d_instab.ensure(1));
@@ -1319,6 +1350,14 @@ static EmitArgs base_args(mmk_ctx *c) {
     a.stage_cap = c->stage_cap;
     a.fast_ok = c->fast_ok;
     a.qfill = c->d_qfill.p;
+    a.err_on = c->err_on ? 1 : 0;
+    a.err_tins = c->err_tins;
+    a.err_tdel = c->err_tdel;
+    a.err_thr = c->d_err_thr.p;
+    a.err_qb = c->d_err_qb.p;
+    a.seed = c->sc.seed;
+    a.sample = c->sc.sample;
+    a.pair_base = c->pair0;
     a.tile_off1 = c->d_tile_off1.p;
     a.tile_off2 = c->d_tile_off2.p;
     a.n_pairs = c->s_npairs;

@@ -126,6 +126,13 @@ struct EmitArgs {
     uint32_t stage_cap;        // bytes of shared-memory stage per stream (fast path)
     int32_t fast_ok;           // host-level eligibility of the fast path (read lengths, format)
     const uint8_t *qfill;      // >= 2 * stage_cap bytes of the quality character (source of the stage fill by bulk copy); null: k_emit
+    // sequencing-error model (optional, off by default; not in the reference — DESIGN.md "Error model")
+    int32_t err_on;
+    uint32_t err_tins, err_tdel;  // insertion / deletion probability scaled by 2^24
+    const uint32_t *err_thr;      // [r1 + r2] substitution thresholds per cycle (R1 cycles, then R2), scaled by 2^24
+    const uint8_t *err_qb;        // [r1 + r2] base Phred quality per cycle
+    uint64_t seed, pair_base;     // pair_base: run-wide index of the shard's first pair
+    uint32_t sample;
 };
 
 #ifdef __cplusplus

@@ -17,7 +17,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, mangled = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "mimick_b200", "_build", "mmk_device.o")], cwd=tmp,
+# NCU_OBJ: the object file of the build that was profiled (default: the current build)
+subprocess.run(["cuobjdump", "-xelf", "all", os.environ.get("NCU_OBJ", os.path.join(ROOT, "mimick_b200", "_build", "mmk_device.o"))], cwd=tmp,
                capture_output=True)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.split("\n")

@@ -3,6 +3,7 @@ without running Julia: the literal format examples of its docs, hand-derived kno
 fixtures, Random123's Philox known-answer vectors, and the analytic laws of the
 distributions it samples.  The reference itself ships no golden outputs ("parity unpinned")."""
 import ctypes as C
+import os
 import re
 
 import numpy as np
@@ -259,3 +260,89 @@ def test_free_running_distributions(tmp_path):
     leeway = m["molsize"] + 1 - tot
     u = (res.insert_start[m["first_read"]] - m["start"] + rng.uniform(0, 1, len(m))) / (leeway + 1)
     assert stats.kstest(u[ok], "uniform").pvalue > 1e-3
+
+
+# ------------------------------------------------------------------------------------------
+# sequencing-error model (not in the reference: reads there are verbatim copies with constant 'I')
+# ------------------------------------------------------------------------------------------
+def _reads(txt):
+    lines = txt.split(b"\n")
+    return lines[1::4], lines[3::4]
+
+
+def test_error_model_off_is_the_reference_text(tmp_path):
+    """All rates zero = the parity default: identical bytes to a run that never heard of the model."""
+    rng = np.random.default_rng(5)
+    p = os.path.join(str(tmp_path), "e.fa")
+    write_fasta(p, [("chrE", random_bases(rng, 120_000))])
+    kw = dict(coverage=8, attempts=300, singletons=0.2)
+    a = O.mimick_single([p], "haplotagging", seed=3, **kw)
+    b = O.mimick_single([p], "haplotagging", seed=3, error_rate=(0.0, 0.0), indel_error=(0.0, 0.0), **kw)
+    assert a.r1 == b.r1 and a.r2 == b.r2
+    assert set(_reads(a.r1)[1]) == {b"I" * 150}
+
+
+def test_error_model_substitution_rate_and_quality_law(tmp_path):
+    """Substitutions only: the per-cycle mismatch rate against the error-free run follows
+    e(c) = e0 + (e1 - e0) c / (S - 1) (chi-square over 10 cycle bins, alpha = 1e-4), a substituted base never equals the
+    template, and the quality of a cycle is 33 + clamp(round(-10 log10 e(c)) + jitter - 10 [substituted], 2, 41) with
+    jitter in {-2, -1, 0, 0, 0, 0, 1, 2} equally likely (chi-square on the jitter histogram, alpha = 1e-4)."""
+    from scipy import stats
+    rng = np.random.default_rng(6)
+    p = os.path.join(str(tmp_path), "e.fa")
+    write_fasta(p, [("chrE", random_bases(rng, 400_000))])
+    kw = dict(coverage=60, attempts=300, singletons=0.2)
+    e0, e1, S = 0.002, 0.03, 150
+    clean = O.mimick_single([p], "haplotagging", seed=11, **kw)
+    noisy = O.mimick_single([p], "haplotagging", seed=11, error_rate=(e0, e1), **kw)
+    for rd, (ct, nt) in enumerate(((clean.r1, noisy.r1), (clean.r2, noisy.r2)), start=1):
+        cs, _ = _reads(ct)
+        ns, nq = _reads(nt)
+        assert len(cs) == len(ns) > 50_000
+        A = np.frombuffer(b"".join(cs), dtype=np.uint8).reshape(-1, S)
+        B = np.frombuffer(b"".join(ns), dtype=np.uint8).reshape(-1, S)
+        Q = np.frombuffer(b"".join(nq), dtype=np.uint8).reshape(-1, S).astype(int) - 33
+        mism = A != B
+        n = A.shape[0]
+        exp_rate = e0 + (e1 - e0) * np.arange(S) / (S - 1)
+        # thresholds are floor(e * 2^24) / 2^24: indistinguishable from e at this sample size
+        obs = mism.sum(axis=0).reshape(10, 15).sum(axis=1)
+        exp = (exp_rate * n).reshape(10, 15).sum(axis=1)
+        chi = ((obs - exp) ** 2 / exp).sum()
+        assert chi < stats.chi2.ppf(1 - 1e-4, 10), (rd, chi, obs, exp)
+        # quality law
+        qb = np.clip(np.floor(-10 * np.log10(np.maximum(exp_rate, 1e-4)) + 0.5).astype(int), 2, 40)
+        jit = Q - qb[None, :] + 10 * mism
+        inner = (qb[None, :] - 12 >= 2) & (qb[None, :] + 2 <= 41)  # clamps cannot bite
+        vals, counts = np.unique(jit[np.broadcast_to(inner, jit.shape)], return_counts=True)
+        assert set(vals.tolist()) <= {-2, -1, 0, 1, 2}
+        h = dict(zip(vals.tolist(), counts.tolist()))
+        tot = sum(h.values())
+        want = {-2: 1 / 8, -1: 1 / 8, 0: 4 / 8, 1: 1 / 8, 2: 1 / 8}
+        chi = sum((h.get(k, 0) - tot * w) ** 2 / (tot * w) for k, w in want.items())
+        assert chi < stats.chi2.ppf(1 - 1e-4, 4), (rd, chi, h)
+        assert Q.min() >= 2 and Q.max() <= 41
+
+
+def test_error_model_indels_shift_the_template(tmp_path):
+    """Insertions and deletions only: read length stays S, a read without an event equals the clean read, the share of
+    touched reads is 1 - (1 - pi - pd)^S within 4 sigma, and after the first event the read follows the template
+    shifted by the net indel length."""
+    rng = np.random.default_rng(7)
+    p = os.path.join(str(tmp_path), "e.fa")
+    write_fasta(p, [("chrE", random_bases(rng, 300_000))])
+    kw = dict(coverage=40, attempts=300, singletons=0.2)
+    pi, pd, S = 0.002, 0.003, 150
+    clean = O.mimick_single([p], "stlfr", seed=12, **kw)
+    noisy = O.mimick_single([p], "stlfr", seed=12, indel_error=(pi, pd), **kw)
+    cs, _ = _reads(clean.r2)
+    ns, nq = _reads(noisy.r2)
+    assert all(len(x) == S for x in ns) and all(len(x) == S for x in nq)
+    touched = sum(1 for a, b in zip(cs, ns) if a != b)
+    n = len(cs)
+    # a read can be touched without changing (an insertion of the base that follows, ...): the observed share is a bit lower
+    p_any = 1 - (1 - pi - pd) ** S
+    assert 0.6 * p_any * n < touched < p_any * n + 4 * (n * p_any * (1 - p_any)) ** 0.5
+    # quality drops by 10 exactly where something was inserted (no substitutions here)
+    ins_marks = sum(q.count(bytes([33 + 23 - 10 + j])) for q in nq[:2000] for j in (-2, -1, 0, 1, 2))
+    assert ins_marks > 0

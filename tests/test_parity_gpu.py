@@ -610,3 +610,57 @@ def test_placement_paths_agree_with_the_oracle(tmp_path, kw):
             alt = gpu_single([p1, p2], "haplotagging", 31, variates=False, **okw)
         assert alt["r1"] == gpu["r1"] and alt["r2"] == gpu["r2"], env
         assert np.array_equal(alt["ins"][0], gpu["ins"][0]) and np.array_equal(alt["ins"][1], gpu["ins"][1]), env
+
+
+# ------------------------------------------------------------------------------------------
+# sequencing-error model: optional, default off; byte parity with the oracle's definition
+# ------------------------------------------------------------------------------------------
+ERR = dict(error_rate=(0.002, 0.02), indel_error=(0.001, 0.0015))
+
+
+def _err_case(fastas, fmt, seed, **kw):
+    gpu = gpu_single(fastas, fmt, seed, variates=False, **kw)
+    orc = O.mimick_single(fastas, fmt, seed=seed, **{k: v for k, v in kw.items() if k != "force_generic"})
+    compare(gpu, orc, f"{fmt} error model")
+    return gpu, orc
+
+
+@pytest.mark.parametrize("fmt", ["haplotagging", "10x", "standard:stlfr"])
+def test_error_model_matches_the_oracle(tmp_path, fmt):
+    """Fast path (k_emit_w's error variant): substitutions, insertions, deletions and per-cycle qualities equal the
+    oracle's erroneous_read byte for byte; the text really differs from the error-free run."""
+    rng = np.random.default_rng(21)
+    p1 = os.path.join(str(tmp_path), "a.fa")
+    p2 = os.path.join(str(tmp_path), "b.fa")
+    write_fasta(p1, [("chrA", random_bases(rng, 400_000)), ("chrB", random_bases(rng, 90_000))])
+    write_fasta(p2, [("chrA", random_bases(rng, 400_100)), ("chrB", random_bases(rng, 89_000))])
+    kw = dict(coverage=12, attempts=300, singletons=0.2)
+    gpu, _ = _err_case([p1, p2], fmt, 17, **kw, **ERR)
+    clean = gpu_single([p1, p2], fmt, 17, variates=False, **kw)
+    assert len(clean["r1"]) == len(gpu["r1"]) and clean["r1"] != gpu["r1"]
+    quals = set(gpu["r2"].split(b"\n")[3::4])
+    assert len(quals) > 100  # qualities vary per cycle
+    # the general writer applies the same model
+    alt = gpu_single([p1, p2], fmt, 17, variates=False, force_generic=True, **kw, **ERR)
+    assert alt["r1"] == gpu["r1"] and alt["r2"] == gpu["r2"]
+
+
+@pytest.mark.parametrize("strict", [False, True])
+def test_error_model_circular_and_iupac(tmp_path, strict):
+    """Reads near the contig ends (clamped, or modular with strict_wrap), tiles that take the general writer, and a
+    4-bit reference with IUPAC symbols (substitutions leave them alone)."""
+    rng = np.random.default_rng(22)
+    p = os.path.join(str(tmp_path), "circ.fa")
+    seq = bytearray(random_bases(rng, 120_000))
+    for i in rng.integers(0, len(seq), size=300):
+        seq[i] = b"RYKMSWN"[i % 7]
+    write_fasta(p, [("plasmid", bytes(seq))])
+    _err_case([p], "stlfr", 9, coverage=30, circular=True, strict_wrap=strict, mol_length=30000, attempts=300, singletons=0.0, **ERR)
+
+
+def test_error_rates_are_validated():
+    import mimick_b200 as M
+    with pytest.raises(M.MimickError):
+        M.Simulator("haplotagging", seed=1, error_rate=(0.4, 0.4), indel_error=(0.1, 0.1))
+    with pytest.raises(M.MimickError):
+        M.Simulator("haplotagging", seed=1, error_rate=(-0.1, 0.0))
