@@ -2,8 +2,9 @@
 # MimickLinkedReads.jl (src/Main.jl:24 and :88) and their keyword surface verbatim.
 #
 # NOT EXECUTED IN THIS REPOSITORY'S CI: Julia is not installed in the build image (SURVEY.md D8).
-# It mirrors, call for call, mimick_b200/api.py, which is what the tests drive.  Output is
-# uncompressed FASTQ (`.fq`); wrap the two `open(..., "w")` in BGZFWriter for the reference's `.fq.gz`.
+# It mirrors, call for call, mimick_b200/api.py, which is what the tests drive.  Output files are the
+# reference's `<prefix>.R{1,2}.fq.gz`: blocked gzip (BGZF) members coded on the device and written as they
+# arrive, closed by the end-of-file member (`simulate_to(...; bgzf=false)` writes plain text instead).
 module MimickB200
 
 export mimick
@@ -33,6 +34,10 @@ mutable struct Params
     force_generic::Int32
     max_chunk_bytes::UInt64
     plan_batch_groups::Int64
+    err_sub_start::Float64   # optional sequencing-error model (all zero = off: the reference has none)
+    err_sub_end::Float64
+    err_ins::Float64
+    err_del::Float64
     Params() = new()
 end
 

@@ -686,7 +686,7 @@ __global__ void k_mol_text(SimConst sc, const SchemaDev *__restrict__ sch, uint6
     const uint32_t molsize = r.size;
     // header text: "@chrom:hap|start:end|" then the format's tail with read digit '1'; assembled in a
     // thread-local buffer and written with 16-byte stores
-    uint8_t buf[208];
+    uint8_t buf[256];  // prefix <= 200 (mmk_place) + tail <= 34, rounded up to the 16-byte stores below
     uint8_t *p = buf;
     *p++ = '@';
     for (int k = 0; k < S.name_len; ++k) *p++ = (uint8_t)S.name[k];
@@ -965,43 +965,31 @@ void emit(const EmitArgs &a, cudaStream_t st) {
         cudaFuncSetAttribute(k_emit<4, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         cudaFuncSetAttribute(k_emit<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         cudaFuncSetAttribute(k_emit<4, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(k_emit_w<2, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(k_emit_w<2, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(k_emit_w<4, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(k_emit_w<2, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        cudaFuncSetAttribute(k_emit_w<4, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_emit_w<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_emit_w<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_emit_w<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        cudaFuncSetAttribute(k_emit_w<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         attr_set[dev & 63] = true;
     }
-    // 32-pair tiles: autonomous warps, stage fill by bulk copy (MMK_EMIT_MODE=cta keeps the CTA-synchronous kernel)
-    static const bool warp_mode = !(getenv("MMK_EMIT_MODE") && strcmp(getenv("MMK_EMIT_MODE"), "cta") == 0);
-    if (a.tile_pairs == 32 && a.qfill && (warp_mode || a.err_on)) {
+    // 32-pair tiles: k_emit_w (stage fill by bulk copy); MMK_EMIT_MODE=cta keeps k_emit (fill by shared-memory stores)
+    static const bool fill_by_copy = !(getenv("MMK_EMIT_MODE") && strcmp(getenv("MMK_EMIT_MODE"), "cta") == 0);
+    if (a.tile_pairs == 32 && a.qfill && (fill_by_copy || a.err_on)) {
         if (a.err_on) {  // the error model's variant: the plain kernels keep their instruction count
-            if (a.bpb == 2) LAUNCH((k_emit_w<2, true, 1>), a.n_tiles, 128, smem, st, a);
-            else LAUNCH((k_emit_w<4, true, 1>), a.n_tiles, 128, smem, st, a);
-        } else if (a.bpb == 2) {
-            static const bool ilp1 = getenv("MMK_EMIT_ILP") && atoi(getenv("MMK_EMIT_ILP")) == 1;  // (profiling) one pair per pass
-            if (ilp1) LAUNCH((k_emit_w<2, false, 1>), a.n_tiles, 128, smem, st, a);
-            else LAUNCH((k_emit_w<2, false, 2>), a.n_tiles, 128, smem, st, a);
-        } else LAUNCH((k_emit_w<4, false, 1>), a.n_tiles, 128, smem, st, a);
+            if (a.bpb == 2) LAUNCH((k_emit_w<2, true>), a.n_tiles, 128, smem, st, a);
+            else LAUNCH((k_emit_w<4, true>), a.n_tiles, 128, smem, st, a);
+        } else if (a.bpb == 2) LAUNCH((k_emit_w<2, false>), a.n_tiles, 128, smem, st, a);
+        else LAUNCH((k_emit_w<4, false>), a.n_tiles, 128, smem, st, a);
         return;
     }
-    if (a.err_on) {  // other tile sizes: every record through the general writer, which applies the model
-        EmitArgs b = a;
-        b.fast_ok = 0;
-        if (a.tile_pairs > 32) {
-            if (a.bpb == 2) LAUNCH((k_emit<2, 256>), a.n_tiles, 256, smem, st, b);
-            else LAUNCH((k_emit<4, 256>), a.n_tiles, 256, smem, st, b);
-        } else if (a.bpb == 2) LAUNCH((k_emit<2, 128>), a.n_tiles, 128, smem, st, b);
-        else LAUNCH((k_emit<4, 128>), a.n_tiles, 128, smem, st, b);
-        return;
-    }
+    EmitArgs b = a;
+    if (a.err_on) b.fast_ok = 0;  // other tile sizes: every record through the general writer, which applies the model
     // one thread per (pair, header piece): 64-pair tiles run 256 threads, 32-pair tiles 128
     if (a.tile_pairs > 32) {
-        if (a.bpb == 2) LAUNCH((k_emit<2, 256>), a.n_tiles, 256, smem, st, a);
-        else LAUNCH((k_emit<4, 256>), a.n_tiles, 256, smem, st, a);
+        if (a.bpb == 2) LAUNCH((k_emit<2, 256>), a.n_tiles, 256, smem, st, b);
+        else LAUNCH((k_emit<4, 256>), a.n_tiles, 256, smem, st, b);
     } else {
-        if (a.bpb == 2) LAUNCH((k_emit<2, 128>), a.n_tiles, 128, smem, st, a);
-        else LAUNCH((k_emit<4, 128>), a.n_tiles, 128, smem, st, a);
+        if (a.bpb == 2) LAUNCH((k_emit<2, 128>), a.n_tiles, 128, smem, st, b);
+        else LAUNCH((k_emit<4, 128>), a.n_tiles, 128, smem, st, b);
     }
 }
 

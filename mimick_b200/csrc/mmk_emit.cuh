@@ -300,12 +300,6 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
 __device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) {
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-// the same stores without the compiler-level memory barrier: the stage is only touched through volatile asm statements,
-// whose mutual order is kept, so loads and arithmetic of a second read pair may be scheduled across them (k_emit_w)
-__device__ __forceinline__ void sts128_nb(uint32_t addr, const uint4 &v) {
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
-}
-__device__ __forceinline__ void sts8_nb(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v)); }
 __device__ __forceinline__ uint32_t lds8(uint32_t addr) {
     uint32_t v;
     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
@@ -402,49 +396,6 @@ __device__ __forceinline__ void emit_pair_seq(const EmitArgs &a, const uint2 rde
         const uint32_t val = (hl == 0 || hl == 2 || hl == 15) ? '\n' : (hl == 1 ? '+' : 'I');
         sts8(smem + addr, val);
     }
-}
-
-// Two read pairs per pass (k_emit_w): the two bodies share no data, so their shuffles, permutes and stores interleave
-// and a warp has twice the independent work in flight.
-struct SeqChunk {
-    uint4 v;
-    uint32_t addr, seq_end, rec_end;
-    bool store;
-};
-__device__ __forceinline__ SeqChunk seq_chunk(const EmitArgs &a, const uint2 rdesc, uint32_t W, uint32_t lane) {
-    const uint32_t half = lane >> 4, hl = lane & 15u;
-    const uint32_t inl = half ? 0u : (uint32_t)a.bclen_inline;
-    const uint32_t S = half ? (uint32_t)a.r2 : (uint32_t)a.r1;
-    const uint32_t seq_off = rdesc.x & 0xfffffu;
-    const int rel = (int)(rdesc.x >> 20);
-    SeqChunk r;
-    r.seq_end = seq_off + S;
-    r.rec_end = r.seq_end + 3u + S + inl + 1u;
-    const uint32_t c = (seq_off >> 4) + hl;
-    const int k0 = (int)(16u * c) - (int)seq_off;
-    const int q = half ? rel + k0 : rel + (int)S - 16 - k0;
-    const int j = q >> 4;
-    const uint32_t sh = ((uint32_t)q & 15u) * 2u;
-    uint32_t lo = __shfl_sync(0xffffffffu, W, (int)((lane & 16u) | ((uint32_t)j & 15u)));
-    const uint32_t hi = __shfl_sync(0xffffffffu, W, (int)((lane & 16u) | ((uint32_t)(j + 1) & 15u)));
-    if (j < 0) lo = 0;
-    uint32_t bits = __funnelshift_r(lo, hi, sh);
-    if (!half) bits = __brev(bits);
-    r.v = expand16(bits, half ? 0x54474341u /* "ACGT" */ : 0x41474354u /* "TCGA" */);
-    r.addr = 16u * c;
-    r.store = 16u * c < r.seq_end;
-    return r;
-}
-__device__ __forceinline__ void emit_pair_seq2(const EmitArgs &a, const uint2 rdA, uint32_t WA, const uint2 rdB, uint32_t WB, bool haveB,
-                                               uint32_t smem, uint32_t lane) {
-    const uint32_t hl = lane & 15u;
-    const SeqChunk A = seq_chunk(a, rdA, WA, lane), B = seq_chunk(a, rdB, WB, lane);
-    if (A.store) sts128_nb(smem + A.addr, A.v);
-    if (B.store && haveB) sts128_nb(smem + B.addr, B.v);
-    __syncwarp();
-    const uint32_t val = (hl == 0 || hl == 2 || hl == 15) ? '\n' : (hl == 1 ? '+' : 'I');
-    sts8_nb(smem + (hl < 15 ? A.seq_end + hl : A.rec_end - 1u), val);
-    if (haveB) sts8_nb(smem + (hl < 15 ? B.seq_end + hl : B.rec_end - 1u), val);
 }
 
 // 8 bases of a 4-bit word (BioSequences one-hot codes A=1 C=2 G=4 T=8) → 8 ASCII bytes; false if any of
@@ -728,17 +679,17 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_emit(const __grid_c
 
 
 // ------------------------------------------------------------------------------------------
-// k_emit_w — the same fast path with autonomous warps (32-pair tiles, 4 warps, 8 consecutive pairs each)
+// k_emit_w — the fast path of 32-pair tiles with the stage filled by the copy engine (the default emit kernel)
 // ------------------------------------------------------------------------------------------
-// What differs from k_emit:
-//   * the quality character arrives in both stages by ONE bulk asynchronous copy (TMA, global -> shared, from an
-//     L2-resident buffer of 'I'), issued by thread 0 before anything else and awaited on an mbarrier: no fill loop, no
-//     shared-memory store wavefronts for 40 % of the text;
-//   * every warp loads the tile's 32 descriptors and scans the record lengths itself, then owns pairs [8w, 8w + 8):
-//     sequences, headers and the copy-out of that sub-range (its own bulk store + edge bytes).  After the barrier that
-//     publishes the mbarrier there is no CTA-wide synchronisation: a warp waiting on memory stalls nobody else.
-//   * header bytes: four lanes per pair — text pieces as 32-bit words of the molecule's header text (funnel-shifted for
-//     the format tail), the two decimal numbers split in a low and a high half.
+// Same phases as k_emit, three differences:
+//   * the quality character arrives in both stages by ONE bulk asynchronous copy (TMA: cp.async.bulk global -> shared from
+//     an L2-resident buffer of 'I', completion on an mbarrier), issued by thread 0 before anything else: no fill loop, a
+//     third of the shared-memory store wavefronts gone;
+//   * a warp has the reference words of all its 8 pairs in flight before its first pass (2-bit references);
+//   * ERR: the optional sequencing-error model rewrites the bases and qualities of every read (err_read_warp) — a template
+//     variant, so the plain kernel keeps its instruction count.
+// Measured (profiles/r02_summary.md): the same time per step as k_emit; variants with autonomous warps, per-warp copy-out,
+// two pairs per pass, look-ahead L2 prefetch and persistent CTAs with two stage sets were all equal or slower.
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -765,68 +716,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
         : "memory");
 }
 
-// header bytes of the warp's 8 pairs, 4 lanes per pair
-__device__ __forceinline__ void emit_headers_warp(const EmitArgs &a, const uint4 *s_fa, const uint2 *s_fb, uint32_t smem, uint32_t t, uint32_t sub) {
-    const FastDesc f = load_fast_desc(s_fa, s_fb, t);
-    const uint32_t P = FD_P(f.pk), SUF = FD_SUF(f.pk), d1 = FD_D1(f.pk), d2 = FD_D2(f.pk);
-    const uint8_t *tx = a.text + (uint64_t)f.mol * a.text_stride;
-    const uint32_t *tw = reinterpret_cast<const uint32_t *>(tx);
-    const uint32_t s1 = smem + f.sb1, s2 = smem + f.sb2;
-    // "@chrom:hap|start:end|": word w of the text, lanes take words sub, sub + 4, ...
-    for (uint32_t w = sub; 4u * w < P; w += 4u) {
-        uint32_t x = __ldg(tw + w);
-#pragma unroll
-        for (uint32_t b = 0; b < 4; ++b) {
-            if (4u * w + b < P) {
-                sts8(s1 + 4u * w + b, x);
-                sts8(s2 + 4u * w + b, x);
-            }
-            x >>= 8;
-        }
-    }
-    {   // format tail (starts at text byte P: two words funnel-shifted); the read digit of R2 is patched below
-        const uint32_t o = P + d1 + 1u + d2, w0 = P >> 2, sh = (P & 3u) * 8u;
-        for (uint32_t w = sub; 4u * w < SUF; w += 4u) {
-            uint32_t x = __funnelshift_r(__ldg(tw + w0 + w), __ldg(tw + w0 + w + 1u), sh);
-#pragma unroll
-            for (uint32_t b = 0; b < 4; ++b) {
-                const uint32_t i = 4u * w + b;
-                if (i < SUF) {
-                    sts8(s1 + o + i, x);
-                    sts8(s2 + o + i, x);
-                }
-                x >>= 8;
-            }
-        }
-        for (uint32_t i = sub; i < (uint32_t)a.bclen_inline; i += 4u) sts8(s1 + o + SUF + i, __ldg(tx + P + 1u + i));  // 10x: barcode before the R1 read
-    }
-    {   // decimal insert breakpoints: lanes 0/1 the low / high five digits of bstart, lanes 2/3 those of bend
-        const uint32_t v = (sub & 2u) ? f.bend : f.bstart, D = (sub & 2u) ? d2 : d1, o = (sub & 2u) ? P + d1 + 1u : P;
-        const uint32_t hi = v / 100000u, lo = v - hi * 100000u;
-        uint32_t x = (sub & 1u) ? hi : lo;
-        uint32_t n = (sub & 1u) ? (D > 5u ? D - 5u : 0u) : (D < 5u ? D : 5u);
-        uint32_t pos = (sub & 1u) ? o + n : o + D;  // one past the last digit this lane writes
-        while (n--) {
-            const uint32_t q = __umulhi(x, 0xCCCCCCCDu) >> 3;
-            const uint32_t ch = '0' + (x - 10u * q);
-            --pos;
-            sts8(s1 + pos, ch);
-            sts8(s2 + pos, ch);
-            x = q;
-        }
-        if (sub == 1u) {
-            sts8(s1 + P + d1, ':');
-            sts8(s2 + P + d1, ':');
-        }
-    }
-    __syncwarp(__activemask());
-    if (sub == 0u) {  // R2's read digit, after the lane that wrote the tail's '1'
-        const uint32_t rd_off = (a.fq_format == MMK_FMT_HAPLOTAGGING || a.fq_format == MMK_FMT_STANDARD) ? 1u : SUF - 13u;
-        sts8(s2 + P + d1 + 1u + d2 + rd_off, '2');
-    }
-}
-
-template <int BPB, bool ERR, int ILP>
+template <int BPB, bool ERR>
 __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     __shared__ uint4 s_fa[32];
@@ -834,23 +724,25 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
     __shared__ uint2 s_rd[64];
     __shared__ uint2 s_er[ERR ? 32 : 1];  // error model: first arena word and length of the pair's haplotype
     __shared__ uint32_t s_off1[33], s_off2[33];
-    __shared__ uint32_t s_done;
     __shared__ __align__(8) unsigned long long s_mbar;
     const uint32_t sm = (uint32_t)__cvta_generic_to_shared(smem), mb = (uint32_t)__cvta_generic_to_shared(&s_mbar);
     if (threadIdx.x == 0) {  // the quality character over both stages, by the copy engine
         mbar_init(mb, 1u);
         mbar_expect_tx(mb, 2u * a.stage_cap);
         bulk_load(sm, a.qfill, 2u * a.stage_cap, mb);
-        s_done = 0;
     }
     const uint32_t tile = a.tile0 + blockIdx.x;
     const uint64_t p0 = (uint64_t)tile * 32u;
     const uint32_t np = (uint32_t)((a.n_pairs - p0) < 32u ? (a.n_pairs - p0) : 32u);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // every load of the prologue is independent of the others: one memory latency, not a chain
     const bool fast = a.fast_ok && a.tile_flags[tile];
-    if (warp == 0) {  // descriptors of the whole tile: every load is independent of the others (one memory latency)
+    const uint64_t t1 = a.tile_off1[tile], t2 = a.tile_off2[tile];
+    const uint32_t bytes1 = (uint32_t)(a.tile_off1[tile + 1] - t1), bytes2 = (uint32_t)(a.tile_off2[tile + 1] - t2);
+    const uint64_t g1 = t1 - a.chunk_off1, g2 = t2 - a.chunk_off2;
+    const uint32_t A1 = (uint32_t)(g1 & 15u), A2 = (uint32_t)(g2 & 15u);
+    if (warp == 0) {  // descriptors of the whole tile
         const uint32_t tile_m0 = a.tile_mol0[tile];
-        const uint32_t A1 = (uint32_t)((a.tile_off1[tile] - a.chunk_off1) & 15u), A2 = (uint32_t)((a.tile_off2[tile] - a.chunk_off2) & 15u);
         const bool have = lane < np;
         const uint4 q = have ? a.fdesc[p0 + lane] : make_uint4(1u, 1u, 0u, 0u);
         if (lane < 4 && blockIdx.x + 1184u < a.n_tiles)  // warm L2 for a tile that a later wave of CTAs will run
@@ -889,7 +781,7 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
             }
         }
     }
-    __syncthreads();  // descriptors and the mbarrier are published; nothing below synchronises the CTA on the fast path
+    __syncthreads();  // descriptors and the mbarrier are published
     if (!fast) {
         // general path: every record byte-wise, straight to global memory (warp per pair)
         const uint32_t tile_m0 = a.tile_mol0[tile];
@@ -909,7 +801,7 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
             s_off2[threadIdx.x + 1] = i2 - d.len2;
         }
         __syncthreads();
-        uint8_t *o1 = a.out1 + (a.tile_off1[tile] - a.chunk_off1), *o2 = a.out2 + (a.tile_off2[tile] - a.chunk_off2);
+        uint8_t *o1 = a.out1 + g1, *o2 = a.out2 + g2;
         for (uint32_t t = warp; t < np; t += 4) {
             PairDesc e;
             decode_pair(a, p0 + t, tile_m0, e);
@@ -919,34 +811,23 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
         mbar_wait(mb, 0u);  // the stage must outlive the copy into it
         return;
     }
-    // this warp's pairs [w0, w1)
-    const uint32_t w0 = 8u * warp, w1 = (w0 + 8u < np) ? w0 + 8u : np;
-    if (w0 < w1) {
-        if (BPB == 2 && !ERR && ILP == 2) {  // two pairs per pass; the words of the next two are loaded meanwhile
-            const uint32_t half = lane >> 4, hl = lane & 15u;
-            const uint32_t *hap_lane = a.hap + hl;
-            uint2 rdA = s_rd[2 * w0 + half], rdB = s_rd[2 * (w0 + 1u < w1 ? w0 + 1u : w0) + half];
-            uint32_t WA = __ldg(hap_lane + rdA.y), WB = __ldg(hap_lane + rdB.y);
+    {   // phase 1: warp per pair (t = warp, warp + 4, ...), half-warp per read
+        const uint32_t half = lane >> 4, hl = lane & 15u;
+        const uint32_t *hap_lane = a.hap + hl;
+        if (BPB == 2 && !ERR) {  // the words of all the warp's pairs in flight at once, then the passes
+            uint32_t W[8];
+#pragma unroll
+            for (uint32_t i = 0; i < 8; ++i) W[i] = __ldg(hap_lane + s_rd[2 * (warp + 4u * i < np ? warp + 4u * i : 0u) + half].y);
             mbar_wait(mb, 0u);  // the quality fill has landed
-            for (uint32_t t = w0; t < w1; t += 2u) {
-                const uint32_t ta = t + 2u < w1 ? t + 2u : t, tb = t + 3u < w1 ? t + 3u : ta;
-                const uint2 rnA = s_rd[2 * ta + half], rnB = s_rd[2 * tb + half];
-                const uint32_t WnA = __ldg(hap_lane + rnA.y), WnB = __ldg(hap_lane + rnB.y);
-                emit_pair_seq2(a, rdA, WA, rdB, WB, t + 1u < w1, sm, lane);
-                rdA = rnA;
-                rdB = rnB;
-                WA = WnA;
-                WB = WnB;
-            }
-        } else
-        {   // sequences: the reference words of the next pair are loaded while this one is expanded
-            const uint32_t half = lane >> 4, hl = lane & 15u;
-            const uint32_t *hap_lane = a.hap + hl;
-            uint2 rd = s_rd[2 * w0 + half];
+#pragma unroll
+            for (uint32_t i = 0; i < 8; ++i)
+                if (warp + 4u * i < np) emit_pair_seq(a, s_rd[2 * (warp + 4u * i) + half], W[i], sm, lane);
+        } else {  // the words of the next pair are loaded while this one is expanded
+            uint2 rd = s_rd[2 * (warp < np ? warp : 0) + half];
             uint32_t W0 = __ldg(hap_lane + rd.y), W1 = BPB == 4 ? __ldg(hap_lane + rd.y + 16) : 0u;
-            mbar_wait(mb, 0u);  // the quality fill has landed
-            for (uint32_t t = w0; t < w1; ++t) {
-                const uint32_t tn = t + 1u < w1 ? t + 1u : t;
+            mbar_wait(mb, 0u);
+            for (uint32_t t = warp; t < np; t += 4) {
+                const uint32_t tn = t + 4u < np ? t + 4u : t;
                 const uint2 rn = s_rd[2 * tn + half];
                 const uint32_t W0n = __ldg(hap_lane + rn.y), W1n = BPB == 4 ? __ldg(hap_lane + rn.y + 16) : 0u;
                 if (BPB == 2) emit_pair_seq(a, rd, W0, sm, lane);
@@ -971,33 +852,24 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
                 W1 = W1n;
             }
         }
-        __syncwarp();
-        if (w0 + (lane >> 2) < w1) emit_headers_warp(a, s_fa, s_fb, sm, w0 + (lane >> 2), lane & 3u);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes → visible to the bulk copy
-    } else
-        mbar_wait(mb, 0u);
-    __syncwarp();
-    // the last warp to get here copies the tile out (the others are done: no barrier, nobody waits)
-    uint32_t ticket = 0;
-    if (lane == 0) {
-        __threadfence_block();
-        ticket = atomicAdd(&s_done, 1u);
-        __threadfence_block();
     }
-    ticket = __shfl_sync(0xffffffffu, ticket, 0);
-    if (ticket != 3u) return;
-    const uint64_t g1 = a.tile_off1[tile] - a.chunk_off1, g2 = a.tile_off2[tile] - a.chunk_off2;
-    const uint32_t bytes1 = (uint32_t)(a.tile_off1[tile + 1] - a.tile_off1[tile]), bytes2 = (uint32_t)(a.tile_off2[tile + 1] - a.tile_off2[tile]);
-    const uint32_t A1 = (uint32_t)(g1 & 15u), A2 = (uint32_t)(g2 & 15u);
+    __syncthreads();
+    if (lane < np) {  // phase 2: one header piece per warp, one pair per lane
+        const FastDesc f = load_fast_desc(s_fa, s_fb, lane);
+        const uint32_t rd_off = (a.fq_format == MMK_FMT_HAPLOTAGGING || a.fq_format == MMK_FMT_STANDARD) ? 1u : FD_SUF(f.pk) - 13u;
+        emit_header_piece(a, f, sm, warp, rd_off);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes → visible to the bulk copy
+    __syncthreads();
     uint8_t *gb1 = a.out1 + (g1 - A1), *gb2 = a.out2 + (g2 - A2);
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
         copy_out_bulk(sm, A1, bytes1, gb1);
         copy_out_bulk(sm + a.stage_cap, A2, bytes2, gb2);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    copy_out_edges(sm, A1, bytes1, gb1, lane);
-    copy_out_edges(sm + a.stage_cap, A2, bytes2, gb2, lane);
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // stage must outlive the copy
+    if (warp == 1) copy_out_edges(sm, A1, bytes1, gb1, lane);
+    if (warp == 2) copy_out_edges(sm + a.stage_cap, A2, bytes2, gb2, lane);
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // stage must outlive the copy
 }
 
 }  // namespace mmkdev

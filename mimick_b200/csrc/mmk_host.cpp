@@ -93,6 +93,7 @@ struct mmk_ctx {
     int bpb = 2;
     DBuf<uint32_t> d_hap;
     DBuf<SchemaDev> d_sch;
+    DBuf<char> d_names;  // contig names of the schemas, back to back (SchemaDev::name points here)
     ContigStats *d_stats = nullptr;
     ContigStats *h_stats = nullptr;  // pinned
 
@@ -605,7 +606,7 @@ extern "C" int32_t mmk_add_contig(mmk_ctx *ctx, const char *name, const char *ba
     if (!ctx->st) return fail(ctx, MMK_ERR_STATE, "context was not created successfully");
     if (ctx->multi_mode) return fail(ctx, MMK_ERR_STATE, "contigs cannot be added after variants were applied");
     if (len >= (1ll << 31)) return fail(ctx, MMK_ERR_UNSUPPORTED, "contig %s has >= 2^31 bases", name);
-    if (strlen(name) > 55) return fail(ctx, MMK_ERR_UNSUPPORTED, "contig name longer than 55 characters: %s", name);
+    if (strlen(name) > 160) return fail(ctx, MMK_ERR_UNSUPPORTED, "contig name longer than 160 characters: %s", name);
     if (haplotype < 0 || haplotype > 65535) return fail(ctx, MMK_ERR_INVALID_ARG, "haplotype index out of range");
     if (ctx->contigs.size() >= 65535) return fail(ctx, MMK_ERR_UNSUPPORTED, "more than 65535 (contig, haplotype) units");
     CU(cudaSetDevice(ctx->par.device));
@@ -717,6 +718,11 @@ extern "C" int32_t mmk_clear_contigs(mmk_ctx *ctx) {
 // upload SchemaDev table
 static int32_t upload_schemas(mmk_ctx *ctx) {
     std::vector<SchemaDev> h(ctx->schemas.size());
+    std::string names;
+    for (const Schema &s : ctx->schemas) names += s.name;
+    CU(ctx->d_names.ensure(names.size() + 1));
+    if (!names.empty()) CU(cudaMemcpyAsync(ctx->d_names.p, names.data(), names.size(), cudaMemcpyHostToDevice, ctx->st));
+    size_t off = 0;
     for (size_t i = 0; i < h.size(); ++i) {
         const Schema &s = ctx->schemas[i];
         memset(&h[i], 0, sizeof(SchemaDev));
@@ -724,11 +730,12 @@ static int32_t upload_schemas(mmk_ctx *ctx) {
         h[i].len = (uint32_t)s.len;
         h[i].haplotype = (uint16_t)s.haplotype;
         h[i].name_len = (uint16_t)s.name.size();
-        memcpy(h[i].name, s.name.data(), s.name.size());
+        h[i].name = ctx->d_names.p + off;
+        off += s.name.size();
     }
     CU(ctx->d_sch.ensure(h.size() ? h.size() : 1));
     if (!h.empty()) CU(cudaMemcpyAsync(ctx->d_sch.p, h.data(), h.size() * sizeof(SchemaDev), cudaMemcpyHostToDevice, ctx->st));
-    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaStreamSynchronize(ctx->st));  // `h` and `names` are host temporaries
     return MMK_OK;
 }
 

@@ -46,12 +46,12 @@ static_assert(sizeof(InsTable) % 16 == 0, "InsTable is staged with 16-byte copie
 // One (contig, haplotype) unit as the kernels see it.
 struct SchemaDev {
     uint64_t word_off;  // first 32-bit word of the packed haplotype in the arena
+    const char *name;   // contig name (device memory, not terminated; the names of all schemas share one buffer)
     uint32_t len;       // bases
     uint16_t haplotype;
     uint16_t name_len;
-    char name[56];
 };
-static_assert(sizeof(SchemaDev) == 72, "SchemaDev layout");
+static_assert(sizeof(SchemaDev) == 24, "SchemaDev layout");
 
 // Per-molecule record written by the placement kernel, read by the emit kernel.
 struct MolRec {

@@ -349,7 +349,10 @@ __global__ void __launch_bounds__(PB_THREADS, 4) k_place_block(const __grid_cons
             uint32_t remaining = (uint32_t)((uint64_t)molsize + 1u - isum), cursor = 0;
             uint2 bits = s_bits[s0];
             uint32_t len = s_len[s0];
-            for (uint32_t k = 0; k < nfrags; ++k) {
+            uint32_t k = 0;
+            // Every gap is uniform on 0..remaining, so the leeway roughly halves per insert and is used up after ~log2(leeway)
+            // of them: from there on every gap is mulhi64(bits, 1) = 0 and the offsets are a running sum of the lengths.
+            for (; k < nfrags && remaining != 0u; ++k) {
                 const uint32_t kn = k + 1u < nfrags ? k + 1u : k;  // next step's operands do not depend on the chain
                 const uint2 nbits = s_bits[s0 + kn];
                 const uint32_t nlen = s_len[s0 + kn];
@@ -365,6 +368,12 @@ __global__ void __launch_bounds__(PB_THREADS, 4) k_place_block(const __grid_cons
                 if (so + len < need_end) status = MMK_ERR_BOUNDS;
                 bits = nbits;
                 len = nlen;
+            }
+            for (; k < nfrags; ++k) {  // no leeway left: back to back
+                const uint32_t l = s_len[s0 + k];
+                s_bits[s0 + k].x = cursor;
+                cursor += l;
+                if (cursor < need_end) status = MMK_ERR_BOUNDS;
             }
             if (!status) first_read_quals(sc, (int64_t)start, s_bits[s0].x, s_len[s0], n_hap, q1, q2);
         }

@@ -1,0 +1,14 @@
+set -x
+python -m pytest tests/test_parity_gpu.py -m gpu -x -q -k "ci_single or circular or c1_multi or formats or placement" > gpurun_out/r2_pytest15.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2_pytest15.log
+tail -6 gpurun_out/r2_pytest15.log
+for v in "MMK_EMIT_MODE=persistent"; do
+  env $v timeout 300 python bench.py --steps 5 --warmup 3 --e2e-steps 0 --no-cpu > gpurun_out/r2_bench15_tmp.json 2> gpurun_out/r2_bench15_tmp.err
+  python -c "
+import json
+d=json.load(open('gpurun_out/r2_bench15_tmp.json')); print('RES $v', d['ms_per_step'], d['phase_ms_per_step'], d['roofline']['frac'])
+"
+done
+export MMK_PROFILE_BGZF=0
+timeout 300 python scripts/profile_step.py 0.1 > gpurun_out/r2_ps15_plain.log 2>&1 && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_emit_p" -c 1 -o gpurun_out/r2_new15 python scripts/profile_step.py 0.1 > gpurun_out/r2_ncu15.log 2>&1
+cat gpurun_out/r2_ps15_plain.log

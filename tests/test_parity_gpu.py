@@ -664,3 +664,19 @@ def test_error_rates_are_validated():
         M.Simulator("haplotagging", seed=1, error_rate=(0.4, 0.4), indel_error=(0.1, 0.1))
     with pytest.raises(M.MimickError):
         M.Simulator("haplotagging", seed=1, error_rate=(-0.1, 0.0))
+
+
+def test_long_contig_names(tmp_path):
+    """Assembly-style contig names: 120 characters (records go through the general writer: header prefix > 64 bytes) next
+    to a short one; the reference has no limit, the library's is 160."""
+    import mimick_b200 as M
+    rng = np.random.default_rng(31)
+    p = os.path.join(str(tmp_path), "long.fa")
+    long_name = "scaffold_" + "x" * 99 + "_pilon_pilon"
+    assert len(long_name) == 120
+    write_fasta(p, [(long_name + " some description", random_bases(rng, 60_000)), ("ctg2", random_bases(rng, 50_000))])
+    gpu, _ = check_single([p], "tellseq", seed=4, coverage=6, **CLI)
+    assert (b"@" + long_name.encode() + b":1|") in gpu["r1"]
+    with M.Simulator("tellseq", seed=1) as sim:
+        with pytest.raises(M.MimickError):
+            sim.add_contig("y" * 161, b"ACGT" * 1000, 1)
