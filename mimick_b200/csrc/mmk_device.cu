@@ -674,50 +674,59 @@ __device__ __forceinline__ void place_chain_one(const SimConst &sc, const Schema
     mol[i] = r;
 }
 
-// Placement, step 3 — one thread per molecule: the header text every record of the molecule shares.
-__global__ void k_mol_text(SimConst sc, const SchemaDev *__restrict__ sch, uint64_t mol0, uint32_t m_lo, uint32_t m_hi, MolRec *mol,
-                           uint8_t *text, uint32_t text_stride) {
-    uint32_t i = m_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m_hi) return;
-    const uint64_t gi = mol0 + i;
-    MolRec r = mol[i];
-    const SchemaDev &S = sch[r.schema];
-    const int64_t start = r.start;
-    const uint32_t molsize = r.size;
-    // header text: "@chrom:hap|start:end|" then the format's tail with read digit '1'; assembled in a
-    // thread-local buffer and written with 16-byte stores
-    uint8_t buf[256];  // prefix <= 200 (mmk_place) + tail <= 34, rounded up to the 16-byte stores below
-    uint8_t *p = buf;
-    *p++ = '@';
-    for (int k = 0; k < S.name_len; ++k) *p++ = (uint8_t)S.name[k];
-    *p++ = ':';
-    p = put_dec(p, S.haplotype);
-    *p++ = '|';
-    p = put_dec(p, (uint64_t)start);
-    *p++ = ':';
-    p = put_dec(p, (uint64_t)(start + molsize));
-    *p++ = '|';
-    uint32_t plen = (uint32_t)(p - buf);
-    uint8_t *sp = p;
-    switch (sc.fq_format) {
-    case MMK_FMT_STLFR: *p++ = '#'; p = put_barcode(p, sc.bc_format, gi); p = put_str(p, " 1:N:0:ATGACA\n"); break;
-    case MMK_FMT_HAPLOTAGGING: p = put_str(p, "/1\tBX:Z:"); p = put_barcode(p, sc.bc_format, gi); *p++ = '\n'; break;
-    case MMK_FMT_TELLSEQ: *p++ = ':'; p = put_barcode(p, sc.bc_format, gi); p = put_str(p, " 1:N:0:ATGACA\n"); break;
-    case MMK_FMT_TENX: *p++ = '|'; p = put_barcode(p, sc.bc_format, gi); p = put_str(p, " 1:N:0:ATGACA\n"); break;
-    default: p = put_str(p, "/1\tVX:i:1\tBX:Z:"); p = put_barcode(p, sc.bc_format, gi); *p++ = '\n'; break;
-    }
-    {
-        uint4 *dst = reinterpret_cast<uint4 *>(text + (uint64_t)i * text_stride);
-        const uint32_t nb = (uint32_t)(p - buf);
-        for (uint32_t o = 0; o < nb; o += 16) {
-            uint4 v;
-            memcpy(&v, buf + o, 16);
-            dst[o >> 4] = v;
+// Placement, step 3 — one thread per molecule: the header text every record of the molecule shares.  A thread builds
+// its text in its own shared-memory row (row stride = text_stride + 4 bytes: an odd number of words, so the byte stores of
+// a warp spread over the banks); the block then copies its rows — contiguous in global memory — with 16-byte stores.
+constexpr uint32_t TEXT_THREADS = 128;
+__global__ void __launch_bounds__(TEXT_THREADS) k_mol_text(SimConst sc, const SchemaDev *__restrict__ sch, uint64_t mol0, uint32_t m_lo, uint32_t m_hi,
+                                                           MolRec *mol, uint8_t *text, uint32_t text_stride) {
+    extern __shared__ __align__(16) uint8_t s_rows[];
+    __shared__ uint32_t s_nb[TEXT_THREADS];
+    const uint32_t row_stride = text_stride + 4u;
+    const uint32_t i0 = m_lo + blockIdx.x * TEXT_THREADS, i = i0 + threadIdx.x;
+    s_nb[threadIdx.x] = 0;
+    if (i < m_hi) {
+        const uint64_t gi = mol0 + i;
+        MolRec r = mol[i];
+        const SchemaDev &S = sch[r.schema];
+        const int64_t start = r.start;
+        const uint32_t molsize = r.size;
+        // "@chrom:hap|start:end|" then the format's tail with read digit '1'
+        uint8_t *buf = s_rows + (size_t)threadIdx.x * row_stride;
+        uint8_t *p = buf;
+        *p++ = '@';
+        for (int k = 0; k < S.name_len; ++k) *p++ = (uint8_t)S.name[k];
+        *p++ = ':';
+        p = put_dec(p, S.haplotype);
+        *p++ = '|';
+        p = put_dec(p, (uint64_t)start);
+        *p++ = ':';
+        p = put_dec(p, (uint64_t)(start + molsize));
+        *p++ = '|';
+        const uint32_t plen = (uint32_t)(p - buf);
+        uint8_t *sp = p;
+        switch (sc.fq_format) {
+        case MMK_FMT_STLFR: *p++ = '#'; p = put_barcode(p, sc.bc_format, gi); p = put_str(p, " 1:N:0:ATGACA\n"); break;
+        case MMK_FMT_HAPLOTAGGING: p = put_str(p, "/1\tBX:Z:"); p = put_barcode(p, sc.bc_format, gi); *p++ = '\n'; break;
+        case MMK_FMT_TELLSEQ: *p++ = ':'; p = put_barcode(p, sc.bc_format, gi); p = put_str(p, " 1:N:0:ATGACA\n"); break;
+        case MMK_FMT_TENX: *p++ = '|'; p = put_barcode(p, sc.bc_format, gi); p = put_str(p, " 1:N:0:ATGACA\n"); break;
+        default: p = put_str(p, "/1\tVX:i:1\tBX:Z:"); p = put_barcode(p, sc.bc_format, gi); *p++ = '\n'; break;
         }
+        s_nb[threadIdx.x] = (uint32_t)(p - buf);
+        r.prefix_len = (uint8_t)plen;
+        r.suffix_len = (uint8_t)(p - sp);
+        mol[i] = r;
     }
-    r.prefix_len = (uint8_t)plen;
-    r.suffix_len = (uint8_t)(p - sp);
-    mol[i] = r;
+    __syncthreads();
+    // the block's rows are contiguous in `text`: 16-byte chunk c of the block lies in row 16 c / text_stride (a multiple of 16)
+    const uint32_t chunks_per_row = text_stride >> 4, n_rows = min(TEXT_THREADS, m_hi - i0);
+    uint4 *dst = reinterpret_cast<uint4 *>(text + (uint64_t)i0 * text_stride);
+    for (uint32_t c = threadIdx.x; c < n_rows * chunks_per_row; c += TEXT_THREADS) {
+        const uint32_t row = c / chunks_per_row, off = (c - row * chunks_per_row) << 4;
+        if (off >= s_nb[row]) continue;  // past the text: those bytes are never read
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(s_rows + (size_t)row * row_stride + off);
+        dst[c] = make_uint4(src[0], src[1], src[2], src[3]);
+    }
 }
 
 void place_prepare(uint64_t mol0, uint32_t n_mol, const uint64_t *d_read_off_global, uint64_t *d_read_off_local,
@@ -798,7 +807,7 @@ void place_segment_chain(const SimConst &sc, const SchemaDev *d_sch, PlanDev pla
     const uint32_t nm = m_hi - m_lo;
     LAUNCH(k_place_chain, (nm + PLACE_BLOCK - 1) / PLACE_BLOCK, 256, 0, st, sc, d_sch, plan, mol0, m_lo, m_hi, d_read_off_local,
            pair_lo, (PairTmp *)d_tmp, d_acc_i, d_ins, d_mol, d_err);
-    LAUNCH(k_mol_text, (nm + 127) / 128, 128, 0, st, sc, d_sch, mol0, m_lo, m_hi, d_mol, d_text, text_stride);
+    LAUNCH(k_mol_text, (nm + TEXT_THREADS - 1) / TEXT_THREADS, TEXT_THREADS, (size_t)TEXT_THREADS * (text_stride + 4u), st, sc, d_sch, mol0, m_lo, m_hi, d_mol, d_text, text_stride);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -812,7 +821,7 @@ uint32_t place_big_cap(uint64_t n_pairs) { return (uint32_t)(n_pairs / PB_BIG + 
 bool place_block_supports(const SimConst &sc) { return (double)sc.insert_length + 9.0 * sc.ins_sd < 65000.0; }
 
 void place_block(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint64_t n_pairs,
-                 uint32_t n_tiles, const uint64_t *d_roff_l, uint32_t *d_tile_mol0, const InsTable *d_tab, uint2 *d_ins, MolRec *d_mol,
+                 uint32_t n_tiles, const uint64_t *d_roff_l, uint32_t *d_tile_mol0, const InsTable *d_tab, MolRec *d_mol,
                  uint8_t *d_text, uint32_t text_stride, uint4 *d_fdesc, uint32_t *d_sum1, uint32_t *d_sum2, uint8_t *d_tile_flags,
                  unsigned long long *d_gather, unsigned long long *d_err, uint32_t *d_weight, uint64_t *d_woff, uint64_t *d_scan_tmp,
                  uint32_t *d_blk, uint32_t *d_big_list, uint32_t *d_big_count, uint32_t stage_cap, int bpb, cudaStream_t st) {
@@ -847,7 +856,6 @@ void place_block(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint6
     a.big_list = d_big_list;
     a.big_count = d_big_count;
     a.big_cap = big_cap;
-    a.ins = d_ins;
     a.mol = d_mol;
     a.fdesc = d_fdesc;
     a.sum1 = d_sum1;
@@ -859,7 +867,11 @@ void place_block(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint6
     LAUNCH(k_place_big, std::min<uint32_t>(big_cap, 592u), PB_THREADS, 0, st, a);  // exits at once when there are no big molecules
     LAUNCH(k_place_block, n_blocks, PB_THREADS, PB_SMEM, st, a);
     LAUNCH(k_tile_flags, (n_tiles + 255) / 256, 256, 0, st, d_sum1, d_sum2, n_tiles, stage_cap, d_tile_flags);
-    LAUNCH(k_mol_text, (n_mol + 127) / 128, 128, 0, st, sc, d_sch, mol0, 0u, n_mol, d_mol, d_text, text_stride);
+    LAUNCH(k_mol_text, (n_mol + TEXT_THREADS - 1) / TEXT_THREADS, TEXT_THREADS, (size_t)TEXT_THREADS * (text_stride + 4u), st, sc, d_sch, mol0, 0u, n_mol, d_mol, d_text, text_stride);
+}
+
+void ins_from_fdesc(const uint4 *d_fdesc, const MolRec *d_mol, const uint32_t *d_tile_mol0, uint64_t n_pairs, uint2 *d_ins, cudaStream_t st) {
+    if (n_pairs) LAUNCH(k_ins_from_fdesc, (unsigned)((n_pairs + 255) / 256), 256, 0, st, d_fdesc, d_mol, d_tile_mol0, n_pairs, d_ins);
 }
 
 __global__ void k_kat_insert_len(const __grid_constant__ SimConst sc, const InsTable *__restrict__ gtab, const uint64_t *__restrict__ bits,

@@ -41,8 +41,16 @@ struct PairDesc {
 
 __device__ __forceinline__ uint32_t window_len(int64_t a, int64_t b, uint32_t n, int strict);
 
+// FD: from the packed descriptor (x = bstart, y = length | dm << 24; every emit kernel) instead of the insert plan (k_tile_prepare,
+// which builds the descriptors of the three-kernel placement)
+template <bool FD>
 __device__ __forceinline__ void decode_pair(const EmitArgs &a, uint64_t p, uint32_t tile_m0, PairDesc &d) {
-    uint2 in = a.ins[p];
+    uint2 in;
+    if (FD) {
+        const uint4 q = a.fdesc[p];
+        in = make_uint2(q.x, q.y);
+    } else
+        in = a.ins[p];
     uint32_t m = tile_m0 + MMK_INS_DM(in.y);
     MolRec mr = a.mol[m];
     const SchemaDev &S = a.sch[mr.schema];
@@ -50,7 +58,7 @@ __device__ __forceinline__ void decode_pair(const EmitArgs &a, uint64_t p, uint3
     d.n = S.len;
     d.mol = m;
     d.pair = p;
-    d.bstart = (uint32_t)mr.start + in.x;
+    d.bstart = FD ? in.x : (uint32_t)mr.start + in.x;
     d.bend = d.bstart + MMK_INS_LEN(in.y) - 1;
     d.d1 = (uint8_t)ndigits_u32(d.bstart);
     d.d2 = (uint8_t)ndigits_u32(d.bend);
@@ -226,7 +234,7 @@ __global__ void __launch_bounds__(256) k_tile_prepare(EmitArgs a, uint32_t tile_
     uint32_t schema = 0, iny = 0;
     if (it < np) {
         const uint32_t m0 = a.tile_mol0[tile];
-        decode_pair(a, p0 + it, m0, d);
+        decode_pair<false>(a, p0 + it, m0, d);
         schema = a.mol[d.mol].schema;
         iny = a.ins[p0 + it].y;
     }
@@ -570,7 +578,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_emit(const __grid_c
         // general path: every record byte-wise, straight to global memory (warp per pair)
         PairDesc d;
         d.len1 = d.len2 = 0;
-        if (threadIdx.x < np) decode_pair(a, p0 + threadIdx.x, tile_m0, d);
+        if (threadIdx.x < np) decode_pair<true>(a, p0 + threadIdx.x, tile_m0, d);
         if (threadIdx.x < MAXP) {
             uint32_t i1 = d.len1, i2 = d.len2;
             for (int o = 1; o < 32; o <<= 1) {
@@ -595,7 +603,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_emit(const __grid_c
         uint8_t *o1 = a.out1 + g1, *o2 = a.out2 + g2;
         for (uint32_t t = warp; t < np; t += EMIT_WARPS) {
             PairDesc e;
-            decode_pair(a, p0 + t, tile_m0, e);
+            decode_pair<true>(a, p0 + t, tile_m0, e);
             write_record_generic<BPB>(a, e, 1, o1 + s_off1[t + 1], lane);
             write_record_generic<BPB>(a, e, 2, o2 + s_off2[t + 1], lane);
         }
@@ -772,12 +780,18 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
                 s_rd[2 * lane] = make_uint2((f.sb1 + FD_HDR(f.pk) + (uint32_t)a.bclen_inline) | (rel1 << 20), f.wbase1);
                 s_rd[2 * lane + 1] = make_uint2((f.sb2 + FD_HDR(f.pk)) | (rel2 << 20), f.wbase2);
                 if (ERR) s_er[lane] = make_uint2(q.z, a.sch[q.w >> 13].len);
-                // start the loads the next phases will need
-                prefetch_l1(a.hap + f.wbase1);
-                prefetch_l1(a.hap + f.wbase1 + (BPB == 2 ? 15 : 31));
-                prefetch_l1(a.hap + f.wbase2);
-                prefetch_l1(a.hap + f.wbase2 + (BPB == 2 ? 15 : 31));
-                prefetch_l1(a.text + (uint64_t)f.mol * a.text_stride);
+            }
+            {   // start the loads the next phases will need — one request per distinct 128-byte line: the last word of a window
+                // is often in the line of the first, and neighbouring pairs share their molecule's header text
+                constexpr uint32_t WL = BPB == 2 ? 15u : 31u;
+                const uint32_t mol_prev = __shfl_up_sync(0xffffffffu, f.mol, 1);
+                if (have) {
+                    prefetch_l1(a.hap + f.wbase1);
+                    if ((f.wbase1 ^ (f.wbase1 + WL)) >> 5) prefetch_l1(a.hap + f.wbase1 + WL);
+                    prefetch_l1(a.hap + f.wbase2);
+                    if ((f.wbase2 ^ (f.wbase2 + WL)) >> 5) prefetch_l1(a.hap + f.wbase2 + WL);
+                    if (lane == 0 || f.mol != mol_prev) prefetch_l1(a.text + (uint64_t)f.mol * a.text_stride);
+                }
             }
         }
     }
@@ -787,7 +801,7 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
         const uint32_t tile_m0 = a.tile_mol0[tile];
         PairDesc d;
         d.len1 = d.len2 = 0;
-        if (threadIdx.x < np) decode_pair(a, p0 + threadIdx.x, tile_m0, d);
+        if (threadIdx.x < np) decode_pair<true>(a, p0 + threadIdx.x, tile_m0, d);
         if (threadIdx.x < 32) {
             uint32_t i1 = d.len1, i2 = d.len2;
             for (int o = 1; o < 32; o <<= 1) {
@@ -804,7 +818,7 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
         uint8_t *o1 = a.out1 + g1, *o2 = a.out2 + g2;
         for (uint32_t t = warp; t < np; t += 4) {
             PairDesc e;
-            decode_pair(a, p0 + t, tile_m0, e);
+            decode_pair<true>(a, p0 + t, tile_m0, e);
             write_record_generic<BPB>(a, e, 1, o1 + s_off1[t + 1], lane);
             write_record_generic<BPB>(a, e, 2, o2 + s_off2[t + 1], lane);
         }

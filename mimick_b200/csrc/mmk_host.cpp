@@ -130,7 +130,8 @@ struct mmk_ctx {
     int32_t rank = 0, world = 1;
     bool placed = false;
     uint64_t mol0 = 0, s_nmol = 0, pair0 = 0, s_npairs = 0;
-    DBuf<uint2> d_ins;
+    DBuf<uint2> d_ins;       // insert plan: written by the three-kernel placement; derived from the descriptors on demand otherwise
+    bool ins_valid = false;
     DBuf<MolRec> d_mol;
     DBuf<uint8_t> d_text;
     DBuf<uint64_t> d_roff_l;
@@ -1438,7 +1439,6 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
         CU(cudaMemsetAsync(ctx->d_qfill.p, 'I', 2 * (size_t)ctx->stage_cap, ctx->st));
     }
 
-    CU(ctx->d_ins.ensure(ctx->s_npairs + 1));
     CU(ctx->d_mol.ensure(ctx->s_nmol + 1));
     CU(ctx->d_text.ensure((size_t)(ctx->s_nmol + 1) * ctx->text_stride));
     CU(ctx->d_roff_l.ensure(ctx->s_nmol + 2));
@@ -1467,6 +1467,7 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     CU(cudaMemsetAsync(d_gather.p, 0, 256 * 8, ctx->st));
     CU(ctx->d_fdesc.ensure(ctx->s_npairs + 1));
     CU(ctx->d_tile_flags.ensure((size_t)ctx->n_tiles + 1));
+    if (!fused) CU(ctx->d_ins.ensure(ctx->s_npairs + 1));  // the three-kernel path writes the insert plan; before base_args takes the pointer
     const EmitArgs targs = base_args(ctx);
     auto run_fused = [&]() -> int32_t {
         const uint32_t nm = (uint32_t)ctx->s_nmol;
@@ -1477,7 +1478,7 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
         CU(ctx->d_big_list.ensure((size_t)place_big_cap(ctx->s_npairs) + 1));
         CU(ctx->d_big_count.ensure(1));
         place_block(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->mol0, nm, ctx->s_npairs, ctx->n_tiles, ctx->d_roff_l.p,
-                    ctx->d_tile_mol0.p, ctx->d_instab.p, ctx->d_ins.p, ctx->d_mol.p, ctx->d_text.p, ctx->text_stride, ctx->d_fdesc.p,
+                    ctx->d_tile_mol0.p, ctx->d_instab.p, ctx->d_mol.p, ctx->d_text.p, ctx->text_stride, ctx->d_fdesc.p,
                     d_sum1.p, d_sum2.p, ctx->d_tile_flags.p, d_gather.p, d_err.p, ctx->d_weight.p, ctx->d_woff.p, ctx->d_scan_tmp.p,
                     ctx->d_blk.p, ctx->d_big_list.p, ctx->d_big_count.p, ctx->stage_cap, ctx->bpb, ctx->st);
         return MMK_OK;
@@ -1549,6 +1550,7 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     for (;;) {
         int32_t rc = fused ? run_fused() : run_legacy();
         if (rc) return rc;
+        ctx->ins_valid = !fused;
         CU(cudaMemcpyAsync(herr, d_err.p, sizeof herr, cudaMemcpyDeviceToHost, ctx->st));
         CU(cudaStreamSynchronize(ctx->st));
         CU(cudaGetLastError());
@@ -2191,11 +2193,26 @@ extern "C" int32_t mmk_dump_molecules(mmk_ctx *ctx, int64_t first, int64_t n, mm
     return MMK_OK;
 }
 
+// the insert plan of the placed shard, derived from the pair descriptors when the block placement ran
+static int32_t ensure_ins(mmk_ctx *ctx) {
+    if (ctx->ins_valid) return MMK_OK;
+    CU(ctx->d_ins.ensure(ctx->s_npairs + 1));
+    ins_from_fdesc(ctx->d_fdesc.p, ctx->d_mol.p, ctx->d_tile_mol0.p, ctx->s_npairs, ctx->d_ins.p, ctx->st);
+    CU(cudaStreamSynchronize(ctx->st));
+    CU(cudaGetLastError());
+    ctx->ins_valid = true;
+    return MMK_OK;
+}
+
 extern "C" int32_t mmk_dump_inserts(mmk_ctx *ctx, int64_t first, int64_t n, int64_t *start, int64_t *stop) {
     if (!ctx || !start || !stop || first < 0 || n < 0) return MMK_ERR_INVALID_ARG;
     if (!ctx->placed) return fail(ctx, MMK_ERR_STATE, "mmk_place has not run");
     if ((uint64_t)(first + n) > ctx->s_npairs) return fail(ctx, MMK_ERR_INVALID_ARG, "pair range out of bounds");
     CU(cudaSetDevice(ctx->par.device));
+    {
+        int32_t rc = ensure_ins(ctx);
+        if (rc) return rc;
+    }
     std::vector<uint2> in(n);
     std::vector<uint64_t> ro(ctx->s_nmol + 1);
     std::vector<MolRec> mr(ctx->s_nmol);
@@ -2217,6 +2234,10 @@ extern "C" int32_t mmk_dump_variates(mmk_ctx *ctx, mmk_variate *out, uint64_t ca
     if (!ctx || !n_out) return MMK_ERR_INVALID_ARG;
     if (!ctx->placed || ctx->world != 1) return fail(ctx, MMK_ERR_STATE, "mmk_dump_variates needs mmk_place on an unsharded context");
     CU(cudaSetDevice(ctx->par.device));
+    {
+        int32_t rc = ensure_ins(ctx);
+        if (rc) return rc;
+    }
     DBuf<uint32_t> d_counts, d_nlive;
     DBuf<uint64_t> d_offsets, d_tmp;
     CU(d_counts.ensure(ctx->n_mol + 1));

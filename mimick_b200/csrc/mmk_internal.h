@@ -191,10 +191,12 @@ uint32_t place_block_count(uint64_t n_pairs, uint32_t n_mol);  // entries of d_b
 uint32_t place_big_cap(uint64_t n_pairs);                      // entries of d_big_list
 bool place_block_supports(const SimConst &sc);
 void place_block(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint64_t mol0, uint32_t n_mol, uint64_t n_pairs,
-                 uint32_t n_tiles, const uint64_t *d_roff_l, uint32_t *d_tile_mol0, const InsTable *d_tab, uint2 *d_ins, MolRec *d_mol,
+                 uint32_t n_tiles, const uint64_t *d_roff_l, uint32_t *d_tile_mol0, const InsTable *d_tab, MolRec *d_mol,
                  uint8_t *d_text, uint32_t text_stride, uint4 *d_fdesc, uint32_t *d_sum1, uint32_t *d_sum2, uint8_t *d_tile_flags,
                  unsigned long long *d_gather, unsigned long long *d_err, uint32_t *d_weight, uint64_t *d_woff, uint64_t *d_scan_tmp,
                  uint32_t *d_blk, uint32_t *d_big_list, uint32_t *d_big_count, uint32_t stage_cap, int bpb, cudaStream_t st);
+// the insert plan of a block-placed shard (the block placement keeps only the descriptors): for the dump entry points
+void ins_from_fdesc(const uint4 *d_fdesc, const MolRec *d_mol, const uint32_t *d_tile_mol0, uint64_t n_pairs, uint2 *d_ins, cudaStream_t st);
 void place_local_roff(uint64_t mol0, uint32_t n_mol, const uint64_t *d_read_off_global, uint64_t *d_read_off_local, cudaStream_t st);
 // KAT: lengths the kernels derive from raw 64-bit draws (table path with its exact fallback); slow[i] = 1 where the fallback ran
 void kat_insert_len(const SimConst &sc, const InsTable *d_tab, const uint64_t *d_bits, uint32_t *d_len, uint8_t *d_slow, int64_t n, cudaStream_t st);

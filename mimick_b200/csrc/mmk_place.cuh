@@ -11,7 +11,8 @@
 //      serial gap chain over shared memory (:27-33), header-piece lengths, the molecule record;
 //   C. one warp per 32-pair tile (aligned to the tiles of the emit kernel): breakpoints, record lengths, the 16-byte
 //      pair descriptors the emit kernel reads, record bytes per tile and stream, the tile's irregular flag.
-// Nothing per pair goes through global scratch.  Molecules with more than PB_BIG pairs do not fit a block's window:
+// Nothing per pair goes through global scratch, and the only per-pair output is the 16-byte descriptor (the insert plan
+// `ins` of the three-kernel path is derived from it on demand: k_ins_from_fdesc).  Molecules with more than PB_BIG pairs do not fit a block's window:
 // k_place_big places them first, one CTA each, and phase C reads their inserts back from global memory.
 //
 // The insert-length table.  trunc(mu + sd * Phi^-1(p(u))) is a non-decreasing step function of the 52-bit uniform
@@ -155,7 +156,6 @@ struct PlaceArgs {
     const uint32_t *big_list;   // shard molecules with more than PB_BIG pairs
     const uint32_t *big_count;
     uint32_t big_cap;
-    uint2 *ins;
     MolRec *mol;
     uint4 *fdesc;
     uint32_t *sum1, *sum2;       // [n_tiles] record bytes per tile and stream; zero on entry
@@ -423,15 +423,14 @@ __global__ void __launch_bounds__(PB_THREADS, 4) k_place_block(const __grid_cons
             const uint32_t dm = ml - a.tile_mol0[tile];
             const uint32_t start = s_start[j];
             uint32_t so, li;
-            if (MPK_BIG(pk)) {
-                const uint2 q = a.ins[p];
-                so = q.x;
+            if (MPK_BIG(pk)) {  // k_place_big left (insert start, length) in the descriptor's first two words
+                const uint4 q = a.fdesc[p];
+                so = q.x - start;
                 li = MMK_INS_LEN(q.y);
             } else {
                 const uint32_t slot = s_so[j] + (i - s_ro[j]);
                 so = s_bits[slot].x;
                 li = s_len[slot];
-                a.ins[p] = make_uint2(so, li | (dm << 24));
             }
             const SchemaDev &S = a.sch[MPK_SCHEMA(pk)];
             const uint32_t n_hap = S.len;
@@ -481,7 +480,10 @@ __global__ void __launch_bounds__(PB_THREADS, 4) k_place_block(const __grid_cons
 constexpr uint32_t BIGC = 1024;  // pairs per chunk
 __global__ void __launch_bounds__(PB_THREADS) k_place_big(const __grid_constant__ PlaceArgs a) {
     __shared__ InsTable tab;
-    __shared__ uint32_t s_lo[BIGC], s_hi[BIGC], s_len[BIGC];
+    __shared__ __align__(16) uint32_t s_lo[2 * BIGC];  // gap bits: low words, then high words (s_hi); doubles in the float-sum pass
+    uint32_t *const s_hi = s_lo + BIGC;
+    __shared__ uint32_t s_len[BIGC];
+    __shared__ double s_sum;
     __shared__ unsigned long long s_red[PB_THREADS / 32];
     __shared__ unsigned long long s_isum;
     __shared__ uint32_t s_flag;
@@ -520,10 +522,33 @@ __global__ void __launch_bounds__(PB_THREADS) k_place_big(const __grid_constant_
                 unsigned long long tot = 0;
                 for (uint32_t w = 0; w < PB_THREADS / 32; ++w) tot += s_red[w];
                 s_isum = tot;
-                s_flag = sum_over(sc, key, g, ms, nfrags, molsize, tot) ? 1u : 0u;
+                // 0 fits, 1 too long, 2 the integer bounds straddle the molecule: the float sum decides (sum_over)
+                s_flag = tot >= (unsigned long long)molsize + 2u ? 1u : (tot + nfrags + 1u <= (unsigned long long)molsize ? 0u : 2u);
             }
             __syncthreads();
             isum = s_isum;
+            if (s_flag == 2u) {
+                // the left-to-right float sum of the oracle: the draws in parallel (double precision, 1024 at a time through
+                // the shared-memory words of the chain below), the additions in order by one thread
+                double *s_x = reinterpret_cast<double *>(s_lo);  // s_lo and s_hi are contiguous: 1024 doubles
+                for (uint32_t c0 = 0; c0 < nfrags; c0 += BIGC) {
+                    const uint32_t cn = min(BIGC, nfrags - c0);
+                    __syncthreads();
+                    for (uint32_t k = tid; k < cn; k += PB_THREADS) {
+                        NoRec rec;
+                        s_x[k] = draw_insert(sc, key, g, ms, c0 + k, rec);
+                    }
+                    __syncthreads();
+                    if (tid == 0) {
+                        double sum = c0 ? s_sum : 0.0;
+                        for (uint32_t k = 0; k < cn; ++k) sum = MMK_ADD(sum, s_x[k]);
+                        s_sum = sum;
+                    }
+                }
+                __syncthreads();
+                if (tid == 0) s_flag = s_sum > (double)molsize ? 1u : 0u;
+                __syncthreads();
+            }
             over = s_flag != 0u;
             if (!over) break;
         }
@@ -570,11 +595,8 @@ __global__ void __launch_bounds__(PB_THREADS) k_place_big(const __grid_constant_
                 }
                 __syncthreads();
                 if (c0 == 0) first_read_quals(sc, start, s_lo[0], s_len[0], n, q1, q2);
-                for (uint32_t k = tid; k < cn; k += PB_THREADS) {
-                    const uint64_t p = ro + c0 + k;
-                    const uint32_t dm = ml - a.tile_mol0[p >> 5];
-                    a.ins[p] = make_uint2(s_lo[k], s_len[k] | (dm << 24));
-                }
+                for (uint32_t k = tid; k < cn; k += PB_THREADS)  // k_place_block completes the descriptor
+                    a.fdesc[ro + c0 + k] = make_uint4((uint32_t)start + s_lo[k], s_len[k], 0u, 0u);
             }
             __syncthreads();
             status = (uint32_t)s_state[2];
@@ -600,6 +622,16 @@ __global__ void __launch_bounds__(PB_THREADS) k_place_big(const __grid_constant_
         }
         __syncthreads();
     }
+}
+
+// (insert start - molecule start, length | dm << 24) per pair from the descriptors: for mmk_dump_inserts / mmk_dump_variates
+__global__ void k_ins_from_fdesc(const uint4 *__restrict__ fdesc, const MolRec *__restrict__ mol, const uint32_t *__restrict__ tile_mol0,
+                                 uint64_t n_pairs, uint2 *ins) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const uint4 q = fdesc[p];
+    const uint32_t m = tile_mol0[p >> 5] + MMK_INS_DM(q.y);
+    ins[p] = make_uint2(q.x - (uint32_t)mol[m].start, q.y);
 }
 
 // tile_flags: 1 = irregular (from k_place_block) -> 1 = every pair regular and the tile fits the emit kernel's stage
