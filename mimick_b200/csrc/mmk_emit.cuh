@@ -301,6 +301,14 @@ __device__ __forceinline__ uint4 expand16(uint32_t bits, uint32_t lut) {
     return v;
 }
 
+// PRMT as the hardware has it: bit 3 of a selector nibble asks for sign replication and must be 0 here (__byte_perm masks every
+// selector with 0x7777 to give its documented behaviour; the callers below already have clean selectors)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
 // shared memory through 32-bit window addresses (computed once per kernel)
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -727,9 +735,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
 template <int BPB, bool ERR>
 __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
+    constexpr bool HOT = BPB == 2 && !ERR;  // the plain 2-bit kernel: per-read records in the form its sequence loop consumes
     __shared__ uint4 s_fa[32];
     __shared__ uint2 s_fb[32];
-    __shared__ uint2 s_rd[64];
+    __shared__ uint2 s_rd[HOT ? 1 : 64];
+    __shared__ uint4 s_rq[HOT ? 64 : 1];  // HOT: first word, address of the read's first 16-byte chunk, base shift, chunk limit
     __shared__ uint2 s_er[ERR ? 32 : 1];  // error model: first arena word and length of the pair's haplotype
     __shared__ uint32_t s_off1[33], s_off2[33];
     __shared__ __align__(8) unsigned long long s_mbar;
@@ -777,9 +787,20 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
                 constexpr uint32_t WM = BPB == 2 ? 15u : 7u;
                 const uint32_t ws1 = f.bstart - 1u, ws2 = f.bend - (uint32_t)a.r2;
                 const uint32_t rel1 = ws1 >= 15u ? ((ws1 - 15u) & WM) + 15u : ws1, rel2 = ws2 >= 15u ? ((ws2 - 15u) & WM) + 15u : ws2;
-                s_rd[2 * lane] = make_uint2((f.sb1 + FD_HDR(f.pk) + (uint32_t)a.bclen_inline) | (rel1 << 20), f.wbase1);
-                s_rd[2 * lane + 1] = make_uint2((f.sb2 + FD_HDR(f.pk)) | (rel2 << 20), f.wbase2);
+                const uint32_t so1 = f.sb1 + FD_HDR(f.pk) + (uint32_t)a.bclen_inline, so2 = f.sb2 + FD_HDR(f.pk);  // stage offsets of the first bases
+                if (HOT) {
+                    // chunk c of a read (16 bytes of the stage, lane hl = c) starts at base k0 = 16 hl - (so & 15) of the read and takes
+                    // the 16 haplotype bases from q = rel + k0 (forward) / rel + S - 16 - k0 (reverse complement) past the first loaded word:
+                    // z = q at hl = 0, w = the first 16 hl that lies past the sequence
+                    s_rq[2 * lane] = make_uint4(f.wbase1, sm + (so1 & ~15u), rel1 + (uint32_t)a.r1 - 16u + (so1 & 15u), (so1 & 15u) + (uint32_t)a.r1);
+                    s_rq[2 * lane + 1] = make_uint4(f.wbase2, sm + (so2 & ~15u), rel2 - (so2 & 15u), (so2 & 15u) + (uint32_t)a.r2);
+                } else {
+                    s_rd[2 * lane] = make_uint2(so1 | (rel1 << 20), f.wbase1);
+                    s_rd[2 * lane + 1] = make_uint2(so2 | (rel2 << 20), f.wbase2);
+                }
                 if (ERR) s_er[lane] = make_uint2(q.z, a.sch[q.w >> 13].len);
+            } else if (HOT) {  // a short last tile: the word loads of the missing pairs stay inside the arena
+                s_rq[2 * lane] = s_rq[2 * lane + 1] = make_uint4(0u, 0u, 0u, 0u);
             }
             {   // start the loads the next phases will need — one request per distinct 128-byte line: the last word of a window
                 // is often in the line of the first, and neighbouring pairs share their molecule's header text
@@ -828,14 +849,47 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
     {   // phase 1: warp per pair (t = warp, warp + 4, ...), half-warp per read
         const uint32_t half = lane >> 4, hl = lane & 15u;
         const uint32_t *hap_lane = a.hap + hl;
-        if (BPB == 2 && !ERR) {  // the words of all the warp's pairs in flight at once, then the passes
+        if constexpr (HOT) {  // the words of all the warp's pairs in flight at once, then the passes
+            // what depends on the lane alone, kept in registers (the asm statements stop the compiler from recomputing it per pass)
+            uint32_t hl16 = 16u * hl, qs = half ? hl16 : 0u - hl16;
+            // R2 (forward): "ACGT"[code], bytes in base order.  R1 (reverse complement): "TGCA"[code], and the 16 bases leave in
+            // reverse order — the two halves of the word swapped (rsh) and the interleaving byte selectors mirrored (selA, selB)
+            uint32_t lut = half ? 0x54474341u : 0x41434754u, rsh = half ? 0u : 16u;
+            uint32_t selA = half ? 0x5140u : 0x2637u, selB = half ? 0x7362u : 0x0415u;
+            // the 15 bytes after the sequence ("\n+\n" and the first quality characters) and the record's final newline
+            uint32_t tval = (hl == 0u || hl == 2u || hl == 15u) ? (uint32_t)'\n' : (hl == 1u ? (uint32_t)'+' : (uint32_t)'I');
+            uint32_t tdelta = hl < 15u ? hl : 3u + (half ? (uint32_t)a.r2 : (uint32_t)a.r1 + (uint32_t)a.bclen_inline);
+            asm volatile("" : "+r"(hl16), "+r"(qs), "+r"(lut), "+r"(rsh), "+r"(selA), "+r"(selB), "+r"(tval), "+r"(tdelta));
+            const uint4 *rq = s_rq + 2u * warp + half;  // pair warp + 4 i: rq[8 i]
             uint32_t W[8];
 #pragma unroll
-            for (uint32_t i = 0; i < 8; ++i) W[i] = __ldg(hap_lane + s_rd[2 * (warp + 4u * i < np ? warp + 4u * i : 0u) + half].y);
+            for (uint32_t i = 0; i < 8; ++i) W[i] = __ldg(a.hap + (rq[8u * i].x + hl));
             mbar_wait(mb, 0u);  // the quality fill has landed
+            auto pass = [&](const uint4 R, const uint32_t Wi) {
+                const int q = (int)(R.z + qs);
+                // words j and j + 1 of the half-warp (width 16: the source lane is taken modulo 16 inside the half).  Lanes whose q is
+                // negative or past the loaded words hold bases outside the read: what they write is rewritten later
+                const uint32_t lo = __shfl_sync(0xffffffffu, Wi, q >> 4, 16);
+                const uint32_t hi = __shfl_sync(0xffffffffu, Wi, (q >> 4) + 1, 16);
+                uint32_t bits = __funnelshift_r(lo, hi, 2u * (uint32_t)q);  // the shift is taken modulo 32: 2 (q mod 16)
+                bits = __funnelshift_l(bits, bits, rsh);
+                uint32_t ev = bits & 0x33333333u, od = (bits >> 2) & 0x33333333u;  // PRMT selectors: one base per nibble
+                asm volatile("" : "+r"(ev), "+r"(od));
+                const uint32_t e_lo = prmt(lut, 0u, ev), e_hi = prmt(lut, 0u, ev >> 16);
+                const uint32_t o_lo = prmt(lut, 0u, od), o_hi = prmt(lut, 0u, od >> 16);
+                const uint4 v = make_uint4(prmt(e_lo, o_lo, selA), prmt(e_lo, o_lo, selB), prmt(e_hi, o_hi, selA), prmt(e_hi, o_hi, selB));
+                if (hl16 < R.w) sts128(R.y + hl16, v);
+                __syncwarp();
+                sts8(R.y + R.w + tdelta, tval);
+            };
+            if (np == 32u) {
 #pragma unroll
-            for (uint32_t i = 0; i < 8; ++i)
-                if (warp + 4u * i < np) emit_pair_seq(a, s_rd[2 * (warp + 4u * i) + half], W[i], sm, lane);
+                for (uint32_t i = 0; i < 8; ++i) pass(rq[8u * i], W[i]);
+            } else {
+#pragma unroll
+                for (uint32_t i = 0; i < 8; ++i)
+                    if (warp + 4u * i < np) pass(rq[8u * i], W[i]);
+            }
         } else {  // the words of the next pair are loaded while this one is expanded
             uint2 rd = s_rd[2 * (warp < np ? warp : 0) + half];
             uint32_t W0 = __ldg(hap_lane + rd.y), W1 = BPB == 4 ? __ldg(hap_lane + rd.y + 16) : 0u;
