@@ -24,6 +24,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # the same TUs must not contract either.
 HOST_FLAGS = "-fPIC,-ffp-contract=off,-fno-fast-math,-Wall,-Wno-unused-function"
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", HOST_FLAGS, "-I", INCLUDE, "-I", CSRC]
+COMMON += os.environ.get("MMK_NVCC_FLAGS", "").split()  # experiment switches (-DMMK_EMIT_ILP=4 ...); the defaults are the product
 
 SOURCES = ["mmk_device.cu", "mmk_host.cpp", "mmk_io.cpp"]
 HEADERS = ["mmk_internal.h", "mmk_sampling.cuh", "mmk_host.h", "mmk_emit.cuh", "mmk_bgzf.cuh", "mmk_bgzf_table.h", "mmk_place.cuh", "mmk_plan.cuh"]

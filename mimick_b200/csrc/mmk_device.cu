@@ -824,7 +824,8 @@ void place_block(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint6
                  uint32_t n_tiles, const uint64_t *d_roff_l, uint32_t *d_tile_mol0, const InsTable *d_tab, MolRec *d_mol,
                  uint8_t *d_text, uint32_t text_stride, uint4 *d_fdesc, uint32_t *d_sum1, uint32_t *d_sum2, uint8_t *d_tile_flags,
                  unsigned long long *d_gather, unsigned long long *d_err, uint32_t *d_weight, uint64_t *d_woff, uint64_t *d_scan_tmp,
-                 uint32_t *d_blk, uint32_t *d_big_list, uint32_t *d_big_count, uint32_t stage_cap, int bpb, cudaStream_t st) {
+                 uint32_t *d_blk, uint32_t *d_big_list, uint32_t *d_big_count, uint32_t stage_cap, int bpb, cudaStream_t st, cudaStream_t st_text,
+                 cudaEvent_t ev_placed, cudaEvent_t ev_text) {
     if (n_mol == 0 || n_pairs == 0) return;
     static bool attr_set = false;
     if (!attr_set) {
@@ -866,8 +867,13 @@ void place_block(const SimConst &sc, const SchemaDev *d_sch, PlanDev plan, uint6
     a.bpb = bpb;
     LAUNCH(k_place_big, std::min<uint32_t>(big_cap, 592u), PB_THREADS, 0, st, a);  // exits at once when there are no big molecules
     LAUNCH(k_place_block, n_blocks, PB_THREADS, PB_SMEM, st, a);
+    // the header text (memory-bound, 1.5 ms for 20 M molecules) runs on the second stream, beside the tile scans, the chunk table
+    // and their host round trips on the main stream; the caller makes the main stream wait for ev_text before anything reads the text
+    cudaEventRecord(ev_placed, st);
+    cudaStreamWaitEvent(st_text, ev_placed, 0);
+    LAUNCH(k_mol_text, (n_mol + TEXT_THREADS - 1) / TEXT_THREADS, TEXT_THREADS, (size_t)TEXT_THREADS * (text_stride + 4u), st_text, sc, d_sch, mol0, 0u, n_mol, d_mol, d_text, text_stride);
+    cudaEventRecord(ev_text, st_text);
     LAUNCH(k_tile_flags, (n_tiles + 255) / 256, 256, 0, st, d_sum1, d_sum2, n_tiles, stage_cap, d_tile_flags);
-    LAUNCH(k_mol_text, (n_mol + TEXT_THREADS - 1) / TEXT_THREADS, TEXT_THREADS, (size_t)TEXT_THREADS * (text_stride + 4u), st, sc, d_sch, mol0, 0u, n_mol, d_mol, d_text, text_stride);
 }
 
 void ins_from_fdesc(const uint4 *d_fdesc, const MolRec *d_mol, const uint32_t *d_tile_mol0, uint64_t n_pairs, uint2 *d_ins, cudaStream_t st) {
@@ -932,36 +938,41 @@ __device__ __forceinline__ uint32_t warp_upper_tile(const uint64_t *off, uint32_
     }
     return lo;
 }
-__global__ void k_chunk_table(const uint64_t *off1, const uint64_t *off2, uint32_t n_tiles, uint64_t cap, uint32_t *bounds,
-                              uint64_t *boff1, uint64_t *boff2, uint32_t max_chunks, uint32_t *n_out) {
-    const uint32_t lane = threadIdx.x;
+__global__ void __launch_bounds__(64) k_chunk_table(const uint64_t *off1, const uint64_t *off2, uint32_t n_tiles, uint64_t cap, uint32_t *bounds,
+                                                    uint64_t *boff1, uint64_t *boff2, uint32_t max_chunks, uint32_t *n_out) {
+    // warp 0 searches the R1 offsets, warp 1 the R2 offsets (each boundary is a chain of dependent probes: the two run side by side)
+    __shared__ uint32_t s_e[2];
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const uint64_t *off = w ? off2 : off1;
     uint32_t t0 = 0, k = 0;
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
         bounds[0] = 0;
         boff1[0] = off1[0];
         boff2[0] = off2[0];
     }
     while (t0 < n_tiles && k < max_chunks) {
-        const uint32_t e1 = warp_upper_tile(off1, t0, n_tiles, off1[t0] + cap, lane);
-        const uint32_t e2 = warp_upper_tile(off2, t0, n_tiles, off2[t0] + cap, lane);
-        const uint32_t best = e1 < e2 ? e1 : e2;
+        const uint32_t e = warp_upper_tile(off, t0, n_tiles, off[t0] + cap, lane);
+        if (lane == 0) s_e[w] = e;
+        __syncthreads();
+        const uint32_t best = s_e[0] < s_e[1] ? s_e[0] : s_e[1];
+        __syncthreads();
         if (best <= t0) {
-            if (lane == 0) *n_out = 0xffffffffu;
+            if (threadIdx.x == 0) *n_out = 0xffffffffu;
             return;
         }
         ++k;
-        if (lane == 0) {
+        if (threadIdx.x == 0) {
             bounds[k] = best;
             boff1[k] = off1[best];
             boff2[k] = off2[best];
         }
         t0 = best;
     }
-    if (lane == 0) *n_out = (t0 < n_tiles) ? 0xfffffffeu : k;
+    if (threadIdx.x == 0) *n_out = (t0 < n_tiles) ? 0xfffffffeu : k;
 }
 void chunk_table(const uint64_t *d_off1, const uint64_t *d_off2, uint32_t n_tiles, uint64_t cap, uint32_t *d_bounds,
                  uint64_t *d_boff1, uint64_t *d_boff2, uint32_t max_chunks, uint32_t *d_n, cudaStream_t st) {
-    LAUNCH(k_chunk_table, 1, 32, 0, st, d_off1, d_off2, n_tiles, cap, d_bounds, d_boff1, d_boff2, max_chunks, d_n);
+    LAUNCH(k_chunk_table, 1, 64, 0, st, d_off1, d_off2, n_tiles, cap, d_bounds, d_boff1, d_boff2, max_chunks, d_n);
 }
 
 

@@ -341,6 +341,9 @@ __device__ __forceinline__ FastDesc load_fast_desc(const uint4 *fa, const uint2 
     f.wbase1 = f.wbase2 = 0; f.mol = y.x; f.pk = y.y;
     return f;
 }
+#ifndef MMK_EMIT_ILP
+#define MMK_EMIT_ILP 8  // read pairs a warp of k_emit_w expands together (1, 2, 4 or 8)
+#endif
 #ifndef MMK_PREFETCH_MODE
 #define MMK_PREFETCH_MODE 1
 #endif
@@ -525,6 +528,64 @@ __device__ __forceinline__ void emit_header_piece(const EmitArgs &a, const FastD
             sts8(s1 + P + d1, ':');
             sts8(s2 + P + d1, ':');
         }
+    }
+}
+
+// Phase 2 as k_emit_w runs it — one warp per piece, one pair per lane, the pieces of about equal length: 0 the prefix,
+// 1 both decimal numbers, 2 the first 16 bytes of the format tail, 3 the rest of it and the inline barcode.  Text is read as
+// aligned 32-bit words and shifted into place (the molecule's text line is 16-byte aligned, its tail starts at byte P).
+__device__ __forceinline__ void copy_text_bytes(const uint8_t *src, uint32_t n, uint32_t d1, uint32_t d2) {
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(src - mis);
+    uint32_t x0 = __ldg(w);
+    for (uint32_t i = 0; i < n; i += 4u) {
+        const uint32_t x1 = __ldg(++w);  // at most one word past the bytes wanted: inside the text array (it has a spare line)
+        uint32_t v = __funnelshift_r(x0, x1, 8u * mis);
+        x0 = x1;
+#pragma unroll
+        for (uint32_t b = 0; b < 4; ++b) {
+            if (i + b < n) {
+                sts8(d1 + i + b, v);
+                sts8(d2 + i + b, v);
+            }
+            v >>= 8;
+        }
+    }
+}
+__device__ __forceinline__ void emit_header_piece_w(const EmitArgs &a, const FastDesc &f, uint32_t smem, uint32_t role, uint32_t rd_off) {
+    const uint32_t P = FD_P(f.pk), SUF = FD_SUF(f.pk), d1 = FD_D1(f.pk), d2 = FD_D2(f.pk);
+    const uint8_t *tx = a.text + (uint64_t)f.mol * a.text_stride;
+    const uint32_t s1 = smem + f.sb1, s2 = smem + f.sb2;
+    if (role == 0) {  // "@chrom:hap|start:end|"
+        copy_text_bytes(tx, P, s1, s2);
+    } else if (role == 1) {  // decimal insert breakpoints and the ':' between them
+        uint32_t v = f.bend;
+        uint32_t o = P + d1 + 1u;
+        for (uint32_t k = d2; k-- > 0;) {
+            const uint32_t q = __umulhi(v, 0xCCCCCCCDu) >> 3;
+            const uint32_t ch = '0' + (v - 10u * q);
+            sts8(s1 + o + k, ch);
+            sts8(s2 + o + k, ch);
+            v = q;
+        }
+        v = f.bstart;
+        o = P;
+        for (uint32_t k = d1; k-- > 0;) {
+            const uint32_t q = __umulhi(v, 0xCCCCCCCDu) >> 3;
+            const uint32_t ch = '0' + (v - 10u * q);
+            sts8(s1 + o + k, ch);
+            sts8(s2 + o + k, ch);
+            v = q;
+        }
+        sts8(s1 + P + d1, ':');
+        sts8(s2 + P + d1, ':');
+    } else {  // format tail: bytes [0, 16) or [16, SUF); the read digit patched for R2; inline barcode for 10x R1
+        const uint32_t o = P + d1 + 1u + d2;
+        const uint32_t lo = role == 2 ? 0u : 16u, hi = role == 2 ? (SUF < 16u ? SUF : 16u) : SUF;
+        if (hi > lo) copy_text_bytes(tx + P + lo, hi - lo, s1 + o + lo, s2 + o + lo);
+        if (rd_off >= lo && rd_off < hi) sts8(s2 + o + rd_off, (uint32_t)'2');
+        if (role == 3)
+            for (uint32_t i = 0; i < (uint32_t)a.bclen_inline; ++i) sts8(s1 + o + SUF + i, __ldg(tx + P + 1u + i));
     }
 }
 
@@ -792,8 +853,14 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
                     // chunk c of a read (16 bytes of the stage, lane hl = c) starts at base k0 = 16 hl - (so & 15) of the read and takes
                     // the 16 haplotype bases from q = rel + k0 (forward) / rel + S - 16 - k0 (reverse complement) past the first loaded word:
                     // z = q at hl = 0, w = the first 16 hl that lies past the sequence
-                    s_rq[2 * lane] = make_uint4(f.wbase1, sm + (so1 & ~15u), rel1 + (uint32_t)a.r1 - 16u + (so1 & 15u), (so1 & 15u) + (uint32_t)a.r1);
-                    s_rq[2 * lane + 1] = make_uint4(f.wbase2, sm + (so2 & ~15u), rel2 - (so2 & 15u), (so2 & 15u) + (uint32_t)a.r2);
+                    // The first loaded word is the one holding the window's first base (no lead: chunks that start before the
+                    // sequence shift in another lane's word, for bytes that are rewritten anyway), and a half-warp loads only the
+                    // words a window can reach: 11 instead of 16 for 150-base reads, 2.2 instead of 2.9 32-byte sectors per read.
+                    f.wbase1 = q.z + (ws1 >> 4);
+                    f.wbase2 = q.z + (ws2 >> 4);
+                    const uint32_t r1_ = ws1 & 15u, r2_ = ws2 & 15u;
+                    s_rq[2 * lane] = make_uint4(f.wbase1, sm + (so1 & ~15u), r1_ + (uint32_t)a.r1 - 16u + (so1 & 15u), (so1 & 15u) + (uint32_t)a.r1);
+                    s_rq[2 * lane + 1] = make_uint4(f.wbase2, sm + (so2 & ~15u), r2_ - (so2 & 15u), (so2 & 15u) + (uint32_t)a.r2);
                 } else {
                     s_rd[2 * lane] = make_uint2(so1 | (rel1 << 20), f.wbase1);
                     s_rd[2 * lane + 1] = make_uint2(so2 | (rel2 << 20), f.wbase2);
@@ -804,13 +871,14 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
             }
             {   // start the loads the next phases will need — one request per distinct 128-byte line: the last word of a window
                 // is often in the line of the first, and neighbouring pairs share their molecule's header text
-                constexpr uint32_t WL = BPB == 2 ? 15u : 31u;
+                const uint32_t WL1 = HOT ? ((uint32_t)a.r1 + 14u) >> 4 : (BPB == 2 ? 15u : 31u);  // last word a half-warp loads
+                const uint32_t WL2 = HOT ? ((uint32_t)a.r2 + 14u) >> 4 : (BPB == 2 ? 15u : 31u);
                 const uint32_t mol_prev = __shfl_up_sync(0xffffffffu, f.mol, 1);
                 if (have) {
                     prefetch_l1(a.hap + f.wbase1);
-                    if ((f.wbase1 ^ (f.wbase1 + WL)) >> 5) prefetch_l1(a.hap + f.wbase1 + WL);
+                    if ((f.wbase1 ^ (f.wbase1 + WL1)) >> 5) prefetch_l1(a.hap + f.wbase1 + WL1);
                     prefetch_l1(a.hap + f.wbase2);
-                    if ((f.wbase2 ^ (f.wbase2 + WL)) >> 5) prefetch_l1(a.hap + f.wbase2 + WL);
+                    if ((f.wbase2 ^ (f.wbase2 + WL2)) >> 5) prefetch_l1(a.hap + f.wbase2 + WL2);
                     if (lane == 0 || f.mol != mol_prev) prefetch_l1(a.text + (uint64_t)f.mol * a.text_stride);
                 }
             }
@@ -861,11 +929,13 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
             uint32_t tdelta = hl < 15u ? hl : 3u + (half ? (uint32_t)a.r2 : (uint32_t)a.r1 + (uint32_t)a.bclen_inline);
             asm volatile("" : "+r"(hl16), "+r"(qs), "+r"(lut), "+r"(rsh), "+r"(selA), "+r"(selB), "+r"(tval), "+r"(tdelta));
             const uint4 *rq = s_rq + 2u * warp + half;  // pair warp + 4 i: rq[8 i]
+            const bool ldw = hl <= (((half ? (uint32_t)a.r2 : (uint32_t)a.r1) + 14u) >> 4);  // words 0 .. (15 + S - 1) / 16 hold the window
             uint32_t W[8];
 #pragma unroll
-            for (uint32_t i = 0; i < 8; ++i) W[i] = __ldg(a.hap + (rq[8u * i].x + hl));
+            for (uint32_t i = 0; i < 8; ++i) W[i] = ldw ? __ldg(a.hap + (rq[8u * i].x + hl)) : 0u;
             mbar_wait(mb, 0u);  // the quality fill has landed
-            auto pass = [&](const uint4 R, const uint32_t Wi) {
+            // 16 bytes of sequence text for this lane's chunk of the read described by R
+            auto chunk = [&](const uint4 R, const uint32_t Wi) -> uint4 {
                 const int q = (int)(R.z + qs);
                 // words j and j + 1 of the half-warp (width 16: the source lane is taken modulo 16 inside the half).  Lanes whose q is
                 // negative or past the loaded words hold bases outside the read: what they write is rewritten later
@@ -877,18 +947,33 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
                 asm volatile("" : "+r"(ev), "+r"(od));
                 const uint32_t e_lo = prmt(lut, 0u, ev), e_hi = prmt(lut, 0u, ev >> 16);
                 const uint32_t o_lo = prmt(lut, 0u, od), o_hi = prmt(lut, 0u, od >> 16);
-                const uint4 v = make_uint4(prmt(e_lo, o_lo, selA), prmt(e_lo, o_lo, selB), prmt(e_hi, o_hi, selA), prmt(e_hi, o_hi, selB));
-                if (hl16 < R.w) sts128(R.y + hl16, v);
-                __syncwarp();
-                sts8(R.y + R.w + tdelta, tval);
+                return make_uint4(prmt(e_lo, o_lo, selA), prmt(e_lo, o_lo, selB), prmt(e_hi, o_hi, selA), prmt(e_hi, o_hi, selB));
             };
-            if (np == 32u) {
+            if (np == 32u) {  // MMK_EMIT_ILP pairs at a time: their dependent chains (LDS -> SHFL -> PRMT -> STS) interleave
 #pragma unroll
-                for (uint32_t i = 0; i < 8; ++i) pass(rq[8u * i], W[i]);
+                for (uint32_t i = 0; i < 8; i += MMK_EMIT_ILP) {
+                    uint4 R[MMK_EMIT_ILP], v[MMK_EMIT_ILP];
+#pragma unroll
+                    for (uint32_t g = 0; g < MMK_EMIT_ILP; ++g) R[g] = rq[8u * (i + g)];
+#pragma unroll
+                    for (uint32_t g = 0; g < MMK_EMIT_ILP; ++g) v[g] = chunk(R[g], W[i + g]);
+#pragma unroll
+                    for (uint32_t g = 0; g < MMK_EMIT_ILP; ++g)
+                        if (hl16 < R[g].w) sts128(R[g].y + hl16, v[g]);
+                    __syncwarp();
+#pragma unroll
+                    for (uint32_t g = 0; g < MMK_EMIT_ILP; ++g) sts8(R[g].y + R[g].w + tdelta, tval);
+                }
             } else {
 #pragma unroll
                 for (uint32_t i = 0; i < 8; ++i)
-                    if (warp + 4u * i < np) pass(rq[8u * i], W[i]);
+                    if (warp + 4u * i < np) {
+                        const uint4 R = rq[8u * i];
+                        const uint4 v = chunk(R, W[i]);
+                        if (hl16 < R.w) sts128(R.y + hl16, v);
+                        __syncwarp();
+                        sts8(R.y + R.w + tdelta, tval);
+                    }
             }
         } else {  // the words of the next pair are loaded while this one is expanded
             uint2 rd = s_rd[2 * (warp < np ? warp : 0) + half];
@@ -925,7 +1010,7 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
     if (lane < np) {  // phase 2: one header piece per warp, one pair per lane
         const FastDesc f = load_fast_desc(s_fa, s_fb, lane);
         const uint32_t rd_off = (a.fq_format == MMK_FMT_HAPLOTAGGING || a.fq_format == MMK_FMT_STANDARD) ? 1u : FD_SUF(f.pk) - 13u;
-        emit_header_piece(a, f, sm, warp, rd_off);
+        emit_header_piece_w(a, f, sm, warp, rd_off);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes → visible to the bulk copy
     __syncthreads();

@@ -1469,6 +1469,7 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     CU(ctx->d_tile_flags.ensure((size_t)ctx->n_tiles + 1));
     if (!fused) CU(ctx->d_ins.ensure(ctx->s_npairs + 1));  // the three-kernel path writes the insert plan; before base_args takes the pointer
     const EmitArgs targs = base_args(ctx);
+    bool text_pending = false;  // block placement: k_mol_text is in flight on the second stream (ev_chain[0] marks its end)
     auto run_fused = [&]() -> int32_t {
         const uint32_t nm = (uint32_t)ctx->s_nmol;
         CU(ctx->d_weight.ensure((size_t)nm + 1));
@@ -1480,7 +1481,9 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
         place_block(ctx->sc, ctx->d_sch.p, plan_dev(ctx), ctx->mol0, nm, ctx->s_npairs, ctx->n_tiles, ctx->d_roff_l.p,
                     ctx->d_tile_mol0.p, ctx->d_instab.p, ctx->d_mol.p, ctx->d_text.p, ctx->text_stride, ctx->d_fdesc.p,
                     d_sum1.p, d_sum2.p, ctx->d_tile_flags.p, d_gather.p, d_err.p, ctx->d_weight.p, ctx->d_woff.p, ctx->d_scan_tmp.p,
-                    ctx->d_blk.p, ctx->d_big_list.p, ctx->d_big_count.p, ctx->stage_cap, ctx->bpb, ctx->st);
+                    ctx->d_blk.p, ctx->d_big_list.p, ctx->d_big_count.p, ctx->stage_cap, ctx->bpb, ctx->st, ctx->st_copy, ctx->ev_draw[0],
+                    ctx->ev_chain[0]);
+        text_pending = ctx->s_nmol != 0 && ctx->s_npairs != 0;
         return MMK_OK;
     };
     auto run_legacy = [&]() -> int32_t
@@ -1557,6 +1560,7 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
         break;
     }
     if (herr[0] != ~0ull) {
+        if (text_pending) cudaStreamWaitEvent(ctx->st, ctx->ev_chain[0], 0);
         uint8_t code = 0;
         CU(cudaMemcpy(&code, ctx->p_status.p + herr[0], 1, cudaMemcpyDeviceToHost));
         return fail(ctx, code, "molecule %llu: %s", herr[0], mmk_strerror(code));
@@ -1587,6 +1591,7 @@ extern "C" int32_t mmk_place(mmk_ctx *ctx, mmk_place_info *out) {
     ctx->place_info.phase_ms[1] = now_ms() - t_phase;
     t_phase = now_ms();
     int32_t rc_chunks = prepare_chunks(ctx);
+    if (text_pending) CU(cudaStreamWaitEvent(ctx->st, ctx->ev_chain[0], 0));  // whatever follows on the main stream sees the header text
     if (rc_chunks) return rc_chunks;
     ctx->place_info.phase_ms[2] = now_ms() - t_phase;
     ctx->place_info.host_ms = now_ms() - t_begin;

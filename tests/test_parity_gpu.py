@@ -154,6 +154,8 @@ def test_circular(tmp_path, strict):
     dict(read_length=(150, 108), mol_length=20000, mol_coverage=0.5, singletons=0.0, attempts=300),
     dict(mol_length=300, singletons=0.0, attempts=300),   # molecule-length law in its quantile branch (tp = e^-10)
     dict(read_length=(250, 250), insert_length=600, insert_stdev=150, singletons=0.0, attempts=300),
+    dict(read_length=(192, 161), insert_length=450, insert_stdev=60, singletons=0.0, attempts=300),   # the fast path's longest reads
+    dict(read_length=(17, 191), insert_length=300, insert_stdev=30, singletons=0.2, attempts=300),    # ... and its shortest
     # truncated(Normal(ins, sd), lower = 200) outside plain rejection (src/Structs.jl:68; the CLI admits -i 0.., mimick/__main__.py:44):
     # (the truncated mean exceeds insert_length there, so molecules whose insert count comes out near molsize / insert_length
     # cannot fit — in the reference too; mol_coverage 0.02 keeps the counts far from that bound)
