@@ -30,6 +30,25 @@ unsigned long long launch_count() { return g_launches; }
         k<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__); \
     } while (0)
 
+// Launch that lets the grid start while the previous kernel of the stream is draining — but only behind a kernel that says so
+// (griddepcontrol.launch_dependents); behind any other kernel, copy or event it is an ordinary launch.  The emit kernels of
+// consecutive chunks write different ring slots and read the same placement: nothing orders them but the stream.
+template <class K, class... A>
+static void launch_overlapped(K kernel, unsigned grid, unsigned block, size_t smem, cudaStream_t st, A... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    ++g_launches;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // ------------------------------------------------------------------------------------------
 // small device helpers
 // ------------------------------------------------------------------------------------------
@@ -998,10 +1017,10 @@ void emit(const EmitArgs &a, cudaStream_t st) {
     static const bool fill_by_copy = !(getenv("MMK_EMIT_MODE") && strcmp(getenv("MMK_EMIT_MODE"), "cta") == 0);
     if (a.tile_pairs == 32 && a.qfill && (fill_by_copy || a.err_on)) {
         if (a.err_on) {  // the error model's variant: the plain kernels keep their instruction count
-            if (a.bpb == 2) LAUNCH((k_emit_w<2, true>), a.n_tiles, 128, smem, st, a);
-            else LAUNCH((k_emit_w<4, true>), a.n_tiles, 128, smem, st, a);
-        } else if (a.bpb == 2) LAUNCH((k_emit_w<2, false>), a.n_tiles, 128, smem, st, a);
-        else LAUNCH((k_emit_w<4, false>), a.n_tiles, 128, smem, st, a);
+            if (a.bpb == 2) launch_overlapped(k_emit_w<2, true>, a.n_tiles, 128, smem, st, a);
+            else launch_overlapped(k_emit_w<4, true>, a.n_tiles, 128, smem, st, a);
+        } else if (a.bpb == 2) launch_overlapped(k_emit_w<2, false>, a.n_tiles, 128, smem, st, a);
+        else launch_overlapped(k_emit_w<4, false>, a.n_tiles, 128, smem, st, a);
         return;
     }
     EmitArgs b = a;

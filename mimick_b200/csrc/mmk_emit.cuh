@@ -805,6 +805,8 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
     __shared__ uint32_t s_off1[33], s_off2[33];
     __shared__ __align__(8) unsigned long long s_mbar;
     const uint32_t sm = (uint32_t)__cvta_generic_to_shared(smem), mb = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+    // the next chunk's kernel (another ring slot, the same placement) may fill the SMs this grid's last wave leaves idle
+    asm volatile("griddepcontrol.launch_dependents;");
     if (threadIdx.x == 0) {  // the quality character over both stages, by the copy engine
         mbar_init(mb, 1u);
         mbar_expect_tx(mb, 2u * a.stage_cap);
