@@ -341,6 +341,14 @@ __device__ __forceinline__ FastDesc load_fast_desc(const uint4 *fa, const uint2 
     f.wbase1 = f.wbase2 = 0; f.mol = y.x; f.pk = y.y;
     return f;
 }
+#ifndef MMK_EMIT_WPF
+#define MMK_EMIT_WPF 0  // 1: warp 1 of k_emit_w prefetches the reference windows of the tile one wave ahead into L2 (measured: 7 % slower — its loads sit on the path to the first barrier)
+#endif
+// look-ahead distances in tiles: one wave of CTAs is 148 SMs x 8 resident CTAs
+#ifndef MMK_EMIT_AHEAD
+#define MMK_EMIT_AHEAD 1184
+#endif
+constexpr uint32_t EMIT_AHEAD_WIN = MMK_EMIT_AHEAD, EMIT_AHEAD_DESC = MMK_EMIT_WPF ? 2u * MMK_EMIT_AHEAD : MMK_EMIT_AHEAD;
 #ifndef MMK_EMIT_ILP
 #define MMK_EMIT_ILP 8  // read pairs a warp of k_emit_w expands together (1, 2, 4 or 8)
 #endif
@@ -826,8 +834,17 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
         const uint32_t tile_m0 = a.tile_mol0[tile];
         const bool have = lane < np;
         const uint4 q = have ? a.fdesc[p0 + lane] : make_uint4(1u, 1u, 0u, 0u);
-        if (lane < 4 && blockIdx.x + 1184u < a.n_tiles)  // warm L2 for a tile that a later wave of CTAs will run
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(a.fdesc + (p0 + 1184ull * 32u)) + 128u * lane));
+        if (lane < 8 && blockIdx.x + EMIT_AHEAD_DESC < a.n_tiles) {  // warm L2 for a tile that a later wave of CTAs will run: its 512 bytes
+            // of descriptors, and the lines of the four per-tile arrays (the 16 or more tiles that share such a line start within
+            // microseconds of each other: without this every one of them waits for the same DRAM access)
+            const uint32_t tn = tile + EMIT_AHEAD_DESC;
+            const char *pf = lane < 4   ? reinterpret_cast<const char *>(a.fdesc + (p0 + (uint64_t)EMIT_AHEAD_DESC * 32u)) + 128u * lane
+                             : lane == 4 ? reinterpret_cast<const char *>(a.tile_off1 + tn + 1)
+                             : lane == 5 ? reinterpret_cast<const char *>(a.tile_off2 + tn + 1)
+                             : lane == 6 ? reinterpret_cast<const char *>(a.tile_flags + tn)
+                                         : reinterpret_cast<const char *>(a.tile_mol0 + tn);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+        }
         if (fast) {
             // stage1 = smem[0, stage_cap), stage2 = smem[stage_cap, 2 stage_cap): record offsets index smem directly
             FastDesc f;
@@ -884,6 +901,21 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
                     if (lane == 0 || f.mol != mol_prev) prefetch_l1(a.text + (uint64_t)f.mol * a.text_stride);
                 }
             }
+        }
+    }
+    if (MMK_EMIT_WPF && BPB == 2 && warp == 1 && blockIdx.x + EMIT_AHEAD_WIN < a.n_tiles) {
+        // while warp 0 unpacks this tile: the reference windows of the tile one wave ahead, into L2 (its descriptors were brought
+        // there by the tile two waves back), so that the CTA that emits it waits an L2 hit, not a DRAM access, for its words
+        const uint32_t tn = tile + EMIT_AHEAD_WIN;
+        const uint64_t pn = (uint64_t)tn * 32u + lane;
+        if (a.tile_flags[tn] && pn < a.n_pairs) {  // fast tile: every window lies inside its haplotype
+            const uint4 qn = a.fdesc[pn];
+            const uint32_t ws1 = qn.x - 1u, ws2 = qn.x + MMK_INS_LEN(qn.y) - 1u - (uint32_t)a.r2;
+            const uint32_t *w1 = a.hap + (qn.z + (ws1 >> 4)), *w2 = a.hap + (qn.z + (ws2 >> 4));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(w1));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(w1 + (((uint32_t)a.r1 + 14u) >> 4)));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(w2));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(w2 + (((uint32_t)a.r2 + 14u) >> 4)));
         }
     }
     __syncthreads();  // descriptors and the mbarrier are published
