@@ -349,6 +349,9 @@ __device__ __forceinline__ FastDesc load_fast_desc(const uint4 *fa, const uint2 
 #define MMK_EMIT_AHEAD 1184
 #endif
 constexpr uint32_t EMIT_AHEAD_WIN = MMK_EMIT_AHEAD, EMIT_AHEAD_DESC = MMK_EMIT_WPF ? 2u * MMK_EMIT_AHEAD : MMK_EMIT_AHEAD;
+#ifndef MMK_EMIT_EARLY
+#define MMK_EMIT_EARLY 1  // k_emit_w: window loads issued by every warp before the tile's descriptors are unpacked
+#endif
 #ifndef MMK_EMIT_ILP
 #define MMK_EMIT_ILP 8  // read pairs a warp of k_emit_w expands together (1, 2, 4 or 8)
 #endif
@@ -830,6 +833,25 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
     const uint32_t bytes1 = (uint32_t)(a.tile_off1[tile + 1] - t1), bytes2 = (uint32_t)(a.tile_off2[tile + 1] - t2);
     const uint64_t g1 = t1 - a.chunk_off1, g2 = t2 - a.chunk_off2;
     const uint32_t A1 = (uint32_t)(g1 & 15u), A2 = (uint32_t)(g2 & 15u);
+    uint32_t W[8];  // HOT: the first packed words of the warp's 8 pairs (lane hl of a half-warp: word hl of the read's window)
+    if (HOT && MMK_EMIT_EARLY && fast) {
+        // every warp starts the loads of its own pairs' windows from the packed descriptors, without waiting for warp 0's pass
+        // over the tile: lanes 0-7 take the R1 windows of pairs warp + 4 i, lanes 8-15 the R2 windows, a shuffle hands them out
+        uint32_t wb = 0u;
+        const uint32_t t = warp + 4u * (lane & 7u);
+        if (lane < 16u && t < np) {
+            const uint4 qe = a.fdesc[p0 + t];
+            const uint32_t ws = lane < 8u ? qe.x - 1u : qe.x + MMK_INS_LEN(qe.y) - 1u - (uint32_t)a.r2;  // 0-based window start
+            wb = qe.z + (ws >> 4);
+        }
+        const uint32_t hl = lane & 15u, half = lane >> 4;
+        const bool ldw = hl <= (((half ? (uint32_t)a.r2 : (uint32_t)a.r1) + 14u) >> 4);  // words 0 .. (15 + S - 1) / 16 hold the window
+#pragma unroll
+        for (uint32_t i = 0; i < 8; ++i) {
+            const uint32_t b = __shfl_sync(0xffffffffu, wb, (int)(i + 8u * half));
+            W[i] = ldw ? __ldg(a.hap + (b + hl)) : 0u;
+        }
+    }
     if (warp == 0) {  // descriptors of the whole tile
         const uint32_t tile_m0 = a.tile_mol0[tile];
         const bool have = lane < np;
@@ -894,10 +916,12 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
                 const uint32_t WL2 = HOT ? ((uint32_t)a.r2 + 14u) >> 4 : (BPB == 2 ? 15u : 31u);
                 const uint32_t mol_prev = __shfl_up_sync(0xffffffffu, f.mol, 1);
                 if (have) {
-                    prefetch_l1(a.hap + f.wbase1);
-                    if ((f.wbase1 ^ (f.wbase1 + WL1)) >> 5) prefetch_l1(a.hap + f.wbase1 + WL1);
-                    prefetch_l1(a.hap + f.wbase2);
-                    if ((f.wbase2 ^ (f.wbase2 + WL2)) >> 5) prefetch_l1(a.hap + f.wbase2 + WL2);
+                    if (!(HOT && MMK_EMIT_EARLY)) {
+                        prefetch_l1(a.hap + f.wbase1);
+                        if ((f.wbase1 ^ (f.wbase1 + WL1)) >> 5) prefetch_l1(a.hap + f.wbase1 + WL1);
+                        prefetch_l1(a.hap + f.wbase2);
+                        if ((f.wbase2 ^ (f.wbase2 + WL2)) >> 5) prefetch_l1(a.hap + f.wbase2 + WL2);
+                    }
                     if (lane == 0 || f.mol != mol_prev) prefetch_l1(a.text + (uint64_t)f.mol * a.text_stride);
                 }
             }
@@ -964,9 +988,10 @@ __global__ void __launch_bounds__(128, 8) k_emit_w(const __grid_constant__ EmitA
             asm volatile("" : "+r"(hl16), "+r"(qs), "+r"(lut), "+r"(rsh), "+r"(selA), "+r"(selB), "+r"(tval), "+r"(tdelta));
             const uint4 *rq = s_rq + 2u * warp + half;  // pair warp + 4 i: rq[8 i]
             const bool ldw = hl <= (((half ? (uint32_t)a.r2 : (uint32_t)a.r1) + 14u) >> 4);  // words 0 .. (15 + S - 1) / 16 hold the window
-            uint32_t W[8];
+            if (!MMK_EMIT_EARLY) {
 #pragma unroll
-            for (uint32_t i = 0; i < 8; ++i) W[i] = ldw ? __ldg(a.hap + (rq[8u * i].x + hl)) : 0u;
+                for (uint32_t i = 0; i < 8; ++i) W[i] = ldw ? __ldg(a.hap + (rq[8u * i].x + hl)) : 0u;
+            }
             mbar_wait(mb, 0u);  // the quality fill has landed
             // 16 bytes of sequence text for this lane's chunk of the read described by R
             auto chunk = [&](const uint4 R, const uint32_t Wi) -> uint4 {
