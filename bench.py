@@ -137,59 +137,118 @@ def make_c4_variants(master, n_samples=C4_SAMPLES, seed=1004, snp_rate=1e-3, ind
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).  Sampled in-process
+    through NVML every few milliseconds, so that even a 100 ms timed region (8 ranks x few steps) gets samples; the
+    `nvidia-smi -lms` loop of the recipe is the fallback when NVML cannot be opened."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
-    def __init__(self, index):
+    def __init__(self, index, pci_bus_id=None, period_s=0.004):
         self.index = index
+        self.pci = pci_bus_id
+        self.period = period_s
         self.proc = None
         self.lines = []
+        self.samples = []          # (sm_mhz, reason bits)
+        self.sm_max = None
+        self.nv = None
+        self.handle = None
+        self.run = False
+        self.thread = None
+        self.how = None
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.handle = nv.nvmlDeviceGetHandleByPciBusId(self.pci.encode() if hasattr(self.pci, "encode") else self.pci) \
+                if self.pci else nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            self._sample_nvml(nv)              # proves the calls work before the timed region depends on them
+            self.samples.clear()
+            self.nv = nv
+            self.run = True
+            self.how = "nvml"
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nv = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.pci or self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.how = "nvidia-smi"
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def _sample_nvml(self, nv):
+        sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+        try:
+            bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        self.samples.append((sm, bits))
+
+    def _loop(self):
+        while self.run:
+            try:
+                self._sample_nvml(self.nv)
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def _pump(self):
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
     def stop(self):
-        if self.proc:
+        sm, mx, reasons = [], [], set()
+        if self.nv is not None:
+            self.run = False
+            self.thread.join(timeout=2)
+            for clk, bits in self.samples:
+                sm.append(clk)
+                for bit, nm in self.REASONS:
+                    if bits & bit:
+                        reasons.add(nm)
+            mx = [self.sm_max]
+            try:
+                self.nv.nvmlShutdown()
+            except Exception:
+                pass
+        elif self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
             except Exception:
                 self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
+            for ln in self.lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "how": self.how}
         sm.sort()
         # median over the samples taken under load (upper half of the clock samples)
         load = sm[len(sm) // 2:]
-        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "how": self.how}
 
 
 def ncu_traffic():
     """DRAM bytes (read + write) of one k_emit launch from the committed `ncu --set full` capture, with the
-    launch's algorithmic bytes for comparison (profiles/r01_k_emit_ncu_full.csv); None if absent."""
-    p = os.path.join(ROOT, "profiles", "r01_k_emit_ncu_full.csv")
+    launch's algorithmic bytes for comparison (profiles/r02_k_emit_w_ncu_full.csv); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r02_k_emit_w_ncu_full.csv")
     if not os.path.exists(p):
         return None, None
     vals = {}
@@ -200,7 +259,7 @@ def ncu_traffic():
             vals[f[0]] = float(f[1]) * mult
     if len(vals) < 2:
         return None, None
-    return sum(vals.values()), "profiles/r01_k_emit_ncu_full.csv (one 2 GiB-chunk launch: 4.35 GB algorithmic)"
+    return sum(vals.values()), "profiles/r02_k_emit_w_ncu_full.csv (one 2 GiB-chunk launch of k_emit_w<2,0>: 4.34 GB of FASTQ + 0.45 GB gathered)"
 
 
 def peak_hbm():
@@ -463,7 +522,8 @@ def cuda_arm(args):
     for _ in range(args.warmup):
         step_resident()
     state["plan_ms"] = state["place_ms"] = state["hap_ms"] = 0.0
-    sampler = ClockSampler(local)
+    _p = torch.cuda.get_device_properties(local)
+    sampler = ClockSampler(local, f"{_p.pci_domain_id:08x}:{_p.pci_bus_id:02x}:{_p.pci_device_id:02x}.0")
     if rank == 0:
         sampler.start()
     barrier()
@@ -612,7 +672,7 @@ def cuda_arm(args):
                        "output_ring": f"2 x 2 x {args.chunk_mib} MiB device buffers, reused chunk after chunk"},
             "fastq_gb_per_s": total_bytes / (ms_per_step / 1e3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_emit", "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "k_emit_w", "peak_source": peak_src,
                          "algorithmic_bytes_per_step": int(algo_bytes), "kernel_ms_per_step": emit_ms / args.steps,
                          "kernel_share_of_step": (emit_ms / args.steps) / ms_per_step},
             "cpu_baseline": cpu,
