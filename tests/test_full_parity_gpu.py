@@ -6,6 +6,10 @@ every `window` read pairs, the text discarded; molecules and insert breakpoints 
 through the C ABI (mmk_emit_stream, host ring) with the same running CRC-32 taken at the same byte offsets.  Equal
 CRCs at every checkpoint = equal bytes window by window; molecules (group, slot, schema, start, size, inserts,
 barcode) and all insert breakpoints are compared element-wise.  Reference loop: src/Main.jl:44-59, :113-126.
+
+The oracle is sequential (0.5 M read pairs/s): the module starts the oracle runs of all selected tests side by side on
+host threads when its first test begins (`oracles` fixture), so the module costs the longest run (C3, 50 M pairs), not
+their sum.
 """
 import os
 import sys
@@ -33,7 +37,7 @@ class Background:
                 self.res = fn(*a, **kw)
             except BaseException as e:  # noqa: BLE001 - re-raised in join()
                 self.exc = e
-        self.t = threading.Thread(target=work)
+        self.t = threading.Thread(target=work, daemon=True)
         self.t.start()
 
     def join(self):
@@ -53,46 +57,90 @@ def bench_workload(wl, **override):
     return fmt, simkw, genome
 
 
-def run_single(wl, window, chunk_mib, shard=None, max_pairs=0, **override):
-    import mimick_b200 as M
-    fmt, simkw, genome = bench_workload(wl, **override)
-    schemas = [(nm, hap, h.numpy()) for nm, hap, h in genome]
+def start_single(wl, window, max_pairs=0, genome=None, **override):
+    """genome of the bench workload + its oracle run started in the background"""
+    fmt, simkw, g = bench_workload(wl, **override)
+    if genome is not None:
+        g = genome
+    schemas = [(nm, hap, h.numpy()) for nm, hap, h in g]
     ofmt = "tenx" if fmt == "10x" else fmt
     bg = Background(oracle_digest, ofmt, schemas, 42, 0, window, max_pairs=max_pairs, **simkw)
-    with M.Simulator(fmt, seed=42, device=0, max_chunk_bytes=chunk_mib << 20, **simkw) as sim:
-        for nm, hap, h in genome:
+    return dict(wl=wl, fmt=fmt, simkw=simkw, genome=g, bg=bg, prefix=bool(max_pairs))
+
+
+def finish_single(job, chunk_mib, shard=None):
+    import mimick_b200 as M
+    with M.Simulator(job["fmt"], seed=42, device=0, max_chunk_bytes=chunk_mib << 20, **job["simkw"]) as sim:
+        for nm, hap, h in job["genome"]:
             sim.add_contig(nm, (h.data_ptr(), h.numel()), hap)
         plan = sim.plan()
         if shard:
             sim.set_shard(*shard)
         place = sim.place()
-        orc = bg.join()
-        n = assert_digest_parity(sim, plan, place, orc, wl, prefix=bool(max_pairs))
+        orc = job["bg"].join()
+        n = assert_digest_parity(sim, plan, place, orc, job["wl"], prefix=job["prefix"])
         got = {s["name"] + "_" + str(s["haplotype"]): s["reads_current"] for s in sim.schemas()}
     return plan, place, orc, n, got
 
 
+C4_SIMKW = dict(coverage=20, n_molecules=2, mol_coverage=0.2, mol_length=80000, insert_length=500, insert_stdev=50,
+                read_length=(150, 150), singletons=0.0, attempts=300)
+
+
+def start_c4_sample():
+    import oracle as O
+    rng = np.random.default_rng(1004)
+    master, per_hap, soa = make_c4_sample(rng, 100_000_000, 110_000, 10_000)
+    mbytes = master.tobytes()
+
+    def oracle_side():
+        haps = [np.frombuffer(O.Oracle.mutate(mbytes, per_hap[h]), dtype=np.uint8) for h in (1, 2)]
+        req = int(O.lib().orc_reads_required(master.ctypes.data, master.size, 20.0, 150, 150))   # inherited from the master
+        res = oracle_digest("tellseq", [("chr1", 1, haps[0], req), ("chr1", 2, haps[1], req)], 42, 3, 500_000, **C4_SIMKW)
+        return haps, res
+    return dict(master=master, mbytes=mbytes, soa=soa, bg=Background(oracle_side))
+
+
+@pytest.fixture(scope="module")
+def oracles(request):
+    """Starts, longest first, the oracle run of every test of this module that was selected; tests join their own."""
+    mine = {it.name for it in request.session.items if str(it.path) == str(request.path)}
+    jobs = {}
+    if "test_c3_full_size_oracle_parity" in mine:
+        jobs["c3"] = start_single("c3", 1_000_000)
+    if "test_c4_sample_full_size_oracle_parity" in mine:
+        jobs["c4"] = start_c4_sample()
+    if "test_c5_prefix_oracle_parity" in mine:
+        jobs["c5"] = start_single("c5", 500_000, max_pairs=5_000_000)
+    c2 = None
+    for strict in (True, False):
+        if f"test_c2_full_size_oracle_parity[{strict}]" in mine:
+            jobs["c2", strict] = start_single("c2", 50_000, genome=c2, strict_wrap=strict)
+            c2 = jobs["c2", strict]["genome"]
+    return jobs
+
+
 @pytest.mark.parametrize("strict", [True, False])
-def test_c2_full_size_oracle_parity(strict):
+def test_c2_full_size_oracle_parity(oracles, strict):
     """configs[1]: 5 Mbp circular, stLFR, 1 haplotype, 50x — 833 333+ pairs; strict (modular) wrap as benchmarked, and
     the reference's literal circular_index (reads past the end become hap[1 : stop % n])."""
-    plan, place, orc, n, _ = run_single("c2", 50_000, 64, strict_wrap=strict)
+    plan, place, orc, n, _ = finish_single(oracles["c2", strict], 64)
     assert plan.n_pairs >= 833_333 and n >= 16
     if not strict:
         assert place.r1_bytes + place.r2_bytes > 1.2 * 833_333 * 700   # the giant D5 reads are really there
 
 
-def test_c3_full_size_oracle_parity():
+def test_c3_full_size_oracle_parity(oracles):
     """configs[2]: 250 Mbp diploid, 10X, 30x, molecule length 50 kbp — 50 M pairs, 39.8 GB of FASTQ, 2 pruning epochs."""
-    plan, place, orc, n, cur = run_single("c3", 1_000_000, 1024)
+    plan, place, orc, n, cur = finish_single(oracles["c3"], 1024)
     assert 50_000_000 <= plan.n_pairs < 50_010_000 and n >= 50 and plan.n_epochs == 2
     assert [int(c) for c in orc.reads_current] == [cur["chr1_1"], cur["chr1_2"]]
 
 
-def test_c5_prefix_oracle_parity():
+def test_c5_prefix_oracle_parity(oracles):
     """configs[4]: 3 Gbp diploid, haplotagging, 30x, 10 % singletons — the first 5 M+ read pairs of the run (the oracle
     stopped at the first group boundary after 5 M pairs) against the head of shard 0 of 64 of the full 600 M-pair plan."""
-    plan, place, orc, n, _ = run_single("c5", 500_000, 512, shard=(0, 64), max_pairs=5_000_000)
+    plan, place, orc, n, _ = finish_single(oracles["c5"], 512, shard=(0, 64))
     assert plan.n_pairs >= 600_000_000 and int(orc.checkpoints["pairs"][-1]) >= 5_000_000 and n >= 10
 
 
@@ -126,31 +174,20 @@ def make_c4_sample(rng, n, n_var, n_indel, p_alt=0.3):
     return master, per_hap, soa
 
 
-def test_c4_sample_full_size_oracle_parity():
+def test_c4_sample_full_size_oracle_parity(oracles):
     """configs[3], one of its 8 samples at full size: 100 Mbp master, 100 k SNPs + 10 k indels, TELLseq, 20x — 13.3 M
     pairs.  Haplotypes: the oracle's mutate (all SNPs, then spliceinto! in reverse file order, ProcessVariants.jl:143-155)
     against the device's segmented gather; then the simulation byte for byte (sample stream 3)."""
     import mimick_b200 as M
-    import oracle as O
-    rng = np.random.default_rng(1004)
-    master, per_hap, soa = make_c4_sample(rng, 100_000_000, 110_000, 10_000)
-    simkw = dict(coverage=20, n_molecules=2, mol_coverage=0.2, mol_length=80000, insert_length=500, insert_stdev=50,
-                 read_length=(150, 150), singletons=0.0, attempts=300)
-    mbytes = master.tobytes()
-
-    def oracle_side():
-        haps = [np.frombuffer(O.Oracle.mutate(mbytes, per_hap[h]), dtype=np.uint8) for h in (1, 2)]
-        req = int(O.lib().orc_reads_required(master.ctypes.data, master.size, 20.0, 150, 150))   # inherited from the master
-        res = oracle_digest("tellseq", [("chr1", 1, haps[0], req), ("chr1", 2, haps[1], req)], 42, 3, 500_000, **simkw)
-        return haps, res
-    bg = Background(oracle_side)
-    with M.Simulator("tellseq", seed=42, device=0, max_chunk_bytes=512 << 20, **simkw) as sim:
-        sim.add_contig("chr1", mbytes, 1)
+    job = oracles["c4"]
+    soa = job["soa"]
+    with M.Simulator("tellseq", seed=42, device=0, max_chunk_bytes=512 << 20, **C4_SIMKW) as sim:
+        sim.add_contig("chr1", job["mbytes"], 1)
         sim.set_sample_variants(3, 2, [0], np.zeros(len(soa["pos"]), dtype=np.int32), soa["pos"], soa["type"], soa["ref_len"],
                                 soa["alt"], soa["hap"])
         plan = sim.plan()
         place = sim.place()
-        haps, orc = bg.join()
+        haps, orc = job["bg"].join()
         for i in (0, 1):
             assert sim.schema_bases(i) == haps[i].tobytes(), f"haplotype {i + 1} differs from the oracle's mutate"
         n = assert_digest_parity(sim, plan, place, orc, "c4 sample 3")

@@ -317,3 +317,68 @@ def test_insert_length_table_reproduces_the_definition(mu, sd):
     zmax = min(7.9, 0.48 * 1024 / sd)
     covered = stats.norm.cdf(zmax) - stats.norm.cdf(max(-zmax, (200 - mu) / sd))   # accepted by the truncation, inside the table
     assert fast[:400_000].mean() > covered - 0.005                                   # the exact path is the exception
+
+
+# ------------------------------------------------------------------------------------------
+# julia/MimickB200.jl cannot run here (no Julia in the image): keep it in step with the header mechanically
+# ------------------------------------------------------------------------------------------
+_C2JL = {"uint32_t": "UInt32", "int32_t": "Int32", "int64_t": "Int64", "uint64_t": "UInt64", "double": "Float64",
+         "float": "Float32", "void*": "Ptr{Cvoid}", "size_t": "Csize_t"}
+
+
+def _c_struct_fields(hdr, name):
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, flags=re.S).group(1)
+    out = []
+    for decl in body.split(";"):
+        decl = " ".join(decl.split())
+        if not decl:
+            continue
+        ctype, rest = decl.split(" ", 1)
+        for item in rest.split(","):
+            item = item.strip()
+            t = ctype
+            if item.startswith("*"):
+                t, item = ctype + "*", item[1:].strip()
+            m = re.fullmatch(r"(\w+)\[(\d+)\]", item)
+            out.append((m.group(1), "NTuple{%s,%s}" % (m.group(2), _C2JL[t])) if m else (item, _C2JL[t]))
+    return out
+
+
+def _jl_struct_fields(src, name):
+    body = re.search(r"struct %s\n(.*?)\nend" % name, src, flags=re.S).group(1)
+    body = re.sub(r"#.*", "", body)
+    return [(m.group(1), m.group(2)) for m in re.finditer(r"(\w+)::([\w{},]+)", body)]
+
+
+def _c_prototypes(hdr):
+    protos = {}
+    for m in re.finditer(r"([\w ]+?[\s\*]+)(mmk_[a-z0-9_]+)\s*\(([^;{]*)\)\s*;", hdr):
+        ret, name, args = " ".join(m.group(1).split()), m.group(2), m.group(3).strip()
+        n = 0 if args in ("", "void") else len(args.split(","))
+        protos[name] = (ret.replace(" *", "*"), n)
+    return protos
+
+
+def test_julia_binding_matches_the_header():
+    """Struct layouts (field order and types) and every ccall (symbol exported, argument count, return type) of
+    julia/MimickB200.jl against include/mimick_b200.h — the wrapper keeps src/Main.jl:24 / :88's two methods."""
+    hdr = open(os.path.join(ROOT, "include", "mimick_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    jl = open(os.path.join(ROOT, "julia", "MimickB200.jl")).read()
+    for c_name, jl_name in (("mmk_params", "Params"), ("mmk_plan_info", "PlanInfo"), ("mmk_place_info", "PlaceInfo"),
+                            ("mmk_chunk", "Chunk")):
+        assert _jl_struct_fields(jl, jl_name) == _c_struct_fields(hdr, c_name), (c_name, jl_name)
+    protos = _c_prototypes(hdr)
+    ret_map = {"Int32": "int32_t", "Cvoid": "void", "Cstring": "const char*", "UInt64": "uint64_t"}
+    calls = re.findall(r"ccall\(\(:(mmk_\w+), LIB\), (\w+), \(([^)]*)\)", jl)
+    assert len(calls) >= 15
+    for sym, ret, args in calls:
+        assert sym in protos, f"{sym} is not declared in include/mimick_b200.h"
+        c_ret, c_n = protos[sym]
+        n = len([a for a in args.split(",") if a.strip()])
+        assert n == c_n, f"{sym}: ccall passes {n} arguments, the header declares {c_n}"
+        assert ret_map[ret] == c_ret, f"{sym}: ccall returns {ret}, the header {c_ret}"
+    # the keyword surface of the reference's two methods (src/Main.jl:24-41, :88-103)
+    for kw in ("coverage", "n_molecules", "mol_coverage", "mol_length", "insert_length", "insert_stdev", "read_length",
+               "singletons", "circular", "attempts", "seed", "mask", "prefix", "outdir", "quiet"):
+        assert re.search(r"\b%s\b\s*(::\w+)?\s*=" % kw, jl), kw
