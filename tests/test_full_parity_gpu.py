@@ -7,9 +7,9 @@ through the C ABI (mmk_emit_stream, host ring) with the same running CRC-32 take
 CRCs at every checkpoint = equal bytes window by window; molecules (group, slot, schema, start, size, inserts,
 barcode) and all insert breakpoints are compared element-wise.  Reference loop: src/Main.jl:44-59, :113-126.
 
-The oracle is sequential (0.5 M read pairs/s): the module starts the oracle runs of all selected tests side by side on
-host threads when its first test begins (`oracles` fixture), so the module costs the longest run (C3, 50 M pairs), not
-their sum.
+The oracle is sequential (0.6 M read pairs/s): the oracle runs of all selected tests of this module start side by side
+on host threads when the test session begins and the module runs last (tests/conftest.py), so they finish beside the
+other GPU tests instead of in front of them.
 """
 import os
 import sys
@@ -101,23 +101,33 @@ def start_c4_sample():
     return dict(master=master, mbytes=mbytes, soa=soa, bg=Background(oracle_side))
 
 
-@pytest.fixture(scope="module")
-def oracles(request):
-    """Starts, longest first, the oracle run of every test of this module that was selected; tests join their own."""
-    mine = {it.name for it in request.session.items if str(it.path) == str(request.path)}
+JOBS = {}
+
+
+def start_jobs(selected):
+    """Starts, longest first, the oracle run of every selected test of this module; tests join their own."""
     jobs = {}
-    if "test_c3_full_size_oracle_parity" in mine:
+    if "test_c3_full_size_oracle_parity" in selected:
         jobs["c3"] = start_single("c3", 1_000_000)
-    if "test_c4_sample_full_size_oracle_parity" in mine:
+    if "test_c4_sample_full_size_oracle_parity" in selected:
         jobs["c4"] = start_c4_sample()
-    if "test_c5_prefix_oracle_parity" in mine:
+    if "test_c5_prefix_oracle_parity" in selected:
         jobs["c5"] = start_single("c5", 500_000, max_pairs=5_000_000)
     c2 = None
     for strict in (True, False):
-        if f"test_c2_full_size_oracle_parity[{strict}]" in mine:
+        if f"test_c2_full_size_oracle_parity[{strict}]" in selected:
             jobs["c2", strict] = start_single("c2", 50_000, genome=c2, strict_wrap=strict)
             c2 = jobs["c2", strict]["genome"]
     return jobs
+
+
+@pytest.fixture(scope="module")
+def oracles(request):
+    """conftest.py starts the jobs with the session and runs this module last, so the oracle works beside the other
+    GPU tests; run on its own, the module starts them here."""
+    if not JOBS:
+        JOBS.update(start_jobs({it.name for it in request.session.items if str(it.path) == str(request.path)}))
+    return JOBS
 
 
 @pytest.mark.parametrize("strict", [True, False])

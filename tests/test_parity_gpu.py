@@ -589,10 +589,10 @@ def _env(**kv):
 
 
 @pytest.mark.parametrize("kw", [
-    dict(coverage=30, singletons=0.1),
-    dict(coverage=30, singletons=1.0),                                  # every molecule one pair
-    dict(coverage=40, mol_length=2_000_000, mol_coverage=0.5, singletons=0.0),   # molecules of 1000s of pairs
-    dict(coverage=30, mol_length=400_000, mol_coverage=0.6, singletons=0.3, n_molecules=4),   # a mix of short and long molecules
+    dict(coverage=15, singletons=0.1),
+    dict(coverage=15, singletons=1.0),                                  # every molecule one pair
+    dict(coverage=20, mol_length=2_000_000, mol_coverage=0.5, singletons=0.0),   # molecules of 1000s of pairs
+    dict(coverage=15, mol_length=400_000, mol_coverage=0.6, singletons=0.3, n_molecules=4),   # a mix of short and long molecules
 ])
 def test_placement_paths_agree_with_the_oracle(tmp_path, kw):
     """The default placement path (one CTA per block of molecules, big molecules through their own kernel) and the
