@@ -247,7 +247,7 @@ class ClockSampler:
 
 def ncu_traffic():
     """DRAM bytes (read + write) of one k_emit launch from the committed `ncu --set full` capture, with the
-    launch's algorithmic bytes for comparison (profiles/r02_k_emit_w_ncu_full.csv); None if absent."""
+    launch's algorithmic bytes for comparison (profiles/r02_final_k_emit_w_ncu_full.csv); None if absent."""
     p = os.path.join(ROOT, "profiles", "r02_k_emit_w_ncu_full.csv")
     if not os.path.exists(p):
         return None, None
@@ -259,7 +259,7 @@ def ncu_traffic():
             vals[f[0]] = float(f[1]) * mult
     if len(vals) < 2:
         return None, None
-    return sum(vals.values()), "profiles/r02_k_emit_w_ncu_full.csv (one 2 GiB-chunk launch of k_emit_w<2,0>: 4.34 GB of FASTQ + 0.45 GB gathered)"
+    return sum(vals.values()), "profiles/r02_final_k_emit_w_ncu_full.csv (one 2 GiB-chunk launch of k_emit_w<2,0>: 4.34 GB of FASTQ + 0.45 GB gathered)"
 
 
 def peak_hbm():
