@@ -20,4 +20,4 @@ for r in rows[1:]:
 total = sum(tot.values())
 print("kernel,launches,total_ms,share_pct")
 for k, v in tot.most_common():
-    print(f"{k},{cnt[k]},{v:.3f},{100 * v / total:.1f}")
+    print(f'"{k}",{cnt[k]},{v:.3f},{100 * v / total:.1f}')
