@@ -545,7 +545,55 @@ __device__ __forceinline__ void emit_header_piece(const EmitArgs &a, const FastD
 // Phase 2 as k_emit_w runs it — one warp per piece, one pair per lane, the pieces of about equal length: 0 the prefix,
 // 1 both decimal numbers, 2 the first 16 bytes of the format tail, 3 the rest of it and the inline barcode.  Text is read as
 // aligned 32-bit words and shifted into place (the molecule's text line is 16-byte aligned, its tail starts at byte P).
+#ifndef MMK_HDR_WORDS
+#define MMK_HDR_WORDS 0  // 1: header text goes into the stages as aligned 32-bit words (byte stores only up to the first and after the last whole word); 0: byte stores.  Measured equal (emit 94.4 / 95.2 ms against 94.9 / 95.0 ms, C5, same box): the header stores' bank conflicts are not what bounds the kernel
+#endif
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// n bytes of text from global memory into both stages, all three at any byte alignment.  The bytes are exactly [0, n) of each
+// destination (the other header pieces are written by other warps at the same time: nothing may spill).  v_j = source bytes
+// [4j, 4j + 4); a destination whose first aligned word starts h bytes in takes funnel(v_j, v_j+1, 8 h) as that word.
+// Reads at most 11 bytes past the text wanted (the text array ends with a spare line).
+__device__ __forceinline__ void copy_text_words(const uint8_t *src, uint32_t n, uint32_t d1, uint32_t d2) {
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(src - mis);
+    uint32_t x0 = __ldg(w);
+    uint32_t x1 = __ldg(++w);
+    uint32_t vp = __funnelshift_r(x0, x1, 8u * mis);
+    x0 = x1;
+    const uint32_t h1 = (4u - (d1 & 3u)) & 3u, h2 = (4u - (d2 & 3u)) & 3u;
+#pragma unroll
+    for (uint32_t b = 0; b < 3; ++b) {
+        if (b < h1 && b < n) sts8(d1 + b, vp >> (8u * b));
+        if (b < h2 && b < n) sts8(d2 + b, vp >> (8u * b));
+    }
+    for (uint32_t o = 0; o < n; o += 4u) {
+        x1 = __ldg(++w);
+        const uint32_t v = __funnelshift_r(x0, x1, 8u * mis);
+        x0 = x1;
+        const uint32_t y1 = __funnelshift_r(vp, v, 8u * h1), y2 = __funnelshift_r(vp, v, 8u * h2);
+        const uint32_t o1 = o + h1, o2 = o + h2;
+        if (o1 + 4u <= n) sts32(d1 + o1, y1);
+        else {
+#pragma unroll
+            for (uint32_t b = 0; b < 3; ++b)
+                if (o1 + b < n) sts8(d1 + o1 + b, y1 >> (8u * b));
+        }
+        if (o2 + 4u <= n) sts32(d2 + o2, y2);
+        else {
+#pragma unroll
+            for (uint32_t b = 0; b < 3; ++b)
+                if (o2 + b < n) sts8(d2 + o2 + b, y2 >> (8u * b));
+        }
+        vp = v;
+    }
+}
 __device__ __forceinline__ void copy_text_bytes(const uint8_t *src, uint32_t n, uint32_t d1, uint32_t d2) {
+#if MMK_HDR_WORDS
+    copy_text_words(src, n, d1, d2);
+    return;
+#endif
     const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u);
     const uint32_t *w = reinterpret_cast<const uint32_t *>(src - mis);
     uint32_t x0 = __ldg(w);
