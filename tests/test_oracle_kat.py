@@ -346,3 +346,107 @@ def test_error_model_indels_shift_the_template(tmp_path):
     # quality drops by 10 exactly where something was inserted (no substitutions here)
     ins_marks = sum(q.count(bytes([33 + 23 - 10 + j])) for q in nq[:2000] for j in (-2, -1, 0, 1, 2))
     assert ins_marks > 0
+
+
+# ------------------------------------------------------------------------------------------
+# A second, independent restatement of the text half (barcode enumerators, extraction, the five record formats),
+# written in Python straight from the Julia sources, run over EVERY record of small oracle runs: the C oracle's
+# plan (molecules, insert breakpoints) goes in, the whole R1 / R2 text must come out.
+# ------------------------------------------------------------------------------------------
+_COMP = bytes.maketrans(b"ACGTMRWSYKVHDBN", b"TGCAKYWSRMBDHVN")   # BioSequences complement of the 4-bit alphabet
+
+
+def _julia_product(k, factors):
+    """k-th element (0-based) of Base.Iterators.product(factors...): the FIRST factor varies fastest (Barcodes.jl:12-34)."""
+    out = []
+    for f in factors:
+        out.append(f[k % len(f)])
+        k //= len(f)
+    assert k == 0, "barcodes exhausted"
+    return out
+
+
+def _py_barcode(style, k):
+    if style == "haplotagging":     # product('A', 1:96, 'C', 1:96, 'B', 1:96, 'D', 1:96) -> A%02dC%02dB%02dD%02d (Barcodes.jl:53-56)
+        a, c, b, d = _julia_product(k, [range(1, 97)] * 4)
+        return b"A%02dC%02dB%02dD%02d" % (a, c, b, d)
+    if style == "stlfr":            # product(1:2000, 1:2000, 1:2000) joined by "_" (Barcodes.jl:64)
+        return b"_".join(b"%d" % x for x in _julia_product(k, [range(1, 2001)] * 3))
+    n = 18 if style == "tellseq" else 16   # product(("ATGC" for i in 1:n)...) joined (Barcodes.jl:72-74)
+    return bytes(_julia_product(k, [b"ATGC"] * n))
+
+
+def _py_circular_index(seq, start, stop):
+    """circular_index (Breakpoints.jl:111-121), literally: 1-based inclusive range; past the end it is
+    seq[start:end] * seq[begin:(stop % n)] (an empty range when start > n, as Julia indexes it)."""
+    n = len(seq)
+    if stop > n:
+        return seq[start - 1:] + seq[:stop % n]
+    return seq[start - 1:stop]
+
+
+def _py_records(fq_format, bc_style, schemas, res, r1_len, r2_len):
+    """format_R1 / format_R2 (FormatFASTQ.jl:8-137) over extract_sequences! (Breakpoints.jl:95-109)."""
+    tails = {
+        "stlfr": (b"#%s 1:N:0:ATGACA", b"#%s 2:N:0:ATGACA"),
+        "haplotagging": (b"/1\tBX:Z:%s", b"/2\tBX:Z:%s"),
+        "tellseq": (b":%s 1:N:0:ATGACA", b":%s 2:N:0:ATGACA"),
+        "tenx": (b"|%s 1:N:0:ATGACA", b"|%s 2:N:0:ATGACA"),
+        "standard": (b"/1\tVX:i:1\tBX:Z:%s", b"/2\tVX:i:1\tBX:Z:%s"),
+    }[fq_format]
+    out1, out2 = [], []
+    for m in res.molecules:
+        name, hap, seq = schemas[int(m["schema"])]
+        bc = _py_barcode(bc_style, int(m["barcode_index"]))
+        start, size = int(m["start"]), int(m["molsize"])
+        header = b"@%s:%d|%d:%d|" % (name.encode(), hap, start, start + size)
+        a, b = int(m["first_read"]), int(m["first_read"]) + int(m["n_frags"])
+        reads = []
+        for bs, be in zip(res.insert_start[a:b].tolist(), res.insert_stop[a:b].tolist()):
+            r1 = _py_circular_index(seq, bs, bs + r1_len - 1).translate(_COMP)[::-1]      # circular_index_R2: reverse complement
+            r2 = _py_circular_index(seq, be - r2_len + 1, be)                               # circular_index_R1: forward
+            reads.append((bs, be, r1, r2))
+        inline = bc if fq_format == "tenx" else b""
+        q1 = b"I" * (len(reads[0][2]) + len(inline))     # "I"^length(first read of the molecule) (+ barcode for 10x R1)
+        q2 = b"I" * len(reads[0][3])
+        for bs, be, r1, r2 in reads:
+            out1.append(header + b"%d:%d" % (bs, be) + tails[0] % bc + b"\n" + inline + r1 + b"\n+\n" + q1 + b"\n")
+            out2.append(header + b"%d:%d" % (bs, be) + tails[1] % bc + b"\n" + r2 + b"\n+\n" + q2 + b"\n")
+    return b"".join(out1), b"".join(out2)
+
+
+@pytest.mark.parametrize("fmt,fq,bc", [
+    ("haplotagging", "haplotagging", "haplotagging"), ("stlfr", "stlfr", "stlfr"), ("tellseq", "tellseq", "tellseq"),
+    ("10x", "tenx", "tenx"), ("standard", "standard", "tellseq"), ("standard:haplotagging", "standard", "haplotagging"),
+    ("standard:stlfr", "standard", "stlfr"),
+])
+def test_every_record_rederived_in_python(tmp_path, fmt, fq, bc):
+    rng = np.random.default_rng(101)
+    p1 = os.path.join(str(tmp_path), "a.fa")
+    p2 = os.path.join(str(tmp_path), "b.fa")
+    recs1 = [("chrA", random_bases(rng, 60_000)), ("scaffold_2", random_bases(rng, 9_000, b"ACGTRYKMSWN"))]
+    recs2 = [("chrA", random_bases(rng, 60_100)), ("scaffold_2", random_bases(rng, 9_050))]
+    write_fasta(p1, recs1)
+    write_fasta(p2, recs2)
+    schemas = [(n, 1, s) for n, s in recs1] + [(n, 2, s) for n, s in recs2]
+    res = O.mimick_single([p1, p2], fmt, seed=12, coverage=6, attempts=300, singletons=0.3, read_length=(150, 120),
+                          mol_length=20000)
+    assert len(res.molecules) > 40 and len(res.insert_start) > 400
+    want1, want2 = _py_records(fq, bc, schemas, res, 150, 120)
+    assert res.r1 == want1 and res.r2 == want2
+
+
+@pytest.mark.parametrize("fmt,fq,bc", [("stlfr", "stlfr", "stlfr"), ("10x", "tenx", "tenx")])
+def test_every_record_rederived_in_python_circular_literal_wrap(tmp_path, fmt, fq, bc):
+    """circular=true with the reference's literal circular_index: molecules start anywhere on the contig, reads
+    that pass the end become seq[start:end] * seq[1:stop % n] — longer or shorter than nominal — and the quality line keeps the
+    length of the molecule's first read."""
+    rng = np.random.default_rng(102)
+    p = os.path.join(str(tmp_path), "c.fa")
+    recs = [("plasmid", random_bases(rng, 30_000))]
+    write_fasta(p, recs)
+    res = O.mimick_single([p], fmt, seed=5, coverage=20, attempts=300, singletons=0.2, circular=True, mol_length=12000)
+    want1, want2 = _py_records(fq, bc, [("plasmid", 1, recs[0][1])], res, 150, 150)
+    assert res.r1 == want1 and res.r2 == want2
+    lens = {len(x) for x in res.r1.split(b"\n")[1::4]}
+    assert len(lens) > 1, "no read crossed the end of the contig: the wrap rule was not exercised"
