@@ -450,3 +450,150 @@ def test_every_record_rederived_in_python_circular_literal_wrap(tmp_path, fmt, f
     assert res.r1 == want1 and res.r2 == want2
     lens = {len(x) for x in res.r1.split(b"\n")[1::4]}
     assert len(lens) > 1, "no read crossed the end of the contig: the wrap rule was not exercised"
+
+
+# ------------------------------------------------------------------------------------------
+# The plan half, the same way: the Julia loop (Main.jl:44-59) restated in Python with every rand() replaced by the next
+# variate of the stream the oracle RECORDED (the replay contract of SURVEY §8a-bis).  The interpreter checks every tag, so
+# a draw taken in another order, a missing redraw or a different truncation branch fails at the first variate.
+# ------------------------------------------------------------------------------------------
+class _Replay:
+    TAGS = dict(NMOL=2, TARGET=3, MOLSIZE=4, SINGLETON=5, NFRAGS=6, INSERT=7, START=8, GAP=9)
+
+    def __init__(self, variates):
+        self.v, self.k = variates, 0
+
+    def _pop(self, tag):
+        e = self.v[self.k]
+        assert int(e["tag"]) == self.TAGS[tag], f"variate {self.k}: stream has tag {int(e['tag'])}, the Julia order wants {tag}"
+        self.k += 1
+        return e
+
+    def real(self, tag):            # rand() / randexp() / randn(): the double itself
+        return float(np.array([self._pop(tag)["bits"]], dtype="<u8").view("<f8")[0])
+
+    def index(self, tag, n):        # rand(a:b) as an offset in [0, n)
+        e = self._pop(tag)
+        r = int(np.array([e["bits"]], dtype="<u8").view("<i8")[0])
+        assert int(e["aux"]) == (n & 0xffffffff) and 0 <= r < n, (tag, n, r)
+        return r
+
+
+def _trunc_exp_rand(rp, tag, theta, lower, upper=None):
+    """rand(truncated(Exponential(theta), lower, upper)) — Distributions.jl src/truncate.jl: rejection on theta * randexp() when
+    the kept mass exceeds 0.25, else the quantile of lcdf + rand() * tp (the third branch, tp <= sqrt(eps), is not reachable here)."""
+    import math
+    cdf = lambda x: -math.expm1(-max(x, 0.0) / theta)
+    lcdf = cdf(lower)
+    tp = (cdf(upper) if upper is not None else 1.0) - lcdf
+    if tp > 0.25:
+        while True:
+            r = theta * rp.real(tag)
+            if r >= lower and (upper is None or r <= upper):
+                return r
+    assert tp > 1.5e-8
+    return -theta * math.log1p(-(lcdf + rp.real(tag) * tp))
+
+
+def _py_replay_plan(variates, schemas, *, n_molecules, mol_length, mol_coverage, insert_length, insert_stdev, singletons,
+                    attempts, circular):
+    """schemas: [(sequence length, reads_required)] in first-seen order.  Returns (molecules, inserts)."""
+    import math
+    rp = _Replay(variates)
+    lowerbound = max(3000, int(mol_length * mol_coverage * 0.25)) if mol_coverage < 1 else mol_coverage * (insert_length + 0.75 * insert_stdev)
+    assert (200 - insert_length) / insert_stdev < -0.6      # truncated(Normal, lower = 200) keeps > 0.3 of the mass: plain rejection
+    current = [0] * len(schemas)
+    live = list(range(len(schemas)))                         # keys(schema) in first-seen order (stated deviation i)
+    mols, ins = [], []
+    while live:                                              # while !isempty(schema)            Main.jl:44
+        if n_molecules > 0:                                  # get_n_molecules                   Common.jl:89-91, Structs.jl:63-67
+            x = _trunc_exp_rand(rp, "NMOL", float(n_molecules), 1.0, 2.5 * n_molecules)
+            n_mol = int(round(x))                            # round(x, digits = 0): ties to even, like Python's round
+        else:
+            n_mol = abs(n_molecules)
+        targets = [live[rp.index("TARGET", len(live))] for _ in range(n_mol)]     # rand(candidates, n_mol)  Main.jl:47
+        for t in targets:
+            seq_len = schemas[t][0]
+            molsize, tries = seq_len + 1, 0                  # get_molecule_size                 Breakpoints.jl:149-163
+            while molsize > seq_len and tries < 30:
+                tries += 1
+                molsize = _trunc_exp_rand(rp, "MOLSIZE", float(mol_length), float(lowerbound))
+            molsize = int(min(molsize, seq_len))
+            if singletons > 0.0 and rp.real("SINGLETON") <= singletons:           # calculate_n_frags    Breakpoints.jl:171-196
+                n = 1
+            else:
+                max_possible = molsize / insert_length
+                if max_possible == 1:
+                    n = 1
+                else:
+                    _n = max(2.0, molsize * mol_coverage / insert_length) if mol_coverage < 1 else float(mol_coverage)
+                    n = int(_trunc_exp_rand(rp, "NFRAGS", _n, 2.0, max_possible))
+
+            def draw_sizes():                                # rand(params.insert_size, n_reads): randn() until >= the lower bound
+                out = []
+                for _ in range(n):
+                    while True:
+                        z = rp.real("INSERT")
+                        if not z < (200 - insert_length) / insert_stdev:
+                            out.append(insert_length + insert_stdev * z)
+                            break
+                return out
+            sizes, tries = draw_sizes(), 0                   # calculate_insert_sizes            Breakpoints.jl:205-218
+            while sum(sizes) > molsize and tries < attempts:     # float sum, left to right (stated deviation iii)
+                tries += 1
+                sizes = draw_sizes()
+            assert not sum(sizes) > molsize
+            lens = [int(s) for s in sizes]                   # trunc.(Int, read_sizes)
+            adjusted_end = seq_len if circular else max(seq_len - molsize, 1)     # get_sequences        Breakpoints.jl:235-242
+            start = 1 + rp.index("START", adjusted_end)
+            remaining = (molsize + 1) - sum(lens)            # length(start:start+molsize) - sum     seq_breakpoints!  :21-35
+            assert remaining >= 0
+            cursor = start
+            first = len(ins)
+            for ln in lens:
+                gap = rp.index("GAP", remaining + 1)
+                s0 = cursor + gap
+                ins.append((s0, s0 + ln - 1))
+                cursor = s0 + ln
+                remaining -= gap
+            mols.append((t, start, molsize, len(lens), first))
+            current[t] += len(lens)                          # tracker                            Main.jl:54
+        live = [t for t in live if current[t] < schemas[t][1]]    # filter!(is_incomplete, schema)    Main.jl:58
+    assert rp.k == len(variates), "the oracle drew variates the Julia order does not account for"
+    return mols, ins, current
+
+
+@pytest.mark.parametrize("kw", [
+    dict(coverage=8, singletons=0.3, n_molecules=2, mol_length=20000),
+    dict(coverage=5, singletons=0.0, n_molecules=-3, mol_length=30000, mol_coverage=0.5),      # fixed molecules per barcode
+    dict(coverage=6, singletons=0.7, n_molecules=3, mol_length=8000, circular=True),
+    dict(coverage=4, singletons=0.1, n_molecules=2, mol_length=20000, insert_length=400, insert_stdev=150),   # redraws at the 200 bound
+])
+def test_plan_rederived_in_python_from_the_recorded_variates(tmp_path, kw):
+    rng = np.random.default_rng(33)
+    p1 = os.path.join(str(tmp_path), "a.fa")
+    p2 = os.path.join(str(tmp_path), "b.fa")
+    # c3 is shorter than most molecules (30 draws, then the cap: Breakpoints.jl:155-161); c4 is the CI fixture's 1 004-base contig:
+    # truncated(Exponential(2), 2, 2.008) keeps 1.5e-3 of the mass, so n_frags comes from the quantile branch
+    recs1 = [("c1", random_bases(rng, 90_000)), ("c2", random_bases(rng, 25_000)), ("c3", random_bases(rng, 6_000)),
+             ("c4", random_bases(rng, 1_004))]
+    recs2 = [("c1", random_bases(rng, 90_500)), ("c2", random_bases(rng, 24_000)), ("c3", random_bases(rng, 6_100)),
+             ("c4", random_bases(rng, 1_004))]
+    write_fasta(p1, recs1)
+    write_fasta(p2, recs2)
+    res = O.mimick_single([p1, p2], "haplotagging", seed=77, attempts=300, record=True, **kw)
+    par = dict(n_molecules=2, mol_length=80000, mol_coverage=0.2, insert_length=500, insert_stdev=50, singletons=0.0,
+               attempts=300, circular=False)
+    par.update({k: v for k, v in kw.items() if k in par})
+    lens = [len(s) for _, s in recs1] + [len(s) for _, s in recs2]
+    schemas = list(zip(lens, [int(r) for r in res.reads_required]))
+    mols, ins, current = _py_replay_plan(res.variates, schemas, **par)
+    m = res.molecules
+    assert len(mols) == len(m) and len(mols) > 30
+    got = np.array(mols, dtype=np.int64)
+    for col, f in enumerate(("schema", "start", "molsize", "n_frags", "first_read")):
+        assert np.array_equal(got[:, col], m[f].astype(np.int64)), f
+    got_ins = np.array(ins, dtype=np.int64)
+    assert np.array_equal(got_ins[:, 0], res.insert_start) and np.array_equal(got_ins[:, 1], res.insert_stop)
+    assert current == [int(c) for c in res.reads_current]
+    assert len({int(x) for x in m["schema"]}) == 8            # every schema was live and drawn
