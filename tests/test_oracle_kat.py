@@ -597,3 +597,45 @@ def test_plan_rederived_in_python_from_the_recorded_variates(tmp_path, kw):
     assert np.array_equal(got_ins[:, 0], res.insert_start) and np.array_equal(got_ins[:, 1], res.insert_stop)
     assert current == [int(c) for c in res.reads_current]
     assert len({int(x) for x in m["schema"]}) == 8            # every schema was live and drawn
+
+
+def _py_mutate(master: bytes, variants):
+    """build_sample_schema's inner loop (ProcessVariants.jl:169-176) on a Python list: every SNP first (seq[pos] = alt[1]), then the
+    non-SNPs in REVERSE file order, each spliceinto!(seq, pos:pos+len(ref)-1, alt) on the sequence as it then is."""
+    seq = bytearray(master)
+    for pos, typ, ref, alt in variants:
+        if typ == 0:
+            seq[pos - 1] = ord(alt[0])
+    for pos, typ, ref, alt in reversed([v for v in variants if v[1] != 0]):
+        seq[pos - 1:pos - 1 + len(ref)] = alt.encode()
+    return bytes(seq)
+
+
+@pytest.mark.parametrize("seed,sorted_sites", [(1, True), (2, True), (3, False)])
+def test_mutate_rederived_in_python(seed, sorted_sites):
+    """Random SNP / insertion / deletion / MNP sets — in file order as a VCF has them, and shuffled with overlapping REF spans,
+    where the reference's reverse-order splice still has a literal meaning — against the oracle's mutate."""
+    rng = np.random.default_rng(seed)
+    master = random_bases(rng, 20_000)
+    pos = np.sort(rng.choice(np.arange(2, 19_900), size=600, replace=False)) if sorted_sites else rng.integers(2, 19_900, size=600)
+    variants = []
+    for p in pos.tolist():
+        kind = rng.integers(0, 4)
+        if kind == 0:
+            variants.append((p, 0, chr(master[p - 1]), "ACGT"[int(rng.integers(0, 4))]))
+        elif kind == 1:      # insertion: REF = anchor, ALT = anchor + k bases
+            variants.append((p, 1, chr(master[p - 1]), chr(master[p - 1]) + random_bases(rng, int(rng.integers(1, 12))).decode()))
+        elif kind == 2:      # deletion: REF = anchor + k bases, ALT = anchor
+            k = int(rng.integers(1, 12))
+            variants.append((p, 1, master[p - 1:p + k].decode(), chr(master[p - 1])))
+        else:                # MNP / complex: both longer than one base
+            k = int(rng.integers(2, 6))
+            variants.append((p, 1, master[p - 1:p - 1 + k].decode(), random_bases(rng, int(rng.integers(2, 6))).decode()))
+    if sorted_sites:         # keep REF spans inside the still-untouched prefix, as a normalised VCF does
+        keep, last_end = [], 0
+        for v in variants:
+            if v[0] > last_end:
+                keep.append(v)
+                last_end = v[0] + len(v[2]) - 1
+        variants = keep
+    assert O.Oracle.mutate(master, variants) == _py_mutate(master, variants)
