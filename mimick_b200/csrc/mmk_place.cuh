@@ -137,7 +137,11 @@ constexpr uint32_t PB_TARGET = MMK_PB_TARGET;                 // weight of a blo
 constexpr uint32_t PB_CAP = PB_TARGET + PB_BIG;               // pairs in shared memory: < TARGET + W + BIG - W * molecules
 constexpr uint32_t PB_MAXM = (PB_TARGET + PB_BIG) / PB_W + 2; // molecules of a block: each weighs >= W
 constexpr uint32_t PB_SORT_MAX = 160;  // blocks with more molecules run phase B in molecule order
-constexpr size_t PB_SMEM = sizeof(InsTable) + (size_t)PB_CAP * 12u + (size_t)(PB_MAXM + 1u) * 16u + (size_t)PB_SORT_MAX * 2u + 16u;
+#ifndef MMK_PB_SCAN
+#define MMK_PB_SCAN 0  // 1: phase B stops a molecule's chain when its leeway is used up; the offsets after that point come from a block-wide prefix sum of the lengths (all threads) instead of the molecule thread's serial loop.  Measured (C5, alternating builds on one box, 63 GPU tests green with it): placement 17.53 ms against 17.79 ms — the serial tail is not what the other warps wait for; kept as a switch
+#endif
+constexpr size_t PB_SMEM = sizeof(InsTable) + (size_t)PB_CAP * 12u + (size_t)(PB_MAXM + 1u) * 16u + (size_t)PB_SORT_MAX * 2u + 16u +
+                           (MMK_PB_SCAN ? (size_t)(PB_MAXM + 1u) * 2u + 2u : 0u);
 
 struct PlaceArgs {
     SimConst sc;
@@ -239,7 +243,10 @@ __global__ void __launch_bounds__(PB_THREADS, 4) k_place_block(const __grid_cons
     uint32_t *s_meta = s_start + PB_MAXM + 1;                                // MPK word
     uint16_t *s_len = reinterpret_cast<uint16_t *>(s_meta + PB_MAXM + 1);    // [PB_CAP]
     uint16_t *s_mj = s_len + PB_CAP;                                         // [PB_CAP] block-local molecule of every slot
-    uint16_t *s_perm = s_mj + PB_CAP;                                        // [PB_SORT_MAX] molecules by decreasing insert count
+    uint16_t *s_perm = s_mj + PB_CAP;                                        // [PB_SORT_MAX] molecules by decreasing insert count; after phase B: warp totals of the scan
+#if MMK_PB_SCAN
+    uint16_t *s_kstop = s_perm + PB_SORT_MAX;                                // [nm] inserts placed by the chain (the rest: prefix sum)
+#endif
     const SimConst &sc = a.sc;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t m_lo = a.blk[blockIdx.x], m_hi = a.blk[blockIdx.x + 1u];
@@ -369,6 +376,13 @@ __global__ void __launch_bounds__(PB_THREADS, 4) k_place_block(const __grid_cons
                 bits = nbits;
                 len = nlen;
             }
+#if MMK_PB_SCAN
+            // no leeway left: inserts k.. lie back to back from `cursor` on — their offsets are a prefix sum of the lengths, taken by the
+            // whole block after this phase.  so + len grows with the insert index, so the bound on the R2 window is decided by insert 0.
+            s_kstop[j] = (uint16_t)k;
+            if (k == 0u && len < need_end) status = MMK_ERR_BOUNDS;
+            if (!status) first_read_quals(sc, (int64_t)start, k ? s_bits[s0].x : 0u, s_len[s0], n_hap, q1, q2);
+#else
             for (; k < nfrags; ++k) {  // no leeway left: back to back
                 const uint32_t l = s_len[s0 + k];
                 s_bits[s0 + k].x = cursor;
@@ -376,7 +390,11 @@ __global__ void __launch_bounds__(PB_THREADS, 4) k_place_block(const __grid_cons
                 if (cursor < need_end) status = MMK_ERR_BOUNDS;
             }
             if (!status) first_read_quals(sc, (int64_t)start, s_bits[s0].x, s_len[s0], n_hap, q1, q2);
+#endif
         }
+#if MMK_PB_SCAN
+        else s_kstop[j] = 0;
+#endif
         uint32_t P, SUF;
         header_lens(sc, S, (int64_t)start, molsize, gi, P, SUF);
         const uint32_t qreg = q1 == (uint32_t)sc.r1 + inl && q2 == (uint32_t)sc.r2;
@@ -397,6 +415,31 @@ __global__ void __launch_bounds__(PB_THREADS, 4) k_place_block(const __grid_cons
         a.mol[ml] = r;
     }
     __syncthreads();
+#if MMK_PB_SCAN
+    // ---- exclusive prefix sum of the (final) lengths over the block's slots, into the high word of the dead gap bits ----------
+    {
+        const uint32_t spt = (ns + PB_THREADS - 1u) / PB_THREADS;
+        const uint32_t b0 = min(tid * spt, ns), b1 = min(b0 + spt, ns);
+        uint32_t tsum = 0;
+        for (uint32_t slot = b0; slot < b1; ++slot) tsum += s_len[slot];
+        uint32_t inc = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((int)lane >= o) inc += y;
+        }
+        uint32_t *s_wtot = reinterpret_cast<uint32_t *>(s_perm);  // the permutation is no longer needed
+        if (lane == 31u) s_wtot[warp] = inc;
+        __syncthreads();
+        uint32_t run = inc - tsum;
+        for (uint32_t w = 0; w < warp; ++w) run += s_wtot[w];
+        for (uint32_t slot = b0; slot < b1; ++slot) {
+            s_bits[slot].y = run;
+            run += s_len[slot];
+        }
+    }
+    __syncthreads();
+#endif
     // ---- phase C: one warp per tile of the emit kernel ---------------------------------------------------------------
     const uint64_t P1 = R0 + np;
     const uint32_t t_lo = (uint32_t)(R0 >> 5), t_hi = (uint32_t)((P1 + 31u) >> 5);
@@ -429,8 +472,18 @@ __global__ void __launch_bounds__(PB_THREADS, 4) k_place_block(const __grid_cons
                 li = MMK_INS_LEN(q.y);
             } else {
                 const uint32_t slot = s_so[j] + (i - s_ro[j]);
-                so = s_bits[slot].x;
                 li = s_len[slot];
+#if MMK_PB_SCAN
+                const uint32_t ks = s_kstop[j], k = i - s_ro[j];
+                if (k < ks) so = s_bits[slot].x;
+                else {  // back to back after the chain's last insert
+                    const uint32_t bs = s_so[j] + ks;
+                    const uint32_t cur = ks ? s_bits[bs - 1u].x + s_len[bs - 1u] : 0u;
+                    so = cur + (s_bits[slot].y - s_bits[bs].y);
+                }
+#else
+                so = s_bits[slot].x;
+#endif
             }
             const SchemaDev &S = a.sch[MPK_SCHEMA(pk)];
             const uint32_t n_hap = S.len;
