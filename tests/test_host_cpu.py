@@ -25,6 +25,8 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
     exported = set(re.findall(r" T (mmk_[a-z0-9_]+)", out))
     assert declared <= exported, declared - exported
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()      # every export is accounted for beside the reference code it replaces
+    assert not [d for d in sorted(declared) if d not in doc], [d for d in sorted(declared) if d not in doc]
     L = _lib.load()
     assert L.mmk_abi_version() == 1
     # no torch / python types in the ABI: the library does not even link libpython or libtorch
