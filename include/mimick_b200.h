@@ -168,6 +168,9 @@ typedef struct mmk_schema_info {
     char name[64];
 } mmk_schema_info;
 int32_t mmk_schema_get(const mmk_ctx *ctx, int32_t i, mmk_schema_info *out);
+/* the schema's chrom (Schema.chrom, src/Structs.jl:78-84) in full, NUL-terminated: mmk_schema_info.name holds only its first
+ * 63 characters, contig names may have 160.  MMK_ERR_INVALID_ARG when `cap` is too small. */
+int32_t mmk_schema_name(const mmk_ctx *ctx, int32_t i, char *out, int64_t cap);
 /* copies schema i back as uppercase ASCII (parity check of haplotype construction) */
 int32_t mmk_schema_bases(mmk_ctx *ctx, int32_t i, char *out, int64_t cap);
 

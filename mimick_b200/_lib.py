@@ -72,7 +72,7 @@ EXPORTS = [
     "mmk_last_error", "mmk_create", "mmk_destroy", "mmk_seed", "mmk_cuda_stream", "mmk_add_contig", "mmk_load_fasta",
     "mmk_n_contigs", "mmk_set_sample_variants", "mmk_vcf_open", "mmk_vcf_close", "mmk_vcf_n_samples",
     "mmk_vcf_sample_name", "mmk_vcf_ploidy", "mmk_vcf_n_contigs", "mmk_vcf_contig_name", "mmk_vcf_n_records",
-    "mmk_apply_vcf_sample", "mmk_n_schemas", "mmk_schema_get", "mmk_schema_bases", "mmk_plan", "mmk_set_shard",
+    "mmk_apply_vcf_sample", "mmk_n_schemas", "mmk_schema_get", "mmk_schema_name", "mmk_schema_bases", "mmk_plan", "mmk_set_shard",
     "mmk_place", "mmk_emit_chunk", "mmk_rewind", "mmk_copy_chunk", "mmk_emit_to_host", "mmk_dump_molecules",
     "mmk_dump_inserts", "mmk_dump_variates", "mmk_dump_mask_variates", "mmk_kat_philox", "mmk_kat_math",
     "mmk_emit_all", "mmk_emit_stream", "mmk_chunk_layout", "mmk_launch_count", "mmk_clear_contigs",
@@ -130,6 +130,7 @@ def load():
     sig("mmk_apply_vcf_sample", i32, vp, vp, i32)
     sig("mmk_n_schemas", i32, vp)
     sig("mmk_schema_get", i32, vp, i32, P(SchemaInfo))
+    sig("mmk_schema_name", i32, vp, i32, vp, i64)
     sig("mmk_schema_bases", i32, vp, i32, vp, i64)
     sig("mmk_plan", i32, vp, P(PlanInfo))
     sig("mmk_set_shard", i32, vp, i32, i32)

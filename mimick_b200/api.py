@@ -199,7 +199,9 @@ class Simulator:
         for i in range(self._L.mmk_n_schemas(self._h)):
             s = SchemaInfo()
             self._ck(self._L.mmk_schema_get(self._h, i, C.byref(s)))
-            out.append(dict(name=s.name.decode(), haplotype=s.haplotype, contig=s.contig, length=s.length,
+            name = C.create_string_buffer(256)     # the info struct keeps 63 characters of the name; this is all of it
+            self._ck(self._L.mmk_schema_name(self._h, i, name, len(name)))
+            out.append(dict(name=name.value.decode(), haplotype=s.haplotype, contig=s.contig, length=s.length,
                             reads_required=s.reads_required, reads_current=s.reads_current))
         return out
 

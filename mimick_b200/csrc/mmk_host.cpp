@@ -1120,6 +1120,20 @@ extern "C" int32_t mmk_schema_get(const mmk_ctx *c, int32_t i, mmk_schema_info *
     snprintf(out->name, sizeof out->name, "%s", s.name.c_str());
     return MMK_OK;
 }
+extern "C" int32_t mmk_schema_name(const mmk_ctx *c, int32_t i, char *out, int64_t cap) {
+    if (!c || !out || cap < 1) return MMK_ERR_INVALID_ARG;
+    const std::string *name = nullptr;
+    if (!c->multi_mode && !c->schemas_ready) {
+        if (i < 0 || i >= (int32_t)c->contigs.size()) return MMK_ERR_INVALID_ARG;
+        name = &c->contigs[i].name;
+    } else {
+        if (i < 0 || i >= (int32_t)c->schemas.size()) return MMK_ERR_INVALID_ARG;
+        name = &c->schemas[i].name;
+    }
+    if ((int64_t)name->size() + 1 > cap) return MMK_ERR_INVALID_ARG;
+    memcpy(out, name->c_str(), name->size() + 1);
+    return MMK_OK;
+}
 extern "C" int32_t mmk_schema_bases(mmk_ctx *ctx, int32_t i, char *out, int64_t cap) {
     if (!ctx || !out) return fail(ctx, MMK_ERR_INVALID_ARG, "mmk_schema_bases: bad argument");
     CU(cudaSetDevice(ctx->par.device));

@@ -679,6 +679,9 @@ def test_long_contig_names(tmp_path):
     write_fasta(p, [(long_name + " some description", random_bases(rng, 60_000)), ("ctg2", random_bases(rng, 50_000))])
     gpu, _ = check_single([p], "tellseq", seed=4, coverage=6, **CLI)
     assert (b"@" + long_name.encode() + b":1|") in gpu["r1"]
+    with M.Simulator("tellseq", seed=4, coverage=6, **CLI) as sim:    # the schema view gives the name in full
+        sim.load_fasta(p)
+        assert [s["name"] for s in sim.schemas()] == [long_name, "ctg2"]
     with M.Simulator("tellseq", seed=1) as sim:
         with pytest.raises(M.MimickError):
             sim.add_contig("y" * 161, b"ACGT" * 1000, 1)
