@@ -639,3 +639,21 @@ def test_mutate_rederived_in_python(seed, sorted_sites):
                 last_end = v[0] + len(v[2]) - 1
         variants = keep
     assert O.Oracle.mutate(master, variants) == _py_mutate(master, variants)
+
+
+def test_oracle_output_is_frozen():
+    """The oracle's bytes for ten seeded cases (all formats, circular literal / strict, fixed molecules per barcode, N masking,
+    Robert's truncated-Normal branch, the error model, the reference's FASTA + VCF fixtures) equal the committed digests:
+    a change of oracle/ or of the shared include/mmk_rng.h that moves the output fails HERE, on the CPU — the GPU parity tests
+    cannot see it, both sides share that header.  tests/golden/make_oracle_digests.py regenerates the file after a deliberate change."""
+    import importlib.util
+    import json
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_oracle_digests", os.path.join(here, "make_oracle_digests.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = json.load(open(os.path.join(here, "oracle_digests.json")))
+    got = mod.compute()
+    assert sorted(got) == sorted(want)
+    for name in sorted(want):
+        assert got[name] == want[name], f"{name}: the oracle's output moved ({[k for k in want[name] if got[name][k] != want[name][k]]})"
