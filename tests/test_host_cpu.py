@@ -384,3 +384,22 @@ def test_julia_binding_matches_the_header():
     for kw in ("coverage", "n_molecules", "mol_coverage", "mol_length", "insert_length", "insert_stdev", "read_length",
                "singletons", "circular", "attempts", "seed", "mask", "prefix", "outdir", "quiet"):
         assert re.search(r"\b%s\b\s*(::\w+)?\s*=" % kw, jl), kw
+
+
+def test_bench_helpers_without_a_gpu():
+    """bench.py's bookkeeping that does not need a device: the clock sampler reports "no samples" instead of failing when neither
+    NVML nor nvidia-smi is there, the roofline's DRAM traffic comes from the committed ncu capture of the final build, and the
+    CUDA arm refuses to run without a device (no CPU fallback)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    s = bench.ClockSampler(0, "00000000:1b:00.0")
+    s.start()
+    out = s.stop()
+    assert out["samples"] == 0 and out["sm_mhz"] is None and out["reasons"] == []
+    traffic, src = bench.ncu_traffic()
+    assert src.startswith("profiles/r02_final_k_emit_w_ncu_full.csv") and 4.5e9 < traffic < 6.0e9   # one 2 GiB-chunk launch: 4.34 GB written + reads
+    peak, how = bench.peak_hbm()
+    assert 5000.0 < peak < 8000.0 and ("measured" in how or "fallback" in how)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+                       env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
